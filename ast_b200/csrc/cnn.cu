@@ -1,0 +1,372 @@
+// CNN front-end pieces (seq2seq.py:158-180): im2col for CNN_0 (K = kh*kw = 117, 1 % of FLOPs),
+// train-mode BatchNorm statistics / apply(+ReLU, + relayout) / backward, the col2im gather for
+// CNN_1's data gradient and the weight (un)permutes.  The convolutions themselves are GEMMs
+// (gemm_simt.cu / gemm_tc.cu); CNN_1 reads its input as an overlapping-rows matrix so no im2col
+// buffer is ever materialised for the 20 %-of-FLOPs layer.
+//
+// HBM layouts (channels-last, time-major rows):
+//   raw0 / a0 : [b][f][t1][C0]          a0p : [b][f][S0][C0]  (S0 = 2*ceil((T1+8)/2), 4 zero rows
+//                                              in front, zeros behind: CNN_1's padding in memory)
+//   raw1      : [b][f][Rs][C1]  with Rs = S0/2 "virtual rows" per (b,f) segment, rows >= T' junk
+//   rnn_in    : [t'][b][c*F'+f] (the reference's feature order, seq2seq.py:177-179)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ast {
+
+// ---- im2col for CNN_0 -------------------------------------------------------------------
+// cols[(b,f,t1)][kt*kw+kd] = X[b][sh*t1 - ph + kt][sw*f + kd]  (zero outside [0,T)), ld = ldc.
+__global__ void im2col0_kernel(const float* __restrict__ X, float* __restrict__ cols, int B, int T,
+                               int D, int Fp, int T1, int kh, int kw, int sh, int sw, int ph, int ldc) {
+    const int K = kh * kw;
+    const size_t total = (size_t)B * Fp * T1 * ldc;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ldc);
+        const size_t row = i / ldc;
+        const int t1 = (int)(row % T1);
+        const int f = (int)((row / T1) % Fp);
+        const int b = (int)(row / ((size_t)T1 * Fp));
+        float v = 0.f;
+        if (k < K) {
+            const int kt = k / kw, kd = k % kw;
+            const int t = sh * t1 - ph + kt, d = sw * f + kd;
+            if (t >= 0 && t < T && d < D) v = X[((size_t)b * T + t) * D + d];
+        }
+        cols[i] = v;
+    }
+}
+
+int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, int Fp, int T1, int kh,
+            int kw, int sh, int sw, int ph, int ldc) {
+    const size_t total = (size_t)B * Fp * T1 * ldc;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    im2col0_kernel<<<grid, 256, 0, st>>>(X, cols, B, T, D, Fp, T1, kh, kw, sh, sw, ph, ldc);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- BN statistics: per-channel sum / sum-of-squares over valid rows (double accumulation) ---
+// x: rows x C (ld = C).  Row r is valid iff (r % seg_rows) < seg_valid.  stats[0..C) += sum,
+// stats[C..2C) += sumsq.  blockDim = (32, 8): x = channel lane, y = row lane.
+__global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int rows, int C,
+                                int seg_rows, int seg_valid, int rows_per_block) {
+    __shared__ double ssum[8][33], ssq[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            if ((r % seg_rows) < seg_valid) {
+                const float v = x[(size_t)r * C + c];
+                s += v; q += (double)v * v;
+            }
+        }
+    }
+    ssum[threadIdx.y][threadIdx.x] = s;
+    ssq[threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { s += ssum[j][threadIdx.x]; q += ssq[j][threadIdx.x]; }
+        atomicAdd(&stats[c], s);
+        atomicAdd(&stats[C + c], q);
+    }
+}
+
+// mean / invstd from the sums, plus Chainer's running-stat update (Appendix A.2):
+// avg_mean = .9*avg_mean + .1*mean ; avg_var = .9*avg_var + .1*var*m/(m-1).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ avg_mean,
+                                   float* __restrict__ avg_var, int C, double m, float eps, float decay,
+                                   int update_running) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mu = stats[c] / m;
+    double var = stats[C + c] / m - mu * mu;
+    if (var < 0) var = 0;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (update_running) {
+        const double adj = m / fmax(m - 1.0, 1.0);
+        avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mu;
+        avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(var * adj);
+    }
+}
+
+// eval-mode: mean = avg_mean, invstd = 1/sqrt(avg_var + eps)
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ avg_mean, const float* __restrict__ avg_var,
+                                       float* __restrict__ mean, float* __restrict__ invstd, int C, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = avg_mean[c];
+    invstd[c] = 1.f / sqrtf(avg_var[c] + eps);
+}
+
+int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid) {
+    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+    const int rpb = std::max(64, cdiv(rows, 148 * 4 / std::max(1, cdiv(C, 32))));
+    dim3 grid(cdiv(C, 32), cdiv(rows, rpb)), block(32, 8);
+    bn_stats_kernel<<<grid, block, 0, st>>>(x, stats, rows, C, seg_rows, seg_valid, rpb);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+int bn_finalize(cudaStream_t st, const double* stats, float* mean, float* invstd, float* avg_mean,
+                float* avg_var, int C, double m, float eps, float decay, bool update_running) {
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats, mean, invstd, avg_mean, avg_var, C, m, eps, decay,
+                                                     update_running ? 1 : 0);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+int bn_eval_prepare(cudaStream_t st, const float* avg_mean, const float* avg_var, float* mean, float* invstd,
+                    int C, float eps) {
+    bn_eval_prepare_kernel<<<cdiv(C, 128), 128, 0, st>>>(avg_mean, avg_var, mean, invstd, C, eps);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- BN apply + ReLU for layer 0: raw0 [seg][T1][C] -> a0p [seg][S0][C] with `pad` zero rows in front
+__global__ void bn_relu_pad_kernel(const float* __restrict__ raw, float* __restrict__ out,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   int nseg, int T1, int S0, int pad, int C) {
+    const int C4 = C >> 2;
+    const size_t total = (size_t)nseg * S0 * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const size_t row = i / C4;
+        const int s = (int)(row % S0);
+        const size_t seg = row / S0;
+        const int t1 = s - pad;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t1 >= 0 && t1 < T1) {
+            const float4 x = *reinterpret_cast<const float4*>(raw + ((seg * T1 + t1) * (size_t)C) + c4 * 4);
+            const float4 mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
+            const float4 is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+            const float4 g = *reinterpret_cast<const float4*>(gamma + c4 * 4);
+            const float4 b = *reinterpret_cast<const float4*>(beta + c4 * 4);
+            o.x = fmaxf(g.x * ((x.x - mu.x) * is.x) + b.x, 0.f);
+            o.y = fmaxf(g.y * ((x.y - mu.y) * is.y) + b.y, 0.f);
+            o.z = fmaxf(g.z * ((x.z - mu.z) * is.z) + b.z, 0.f);
+            o.w = fmaxf(g.w * ((x.w - mu.w) * is.w) + b.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(out + row * (size_t)C + c4 * 4) = o;
+    }
+}
+
+int bn_relu_pad(cudaStream_t st, const float* raw, float* out, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, int nseg, int T1, int S0, int pad, int C) {
+    AST_CHECK(C % 4 == 0, "bn_relu_pad: C %% 4 != 0");
+    const size_t total = (size_t)nseg * S0 * (C / 4);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    bn_relu_pad_kernel<<<grid, 256, 0, st>>>(raw, out, mean, invstd, gamma, beta, nseg, T1, S0, pad, C);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- BN apply + ReLU + relayout for the last CNN layer -------------------------------------
+// raw1 [b][f][Rs][C] (rows t' < Tp valid) -> rnn_in[t'][b][c*Fp+f] and (optionally) the step-ordered
+// copy for the reverse stack rnn_rev[i] = rnn_in[(-i) mod Tp]  (seq2seq.py:219 `X[-i]`).
+__global__ void bn_relu_to_rnn_kernel(const float* __restrict__ raw, float* __restrict__ rnn_in,
+                                      float* __restrict__ rnn_rev, const float* __restrict__ mean,
+                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int B, int Fp, int Rs, int Tp, int C) {
+    const size_t total = (size_t)B * Fp * Tp * C;
+    const int R = C * Fp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int t = (int)(r % Tp); r /= Tp;
+        const int f = (int)(r % Fp);
+        const int b = (int)(r / Fp);
+        const float x = raw[(((size_t)b * Fp + f) * Rs + t) * C + c];
+        const float v = fmaxf(gamma[c] * ((x - mean[c]) * invstd[c]) + beta[c], 0.f);
+        rnn_in[((size_t)t * B + b) * R + c * Fp + f] = v;
+        if (rnn_rev) {
+            const int i_rev = (Tp - t) % Tp;          // step i with (-i) mod Tp == t
+            rnn_rev[((size_t)i_rev * B + b) * R + c * Fp + f] = v;
+        }
+    }
+}
+
+int bn_relu_to_rnn(cudaStream_t st, const float* raw, float* rnn_in, float* rnn_rev, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, int B, int Fp, int Rs, int Tp,
+                   int C) {
+    const size_t total = (size_t)B * Fp * Tp * C;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    bn_relu_to_rnn_kernel<<<grid, 256, 0, st>>>(raw, rnn_in, rnn_rev, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- BN + ReLU backward --------------------------------------------------------------------
+// Generic over an index functor giving, for (valid row r, channel c), where dy lives.
+// Pass 1: dbeta[c] = sum dy*mask, dgamma[c] = sum dy*mask*xhat   (double atomics into stats[2C])
+// Pass 2: dx = gamma*invstd*(dy*mask - dbeta/m - xhat*dgamma/m)  (junk rows get 0)
+struct DyFromRnn {          // last CNN layer: dy = d_rnn_in[t'][b][c*Fp+f] (+ d_rnn_rev[(Tp-t')%Tp][b][..])
+    const float* d_in; const float* d_rev; int B, Fp, Rs, Tp, C;
+    __device__ __forceinline__ float operator()(int r, int c) const {
+        const int t = r % Rs; const int sf = r / Rs; const int f = sf % Fp; const int b = sf / Fp;
+        const int R = C * Fp;
+        float v = d_in[((size_t)t * B + b) * R + c * Fp + f];
+        if (d_rev) v += d_rev[((size_t)((Tp - t) % Tp) * B + b) * R + c * Fp + f];
+        return v;
+    }
+};
+struct DyFromPadded {       // layer 0: dy = da0p[seg][pad + t1][c]
+    const float* d; int T1, S0, pad, C;
+    __device__ __forceinline__ float operator()(int r, int c) const {
+        const int t1 = r % T1; const int seg = r / T1;
+        return d[((size_t)seg * S0 + pad + t1) * C + c];
+    }
+};
+
+template <class DY>
+__global__ void bn_bwd_reduce_kernel(DY dyf, const float* __restrict__ raw, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, double* __restrict__ stats, int rows, int C,
+                                     int seg_rows, int seg_valid, int rows_per_block) {
+    __shared__ double sb[8][33], sg[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    double db = 0.0, dg = 0.0;
+    if (c < C) {
+        const float mu = mean[c], is = invstd[c], g = gamma[c], bt = beta[c];
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            if ((r % seg_rows) < seg_valid) {
+                const float xh = (raw[(size_t)r * C + c] - mu) * is;
+                if (g * xh + bt > 0.f) {
+                    const float dy = dyf(r, c);
+                    db += dy; dg += (double)dy * xh;
+                }
+            }
+        }
+    }
+    sb[threadIdx.y][threadIdx.x] = db;
+    sg[threadIdx.y][threadIdx.x] = dg;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { db += sb[j][threadIdx.x]; dg += sg[j][threadIdx.x]; }
+        atomicAdd(&stats[c], db);
+        atomicAdd(&stats[C + c], dg);
+    }
+}
+
+template <class DY>
+__global__ void bn_bwd_apply_kernel(DY dyf, const float* __restrict__ raw, float* __restrict__ dx,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const double* __restrict__ stats, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int rows, int C, int seg_rows, int seg_valid,
+                                    double m) {
+    const size_t total = (size_t)rows * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int r = (int)(i / C);
+        float o = 0.f;
+        const float db = (float)stats[c], dg = (float)stats[C + c];
+        if ((r % seg_rows) < seg_valid) {
+            const float is = invstd[c], g = gamma[c];
+            const float xh = (raw[i] - mean[c]) * is;
+            const float dy = (g * xh + beta[c] > 0.f) ? dyf(r, c) : 0.f;
+            o = g * is * (dy - db / (float)m - xh * (dg / (float)m));
+        }
+        dx[i] = o;
+        if (r == 0) { dgamma[c] = dg; dbeta[c] = db; }
+    }
+}
+
+template <class DY>
+static int bn_bwd_impl(cudaStream_t st, DY dyf, const float* raw, float* dx, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, double* stats,
+                       float* dgamma, float* dbeta, int rows, int C, int seg_rows, int seg_valid, double m) {
+    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+    const int rpb = std::max(64, cdiv(rows, 148 * 4 / std::max(1, cdiv(C, 32))));
+    dim3 grid(cdiv(C, 32), cdiv(rows, rpb)), block(32, 8);
+    bn_bwd_reduce_kernel<DY><<<grid, block, 0, st>>>(dyf, raw, mean, invstd, gamma, beta, stats, rows, C,
+                                                      seg_rows, seg_valid, rpb);
+    AST_LAUNCH_OK();
+    const size_t total = (size_t)rows * C;
+    const int g2 = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    bn_bwd_apply_kernel<DY><<<g2, 256, 0, st>>>(dyf, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta,
+                                                 rows, C, seg_rows, seg_valid, m);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, const float* raw, float* dx,
+                    const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    double* stats, float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C) {
+    DyFromRnn f{d_in, d_rev, B, Fp, Rs, Tp, C};
+    return bn_bwd_impl(st, f, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B * Fp * Rs, C, Rs, Tp,
+                       (double)B * Fp * Tp);
+}
+
+int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, double* stats,
+                       float* dgamma, float* dbeta, int nseg, int T1, int S0, int pad, int C) {
+    DyFromPadded f{da0p, T1, S0, pad, C};
+    return bn_bwd_impl(st, f, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, nseg * T1, C, T1, T1,
+                       (double)nseg * T1);
+}
+
+// ---- col2im gather for CNN_1's data gradient ------------------------------------------------
+// dA: virtual rows [seg][Rs][kh*C0] (row r covers padded input rows sh*r .. sh*r+kh-1).
+// da0p[seg][s][ci] = sum_{kt : (s-kt) % sh == 0, r=(s-kt)/sh in [0,Tp)} dA[seg][r][kt*C0+ci]
+__global__ void col2im1_kernel(const float* __restrict__ dA, float* __restrict__ da0p, int nseg, int S0,
+                               int Rs, int Tp, int C0, int kh, int sh) {
+    const int C4 = C0 >> 2;
+    const size_t total = (size_t)nseg * S0 * C4;
+    const int ldA = kh * C0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const size_t row = i / C4;
+        const int s = (int)(row % S0);
+        const size_t seg = row / S0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kt = s % sh; kt < kh; kt += sh) {
+            const int r = (s - kt) / sh;
+            if (s - kt >= 0 && r < Tp) {
+                const float4 v = *reinterpret_cast<const float4*>(dA + (seg * Rs + r) * (size_t)ldA + kt * C0 + c4 * 4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        *reinterpret_cast<float4*>(da0p + row * (size_t)C0 + c4 * 4) = acc;
+    }
+}
+
+int col2im1(cudaStream_t st, const float* dA, float* da0p, int nseg, int S0, int Rs, int Tp, int C0, int kh, int sh) {
+    const size_t total = (size_t)nseg * S0 * (C0 / 4);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    col2im1_kernel<<<grid, 256, 0, st>>>(dA, da0p, nseg, S0, Rs, Tp, C0, kh, sh);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- weight permutes: W1 (co, ci, kt) <-> W1p (co, kt, ci) ------------------------------------
+__global__ void permute_w1_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int Kt,
+                                  int to_p) {
+    const int total = Co * Ci * Kt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // i indexes the (co, kt, ci) layout
+        const int ci = i % Ci; const int kt = (i / Ci) % Kt; const int co = i / (Ci * Kt);
+        const int j = (co * Ci + ci) * Kt + kt;       // (co, ci, kt)
+        if (to_p) dst[i] = src[j]; else dst[j] = src[i];
+    }
+}
+int permute_w1(cudaStream_t st, const float* src, float* dst, int Co, int Ci, int Kt, bool to_p) {
+    permute_w1_kernel<<<std::min(cdiv(Co * Ci * Kt, 256), 148 * 8), 256, 0, st>>>(src, dst, Co, Ci, Kt, to_p ? 1 : 0);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace ast

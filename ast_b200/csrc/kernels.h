@@ -1,0 +1,124 @@
+// Internal launcher interface between model.cu (orchestration) and the kernel translation units.
+// Every launcher returns 0 on success, <0 on error (message via ast::get_last_error()).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <algorithm>
+
+#define AST_MAX_CHAINS 4
+
+namespace ast {
+
+// ---- dense GEMM (row-major, see gemm_simt.cu) -----------------------------------------------
+int sgemm_simt(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alpha, const float* A, int lda,
+               const float* B, int ldb, float beta, float* C, int ldc, const float* bias);
+// TF32 tcgen05/TMEM/TMA GEMM for C = A(MxK, k-contig) * B(NxK, k-contig)^T (+bias); returns 1 when the
+// shape is not supported by the tensor-core kernel (caller falls back to sgemm_simt).
+int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+               int ldc, const float* bias, float beta);
+
+// ---- CNN front-end ---------------------------------------------------------------------------
+int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, int Fp, int T1, int kh, int kw, int sh,
+            int sw, int ph, int ldc);
+int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid);
+int bn_finalize(cudaStream_t st, const double* stats, float* mean, float* invstd, float* avg_mean, float* avg_var,
+                int C, double m, float eps, float decay, bool update_running);
+int bn_eval_prepare(cudaStream_t st, const float* avg_mean, const float* avg_var, float* mean, float* invstd, int C,
+                    float eps);
+int bn_relu_pad(cudaStream_t st, const float* raw, float* out, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, int nseg, int T1, int S0, int pad, int C);
+int bn_relu_to_rnn(cudaStream_t st, const float* raw, float* rnn_in, float* rnn_rev, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, int B, int Fp, int Rs, int Tp, int C);
+int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, const float* raw, float* dx,
+                    const float* mean, const float* invstd, const float* gamma, const float* beta, double* stats,
+                    float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C);
+int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, double* stats, float* dgamma,
+                       float* dbeta, int nseg, int T1, int S0, int pad, int C);
+int col2im1(cudaStream_t st, const float* dA, float* da0p, int nseg, int S0, int Rs, int Tp, int C0, int kh, int sh);
+int permute_w1(cudaStream_t st, const float* src, float* dst, int Co, int Ci, int Kt, bool to_p);
+
+// ---- persistent LSTM recurrence ----------------------------------------------------------------
+struct LstmChain {
+    float* G;            // (T x B x 4h): in  x-projection + bias ; out  activated gates (fwd) / dG (bwd)
+    const float* Wl;     // (4h x h) lateral weight
+    float* Hs;           // ((T+1) x B x h) link state h, slot 0 = initial state
+    float* Cs;           // ((T+1) x B x h) cell state,  slot 0 = initial state
+    float* out;          // fwd: post-dropout output, element (i,b,j) at out[i*out_si + b*out_sb + j]
+    const float* dout;   // bwd: gradient w.r.t. that output, same addressing
+    long long out_si, out_sb;
+    const float* dh_fin; // bwd: gradient w.r.t. the final link state, element (b,j) at dh_fin[b*ld_dh_fin + j], or null
+    const float* dc_fin;
+    int ld_dh_fin, ld_dc_fin;
+    float* dh0;          // bwd: gradient w.r.t. the initial state (B x h) or null
+    float* dc0;
+    unsigned drop_stream;
+};
+struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
+int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
+                 unsigned long long seed, bool exact);
+int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
+                 unsigned long long seed, bool exact);
+
+// ---- decoder step kernels ------------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_TANH = 1, EPI_LSTM = 2, EPI_TANHBWD = 3 };
+struct SkinnyArgs {
+    const float* X[2]; int ldx[2]; int K[2];
+    const float* W[2]; int ldw[2];
+    const float* bias;
+    int B, N, epi;
+    float* Y; int ldy;
+    const float* add; int ld_add;      // optional additive term (before the activation)
+    const float* aux; int ld_aux;      // EPI_TANHBWD: tanh output
+    // EPI_LSTM
+    const float* c_prev; float* c_out; float* h_out; float* hd_out; int ld_hd;
+    float drop; unsigned long long seed; unsigned drop_stream; size_t drop_base;
+};
+int skinny(cudaStream_t st, const SkinnyArgs& p, bool exact);
+int embed_concat(cudaStream_t st, const float* emb, const int* y, int ldy_tok, const unsigned char* use_true,
+                 const int* prev_argmax, const int* forced_words, const float* ht_prev, int ld_ht, float* x0,
+                 int* words_used, int B, int E, int A, int V, int step, float drop, unsigned long long seed,
+                 unsigned drop_stream);
+int embed_scatter(cudaStream_t st, float* demb, const float* dx0, int ld_dx, const int* words, int B, int E, int step,
+                  float drop, unsigned long long seed, unsigned drop_stream);
+int attn_dot(cudaStream_t st, const float* enc, long long enc_bs, const float* v, int ldv, float* s, int B, int Tp, int H);
+int attn_ctx(cudaStream_t st, const float* enc, long long enc_bs, const float* s, float* alpha, float* cv, int ld_cv,
+             int B, int Tp, int H);
+int attn_bwd(cudaStream_t st, const float* enc, float* d_enc, long long enc_bs, const float* alpha, const float* dalpha,
+             const float* dcv, int ld_dcv, const float* qv, int ld_q, float* dq, int ld_dq, int B, int Tp, int H);
+int softmax_ce(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, int step_next, float* row_loss,
+               int* argmax_out, int B, int V, bool write_grad);
+int loss_reduce(cudaStream_t st, const float* row_loss, int n, float* loss);
+int lstm_cell_bwd(cudaStream_t st, float* act, const float* c, const float* c_prev, const float* d_out, int ld_dout,
+                  const float* dh_rec, int ld_dhrec, float* dc, int B, int H, int step_row0, float drop,
+                  unsigned long long seed, unsigned drop_stream);
+
+// ---- optimizer / data / misc -----------------------------------------------------------------------
+struct FrozenRanges { int n; size_t begin[8]; size_t end[8]; };
+int opt_sqnorm(cudaStream_t st, const float* g, const float* p, size_t n, float gscale, float wd, double* norm_sq);
+int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, float* vhat, size_t n, float gscale,
+                float wd, float clip, const double* norm_sq, float alpha_t, float beta1, float beta2, float eps,
+                const FrozenRanges& fr);
+int pack_cmvn(cudaStream_t st, const float* raw, const long long* row_off, const int* lens, const float* scale,
+              const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
+              unsigned long long seed, float* X, int B, int T, int D);
+int mul_noise(cudaStream_t st, const float* X, float* Y, const float* noise, float sigma, unsigned long long seed, size_t n);
+int transpose(cudaStream_t st, const float* src, int ld_src, float* dst, int ld_dst, int R, int C);
+int colsum(cudaStream_t st, const float* x, int ld, float* out, int rows, int C, bool accumulate);
+int copy2d(cudaStream_t st, const float* src, long long ld_src, float* dst, long long ld_dst, int R, int C);
+int add_inplace(cudaStream_t st, float* dst, const float* src, size_t n);
+int greedy_track(cudaStream_t st, const int* argmax, int* preds, int* seen, int* done_step, int B, int step, int eos);
+
+// ---- beam search ---------------------------------------------------------------------------------------
+struct BeamState {
+    float* score; int* finished; int* n_active; int* done; int* steps_done;
+    float* new_score; int* new_parent; int* new_tok; int* new_finished;
+};
+struct BeamGather { int n; const float* cur[8]; const float* post[8]; float* nxt[8]; int width[8]; };
+int beam_topk(cudaStream_t st, const float* z, int ldz, int V, int K, int N, const BeamState& bs, float* cand_lp, int* cand_tok);
+int beam_prune(cudaStream_t st, const BeamState& bs, const float* cand_lp, const int* cand_tok, int N, int K, int step,
+               int eos, int* hist_parent, int* hist_tok);
+int beam_gather(cudaStream_t st, const BeamState& bs, const BeamGather& gd, int N, int step, int Tp,
+                const float* alpha_step, float* alpha_hist, const int* last_tok_prev, int* last_tok_next);
+
+}  // namespace ast

@@ -1,0 +1,240 @@
+// Memory-bound helpers: fused multi-tensor optimizer (nn.py:81-119 + Appendix A.10), utterance
+// pack + CMVN (+frame-drop, +noise) (dataloader.py:83-108,156; seq2seq.py:297-305; Kaldi apply-cmvn),
+// transposes, column sums, small copies.  All coalesced / float4 where the layout allows; grids are
+// sized in multiples of the 148 SMs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ast {
+
+// ---- optimizer -----------------------------------------------------------------------------
+// pass 1: sum over the flat buffer of (gscale*g + wd*p)^2  -> norm_sq[0] (double)
+__global__ void opt_sqnorm_kernel(const float* __restrict__ g, const float* __restrict__ p, size_t n, float gscale,
+                                  float wd, double* __restrict__ norm_sq) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    const size_t n4 = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        const float4 pv = reinterpret_cast<const float4*>(p)[i];
+        const float a = gscale * gv.x + wd * pv.x, b = gscale * gv.y + wd * pv.y;
+        const float c = gscale * gv.z + wd * pv.z, d = gscale * gv.w + wd * pv.w;
+        s += (double)a * a + (double)b * b + (double)c * c + (double)d * d;
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        atomicAdd(norm_sq, t);
+    }
+}
+
+// pass 2: WeightDecay -> GradientClipping(global norm) -> AMSGrad (eps outside the sqrt)
+__global__ void opt_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                   float* __restrict__ v, float* __restrict__ vhat, size_t n, float gscale, float wd,
+                                   float clip, const double* __restrict__ norm_sq, float alpha_t, float beta1,
+                                   float beta2, float eps, FrozenRanges fr) {
+    const double nrm = sqrt(norm_sq[0]);
+    float rate = 1.f;
+    if (clip > 0.f && nrm > 0.0) { const double r = (double)clip / nrm; if (r < 1.0) rate = (float)r; }
+    const size_t n4 = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        bool frozen = false;
+        for (int k = 0; k < fr.n; ++k) frozen |= (i * 4 >= fr.begin[k] && i * 4 < fr.end[k]);
+        if (frozen) continue;
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i], hv = reinterpret_cast<float4*>(vhat)[i];
+#define AST_ADAM1(c)                                                      \
+        {                                                                 \
+            const float gg = (gscale * gv.c + wd * pv.c) * rate;          \
+            mv.c += (1.f - beta1) * (gg - mv.c);                          \
+            vv.c += (1.f - beta2) * (gg * gg - vv.c);                     \
+            hv.c = fmaxf(hv.c, vv.c);                                     \
+            pv.c -= alpha_t * mv.c / (sqrtf(hv.c) + eps);                 \
+        }
+        AST_ADAM1(x) AST_ADAM1(y) AST_ADAM1(z) AST_ADAM1(w)
+#undef AST_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        reinterpret_cast<float4*>(vhat)[i] = hv;
+    }
+}
+
+int opt_sqnorm(cudaStream_t st, const float* g, const float* p, size_t n, float gscale, float wd, double* norm_sq) {
+    AST_CHECK(n % 4 == 0, "opt_sqnorm: flat size must be a multiple of 4");
+    AST_CUDA_OK(cudaMemsetAsync(norm_sq, 0, sizeof(double), st));
+    opt_sqnorm_kernel<<<148 * 4, 256, 0, st>>>(g, p, n, gscale, wd, norm_sq);
+    AST_LAUNCH_OK();
+    return 0;
+}
+int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, float* vhat, size_t n, float gscale,
+                float wd, float clip, const double* norm_sq, float alpha_t, float beta1, float beta2, float eps,
+                const FrozenRanges& fr) {
+    AST_CHECK(n % 4 == 0, "opt_amsgrad: flat size must be a multiple of 4");
+    opt_amsgrad_kernel<<<148 * 4, 256, 0, st>>>(p, g, m, v, vhat, n, gscale, wd, clip, norm_sq, alpha_t, beta1, beta2, eps, fr);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- pack + CMVN (+ frame drop + multiplicative noise) ---------------------------------------
+// raw: concatenated utterances (sum_len x D); X[b][t][d] = t < len_b ? (raw*scale[b][d]+offset[b][d]) * keep * noise : 0
+// Box-Muller normal from the counter RNG when noise_sigma > 0 and no explicit noise tensor is given.
+__global__ void pack_cmvn_kernel(const float* __restrict__ raw, const long long* __restrict__ row_off,
+                                 const int* __restrict__ lens, const float* __restrict__ scale,
+                                 const float* __restrict__ offset, const unsigned char* __restrict__ keep,
+                                 const float* __restrict__ noise, float noise_sigma, unsigned long long seed,
+                                 float* __restrict__ X, int B, int T, int D) {
+    const size_t total = (size_t)B * T * D;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const size_t bt = i / D;
+        const int t = (int)(bt % T);
+        const int b = (int)(bt / T);
+        float v = 0.f;
+        if (t < lens[b] && (keep == nullptr || keep[bt])) {
+            v = raw[(size_t)(row_off[b] + t) * D + d];
+            if (scale) v = v * scale[b * D + d] + offset[b * D + d];
+            if (noise) v *= noise[i];
+            else if (noise_sigma > 0.f) {
+                const float u1 = fmaxf(rng_uniform(seed, 0x51u, (uint32_t)i), 1e-7f);
+                const float u2 = rng_uniform(seed, 0x52u, (uint32_t)i);
+                v *= 1.f + noise_sigma * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+            }
+        }
+        X[i] = v;
+    }
+}
+int pack_cmvn(cudaStream_t st, const float* raw, const long long* row_off, const int* lens, const float* scale,
+              const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
+              unsigned long long seed, float* X, int B, int T, int D) {
+    const size_t total = (size_t)B * T * D;
+    if (total == 0) return 0;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    pack_cmvn_kernel<<<grid, 256, 0, st>>>(raw, row_off, lens, scale, offset, keep, noise, noise_sigma, seed, X, B, T, D);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// X *= noise (explicit tensor) or X *= N(1, sigma)   (seq2seq.py:297-305 on an already packed batch)
+__global__ void mul_noise_kernel(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ noise,
+                                 float sigma, unsigned long long seed, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float f;
+        if (noise) f = noise[i];
+        else {
+            const float u1 = fmaxf(rng_uniform(seed, 0x51u, (uint32_t)i), 1e-7f);
+            const float u2 = rng_uniform(seed, 0x52u, (uint32_t)i);
+            f = 1.f + sigma * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+        }
+        Y[i] = X[i] * f;
+    }
+}
+int mul_noise(cudaStream_t st, const float* X, float* Y, const float* noise, float sigma, unsigned long long seed, size_t n) {
+    if (n == 0) return 0;
+    mul_noise_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(X, Y, noise, sigma, seed, n);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- transpose: dst (C x R, ld_dst) = src (R x C, ld_src)^T ------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst, int R, int C) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < R && c < C) ? src[(size_t)r * ld_src + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (c < C && r < R) dst[(size_t)c * ld_dst + r] = tile[threadIdx.x][j];
+    }
+}
+int transpose(cudaStream_t st, const float* src, int ld_src, float* dst, int ld_dst, int R, int C) {
+    dim3 grid(cdiv(C, 32), cdiv(R, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(src, ld_src, dst, ld_dst, R, C);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- column sums: out[c] (+)= sum_r x[r][c]  (bias gradients) ---------------------------------
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, float* __restrict__ out, int rows, int C, int rows_per_block) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    if (c < C) for (int r = r0 + threadIdx.y; r < r1; r += 8) s += x[(size_t)r * ld + c];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) s += sh[j][threadIdx.x];
+        atomicAdd(&out[c], s);
+    }
+}
+int colsum(cudaStream_t st, const float* x, int ld, float* out, int rows, int C, bool accumulate) {
+    if (!accumulate) AST_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    if (rows <= 0) return 0;
+    const int rpb = std::max(32, cdiv(rows, std::max(1, 148 * 2 / std::max(1, cdiv(C, 32)))));
+    dim3 grid(cdiv(C, 32), cdiv(rows, rpb)), block(32, 8);
+    colsum_kernel<<<grid, block, 0, st>>>(x, ld, out, rows, C, rpb);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// ---- strided 2-D copy: dst[r][c] = src[r][c] ---------------------------------------------------
+__global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst, long long ld_dst,
+                              int R, int C) {
+    const size_t total = (size_t)R * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const size_t r = i / C;
+        dst[r * ld_dst + c] = src[r * ld_src + c];
+    }
+}
+int copy2d(cudaStream_t st, const float* src, long long ld_src, float* dst, long long ld_dst, int R, int C) {
+    const size_t total = (size_t)R * C;
+    if (total == 0) return 0;
+    copy2d_kernel<<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(src, ld_src, dst, ld_dst, R, C);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// dst[i] += src[i]
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+int add_inplace(cudaStream_t st, float* dst, const float* src, size_t n) {
+    if (n == 0) return 0;
+    add_inplace_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dst, src, n);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// greedy decode bookkeeping (seq2seq.py:510-521): preds[step][b] = argmax[b]; seen_eos |= ...;
+// done_step = first step after which every row has emitted EOS.
+__global__ void greedy_track_kernel(const int* __restrict__ argmax, int* __restrict__ preds, int* __restrict__ seen,
+                                    int* __restrict__ done_step, int B, int step, int eos) {
+    __shared__ int all_seen;
+    if (threadIdx.x == 0) all_seen = 1;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int wd = argmax[b];
+        preds[(size_t)step * B + b] = wd;
+        int s = seen[b] | (wd == eos ? 1 : 0);
+        seen[b] = s;
+        if (!s) all_seen = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && all_seen && done_step[0] < 0) done_step[0] = step;
+}
+int greedy_track(cudaStream_t st, const int* argmax, int* preds, int* seen, int* done_step, int B, int step, int eos) {
+    greedy_track_kernel<<<1, 64, 0, st>>>(argmax, preds, seen, done_step, B, step, eos);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace ast

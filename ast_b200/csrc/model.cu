@@ -1,0 +1,977 @@
+// Orchestration of the hot path behind the C ABI (include/ast_b200.h): parameter table, workspace
+// plan, encoder / decoder / loss forward, full backward, optimizer step, greedy and beam decoding.
+// The host loops that Chainer ran in Python (seq2seq.py:211, :423; nn.py:307) run here in C++ and
+// only enqueue kernels; nothing in the training step synchronises with the host.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/ast_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ast {
+
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
+constexpr int MAXL = 4;
+
+struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
+
+struct Arena {
+    char* base = nullptr; size_t cap = 0, used = 0; bool dry = true;
+    template <class T> T* get(size_t n) {
+        used = align_up(used, 256);
+        T* p = dry ? nullptr : reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace ast
+
+using namespace ast;
+
+struct ast_model {
+    ast_config cfg{};
+    int device = 0;
+    // derived dims
+    int D, C0, C1, Fp, H, h, E, A, V, Vp, NL, R, ld0, K1;
+    std::vector<ParamInfo> pinfo;
+    long long nfloats = 0;
+    float *P = nullptr, *G = nullptr, *bn_state = nullptr;
+    // options
+    int exact = 1, tc_gemm = 0;
+    unsigned long long seed = 0x5eed1234ULL, cur_seed = 0;
+    unsigned long long step_counter = 0;
+    // workspace
+    Arena ws; int wsB = 0, wsT = 0, wsL = 0, wsN = 0, wsSteps = 0;
+    // ---- buffers (valid after bind_workspace) ----
+    float *cols0, *W0pad, *raw0, *a0p, *W1p, *raw1, *mean0, *invstd0, *mean1, *invstd1, *rnn_in, *rnn_rev, *Xn;
+    double *bnstats, *norm_sq;
+    float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
+    float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
+    float *draw1, *dA1, *da0p, *draw0, *dW1p, *dW0pad;
+    // decoder (training)
+    float *x0, *actd[MAXL], *Hdec[MAXL], *Cdec[MAXL], *hdd[MAXL], *q, *scores, *alpha, *cvh, *ht, *logits, *row_loss;
+    float *du, *dcvh, *dalpha, *dq, *dhtop, *dxh[MAXL], *dcd[MAXL];
+    int *words_used, *argmax_steps;
+    float *WoT, *WcT, *WaT, *WcatT[MAXL];
+    float *loss_dev;
+    // decode-time state (greedy / beam / decode_step): two banks
+    float *st_h[2][MAXL], *st_c[2][MAXL], *st_ht[2], *st_hpost[MAXL], *st_cpost[MAXL];
+    float *s_x0, *s_act, *s_hd[MAXL], *s_q, *s_scores, *s_alpha, *s_cvh, *s_htout, *s_logits;
+    int *s_words[2], *s_argmax, *g_preds, *g_seen, *g_done;
+    float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
+    int *h_pinned = nullptr;   // small pinned host mailbox
+    // last-call shapes
+    int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
+    bool weights_dirty = true, have_fwd = false;
+    int dec_Bd = 0;
+
+    float* p(const char* name) const {
+        for (auto& pi : pinfo) if (pi.name == name) return P + pi.off;
+        return nullptr;
+    }
+    float* g(const char* name) const {
+        for (auto& pi : pinfo) if (pi.name == name) return G + pi.off;
+        return nullptr;
+    }
+    int in_dec(int l) const { return l == 0 ? E + A : H; }
+    int in_enc(int l) const { return l == 0 ? R : h; }
+};
+
+namespace ast {
+
+static int conv_len(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
+
+static std::string lname(int l, const char* stack) { return "L" + std::to_string(l) + "_" + stack; }
+
+static void add_param(ast_model* m, const std::string& name, std::initializer_list<int> shp) {
+    ParamInfo pi; pi.name = name; pi.ndim = (int)shp.size(); pi.count = 1;
+    int i = 0; for (int s : shp) { pi.shape[i++] = s; pi.count *= s; }
+    for (; i < 4; ++i) pi.shape[i] = 1;
+    m->nfloats = (long long)align_up((size_t)m->nfloats, 64);
+    pi.off = m->nfloats; m->nfloats += pi.count;
+    m->pinfo.push_back(pi);
+}
+
+static int build_param_table(ast_model* m) {
+    const ast_config& c = m->cfg;
+    add_param(m, "CNN_0/W", {c.cnn_cout[0], 1, c.cnn_kh[0], c.cnn_kw[0]});
+    add_param(m, "CNN_0_bn/gamma", {c.cnn_cout[0]});
+    add_param(m, "CNN_0_bn/beta", {c.cnn_cout[0]});
+    add_param(m, "CNN_1/W", {c.cnn_cout[1], c.cnn_cout[0], c.cnn_kh[1], c.cnn_kw[1]});
+    add_param(m, "CNN_1_bn/gamma", {c.cnn_cout[1]});
+    add_param(m, "CNN_1_bn/beta", {c.cnn_cout[1]});
+    for (const char* stack : {"enc", "rev_enc"})
+        for (int l = 0; l < m->NL; ++l) {
+            add_param(m, lname(l, stack) + "/upward/W", {4 * m->h, m->in_enc(l)});
+            add_param(m, lname(l, stack) + "/upward/b", {4 * m->h});
+            add_param(m, lname(l, stack) + "/lateral/W", {4 * m->h, m->h});
+        }
+    add_param(m, "attn_Wa/W", {m->H, m->H});
+    add_param(m, "attn_Wa/b", {m->H});
+    add_param(m, "context/W", {m->A, 2 * m->H});
+    add_param(m, "context/b", {m->A});
+    add_param(m, "embed_dec/W", {m->V, m->E});
+    for (int l = 0; l < m->NL; ++l) {
+        add_param(m, lname(l, "dec") + "/upward/W", {4 * m->H, m->in_dec(l)});
+        add_param(m, lname(l, "dec") + "/upward/b", {4 * m->H});
+        add_param(m, lname(l, "dec") + "/lateral/W", {4 * m->H, m->H});
+    }
+    add_param(m, "out/W", {m->V, m->A});
+    add_param(m, "out/b", {m->V});
+    m->nfloats = (long long)align_up((size_t)m->nfloats, 64);
+    return 0;
+}
+
+static void shapes_for(const ast_model* m, int T, int& T1, int& Tp, int& S0, int& Rs) {
+    const ast_config& c = m->cfg;
+    T1 = conv_len(T, c.cnn_kh[0], c.cnn_sh[0], c.cnn_ph[0]);
+    Tp = conv_len(T1, c.cnn_kh[1], c.cnn_sh[1], c.cnn_ph[1]);
+    const int sh = c.cnn_sh[1];
+    S0 = sh * cdiv(T1 + 2 * c.cnn_ph[1], sh);
+    // every valid virtual row r < Tp must stay inside its segment: sh*(Tp-1)+kh <= S0
+    while (sh * (Tp - 1) + c.cnn_kh[1] > S0) S0 += sh;
+    Rs = S0 / sh;
+}
+
+// Lay out every buffer for (B,T,L,N,steps).  dry run computes the size only.
+static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) {
+    int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs);
+    const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, H = m->H, h = m->h, E = m->E, A = m->A, Vp = m->Vp, R = m->R, NL = m->NL;
+    const size_t M0 = (size_t)B * Fp * T1, M1 = (size_t)B * Fp * Rs, TB = (size_t)Tp * B;
+    const int S = std::max(L - 1, 1);
+    const int Bd = std::max(std::max(B, N), 1);
+    m->Xn = a.get<float>((size_t)B * T * m->D);
+    m->cols0 = a.get<float>(M0 * m->ld0);
+    m->W0pad = a.get<float>((size_t)C0 * m->ld0);
+    m->raw0 = a.get<float>(M0 * C0);
+    m->a0p = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
+    m->W1p = a.get<float>((size_t)C1 * m->K1);
+    m->raw1 = a.get<float>(M1 * C1);
+    m->bnstats = a.get<double>(2 * (size_t)std::max(C0, C1));
+    m->norm_sq = a.get<double>(2);
+    m->mean0 = a.get<float>(C0); m->invstd0 = a.get<float>(C0);
+    m->mean1 = a.get<float>(C1); m->invstd1 = a.get<float>(C1);
+    m->rnn_in = a.get<float>(TB * R); m->rnn_rev = a.get<float>(TB * R);
+    for (int l = 0; l < NL; ++l)
+        for (int d = 0; d < 2; ++d) {
+            m->Genc[l][d] = a.get<float>(TB * 4 * h);
+            m->Hs[l][d] = a.get<float>((TB + B) * h);
+            m->Cs[l][d] = a.get<float>((TB + B) * h);
+            m->Hd[l][d] = a.get<float>(TB * h);
+            m->dHd[l][d] = a.get<float>(TB * h);
+        }
+    m->enc_states = a.get<float>(TB * H);
+    m->d_enc = a.get<float>(TB * H);
+    m->d_rnn_in = a.get<float>(TB * R); m->d_rnn_rev = a.get<float>(TB * R);
+    m->draw1 = a.get<float>(M1 * C1);
+    m->dA1 = a.get<float>(M1 * m->K1);
+    m->da0p = a.get<float>((size_t)B * Fp * S0 * C0);
+    m->draw0 = a.get<float>(M0 * C0);
+    m->dW1p = a.get<float>((size_t)C1 * m->K1);
+    m->dW0pad = a.get<float>((size_t)C0 * m->ld0);
+    // decoder (training)
+    const size_t SB = (size_t)S * B;
+    m->x0 = a.get<float>(SB * (E + A));
+    for (int l = 0; l < NL; ++l) {
+        m->actd[l] = a.get<float>(SB * 4 * H);
+        m->Hdec[l] = a.get<float>((SB + B) * H);
+        m->Cdec[l] = a.get<float>((SB + B) * H);
+        m->hdd[l] = a.get<float>(SB * H);
+        m->dxh[l] = a.get<float>((size_t)B * (m->in_dec(l) + H));
+        m->dcd[l] = a.get<float>((size_t)B * H);
+        m->WcatT[l] = a.get<float>((size_t)(m->in_dec(l) + H) * 4 * H);
+    }
+    m->q = a.get<float>(SB * H);
+    m->scores = a.get<float>((size_t)Bd * Tp);
+    m->alpha = a.get<float>(SB * Tp);
+    m->cvh = a.get<float>(SB * 2 * H);
+    m->ht = a.get<float>(SB * A);
+    m->logits = a.get<float>(SB * Vp);
+    m->row_loss = a.get<float>(SB);
+    m->du = a.get<float>(SB * A);
+    m->dcvh = a.get<float>((size_t)B * 2 * H);
+    m->dalpha = a.get<float>((size_t)B * Tp);
+    m->dq = a.get<float>(SB * H);
+    m->dhtop = a.get<float>((size_t)B * H);
+    m->words_used = a.get<int>(SB);
+    m->argmax_steps = a.get<int>(SB);
+    m->WoT = a.get<float>((size_t)A * Vp);
+    m->WcT = a.get<float>((size_t)2 * H * A);
+    m->WaT = a.get<float>((size_t)H * H);
+    m->loss_dev = a.get<float>(4);
+    // decode-time
+    for (int k = 0; k < 2; ++k) {
+        for (int l = 0; l < NL; ++l) { m->st_h[k][l] = a.get<float>((size_t)Bd * H); m->st_c[k][l] = a.get<float>((size_t)Bd * H); }
+        m->st_ht[k] = a.get<float>((size_t)Bd * A);
+        m->s_words[k] = a.get<int>(Bd);
+    }
+    for (int l = 0; l < NL; ++l) {
+        m->st_hpost[l] = a.get<float>((size_t)Bd * H); m->st_cpost[l] = a.get<float>((size_t)Bd * H);
+        m->s_hd[l] = a.get<float>((size_t)Bd * H);
+    }
+    m->s_x0 = a.get<float>((size_t)Bd * (E + A));
+    m->s_act = a.get<float>((size_t)Bd * 4 * H);
+    m->s_q = a.get<float>((size_t)Bd * H);
+    m->s_scores = a.get<float>((size_t)Bd * Tp);
+    m->s_alpha = a.get<float>((size_t)Bd * Tp);
+    m->s_cvh = a.get<float>((size_t)Bd * 2 * H);
+    m->s_htout = a.get<float>((size_t)Bd * A);
+    m->s_logits = a.get<float>((size_t)Bd * Vp);
+    m->s_argmax = a.get<int>(Bd);
+    m->g_preds = a.get<int>((size_t)std::max(steps, 1) * Bd);
+    m->g_seen = a.get<int>(Bd);
+    m->g_done = a.get<int>(4);
+    m->b_cand_lp = a.get<float>((size_t)Bd * 64);
+    m->b_cand_tok = a.get<int>((size_t)Bd * 64);
+    m->b_score = a.get<float>(Bd); m->b_new_score = a.get<float>(Bd);
+    m->b_ints = a.get<int>((size_t)4 * Bd + 8);
+}
+
+static cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// NT GEMM dispatcher: tcgen05 TF32 kernel when enabled and the shape qualifies, fp32 SIMT otherwise.
+static int gemm_nt(ast_model* m, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, const float* bias, float beta = 0.f) {
+    if (m->tc_gemm && !m->exact) {
+        const int r = gemm_tc_nt(st, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+        if (r <= 0) return r;
+    }
+    return sgemm_simt(st, false, true, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, bias);
+}
+
+// Derived weight copies: padded W0, permuted W1, transposed decoder weights.
+static int refresh_weights(ast_model* m, cudaStream_t st) {
+    const ast_config& c = m->cfg;
+    const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
+    AST_CUDA_OK(cudaMemsetAsync(m->W0pad, 0, sizeof(float) * m->C0 * m->ld0, st));
+    AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
+    AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
+    AST_CUDA_OK(cudaMemsetAsync(m->WoT, 0, sizeof(float) * m->A * m->Vp, st));
+    AST_TRY(transpose(st, m->p("out/W"), m->A, m->WoT, m->Vp, m->V, m->A));
+    AST_TRY(transpose(st, m->p("context/W"), 2 * m->H, m->WcT, m->A, m->A, 2 * m->H));
+    AST_TRY(transpose(st, m->p("attn_Wa/W"), m->H, m->WaT, m->H, m->H, m->H));
+    for (int l = 0; l < m->NL; ++l) {
+        const int in = m->in_dec(l);
+        AST_TRY(transpose(st, m->p((lname(l, "dec") + "/upward/W").c_str()), in, m->WcatT[l], 4 * m->H, 4 * m->H, in));
+        AST_TRY(transpose(st, m->p((lname(l, "dec") + "/lateral/W").c_str()), m->H, m->WcatT[l] + (size_t)in * 4 * m->H,
+                          4 * m->H, 4 * m->H, m->H));
+    }
+    m->weights_dirty = false;
+    return 0;
+}
+
+static int require_ready(ast_model* m, int B, int T, int L, int N, int steps) {
+    AST_CHECK(m->P && m->G, "parameters not bound (ast_bind_params)");
+    AST_CHECK(!m->ws.dry && m->ws.base, "workspace not bound (ast_bind_workspace)");
+    AST_CHECK(B <= m->wsB && T <= m->wsT && L <= m->wsL && N <= m->wsN && steps <= m->wsSteps,
+              "workspace too small: need (B=%d,T=%d,L=%d,N=%d,steps=%d), bound for (%d,%d,%d,%d,%d)", B, T, L, N, steps,
+              m->wsB, m->wsT, m->wsL, m->wsN, m->wsSteps);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder forward (seq2seq.py:293-315)
+// ------------------------------------------------------------------------------------------------
+static int encode_impl(ast_model* m, const float* X, int B, int T, int train, const float* noise, float sigma,
+                       cudaStream_t st) {
+    const ast_config& c = m->cfg;
+    AST_CHECK(B >= 1 && B <= 32, "encode: batch %d unsupported (1..32 per call; shard larger batches)", B);
+    int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs);
+    AST_CHECK(Tp >= 1, "encode: utterance too short (T=%d)", T);
+    m->B = B; m->T = T; m->T1 = T1; m->Tp = Tp; m->S0 = S0; m->Rs = Rs; m->train = train;
+    if (m->weights_dirty) AST_TRY(refresh_weights(m, st));
+    const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, h = m->h, R = m->R, NL = m->NL;
+    const int M0 = B * Fp * T1, M1 = B * Fp * Rs, TB = Tp * B;
+    const float drop = train ? c.drop_rnn : 0.f;
+    if (train) m->cur_seed = m->seed + 0x9E3779B97F4A7C15ULL * (++m->step_counter);
+
+    // input noise (seq2seq.py:297-305), train only
+    const float* Xin = X;
+    if (train && (noise || sigma > 0.f)) {
+        AST_TRY(mul_noise(st, X, m->Xn, noise, sigma, m->cur_seed, (size_t)B * T * m->D));
+        Xin = m->Xn;
+    }
+    // CNN_0: im2col + GEMM, BN statistics, BN+ReLU into the padded layout
+    AST_TRY(im2col0(st, Xin, m->cols0, B, T, m->D, Fp, T1, c.cnn_kh[0], c.cnn_kw[0], c.cnn_sh[0], c.cnn_sw[0], c.cnn_ph[0], m->ld0));
+    AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr));
+    float* bn0 = m->bn_state; float* bn1 = m->bn_state + 2 * C0;
+    if (train) {
+        AST_TRY(bn_stats(st, m->raw0, m->bnstats, M0, C0, T1, T1));
+        AST_TRY(bn_finalize(st, m->bnstats, m->mean0, m->invstd0, bn0, bn0 + C0, C0, (double)M0, BN_EPS, BN_DECAY, true));
+    } else {
+        AST_TRY(bn_eval_prepare(st, bn0, bn0 + C0, m->mean0, m->invstd0, C0, BN_EPS));
+    }
+    AST_TRY(bn_relu_pad(st, m->raw0, m->a0p, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
+                        B * Fp, T1, S0, c.cnn_ph[1], C0));
+    AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
+    // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
+    AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr));
+    if (train) {
+        AST_TRY(bn_stats(st, m->raw1, m->bnstats, M1, C1, Rs, Tp));
+        AST_TRY(bn_finalize(st, m->bnstats, m->mean1, m->invstd1, bn1, bn1 + C1, C1, (double)B * Fp * Tp, BN_EPS, BN_DECAY, true));
+    } else {
+        AST_TRY(bn_eval_prepare(st, bn1, bn1 + C1, m->mean1, m->invstd1, C1, BN_EPS));
+    }
+    AST_TRY(bn_relu_to_rnn(st, m->raw1, m->rnn_in, m->rnn_rev, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
+                           m->p("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
+
+    // encoder stacks, layer-major: one batched input-projection GEMM per (layer, direction), then the
+    // persistent recurrence for both directions in one launch.
+    for (int l = 0; l < NL; ++l) {
+        LstmChains ch{};
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
+            AST_TRY(gemm_nt(m, st, TB, 4 * h, m->in_enc(l), xin, m->in_enc(l), m->p((ln + "/upward/W").c_str()), m->in_enc(l),
+                            m->Genc[l][d], 4 * h, m->p((ln + "/upward/b").c_str())));
+            AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
+            AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
+            LstmChain& cc = ch.c[d];
+            cc.G = m->Genc[l][d]; cc.Wl = m->p((ln + "/lateral/W").c_str());
+            cc.Hs = m->Hs[l][d]; cc.Cs = m->Cs[l][d];
+            if (l == NL - 1) {       // top layer writes enc_states (B,T',H) directly; reverse stack flipped (:231)
+                if (d == 0) { cc.out = m->enc_states; cc.out_si = m->H; }
+                else { cc.out = m->enc_states + (size_t)(Tp - 1) * m->H + h; cc.out_si = -(long long)m->H; }
+                cc.out_sb = (long long)Tp * m->H;
+            } else { cc.out = m->Hd[l][d]; cc.out_si = (long long)B * h; cc.out_sb = h; }
+            cc.drop_stream = 1 + 2 * l + d;
+        }
+        AST_TRY(lstm_seq_fwd(st, ch, 2, Tp, B, h, drop, m->cur_seed, m->exact != 0));
+    }
+    m->have_fwd = false;
+    return 0;
+}
+
+// decoder initial state from the encoder finals (seq2seq.py:318-334): dst_h/c (B x H) = [fwd ; rev]
+static int init_dec_state(ast_model* m, float* const* dst_h, float* const* dst_c, int Bd, cudaStream_t st) {
+    const int B = m->B, h = m->h, H = m->H, Tp = m->Tp;
+    AST_CHECK(Bd == B || B == 1, "init_decoder_state: decoder batch %d incompatible with encoder batch %d", Bd, B);
+    for (int l = 0; l < m->NL; ++l)
+        for (int d = 0; d < 2; ++d) {
+            const float* hsrc = m->Hs[l][d] + (size_t)Tp * B * h;
+            const float* csrc = m->Cs[l][d] + (size_t)Tp * B * h;
+            const long long lds = (Bd == B) ? h : 0;       // broadcast one utterance to all hypotheses
+            AST_TRY(copy2d(st, hsrc, lds, dst_h[l] + d * h, H, Bd, h));
+            AST_TRY(copy2d(st, csrc, lds, dst_c[l] + d * h, H, Bd, h));
+        }
+    return 0;
+}
+
+// One decoder step (seq2seq.py:361-396).  All pointers are for this step.
+struct StepIO {
+    int Bd; int step; bool train;
+    const int* y; int ldy; const unsigned char* use_true; const int* prev_argmax; const int* forced_words;
+    const float* ht_prev; float* x0; int* words_used;
+    float* act[MAXL]; const float* h_prev[MAXL]; const float* c_prev[MAXL]; float* h_out[MAXL]; float* c_out[MAXL];
+    float* hd[MAXL]; int ld_hd[MAXL];       // post-dropout outputs; top layer -> cvh[:, H:]
+    float* q; float* scores; float* alpha; float* cvh; float* ht_out; float* logits;
+};
+
+static int dec_step_fwd(ast_model* m, const StepIO& io, cudaStream_t st) {
+    const ast_config& c = m->cfg;
+    const int Bd = io.Bd, H = m->H, E = m->E, A = m->A, NL = m->NL;
+    const bool ex = m->exact != 0;
+    const float de = io.train ? c.drop_embed : 0.f, dr = io.train ? c.drop_rnn : 0.f;
+    AST_TRY(embed_concat(st, m->p("embed_dec/W"), io.y, io.ldy, io.use_true, io.prev_argmax, io.forced_words, io.ht_prev, A,
+                         io.x0, io.words_used, Bd, E, A, m->V, io.step, de, m->cur_seed, 32));
+    for (int l = 0; l < NL; ++l) {
+        const std::string ln = lname(l, "dec");
+        SkinnyArgs s{};
+        s.X[0] = l == 0 ? io.x0 : io.hd[l - 1]; s.ldx[0] = l == 0 ? E + A : io.ld_hd[l - 1]; s.K[0] = m->in_dec(l);
+        s.W[0] = m->p((ln + "/upward/W").c_str()); s.ldw[0] = m->in_dec(l);
+        s.X[1] = io.h_prev[l]; s.ldx[1] = H; s.K[1] = H; s.W[1] = m->p((ln + "/lateral/W").c_str()); s.ldw[1] = H;
+        s.bias = m->p((ln + "/upward/b").c_str());
+        s.B = Bd; s.N = 4 * H; s.epi = EPI_LSTM; s.Y = io.act[l]; s.ldy = 4 * H;
+        s.c_prev = io.c_prev[l]; s.c_out = io.c_out[l]; s.h_out = io.h_out[l]; s.hd_out = io.hd[l]; s.ld_hd = io.ld_hd[l];
+        s.drop = dr; s.seed = m->cur_seed; s.drop_stream = 16 + l; s.drop_base = (size_t)io.step * Bd * H;
+        AST_TRY(skinny(st, s, ex));
+    }
+    const float* htop = io.hd[NL - 1]; const int ldtop = io.ld_hd[NL - 1];
+    {   // q = attn_Wa(h)  (:341)
+        SkinnyArgs s{}; s.X[0] = htop; s.ldx[0] = ldtop; s.K[0] = H; s.W[0] = m->p("attn_Wa/W"); s.ldw[0] = H;
+        s.bias = m->p("attn_Wa/b"); s.B = Bd; s.N = H; s.epi = EPI_NONE; s.Y = io.q; s.ldy = H;
+        AST_TRY(skinny(st, s, ex));
+    }
+    const long long ebs = (m->B == Bd) ? (long long)m->Tp * H : 0;
+    AST_TRY(attn_dot(st, m->enc_states, ebs, io.q, H, io.scores, Bd, m->Tp, H));
+    AST_TRY(attn_ctx(st, m->enc_states, ebs, io.scores, io.alpha, io.cvh, 2 * H, Bd, m->Tp, H));
+    {   // ht = tanh(context([cv;h]))  (:386-390)
+        SkinnyArgs s{}; s.X[0] = io.cvh; s.ldx[0] = 2 * H; s.K[0] = 2 * H; s.W[0] = m->p("context/W"); s.ldw[0] = 2 * H;
+        s.bias = m->p("context/b"); s.B = Bd; s.N = A; s.epi = EPI_TANH; s.Y = io.ht_out; s.ldy = A;
+        AST_TRY(skinny(st, s, ex));
+    }
+    {   // logits = out(ht)  (:394; dropout 'out' ratio is 0 in every shipped config)
+        SkinnyArgs s{}; s.X[0] = io.ht_out; s.ldx[0] = A; s.K[0] = A; s.W[0] = m->p("out/W"); s.ldw[0] = A;
+        s.bias = m->p("out/b"); s.B = Bd; s.N = m->V; s.epi = EPI_NONE; s.Y = io.logits; s.ldy = m->Vp;
+        AST_TRY(skinny(st, s, ex));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward_loss (seq2seq.py:399-473)
+// ------------------------------------------------------------------------------------------------
+static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, int T, int L, const unsigned char* use_true,
+                             const float* noise, float sigma, float* loss_out, cudaStream_t st) {
+    AST_CHECK(L >= 2, "forward_loss: need at least 2 target tokens (got %d)", L);
+    AST_CHECK(m->cfg.drop_out == 0.f, "dropout on the output layer is not supported (0 in every shipped config)");
+    AST_TRY(encode_impl(m, X, B, T, 1, noise, sigma, st));
+    const int H = m->H, E = m->E, A = m->A, NL = m->NL, Tp = m->Tp, S = L - 1;
+    m->L = L;
+    float* hinit[MAXL]; float* cinit[MAXL];
+    for (int l = 0; l < NL; ++l) { hinit[l] = m->Hdec[l]; cinit[l] = m->Cdec[l]; }
+    AST_TRY(init_dec_state(m, hinit, cinit, B, st));
+    for (int s = 0; s < S; ++s) {
+        StepIO io{};
+        io.Bd = B; io.step = s; io.train = true; io.y = y; io.ldy = L; io.use_true = use_true;
+        io.prev_argmax = s > 0 ? m->argmax_steps + (size_t)(s - 1) * B : nullptr;
+        io.ht_prev = s > 0 ? m->ht + (size_t)(s - 1) * B * A : nullptr;
+        io.x0 = m->x0 + (size_t)s * B * (E + A);
+        io.words_used = m->words_used + (size_t)s * B;
+        for (int l = 0; l < NL; ++l) {
+            io.act[l] = m->actd[l] + (size_t)s * B * 4 * H;
+            io.h_prev[l] = m->Hdec[l] + (size_t)s * B * H; io.c_prev[l] = m->Cdec[l] + (size_t)s * B * H;
+            io.h_out[l] = m->Hdec[l] + (size_t)(s + 1) * B * H; io.c_out[l] = m->Cdec[l] + (size_t)(s + 1) * B * H;
+            if (l == NL - 1) { io.hd[l] = m->cvh + (size_t)s * B * 2 * H + H; io.ld_hd[l] = 2 * H; }
+            else { io.hd[l] = m->hdd[l] + (size_t)s * B * H; io.ld_hd[l] = H; }
+        }
+        io.q = m->q + (size_t)s * B * H; io.scores = m->scores; io.alpha = m->alpha + (size_t)s * B * Tp;
+        io.cvh = m->cvh + (size_t)s * B * 2 * H; io.ht_out = m->ht + (size_t)s * B * A;
+        io.logits = m->logits + (size_t)s * B * m->Vp;
+        AST_TRY(dec_step_fwd(m, io, st));
+        // CE against y[:, s+1], gradient in place, argmax for scheduled sampling (:448,468)
+        AST_TRY(softmax_ce(st, io.logits, m->Vp, y, L, s + 1, m->row_loss + (size_t)s * B, m->argmax_steps + (size_t)s * B, B,
+                           m->V, true));
+    }
+    AST_TRY(loss_reduce(st, m->row_loss, S * B, m->loss_dev));
+    if (loss_out) AST_CUDA_OK(cudaMemcpyAsync(loss_out, m->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    m->have_fwd = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (nn.py:180-181)
+// ------------------------------------------------------------------------------------------------
+static int backward_impl(ast_model* m, cudaStream_t st) {
+    AST_CHECK(m->have_fwd, "backward: no forward_loss to differentiate");
+    const ast_config& c = m->cfg;
+    const int B = m->B, H = m->H, h = m->h, E = m->E, A = m->A, NL = m->NL, Tp = m->Tp, S = m->L - 1, Vp = m->Vp, V = m->V;
+    const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, R = m->R, T1 = m->T1, S0 = m->S0, Rs = m->Rs;
+    const bool ex = m->exact != 0;
+    const float de = c.drop_embed, dr = c.drop_rnn;
+    const int SB = S * B, TB = Tp * B;
+    {   // cleargrads for the accumulate-style outputs
+        const ParamInfo* pe = nullptr; for (auto& pi : m->pinfo) if (pi.name == "embed_dec/W") pe = &pi;
+        AST_CUDA_OK(cudaMemsetAsync(m->G + pe->off, 0, sizeof(float) * pe->count, st));
+        AST_CUDA_OK(cudaMemsetAsync(m->d_enc, 0, sizeof(float) * (size_t)TB * H, st));
+        for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
+    }
+    // ---- decoder BPTT: data gradients step by step -----------------------------------------------
+    for (int s = S - 1; s >= 0; --s) {
+        const float* dz = m->logits + (size_t)s * B * Vp;
+        float* du = m->du + (size_t)s * B * A;
+        {   // du = (dz . Wo + dht_feed) * (1 - ht^2)
+            SkinnyArgs k{}; k.X[0] = dz; k.ldx[0] = Vp; k.K[0] = Vp; k.W[0] = m->WoT; k.ldw[0] = Vp;
+            k.B = B; k.N = A; k.epi = EPI_TANHBWD; k.Y = du; k.ldy = A;
+            if (s < S - 1) { k.add = m->dxh[0] + E; k.ld_add = E + A + H; }
+            k.aux = m->ht + (size_t)s * B * A; k.ld_aux = A;
+            AST_TRY(skinny(st, k, ex));
+        }
+        {   // dcvh = du . Wc
+            SkinnyArgs k{}; k.X[0] = du; k.ldx[0] = A; k.K[0] = A; k.W[0] = m->WcT; k.ldw[0] = A;
+            k.B = B; k.N = 2 * H; k.epi = EPI_NONE; k.Y = m->dcvh; k.ldy = 2 * H;
+            AST_TRY(skinny(st, k, ex));
+        }
+        const long long ebs = (long long)Tp * H;
+        AST_TRY(attn_dot(st, m->enc_states, ebs, m->dcvh, 2 * H, m->dalpha, B, Tp, H));
+        float* dq = m->dq + (size_t)s * B * H;
+        AST_TRY(attn_bwd(st, m->enc_states, m->d_enc, ebs, m->alpha + (size_t)s * B * Tp, m->dalpha, m->dcvh, 2 * H,
+                         m->q + (size_t)s * B * H, H, dq, H, B, Tp, H));
+        {   // dh_top = dcvh[:, H:] + dq . Wa
+            SkinnyArgs k{}; k.X[0] = dq; k.ldx[0] = H; k.K[0] = H; k.W[0] = m->WaT; k.ldw[0] = H;
+            k.B = B; k.N = H; k.epi = EPI_NONE; k.Y = m->dhtop; k.ldy = H; k.add = m->dcvh + H; k.ld_add = 2 * H;
+            AST_TRY(skinny(st, k, ex));
+        }
+        for (int l = NL - 1; l >= 0; --l) {
+            const int in = m->in_dec(l);
+            const float* d_out = l == NL - 1 ? m->dhtop : m->dxh[l + 1];
+            const int ld_dout = l == NL - 1 ? H : m->in_dec(l + 1) + H;
+            float* act = m->actd[l] + (size_t)s * B * 4 * H;
+            AST_TRY(lstm_cell_bwd(st, act, m->Cdec[l] + (size_t)(s + 1) * B * H, m->Cdec[l] + (size_t)s * B * H, d_out, ld_dout,
+                                  s < S - 1 ? m->dxh[l] + in : nullptr, in + H, m->dcd[l], B, H, s * B, dr, m->cur_seed, 16 + l));
+            SkinnyArgs k{}; k.X[0] = act; k.ldx[0] = 4 * H; k.K[0] = 4 * H; k.W[0] = m->WcatT[l]; k.ldw[0] = 4 * H;
+            k.B = B; k.N = in + H; k.epi = EPI_NONE; k.Y = m->dxh[l]; k.ldy = in + H;
+            AST_TRY(skinny(st, k, ex));
+        }
+        AST_TRY(embed_scatter(st, m->g("embed_dec/W"), m->dxh[0], E + A + H, m->words_used + (size_t)s * B, B, E, s, de,
+                              m->cur_seed, 32));
+    }
+    // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
+    AST_TRY(sgemm_simt(st, true, false, V, A, SB, 1.f, m->logits, Vp, m->ht, A, 0.f, m->g("out/W"), A, nullptr));
+    AST_TRY(colsum(st, m->logits, Vp, m->g("out/b"), SB, V, false));
+    AST_TRY(sgemm_simt(st, true, false, A, 2 * H, SB, 1.f, m->du, A, m->cvh, 2 * H, 0.f, m->g("context/W"), 2 * H, nullptr));
+    AST_TRY(colsum(st, m->du, A, m->g("context/b"), SB, A, false));
+    AST_TRY(sgemm_simt(st, true, false, H, H, SB, 1.f, m->dq, H, m->cvh + H, 2 * H, 0.f, m->g("attn_Wa/W"), H, nullptr));
+    AST_TRY(colsum(st, m->dq, H, m->g("attn_Wa/b"), SB, H, false));
+    for (int l = 0; l < NL; ++l) {
+        const std::string ln = lname(l, "dec");
+        const int in = m->in_dec(l);
+        const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
+        AST_TRY(sgemm_simt(st, true, false, 4 * H, in, SB, 1.f, m->actd[l], 4 * H, xin, in, 0.f,
+                           m->g((ln + "/upward/W").c_str()), in, nullptr));
+        AST_TRY(sgemm_simt(st, true, false, 4 * H, H, SB, 1.f, m->actd[l], 4 * H, m->Hdec[l], H, 0.f,
+                           m->g((ln + "/lateral/W").c_str()), H, nullptr));
+        AST_TRY(colsum(st, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
+    }
+    // ---- encoder BPTT, layer-major top-down; both directions per launch ------------------------------
+    for (int l = NL - 1; l >= 0; --l) {
+        LstmChains ch{};
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            LstmChain& cc = ch.c[d];
+            cc.G = m->Genc[l][d]; cc.Wl = m->p((ln + "/lateral/W").c_str()); cc.Hs = m->Hs[l][d]; cc.Cs = m->Cs[l][d];
+            if (l == NL - 1) {
+                if (d == 0) { cc.dout = m->d_enc; cc.out_si = H; }
+                else { cc.dout = m->d_enc + (size_t)(Tp - 1) * H + h; cc.out_si = -(long long)H; }
+                cc.out_sb = (long long)Tp * H;
+            } else { cc.dout = m->dHd[l][d]; cc.out_si = (long long)B * h; cc.out_sb = h; }
+            cc.dh_fin = m->dxh[l] + m->in_dec(l) + d * h; cc.ld_dh_fin = m->in_dec(l) + H;
+            cc.dc_fin = m->dcd[l] + d * h; cc.ld_dc_fin = H;
+            cc.drop_stream = 1 + 2 * l + d;
+        }
+        AST_TRY(lstm_seq_bwd(st, ch, 2, Tp, B, h, dr, m->cur_seed, ex));
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            const int in = m->in_enc(l);
+            const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
+            float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
+            const float* Wup = m->p((ln + "/upward/W").c_str());
+            AST_TRY(sgemm_simt(st, false, false, TB, in, 4 * h, 1.f, m->Genc[l][d], 4 * h, Wup, in, 0.f, dx, in, nullptr));
+            AST_TRY(sgemm_simt(st, true, false, 4 * h, in, TB, 1.f, m->Genc[l][d], 4 * h, xin, in, 0.f,
+                               m->g((ln + "/upward/W").c_str()), in, nullptr));
+            AST_TRY(sgemm_simt(st, true, false, 4 * h, h, TB, 1.f, m->Genc[l][d], 4 * h, m->Hs[l][d], h, 0.f,
+                               m->g((ln + "/lateral/W").c_str()), h, nullptr));
+            AST_TRY(colsum(st, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
+        }
+    }
+    // ---- CNN backward ------------------------------------------------------------------------------------
+    const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
+    AST_TRY(bn_bwd_from_rnn(st, m->d_rnn_in, m->d_rnn_rev, m->raw1, m->draw1, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
+                            m->p("CNN_1_bn/beta"), m->bnstats, m->g("CNN_1_bn/gamma"), m->g("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
+    AST_TRY(sgemm_simt(st, true, false, C1, m->K1, M1, 1.f, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, 0.f, m->dW1p, m->K1, nullptr));
+    AST_TRY(permute_w1(st, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
+    AST_TRY(sgemm_simt(st, false, false, M1, m->K1, C1, 1.f, m->draw1, C1, m->W1p, m->K1, 0.f, m->dA1, m->K1, nullptr));
+    AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
+    AST_TRY(bn_bwd_from_padded(st, m->da0p, m->raw0, m->draw0, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
+                               m->bnstats, m->g("CNN_0_bn/gamma"), m->g("CNN_0_bn/beta"), B * Fp, T1, S0, c.cnn_ph[1], C0));
+    AST_TRY(sgemm_simt(st, true, false, C0, m->ld0, M0, 1.f, m->draw0, C0, m->cols0, m->ld0, 0.f, m->dW0pad, m->ld0, nullptr));
+    const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
+    AST_TRY(copy2d(st, m->dW0pad, m->ld0, m->g("CNN_0/W"), K0, C0, K0));
+    m->have_fwd = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode-time helpers: one step on the model's own state banks
+// ------------------------------------------------------------------------------------------------
+static int decode_bank_step(ast_model* m, int bank, int Bd, const int* words, const float* ht_in, float* logits_out,
+                            float* ht_out, float* alpha_out, bool to_post, cudaStream_t st) {
+    StepIO io{};
+    io.Bd = Bd; io.step = 0; io.train = false; io.forced_words = words; io.ht_prev = ht_in;
+    io.x0 = m->s_x0;
+    for (int l = 0; l < m->NL; ++l) {
+        io.act[l] = m->s_act; io.h_prev[l] = m->st_h[bank][l]; io.c_prev[l] = m->st_c[bank][l];
+        io.h_out[l] = to_post ? m->st_hpost[l] : m->st_h[bank ^ 1][l];
+        io.c_out[l] = to_post ? m->st_cpost[l] : m->st_c[bank ^ 1][l];
+        if (l == m->NL - 1) { io.hd[l] = m->s_cvh + m->H; io.ld_hd[l] = 2 * m->H; }
+        else { io.hd[l] = m->s_hd[l]; io.ld_hd[l] = m->H; }
+    }
+    io.q = m->s_q; io.scores = m->s_scores; io.alpha = alpha_out ? alpha_out : m->s_alpha; io.cvh = m->s_cvh;
+    io.ht_out = ht_out; io.logits = logits_out;
+    return dec_step_fwd(m, io, st);
+}
+
+}  // namespace ast
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* ast_last_error(void) { return ast::get_last_error(); }
+int ast_abi_version(void) { return 1; }
+
+int ast_create(const ast_config* cfg, int device, ast_model** out) {
+    AST_CHECK(cfg && out, "ast_create: null argument");
+    ast_model* m = new ast_model();
+    m->cfg = *cfg; m->device = device;
+    const ast_config& c = m->cfg;
+    m->D = c.feat_dim; m->C0 = c.cnn_cout[0]; m->C1 = c.cnn_cout[1];
+    m->H = c.hidden_units; m->h = m->H / 2; m->E = c.embedding_units; m->A = c.attn_units; m->V = c.vocab;
+    m->Vp = (int)align_up((size_t)m->V, 16); m->NL = c.enc_layers;
+#define AST_CREATE_CHECK(cond, ...) do { if (!(cond)) { ast::set_last_error(__VA_ARGS__); delete m; return -1; } } while (0)
+    AST_CREATE_CHECK(c.enc_layers == c.dec_layers && c.enc_layers >= 1 && c.enc_layers <= MAXL,
+                     "enc_layers/dec_layers must be equal and in 1..%d (init_decoder_state zips them, seq2seq.py:323)", MAXL);
+    AST_CREATE_CHECK(c.cnn_kw[1] == 1 && c.cnn_sw[1] == 1 && c.cnn_pw[1] == 0, "second CNN layer must be 1-wide on the feature axis");
+    AST_CREATE_CHECK(c.cnn_pw[0] == 0, "first CNN layer feature-axis padding must be 0");
+    AST_CREATE_CHECK(m->C0 % 4 == 0 && m->C1 % 4 == 0, "CNN channel counts must be multiples of 4");
+    AST_CREATE_CHECK(m->H % 128 == 0 && m->h <= 256, "hidden_units must be a multiple of 128 and <= 512");
+    AST_CREATE_CHECK(m->E % 16 == 0 && m->A % 16 == 0, "embedding_units and attn_units must be multiples of 16");
+    AST_CREATE_CHECK(m->V >= 4, "vocab must include the 4 special symbols");
+    m->Fp = conv_len(m->D, c.cnn_kw[0], c.cnn_sw[0], c.cnn_pw[0]);
+    AST_CREATE_CHECK(m->Fp >= 1, "feature dim %d too small for the first CNN kernel", m->D);
+    m->R = m->C1 * m->Fp;
+    m->ld0 = (int)align_up((size_t)c.cnn_kh[0] * c.cnn_kw[0], 4);
+    m->K1 = c.cnn_kh[1] * m->C0;
+    build_param_table(m);
+    cudaError_t e = cudaSetDevice(device);
+    AST_CREATE_CHECK(e == cudaSuccess, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    e = cudaMallocHost(&m->h_pinned, 64 * sizeof(int));
+    AST_CREATE_CHECK(e == cudaSuccess, "cudaMallocHost: %s", cudaGetErrorString(e));
+#undef AST_CREATE_CHECK
+    *out = m;
+    return 0;
+}
+
+int ast_destroy(ast_model* m) {
+    if (!m) return 0;
+    if (m->h_pinned) cudaFreeHost(m->h_pinned);
+    delete m;
+    return 0;
+}
+
+long long ast_param_floats(const ast_model* m) { return m->nfloats; }
+int ast_param_count(const ast_model* m) { return (int)m->pinfo.size(); }
+int ast_param_info(const ast_model* m, int idx, char* name, int name_cap, long long* offset, int* ndim, int* shape4) {
+    AST_CHECK(idx >= 0 && idx < (int)m->pinfo.size(), "ast_param_info: index %d out of range", idx);
+    const ParamInfo& pi = m->pinfo[idx];
+    if (name && name_cap > 0) { strncpy(name, pi.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (offset) *offset = pi.off;
+    if (ndim) *ndim = pi.ndim;
+    if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = pi.shape[i];
+    return 0;
+}
+int ast_bn_state_floats(const ast_model* m) { return 2 * (m->C0 + m->C1); }
+int ast_bind_params(ast_model* m, float* params, float* grads, float* bn_state) {
+    AST_CHECK(params && grads && bn_state, "ast_bind_params: null pointer");
+    AST_CHECK((uintptr_t)params % 256 == 0 && (uintptr_t)grads % 256 == 0, "param/grad buffers must be 256-byte aligned");
+    m->P = params; m->G = grads; m->bn_state = bn_state; m->weights_dirty = true;
+    return 0;
+}
+int ast_weights_changed(ast_model* m) { m->weights_dirty = true; return 0; }
+
+long long ast_workspace_bytes(const ast_model* m, int B, int T, int L, int beam_n, int max_steps) {
+    ast_model tmp = *m;            // plan() only writes pointer members of the copy
+    Arena a; a.dry = true;
+    plan(&tmp, a, B, T, L, beam_n, max_steps);
+    return (long long)align_up(a.used, 256) + 256;
+}
+int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, int L, int beam_n, int max_steps) {
+    AST_CHECK(ws && (uintptr_t)ws % 256 == 0, "workspace must be non-null and 256-byte aligned");
+    Arena a; a.dry = false; a.base = (char*)ws; a.cap = (size_t)bytes;
+    plan(m, a, B, T, L, beam_n, max_steps);
+    AST_CHECK((long long)a.used <= bytes, "workspace too small: need %zu bytes, got %lld", a.used, bytes);
+    m->ws = a; m->wsB = B; m->wsT = T; m->wsL = L; m->wsN = beam_n; m->wsSteps = max_steps;
+    m->weights_dirty = true; m->have_fwd = false; m->Tp = 0; m->L = 0;
+    return 0;
+}
+
+int ast_set_option(ast_model* m, const char* key, double value) {
+    if (!strcmp(key, "exact")) m->exact = value != 0;
+    else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
+    else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
+    else { ast::set_last_error("unknown option '%s'", key); return -1; }
+    return 0;
+}
+double ast_get_option(const ast_model* m, const char* key) {
+    if (!strcmp(key, "exact")) return m->exact;
+    if (!strcmp(key, "tc_gemm")) return m->tc_gemm;
+    if (!strcmp(key, "seed")) return (double)m->seed;
+    return -1;
+}
+
+int ast_enc_len(const ast_model* m, int T) { int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs); return Tp; }
+
+int ast_encode(ast_model* m, const float* X, int B, int T, int train, const float* noise, float noise_sigma, void* stream) {
+    AST_TRY(require_ready(m, B, T, 0, 0, 0));
+    return encode_impl(m, X, B, T, train, noise, noise_sigma, S_(stream));
+}
+int ast_get_enc_states(ast_model* m, float* out, void* stream) {
+    AST_CHECK(m->Tp > 0, "no encoder output yet");
+    AST_CUDA_OK(cudaMemcpyAsync(out, m->enc_states, sizeof(float) * (size_t)m->B * m->Tp * m->H, cudaMemcpyDeviceToDevice, S_(stream)));
+    return 0;
+}
+
+int ast_forward_loss(ast_model* m, const float* X, const int* y, int B, int T, int L, const unsigned char* use_true,
+                     const float* noise, float noise_sigma, float* loss_out, void* stream) {
+    AST_TRY(require_ready(m, B, T, L, 0, 0));
+    return forward_loss_impl(m, X, y, B, T, L, use_true, noise, noise_sigma, loss_out, S_(stream));
+}
+int ast_backward(ast_model* m, void* stream) { return backward_impl(m, S_(stream)); }
+int ast_get_step_argmax(ast_model* m, int* out, void* stream) {
+    AST_CHECK(m->L >= 2, "no forward_loss yet");
+    AST_CUDA_OK(cudaMemcpyAsync(out, m->argmax_steps, sizeof(int) * (size_t)(m->L - 1) * m->B, cudaMemcpyDeviceToDevice, S_(stream)));
+    return 0;
+}
+
+int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr, float l2, float clip, float beta1,
+                 float beta2, float eps, float grad_scale, const int* frozen_idx, int n_frozen, void* stream) {
+    AST_CHECK(m->P && m->G && !m->ws.dry, "opt_step: params/workspace not bound");
+    AST_CHECK(t >= 1, "opt_step: t is 1-based");
+    AST_CHECK(n_frozen <= 8, "opt_step: at most 8 frozen tensors");
+    FrozenRanges fr{}; fr.n = 0;
+    for (int i = 0; i < n_frozen; ++i) {
+        AST_CHECK(frozen_idx[i] >= 0 && frozen_idx[i] < (int)m->pinfo.size(), "opt_step: bad frozen index");
+        const ParamInfo& pi = m->pinfo[frozen_idx[i]];
+        fr.begin[fr.n] = (size_t)pi.off; fr.end[fr.n] = align_up((size_t)(pi.off + pi.count), 64); ++fr.n;
+    }
+    const double fix1 = 1.0 - pow((double)beta1, t), fix2 = 1.0 - pow((double)beta2, t);
+    const float alpha_t = (float)(lr * sqrt(fix2) / fix1);
+    cudaStream_t st = S_(stream);
+    AST_TRY(opt_sqnorm(st, m->G, m->P, (size_t)m->nfloats, grad_scale, l2, m->norm_sq));
+    AST_TRY(opt_amsgrad(st, m->P, m->G, m1, v, vhat, (size_t)m->nfloats, grad_scale, l2, clip, m->norm_sq, alpha_t, beta1, beta2, eps, fr));
+    m->weights_dirty = true;
+    return 0;
+}
+double ast_last_grad_norm(ast_model* m, void* stream) {
+    double v = 0;
+    if (cudaMemcpyAsync(&v, m->norm_sq, sizeof(double), cudaMemcpyDeviceToHost, S_(stream)) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(S_(stream)) != cudaSuccess) return -1;
+    return sqrt(v);
+}
+
+// ---- decoder state protocol -----------------------------------------------------------------------
+int ast_init_decoder_state(ast_model* m, int Bd, void* stream) {
+    AST_CHECK(m->Tp > 0, "init_decoder_state: encode first");
+    AST_CHECK(Bd >= 1 && Bd <= std::max(m->wsB, m->wsN), "init_decoder_state: Bd %d exceeds workspace", Bd);
+    m->dec_Bd = Bd;
+    return init_dec_state(m, m->st_h[0], m->st_c[0], Bd, S_(stream));
+}
+int ast_get_encoder_states(ast_model* m, float* states, void* stream) {
+    AST_CHECK(m->Tp > 0, "get_encoder_states: encode first");
+    const int B = m->B, H = m->H;
+    float* hp[MAXL]; float* cp[MAXL];
+    for (int l = 0; l < m->NL; ++l) { cp[l] = states + (size_t)(2 * l) * B * H; hp[l] = states + (size_t)(2 * l + 1) * B * H; }
+    return init_dec_state(m, hp, cp, B, S_(stream));
+}
+int ast_get_decoder_states(ast_model* m, float* states, int Bd, void* stream) {
+    const int H = m->H;
+    for (int l = 0; l < m->NL; ++l) {
+        AST_CUDA_OK(cudaMemcpyAsync(states + (size_t)(2 * l) * Bd * H, m->st_c[0][l], sizeof(float) * Bd * H, cudaMemcpyDeviceToDevice, S_(stream)));
+        AST_CUDA_OK(cudaMemcpyAsync(states + (size_t)(2 * l + 1) * Bd * H, m->st_h[0][l], sizeof(float) * Bd * H, cudaMemcpyDeviceToDevice, S_(stream)));
+    }
+    return 0;
+}
+int ast_set_decoder_states(ast_model* m, const float* states, int Bd, void* stream) {
+    const int H = m->H;
+    AST_CHECK(Bd >= 1 && Bd <= std::max(m->wsB, m->wsN), "set_decoder_states: Bd %d exceeds workspace", Bd);
+    m->dec_Bd = Bd;
+    for (int l = 0; l < m->NL; ++l) {
+        AST_CUDA_OK(cudaMemcpyAsync(m->st_c[0][l], states + (size_t)(2 * l) * Bd * H, sizeof(float) * Bd * H, cudaMemcpyDeviceToDevice, S_(stream)));
+        AST_CUDA_OK(cudaMemcpyAsync(m->st_h[0][l], states + (size_t)(2 * l + 1) * Bd * H, sizeof(float) * Bd * H, cudaMemcpyDeviceToDevice, S_(stream)));
+    }
+    return 0;
+}
+int ast_decode_step(ast_model* m, const int* word, const float* ht_in, int Bd, float* logits, float* ht_out, float* alphas,
+                    void* stream) {
+    AST_CHECK(m->Tp > 0, "decode_step: encode first");
+    AST_CHECK(Bd == m->dec_Bd, "decode_step: batch %d != decoder state batch %d", Bd, m->dec_Bd);
+    AST_CHECK(Bd == m->B || m->B == 1, "decode_step: decoder batch %d incompatible with encoder batch %d", Bd, m->B);
+    cudaStream_t st = S_(stream);
+    if (m->weights_dirty) AST_TRY(refresh_weights(m, st));
+    // state bank 0 -> post buffers -> back into bank 0 (the link state after the call, seq2seq.py:375)
+    AST_TRY(decode_bank_step(m, 0, Bd, word, ht_in, m->s_logits, m->s_htout, alphas ? alphas : nullptr, true, st));
+    for (int l = 0; l < m->NL; ++l) {
+        AST_CUDA_OK(cudaMemcpyAsync(m->st_h[0][l], m->st_hpost[l], sizeof(float) * Bd * m->H, cudaMemcpyDeviceToDevice, st));
+        AST_CUDA_OK(cudaMemcpyAsync(m->st_c[0][l], m->st_cpost[l], sizeof(float) * Bd * m->H, cudaMemcpyDeviceToDevice, st));
+    }
+    AST_TRY(copy2d(st, m->s_logits, m->Vp, logits, m->V, Bd, m->V));
+    AST_CUDA_OK(cudaMemcpyAsync(ht_out, m->s_htout, sizeof(float) * Bd * m->A, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- greedy decode -----------------------------------------------------------------------------------
+int ast_predict(ast_model* m, const float* X, int B, int T, int start_token, int end_token, int stop_limit, int* preds,
+                int* n_steps, void* stream) {
+    AST_TRY(require_ready(m, B, T, 0, 0, stop_limit));
+    cudaStream_t st = S_(stream);
+    AST_TRY(encode_impl(m, X, B, T, 0, nullptr, 0.f, st));
+    AST_TRY(init_dec_state(m, m->st_h[0], m->st_c[0], B, st));
+    m->dec_Bd = B;
+    std::vector<int> start(B, start_token);
+    AST_CUDA_OK(cudaMemcpyAsync(m->s_words[0], start.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaStreamSynchronize(st));       // `start` is pageable host memory
+    AST_CUDA_OK(cudaMemsetAsync(m->g_seen, 0, sizeof(int) * B, st));
+    AST_CUDA_OK(cudaMemsetAsync(m->g_done, 0xff, sizeof(int), st));
+    AST_CUDA_OK(cudaMemsetAsync(m->st_ht[0], 0, sizeof(float) * B * m->A, st));
+    int bank = 0, steps = 0;
+    for (int s = 0; s < stop_limit; ++s) {
+        AST_TRY(decode_bank_step(m, bank, B, s == 0 ? m->s_words[0] : m->s_argmax, m->st_ht[bank], m->s_logits, m->st_ht[bank ^ 1],
+                                 nullptr, false, st));
+        AST_TRY(softmax_ce(st, m->s_logits, m->Vp, nullptr, 0, 0, nullptr, m->s_argmax, B, m->V, false));
+        AST_TRY(greedy_track(st, m->s_argmax, m->g_preds, m->g_seen, m->g_done, B, s, end_token));
+        bank ^= 1; steps = s + 1;
+        if ((s & 7) == 7 || s == stop_limit - 1) {
+            AST_CUDA_OK(cudaMemcpyAsync(m->h_pinned, m->g_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            AST_CUDA_OK(cudaStreamSynchronize(st));
+            if (m->h_pinned[0] >= 0) { steps = m->h_pinned[0] + 1; break; }
+        }
+    }
+    // reference semantics (seq2seq.py:502-524): the loop body runs for npred = 0..stop_limit-1 and breaks
+    // right after the step at which every row has emitted EOS.
+    AST_CUDA_OK(cudaMemcpyAsync(preds, m->g_preds, sizeof(int) * (size_t)steps * B, cudaMemcpyDeviceToDevice, st));
+    if (n_steps) *n_steps = steps;
+    return 0;
+}
+
+// ---- beam search ---------------------------------------------------------------------------------------
+int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, int K, int go_token, int eos_token,
+                    int* n_steps, int* n_hyps, int* hist_parent, int* hist_tok, float* scores, float* alpha_hist,
+                    float* final_states, float* final_attn_v, void* stream) {
+    AST_TRY(require_ready(m, 1, T, 0, N, stop_limit));
+    AST_CHECK(N >= 1 && N <= 32 && K >= 1 && K <= 64 && K <= m->V, "beam_search: need 1<=N<=32, 1<=K<=min(64,V)");
+    AST_CHECK(hist_parent && hist_tok && scores, "beam_search: null output");
+    cudaStream_t st = S_(stream);
+    AST_TRY(encode_impl(m, X, 1, T, 0, nullptr, 0.f, st));
+    const int H = m->H, A = m->A, NL = m->NL, Tp = m->Tp;
+    // zero both state banks so idle slots stay finite, then slot 0 <- encoder finals
+    for (int k = 0; k < 2; ++k) {
+        for (int l = 0; l < NL; ++l) {
+            AST_CUDA_OK(cudaMemsetAsync(m->st_h[k][l], 0, sizeof(float) * N * H, st));
+            AST_CUDA_OK(cudaMemsetAsync(m->st_c[k][l], 0, sizeof(float) * N * H, st));
+        }
+        AST_CUDA_OK(cudaMemsetAsync(m->st_ht[k], 0, sizeof(float) * N * A, st));
+    }
+    AST_TRY(init_dec_state(m, m->st_h[0], m->st_c[0], 1, st));
+    m->dec_Bd = N;
+    // scalars: b_ints = [finished N][new_parent N][new_tok N][new_finished N][n_active, done, steps_done]
+    int* finished = m->b_ints; int* new_parent = finished + N; int* new_tok = new_parent + N; int* new_fin = new_tok + N;
+    int* scal = new_fin + N;
+    std::vector<int> init(4 * N + 8, 0); init[4 * N + 0] = 1;
+    std::vector<int> w0(N, go_token);
+    AST_CUDA_OK(cudaMemcpyAsync(m->b_ints, init.data(), sizeof(int) * (4 * N + 8), cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaMemcpyAsync(m->s_words[0], w0.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaStreamSynchronize(st));
+    AST_CUDA_OK(cudaMemsetAsync(m->b_score, 0, sizeof(float) * N, st));
+    AST_CUDA_OK(cudaMemsetAsync(hist_parent, 0, sizeof(int) * (size_t)stop_limit * N, st));
+    AST_CUDA_OK(cudaMemsetAsync(hist_tok, 0xff, sizeof(int) * (size_t)stop_limit * N, st));
+    BeamState bs{}; bs.score = m->b_score; bs.finished = finished; bs.n_active = scal; bs.done = scal + 1; bs.steps_done = scal + 2;
+    bs.new_score = m->b_new_score; bs.new_parent = new_parent; bs.new_tok = new_tok; bs.new_finished = new_fin;
+    int bank = 0;
+    for (int s = 0; s < stop_limit; ++s) {
+        AST_TRY(decode_bank_step(m, bank, N, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st));
+        AST_TRY(beam_topk(st, m->s_logits, m->Vp, m->V, K, N, bs, m->b_cand_lp, m->b_cand_tok));
+        AST_TRY(beam_prune(st, bs, m->b_cand_lp, m->b_cand_tok, N, K, s, eos_token, hist_parent, hist_tok));
+        BeamGather gd{}; gd.n = 0;
+        for (int l = 0; l < NL; ++l) {
+            gd.cur[gd.n] = m->st_h[bank][l]; gd.post[gd.n] = m->st_hpost[l]; gd.nxt[gd.n] = m->st_h[bank ^ 1][l]; gd.width[gd.n++] = H;
+            gd.cur[gd.n] = m->st_c[bank][l]; gd.post[gd.n] = m->st_cpost[l]; gd.nxt[gd.n] = m->st_c[bank ^ 1][l]; gd.width[gd.n++] = H;
+        }
+        gd.cur[gd.n] = m->st_ht[bank]; gd.post[gd.n] = m->s_htout; gd.nxt[gd.n] = m->st_ht[bank ^ 1]; gd.width[gd.n++] = A;
+        float* ah = alpha_hist ? alpha_hist : nullptr;
+        AST_CHECK(alpha_hist != nullptr, "beam_search: alpha_hist buffer required");
+        AST_TRY(beam_gather(st, bs, gd, N, s, Tp, m->s_alpha, ah, m->s_words[bank], m->s_words[bank ^ 1]));
+        bank ^= 1;
+        if ((s & 15) == 15 || s == stop_limit - 1) {
+            AST_CUDA_OK(cudaMemcpyAsync(m->h_pinned, scal, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+            AST_CUDA_OK(cudaStreamSynchronize(st));
+            if (m->h_pinned[1]) break;
+        }
+    }
+    AST_CUDA_OK(cudaMemcpyAsync(m->h_pinned, scal, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+    AST_CUDA_OK(cudaStreamSynchronize(st));
+    const int steps = m->h_pinned[2];
+    if (n_steps) *n_steps = steps;
+    if (n_hyps) *n_hyps = m->h_pinned[0];
+    // the live bank after `steps` prunes: bank toggled once per executed iteration; the state of the kept
+    // hypotheses is in bank (steps & 1) because idle iterations do not move data but do toggle.
+    const int fb = steps & 1;
+    AST_CUDA_OK(cudaMemcpyAsync(scores, m->b_score, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    if (final_states)
+        for (int l = 0; l < NL; ++l) {
+            AST_CUDA_OK(cudaMemcpyAsync(final_states + (size_t)(2 * l) * N * H, m->st_c[fb][l], sizeof(float) * N * H, cudaMemcpyDeviceToDevice, st));
+            AST_CUDA_OK(cudaMemcpyAsync(final_states + (size_t)(2 * l + 1) * N * H, m->st_h[fb][l], sizeof(float) * N * H, cudaMemcpyDeviceToDevice, st));
+        }
+    if (final_attn_v) AST_CUDA_OK(cudaMemcpyAsync(final_attn_v, m->st_ht[fb], sizeof(float) * N * A, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- stateless kernels ------------------------------------------------------------------------------------
+int ast_pack_cmvn(const float* raw, const long long* row_off, const int* lens, const float* scale, const float* offset,
+                  const unsigned char* keep, const float* noise, float noise_sigma, unsigned long long seed, float* X, int B,
+                  int T, int D, void* stream) {
+    return pack_cmvn(S_(stream), raw, row_off, lens, scale, offset, keep, noise, noise_sigma, seed, X, B, T, D);
+}
+int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V, float* row_loss, int* argmax, void* stream) {
+    return softmax_ce(S_(stream), logits_inout, ld, targets, 1, 0, row_loss, argmax, B, V, true);
+}
+int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+             float beta, float* C, int ldc, const float* bias, void* stream) {
+    if (which == 1) {
+        AST_CHECK(!ta && tb && alpha == 1.f, "tcgen05 GEMM supports C = A*B^T (+bias, +beta*C) only");
+        const int r = gemm_tc_nt(S_(stream), M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+        AST_CHECK(r <= 0, "tcgen05 GEMM: unsupported shape M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+        return r;
+    }
+    return sgemm_simt(S_(stream), ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+}
+int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, float* out_or_dout, int T, int B, int h,
+                 const float* dh_fin, const float* dc_fin, int exact, void* stream) {
+    LstmChains ch{};
+    LstmChain& c = ch.c[0];
+    c.G = G; c.Wl = Wl; c.Hs = Hs; c.Cs = Cs; c.out = out_or_dout; c.dout = out_or_dout;
+    c.out_si = (long long)B * h; c.out_sb = h; c.dh_fin = dh_fin; c.dc_fin = dc_fin; c.ld_dh_fin = h; c.ld_dc_fin = h;
+    c.drop_stream = 0;
+    return backward ? lstm_seq_bwd(S_(stream), ch, 1, T, B, h, 0.f, 0, exact != 0)
+                    : lstm_seq_fwd(S_(stream), ch, 1, T, B, h, 0.f, 0, exact != 0);
+}
+
+// Test hook: copy a named internal buffer (device -> caller's device buffer).
+int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_floats, long long* n_out, void* stream) {
+    const int B = m->B, Tp = m->Tp, h = m->h, H = m->H;
+    const size_t M0 = (size_t)B * m->Fp * m->T1, M1 = (size_t)B * m->Fp * m->Rs, TB = (size_t)Tp * B;
+    const float* src = nullptr; size_t n = 0;
+    std::string s(name);
+    if (s == "cols0") { src = m->cols0; n = M0 * m->ld0; }
+    else if (s == "raw0") { src = m->raw0; n = M0 * m->C0; }
+    else if (s == "a0p") { src = m->a0p; n = (size_t)B * m->Fp * m->S0 * m->C0; }
+    else if (s == "raw1") { src = m->raw1; n = M1 * m->C1; }
+    else if (s == "rnn_in") { src = m->rnn_in; n = TB * m->R; }
+    else if (s == "rnn_rev") { src = m->rnn_rev; n = TB * m->R; }
+    else if (s == "d_enc") { src = m->d_enc; n = TB * H; }
+    else if (s == "d_rnn_in") { src = m->d_rnn_in; n = TB * m->R; }
+    else if (s == "d_rnn_rev") { src = m->d_rnn_rev; n = TB * m->R; }
+    else if (s == "draw1") { src = m->draw1; n = M1 * m->C1; }
+    else if (s == "da0p") { src = m->da0p; n = (size_t)B * m->Fp * m->S0 * m->C0; }
+    else if (s == "draw0") { src = m->draw0; n = M0 * m->C0; }
+    else if (s == "logits") { src = m->logits; n = (size_t)(m->L - 1) * B * m->Vp; }
+    else if (s == "ht") { src = m->ht; n = (size_t)(m->L - 1) * B * m->A; }
+    else if (s == "row_loss") { src = m->row_loss; n = (size_t)(m->L - 1) * B; }
+    else if (s == "W1p") { src = m->W1p; n = (size_t)m->C1 * m->K1; }
+    else if (s.size() == 4 && (s[0] == 'G' || s[0] == 'H' || s[0] == 'C' || s[0] == 'O') && s[1] == '_') {
+        const int l = s[2] - '0', d = s[3] - '0';
+        AST_CHECK(l >= 0 && l < m->NL && d >= 0 && d < 2, "debug_fetch: bad layer/dir in %s", name);
+        if (s[0] == 'G') { src = m->Genc[l][d]; n = TB * 4 * h; }
+        else if (s[0] == 'H') { src = m->Hs[l][d]; n = (TB + B) * h; }
+        else if (s[0] == 'C') { src = m->Cs[l][d]; n = (TB + B) * h; }
+        else { src = m->Hd[l][d]; n = TB * h; }
+    }
+    AST_CHECK(src != nullptr, "debug_fetch: unknown buffer '%s'", name);
+    if (n_out) *n_out = (long long)n;
+    if (out) {
+        AST_CHECK((long long)n <= max_floats, "debug_fetch: buffer '%s' has %zu floats, room for %lld", name, n, max_floats);
+        AST_CUDA_OK(cudaMemcpyAsync(out, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, S_(stream)));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+"""Drop-in for the reference runtime nn.py::NN (model build + resume, optimizer + hooks, train_epoch,
+greedy predict, beam search) over the CUDA engine.  Same attributes and method names as
+/root/reference/nn.py so train.py / beam.py / copy_params.py keep working.
+"""
+import contextlib
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import serializers
+from .config import Config
+from .dataloader import FisherDataLoader, GlobalPhoneDataLoader
+from .seq2seq import SpeechEncoderDecoder, Variable, config as _train_config
+from .symbols import SYMBOLS
+
+_ADAM = 0
+_SGD = 1
+
+
+@contextlib.contextmanager
+def using_config(name, value):
+    """chainer.using_config('train', flag) stand-in (nn.py:174,216)."""
+    assert name == "train"
+    old = _train_config.train
+    _train_config.train = value
+    try:
+        yield
+    finally:
+        _train_config.train = old
+
+
+# ---- optimizer + hooks (nn.py:81-119; Appendix A.10) --------------------------------------------------
+class WeightDecay:
+    name = "WeightDecay"
+
+    def __init__(self, rate):
+        self.rate = rate
+
+
+class GradientClipping:
+    name = "GradientClipping"
+
+    def __init__(self, threshold):
+        self.threshold = threshold
+
+
+class GradientNoise:
+    name = "GradientNoise"
+
+    def __init__(self, eta):
+        self.eta = eta
+
+
+class Adam:
+    """optimizers.Adam(alpha, beta1, beta2, eps, amsgrad=True) as one fused multi-tensor kernel over the
+    flat parameter buffer: WeightDecay -> GradientClipping (global L2 norm, computed on device, no host
+    sync) -> AMSGrad.  ``grad_scale`` is 1/world_size under data parallelism."""
+
+    def __init__(self, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, amsgrad=True):
+        if not amsgrad:
+            raise NotImplementedError("the reference always sets amsgrad=True (nn.py:89)")
+        self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
+        self.t = 0
+        self.l2 = 0.0
+        self.clip = 0.0
+        self.grad_scale = 1.0
+        self.target = None
+        self._m = self._v = self._vhat = None
+        self.pre_update = None        # e.g. the data-parallel all-reduce
+
+    def setup(self, model):
+        self.target = model
+        return self
+
+    def add_hook(self, hook):
+        if isinstance(hook, WeightDecay):
+            self.l2 = hook.rate
+        elif isinstance(hook, GradientClipping):
+            self.clip = float(hook.threshold)
+        elif isinstance(hook, GradientNoise):
+            raise NotImplementedError("GradientNoise (grad_noise_eta > 0) is not supported; 0 in every shipped config")
+        else:
+            raise TypeError(f"unknown hook {hook!r}")
+
+    def _state(self, e):
+        if self._m is None:
+            self._m = torch.zeros_like(e.params)
+            self._v = torch.zeros_like(e.params)
+            self._vhat = torch.zeros_like(e.params)
+
+    def frozen(self):
+        out = []
+        for name, link in self.target._links.items():
+            if not link.update_enabled:
+                out += link.param_keys()
+        return out
+
+    def update(self):
+        e = self.target._require()
+        self._state(e)
+        if self.pre_update is not None:
+            self.pre_update()
+        self.t += 1
+        e.opt_step(self._m, self._v, self._vhat, self.t, self.alpha, self.l2, self.clip, self.beta1, self.beta2, self.eps,
+                   self.grad_scale, self.frozen())
+
+
+class SGD:
+    def __init__(self, lr=0.01):
+        raise NotImplementedError("optimizer.type=1 (SGD) is outside the hot path; every shipped config uses Adam (type 0)")
+
+
+def beam_result_to_entries(r, go_id=SYMBOLS.GO_ID, model=None):
+    """Device beam-search buffers -> the reference's list of hypothesis dicts (nn.py:286-294)."""
+    ns, nh = r["n_steps"], r["n_hyps"]
+    hp = r["hist_parent"][:ns].cpu().numpy()
+    hk = r["hist_tok"][:ns].cpu().numpy()
+    ah = r["alpha_hist"][:ns].cpu().numpy()
+    sc = r["scores"].cpu().numpy()
+    out = []
+    for j in range(nh):
+        toks, als = [], []
+        slot = j
+        for s in range(ns - 1, -1, -1):
+            if hk[s, slot] >= 0:
+                toks.append(int(hk[s, slot]))
+                als.append(ah[s, slot].copy())
+            slot = int(hp[s, slot])
+        st = r["states"][:, :, j:j + 1, :]
+        out.append({"hyp": [go_id] + toks[::-1], "score": np.float32(sc[j]) if ns > 0 else 0,
+                    "dec_state": {"c": [Variable(st[l, 0]) for l in range(st.shape[0])],
+                                  "h": [Variable(st[l, 1]) for l in range(st.shape[0])]},
+                    "attn_v": Variable(r["attn_v"][j:j + 1]),
+                    "attn_history": als[::-1]})
+    return out
+
+
+class NN:
+    def __init__(self, cfg_path, feat_dim=None, data_loader=None, cfg=None):
+        """nn.py:43-79.  ``feat_dim`` / ``data_loader`` / ``cfg`` are optional injection points (synthetic
+        benchmarks, tests); with only ``cfg_path`` this behaves like the reference."""
+        self.cfg = cfg if cfg is not None else Config(cfg_path)
+        self.model_dir = self.cfg.model["model_dir"]
+        self.gpuid = self.cfg.train["gpuid"]
+        random.seed(self.cfg.train["seed"])
+        if data_loader is not None:
+            self.data_loader = data_loader
+        elif self.cfg.train["data"].get("dataloader") == "globalphone":
+            self.data_loader = GlobalPhoneDataLoader(self.cfg.train["data"], self.model_dir, self.gpuid)
+        else:
+            self.data_loader = FisherDataLoader(self.cfg.train["data"], self.model_dir, self.gpuid)
+        if feat_dim is None:
+            feat_dim = getattr(self.data_loader, "feat_dim", None)
+        self._feat_dim = feat_dim
+        self.get_model()
+        self.init_optimizer(self.cfg.train["optimizer"])
+        self.train_log = os.path.join(self.model_dir, "train.log")
+        self.dev_log = os.path.join(self.model_dir, "dev.log")
+
+    def init_optimizer(self, opt_cfg):
+        """nn.py:81-119"""
+        if opt_cfg["type"] == _ADAM:
+            self.optimizer = Adam(alpha=opt_cfg["lr"], beta1=0.9, beta2=0.999, eps=1e-08, amsgrad=True)
+        else:
+            self.optimizer = SGD(lr=opt_cfg["lr"])
+        self.optimizer.setup(self.model)
+        if opt_cfg["l2"] > 0:
+            self.optimizer.add_hook(WeightDecay(opt_cfg["l2"]))
+        self.optimizer.add_hook(GradientClipping(threshold=opt_cfg["grad_clip"]))
+        if opt_cfg["grad_noise_eta"] > 0:
+            self.optimizer.add_hook(GradientNoise(eta=opt_cfg["grad_noise_eta"]))
+        for l in opt_cfg["freeze"]:
+            if l in self.model.__dict__:
+                print("freezing: {0:s}".format(l))
+                self.model[l].disable_update()
+            else:
+                print("layer {0:s} not in model".format(l))
+
+    def get_model(self):
+        """nn.py:122-155: build, then resume from the newest seq2seq_<N>.model in the model dir."""
+        self.model_fname = os.path.join(self.model_dir, "seq2seq.model")
+        self.model = SpeechEncoderDecoder(self.gpuid, self.cfg.model, feat_dim=self._feat_dim)
+        self.model.to_gpu(self.gpuid)
+        self.max_epoch = 0
+        model_fil = self.model_fname
+        d = os.path.dirname(model_fil)
+        stem = os.path.basename(model_fil).replace(".model", "")
+        model_files = [f for f in os.listdir(d) if stem in f] if os.path.isdir(d) else []
+        if len(model_files) > 0:
+            max_model_fil = max(model_files, key=lambda s: int(s.split("_")[-1].split(".")[0]))
+            max_model_fil = os.path.join(d, max_model_fil)
+            print("model found = \n{0:s}".format(max_model_fil))
+            serializers.load_npz(max_model_fil, self.model)
+            self.max_epoch = int(max_model_fil.split("_")[-1].split(".")[0])
+        else:
+            print("model not found")
+
+    def train_epoch(self, set_key, max_batches=None):
+        """nn.py:158-200.  The per-batch loss read-back is one step late (pinned, asynchronous) so the
+        training loop never blocks on the device; the returned average is the same quantity."""
+        total_loss, n_batches = 0.0, 0
+        batch_size = self.cfg.train["batch_size"]
+        random_out = self.cfg.train["extras"]["random_out"]
+        add_noise = self.cfg.train["extras"]["speech_noise"]
+        teach_ratio = self.cfg.train["extras"]["teach_ratio"]
+        pending = []
+        for batch in self.data_loader.get_batch(batch_size, set_key, train=True, labels=True):
+            with using_config("train", True):
+                loss = self.model.forward_loss(X=batch["X"], y=batch["y"], teach_ratio=teach_ratio, random_out=random_out,
+                                               add_noise=add_noise)
+                self.model.cleargrads()
+                loss.backward()
+                self.optimizer.update()
+            pending.append((loss.data, len(batch["y"])))
+            n_batches += 1
+            if len(pending) > 1:
+                l, n = pending.pop(0)
+                total_loss += float(l) / n
+            if max_batches is not None and n_batches >= max_batches:
+                break
+        for l, n in pending:
+            total_loss += float(l) / n
+        return total_loss / max(n_batches, 1)
+
+    def predict(self, set_key):
+        """nn.py:202-233"""
+        batch_size = self.cfg.train["batch_size"]
+        stop_limit = self.cfg.train["data"]["max_pred"]
+        preds = []
+        for batch in self.data_loader.get_batch(batch_size, set_key, train=False, labels=False):
+            with using_config("train", False):
+                p = self.model.predict(batch["X"], SYMBOLS.GO_ID, SYMBOLS.EOS_ID, stop_limit)
+                preds.extend(zip(batch["utts"], p.tolist()))
+        return preds
+
+    def init_hyp(self):
+        """nn.py:235-243"""
+        e = self.model._engine
+        return {"hyp": [SYMBOLS.GO_ID], "score": 0, "dec_state": self.model.get_encoder_states(),
+                "attn_v": Variable(torch.zeros(1, e.A, device=e.device)), "attn_history": []}
+
+    def decode_beam_step(self, decode_entry, beam_width):
+        """nn.py:245-297, one hypothesis through the public decode_step protocol (host-driven; the
+        production path is decode_beam below, which keeps the whole search on the device)."""
+        with using_config("train", False):
+            self.model.set_decoder_states(decode_entry["dec_state"])
+            e = self.model._engine
+            word = torch.full((1,), int(decode_entry["hyp"][-1]), dtype=torch.int32, device=e.device)
+            pred_out, ht, alphas = self.model.decode_step(word, decode_entry["attn_v"])
+            z = pred_out.data[0]
+            m = z.max()
+            lp = (z - (m + torch.log(torch.exp(z - m).sum()))).cpu().numpy()
+            top = np.argsort(lp, kind="stable")[-beam_width:]
+            st = self.model.get_decoder_states()
+            out = []
+            for pi in top[::-1]:
+                out.append({"hyp": decode_entry["hyp"] + [int(pi)],
+                            "score": np.float32(np.float32(decode_entry["score"]) + lp[pi]),
+                            "dec_state": st, "attn_v": ht,
+                            "attn_history": decode_entry["attn_history"] + [alphas.data[0, :, 0].cpu().numpy()]})
+            return out
+
+    def decode_beam(self, X, stop_limit, N, K):
+        """nn.py:299-322 with the search loop, top-K, pruning and state gather on the device."""
+        X = X.data if isinstance(X, Variable) else X
+        with using_config("train", False):
+            e = self.model._require(X)
+            r = e.beam_search(X, int(stop_limit), int(N), int(K), SYMBOLS.GO_ID, SYMBOLS.EOS_ID)
+            self.model.enc_states = None
+            if r["n_steps"] == 0:
+                return [self.init_hyp()]
+            return beam_result_to_entries(r, SYMBOLS.GO_ID)

@@ -1,0 +1,132 @@
+/* ast_b200 — C ABI of the B200-native hot path of 0xSameer/ast.
+ *
+ * The reference has no FFI layer (pure Python on Chainer/CuPy); its boundary is the
+ * Python object protocol between nn.py / beam.py and seq2seq.py::SpeechEncoderDecoder.  Each entry
+ * point below names the reference interface it replaces (file:line under /root/reference).  The
+ * Python drop-in (ast_b200/seq2seq.py, ast_b200/nn.py) binds these through ctypes; INTEGRATION.md
+ * shows the stub.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (ast_last_error() gives the text);
+ * nothing throws across the ABI.  All tensors are caller-owned DEVICE pointers, fp32 row-major unless
+ * noted; `stream` is a cudaStream_t passed as void*.  No hidden allocation: parameters, gradients,
+ * optimizer moments and the workspace are caller-owned buffers whose sizes are queried first.
+ * One ast_model per (device, stream); not thread-safe.
+ */
+#ifndef AST_B200_H
+#define AST_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ast_model ast_model;
+
+/* model_cfg.json (+ config.py:25 dec_vocab_size) flattened; seq2seq.py:23-156 */
+typedef struct ast_config {
+    int feat_dim;                 /* D: 13 (shipped MFCC configs) or 40 (fbank) */
+    int cnn_cout[2], cnn_kh[2], cnn_kw[2], cnn_sh[2], cnn_sw[2], cnn_ph[2], cnn_pw[2];
+    int enc_layers, dec_layers;
+    int hidden_units, embedding_units, attn_units, vocab;
+    float drop_embed, drop_rnn, drop_out;
+} ast_config;
+
+const char* ast_last_error(void);
+int ast_abi_version(void);
+
+/* SpeechEncoderDecoder.__init__ (seq2seq.py:23-33); to_gpu (nn.py:133) is the `device` argument. */
+int ast_create(const ast_config* cfg, int device, ast_model** out);
+int ast_destroy(ast_model* m);
+
+/* Flat parameter buffer layout.  Tensors keep chainer's shapes and serializer names (Appendix A.9:
+ * "CNN_0/W", "L0_enc/upward/W", ...), each starting at a 256-byte aligned offset.  Used by
+ * serializers.load_npz/save_npz (nn.py:150, train.py:75) and copy_params.py:26-43. */
+long long ast_param_floats(const ast_model* m);
+int ast_param_count(const ast_model* m);
+int ast_param_info(const ast_model* m, int idx, char* name, int name_cap, long long* offset, int* ndim, int* shape4);
+/* params/grads: ast_param_floats() floats each; bn_state: per CNN layer avg_mean[C] then avg_var[C]. */
+int ast_bn_state_floats(const ast_model* m);
+int ast_bind_params(ast_model* m, float* params, float* grads, float* bn_state);
+/* Must be called after params change outside ast_opt_step (init, load_npz, copy_params). */
+int ast_weights_changed(ast_model* m);
+
+/* Workspace for batches up to (B, T frames, L target tokens) and beam width N. */
+long long ast_workspace_bytes(const ast_model* m, int B, int T, int L, int beam_n, int max_steps);
+int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, int L, int beam_n, int max_steps);
+
+/* options: "exact" (1: fp32-faithful 3xTF32 / fp32 FMA everywhere, 0: single-pass TF32 tensor cores),
+ *          "seed" (dropout / noise RNG), "tc_gemm" (1: tcgen05 GEMM for the batched contractions). */
+int ast_set_option(ast_model* m, const char* key, double value);
+double ast_get_option(const ast_model* m, const char* key);
+
+/* encode (seq2seq.py:293-315): X (B,T,D).  train!=0: BN batch statistics + running-stat update,
+ * dropout and optional multiplicative input noise (explicit tensor or N(1,sigma) generated on device).
+ * Sets the model's enc_states (B,T',H) and the encoder link states. */
+int ast_encode(ast_model* m, const float* X, int B, int T, int train, const float* noise, float noise_sigma,
+               void* stream);
+int ast_enc_len(const ast_model* m, int T);                      /* T' for T input frames */
+int ast_get_enc_states(ast_model* m, float* out, void* stream); /* (B,T',H) */
+
+/* forward_loss (seq2seq.py:399-473; nn.py:175-179): y (B,L) int32, use_true (L-1 bytes, device, may be
+ * NULL = teach_ratio 1: the host's random.random() draws of :431-436), loss_out: 1 float (device).
+ * Also init_decoder_state (:318-334), decode_step x (L-1) and the PAD-weighted softmax-CE (:468). */
+int ast_forward_loss(ast_model* m, const float* X, const int* y, int B, int T, int L,
+                     const unsigned char* use_true, const float* noise, float noise_sigma, float* loss_out,
+                     void* stream);
+/* loss.backward() (nn.py:181) after cleargrads (:180): fills the bound grads buffer. */
+int ast_backward(ast_model* m, void* stream);
+/* per-step argmax tokens of the last forward_loss: (L-1, B) int32 */
+int ast_get_step_argmax(ast_model* m, int* out, void* stream);
+
+/* optimizer.update() (nn.py:81-119,182): WeightDecay -> GradientClipping(global L2) -> AMSGrad.
+ * moments m1,v,vhat: ast_param_floats() floats each; grad_scale multiplies grads first (1/world_size
+ * after a data-parallel sum all-reduce); t = 1-based update count; frozen tensors by index list. */
+int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr, float l2, float clip,
+                 float beta1, float beta2, float eps, float grad_scale, const int* frozen_idx, int n_frozen,
+                 void* stream);
+double ast_last_grad_norm(ast_model* m, void* stream);   /* synchronises; for logging / tests */
+
+/* decode_step / get|set_decoder_states / get_encoder_states (seq2seq.py:361-396, 529-569; nn.py:238-274).
+ * Decoder state lives in the model: per layer c (Bd,H) and h (Bd,H).  states layout: [layer][c|h][Bd][H]. */
+int ast_init_decoder_state(ast_model* m, int Bd, void* stream);     /* from encoder finals; Bd = B, or broadcast */
+int ast_get_encoder_states(ast_model* m, float* states, void* stream);
+int ast_get_decoder_states(ast_model* m, float* states, int Bd, void* stream);
+int ast_set_decoder_states(ast_model* m, const float* states, int Bd, void* stream);
+/* word (Bd) int32, ht_in (Bd,A) -> logits (Bd,V), ht_out (Bd,A), alphas (Bd,T'). Eval mode. */
+int ast_decode_step(ast_model* m, const int* word, const float* ht_in, int Bd, float* logits, float* ht_out,
+                    float* alphas, void* stream);
+
+/* predict (seq2seq.py:475-527; nn.py:217-220): greedy batched decode; preds (stop_limit,B) int32 device,
+ * n_steps (host) = rows actually produced (not cut at EOS per row, as the reference). */
+int ast_predict(ast_model* m, const float* X, int B, int T, int start_token, int end_token, int stop_limit,
+                int* preds, int* n_steps, void* stream);
+
+/* decode_beam (nn.py:235-322; beam.py:117): one utterance X (1,T,D), N kept hyps, K expansions each.
+ * Outputs (host pointers): n_steps, n_hyps; device outputs: hist_parent/hist_tok (stop_limit,N) int32,
+ * scores (N) f32, alpha_hist (stop_limit,N,T') f32 (may be NULL), final states (see get_decoder_states)
+ * and attn_v (N,A) (may be NULL). */
+int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, int K, int go_token, int eos_token,
+                    int* n_steps, int* n_hyps, int* hist_parent, int* hist_tok, float* scores, float* alpha_hist,
+                    float* final_states, float* final_attn_v, void* stream);
+
+/* ---- stateless kernels (unit-testable pieces; also what a foreign host would call directly) ---- */
+/* Kaldi apply-cmvn + dataloader.py:103,156 pad_sequence (+ :83-93 frame zeroing, seq2seq.py:300 noise) */
+int ast_pack_cmvn(const float* raw, const long long* row_off, const int* lens, const float* scale,
+                  const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
+                  unsigned long long seed, float* X, int B, int T, int D, void* stream);
+/* F.softmax_cross_entropy(class_weight=mask_pad_id) fwd+bwd+argmax (seq2seq.py:448,468) */
+int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V, float* row_loss, int* argmax,
+                   void* stream);
+/* C = alpha*op(A)op(B) + beta*C + bias ; which: 0 = fp32 SIMT, 1 = tcgen05 TF32 (NT only) */
+int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+             int ldb, float beta, float* C, int ldc, const float* bias, void* stream);
+/* persistent LSTM recurrence over a sequence, one chain (kernel-level test hook) */
+int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, float* out_or_dout, int T, int B, int h,
+                 const float* dh_fin, const float* dc_fin, int exact, void* stream);
+
+/* test hook: copy a named internal buffer ("raw0", "rnn_in", "G_00", "H_21", "d_enc", ...) */
+int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_floats, long long* n_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AST_B200_H */
