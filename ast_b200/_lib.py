@@ -32,6 +32,7 @@ _ULL = C.c_ulonglong
 SIGNATURES = {
     "ast_last_error": (C.c_char_p, []),
     "ast_abi_version": (_I, []),
+    "ast_launch_count": (_ULL, [_I]),
     "ast_create": (_I, [C.POINTER(AstConfig), _I, C.POINTER(_P)]),
     "ast_destroy": (_I, [_P]),
     "ast_param_floats": (_LL, [_P]),

@@ -18,3 +18,15 @@ class Config:
         self.model["rnn_config"]["dec_vocab_size"] = vocab_size
         print("vocab size {0:s} = {1:d}".format(self.train["data"]["dec_key"], vocab_size))
         self.model["model_dir"] = cfg_path
+
+
+def es_en_20h_model_cfg(vocab=1098, dropout=(0.3, 0.3, 0.0)):
+    """The shipped experiments/es_en_20h/model_cfg.json as a dict (+ injected dec_vocab_size)."""
+    return {
+        "dropout": {"embed": dropout[0], "rnn": dropout[1], "out": dropout[2]},
+        "rnn_config": {"bi_rnn": True, "enc_layers": 3, "dec_layers": 3, "hidden_units": 512, "embedding_units": 128,
+                       "attn_units": 512, "n_attn": 1, "feed_attn": True, "ln": False, "dec_vocab_size": vocab},
+        "cnn_config": {"bn": True, "cnn_layers": [
+            {"in_channels": None, "out_channels": 128, "ksize": [9, 13], "stride": [2, 13], "pad": [4, 0]},
+            {"in_channels": None, "out_channels": 512, "ksize": [9, 1], "stride": [2, 1], "pad": [4, 0]}]},
+    }

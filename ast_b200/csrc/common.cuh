@@ -9,6 +9,7 @@ namespace ast {
 // ---- error plumbing (never throw across the C ABI) ------------------------------------
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
+extern unsigned long long g_kernel_launches;   // every kernel this library enqueues (bench.py gpu_launches)
 
 #define AST_CUDA_OK(expr)                                                                   \
     do {                                                                                    \
@@ -22,6 +23,7 @@ const char* get_last_error();
 
 #define AST_LAUNCH_OK()                                                                     \
     do {                                                                                    \
+        ++ast::g_kernel_launches;                                                           \
         cudaError_t _e = cudaGetLastError();                                                \
         if (_e != cudaSuccess) {                                                            \
             ast::set_last_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,           \

@@ -300,6 +300,7 @@ static int launch_cluster(KernT kern, cudaStream_t st, int nchains, size_t smem,
     at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ch, T, B, h, drop, seed));
+    ++g_kernel_launches;
     return 0;
 }
 

@@ -17,6 +17,7 @@ void set_last_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+unsigned long long g_kernel_launches = 0;
 
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
@@ -609,6 +610,11 @@ extern "C" {
 
 const char* ast_last_error(void) { return ast::get_last_error(); }
 int ast_abi_version(void) { return 1; }
+unsigned long long ast_launch_count(int reset) {
+    const unsigned long long v = ast::g_kernel_launches;
+    if (reset) ast::g_kernel_launches = 0;
+    return v;
+}
 
 int ast_create(const ast_config* cfg, int device, ast_model** out) {
     AST_CHECK(cfg && out, "ast_create: null argument");

@@ -1,0 +1,101 @@
+"""Data-parallel training over the 8 B200s of one box: one process per GPU, full replica per
+rank, disjoint slice of every global batch, one NCCL sum all-reduce of the flat gradient buffer
+(14.4 M fp32 = 57.7 MB, ~0.2 ms over NVLink 5 / NVSwitch) folded into the optimizer as
+``grad_scale = 1/world_size``; WeightDecay -> global-norm clip -> AMSGrad then run identically on every
+rank, the clip norm being that of the REDUCED gradient.  BatchNorm statistics stay per replica (the
+reference has no DP; parity is defined per replica).
+
+The reference has no collective anywhere; this is new work required by BASELINE config 4.
+The host-side logic (sharding, bucket order, reduction arithmetic) is backend-agnostic and is covered by
+world_size-2 gloo tests on CPU.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init_process_group(backend=None):
+    """Join the job described by RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun)."""
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def shard_utterances(utts, rank, world):
+    """Rank r takes utterances r::G of a global batch: every rank sees the same bucket, so the
+    padded lengths - and step times - stay balanced."""
+    return list(utts[rank::world])
+
+
+def shard_batch_plan(batches, rank, world):
+    """Global batch plan [(utts, width)] built with batch_size*world -> this rank's plan.  All ranks must
+    have seeded Python's `random` identically so the plans agree (nn.py:54)."""
+    out = []
+    for utts, width in batches:
+        mine = shard_utterances(utts, rank, world)
+        if len(mine) == 0:           # tail batch smaller than the world: every rank still needs a step
+            mine = [utts[rank % len(utts)]]
+        out.append((mine, width))
+    return out
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place sum all-reduce of a flat fp32 tensor (gradient bucket)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+class GradAllReduce:
+    """optimizer.pre_update hook: all-reduce the flat gradient buffer, optionally on a side stream and in
+    buckets ordered decoder -> attention -> encoder -> CNN so communication of finished buckets overlaps
+    the rest of backward (the buffer is contiguous, buckets are views)."""
+
+    def __init__(self, engine, optimizer, world, n_buckets=1):
+        self.e, self.opt, self.world, self.n_buckets = engine, optimizer, world, max(1, n_buckets)
+        optimizer.grad_scale = 1.0 / world
+        optimizer.pre_update = self
+
+    def __call__(self):
+        if self.world <= 1:
+            return
+        g = self.e.grads
+        n = g.numel()
+        step = (n + self.n_buckets - 1) // self.n_buckets
+        for i in range(self.n_buckets):
+            allreduce_sum_(g[i * step:min(n, (i + 1) * step)])
+
+
+def broadcast_params_(engine, src=0):
+    """Make every replica start from rank `src`'s parameters and BN running statistics."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(engine.params, src)
+        dist.broadcast(engine.bn_state, src)
+        engine.weights_changed()
+
+
+def max_over_ranks(value, device):
+    """Timing rule: every multi-GPU number is the max over ranks."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device):
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -161,7 +161,10 @@ class Engine:
         self.ensure_workspace(B=B, T=T, L=L)
         ut = None
         if use_true is not None:
-            ut = torch.as_tensor(np.asarray(use_true, dtype=np.uint8), device=self.device)
+            if isinstance(use_true, torch.Tensor):
+                ut = use_true.to(device=self.device, dtype=torch.uint8).contiguous()
+            else:
+                ut = torch.as_tensor(np.asarray(use_true, dtype=np.uint8), device=self.device)
             assert ut.numel() == L - 1
         nz = self._as_f32(noise) if noise is not None else None
         loss = torch.empty(1, dtype=torch.float32, device=self.device)

@@ -22,6 +22,12 @@ class _Config:
 config = _Config()
 
 
+def draw_use_true(L, teach_ratio):
+    """Scheduled-sampling bits for L-1 decode steps with the reference's exact random.random() call
+    order (seq2seq.py:431-436): one draw for each 1 <= i <= L-3, steps 0 and >= L-2 always teacher-forced."""
+    return [True if not (0 < i < L - 2) else (random.random() < teach_ratio) for i in range(L - 1)]
+
+
 class Variable:
     """Minimal chainer.Variable stand-in: ``.data`` is a torch CUDA tensor."""
 
@@ -350,7 +356,7 @@ class SpeechEncoderDecoder:
         e = self._require(X)
         L = int(y.shape[1])
         if use_true is None:
-            use_true = [True if not (0 < i < L - 2) else (random.random() < teach_ratio) for i in range(L - 1)]
+            use_true = draw_use_true(L, teach_ratio)
         loss = e.forward_loss(X, y, use_true=use_true, noise_sigma=float(add_noise) if add_noise else 0.0)
         self.loss = Variable(loss.reshape(()), backward_fn=e.backward)
         return self.loss

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: es_en_20h-shaped training steps (fwd + bwd + optimizer) over bucketed,
+Fisher-shaped synthetic batches -> train input frames / second (BASELINE.json metric, configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU
+                                                             # (numpy oracle; real Chainer is not installable)
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each field means.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, V, BATCH = 40, 1098, 32
+TRAIN_EXTRAS = {"random_out": 0, "speech_noise": 0.25, "teach_ratio": 0.8}
+DATA_CFG = {"buckets_num": 20, "buckets_width": 80, "train_scale": 1, "max_pred": 175, "zero_input": 0.1,
+            "dec_key": "bpe_w", "enc_key": "sp"}
+OPT_CFG = {"type": 0, "lr": 0.001, "l2": 0.0001, "grad_clip": 2, "grad_noise_eta": 0, "freeze": []}
+DROPOUT = (0.3, 0.3, 0.0)          # experiments/es_en_20h/model_cfg.json
+SET = "fisher_train"
+
+
+def model_cfg():
+    from ast_b200.config import es_en_20h_model_cfg
+    return es_en_20h_model_cfg(vocab=V, dropout=DROPOUT)
+
+
+def make_plan(world, n_batches, seed=1234):
+    """Global batch plan of the synthetic epoch (same on every rank and for both impls)."""
+    from ast_b200.dataloader import SyntheticDataLoader, plan_batches
+    random.seed("seed-ast-20h")                          # train_cfg.json seed, nn.py:54
+    np.random.seed(seed)
+    loader = SyntheticDataLoader.fisher_shaped(DATA_CFG, None, 0, D, V, n_utts=17306 * max(1, world), seed=seed, set_key=SET)
+    plan = plan_batches(loader.buckets[SET], BATCH * world)
+    plan = [p for p in plan if len(p[0]) == BATCH * world][:n_batches]
+    return loader, plan
+
+
+def host_batch(loader, utts):
+    """Host-side batch exactly as the loader would build it (features, keep masks, labels)."""
+    from ast_b200.dataloader import drop_frame_mask
+    max_sp = (DATA_CFG["buckets_num"] + 1) * DATA_CFG["buckets_width"]
+    feats = [loader._load_utt(u, SET)[:max_sp] for u in utts]
+    keep = [drop_frame_mask(len(f), DATA_CFG["zero_input"]) for f in feats]
+    ys = [np.asarray([1] + loader._labels(u, SET)[:DATA_CFG["max_pred"] - 2] + [2], dtype=np.int32) for u in utts]
+    L = max(len(v) for v in ys)
+    y = np.zeros((len(ys), L), dtype=np.int32)
+    for i, v in enumerate(ys):
+        y[i, :len(v)] = v
+    frames = int(sum(len(f) for f in feats))
+    return feats, keep, y, frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        mx = [float(r[2]) for r in rows if len(r) >= 9]
+        reasons = set()
+        for r in rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], j["bf16_tflops"], j.get("bf16_tflops_sustained", j["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (numpy oracle, OpenBLAS on all cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_rate(loader, plan, n_steps, budget_s=25.0):
+    """frames/s of fwd+bwd+update for up to n_steps batches (bounded by budget_s of CPU work)."""
+    from oracle import ast_oracle as O
+    cfg = model_cfg()
+    cfg["dropout"] = {"embed": 0.0, "rnn": 0.0, "out": 0.0}     # mask multiplies are a rounding error of the CPU time
+    P = O.init_params(cfg, D, seed=0)
+    om = O.OracleModel(cfg, P, dtype=np.float32)
+    opt = O.OracleAMSGrad(om.p, lr=OPT_CFG["lr"], l2=OPT_CFG["l2"], grad_clip=OPT_CFG["grad_clip"])
+    frames, t_total, done = 0, 0.0, 0
+    desc = []
+    for utts, _ in plan[:n_steps]:
+        feats, keep, y, fr = host_batch(loader, utts[:BATCH])
+        X = O.pad_sequence([f * k[:, None] for f, k in zip(feats, keep)], 0)
+        bits = O.teacher_forcing_bits(y.shape[1], TRAIN_EXTRAS["teach_ratio"])
+        t0 = time.perf_counter()
+        om.forward_loss(X, y, tf_bits=bits)
+        g = om.backward()
+        opt.update(om.p, g)
+        t_total += time.perf_counter() - t0
+        frames += fr
+        done += 1
+        desc.append(f"B{X.shape[0]}xT{X.shape[1]}xL{y.shape[1]}")
+        if t_total > budget_s:
+            break
+    return frames / t_total, done, t_total, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    loader, plan = make_plan(1, max(args.steps + args.warmup, 2))
+    rate, done, t_total, desc = cpu_step_rate(loader, plan[args.warmup:], args.steps, budget_s=150.0)
+    line = {"impl": "reference", "metric": "train_frames_per_sec", "value": rate, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": done, "warmup": 0, "ms_per_step": 1e3 * t_total / max(done, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "es_en_20h bucketed training steps (B=32, Fisher-shaped lengths, D=40, V=1098): fwd+bwd+AMSGrad",
+                       "steps_run": desc},
+            "cpu_baseline": {"value": rate, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{done} training steps of the same batch plan; numpy restatement of the reference "
+                                       "(real Chainer/CuPy is not installable), OpenBLAS on all host cores"},
+            "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def roofline_dominant(engine, torch, peaks):
+    """Time the dominant kernel of the step in isolation at its workload shape with CUDA events and
+    report achieved / measured peak.  Dominant kernel: see profiles/ (ncu launch list)."""
+    import ctypes as C
+    from ast_b200._lib import ptr, check
+    hbm, tf_burst, tf_sus, how = peaks
+    lib = engine.lib
+    dev = engine.device
+    # L0 encoder input projection of a median batch: (T'*B x R) . (4h x R)^T, R = 1536, 4h = 1024
+    Tp, B, R, N = 100, BATCH, 1536, 1024
+    M = Tp * B
+    A = torch.randn(M, R, device=dev); W = torch.randn(N, R, device=dev); Cc = torch.empty(M, N, device=dev)
+    bias = torch.randn(N, device=dev)
+    which = 1 if engine.get_option("tc_gemm") and not engine.get_option("exact") else 0
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.ast_gemm(which, 0, 1, M, N, R, 1.0, ptr(A), R, ptr(W), R, 0.0, ptr(Cc), N, ptr(bias), st), "ast_gemm")
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    flops = 2.0 * M * N * R
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = tf_burst / 2.0 if which == 1 else tf_burst / 2.0      # TF32 dense = 1/2 of the measured bf16 figure
+    return {"bound": "tensor", "kernel": "gemm_tc_nt (tcgen05 TF32)" if which == 1 else "sgemm_kernel (fp32 SIMT)",
+            "shape": f"M{M} N{N} K{R}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms, "traffic": None}
+
+
+def run_ours(args):
+    import torch
+    from ast_b200 import dist as adist
+    from ast_b200 import _lib
+    from ast_b200.dataloader import DevicePacker
+    from ast_b200.nn import Adam, GradientClipping, WeightDecay
+    from ast_b200.seq2seq import SpeechEncoderDecoder, config as train_config, draw_use_true
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    rank, local_rank, world = adist.init_process_group()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    K, W = args.steps, max(args.warmup, 3)
+    loader, gplan = make_plan(world, K + W)
+    plan = adist.shard_batch_plan(gplan, rank, world)
+    cfg = model_cfg()
+    model = SpeechEncoderDecoder(local_rank, cfg, feat_dim=D)
+    model._seed = 0
+    model.init_params(seed=0)
+    e = model._engine
+    e.set_option("exact", 0 if args.precision == "tf32" else 1)
+    e.set_option("tc_gemm", 1 if args.precision == "tf32" else 0)
+    adist.broadcast_params_(e)
+    opt = Adam(alpha=OPT_CFG["lr"]).setup(model)
+    opt.add_hook(WeightDecay(OPT_CFG["l2"]))
+    opt.add_hook(GradientClipping(OPT_CFG["grad_clip"]))
+    adist.GradAllReduce(e, opt, world)
+    packer = DevicePacker(dev)
+    train_config.train = True
+    lib = _lib.load()
+
+    # ---- host batches (features, masks, labels, scheduled-sampling bits) -----------------------------
+    random.seed(1000 + rank)
+    host = []
+    for utts, _ in plan:
+        feats, keep, y, frames = host_batch(loader, utts)
+        bits = np.asarray(draw_use_true(y.shape[1], TRAIN_EXTRAS["teach_ratio"]), dtype=np.uint8)
+        host.append((feats, keep, y, bits, frames))
+    max_sp = (DATA_CFG["buckets_num"] + 1) * DATA_CFG["buckets_width"]
+
+    def step_resident(Xd, yd, bits):
+        loss = e.forward_loss(Xd, yd, use_true=bits, noise_sigma=TRAIN_EXTRAS["speech_noise"])
+        e.backward()
+        opt.update()
+        return loss
+
+    # ---- (1) device-resident: inputs already in HBM when the timed region starts --------------------
+    resident = [(packer.pack(f, max_sp, k), torch.from_numpy(y).to(dev), torch.from_numpy(bits).to(dev), fr) for f, k, y, bits, fr in host]
+    maxT = max(x[0].shape[1] for x in resident); maxL = max(x[1].shape[1] for x in resident)
+    e.ensure_workspace(B=BATCH, T=maxT, L=maxL, N=16, steps=1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    for i in range(W):
+        step_resident(*resident[i][:3])
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.ast_launch_count(1)
+    evs = []
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(W, W + K):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident(*resident[i][:3])
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = int(lib.ast_launch_count(0))
+    if world > 1:
+        torch.distributed.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_dev = sum(a.elapsed_time(b) for a, b in evs)
+    frames = sum(x[3] for x in resident[W:W + K])
+    t_max = adist.max_over_ranks(ms_dev * 1e-3, dev)
+    frames_all = adist.sum_over_ranks(frames, dev)
+    value = frames_all / t_max
+
+    # ---- (2) end to end through the public API: host buffers, pinned H2D pack, loss read-back --------
+    random.seed(2000 + rank)
+    for i in range(min(2, W)):
+        f, k, y, bits, fr = host[i]
+        float(step_resident(packer.pack(f, max_sp, k), torch.from_numpy(y).to(dev), bits))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    pending = None
+    for i in range(W, W + K):
+        f, k, y, bits, fr = host[i]
+        Xd = packer.pack(f, max_sp, k)                      # pinned host -> device + pack kernel
+        yd = torch.from_numpy(y).pin_memory().to(dev, non_blocking=True)
+        loss = step_resident(Xd, yd, bits)
+        h2d += sum(x.nbytes for x in f) + sum(m.nbytes for m in k) + y.nbytes + bits.nbytes
+        if pending is not None:
+            float(pending); d2h += 4                        # loss read one step late (asynchronous logging)
+        pending = loss
+    float(pending); d2h += 4
+    torch.cuda.synchronize()
+    t_e2e = adist.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = frames_all / t_e2e
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    roof = roofline_dominant(e, torch, peaks)
+    cpu_rate, cpu_done, cpu_t, cpu_desc = (None, 0, 0.0, [])
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_rate, cpu_done, cpu_t, cpu_desc = cpu_step_rate(loader, gplan[W:], 3, budget_s=20.0)
+    line = {
+        "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32 tensor-core GEMMs, fp32 accumulate/state" if args.precision == "tf32" else "f32 (3xTF32 / fp32 FMA, fp32-faithful)",
+        "data": "synthetic",
+        "config": {"workload": "es_en_20h bucketed training steps (configs[1]): B=32/GPU, Fisher-shaped lengths (20x80-frame buckets, "
+                               "truncated at 1680), D=40 fbank, V=1098, 2xCNN + 2x3-layer LSTM encoder + 3-layer attention decoder; "
+                               "fwd + bwd + WD/clip/AMSGrad; dropout .3/.3, speech_noise .25, teach_ratio .8, zero_input .1",
+                   "global_batch": BATCH * world, "parallelism": f"dp{world}", "l2_flush_between_steps": True,
+                   "frames_counted": "true (unpadded, post-truncation) input frames",
+                   "wall_ms_per_step_incl_flush": 1e3 * t_wall / K},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roof,
+    }
+    if cpu_rate is not None:
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{cpu_done} training steps ({', '.join(cpu_desc)}) of the same batch plan in {cpu_t:.1f}s; "
+                                          "numpy restatement of the reference (Chainer/CuPy not installable), OpenBLAS all cores"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

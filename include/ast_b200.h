@@ -32,6 +32,8 @@ typedef struct ast_config {
 
 const char* ast_last_error(void);
 int ast_abi_version(void);
+/* number of CUDA kernels this library has enqueued so far (optionally reset) */
+unsigned long long ast_launch_count(int reset);
 
 /* SpeechEncoderDecoder.__init__ (seq2seq.py:23-33); to_gpu (nn.py:133) is the `device` argument. */
 int ast_create(const ast_config* cfg, int device, ast_model** out);

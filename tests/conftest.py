@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The C-ABI library; built in-tree on demand (nvcc cross-compiles without a GPU)."""
+    from ast_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from ast_b200 import build
+        build.build()
+    return _lib.load()

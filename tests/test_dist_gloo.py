@@ -1,0 +1,53 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: identical batch plans on every rank,
+disjoint utterance shards, sum all-reduce + 1/world scaling equals the big-batch mean gradient."""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from ast_b200 import dist as adist
+    from ast_b200.dataloader import create_buckets, plan_batches
+    r, lr, w = adist.init_process_group("gloo")
+    assert (r, w) == (rank, world)
+    info = {f"u{i:03d}": {"sp": 30 + 7 * i} for i in range(40)}
+    random.seed("seed-ast-20h")                     # every rank seeds identically (nn.py:54)
+    plan = plan_batches(create_buckets(info, 20, 80, "sp", 1, "haha"), 4 * world)
+    mine = adist.shard_batch_plan(plan, rank, world)
+    assert len(mine) == len(plan)
+    # gradients: rank-local mean gradients -> sum all-reduce -> x 1/world
+    rng = np.random.default_rng(rank)
+    g = torch.tensor(rng.standard_normal(1000), dtype=torch.float32)
+    local = g.clone()
+    adist.allreduce_sum_(g)
+    tmax = adist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    tsum = adist.sum_over_ranks(float(rank + 1), torch.device("cpu"))
+    torch.save({"plan": plan, "mine": mine, "local": local, "reduced": g, "tmax": tmax, "tsum": tsum}, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_host_logic_world2(tmp_path):
+    world, port = 2, 29000 + random.randrange(2000)
+    out = str(tmp_path / "r")
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    res = [torch.load(out + f".{r}", weights_only=False) for r in range(world)]
+    assert res[0]["plan"] == res[1]["plan"]
+    for b in range(len(res[0]["plan"])):
+        utts = res[0]["plan"][b][0]
+        s0, s1 = res[0]["mine"][b][0], res[1]["mine"][b][0]
+        if len(utts) >= world:
+            assert sorted(s0 + s1) == sorted(utts) and not set(s0) & set(s1)
+        assert len(s0) >= 1 and len(s1) >= 1
+    want = res[0]["local"] + res[1]["local"]
+    assert torch.allclose(res[0]["reduced"], want) and torch.allclose(res[1]["reduced"], want)
+    assert res[0]["tmax"] == 2.0 and res[1]["tsum"] == 3.0
