@@ -1,8 +1,299 @@
-// tcgen05 / TMEM / TMA TF32 GEMM (placeholder until the kernel lands): reports "unsupported".
+// TF32 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma.kind::tf32 (one elected thread issues) -> fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   C[m,n] (+)= sum_k opA(m,k) * opB(k,n) (+ bias[n])          row-major fp32 everywhere
+//   opA(m,k) = ta ? A[k*lda + m] : A[m*lda + k]     (ta = 0: K-major,  ta = 1: M-major operand)
+//   opB(k,n) = tb ? B[n*ldb + k] : B[k*ldb + n]     (tb = 1: K-major,  tb = 0: N-major operand)
+//
+// fp32 data is consumed directly as TF32 (the tensor core reads the top 19 bits), so no conversion pass
+// touches HBM.  Both operand majors are expressed through the UMMA instruction descriptor (a_major /
+// b_major), which lets the backward data-gradient (NN) and weight-gradient (TN) contractions read the
+// forward tensors in place -- no transposed copies.  Weight gradients have K = T'*B (thousands) and a
+// small output, so they run split-K over blockIdx.z with fp32 red.global.add into a zeroed C.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+// (TMEM lane quadrant = warp_id % 4).  Tile 128 x 128 x 32 (one 128-byte swizzle row of fp32 per k-block),
+// 5-stage mbarrier ring (32 KB per stage).
+#include <cuda.h>
+#include <map>
+#include <tuple>
 #include "common.cuh"
 #include "kernels.h"
+
 namespace ast {
-int gemm_tc_nt(cudaStream_t, int, int, int, const float*, int, const float*, int, float*, int, const float*, float) {
-    return 1;
+
+constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 5;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t STAGE_A_BYTES = TBM * TBK * 4, STAGE_B_BYTES = TBN * TBK * 4;
+constexpr uint32_t TC_SMEM = TSTAGES * (STAGE_A_BYTES + STAGE_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start address, leading /
+// stride byte offsets (all >> 4), version 1, layout type.
+//   K-major fp32 : SWIZZLE_128B (2): rows of 128 B (32 k), 16-byte chunks XOR-ed with (row % 8); SBO = 8 rows.
+//   MN-major fp32: SWIZZLE_128B_BASE32B (1) is the only layout the tensor core accepts for 32-bit MN-major
+//                  operands: rows of 128 B (32 mn) per k, 32-byte chunks XOR-ed with (k-row % 4); SBO = 4 k-rows,
+//                  LBO = stride between 32-wide MN chunks.  TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;           // version = 1 (Blackwell)
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+struct TcParams {
+    int M, N, K;
+    float* C; int ldc;
+    const float* bias;
+    float beta;
+    int atomic;          // split-K: red.add into C
+    int kb_per_split;    // k-blocks per blockIdx.z
+};
+
+// TA: A operand is M-major (A stored K x M).  NB: B operand is N-major (B stored K x N).
+template <bool TA, bool NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TSTAGES * STAGE_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TSTAGES * (STAGE_A_BYTES + STAGE_B_BYTES));
+    uint64_t* full = bars;                 // [TSTAGES]
+    uint64_t* empty = bars + TSTAGES;      // [TSTAGES]
+    uint64_t* tmem_full = bars + 2 * TSTAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TSTAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+    const int nkb_total = (p.K + TBK - 1) / TBK;
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int nkb = min(p.kb_per_split, nkb_total - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TSTAGES;
+                const uint32_t ph = (i / TSTAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], STAGE_A_BYTES + STAGE_B_BYTES);
+                const int k0 = (kb0 + i) * TBK;
+                uint8_t* a = sA + s * STAGE_A_BYTES;
+                uint8_t* b = sB + s * STAGE_B_BYTES;
+                if (!TA) tma_load_2d(&mapA, &full[s], a, k0, m0);                     // box {32 k, 128 m}
+                else
+#pragma unroll
+                    for (int j = 0; j < TBM / 32; ++j) tma_load_2d(&mapA, &full[s], a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
+                if (!NB) tma_load_2d(&mapB, &full[s], b, k0, n0);
+                else
+#pragma unroll
+                    for (int j = 0; j < TBN / 32; ++j) tma_load_2d(&mapB, &full[s], b + j * (TBK * 128), n0 + 32 * j, k0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((NB ? 1u : 0u) << 16) |
+                                   ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % TSTAGES;
+                const uint32_t ph = (i / TSTAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(sA + s * STAGE_A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + s * STAGE_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TBK / 8; ++k) {
+                    // K-major: advance 32 B inside the 128 B swizzle row; SBO = 8 rows * 128 B.
+                    // MN-major: each k-step is the next 8-row group (1024 B); LBO = stride between 32-wide MN chunks.
+                    const uint64_t ad = TA ? make_smem_desc(a_addr + k * 1024, TBK * 128, 512, 1) : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+                    const uint64_t bd = NB ? make_smem_desc(b_addr + k * 1024, TBK * 128, 512, 1) : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                    umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+            }
+            umma_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int wq = warp & 3;                 // TMEM lane quadrant this warp may access
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = m0 + wq * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < TBN / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+            if (m < p.M && nkb > 0) {
+                float* crow = p.C + (size_t)m * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c * 32 + j;
+                    if (n < p.N) {
+                        float x = v[j];
+                        if (p.bias && blockIdx.z == 0) x += p.bias[n];
+                        if (p.atomic) atomicAdd(crow + n, x);
+                        else crow[n] = (p.beta != 0.f) ? x + p.beta * crow[n] : x;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TBN));
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: dims {inner, outer}, row stride ld (floats), box {32, box_outer}, 128B swizzle, zero OOB fill.
+static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, int ld, uint32_t box_outer, bool mn_major) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    if ((uintptr_t)ptr % 16 != 0 || ld % 4 != 0) return false;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool TA, bool NB>
+static int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid) {
+    auto kern = gemm_tc_kernel<TA, NB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr_set = true;
+    }
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// General entry: returns 1 when the tensor-core path cannot take the problem (caller falls back to SIMT).
+int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+            int ldc, const float* bias, float beta, int split_k) {
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    CUtensorMap ma, mb;
+    const bool okA = ta ? make_map(&ma, A, (uint64_t)M, (uint64_t)K, lda, 32, true) : make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false);
+    const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
+    if (!okA || !okB) return 1;
+    const int nkb = cdiv(K, TBK);
+    const int tiles = cdiv(M, TBM) * cdiv(N, TBN);
+    int splits = 1;
+    if (split_k != 0) {
+        // fill ~2 waves of 148 SMs, keep >= 8 k-blocks per split
+        splits = split_k > 0 ? split_k : std::max(1, std::min(nkb / 8, (2 * 148) / std::max(tiles, 1)));
+        splits = std::max(1, std::min(splits, nkb));
+    }
+    const int kbps = cdiv(nkb, splits);
+    splits = cdiv(nkb, kbps);
+    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps};
+    if (splits > 1) {
+        if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+        else if (beta != 1.f) return 1;
+    }
+    dim3 grid(cdiv(N, TBN), cdiv(M, TBM), splits);
+    if (!ta && tb) return launch_tc<false, false>(st, ma, mb, p, grid);
+    if (!ta && !tb) return launch_tc<false, true>(st, ma, mb, p, grid);
+    if (ta && !tb) return launch_tc<true, true>(st, ma, mb, p, grid);
+    return launch_tc<true, false>(st, ma, mb, p, grid);
+}
+
+int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+               const float* bias, float beta) {
+    return gemm_tc(st, false, true, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, 0);
+}
+
 }  // namespace ast

@@ -16,6 +16,9 @@ int sgemm_simt(cudaStream_t st, bool ta, bool tb, int M, int N, int K, float alp
 // shape is not supported by the tensor-core kernel (caller falls back to sgemm_simt).
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                int ldc, const float* bias, float beta);
+// General form (any operand major); split_k: 0 = none, -1 = automatic (weight gradients), >0 = that many.
+int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+            float* C, int ldc, const float* bias, float beta, int split_k);
 
 // ---- CNN front-end ---------------------------------------------------------------------------
 int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, int Fp, int T1, int kh, int kw, int sh,
@@ -53,6 +56,7 @@ struct LstmChain {
     float* dh0;          // bwd: gradient w.r.t. the initial state (B x h) or null
     float* dc0;
     unsigned drop_stream;
+    int b0, nb;          // batch rows [b0, b0+nb) of the B-row buffers handled by this chain (nb = 0: all B rows)
 };
 struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
 int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,

@@ -1,16 +1,18 @@
 // Persistent LSTM recurrence over a whole sequence (seq2seq.py:192-225, chainer L.LSTM / F.lstm).
 //
-// One thread-block CLUSTER of 8 CTAs owns one (layer, direction) chain for all T steps: the lateral
-// weight W_h (4h x h fp32, 1 MB at h = 256) is loaded into the cluster's shared memory ONCE
-// (128 KB per CTA) and stays resident; per step the cluster does the (B x h)·(h x 4h) recurrent
-// GEMM on tensor cores (mma.sync m16n8k8 TF32 with the 3-term split for fp32 accuracy -- batch is
-// the M dimension, and M = 16 is exactly one mma tile, so a tcgen05 tile with M >= 64 would be
-// >= 75 % padding), fuses the gate non-linearities, the cell update and the dropout mask, and
-// all-gathers the new h through distributed shared memory followed by one cluster barrier.
-// The input projections X·W_x^T + b for all timesteps are a single batched GEMM done beforehand.
+// One thread-block CLUSTER of 8 CTAs owns one chain = (layer, direction, 16-row batch slice) for all T
+// steps: the lateral weight W_h (4h x h fp32, 1 MB at h = 256) is loaded into the cluster's shared memory
+// ONCE (128 KB per CTA) and stays resident; per step the cluster does the (16 x h)·(h x 4h) recurrent GEMM
+// on tensor cores (mma.sync m16n8k8 TF32; the 3-term split gives fp32 accuracy in "exact" mode -- batch is
+// the M dimension, and M = 16 is exactly one mma tile, so a tcgen05 tile with M >= 64 would be >= 75 %
+// padding), fuses the gate non-linearities, the cell update and the dropout mask, and all-gathers the new h
+// through distributed shared memory.  The per-step critical path is kept short: the cluster barrier is split
+// into arrive (right after the DSMEM stores) and wait (after the global stores and the prefetch of the next
+// step's inputs), so HBM latency never sits between two steps.
+// The input projections X·W_x^T + b for all timesteps are a single batched tcgen05 GEMM done beforehand.
 //
-// Chainer's interleaved gate layout (row 4j+k of W, k = a,i,f,o) means a contiguous block of 4U
-// rows is exactly U hidden units with all four gates, so each CTA owns U = h/8 units outright.
+// Chainer's interleaved gate layout (row 4j+k of W, k = a,i,f,o) means a contiguous block of 4U rows is
+// exactly U hidden units with all four gates, so each CTA owns U = h/8 units outright.
 //
 // Backward runs the same structure in reverse: dG_t (pre-activation gate gradients) is produced
 // elementwise, written in place over the saved activations, multiplied by the resident W_h slice and
@@ -25,8 +27,33 @@ namespace ast {
 
 constexpr int NC = 8;            // CTAs per cluster
 constexpr int LTHREADS = 256;
+constexpr int MROWS = 16;        // batch rows per chain (one mma M tile)
 
-template <int MT, bool EXACT>
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <bool EXACT>
+struct Frag {            // an mma operand register, optionally with its low-order TF32 term
+    uint32_t hi, lo;
+    __device__ __forceinline__ void set(float x) {
+        hi = f2tf32(x);
+        if (EXACT) lo = f2tf32(x - __uint_as_float(hi));
+    }
+};
+template <bool EXACT>
+__device__ __forceinline__ void mma_frag(float (&c)[4], const Frag<EXACT> (&a)[4], const Frag<EXACT> (&b)[2]) {
+    const uint32_t ah[4] = {a[0].hi, a[1].hi, a[2].hi, a[3].hi};
+    const uint32_t bh[2] = {b[0].hi, b[1].hi};
+    if (EXACT) {
+        const uint32_t al[4] = {a[0].lo, a[1].lo, a[2].lo, a[3].lo};
+        const uint32_t bl[2] = {b[0].lo, b[1].lo};
+        mma_tf32(c, al, bh);
+        mma_tf32(c, ah, bl);
+    }
+    mma_tf32(c, ah, bh);
+}
+
+template <bool EXACT>
 __global__ void __launch_bounds__(LTHREADS, 1)
 lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned long long seed) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -35,7 +62,7 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
     const int U = h / NC;                 // hidden units owned by this CTA
     const int ldw = h + 4;                // padded smem row stride (conflict-free fragment loads)
     const int H4 = 4 * h;
-    constexpr int MROWS = 16 * MT;
+    const int nb = a.nb, b0 = a.b0;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;                     // [4U][ldw], rows permuted into (a,i)/(f,o) n-tiles per warp
     float* hb = Ws + (size_t)4 * U * ldw; // [2][MROWS][ldw]
@@ -52,101 +79,96 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
         const float4 v = *reinterpret_cast<const float4*>(a.Wl + (size_t)(4 * (U * rank + unit) + gate) * h + k4 * 4);
         *reinterpret_cast<float4*>(Ws + (size_t)p * ldw + k4 * 4) = v;
     }
-    // h_{-1} from slot 0 of Hs into buffer 0 (rows >= B stay zero for the whole run)
+    // h_{-1} from slot 0 of Hs into buffer 0 (rows >= nb stay zero for the whole run)
     for (int idx = tid; idx < 2 * MROWS * ldw; idx += LTHREADS) hb[idx] = 0.f;
     __syncthreads();
-    for (int idx = tid; idx < B * h4; idx += LTHREADS) {
+    for (int idx = tid; idx < nb * h4; idx += LTHREADS) {
         const int m = idx / h4, k4 = idx % h4;
         *reinterpret_cast<float4*>(hb + (size_t)m * ldw + k4 * 4) =
-            *reinterpret_cast<const float4*>(a.Hs + (size_t)m * h + k4 * 4);
+            *reinterpret_cast<const float4*>(a.Hs + (size_t)(b0 + m) * h + k4 * 4);
     }
     const bool wact = w < (U >> 2);       // warps beyond U/4 only take part in the barriers
     const int ju = U * rank + 4 * w + q;  // this thread's hidden unit
-    float creg[MT][2];
+    float creg[2];
+    float4 gx[2];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int row = mt * 16 + g + 8 * hf;
-            creg[mt][hf] = (wact && row < B) ? a.Cs[(size_t)row * h + ju] : 0.f;
-        }
+    for (int hf = 0; hf < 2; ++hf) {
+        const int row = g + 8 * hf;
+        const bool v = wact && row < nb;
+        creg[hf] = v ? a.Cs[(size_t)(b0 + row) * h + ju] : 0.f;
+        gx[hf] = v ? *reinterpret_cast<const float4*>(a.G + (size_t)(b0 + row) * H4 + 4 * ju) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
-    cluster.sync();
+    cluster_arrive();
+    cluster_wait();
 
     const int ksteps = h >> 3;
     for (int i = 0; i < T; ++i) {
         const float* hc = hb + (size_t)(i & 1) * MROWS * ldw;
         float* hn = hb + (size_t)((i + 1) & 1) * MROWS * ldw;
-        float acc[2][MT][4];
         if (wact) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int row = mt * 16 + g + 8 * hf;
-                    float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row < B) gx = *reinterpret_cast<const float4*>(a.G + ((size_t)i * B + row) * H4 + 4 * ju);
-                    acc[0][mt][2 * hf] = gx.x; acc[0][mt][2 * hf + 1] = gx.y;
-                    acc[1][mt][2 * hf] = gx.z; acc[1][mt][2 * hf + 1] = gx.w;
-                }
+            float acc[2][4];
+            acc[0][0] = gx[0].x; acc[0][1] = gx[0].y; acc[0][2] = gx[1].x; acc[0][3] = gx[1].y;   // tile 0: gates a,i
+            acc[1][0] = gx[0].z; acc[1][1] = gx[0].w; acc[1][2] = gx[1].z; acc[1][3] = gx[1].w;   // tile 1: gates f,o
             const float* w0 = Ws + (size_t)(w * 16 + g) * ldw + q;
             const float* w1 = w0 + (size_t)8 * ldw;
+            const float* hr = hc + (size_t)g * ldw + q;
 #pragma unroll 4
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int k0 = ks * 8;
-                const float b0[2] = {w0[k0], w0[k0 + 4]};
-                const float b1[2] = {w1[k0], w1[k0 + 4]};
+                Frag<EXACT> fa[4], fb0[2], fb1[2];
+                fa[0].set(hr[k0]); fa[1].set(hr[(size_t)8 * ldw + k0]); fa[2].set(hr[k0 + 4]); fa[3].set(hr[(size_t)8 * ldw + k0 + 4]);
+                fb0[0].set(w0[k0]); fb0[1].set(w0[k0 + 4]);
+                fb1[0].set(w1[k0]); fb1[1].set(w1[k0 + 4]);
+                mma_frag<EXACT>(acc[0], fa, fb0);
+                mma_frag<EXACT>(acc[1], fa, fb1);
+            }
+            // gates -> cell -> h ; all-gather first (critical path), bookkeeping stores after the arrive
+            float4 actv[2]; float cv[2], hv[2];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const float* hr = hc + (size_t)(mt * 16 + g) * ldw + k0 + q;
-                    const float af[4] = {hr[0], hr[(size_t)8 * ldw], hr[4], hr[(size_t)8 * ldw + 4]};
-                    mma_f32<EXACT>(acc[0][mt], af, b0);
-                    mma_f32<EXACT>(acc[1][mt], af, b1);
+            for (int hf = 0; hf < 2; ++hf) {
+                const int row = g + 8 * hf;
+                const float ga = tanhf(acc[0][2 * hf]);
+                const float gi = sigmoidf_(acc[0][2 * hf + 1]);
+                const float gf = sigmoidf_(acc[1][2 * hf]);
+                const float go = sigmoidf_(acc[1][2 * hf + 1]);
+                const float c = ga * gi + gf * creg[hf];
+                const float hval = (row < nb) ? go * tanhf(c) : 0.f;
+                actv[hf] = make_float4(ga, gi, gf, go); cv[hf] = c; hv[hf] = hval;
+                if (row < nb) creg[hf] = c;
+                // quad-gather 4 consecutive units, then each lane pushes the float4 to 2 CTAs
+                const int qb = lane & ~3;
+                float4 v4;
+                v4.x = __shfl_sync(0xffffffffu, hval, qb + 0);
+                v4.y = __shfl_sync(0xffffffffu, hval, qb + 1);
+                v4.z = __shfl_sync(0xffffffffu, hval, qb + 2);
+                v4.w = __shfl_sync(0xffffffffu, hval, qb + 3);
+                float* dst_local = hn + (size_t)row * ldw + U * rank + 4 * w;
+#pragma unroll
+                for (int d = 0; d < 2; ++d) *reinterpret_cast<float4*>(cluster.map_shared_rank(dst_local, 2 * q + d)) = v4;
+            }
+            cluster_arrive();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int row = g + 8 * hf;
+                if (row < nb) {
+                    const size_t r = (size_t)i * B + b0 + row;
+                    *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = actv[hf];
+                    a.Cs[(r + B) * h + ju] = cv[hf];
+                    a.Hs[(r + B) * h + ju] = hv[hf];
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    a.out[(long long)i * a.out_si + (long long)(b0 + row) * a.out_sb + ju] = hv[hf] * dm;
+                    if (i + 1 < T) gx[hf] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);   // prefetch
                 }
             }
-            // gates -> cell -> h ; write saved activations, states and the all-gather
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int row = mt * 16 + g + 8 * hf;
-                    const float ga = tanhf(acc[0][mt][2 * hf]);
-                    const float gi = sigmoidf_(acc[0][mt][2 * hf + 1]);
-                    const float gf = sigmoidf_(acc[1][mt][2 * hf]);
-                    const float go = sigmoidf_(acc[1][mt][2 * hf + 1]);
-                    const float c = ga * gi + gf * creg[mt][hf];
-                    float hv = go * tanhf(c);
-                    if (row < B) {
-                        creg[mt][hf] = c;
-                        const size_t r = (size_t)i * B + row;
-                        *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = make_float4(ga, gi, gf, go);
-                        a.Cs[(r + B) * h + ju] = c;
-                        a.Hs[(r + B) * h + ju] = hv;
-                        const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
-                        a.out[(long long)i * a.out_si + (long long)row * a.out_sb + ju] = hv * dm;
-                    } else {
-                        hv = 0.f;
-                    }
-                    // quad-gather 4 consecutive units, then each lane pushes the float4 to 2 CTAs
-                    const int qb = lane & ~3;
-                    float4 v4;
-                    v4.x = __shfl_sync(0xffffffffu, hv, qb + 0);
-                    v4.y = __shfl_sync(0xffffffffu, hv, qb + 1);
-                    v4.z = __shfl_sync(0xffffffffu, hv, qb + 2);
-                    v4.w = __shfl_sync(0xffffffffu, hv, qb + 3);
-                    float* dst_local = hn + (size_t)row * ldw + U * rank + 4 * w;
-#pragma unroll
-                    for (int d = 0; d < 2; ++d) {
-                        float* dst = cluster.map_shared_rank(dst_local, 2 * q + d);
-                        *reinterpret_cast<float4*>(dst) = v4;
-                    }
-                }
+        } else {
+            cluster_arrive();
         }
-        cluster.sync();
+        cluster_wait();
     }
 }
 
-template <int MT, bool EXACT>
+template <bool EXACT>
 __global__ void __launch_bounds__(LTHREADS, 1)
 lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned long long seed) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -157,7 +179,7 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
     const int ldw = h + 8;                // bank = 8q + g
     const int ldg = K4 + 4;               // bank = 4g + q
     const int H4 = 4 * h;
-    constexpr int MROWS = 16 * MT;
+    const int nb = a.nb, b0 = a.b0;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;                               // [K4][ldw]  natural row order
     float* dgs = Ws + (size_t)K4 * ldw;             // [MROWS][ldg]
@@ -173,18 +195,28 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
     for (int idx = tid; idx < MROWS * ldg; idx += LTHREADS) dgs[idx] = 0.f;
     for (int idx = tid; idx < 2 * NC * MROWS * U; idx += LTHREADS) red[idx] = 0.f;
 
-    // elementwise ownership: pair e -> (m, ul) with ul fastest (coalesced)
+    // elementwise ownership: pair e -> (m, ul) with ul fastest (coalesced); MROWS*U <= 512 -> <= 2 per thread
     const int npairs = MROWS * U;
-    constexpr int MAXE = MT * 2;          // MROWS*U/256 <= 16*MT*32/256
+    constexpr int MAXE = 2;
     float dc[MAXE];
+    // prefetched inputs of the current step
+    float4 p_act[MAXE]; float p_c[MAXE], p_cp[MAXE], p_dout[MAXE];
 #pragma unroll
     for (int e = 0; e < MAXE; ++e) {
         const int idx = tid + e * LTHREADS;
-        const int m = idx / U, ul = idx % U;
-        dc[e] = (idx < npairs && m < B && a.dc_fin) ? a.dc_fin[(size_t)m * a.ld_dc_fin + U * rank + ul] : 0.f;
+        const int m = idx / U, ul = idx % U, ju = U * rank + ul;
+        const bool v = idx < npairs && m < nb;
+        dc[e] = (v && a.dc_fin) ? a.dc_fin[(size_t)(b0 + m) * a.ld_dc_fin + ju] : 0.f;
+        if (v) {
+            const size_t r = (size_t)(T - 1) * B + b0 + m;
+            p_act[e] = *reinterpret_cast<const float4*>(a.G + r * H4 + 4 * ju);
+            p_c[e] = a.Cs[(r + B) * h + ju]; p_cp[e] = a.Cs[r * h + ju];
+            p_dout[e] = a.dout[(long long)(T - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
+        } else { p_act[e] = make_float4(0.f, 0.f, 0.f, 0.f); p_c[e] = p_cp[e] = p_dout[e] = 0.f; }
     }
     __syncthreads();
-    cluster.sync();
+    cluster_arrive();
+    cluster_wait();
 
     const int ntile_per_warp = (h >> 3) / (LTHREADS / 32);   // n-tiles (8 cols) per warp
     for (int i = T - 1; i >= 0; --i) {
@@ -198,20 +230,20 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                 const int m = idx / U, ul = idx % U;
                 const int ju = U * rank + ul;
                 float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < B) {
+                if (m < nb) {
                     float dh;
                     if (i == T - 1) {
-                        dh = a.dh_fin ? a.dh_fin[(size_t)m * a.ld_dh_fin + ju] : 0.f;
+                        dh = a.dh_fin ? a.dh_fin[(size_t)(b0 + m) * a.ld_dh_fin + ju] : 0.f;
                     } else {
                         dh = 0.f;
 #pragma unroll
                         for (int s = 0; s < NC; ++s) dh += rprev[((size_t)s * MROWS + m) * U + ul];
                     }
-                    const size_t r = (size_t)i * B + m;
+                    const size_t r = (size_t)i * B + b0 + m;
                     const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
-                    dh += a.dout[(long long)i * a.out_si + (long long)m * a.out_sb + ju] * dm;
-                    const float4 act = *reinterpret_cast<const float4*>(a.G + r * H4 + 4 * ju);
-                    const float c = a.Cs[(r + B) * h + ju], cp = a.Cs[r * h + ju];
+                    dh += p_dout[e] * dm;
+                    const float4 act = p_act[e];
+                    const float c = p_c[e], cp = p_cp[e];
                     const float tc = tanhf(c);
                     const float dct = dc[e] + dh * act.w * (1.f - tc * tc);
                     dg.x = dct * act.y * (1.f - act.x * act.x);
@@ -219,7 +251,7 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                     dg.z = dct * cp * act.z * (1.f - act.z);
                     dg.w = dh * tc * act.w * (1.f - act.w);
                     dc[e] = dct * act.z;
-                    *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = dg;
+                    p_act[e] = dg;        // written back after the arrive
                 }
                 *reinterpret_cast<float4*>(dgs + (size_t)m * ldg + 4 * ul) = dg;
             }
@@ -229,34 +261,42 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
             // 2. partial dh_{t-1}[m][n] = sum_p dG[m][p] * W[p][n] over this CTA's K4 gate rows
             for (int nt = 0; nt < ntile_per_warp; ++nt) {
                 const int n0 = (w * ntile_per_warp + nt) * 8;
-                float acc[MT][4];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[mt][j] = 0.f;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* dr = dgs + (size_t)g * ldg + q;
 #pragma unroll 4
                 for (int ks = 0; ks < (K4 >> 3); ++ks) {
                     const int k0 = ks * 8;
-                    const float bf[2] = {Ws[(size_t)(k0 + q) * ldw + n0 + g], Ws[(size_t)(k0 + q + 4) * ldw + n0 + g]};
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const float* dr = dgs + (size_t)(mt * 16 + g) * ldg + k0 + q;
-                        const float af[4] = {dr[0], dr[(size_t)8 * ldg], dr[4], dr[(size_t)8 * ldg + 4]};
-                        mma_f32<EXACT>(acc[mt], af, bf);
-                    }
+                    Frag<EXACT> fa[4], fb[2];
+                    fb[0].set(Ws[(size_t)(k0 + q) * ldw + n0 + g]); fb[1].set(Ws[(size_t)(k0 + q + 4) * ldw + n0 + g]);
+                    fa[0].set(dr[k0]); fa[1].set(dr[(size_t)8 * ldg + k0]); fa[2].set(dr[k0 + 4]); fa[3].set(dr[(size_t)8 * ldg + k0 + 4]);
+                    mma_frag<EXACT>(acc, fa, fb);
                 }
                 // 3. reduce-scatter: columns n0+2q, n0+2q+1 belong to CTA (n/U)
                 const int n = n0 + 2 * q;
                 const int owner = n / U, ul = n % U;
                 float* base = cluster.map_shared_rank(red, owner) + ((size_t)(buf * NC + rank) * MROWS) * U + ul;
+                *reinterpret_cast<float2*>(base + (size_t)g * U) = make_float2(acc[0], acc[1]);
+                *reinterpret_cast<float2*>(base + (size_t)(g + 8) * U) = make_float2(acc[2], acc[3]);
+            }
+        }
+        cluster_arrive();
+        // 4. off the critical path: write dG_t in place, prefetch step i-1
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    *reinterpret_cast<float2*>(base + (size_t)(mt * 16 + g) * U) = make_float2(acc[mt][0], acc[mt][1]);
-                    *reinterpret_cast<float2*>(base + (size_t)(mt * 16 + g + 8) * U) = make_float2(acc[mt][2], acc[mt][3]);
+        for (int e = 0; e < MAXE; ++e) {
+            const int idx = tid + e * LTHREADS;
+            const int m = idx / U, ul = idx % U, ju = U * rank + ul;
+            if (idx < npairs && m < nb) {
+                const size_t r = (size_t)i * B + b0 + m;
+                *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = p_act[e];
+                if (i > 0) {
+                    const size_t rp = r - B;
+                    p_act[e] = *reinterpret_cast<const float4*>(a.G + rp * H4 + 4 * ju);
+                    p_c[e] = p_cp[e]; p_cp[e] = a.Cs[rp * h + ju];
+                    p_dout[e] = a.dout[(long long)(i - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
                 }
             }
         }
-        cluster.sync();
+        cluster_wait();
     }
     // gradients w.r.t. the initial state (slot 0), when requested
     if (a.dh0 || a.dc0) {
@@ -266,24 +306,24 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
             const int idx = tid + e * LTHREADS;
             if (idx < npairs) {
                 const int m = idx / U, ul = idx % U;
-                if (m < B) {
+                if (m < nb) {
                     const int ju = U * rank + ul;
                     if (a.dh0) {
                         float s = 0.f;
                         for (int sidx = 0; sidx < NC; ++sidx) s += r0[((size_t)sidx * MROWS + m) * U + ul];
-                        a.dh0[(size_t)m * h + ju] = s;
+                        a.dh0[(size_t)(b0 + m) * h + ju] = s;
                     }
-                    if (a.dc0) a.dc0[(size_t)m * h + ju] = dc[e];
+                    if (a.dc0) a.dc0[(size_t)(b0 + m) * h + ju] = dc[e];
                 }
             }
         }
     }
 }
 
-static size_t fwd_smem(int h, int MT) { return sizeof(float) * ((size_t)4 * (h / NC) * (h + 4) + (size_t)2 * 16 * MT * (h + 4)); }
-static size_t bwd_smem(int h, int MT) {
+static size_t fwd_smem(int h) { return sizeof(float) * ((size_t)4 * (h / NC) * (h + 4) + (size_t)2 * MROWS * (h + 4)); }
+static size_t bwd_smem(int h) {
     const int U = h / NC;
-    return sizeof(float) * ((size_t)4 * U * (h + 8) + (size_t)16 * MT * (4 * U + 4) + (size_t)2 * NC * 16 * MT * U);
+    return sizeof(float) * ((size_t)4 * U * (h + 8) + (size_t)MROWS * (4 * U + 4) + (size_t)2 * NC * MROWS * U);
 }
 
 template <class KernT>
@@ -304,34 +344,41 @@ static int launch_cluster(KernT kern, cudaStream_t st, int nchains, size_t smem,
     return 0;
 }
 
-static int check_shape(const char* who, int nchains, int T, int B, int h) {
-    AST_CHECK(nchains >= 1 && nchains <= AST_MAX_CHAINS, "%s: nchains %d out of range", who, nchains);
+// Split every logical chain (covering rows [b0, b0+nb)) into 16-row chains: batch rows are independent, so a
+// larger batch simply uses more clusters at the same per-step latency.
+static int expand_chains(const char* who, const LstmChains& in, int nchains, int T, int B, int h, LstmChains& out, int& nout) {
     AST_CHECK(h % 64 == 0 && h >= 64 && h <= 256, "%s: per-direction hidden size %d unsupported (need multiple of 64, <= 256)", who, h);
-    AST_CHECK(B >= 1 && B <= 32, "%s: batch %d unsupported by the persistent recurrence (1..32); split the batch", who, B);
-    AST_CHECK(T >= 1, "%s: T must be >= 1", who);
+    AST_CHECK(T >= 1 && B >= 1, "%s: T and B must be >= 1", who);
+    nout = 0;
+    for (int c = 0; c < nchains; ++c) {
+        const int nb_total = in.c[c].nb > 0 ? in.c[c].nb : B;
+        for (int r0 = 0; r0 < nb_total; r0 += MROWS) {
+            AST_CHECK(nout < AST_MAX_CHAINS, "%s: too many 16-row chains (batch %d x %d chains > %d clusters per launch)", who, B, nchains, AST_MAX_CHAINS);
+            out.c[nout] = in.c[c];
+            out.c[nout].b0 = in.c[c].b0 + r0;
+            out.c[nout].nb = std::min(MROWS, nb_total - r0);
+            ++nout;
+        }
+    }
     return 0;
 }
 
 int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact) {
-    AST_TRY(check_shape("lstm_seq_fwd", nchains, T, B, h));
-    const int MT = B <= 16 ? 1 : 2;
-    const size_t smem = fwd_smem(h, MT);
-    if (MT == 1) return exact ? launch_cluster(lstm_seq_fwd_kernel<1, true>, st, nchains, smem, ch, T, B, h, drop, seed)
-                              : launch_cluster(lstm_seq_fwd_kernel<1, false>, st, nchains, smem, ch, T, B, h, drop, seed);
-    return exact ? launch_cluster(lstm_seq_fwd_kernel<2, true>, st, nchains, smem, ch, T, B, h, drop, seed)
-                 : launch_cluster(lstm_seq_fwd_kernel<2, false>, st, nchains, smem, ch, T, B, h, drop, seed);
+    LstmChains ex{}; int n = 0;
+    AST_TRY(expand_chains("lstm_seq_fwd", ch, nchains, T, B, h, ex, n));
+    const size_t smem = fwd_smem(h);
+    return exact ? launch_cluster(lstm_seq_fwd_kernel<true>, st, n, smem, ex, T, B, h, drop, seed)
+                 : launch_cluster(lstm_seq_fwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);
 }
 
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact) {
-    AST_TRY(check_shape("lstm_seq_bwd", nchains, T, B, h));
-    const int MT = B <= 16 ? 1 : 2;
-    const size_t smem = bwd_smem(h, MT);
-    if (MT == 1) return exact ? launch_cluster(lstm_seq_bwd_kernel<1, true>, st, nchains, smem, ch, T, B, h, drop, seed)
-                              : launch_cluster(lstm_seq_bwd_kernel<1, false>, st, nchains, smem, ch, T, B, h, drop, seed);
-    return exact ? launch_cluster(lstm_seq_bwd_kernel<2, true>, st, nchains, smem, ch, T, B, h, drop, seed)
-                 : launch_cluster(lstm_seq_bwd_kernel<2, false>, st, nchains, smem, ch, T, B, h, drop, seed);
+    LstmChains ex{}; int n = 0;
+    AST_TRY(expand_chains("lstm_seq_bwd", ch, nchains, T, B, h, ex, n));
+    const size_t smem = bwd_smem(h);
+    return exact ? launch_cluster(lstm_seq_bwd_kernel<true>, st, n, smem, ex, T, B, h, drop, seed)
+                 : launch_cluster(lstm_seq_bwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);
 }
 
 }  // namespace ast

@@ -48,6 +48,11 @@ struct ast_model {
     float *P = nullptr, *G = nullptr, *bn_state = nullptr;
     // options
     int exact = 1, tc_gemm = 0;
+    // bit i set -> GEMM call-site class i stays on the fp32 SIMT kernel.  Default: the two forward convolutions.
+    // They feed train-mode BatchNorm, whose parameter gradients are cancellation-dominated (d beta_0 is ~0 by
+    // construction); TF32's truncated inputs there show up as O(1) relative errors in dbeta/dgamma/dW (measured:
+    // tools/precision_modes.py), while every other contraction stays within 3e-3 on TF32.
+    unsigned tc_mask = 0x3;
     unsigned long long seed = 0x5eed1234ULL, cur_seed = 0;
     unsigned long long step_counter = 0;
     // workspace
@@ -240,13 +245,23 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
 static cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // NT GEMM dispatcher: tcgen05 TF32 kernel when enabled and the shape qualifies, fp32 SIMT otherwise.
+static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, const float* bias, float beta, int split_k, int site);
 static int gemm_nt(ast_model* m, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                   float* C, int ldc, const float* bias, float beta = 0.f) {
-    if (m->tc_gemm && !m->exact) {
-        const int r = gemm_tc_nt(st, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+                   float* C, int ldc, const float* bias, int site) {
+    return gemm(m, st, false, true, M, N, K, A, lda, B, ldb, C, ldc, bias, 0.f, 0, site);
+}
+
+// General GEMM dispatcher (row-major, see gemm_simt.cu for the operand convention).
+enum { SITE_CONV0 = 0, SITE_CONV1 = 1, SITE_ENC_PROJ = 2, SITE_DEC_WGRAD = 3, SITE_ENC_DX = 4, SITE_ENC_WGRAD = 5,
+       SITE_CONV1_WGRAD = 6, SITE_CONV1_DX = 7, SITE_CONV0_WGRAD = 8 };
+static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, const float* bias, float beta, int split_k, int site) {
+    if (m->tc_gemm && !m->exact && !((m->tc_mask >> site) & 1u)) {
+        const int r = gemm_tc(st, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, split_k);
         if (r <= 0) return r;
     }
-    return sgemm_simt(st, false, true, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, bias);
+    return sgemm_simt(st, ta, tb, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, bias);
 }
 
 // Derived weight copies: padded W0, permuted W1, transposed decoder weights.
@@ -303,7 +318,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     }
     // CNN_0: im2col + GEMM, BN statistics, BN+ReLU into the padded layout
     AST_TRY(im2col0(st, Xin, m->cols0, B, T, m->D, Fp, T1, c.cnn_kh[0], c.cnn_kw[0], c.cnn_sh[0], c.cnn_sw[0], c.cnn_ph[0], m->ld0));
-    AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr));
+    AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr, SITE_CONV0));
     float* bn0 = m->bn_state; float* bn1 = m->bn_state + 2 * C0;
     if (train) {
         AST_TRY(bn_stats(st, m->raw0, m->bnstats, M0, C0, T1, T1));
@@ -315,7 +330,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
                         B * Fp, T1, S0, c.cnn_ph[1], C0));
     AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
-    AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr));
+    AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr, SITE_CONV1));
     if (train) {
         AST_TRY(bn_stats(st, m->raw1, m->bnstats, M1, C1, Rs, Tp));
         AST_TRY(bn_finalize(st, m->bnstats, m->mean1, m->invstd1, bn1, bn1 + C1, C1, (double)B * Fp * Tp, BN_EPS, BN_DECAY, true));
@@ -333,7 +348,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
             AST_TRY(gemm_nt(m, st, TB, 4 * h, m->in_enc(l), xin, m->in_enc(l), m->p((ln + "/upward/W").c_str()), m->in_enc(l),
-                            m->Genc[l][d], 4 * h, m->p((ln + "/upward/b").c_str())));
+                            m->Genc[l][d], 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
             AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
             AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
             LstmChain& cc = ch.c[d];
@@ -517,20 +532,18 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                               m->cur_seed, 32));
     }
     // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
-    AST_TRY(sgemm_simt(st, true, false, V, A, SB, 1.f, m->logits, Vp, m->ht, A, 0.f, m->g("out/W"), A, nullptr));
+    AST_TRY(gemm(m, st, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
     AST_TRY(colsum(st, m->logits, Vp, m->g("out/b"), SB, V, false));
-    AST_TRY(sgemm_simt(st, true, false, A, 2 * H, SB, 1.f, m->du, A, m->cvh, 2 * H, 0.f, m->g("context/W"), 2 * H, nullptr));
+    AST_TRY(gemm(m, st, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
     AST_TRY(colsum(st, m->du, A, m->g("context/b"), SB, A, false));
-    AST_TRY(sgemm_simt(st, true, false, H, H, SB, 1.f, m->dq, H, m->cvh + H, 2 * H, 0.f, m->g("attn_Wa/W"), H, nullptr));
+    AST_TRY(gemm(m, st, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
     AST_TRY(colsum(st, m->dq, H, m->g("attn_Wa/b"), SB, H, false));
     for (int l = 0; l < NL; ++l) {
         const std::string ln = lname(l, "dec");
         const int in = m->in_dec(l);
         const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
-        AST_TRY(sgemm_simt(st, true, false, 4 * H, in, SB, 1.f, m->actd[l], 4 * H, xin, in, 0.f,
-                           m->g((ln + "/upward/W").c_str()), in, nullptr));
-        AST_TRY(sgemm_simt(st, true, false, 4 * H, H, SB, 1.f, m->actd[l], 4 * H, m->Hdec[l], H, 0.f,
-                           m->g((ln + "/lateral/W").c_str()), H, nullptr));
+        AST_TRY(gemm(m, st, true, false, 4 * H, in, SB, m->actd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(gemm(m, st, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
         AST_TRY(colsum(st, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
     // ---- encoder BPTT, layer-major top-down; both directions per launch ------------------------------
@@ -556,11 +569,9 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
             float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
             const float* Wup = m->p((ln + "/upward/W").c_str());
-            AST_TRY(sgemm_simt(st, false, false, TB, in, 4 * h, 1.f, m->Genc[l][d], 4 * h, Wup, in, 0.f, dx, in, nullptr));
-            AST_TRY(sgemm_simt(st, true, false, 4 * h, in, TB, 1.f, m->Genc[l][d], 4 * h, xin, in, 0.f,
-                               m->g((ln + "/upward/W").c_str()), in, nullptr));
-            AST_TRY(sgemm_simt(st, true, false, 4 * h, h, TB, 1.f, m->Genc[l][d], 4 * h, m->Hs[l][d], h, 0.f,
-                               m->g((ln + "/lateral/W").c_str()), h, nullptr));
+            AST_TRY(gemm(m, st, false, false, TB, in, 4 * h, m->Genc[l][d], 4 * h, Wup, in, dx, in, nullptr, 0.f, 0, SITE_ENC_DX));
+            AST_TRY(gemm(m, st, true, false, 4 * h, in, TB, m->Genc[l][d], 4 * h, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_ENC_WGRAD));
+            AST_TRY(gemm(m, st, true, false, 4 * h, h, TB, m->Genc[l][d], 4 * h, m->Hs[l][d], h, m->g((ln + "/lateral/W").c_str()), h, nullptr, 0.f, -1, SITE_ENC_WGRAD));
             AST_TRY(colsum(st, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
         }
     }
@@ -568,13 +579,13 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
     AST_TRY(bn_bwd_from_rnn(st, m->d_rnn_in, m->d_rnn_rev, m->raw1, m->draw1, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
                             m->p("CNN_1_bn/beta"), m->bnstats, m->g("CNN_1_bn/gamma"), m->g("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
-    AST_TRY(sgemm_simt(st, true, false, C1, m->K1, M1, 1.f, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, 0.f, m->dW1p, m->K1, nullptr));
+    AST_TRY(gemm(m, st, true, false, C1, m->K1, M1, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, m->dW1p, m->K1, nullptr, 0.f, -1, SITE_CONV1_WGRAD));
     AST_TRY(permute_w1(st, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
-    AST_TRY(sgemm_simt(st, false, false, M1, m->K1, C1, 1.f, m->draw1, C1, m->W1p, m->K1, 0.f, m->dA1, m->K1, nullptr));
+    AST_TRY(gemm(m, st, false, false, M1, m->K1, C1, m->draw1, C1, m->W1p, m->K1, m->dA1, m->K1, nullptr, 0.f, 0, SITE_CONV1_DX));
     AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
     AST_TRY(bn_bwd_from_padded(st, m->da0p, m->raw0, m->draw0, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
                                m->bnstats, m->g("CNN_0_bn/gamma"), m->g("CNN_0_bn/beta"), B * Fp, T1, S0, c.cnn_ph[1], C0));
-    AST_TRY(sgemm_simt(st, true, false, C0, m->ld0, M0, 1.f, m->draw0, C0, m->cols0, m->ld0, 0.f, m->dW0pad, m->ld0, nullptr));
+    AST_TRY(gemm(m, st, true, false, C0, m->ld0, M0, m->draw0, C0, m->cols0, m->ld0, m->dW0pad, m->ld0, nullptr, 0.f, -1, SITE_CONV0_WGRAD));
     const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
     AST_TRY(copy2d(st, m->dW0pad, m->ld0, m->g("CNN_0/W"), K0, C0, K0));
     m->have_fwd = false;
@@ -694,6 +705,7 @@ int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, in
 int ast_set_option(ast_model* m, const char* key, double value) {
     if (!strcmp(key, "exact")) m->exact = value != 0;
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
+    else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
     return 0;
@@ -922,10 +934,11 @@ int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V
 }
 int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
              float beta, float* C, int ldc, const float* bias, void* stream) {
-    if (which == 1) {
-        AST_CHECK(!ta && tb && alpha == 1.f, "tcgen05 GEMM supports C = A*B^T (+bias, +beta*C) only");
-        const int r = gemm_tc_nt(S_(stream), M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
-        AST_CHECK(r <= 0, "tcgen05 GEMM: unsupported shape M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+    if (which >= 1) {   // 1: tcgen05 TF32, no split-K ; 2: automatic split-K ; >2: that many splits
+        AST_CHECK(alpha == 1.f, "tcgen05 GEMM supports alpha = 1 only");
+        const int r = gemm_tc(S_(stream), ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta,
+                              which == 1 ? 0 : (which == 2 ? -1 : which));
+        AST_CHECK(r <= 0, "tcgen05 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d (alignment / tensor-map encode)", M, N, K, lda, ldb);
         return r;
     }
     return sgemm_simt(S_(stream), ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);

@@ -297,6 +297,43 @@ def test_full_size_step_properties(dev):
     for k in e.info:
         assert _relerr(e.view(k, grad=True).cpu().numpy(), g[k]) <= GRAD_RTOL, ("tf32", k)
     assert abs(float(torch.linalg.vector_norm(e.grads)) - n_exact) <= 1e-2 * n_exact
+    # ... and so does the training configuration of bench.py: tcgen05 TF32 GEMMs for every batched contraction
+    e.set_option("tc_gemm", 1)
+    got_tc = float(e.forward_loss(X, y))
+    assert abs(got_tc - loss) <= LOSS_RTOL * abs(loss)
+    e.backward()
+    for k in e.info:
+        assert _relerr(e.view(k, grad=True).cpu().numpy(), g[k]) <= GRAD_RTOL, ("tc_gemm", k)
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K,which", [(0, 1, 300, 200, 120, 1), (0, 1, 4000, 1024, 1536, 1), (0, 0, 130, 260, 72, 1),
+                                               (1, 0, 116, 96, 1000, 1), (1, 0, 1024, 256, 4000, 2), (1, 1, 256, 128, 64, 1)])
+def test_tcgen05_tf32_gemm(lib, dev, ta, tb, M, N, K, which):
+    """TMA + tcgen05.mma.kind::tf32 + TMEM GEMM, every operand-major combination, tails and split-K, against fp64
+    within TF32 input precision (10-bit mantissa, truncated): |err| <= 6e-3 * sqrt(K) for N(0,1) operands."""
+    from ast_b200._lib import check, ptr
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    want = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64) + bias
+    dA, dB, db = (torch.as_tensor(x, device=dev) for x in (A, B, bias))
+    dC = torch.full((M, N), 7.0, device=dev)
+    check(lib.ast_gemm(which, ta, tb, M, N, K, 1.0, ptr(dA), A.shape[1], ptr(dB), B.shape[1], 0.0, ptr(dC), N, ptr(db), _stream(dev)))
+    assert np.abs(dC.cpu().numpy() - want).max() <= 6e-3 * np.sqrt(K)
+
+
+def test_tcgen05_implicit_conv_overlapping_rows(lib, dev):
+    """CNN_1 as an implicit GEMM: the A tensor map has row stride (256 floats) < row length (1152), i.e. rows overlap."""
+    from ast_b200._lib import check, ptr
+    rng = np.random.default_rng(5)
+    M, N, K, lda = 500, 512, 1152, 256
+    buf = rng.standard_normal(M * lda + K).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    want = np.lib.stride_tricks.as_strided(buf, (M, K), (lda * 4, 4)).astype(np.float64) @ W.T.astype(np.float64)
+    dbuf, dW, dC = torch.as_tensor(buf, device=dev), torch.as_tensor(W, device=dev), torch.zeros(M, N, device=dev)
+    check(lib.ast_gemm(1, 0, 1, M, N, K, 1.0, ptr(dbuf), lda, ptr(dW), K, 0.0, ptr(dC), N, None, _stream(dev)))
+    assert np.abs(dC.cpu().numpy() - want).max() <= 6e-3 * np.sqrt(K)
 
 
 def test_dropout_is_consistent_between_forward_and_backward(dev):
