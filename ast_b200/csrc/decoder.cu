@@ -1,127 +1,22 @@
 // Per-step decoder kernels (seq2seq.py:336-396, 468): batch-as-M "skinny" tensor-core GEMM with
-// fused epilogues (bias / tanh / LSTM cell / tanh-backward), Luong attention forward+backward with
-// warp-shuffle reductions, fused softmax-cross-entropy forward+backward+argmax, embedding
-// gather/scatter and the LSTM cell backward.
+// fused epilogues (bias / tanh / LSTM cell / tanh-backward / cell-backward), Luong attention forward+backward,
+// fused softmax-cross-entropy forward+backward+argmax, embedding gather/scatter and the LSTM cell backward.
+// These are the one-kernel-per-op versions used by the decode_step protocol, greedy / beam decoding and as the
+// cross-check for the persistent decoder-sequence kernels in dec_seq.cu; the arithmetic lives in decoder_dev.cuh.
 //
-// The decoder is strictly sequential (input feeding + scheduled sampling), its weights (31.6 MB
-// fp32) live in B200's 126 MB L2 across steps, and every GEMM has M = batch (16..32): the bound is
-// L2 weight streaming + launch latency, not tensor throughput.  mma.sync m16n8k8 TF32 (3-term
-// split = fp32 accuracy) matches M = 16 exactly; a tcgen05 tile (M >= 64) would be >= 75 % padding.
-#include "common.cuh"
-#include "kernels.h"
+// The decoder is strictly sequential (input feeding + scheduled sampling), its weights (31.6 MB fp32) live in
+// B200's 126 MB L2 across steps, and every GEMM has M = batch (16..32): the bound is L2 weight streaming +
+// dependency latency, not tensor throughput.  mma.sync m16n8k8 TF32 (3-term split = fp32 accuracy) matches
+// M = 16 exactly; a tcgen05 tile (M >= 64) would be >= 75 % padding.
+#include "decoder_dev.cuh"
 
 namespace ast {
-
-// =========================================================================================
-// skinny GEMM:  Y[b][n] = epi( sum_seg sum_k X_seg[b][k] * W_seg[n][k]  + bias[n] )
-// CTA = 8 warps = 16 output columns (two n-tiles), K split over the warps in chunks of 16,
-// cross-warp reduction through smem, then the epilogue.
-// =========================================================================================
-constexpr int SK_THREADS = 256;
-constexpr int SK_COLS = 16;
 
 template <int MT, bool EXACT>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_kernel(SkinnyArgs p) {
-    constexpr int MROWS = 16 * MT;
-    __shared__ float red[8][MROWS][SK_COLS + 1];
-    __shared__ float outv[MROWS][SK_COLS + 1];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
-    const int n0 = blockIdx.x * SK_COLS;
-
-    float acc[2][MT][4];
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[s][mt][j] = 0.f;
-
-    const int nch0 = p.K[0] >> 4, nch1 = p.K[1] >> 4;
-    const int nn0 = n0 + g, nn1 = n0 + 8 + g;
-#pragma unroll 2
-    for (int c = w; c < nch0 + nch1; c += 8) {
-        const int seg = c < nch0 ? 0 : 1;
-        const int k = ((seg ? c - nch0 : c) << 4) + 4 * q;
-        const float* __restrict__ W = p.W[seg];
-        const float* __restrict__ X = p.X[seg];
-        const int ldw = p.ldw[seg], ldx = p.ldx[seg];
-        float4 wv0 = make_float4(0.f, 0.f, 0.f, 0.f), wv1 = wv0;
-        if (nn0 < p.N) wv0 = *reinterpret_cast<const float4*>(W + (size_t)nn0 * ldw + k);
-        if (nn1 < p.N) wv1 = *reinterpret_cast<const float4*>(W + (size_t)nn1 * ldw + k);
-        float4 xv[MT][2];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int row = mt * 16 + g + 8 * hf;
-                xv[mt][hf] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.B) xv[mt][hf] = *reinterpret_cast<const float4*>(X + (size_t)row * ldx + k);
-            }
-        // two k-steps; lane q supplies physical k = 4q+{0,1} then 4q+{2,3} for both operands
-        const float b0a[2] = {wv0.x, wv0.y}, b0b[2] = {wv0.z, wv0.w};
-        const float b1a[2] = {wv1.x, wv1.y}, b1b[2] = {wv1.z, wv1.w};
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const float aa[4] = {xv[mt][0].x, xv[mt][1].x, xv[mt][0].y, xv[mt][1].y};
-            const float ab[4] = {xv[mt][0].z, xv[mt][1].z, xv[mt][0].w, xv[mt][1].w};
-            mma_f32<EXACT>(acc[0][mt], aa, b0a);
-            mma_f32<EXACT>(acc[0][mt], ab, b0b);
-            mma_f32<EXACT>(acc[1][mt], aa, b1a);
-            mma_f32<EXACT>(acc[1][mt], ab, b1b);
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            red[w][mt * 16 + g][s * 8 + 2 * q] = acc[s][mt][0];
-            red[w][mt * 16 + g][s * 8 + 2 * q + 1] = acc[s][mt][1];
-            red[w][mt * 16 + g + 8][s * 8 + 2 * q] = acc[s][mt][2];
-            red[w][mt * 16 + g + 8][s * 8 + 2 * q + 1] = acc[s][mt][3];
-        }
-    __syncthreads();
-    for (int idx = tid; idx < MROWS * SK_COLS; idx += SK_THREADS) {
-        const int row = idx >> 4, col = idx & 15;
-        float v = 0.f;
-#pragma unroll
-        for (int ww = 0; ww < 8; ++ww) v += red[ww][row][col];
-        const int n = n0 + col;
-        if (p.bias && n < p.N) v += p.bias[n];
-        outv[row][col] = v;
-    }
-    __syncthreads();
-
-    if (p.epi == EPI_LSTM) {
-        // 16 columns = 4 hidden units x (a,i,f,o)
-        for (int idx = tid; idx < MROWS * 4; idx += SK_THREADS) {
-            const int row = idx >> 2, ul = idx & 3;
-            const int unit = (n0 >> 2) + ul;
-            if (row < p.B && 4 * unit < p.N) {
-                const int Hh = p.N >> 2;
-                const float ga = tanhf(outv[row][4 * ul]), gi = sigmoidf_(outv[row][4 * ul + 1]);
-                const float gf = sigmoidf_(outv[row][4 * ul + 2]), go = sigmoidf_(outv[row][4 * ul + 3]);
-                const float c = ga * gi + gf * p.c_prev[(size_t)row * Hh + unit];
-                const float hv = go * tanhf(c);
-                *reinterpret_cast<float4*>(p.Y + (size_t)row * p.ldy + 4 * unit) = make_float4(ga, gi, gf, go);
-                p.c_out[(size_t)row * Hh + unit] = c;
-                p.h_out[(size_t)row * Hh + unit] = hv;
-                const float dm = dropout_scale(p.seed, p.drop_stream, (uint32_t)(p.drop_base + (size_t)row * Hh + unit), p.drop);
-                p.hd_out[(size_t)row * p.ld_hd + unit] = hv * dm;
-            }
-        }
-        return;
-    }
-    for (int idx = tid; idx < MROWS * SK_COLS; idx += SK_THREADS) {
-        const int row = idx >> 4, col = idx & 15;
-        const int n = n0 + col;
-        if (row >= p.B || n >= p.N) continue;
-        float v = outv[row][col];
-        if (p.add) v += p.add[(size_t)row * p.ld_add + n];
-        if (p.epi == EPI_TANH) v = tanhf(v);
-        else if (p.epi == EPI_TANHBWD) { const float t = p.aux[(size_t)row * p.ld_aux + n]; v *= (1.f - t * t); }
-        p.Y[(size_t)row * p.ldy + n] = v;
-    }
+    __shared__ SkinnySmem sm;
+    skinny_tile<MT, EXACT>(p, blockIdx.x * SK_COLS, sm);
 }
 
 int skinny(cudaStream_t st, const SkinnyArgs& p, bool exact) {
@@ -196,23 +91,9 @@ int embed_scatter(cudaStream_t st, float* demb, const float* dx0, int ld_dx, con
 // =========================================================================================
 // attention (seq2seq.py:336-358), no length mask (the reference's is commented out, :344-347)
 // =========================================================================================
-// s[b][t] = enc[eb][t][:] . v[b][:]      (eb = b, or 0 when one utterance is shared by all hyps)
-__global__ void attn_dot_kernel(const float* __restrict__ enc, long long enc_bs, const float* __restrict__ v, int ldv,
-                                float* __restrict__ s, int Tp, int H) {
-    const int b = blockIdx.y;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (t >= Tp) return;
-    const float* e = enc + (size_t)b * enc_bs + (size_t)t * H;
-    const float* vv = v + (size_t)b * ldv;
-    float acc = 0.f;
-    for (int j = lane * 4; j < H; j += 128) {
-        const float4 a = *reinterpret_cast<const float4*>(e + j);
-        const float4 c = *reinterpret_cast<const float4*>(vv + j);
-        acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) s[(size_t)b * Tp + t] = acc;
+__global__ void __launch_bounds__(256) attn_dot_kernel(const float* __restrict__ enc, long long enc_bs, const float* v, int ldv,
+                                                       float* s, int Tp, int H) {
+    attn_dot_block(enc, enc_bs, v, ldv, s, Tp, H, blockIdx.y, blockIdx.x);
 }
 int attn_dot(cudaStream_t st, const float* enc, long long enc_bs, const float* v, int ldv, float* s, int B, int Tp, int H) {
     AST_CHECK(H % 4 == 0 && ldv % 4 == 0, "attn_dot: H/ldv must be multiples of 4");
@@ -222,93 +103,35 @@ int attn_dot(cudaStream_t st, const float* enc, long long enc_bs, const float* v
     return 0;
 }
 
-// alpha = softmax_t(s) ; cv[b][j] = sum_t alpha[t] * enc[eb][t][j]
-__global__ void attn_ctx_kernel(const float* __restrict__ enc, long long enc_bs, const float* __restrict__ s,
-                                float* __restrict__ alpha, float* __restrict__ cv, int ld_cv, int Tp, int H) {
-    extern __shared__ float sa[];          // Tp alphas
+__global__ void __launch_bounds__(256) attn_ctx_kernel(const float* __restrict__ enc, long long enc_bs, const float* s, float* alpha,
+                                                       float* cv, int ld_cv, int Tp, int H) {
+    extern __shared__ float dsm[];          // Tp alphas + 8*128 partials
     __shared__ float scratch[32];
-    const int b = blockIdx.y;
-    const float* sb = s + (size_t)b * Tp;
-    float mx = -INFINITY;
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) mx = fmaxf(mx, sb[t]);
-    mx = block_max(mx, scratch);
-    float sum = 0.f;
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) { const float e = expf(sb[t] - mx); sa[t] = e; sum += e; }
-    sum = block_sum(sum, scratch);
-    const float inv = 1.f / sum;
-    __syncthreads();
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
-        const float al = sa[t] * inv;
-        sa[t] = al;
-        if (blockIdx.x == 0) alpha[(size_t)b * Tp + t] = al;
-    }
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= H) return;
-    const float* e = enc + (size_t)b * enc_bs + j;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int t = 0;
-    for (; t + 3 < Tp; t += 4) {
-        a0 = fmaf(sa[t], e[(size_t)t * H], a0);
-        a1 = fmaf(sa[t + 1], e[(size_t)(t + 1) * H], a1);
-        a2 = fmaf(sa[t + 2], e[(size_t)(t + 2) * H], a2);
-        a3 = fmaf(sa[t + 3], e[(size_t)(t + 3) * H], a3);
-    }
-    for (; t < Tp; ++t) a0 = fmaf(sa[t], e[(size_t)t * H], a0);
-    cv[(size_t)b * ld_cv + j] = (a0 + a1) + (a2 + a3);
+    attn_ctx_block(enc, enc_bs, s, alpha, cv, ld_cv, Tp, H, blockIdx.y, blockIdx.x, dsm, dsm + ((Tp + 3) & ~3), scratch);
 }
 int attn_ctx(cudaStream_t st, const float* enc, long long enc_bs, const float* s, float* alpha, float* cv, int ld_cv,
              int B, int Tp, int H) {
+    AST_CHECK(H % 4 == 0 && ld_cv % 4 == 0, "attn_ctx: H/ld must be multiples of 4");
     dim3 grid(cdiv(H, 128), B);
-    attn_ctx_kernel<<<grid, 128, sizeof(float) * Tp, st>>>(enc, enc_bs, s, alpha, cv, ld_cv, Tp, H);
+    attn_ctx_kernel<<<grid, 256, sizeof(float) * (Tp + 4 + 8 * 128), st>>>(enc, enc_bs, s, alpha, cv, ld_cv, Tp, H);
     AST_LAUNCH_OK();
     return 0;
 }
 
-// backward: ds = alpha*(dalpha - sum alpha*dalpha); dq[j] = sum_t ds[t]*enc[t][j];
-//           d_enc[t][j] += alpha[t]*dcv[j] + ds[t]*q[j]
-__global__ void attn_bwd_kernel(const float* __restrict__ enc, float* __restrict__ d_enc, long long enc_bs,
-                                const float* __restrict__ alpha, const float* __restrict__ dalpha,
-                                const float* __restrict__ dcv, int ld_dcv, const float* __restrict__ qv, int ld_q,
-                                float* __restrict__ dq, int ld_dq, int Tp, int H) {
-    extern __shared__ float sm[];          // alpha[Tp], ds[Tp]
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ enc, float* d_enc, long long enc_bs, const float* alpha,
+                                                       const float* dalpha, const float* dcv, int ld_dcv, const float* qv, int ld_q,
+                                                       float* dq, int ld_dq, int Tp, int H) {
+    extern __shared__ float dsm[];          // alpha[Tp], ds[Tp], 8*128 partials
     __shared__ float scratch[32];
-    float* sal = sm; float* sds = sm + Tp;
-    const int b = blockIdx.y;
-    float dot = 0.f;
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) {
-        const float al = alpha[(size_t)b * Tp + t], da = dalpha[(size_t)b * Tp + t];
-        sal[t] = al; sds[t] = da; dot = fmaf(al, da, dot);
-    }
-    dot = block_sum(dot, scratch);
-    __syncthreads();
-    for (int t = threadIdx.x; t < Tp; t += blockDim.x) sds[t] = sal[t] * (sds[t] - dot);
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= H) return;
-    const float dcvj = dcv[(size_t)b * ld_dcv + j], qj = qv[(size_t)b * ld_q + j];
-    const float* e = enc + (size_t)b * enc_bs + j;
-    float* de = d_enc + (size_t)b * enc_bs + j;
-    float a0 = 0.f, a1 = 0.f;
-    int t = 0;
-    for (; t + 1 < Tp; t += 2) {
-        const float e0 = e[(size_t)t * H], e1 = e[(size_t)(t + 1) * H];
-        const float d0 = de[(size_t)t * H], d1 = de[(size_t)(t + 1) * H];
-        a0 = fmaf(sds[t], e0, a0); a1 = fmaf(sds[t + 1], e1, a1);
-        de[(size_t)t * H] = d0 + sal[t] * dcvj + sds[t] * qj;
-        de[(size_t)(t + 1) * H] = d1 + sal[t + 1] * dcvj + sds[t + 1] * qj;
-    }
-    for (; t < Tp; ++t) {
-        a0 = fmaf(sds[t], e[(size_t)t * H], a0);
-        de[(size_t)t * H] += sal[t] * dcvj + sds[t] * qj;
-    }
-    dq[(size_t)b * ld_dq + j] = a0 + a1;
+    attn_bwd_block(enc, d_enc, enc_bs, alpha, dalpha, dcv, ld_dcv, qv, ld_q, dq, ld_dq, Tp, H, blockIdx.y, blockIdx.x, dsm,
+                   dsm + ((2 * Tp + 3) & ~3), scratch);
 }
 int attn_bwd(cudaStream_t st, const float* enc, float* d_enc, long long enc_bs, const float* alpha, const float* dalpha,
              const float* dcv, int ld_dcv, const float* qv, int ld_q, float* dq, int ld_dq, int B, int Tp, int H) {
+    AST_CHECK(H % 4 == 0 && ld_dcv % 4 == 0 && ld_q % 4 == 0, "attn_bwd: H/ld must be multiples of 4");
     dim3 grid(cdiv(H, 128), B);
-    attn_bwd_kernel<<<grid, 128, sizeof(float) * 2 * Tp, st>>>(enc, d_enc, enc_bs, alpha, dalpha, dcv, ld_dcv, qv, ld_q,
-                                                              dq, ld_dq, Tp, H);
+    attn_bwd_kernel<<<grid, 256, sizeof(float) * (2 * Tp + 4 + 8 * 128), st>>>(enc, d_enc, enc_bs, alpha, dalpha, dcv, ld_dcv, qv, ld_q,
+                                                                         dq, ld_dq, Tp, H);
     AST_LAUNCH_OK();
     return 0;
 }
@@ -317,53 +140,16 @@ int attn_bwd(cudaStream_t st, const float* enc, float* d_enc, long long enc_bs, 
 // fused softmax cross-entropy forward + backward + argmax (seq2seq.py:448,468; Appendix A.7)
 // =========================================================================================
 // One CTA per batch row.  row_loss[b] = -w[t]*logp[t]/B ; z <- (softmax(z) - onehot(t)) * w[t]/B in place
-// (cols [V,ldz) zeroed) ; argmax[b] = lowest index of the row maximum.  target < 0 -> argmax only.
-__global__ void softmax_ce_kernel(float* __restrict__ z, int ldz, const int* __restrict__ y, int ldy_tok, int step_next,
-                                  float* __restrict__ row_loss, int* __restrict__ argmax_out, int B, int V,
-                                  int write_grad) {
+// (cols [V,ldz) zeroed) ; argmax[b] = lowest index of the row maximum.  write_grad = 0 -> argmax only.
+__global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ z, int ldz, const int* __restrict__ y, int ldy_tok,
+                                                         int step_next, float* __restrict__ row_loss, int* __restrict__ argmax_out,
+                                                         int B, int V, int write_grad) {
     __shared__ float scratch[32];
     __shared__ int iscratch[32];
     const int b = blockIdx.x;
-    float* zr = z + (size_t)b * ldz;
-    float mx = -INFINITY; int mi = 0x7fffffff;
-    for (int n = threadIdx.x; n < V; n += blockDim.x) {
-        const float v = zr[n];
-        if (v > mx) { mx = v; mi = n; }
-    }
-    // (max, lowest index) reduction
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
-    }
-    if (lane == 0) { scratch[w] = mx; iscratch[w] = mi; }
-    __syncthreads();
-    mx = (lane < nw) ? scratch[lane] : -INFINITY;
-    mi = (lane < nw) ? iscratch[lane] : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
-    }
+    const int t = write_grad ? y[(size_t)b * ldy_tok + step_next] : 0;
+    const int mi = softmax_ce_row(z + (size_t)b * ldz, ldz, V, t, B, row_loss ? row_loss + b : nullptr, write_grad, scratch, iscratch);
     if (threadIdx.x == 0 && argmax_out) argmax_out[b] = mi;
-    if (!write_grad) return;
-    float sum = 0.f;
-    for (int n = threadIdx.x; n < V; n += blockDim.x) sum += expf(zr[n] - mx);
-    sum = block_sum(sum, scratch);
-    const float lse = mx + logf(sum);
-    const int t = y[(size_t)b * ldy_tok + step_next];
-    const float wt = (t == 0) ? 0.f : 1.f;                      // mask_pad_id: class weight 0 for PAD
-    const float scale = wt / (float)B;
-    if (threadIdx.x == 0) row_loss[b] = -scale * (zr[t] - lse);
-    __syncthreads();
-    for (int n = threadIdx.x; n < ldz; n += blockDim.x) {
-        float gz = 0.f;
-        if (n < V) gz = (expf(zr[n] - lse) - (n == t ? 1.f : 0.f)) * scale;
-        zr[n] = gz;
-    }
 }
 int softmax_ce(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, int step_next, float* row_loss,
                int* argmax_out, int B, int V, bool write_grad) {

@@ -65,7 +65,7 @@ int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
                  unsigned long long seed, bool exact);
 
 // ---- decoder step kernels ------------------------------------------------------------------------
-enum { EPI_NONE = 0, EPI_TANH = 1, EPI_LSTM = 2, EPI_TANHBWD = 3 };
+enum { EPI_NONE = 0, EPI_TANH = 1, EPI_LSTM = 2, EPI_TANHBWD = 3, EPI_CELLBWD = 4 };
 struct SkinnyArgs {
     const float* X[2]; int ldx[2]; int K[2];
     const float* W[2]; int ldw[2];
@@ -77,7 +77,31 @@ struct SkinnyArgs {
     // EPI_LSTM
     const float* c_prev; float* c_out; float* h_out; float* hd_out; int ld_hd;
     float drop; unsigned long long seed; unsigned drop_stream; size_t drop_base;
+    float* Y2; int ldy2;               // optional second copy of the output (e.g. ht -> next step's input feeding slot)
+    // EPI_CELLBWD: the output value (after `add`) is d(out) of hidden unit n of the layer below; the epilogue does that
+    // layer's LSTM cell backward in place (act -> dG) for rows x units of this column group.
+    float* cb_act; const float* cb_c; const float* cb_c_prev; float* cb_dc; const float* cb_dh_rec; int cb_ld_dh_rec; int cb_H;
+    int cb_ncols;                      // the cell backward applies to output columns n < cb_ncols
+    float* sc_demb; const int* sc_words; int sc_E;   // optional EmbedID scatter-add of columns n < sc_E
 };
+
+// Persistent decoder-sequence kernels (dec_seq.cu): everything a forward_loss decoder pass touches.
+#define AST_MAXL 4
+struct DecSeq {
+    int B, S, L, H, E, A, V, Vp, Tp, NL;
+    const float* emb; const float* Wup[AST_MAXL]; const float* bup[AST_MAXL]; const float* Wlat[AST_MAXL];
+    const float* Wa; const float* ba; const float* Wc; const float* bc; const float* Wo; const float* bo;
+    const float* WoT; const float* WcT; const float* WaT; const float* WcatT[AST_MAXL];
+    const int* y; const unsigned char* use_true;
+    const float* enc; float* d_enc;
+    float* x0; float* act[AST_MAXL]; float* Hd[AST_MAXL]; float* Cd[AST_MAXL]; float* hdd[AST_MAXL];
+    float* q; float* scores; float* alpha; float* cvh; float* ht; float* logits; float* row_loss;
+    int* words_used; int* argmax_steps;
+    float* du; float* dcvh; float* dalpha; float* dq; float* dxh[AST_MAXL]; float* dcd[AST_MAXL]; float* demb;
+    float drop_embed, drop_rnn; unsigned long long seed;
+};
+int dec_seq_fwd(cudaStream_t st, const DecSeq& p, bool exact);
+int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);
 int skinny(cudaStream_t st, const SkinnyArgs& p, bool exact);
 int embed_concat(cudaStream_t st, const float* emb, const int* y, int ldy_tok, const unsigned char* use_true,
                  const int* prev_argmax, const int* forced_words, const float* ht_prev, int ld_ht, float* x0,

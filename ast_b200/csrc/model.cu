@@ -47,7 +47,7 @@ struct ast_model {
     long long nfloats = 0;
     float *P = nullptr, *G = nullptr, *bn_state = nullptr;
     // options
-    int exact = 1, tc_gemm = 0;
+    int exact = 1, tc_gemm = 0, dec_fused = 1;   // dec_fused: persistent decoder-sequence kernels (dec_seq.cu)
     // bit i set -> GEMM call-site class i stays on the fp32 SIMT kernel.  Default: the two forward convolutions.
     // They feed train-mode BatchNorm, whose parameter gradients are cancellation-dominated (d beta_0 is ~0 by
     // construction); TF32's truncated inputs there show up as O(1) relative errors in dbeta/dgamma/dW (measured:
@@ -78,6 +78,7 @@ struct ast_model {
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
     bool weights_dirty = true, have_fwd = false;
+    const int* y_dev = nullptr; const unsigned char* use_true_dev = nullptr;   // of the last forward_loss
     int dec_Bd = 0;
 
     float* p(const char* name) const {
@@ -433,6 +434,27 @@ static int dec_step_fwd(ast_model* m, const StepIO& io, cudaStream_t st) {
     return 0;
 }
 
+// Everything the persistent decoder-sequence kernels touch (dec_seq.cu).
+static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_true, bool train) {
+    DecSeq p{};
+    p.B = m->B; p.S = m->L - 1; p.L = m->L; p.H = m->H; p.E = m->E; p.A = m->A; p.V = m->V; p.Vp = m->Vp; p.Tp = m->Tp; p.NL = m->NL;
+    p.emb = m->p("embed_dec/W");
+    for (int l = 0; l < m->NL; ++l) {
+        const std::string ln = lname(l, "dec");
+        p.Wup[l] = m->p((ln + "/upward/W").c_str()); p.bup[l] = m->p((ln + "/upward/b").c_str()); p.Wlat[l] = m->p((ln + "/lateral/W").c_str());
+        p.WcatT[l] = m->WcatT[l]; p.act[l] = m->actd[l]; p.Hd[l] = m->Hdec[l]; p.Cd[l] = m->Cdec[l]; p.hdd[l] = m->hdd[l];
+        p.dxh[l] = m->dxh[l]; p.dcd[l] = m->dcd[l];
+    }
+    p.Wa = m->p("attn_Wa/W"); p.ba = m->p("attn_Wa/b"); p.Wc = m->p("context/W"); p.bc = m->p("context/b");
+    p.Wo = m->p("out/W"); p.bo = m->p("out/b"); p.WoT = m->WoT; p.WcT = m->WcT; p.WaT = m->WaT;
+    p.y = y; p.use_true = use_true; p.enc = m->enc_states; p.d_enc = m->d_enc;
+    p.x0 = m->x0; p.q = m->q; p.scores = m->scores; p.alpha = m->alpha; p.cvh = m->cvh; p.ht = m->ht; p.logits = m->logits;
+    p.row_loss = m->row_loss; p.words_used = m->words_used; p.argmax_steps = m->argmax_steps;
+    p.du = m->du; p.dcvh = m->dcvh; p.dalpha = m->dalpha; p.dq = m->dq; p.demb = m->g("embed_dec/W");
+    p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward_loss (seq2seq.py:399-473)
 // ------------------------------------------------------------------------------------------------
@@ -446,7 +468,9 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     float* hinit[MAXL]; float* cinit[MAXL];
     for (int l = 0; l < NL; ++l) { hinit[l] = m->Hdec[l]; cinit[l] = m->Cdec[l]; }
     AST_TRY(init_dec_state(m, hinit, cinit, B, st));
-    for (int s = 0; s < S; ++s) {
+    m->y_dev = y; m->use_true_dev = use_true;
+    if (m->dec_fused) AST_TRY(dec_seq_fwd(st, make_dec_seq(m, y, use_true, true), m->exact != 0));
+    else for (int s = 0; s < S; ++s) {
         StepIO io{};
         io.Bd = B; io.step = s; io.train = true; io.y = y; io.ldy = L; io.use_true = use_true;
         io.prev_argmax = s > 0 ? m->argmax_steps + (size_t)(s - 1) * B : nullptr;
@@ -492,7 +516,8 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
     }
     // ---- decoder BPTT: data gradients step by step -----------------------------------------------
-    for (int s = S - 1; s >= 0; --s) {
+    if (m->dec_fused) AST_TRY(dec_seq_bwd(st, make_dec_seq(m, m->y_dev, m->use_true_dev, true), ex));
+    else for (int s = S - 1; s >= 0; --s) {
         const float* dz = m->logits + (size_t)s * B * Vp;
         float* du = m->du + (size_t)s * B * A;
         {   // du = (dz . Wo + dht_feed) * (1 - ht^2)
@@ -706,6 +731,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     if (!strcmp(key, "exact")) m->exact = value != 0;
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
     else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
+    else if (!strcmp(key, "dec_fused")) m->dec_fused = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
     return 0;
@@ -713,6 +739,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
 double ast_get_option(const ast_model* m, const char* key) {
     if (!strcmp(key, "exact")) return m->exact;
     if (!strcmp(key, "tc_gemm")) return m->tc_gemm;
+    if (!strcmp(key, "dec_fused")) return m->dec_fused;
     if (!strcmp(key, "seed")) return (double)m->seed;
     return -1;
 }

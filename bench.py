@@ -21,6 +21,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 D, V, BATCH = 40, 1098, 32
 TRAIN_EXTRAS = {"random_out": 0, "speech_noise": 0.25, "teach_ratio": 0.8}
@@ -158,7 +165,7 @@ def run_reference(args):
                              "sample": f"{done} training steps of the same batch plan; numpy restatement of the reference "
                                        "(real Chainer/CuPy is not installable), OpenBLAS on all host cores"},
             "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,6 +204,31 @@ def roofline_dominant(engine, torch, peaks):
     return {"bound": "tensor", "kernel": "gemm_tc_nt (tcgen05 TF32)" if which == 1 else "sgemm_kernel (fp32 SIMT)",
             "shape": f"M{M} N{N} K{R}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms, "traffic": None}
+
+
+def beam_rate(model, torch, T, n_utts, eos_boost, N=10, K=10, max_pred=175):
+    """beam-10 decode utterances / second (BASELINE metric ii), fp32-faithful mode, host feature buffers
+    in, hypotheses out.  eos_boost > 0 is the 'trained-like' variant (EOS reachable -> realistic lengths)."""
+    from ast_b200.nn import beam_result_to_entries
+    e = model._engine
+    old = e.view("out/b")[2].item()
+    e.view("out/b")[2] += eos_boost
+    e.weights_changed()
+    rng = np.random.default_rng(7)
+    utts = [rng.standard_normal((1, T, D), dtype=np.float32) for _ in range(n_utts + 1)]
+    steps = 0
+    for i, x in enumerate(utts):
+        if i == 1:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = e.beam_search(x, max_pred, N, K)
+        ent = beam_result_to_entries(r)
+        if i >= 1:
+            steps += r["n_steps"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e.view("out/b")[2] = old
+    e.weights_changed()
+    return {"utts_per_s": n_utts / dt, "T": T, "avg_steps": steps / n_utts, "n_utts": n_utts, "N": N, "K": K}
 
 
 def run_ours(args):
@@ -330,11 +362,18 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roof,
     }
+    if world == 1 and not args.no_beam:
+        e.set_option("exact", 1)
+        train_config.train = False
+        line["beam"] = {"metric": "beam10_decode_utts_per_sec", "mode": "exact fp32-faithful, batch-size-1 utterances (beam.py:111)",
+                        "random_init_worst_case": beam_rate(model, torch, 1000, 6, 0.0),
+                        "trained_like_T1000": beam_rate(model, torch, 1000, 12, 6.0),
+                        "trained_like_T3000": beam_rate(model, torch, 3000, 6, 6.0)}
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{cpu_done} training steps ({', '.join(cpu_desc)}) of the same batch plan in {cpu_t:.1f}s; "
                                           "numpy restatement of the reference (Chainer/CuPy not installable), OpenBLAS all cores"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -343,9 +382,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="f32", choices=["f32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["f32", "tf32"],
+                    help="tf32: tcgen05 TF32 GEMMs + single-pass TF32 recurrences (training mode, inside the parity "
+                         "tolerances); f32: fp32-faithful everywhere (the decode / hypothesis-identity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true")
     args = ap.parse_args()
+    # keep stdout clean for the ONE JSON line: library banners (e.g. NCCL's version line) go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -185,6 +185,28 @@ def test_forward_backward_optimizer_parity(dev, B, T, D, V, Lmin, Lmax, seed, ss
             assert np.abs(e.view(k).cpu().numpy() - om.p[k]).max() < 5e-6, (t, k)
 
 
+def test_fused_and_per_step_decoder_paths_agree(dev):
+    """The persistent decoder-sequence kernels (one cooperative launch per pass) and the kernel-per-op path run the
+    same arithmetic: identical argmax tokens, loss and gradients to fp32 round-off, with dropout + scheduled sampling."""
+    cfg = O.default_model_cfg(vocab=333, dropout=(0.3, 0.3, 0.0))
+    P = _perturbed(cfg, 40, 61)
+    X, y, _ = O.synth_batch(19, 140, 40, 333, 4, 11, seed=62, Tmin=100)
+    L = y.shape[1]
+    bits = [bool(b) or i == 0 or i >= L - 2 for i, b in enumerate(np.random.default_rng(6).random(L - 1) < 0.5)]
+    out = []
+    for fused in (1, 0):
+        e = _engine(cfg, 40, P)
+        e.set_option("dec_fused", fused)
+        e.set_option("seed", 5)
+        loss = float(e.forward_loss(X, y, use_true=bits, noise_sigma=0.25))
+        am = e.step_argmax().cpu().numpy()
+        e.backward()
+        out.append((loss, am, e.grads.cpu().numpy().copy()))
+    assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[1][0])
+    assert (out[0][1] == out[1][1]).all()
+    assert np.abs(out[0][2] - out[1][2]).max() <= 1e-4 * np.abs(out[1][2]).max()
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_golden_fixtures(dev, name):
     cfg, D, P, z = load_case(name)
