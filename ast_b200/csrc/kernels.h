@@ -63,6 +63,9 @@ int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
                  unsigned long long seed, bool exact);
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact);
+// tcgen05 versions (lstm_seq_tc.cu): TF32 mode, h == 256, chains already split into 16-row slices
+int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);
+int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);
 
 // ---- decoder step kernels ------------------------------------------------------------------------
 enum { EPI_NONE = 0, EPI_TANH = 1, EPI_LSTM = 2, EPI_TANHBWD = 3, EPI_CELLBWD = 4 };

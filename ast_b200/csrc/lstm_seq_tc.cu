@@ -1,0 +1,411 @@
+// Persistent LSTM recurrence on 5th-generation tensor cores (TF32 training mode, per-direction h = 256).
+//
+// Same cluster organisation as lstm_seq.cu (8 CTAs per chain, each owning 32 hidden units = 128 gate rows, W_h
+// resident in shared memory for all T steps, h exchanged with st.async + mbarrier complete_tx), but the per-step
+// GEMM is issued as tcgen05.mma with the operands SWAPPED: gates^T (128 gate rows x 16 batch rows) =
+// W_slice (128 x 256, the M side, K-major, resident) · h^T (256 x 16, the N side).  With the weight on the
+// M = 128 side the tensor core runs at full rate (32 MMAs of 128x16x8, ~8 cycles each) instead of the legacy
+// mma.sync path, whose issue rate (~16 cycles per m16n8k8 per SM sub-partition, measured) made the recurrent
+// GEMM cost ~2050 cycles per step.  The fp32 accumulator lives in TMEM (16 columns) and is read back with
+// tcgen05.ld for the fused gate / cell / dropout epilogue.
+//
+// Warp roles: warps 0..7 = epilogue (gates, cell, sends, bookkeeping), warp 8 = MMA issuer.  The issuer does
+// nothing else, so the tensor core starts the moment the last slice of h lands; its descriptors are precomputed
+// and advanced by immediates (building them per MMA cost ~66 cycles each in a single dependent thread, measured).
+//
+// Operands are rounded to TF32 with round-to-nearest when they are written to shared memory (W once, h by the
+// producing CTA), so the tensor core never truncates.  Backward uses the same trick for dh^T (256 x 16) =
+// W_slice^T (256 x 128, M-major operand in the SWIZZLE_128B_BASE32B layout) · dG^T (128 x 16).
+#include "cluster_dev.cuh"
+#include "kernels.h"
+
+namespace ast {
+
+constexpr int TNC = 8;           // CTAs per cluster
+constexpr int TH = 256;          // per-direction hidden size handled by this kernel
+constexpr int TU = TH / TNC;     // 32 hidden units per CTA
+constexpr int TROWS = 16;        // batch rows per chain = UMMA N
+constexpr int TC_EPI = 256;      // epilogue threads
+constexpr int TC_THREADS = TC_EPI + 32;
+
+__device__ __forceinline__ float rnd_tf32(float x) { return __uint_as_float(f2tf32(x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }   // epilogue warps only
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B operand made of k-blocks of 32 floats:
+// [kb][rows][128 B], 16-byte chunks XOR-ed with (row % 8)
+__device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows_per_block) {
+    const int kb = k >> 5, c = (k & 31) >> 2;
+    return (uint32_t)(kb * rows_per_block * 128 + row * 128 + ((c ^ (row & 7)) << 4) + ((k & 3) << 2));
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+constexpr uint32_t FW_A_BYTES = 8 * 128 * 128;          // W slice: 8 k-blocks x 128 gate rows x 128 B
+constexpr uint32_t FW_H_BYTES = 8 * TROWS * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B
+constexpr uint32_t FW_XG_BYTES = 4 * TROWS * TU * 4;    // gate exchange [gate][batch][unit]
+constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + 64 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed) {
+    const int rank = (int)cluster_rank();
+    const LstmChain a = ch.c[blockIdx.x / TNC];
+    constexpr int h = TH, H4 = 4 * TH;
+    const int nb = a.nb, b0 = a.b0;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = sm;                                  // resident W slice, rows p = 32*gate + unit
+    uint8_t* sH = sm + FW_A_BYTES;                     // [2] h buffers (UMMA B operand)
+    float* xg = reinterpret_cast<float*>(sm + FW_A_BYTES + 2 * FW_H_BYTES);
+    uint64_t* mbar_h = reinterpret_cast<uint64_t*>(sm + FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES);   // [2]
+    uint64_t* mbar_mma = mbar_h + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_h + 3);
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // resident weight slice: smem row p = 32*gate + unit  <-  W_lat row 4*(32*rank + unit) + gate, rounded to TF32
+    for (int idx = tid; idx < 128 * (h / 4); idx += TC_THREADS) {
+        const int p = idx / (h / 4), k4 = idx % (h / 4);
+        const int gate = p >> 5, unit = p & 31;
+        float4 v = *reinterpret_cast<const float4*>(a.Wl + (size_t)(4 * (TU * rank + unit) + gate) * h + k4 * 4);
+        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
+        *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) = v;
+    }
+    for (int idx = tid; idx < (int)(2 * FW_H_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sH)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&mbar_h[0], 1); mbar_init(&mbar_h[1], 1); mbar_init(mbar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(tmem_slot)), "n"(32));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * (h / 4); idx += TC_THREADS) {          // h_{-1} (slot 0 of Hs) into buffer 0
+        const int m = idx / (h / 4), k4 = idx % (h / 4);
+        float4 v = *reinterpret_cast<const float4*>(a.Hs + (size_t)(b0 + m) * h + k4 * 4);
+        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
+        *reinterpret_cast<float4*>(sH + kmajor_off(m, 4 * k4, TROWS)) = v;
+    }
+    fence_proxy_async();                  // generic-proxy writes of the operands -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sA_addr = saddr(sA), sH_addr = saddr(sH);
+    cluster_sync_all();                   // all CTAs have initialised buffers / barriers before any remote store
+
+    if (w == 8) {
+        // ===== MMA issuer: one thread, nothing else on its plate =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, TROWS, false, false);
+            const uint64_t a0 = umma_smem_desc(sA_addr, 16, 1024, 2);
+            const uint64_t b0d = umma_smem_desc(sH_addr, 16, 1024, 2);
+            for (int i = 0; i < T; ++i) {
+                const int cur = i & 1;
+                if (i + 1 < T) mbar_expect_tx(&mbar_h[cur ^ 1], FW_H_BYTES);    // arm the buffer this step fills
+                if (i > 0) mbar_wait(&mbar_h[cur], ((i - 1) >> 1) & 1);         // all 8 slices of h_{i-1} have landed
+                fence_proxy_async();
+                tc_fence_after();
+                const uint64_t bcur = b0d + (uint64_t)((cur * FW_H_BYTES) >> 4);
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_tf32_ss(tmem_base, a0 + (uint64_t)((kb * 16384 + ks * 32) >> 4),
+                                     bcur + (uint64_t)((kb * (TROWS * 128) + ks * 32) >> 4), idesc, (kb | ks) ? 1u : 0u);
+                umma_commit_arrive(mbar_mma);
+            }
+        }
+    } else {
+        // ===== epilogue: thread (w, lane) owns hidden unit `lane`, batch rows 2w and 2w+1 =====
+        const int ju = TU * rank + lane;
+        float creg[2];
+        float4 gx[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int b = 2 * w + j;
+            creg[j] = b < nb ? a.Cs[(size_t)(b0 + b) * h + ju] : 0.f;
+            gx[j] = b < nb ? *reinterpret_cast<const float4*>(a.G + (size_t)(b0 + b) * H4 + 4 * ju) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int gate = w & 3, bh = w >> 2;          // TMEM quadrant = gate; this warp reads batch columns 8*bh..+7
+        for (int i = 0; i < T; ++i) {
+            const int nxt = (i & 1) ^ 1;
+            mbar_wait(mbar_mma, i & 1);
+            tc_fence_after();
+            {
+                float v[8];
+                tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + 8 * bh, v);
+                tc_fence_before();
+#pragma unroll
+                for (int b = 0; b < 8; ++b) xg[(gate * TROWS + 8 * bh + b) * TU + lane] = v[b];
+            }
+            epi_barrier();
+            float4 actv[2]; float cv[2], hv[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = 2 * w + j;
+                const float ga = fast_tanh(xg[(0 * TROWS + b) * TU + lane] + gx[j].x);
+                const float gi = fast_sigmoid(xg[(1 * TROWS + b) * TU + lane] + gx[j].y);
+                const float gf = fast_sigmoid(xg[(2 * TROWS + b) * TU + lane] + gx[j].z);
+                const float go = fast_sigmoid(xg[(3 * TROWS + b) * TU + lane] + gx[j].w);
+                const float c = ga * gi + gf * creg[j];
+                const float hval = b < nb ? go * fast_tanh(c) : 0.f;
+                actv[j] = make_float4(ga, gi, gf, go); cv[j] = c; hv[j] = hval;
+                if (b < nb) creg[j] = c;
+            }
+            if (i + 1 < T) {
+                // quad of lanes = 4 consecutive units x 2 batch rows = two 16-byte chunks; lane l sends chunk (l & 1)
+                // to CTAs 4*((l >> 1) & 1) .. +3  (TF32-rounded: this copy is the next step's MMA operand)
+                const int qb = lane & ~3;
+                float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float r = rnd_tf32(hv[j]);
+                    float4 t;
+                    t.x = __shfl_sync(0xffffffffu, r, qb + 0);
+                    t.y = __shfl_sync(0xffffffffu, r, qb + 1);
+                    t.z = __shfl_sync(0xffffffffu, r, qb + 2);
+                    t.w = __shfl_sync(0xffffffffu, r, qb + 3);
+                    if ((lane & 1) == j) mine = t;
+                }
+                const int b = 2 * w + (lane & 1);
+                const uint32_t dst = sH_addr + nxt * FW_H_BYTES + kmajor_off(b, TU * rank + 4 * (lane >> 2), TROWS);
+                const uint32_t bar = saddr(&mbar_h[nxt]);
+                const int d0 = 4 * ((lane >> 1) & 1);
+#pragma unroll
+                for (int d = 0; d < 4; ++d) st_async_v4(mapa(dst, d0 + d), mine, mapa(bar, d0 + d));
+            }
+            // bookkeeping: overlaps the other CTAs' sends and the next step's MMA
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = 2 * w + j;
+                if (b < nb) {
+                    const size_t r = (size_t)i * B + b0 + b;
+                    *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = actv[j];
+                    a.Cs[(r + B) * h + ju] = cv[j];
+                    a.Hs[(r + B) * h + ju] = hv[j];
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    a.out[(long long)i * a.out_si + (long long)(b0 + b) * a.out_sb + ju] = hv[j] * dm;
+                    if (i + 1 < T) gx[j] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32));
+    cluster_sync_all();
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+constexpr uint32_t BW_A_BYTES = 8 * 128 * 128;          // W slice as M-major operand: 8 unit-chunks x 128 gate rows x 128 B
+constexpr uint32_t BW_G_BYTES = 4 * TROWS * 128;        // dG: 4 k-blocks x 16 batch rows x 128 B (K-major)
+constexpr uint32_t BW_R_BYTES = TNC * TU * TROWS * 4;   // one reduce buffer [src][unit][batch]
+constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + 64 + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed) {
+    const int rank = (int)cluster_rank();
+    const LstmChain a = ch.c[blockIdx.x / TNC];
+    constexpr int h = TH, H4 = 4 * TH;
+    const int nb = a.nb, b0 = a.b0;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = sm;                                   // A[m = unit][k = gate row p] (M-major, SWIZZLE_128B_BASE32B)
+    uint8_t* sG = sm + BW_A_BYTES;                      // B[n = batch][k = gate row p] (K-major, SWIZZLE_128B)
+    float* red = reinterpret_cast<float*>(sm + BW_A_BYTES + BW_G_BYTES);     // [2][src][unit][batch]
+    uint64_t* mbar_r = reinterpret_cast<uint64_t*>(sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES);   // [2]
+    uint64_t* mbar_mma = mbar_r + 2;
+    uint64_t* mbar_g = mbar_r + 3;                      // dG operand written by all 256 epilogue threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_r + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // W slice rows p = 4*unit + gate (natural order, = dG's k index), all 256 unit columns n:
+    // chunk j = n/32 at j*16 KB, k-row p at p*128 B, 32-byte sub-chunk ((n%32)/8) XOR (p % 4)
+    for (int idx = tid; idx < 128 * (h / 4); idx += TC_THREADS) {
+        const int p = idx / (h / 4), n4 = idx % (h / 4), n = 4 * n4;
+        float4 v = *reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n);
+        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
+        const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
+        *reinterpret_cast<float4*>(sA + off) = v;
+    }
+    for (int idx = tid; idx < (int)(BW_G_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sG)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < (int)(2 * BW_R_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(red)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&mbar_r[0], 1); mbar_init(&mbar_r[1], 1); mbar_init(mbar_mma, 1); mbar_init(mbar_g, TC_EPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(tmem_slot)), "n"(32));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sA_addr = saddr(sA), sG_addr = saddr(sG), red_addr = saddr(red);
+    cluster_sync_all();
+
+    if (w == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, TROWS, true, false);
+            const uint64_t a0 = umma_smem_desc(sA_addr, 16384, 512, 1);
+            const uint64_t g0 = umma_smem_desc(sG_addr, 16, 1024, 2);
+            int step = 0;
+            for (int i = T - 1; i >= 1; --i, ++step) {
+                mbar_expect_tx(&mbar_r[i & 1], BW_R_BYTES);       // arm the reduce buffer this step's sends fill
+                mbar_wait(mbar_g, step & 1);                      // dG_i operand complete in smem
+                tc_fence_after();
+                // dh^T (256 x 16) = W_slice^T (256 x 128) · dG^T (128 x 16): two M = 128 halves, 16 k-steps each
+#pragma unroll
+                for (int hm = 0; hm < 2; ++hm)
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks)
+                        umma_tf32_ss(tmem_base + hm * TROWS, a0 + (uint64_t)((hm * 4 * 16384 + ks * 1024) >> 4),
+                                     g0 + (uint64_t)(((ks >> 2) * (TROWS * 128) + (ks & 3) * 32) >> 4), idesc, ks ? 1u : 0u);
+                umma_commit_arrive(mbar_mma);
+            }
+        }
+    } else {
+        // ===== epilogue / elementwise: pair e -> batch row m = idx % 16, unit ul = idx / 16 =====
+        float dc[2];
+        float4 p_act[2]; float p_c[2], p_cp[2], p_dout[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid + e * TC_EPI;
+            const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
+            const bool v = m < nb;
+            dc[e] = (v && a.dc_fin) ? a.dc_fin[(size_t)(b0 + m) * a.ld_dc_fin + ju] : 0.f;
+            if (v) {
+                const size_t r = (size_t)(T - 1) * B + b0 + m;
+                p_act[e] = *reinterpret_cast<const float4*>(a.G + r * H4 + 4 * ju);
+                p_c[e] = a.Cs[(r + B) * h + ju]; p_cp[e] = a.Cs[r * h + ju];
+                p_dout[e] = a.dout[(long long)(T - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
+            } else { p_act[e] = make_float4(0.f, 0.f, 0.f, 0.f); p_c[e] = p_cp[e] = p_dout[e] = 0.f; }
+        }
+        int step = 0;
+        for (int i = T - 1; i >= 0; --i, ++step) {
+            const int buf = i & 1;
+            const bool send = i > 0;
+            const float* rprev = red + (size_t)(buf ^ 1) * (BW_R_BYTES / 4);
+            if (i < T - 1) mbar_wait(&mbar_r[buf ^ 1], ((T - 2 - i) >> 1) & 1);     // partial dh of step i+1 from all CTAs
+            // 1. dG_t for the owned units (K-major UMMA operand, TF32-rounded)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int idx = tid + e * TC_EPI;
+                const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
+                float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < nb) {
+                    float dh;
+                    if (i == T - 1) {
+                        dh = a.dh_fin ? a.dh_fin[(size_t)(b0 + m) * a.ld_dh_fin + ju] : 0.f;
+                    } else {
+                        dh = 0.f;
+#pragma unroll
+                        for (int s = 0; s < TNC; ++s) dh += rprev[(s * TU + ul) * TROWS + m];
+                    }
+                    const size_t r = (size_t)i * B + b0 + m;
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    dh += p_dout[e] * dm;
+                    const float4 act = p_act[e];
+                    const float c = p_c[e], cp = p_cp[e];
+                    const float tc = fast_tanh(c);
+                    const float dct = dc[e] + dh * act.w * (1.f - tc * tc);
+                    dg.x = dct * act.y * (1.f - act.x * act.x);
+                    dg.y = dct * act.x * act.y * (1.f - act.y);
+                    dg.z = dct * cp * act.z * (1.f - act.z);
+                    dg.w = dh * tc * act.w * (1.f - act.w);
+                    dc[e] = dct * act.z;
+                    p_act[e] = dg;
+                }
+                if (send)
+                    *reinterpret_cast<float4*>(sG + kmajor_off(m, 4 * ul, TROWS)) =
+                        make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w));
+            }
+            if (send) {
+                fence_proxy_async();
+                mbar_arrive(mbar_g);              // hand the operand to the issuer warp
+            }
+            // 2. bookkeeping while the tensor core works: write dG_t in place, prefetch step i-1
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int idx = tid + e * TC_EPI;
+                const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
+                if (m < nb) {
+                    const size_t r = (size_t)i * B + b0 + m;
+                    *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = p_act[e];
+                    if (i > 0) {
+                        const size_t rp = r - B;
+                        p_act[e] = *reinterpret_cast<const float4*>(a.G + rp * H4 + 4 * ju);
+                        p_c[e] = p_cp[e]; p_cp[e] = a.Cs[rp * h + ju];
+                        p_dout[e] = a.dout[(long long)(i - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
+                    }
+                }
+            }
+            if (send) {
+                // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
+                mbar_wait(mbar_mma, step & 1);
+                tc_fence_after();
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (w >> 2) * TROWS, v);
+                tc_fence_before();
+                const int owner = (w >> 2) * 4 + (w & 3);
+                const uint32_t dst = mapa(red_addr + (uint32_t)(((buf * TNC + rank) * TU + lane) * TROWS * 4), owner);
+                const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_async_v4(dst + 16 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), bar);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32));
+    cluster_sync_all();
+}
+
+template <class KernT>
+static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B,
+                     float drop, unsigned long long seed) {
+    AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nchains * TNC);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TNC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ch, T, B, drop, seed));
+    ++g_kernel_launches;
+    return 0;
+}
+
+// `ch` already holds 16-row chains (lstm_seq.cu::expand_chains).  Preconditions checked by the caller: h == 256.
+int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {
+    return launch_tc(lstm_seq_fwd_tc_kernel, st, nchains, FW_SMEM, ch, T, B, drop, seed);
+}
+int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {
+    return launch_tc(lstm_seq_bwd_tc_kernel, st, nchains, BW_SMEM, ch, T, B, drop, seed);
+}
+
+}  // namespace ast

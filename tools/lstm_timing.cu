@@ -27,14 +27,56 @@
 // elementwise, written in place over the saved activations, multiplied by the resident W_h slice and
 // reduce-scattered across the cluster (same st.async / mbarrier scheme).  Weight gradients are batched GEMMs
 // over the saved dG.
-#include "cluster_dev.cuh"
-#include "kernels.h"
+#include "/root/repo/ast_b200/csrc/common.cuh"
+#include "/root/repo/ast_b200/csrc/kernels.h"
 
 namespace ast {
-
+__device__ long long* g_dbg = nullptr;
+unsigned long long g_kernel_launches = 0;
+void set_last_error(const char*, ...) {}
 constexpr int NC = 8;            // CTAs per cluster
 constexpr int LTHREADS = 256;
 constexpr int MROWS = 16;        // batch rows per chain (one mma M tile)
+
+// ---- cluster / mbarrier / st.async PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LD_%=;\n"
+        "bra LW_%=;\n"
+        "LD_%=:\n"
+        "}\n" ::"r"(saddr(bar)), "r"(parity) : "memory");
+}
+// 16-byte / 8-byte asynchronous store into another CTA's shared memory, completing bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+                 "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, float2 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(rbar) : "memory");
+}
 
 // ---- activations -------------------------------------------------------------------------------------
 template <bool EXACT> __device__ __forceinline__ float act_sigmoid(float x) {
@@ -123,11 +165,13 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
     const int ksteps = h >> 3;
     if (wact) {
         for (int i = 0; i < T; ++i) {
+            long long tk[8]; tk[0] = clock64();
             const int cur = i & 1, nxt = cur ^ 1;
             const float* hc = hb + (size_t)cur * MROWS * ldw;
             if (tid == 0 && i + 1 < T) mbar_expect_tx(&mbar[nxt], tx_bytes);     // arm the buffer this step fills
             if (i > 0) mbar_wait(&mbar[cur], ((i - 1) >> 1) & 1);                // all 8 slices of h_{i-1} have landed
 
+            tk[1] = clock64();
             float acc[2][4][4];           // [tile: (a,i) | (f,o)][independent k-chain][mma C fragment]
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2)
@@ -150,6 +194,7 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                     mma_frag<EXACT>(acc[1][pp], fa, fb1);
                 }
             }
+            tk[2] = clock64();
             float pre[2][4];
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2)
@@ -184,6 +229,7 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                     for (int d = 0; d < 2; ++d) st_async_v4(mapa(dst, 2 * q + d), v4, mapa(bar_local, 2 * q + d));
                 }
             }
+            tk[3] = clock64();
             // bookkeeping off the critical path: saved activations / states, layer output, next input projection
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -198,6 +244,8 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                     if (i + 1 < T) gx[hf] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);   // prefetch
                 }
             }
+            tk[4] = clock64();
+            if (g_dbg && tid == 0 && rank == 0 && blockIdx.x < NC && i >= 100 && i < 104) for (int z = 0; z < 5; ++z) g_dbg[(i - 100) * 8 + z] = tk[z];
         }
     }
     cluster_sync_all();                   // nobody exits while a peer could still address its shared memory
@@ -258,11 +306,13 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
     const uint32_t tx_bytes = (uint32_t)(NC * MROWS * U * sizeof(float));
     const int ntpw = (h >> 3) / (LTHREADS / 32);   // n-tiles (8 output columns) per warp: h/64
     for (int i = T - 1; i >= 0; --i) {
+        long long tb[8]; tb[0] = clock64();
         const int buf = i & 1;
         const bool send = (i > 0) || (a.dh0 != nullptr);
         const float* rprev = red + (size_t)(buf ^ 1) * NC * MROWS * U;
         if (tid == 0 && send) mbar_expect_tx(&mbar[buf], tx_bytes);
         if (i < T - 1) mbar_wait(&mbar[buf ^ 1], ((T - 2 - i) >> 1) & 1);      // partial dh of step i+1 from all 8 CTAs
+        tb[1] = clock64();
         __syncthreads();                  // every warp is done reading dgs of the previous step
         // 1. dG_t for the owned units
 #pragma unroll
@@ -298,7 +348,9 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                 *reinterpret_cast<float4*>(dgs + (size_t)m * ldg + 4 * ul) = dg;
             }
         }
+        tb[2] = clock64();
         __syncthreads();
+        tb[3] = clock64();
         if (send) {
             // 2. partial dh_{t-1}[m][n] = sum_p dG[m][p] * W[p][n] over this CTA's K4 gate rows, two n-tiles x two
             //    independent k-chains at a time; 3. reduce-scatter to the owner of columns n (CTA n / U)
@@ -343,6 +395,7 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                 }
             }
         }
+        tb[4] = clock64();
         // 4. off the critical path: write dG_t in place, prefetch step i-1
 #pragma unroll
         for (int e = 0; e < MAXE; ++e) {
@@ -359,6 +412,8 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                 }
             }
         }
+        tb[5] = clock64();
+        if (g_dbg && tid == 0 && rank == 0 && blockIdx.x < NC && i >= 100 && i < 104) for (int z = 0; z < 6; ++z) g_dbg[32 + (i - 100) * 8 + z] = tb[z];
     }
     // gradients w.r.t. the initial state (slot 0), when requested
     if (a.dh0 || a.dc0) {
@@ -431,7 +486,6 @@ int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
                  unsigned long long seed, bool exact) {
     LstmChains ex{}; int n = 0;
     AST_TRY(expand_chains("lstm_seq_fwd", ch, nchains, T, B, h, ex, n));
-    if (!exact && h == 256) return lstm_seq_fwd_tc(st, ex, n, T, B, drop, seed);     // tcgen05 path (TF32 training mode)
     const size_t smem = fwd_smem(h);
     return exact ? launch_cluster(lstm_seq_fwd_kernel<true>, st, n, smem, ex, T, B, h, drop, seed)
                  : launch_cluster(lstm_seq_fwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);
@@ -441,12 +495,36 @@ int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
                  unsigned long long seed, bool exact) {
     LstmChains ex{}; int n = 0;
     AST_TRY(expand_chains("lstm_seq_bwd", ch, nchains, T, B, h, ex, n));
-    bool wants_init_grads = false;
-    for (int c = 0; c < n; ++c) wants_init_grads |= (ex.c[c].dh0 != nullptr) || (ex.c[c].dc0 != nullptr);
-    if (!exact && h == 256 && !wants_init_grads) return lstm_seq_bwd_tc(st, ex, n, T, B, drop, seed);
     const size_t smem = bwd_smem(h);
     return exact ? launch_cluster(lstm_seq_bwd_kernel<true>, st, n, smem, ex, T, B, h, drop, seed)
                  : launch_cluster(lstm_seq_bwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);
 }
 
 }  // namespace ast
+
+int main() {
+    using namespace ast;
+    const int T = 250, B = 16, h = 256;
+    float *G, *W, *Hs, *Cs, *out; long long* dbg;
+    cudaMalloc(&G, sizeof(float) * T * B * 4 * h); cudaMalloc(&W, sizeof(float) * 4 * h * h);
+    cudaMalloc(&Hs, sizeof(float) * (T + 1) * B * h); cudaMalloc(&Cs, sizeof(float) * (T + 1) * B * h); cudaMalloc(&out, sizeof(float) * T * B * h);
+    cudaMalloc(&dbg, sizeof(long long) * 64);
+    cudaMemset(G, 0, sizeof(float) * T * B * 4 * h); cudaMemset(W, 0, sizeof(float) * 4 * h * h); cudaMemset(Hs, 0, sizeof(float) * (T + 1) * B * h); cudaMemset(Cs, 0, sizeof(float) * (T + 1) * B * h);
+    cudaMemset(out, 0, sizeof(float) * T * B * h);
+    cudaMemcpyToSymbol(g_dbg, &dbg, sizeof(dbg));
+    LstmChains ch{}; ch.c[0].G = G; ch.c[0].Wl = W; ch.c[0].Hs = Hs; ch.c[0].Cs = Cs; ch.c[0].out = out; ch.c[0].dout = out; ch.c[0].out_si = B * h; ch.c[0].out_sb = h;
+    for (int exact = 0; exact < 2; ++exact) {
+        for (int rep = 0; rep < 2; ++rep) lstm_seq_fwd(0, ch, 1, T, B, h, 0.f, 0, exact);
+        for (int rep = 0; rep < 2; ++rep) lstm_seq_bwd(0, ch, 1, T, B, h, 0.f, 0, exact);
+        cudaDeviceSynchronize();
+        long long hd[64]; cudaMemcpy(hd, dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+        printf("exact=%d FWD cycles: arm+wait | mma_loop | gates+send | bookkeeping || step-to-step\n", exact);
+        for (int i = 0; i < 4; ++i) { long long* t = hd + i * 8;
+            printf("  step %d: %lld | %lld | %lld | %lld || %lld\n", 100 + i, t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], i < 3 ? hd[(i+1)*8]-t[0] : 0LL); }
+        printf("exact=%d BWD cycles: arm+wait | sync+elementwise | sync | mma+send | bookkeeping || step-to-step\n", exact);
+        for (int i = 3; i >= 0; --i) { long long* t = hd + 32 + i * 8;
+            printf("  step %d: %lld | %lld | %lld | %lld | %lld || %lld\n", 100 + i, t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[5]-t[4], i > 0 ? hd[32+(i-1)*8]-t[0] : 0LL); }
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
