@@ -164,22 +164,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((NB ? 1u : 0u) << 16) |
                                    ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            // Base descriptors are built once; per MMA only the 14-bit start-address field advances (an add of an
+            // immediate): building descriptors inside the loop cost ~66 cycles per MMA in this single dependent thread.
+            // K-major: advance 32 B inside the 128 B swizzle row; SBO = 8 rows * 128 B.
+            // MN-major: each k-step is the next 8-row group (1024 B); LBO = stride between 32-wide MN chunks.
+            const uint64_t a_base = TA ? make_smem_desc(smem_u32(sA), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sA), 16, 1024, 2);
+            const uint64_t b_base = NB ? make_smem_desc(smem_u32(sB), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sB), 16, 1024, 2);
+            constexpr uint32_t a_kstep = (TA ? 1024 : 32) >> 4, b_kstep = (NB ? 1024 : 32) >> 4;
+            int s = 0; uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % TSTAGES;
-                const uint32_t ph = (i / TSTAGES) & 1;
                 mbar_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(sA + s * STAGE_A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + s * STAGE_B_BYTES);
+                const uint64_t ad0 = a_base + (uint64_t)(s * (STAGE_A_BYTES >> 4));
+                const uint64_t bd0 = b_base + (uint64_t)(s * (STAGE_B_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < TBK / 8; ++k) {
-                    // K-major: advance 32 B inside the 128 B swizzle row; SBO = 8 rows * 128 B.
-                    // MN-major: each k-step is the next 8-row group (1024 B); LBO = stride between 32-wide MN chunks.
-                    const uint64_t ad = TA ? make_smem_desc(a_addr + k * 1024, TBK * 128, 512, 1) : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-                    const uint64_t bd = NB ? make_smem_desc(b_addr + k * 1024, TBK * 128, 512, 1) : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-                    umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < TBK / 8; ++k)
+                    umma_tf32(tmem_base, ad0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+                if (++s == TSTAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(tmem_full);              // accumulator complete
         }
@@ -188,24 +190,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int wq = warp & 3;                 // TMEM lane quadrant this warp may access
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + wq * 32 + lane;
+        // Each thread holds one accumulator ROW (32 columns per tcgen05.ld); a per-warp 32x33 smem transpose (the
+        // pipeline stages are free once tmem_full fired) turns the stores into full 128-byte row segments.
+        float* stg = reinterpret_cast<float*>(sA) + wq * (32 * 33);
 #pragma unroll 1
         for (int c = 0; c < TBN / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
-            if (m < p.M && nkb > 0) {
-                float* crow = p.C + (size_t)m * p.ldc;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c * 32 + j;
-                    if (n < p.N) {
-                        float x = v[j];
-                        if (p.bias && blockIdx.z == 0) x += p.bias[n];
-                        if (p.atomic) atomicAdd(crow + n, x);
-                        else crow[n] = (p.beta != 0.f) ? x + p.beta * crow[n] : x;
-                    }
+            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int n = n0 + c * 32 + lane;
+            if (n < p.N && nkb > 0) {
+                const float bv = (p.bias && blockIdx.z == 0) ? p.bias[n] : 0.f;
+                const int mrow0 = m0 + wq * 32;
+                const int rmax = min(32, p.M - mrow0);
+                float* cp = p.C + (size_t)mrow0 * p.ldc + n;
+                for (int r = 0; r < rmax; ++r, cp += p.ldc) {
+                    const float x = stg[r * 33 + lane] + bv;
+                    if (p.atomic) atomicAdd(cp, x);
+                    else *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
                 }
             }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
