@@ -12,6 +12,26 @@ namespace cg = cooperative_groups;
 
 namespace ast {
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+// grid barrier + optional timestamp (phase-timing probe, tools/dec_phase_times.py)
+// Grid barrier on one monotonically increasing global counter (zeroed by the host before the launch; the cooperative
+// launch guarantees co-residency).  One release-add per CTA, one acquire-poll loop in thread 0: measured ~X us against
+// cooperative_groups' grid.sync() (tools/dec_phase_times.py prints both).
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+#define GRID_SYNC() do { if (p.bar) grid_barrier(p.bar, bar_target); else grid.sync(); \
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer(); p.prof[0] = (unsigned long long)nprof; } } while (0)
+
 // x0[s][b][0:E] = Emb[word] * dropmask ; words_used[s][b] = word ; (s == 0) x0[0][b][E:] = 0
 __device__ __forceinline__ void embed_row(const DecSeq& p, int s, int b, int word) {
     word = min(max(word, 0), p.V - 1);
@@ -29,6 +49,14 @@ template <int MT, bool EXACT>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 dec_seq_fwd_kernel(DecSeq p) {
     cg::grid_group grid = cg::this_grid();
+    int nprof = 0;
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[1] = gtimer();
+    nprof = 1;
+    unsigned bar_target = 0;
+    if (p.prof) {      // barrier micro-benchmark: 4 x cooperative_groups, then 4 x the counter barrier
+        for (int i = 0; i < 4; ++i) { grid.sync(); if (blockIdx.x == 0 && threadIdx.x == 0) p.prof[++nprof] = gtimer(); }
+        if (p.bar) for (int i = 0; i < 4; ++i) { grid_barrier(p.bar, bar_target); if (blockIdx.x == 0 && threadIdx.x == 0) p.prof[++nprof] = gtimer(); }
+    }
     __shared__ SkinnySmem sm;
     __shared__ float scratch[32];
     __shared__ int iscratch[32];
@@ -38,7 +66,7 @@ dec_seq_fwd_kernel(DecSeq p) {
     const int ldx0 = E + A;
 
     for (int b = cta; b < B; b += ncta) embed_row(p, 0, b, p.y[(size_t)b * L]);
-    grid.sync();
+    GRID_SYNC();
 
     for (int s = 0; s < S; ++s) {
         // ---- LSTM stack (seq2seq.py:375) ----------------------------------------------------------------
@@ -57,7 +85,7 @@ dec_seq_fwd_kernel(DecSeq p) {
             else { a.hd_out = p.hdd[l] + (size_t)s * B * H; a.ld_hd = H; }
             a.drop = p.drop_rnn; a.seed = p.seed; a.drop_stream = 16 + l; a.drop_base = (size_t)s * B * H;
             for (int g = cta; g < (4 * H) / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         const float* htop = p.cvh + (size_t)s * B * 2 * H + H;
         float* q = p.q + (size_t)s * B * H;
@@ -66,20 +94,20 @@ dec_seq_fwd_kernel(DecSeq p) {
             a.X[0] = htop; a.ldx[0] = 2 * H; a.K[0] = H; a.W[0] = p.Wa; a.ldw[0] = H; a.bias = p.ba;
             a.B = B; a.N = H; a.epi = EPI_NONE; a.Y = q; a.ldy = H;
             for (int g = cta; g < H / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         const long long ebs = (long long)Tp * H;
         {   // scores (:342)
             const int ntb = (Tp + 7) / 8;
             for (int i = cta; i < ntb * B; i += ncta) attn_dot_block(p.enc, ebs, q, H, p.scores, Tp, H, i / ntb, i % ntb);
-            grid.sync();
+            GRID_SYNC();
         }
         {   // softmax over T' + context (:351-355)
             const int njb = (H + 127) / 128;
             for (int i = cta; i < njb * B; i += ncta)
                 attn_ctx_block(p.enc, ebs, p.scores, p.alpha + (size_t)s * B * Tp, p.cvh + (size_t)s * B * 2 * H, 2 * H, Tp, H,
                                i / njb, i % njb, dsm, dsm + ((Tp + 3) & ~3), scratch);
-            grid.sync();
+            GRID_SYNC();
         }
         {   // ht = tanh(context([cv;h]))  (:386-390); also the next step's input-feeding slot
             SkinnyArgs a{};
@@ -87,7 +115,7 @@ dec_seq_fwd_kernel(DecSeq p) {
             a.B = B; a.N = A; a.epi = EPI_TANH; a.Y = p.ht + (size_t)s * B * A; a.ldy = A;
             if (s + 1 < S) { a.Y2 = p.x0 + (size_t)(s + 1) * B * ldx0 + E; a.ldy2 = ldx0; }
             for (int g = cta; g < A / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         float* z = p.logits + (size_t)s * B * p.Vp;
         {   // logits = out(ht)  (:394)
@@ -95,7 +123,7 @@ dec_seq_fwd_kernel(DecSeq p) {
             a.X[0] = p.ht + (size_t)s * B * A; a.ldx[0] = A; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
             a.B = B; a.N = p.V; a.epi = EPI_NONE; a.Y = z; a.ldy = p.Vp;
             for (int g = cta; g < (p.V + SK_COLS - 1) / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         // softmax-CE (+ gradient in place) + argmax (:448,468) + next decoder input (:431-436)
         for (int b = cta; b < B; b += ncta) {
@@ -108,7 +136,7 @@ dec_seq_fwd_kernel(DecSeq p) {
             }
             __syncthreads();
         }
-        grid.sync();
+        GRID_SYNC();
     }
 }
 
@@ -116,6 +144,14 @@ template <int MT, bool EXACT>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 dec_seq_bwd_kernel(DecSeq p) {
     cg::grid_group grid = cg::this_grid();
+    int nprof = 0;
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[1] = gtimer();
+    nprof = 1;
+    unsigned bar_target = 0;
+    if (p.prof) {      // barrier micro-benchmark: 4 x cooperative_groups, then 4 x the counter barrier
+        for (int i = 0; i < 4; ++i) { grid.sync(); if (blockIdx.x == 0 && threadIdx.x == 0) p.prof[++nprof] = gtimer(); }
+        if (p.bar) for (int i = 0; i < 4; ++i) { grid_barrier(p.bar, bar_target); if (blockIdx.x == 0 && threadIdx.x == 0) p.prof[++nprof] = gtimer(); }
+    }
     __shared__ SkinnySmem sm;
     __shared__ float scratch[32];
     extern __shared__ float dsm[];
@@ -133,19 +169,19 @@ dec_seq_bwd_kernel(DecSeq p) {
             if (s < S - 1) { a.add = p.dxh[0] + E; a.ld_add = ld0; }
             a.aux = p.ht + (size_t)s * B * A; a.ld_aux = A;
             for (int g = cta; g < A / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         {   // dcvh = du . Wc
             SkinnyArgs a{};
             a.X[0] = du; a.ldx[0] = A; a.K[0] = A; a.W[0] = p.WcT; a.ldw[0] = A;
             a.B = B; a.N = 2 * H; a.epi = EPI_NONE; a.Y = p.dcvh; a.ldy = 2 * H;
             for (int g = cta; g < (2 * H) / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         {   // dalpha[b][t] = enc[b][t][:] . dcv[b][:]
             const int ntb = (Tp + 7) / 8;
             for (int i = cta; i < ntb * B; i += ncta) attn_dot_block(p.enc, ebs, p.dcvh, 2 * H, p.dalpha, Tp, H, i / ntb, i % ntb);
-            grid.sync();
+            GRID_SYNC();
         }
         float* dq = p.dq + (size_t)s * B * H;
         {   // softmax / scores / context backward, d_enc accumulation
@@ -153,7 +189,7 @@ dec_seq_bwd_kernel(DecSeq p) {
             for (int i = cta; i < njb * B; i += ncta)
                 attn_bwd_block(p.enc, p.d_enc, ebs, p.alpha + (size_t)s * B * Tp, p.dalpha, p.dcvh, 2 * H, p.q + (size_t)s * B * H, H,
                                dq, H, Tp, H, i / njb, i % njb, dsm, dsm + ((2 * Tp + 3) & ~3), scratch);
-            grid.sync();
+            GRID_SYNC();
         }
         {   // dh_top = dcvh[:, H:] + dq . Wa ; fused: cell backward of the top LSTM layer
             const int l = NL - 1, in = l == 0 ? E + A : H;
@@ -165,7 +201,7 @@ dec_seq_bwd_kernel(DecSeq p) {
             if (s < S - 1) { a.cb_dh_rec = p.dxh[l] + in; a.cb_ld_dh_rec = in + H; }
             a.drop = p.drop_rnn; a.seed = p.seed; a.drop_stream = 16 + l; a.drop_base = (size_t)s * B * H;
             for (int g = cta; g < H / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
         for (int l = NL - 1; l >= 0; --l) {
             // [dx | dh_rec] = dG_l . [W_up | W_lat] ; fused: cell backward of layer l-1 on the dx columns,
@@ -186,7 +222,7 @@ dec_seq_bwd_kernel(DecSeq p) {
                 a.drop = p.drop_embed; a.seed = p.seed; a.drop_stream = 32; a.drop_base = (size_t)s * B * E;
             }
             for (int g = cta; g < (in + H) / SK_COLS; g += ncta) skinny_tile<MT, EXACT>(a, g * SK_COLS, sm);
-            grid.sync();
+            GRID_SYNC();
         }
     }
 }
@@ -199,6 +235,7 @@ static int launch_coop(KernT kern, cudaStream_t st, const DecSeq& p, size_t dsm_
     AST_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SK_THREADS, dsm_bytes));
     AST_CHECK(occ >= 1, "decoder sequence kernel does not fit on an SM");
     DecSeq pp = p;
+    if (pp.bar) AST_CUDA_OK(cudaMemsetAsync(pp.bar, 0, sizeof(unsigned), st));
     void* args[] = {&pp};
     AST_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(sms), dim3(SK_THREADS), args, dsm_bytes, st));
     ++g_kernel_launches;

@@ -102,6 +102,8 @@ struct DecSeq {
     int* words_used; int* argmax_steps;
     float* du; float* dcvh; float* dalpha; float* dq; float* dxh[AST_MAXL]; float* dcd[AST_MAXL]; float* demb;
     float drop_embed, drop_rnn; unsigned long long seed;
+    unsigned* bar;                     // grid-barrier counter (null: cooperative_groups grid.sync)
+    unsigned long long* prof;          // optional phase-timing probe: CTA 0 stores %globaltimer after each grid barrier
 };
 int dec_seq_fwd(cudaStream_t st, const DecSeq& p, bool exact);
 int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);

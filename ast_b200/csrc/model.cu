@@ -69,12 +69,17 @@ struct ast_model {
     int *words_used, *argmax_steps;
     float *WoT, *WcT, *WaT, *WcatT[MAXL];
     float *loss_dev;
+    unsigned long long *dec_prof;      // [2][4096] phase-timing probe of the decoder-sequence kernels (option dec_prof)
+    int dec_prof_on = 0, dec_fast_barrier = 1;
+    unsigned* dec_bar;
     // decode-time state (greedy / beam / decode_step): two banks
     float *st_h[2][MAXL], *st_c[2][MAXL], *st_ht[2], *st_hpost[MAXL], *st_cpost[MAXL];
     float *s_x0, *s_act, *s_hd[MAXL], *s_q, *s_scores, *s_alpha, *s_cvh, *s_htout, *s_logits;
     int *s_words[2], *s_argmax, *g_preds, *g_seen, *g_done;
     float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
     int *h_pinned = nullptr;   // small pinned host mailbox
+    // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr; int overlap = 1;
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
     bool weights_dirty = true, have_fwd = false;
@@ -215,6 +220,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->WcT = a.get<float>((size_t)2 * H * A);
     m->WaT = a.get<float>((size_t)H * H);
     m->loss_dev = a.get<float>(4);
+    m->dec_prof = a.get<unsigned long long>(2 * 4096);
+    m->dec_bar = a.get<unsigned>(64);
     // decode-time
     for (int k = 0; k < 2; ++k) {
         for (int l = 0; l < NL; ++l) { m->st_h[k][l] = a.get<float>((size_t)Bd * H); m->st_c[k][l] = a.get<float>((size_t)Bd * H); }
@@ -452,6 +459,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
     p.row_loss = m->row_loss; p.words_used = m->words_used; p.argmax_steps = m->argmax_steps;
     p.du = m->du; p.dcvh = m->dcvh; p.dalpha = m->dalpha; p.dq = m->dq; p.demb = m->g("embed_dec/W");
     p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
+    p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr;
     return p;
 }
 
@@ -469,7 +477,11 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     for (int l = 0; l < NL; ++l) { hinit[l] = m->Hdec[l]; cinit[l] = m->Cdec[l]; }
     AST_TRY(init_dec_state(m, hinit, cinit, B, st));
     m->y_dev = y; m->use_true_dev = use_true;
-    if (m->dec_fused) AST_TRY(dec_seq_fwd(st, make_dec_seq(m, y, use_true, true), m->exact != 0));
+    if (m->dec_fused) {
+        DecSeq ds = make_dec_seq(m, y, use_true, true);
+        if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof;
+        AST_TRY(dec_seq_fwd(st, ds, m->exact != 0));
+    }
     else for (int s = 0; s < S; ++s) {
         StepIO io{};
         io.Bd = B; io.step = s; io.train = true; io.y = y; io.ldy = L; io.use_true = use_true;
@@ -516,7 +528,11 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
     }
     // ---- decoder BPTT: data gradients step by step -----------------------------------------------
-    if (m->dec_fused) AST_TRY(dec_seq_bwd(st, make_dec_seq(m, m->y_dev, m->use_true_dev, true), ex));
+    if (m->dec_fused) {
+        DecSeq ds = make_dec_seq(m, m->y_dev, m->use_true_dev, true);
+        if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof + 4096;
+        AST_TRY(dec_seq_bwd(st, ds, ex));
+    }
     else for (int s = S - 1; s >= 0; --s) {
         const float* dz = m->logits + (size_t)s * B * Vp;
         float* du = m->du + (size_t)s * B * A;
@@ -556,20 +572,33 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(embed_scatter(st, m->g("embed_dec/W"), m->dxh[0], E + A + H, m->words_used + (size_t)s * B, B, E, s, de,
                               m->cur_seed, 32));
     }
+    // Weight gradients are off the critical path (which is: decoder BPTT -> encoder recurrences top-down, each followed by
+    // its dx GEMM -> CNN backward); they run on the side stream, forked after the kernel that produces their operands and
+    // joined at the end, so they fill the SMs the latency-bound recurrences leave idle.
+    cudaStream_t sw = m->overlap ? m->side : st;
+    int nfork = 0;
+    auto fork = [&]() -> int {
+        if (sw == st) return 0;
+        AST_CUDA_OK(cudaEventRecord(m->ev_fork[nfork], st));
+        AST_CUDA_OK(cudaStreamWaitEvent(sw, m->ev_fork[nfork], 0));
+        ++nfork;
+        return 0;
+    };
     // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
-    AST_TRY(gemm(m, st, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(st, m->logits, Vp, m->g("out/b"), SB, V, false));
-    AST_TRY(gemm(m, st, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(st, m->du, A, m->g("context/b"), SB, A, false));
-    AST_TRY(gemm(m, st, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(st, m->dq, H, m->g("attn_Wa/b"), SB, H, false));
+    AST_TRY(fork());
+    AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, false));
+    AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->du, A, m->g("context/b"), SB, A, false));
+    AST_TRY(gemm(m, sw, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->dq, H, m->g("attn_Wa/b"), SB, H, false));
     for (int l = 0; l < NL; ++l) {
         const std::string ln = lname(l, "dec");
         const int in = m->in_dec(l);
         const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
-        AST_TRY(gemm(m, st, true, false, 4 * H, in, SB, m->actd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(gemm(m, st, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(colsum(st, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, m->actd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
     // ---- encoder BPTT, layer-major top-down; both directions per launch ------------------------------
     for (int l = NL - 1; l >= 0; --l) {
@@ -588,6 +617,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             cc.drop_stream = 1 + 2 * l + d;
         }
         AST_TRY(lstm_seq_bwd(st, ch, 2, Tp, B, h, dr, m->cur_seed, ex));
+        AST_TRY(fork());
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
@@ -595,17 +625,18 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
             const float* Wup = m->p((ln + "/upward/W").c_str());
             AST_TRY(gemm(m, st, false, false, TB, in, 4 * h, m->Genc[l][d], 4 * h, Wup, in, dx, in, nullptr, 0.f, 0, SITE_ENC_DX));
-            AST_TRY(gemm(m, st, true, false, 4 * h, in, TB, m->Genc[l][d], 4 * h, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_ENC_WGRAD));
-            AST_TRY(gemm(m, st, true, false, 4 * h, h, TB, m->Genc[l][d], 4 * h, m->Hs[l][d], h, m->g((ln + "/lateral/W").c_str()), h, nullptr, 0.f, -1, SITE_ENC_WGRAD));
-            AST_TRY(colsum(st, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
+            AST_TRY(gemm(m, sw, true, false, 4 * h, in, TB, m->Genc[l][d], 4 * h, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_ENC_WGRAD));
+            AST_TRY(gemm(m, sw, true, false, 4 * h, h, TB, m->Genc[l][d], 4 * h, m->Hs[l][d], h, m->g((ln + "/lateral/W").c_str()), h, nullptr, 0.f, -1, SITE_ENC_WGRAD));
+            AST_TRY(colsum(sw, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
         }
     }
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
     AST_TRY(bn_bwd_from_rnn(st, m->d_rnn_in, m->d_rnn_rev, m->raw1, m->draw1, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
                             m->p("CNN_1_bn/beta"), m->bnstats, m->g("CNN_1_bn/gamma"), m->g("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
-    AST_TRY(gemm(m, st, true, false, C1, m->K1, M1, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, m->dW1p, m->K1, nullptr, 0.f, -1, SITE_CONV1_WGRAD));
-    AST_TRY(permute_w1(st, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
+    AST_TRY(fork());
+    AST_TRY(gemm(m, sw, true, false, C1, m->K1, M1, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, m->dW1p, m->K1, nullptr, 0.f, -1, SITE_CONV1_WGRAD));
+    AST_TRY(permute_w1(sw, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
     AST_TRY(gemm(m, st, false, false, M1, m->K1, C1, m->draw1, C1, m->W1p, m->K1, m->dA1, m->K1, nullptr, 0.f, 0, SITE_CONV1_DX));
     AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
     AST_TRY(bn_bwd_from_padded(st, m->da0p, m->raw0, m->draw0, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
@@ -613,6 +644,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     AST_TRY(gemm(m, st, true, false, C0, m->ld0, M0, m->draw0, C0, m->cols0, m->ld0, m->dW0pad, m->ld0, nullptr, 0.f, -1, SITE_CONV0_WGRAD));
     const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
     AST_TRY(copy2d(st, m->dW0pad, m->ld0, m->g("CNN_0/W"), K0, C0, K0));
+    if (sw != st) {
+        AST_CUDA_OK(cudaEventRecord(m->ev_join, sw));
+        AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_join, 0));
+    }
     m->have_fwd = false;
     return 0;
 }
@@ -679,6 +714,11 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     AST_CREATE_CHECK(e == cudaSuccess, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     e = cudaMallocHost(&m->h_pinned, 64 * sizeof(int));
     AST_CREATE_CHECK(e == cudaSuccess, "cudaMallocHost: %s", cudaGetErrorString(e));
+    e = cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking);
+    AST_CREATE_CHECK(e == cudaSuccess, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
+    AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
     *out = m;
     return 0;
@@ -687,6 +727,9 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
 int ast_destroy(ast_model* m) {
     if (!m) return 0;
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
+    for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->side) cudaStreamDestroy(m->side);
     delete m;
     return 0;
 }
@@ -732,6 +775,9 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
     else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
     else if (!strcmp(key, "dec_fused")) m->dec_fused = value != 0;
+    else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
+    else if (!strcmp(key, "overlap")) m->overlap = value != 0;
+    else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
     return 0;
@@ -1003,6 +1049,7 @@ int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_fl
     else if (s == "ht") { src = m->ht; n = (size_t)(m->L - 1) * B * m->A; }
     else if (s == "row_loss") { src = m->row_loss; n = (size_t)(m->L - 1) * B; }
     else if (s == "W1p") { src = m->W1p; n = (size_t)m->C1 * m->K1; }
+    else if (s == "dec_prof") { src = reinterpret_cast<const float*>(m->dec_prof); n = 2 * 2 * 4096; }
     else if (s.size() == 4 && (s[0] == 'G' || s[0] == 'H' || s[0] == 'C' || s[0] == 'O') && s[1] == '_') {
         const int l = s[2] - '0', d = s[3] - '0';
         AST_CHECK(l >= 0 && l < m->NL && d >= 0 && d < 2, "debug_fetch: bad layer/dir in %s", name);

@@ -206,29 +206,42 @@ def roofline_dominant(engine, torch, peaks):
             "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms, "traffic": None}
 
 
-def beam_rate(model, torch, T, n_utts, eos_boost, N=10, K=10, max_pred=175):
+def beam_rate(model, torch, T, n_utts, stop_limit, N=10, K=10):
     """beam-10 decode utterances / second (BASELINE metric ii), fp32-faithful mode, host feature buffers
-    in, hypotheses out.  eos_boost > 0 is the 'trained-like' variant (EOS reachable -> realistic lengths)."""
+    in, hypotheses out, on FRESH random-init weights (a model that has just fitted the synthetic unigram law emits EOS
+    at once, which would time a 2-step search).  Random-init hypotheses never end in EOS, so every search runs exactly
+    `stop_limit` steps: 175 (= max_pred, beam.py:104) is the worst case, 40 a typical Fisher hypothesis length."""
     from ast_b200.nn import beam_result_to_entries
     e = model._engine
-    old = e.view("out/b")[2].item()
-    e.view("out/b")[2] += eos_boost
-    e.weights_changed()
     rng = np.random.default_rng(7)
     utts = [rng.standard_normal((1, T, D), dtype=np.float32) for _ in range(n_utts + 1)]
     steps = 0
     for i, x in enumerate(utts):
         if i == 1:
             torch.cuda.synchronize(); t0 = time.perf_counter()
-        r = e.beam_search(x, max_pred, N, K)
+        r = e.beam_search(x, stop_limit, N, K)
         ent = beam_result_to_entries(r)
         if i >= 1:
             steps += r["n_steps"]
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    e.view("out/b")[2] = old
-    e.weights_changed()
-    return {"utts_per_s": n_utts / dt, "T": T, "avg_steps": steps / n_utts, "n_utts": n_utts, "N": N, "K": K}
+    return {"utts_per_s": n_utts / dt, "T": T, "stop_limit": stop_limit, "avg_steps": steps / n_utts, "n_utts": n_utts,
+            "N": N, "K": K, "us_per_beam_step": 1e6 * dt / max(steps, 1)}
+
+
+def beam_cpu_rate(T, stop_limit, n_utts=1, N=10, K=10):
+    """The reference's beam search (nn.py:235-322 restated in the numpy oracle) on the host cores, same inputs."""
+    from oracle import ast_oracle as O
+    cfg = model_cfg()
+    P = O.init_params(cfg, D, seed=0)
+    om = O.OracleModel(cfg, P, dtype=np.float32)
+    rng = np.random.default_rng(7)
+    utts = [rng.standard_normal((1, T, D), dtype=np.float32) for _ in range(n_utts)]
+    t0 = time.perf_counter()
+    for x in utts:
+        om.decode_beam(x, stop_limit, N, K)
+    dt = time.perf_counter() - t0
+    return {"utts_per_s": n_utts / dt, "T": T, "stop_limit": stop_limit, "n_utts": n_utts, "cores": os.cpu_count(), "kind": "port"}
 
 
 def run_ours(args):
@@ -365,10 +378,18 @@ def run_ours(args):
     if world == 1 and not args.no_beam:
         e.set_option("exact", 1)
         train_config.train = False
-        line["beam"] = {"metric": "beam10_decode_utts_per_sec", "mode": "exact fp32-faithful, batch-size-1 utterances (beam.py:111)",
-                        "random_init_worst_case": beam_rate(model, torch, 1000, 6, 0.0),
-                        "trained_like_T1000": beam_rate(model, torch, 1000, 12, 6.0),
-                        "trained_like_T3000": beam_rate(model, torch, 3000, 6, 6.0)}
+        model.init_params(seed=0)                     # fresh weights + BatchNorm running statistics
+        e.bn_state.zero_()
+        for k in ("CNN_0_bn/avg_var", "CNN_1_bn/avg_var"):
+            e.bn_view(k).fill_(1.0)
+        e.weights_changed()
+        line["beam"] = {"metric": "beam10_decode_utts_per_sec", "mode": "exact fp32-faithful, batch-size-1 utterances (beam.py:111), "
+                        "random-init weights: every search runs stop_limit steps",
+                        "T1000_175steps_worst_case": beam_rate(model, torch, 1000, 4, 175),
+                        "T1000_40steps": beam_rate(model, torch, 1000, 12, 40),
+                        "T3000_40steps": beam_rate(model, torch, 3000, 6, 40)}
+        if not args.no_cpu_baseline:
+            line["beam"]["cpu_baseline_T1000_40steps"] = beam_cpu_rate(1000, 40, 2)
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{cpu_done} training steps ({', '.join(cpu_desc)}) of the same batch plan in {cpu_t:.1f}s; "
