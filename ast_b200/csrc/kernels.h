@@ -56,6 +56,7 @@ struct LstmChain {
     float* dh0;          // bwd: gradient w.r.t. the initial state (B x h) or null
     float* dc0;
     unsigned drop_stream;
+    unsigned drop_off;   // added to the dropout counter: (t0 * B * h) when this launch covers steps [t0, t0+T) of a longer sequence
     int b0, nb;          // batch rows [b0, b0+nb) of the B-row buffers handled by this chain (nb = 0: all B rows)
 };
 struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };

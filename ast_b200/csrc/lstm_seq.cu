@@ -193,7 +193,7 @@ lstm_seq_fwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                     *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = actv[hf];
                     a.Cs[(r + B) * h + ju] = cv[hf];
                     a.Hs[(r + B) * h + ju] = hv[hf];
-                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
                     a.out[(long long)i * a.out_si + (long long)(b0 + row) * a.out_sb + ju] = hv[hf] * dm;
                     if (i + 1 < T) gx[hf] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);   // prefetch
                 }
@@ -282,7 +282,7 @@ lstm_seq_bwd_kernel(LstmChains ch, int T, int B, int h, float drop, unsigned lon
                         for (int s = 0; s < NC; ++s) dh += rprev[((size_t)s * MROWS + m) * U + ul];
                     }
                     const size_t r = (size_t)i * B + b0 + m;
-                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
                     dh += p_dout[e] * dm;
                     const float4 act = p_act[e];
                     const float c = p_c[e], cp = p_cp[e];
@@ -443,7 +443,8 @@ int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
     AST_TRY(expand_chains("lstm_seq_bwd", ch, nchains, T, B, h, ex, n));
     bool wants_init_grads = false;
     for (int c = 0; c < n; ++c) wants_init_grads |= (ex.c[c].dh0 != nullptr) || (ex.c[c].dc0 != nullptr);
-    if (!exact && h == 256 && !wants_init_grads) return lstm_seq_bwd_tc(st, ex, n, T, B, drop, seed);
+    (void)wants_init_grads;
+    if (!exact && h == 256) return lstm_seq_bwd_tc(st, ex, n, T, B, drop, seed);
     const size_t smem = bwd_smem(h);
     return exact ? launch_cluster(lstm_seq_bwd_kernel<true>, st, n, smem, ex, T, B, h, drop, seed)
                  : launch_cluster(lstm_seq_bwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);

@@ -198,7 +198,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = actv[j];
                     a.Cs[(r + B) * h + ju] = cv[j];
                     a.Hs[(r + B) * h + ju] = hv[j];
-                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
                     a.out[(long long)i * a.out_si + (long long)(b0 + b) * a.out_sb + ju] = hv[j] * dm;
                     if (i + 1 < T) gx[j] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);
                 }
@@ -271,7 +271,8 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             const uint64_t a0 = umma_smem_desc(sA_addr, 16384, 512, 1);
             const uint64_t g0 = umma_smem_desc(sG_addr, 16, 1024, 2);
             int step = 0;
-            for (int i = T - 1; i >= 1; --i, ++step) {
+            const int i_last = a.dh0 ? 0 : 1;       // dh0 requested: step 0 also sends (gradient w.r.t. the initial h)
+            for (int i = T - 1; i >= i_last; --i, ++step) {
                 mbar_expect_tx(&mbar_r[i & 1], BW_R_BYTES);       // arm the reduce buffer this step's sends fill
                 mbar_wait(mbar_g, step & 1);                      // dG_i operand complete in smem
                 tc_fence_after();
@@ -305,7 +306,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         int step = 0;
         for (int i = T - 1; i >= 0; --i, ++step) {
             const int buf = i & 1;
-            const bool send = i > 0;
+            const bool send = i > 0 || a.dh0 != nullptr;
             const float* rprev = red + (size_t)(buf ^ 1) * (BW_R_BYTES / 4);
             if (i < T - 1) mbar_wait(&mbar_r[buf ^ 1], ((T - 2 - i) >> 1) & 1);     // partial dh of step i+1 from all CTAs
             // 1. dG_t for the owned units (K-major UMMA operand, TF32-rounded)
@@ -324,7 +325,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                         for (int s = 0; s < TNC; ++s) dh += rprev[(s * TU + ul) * TROWS + m];
                     }
                     const size_t r = (size_t)i * B + b0 + m;
-                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju), drop);
+                    const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
                     dh += p_dout[e] * dm;
                     const float4 act = p_act[e];
                     const float c = p_c[e], cp = p_cp[e];
@@ -373,6 +374,24 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) st_async_v4(dst + 16 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), bar);
+            }
+        }
+        // gradients w.r.t. the initial state (slot 0): the carry into the previous chunk of a longer sequence
+        if (a.dh0 || a.dc0) {
+            if (a.dh0) mbar_wait(&mbar_r[0], ((T - 1) >> 1) & 1);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int idx = tid + e * TC_EPI;
+                const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
+                if (m < nb) {
+                    if (a.dh0) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int sidx = 0; sidx < TNC; ++sidx) s += red[(sidx * TU + ul) * TROWS + m];
+                        a.dh0[(size_t)(b0 + m) * h + ju] = s;
+                    }
+                    if (a.dc0) a.dc0[(size_t)(b0 + m) * h + ju] = dc[e];
+                }
             }
         }
     }

@@ -80,6 +80,9 @@ struct ast_model {
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr; int overlap = 1;
+    // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
+    cudaStream_t lay[MAXL] = {}; cudaEvent_t ev_pool[128] = {}; int enc_chunk = 32;
+    float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
     bool weights_dirty = true, have_fwd = false;
@@ -180,6 +183,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
             m->Cs[l][d] = a.get<float>((TB + B) * h);
             m->Hd[l][d] = a.get<float>(TB * h);
             m->dHd[l][d] = a.get<float>(TB * h);
+            m->dh_carry[l][d] = a.get<float>((size_t)B * h);
+            m->dc_carry[l][d] = a.get<float>((size_t)B * h);
         }
     m->enc_states = a.get<float>(TB * H);
     m->d_enc = a.get<float>(TB * H);
@@ -348,28 +353,62 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     AST_TRY(bn_relu_to_rnn(st, m->raw1, m->rnn_in, m->rnn_rev, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
                            m->p("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
 
-    // encoder stacks, layer-major: one batched input-projection GEMM per (layer, direction), then the
-    // persistent recurrence for both directions in one launch.
-    for (int l = 0; l < NL; ++l) {
-        LstmChains ch{};
+    // encoder stacks: one input-projection GEMM per (layer, direction, chunk), then the persistent recurrence for both
+    // directions in one launch.  With enc_chunk > 0 the time axis is cut into chunks and the layers run as a wavefront
+    // (layer l on chunk c while layer l-1 is on chunk c+1), one stream per layer: the per-step latency chain of a
+    // 3-layer stack shrinks from 3*T' to about T' + 2*chunk steps.  Link states (Hs/Cs slots) carry across chunks.
+    const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
+    const int nch = (Tp + CH - 1) / CH;
+    const bool wave = nch > 1 && NL * nch + 2 <= 128;
+    for (int l = 0; l < NL; ++l)
         for (int d = 0; d < 2; ++d) {
-            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
-            const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
-            AST_TRY(gemm_nt(m, st, TB, 4 * h, m->in_enc(l), xin, m->in_enc(l), m->p((ln + "/upward/W").c_str()), m->in_enc(l),
-                            m->Genc[l][d], 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
             AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
             AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
-            LstmChain& cc = ch.c[d];
-            cc.G = m->Genc[l][d]; cc.Wl = m->p((ln + "/lateral/W").c_str());
-            cc.Hs = m->Hs[l][d]; cc.Cs = m->Cs[l][d];
-            if (l == NL - 1) {       // top layer writes enc_states (B,T',H) directly; reverse stack flipped (:231)
-                if (d == 0) { cc.out = m->enc_states; cc.out_si = m->H; }
-                else { cc.out = m->enc_states + (size_t)(Tp - 1) * m->H + h; cc.out_si = -(long long)m->H; }
-                cc.out_sb = (long long)Tp * m->H;
-            } else { cc.out = m->Hd[l][d]; cc.out_si = (long long)B * h; cc.out_sb = h; }
-            cc.drop_stream = 1 + 2 * l + d;
         }
-        AST_TRY(lstm_seq_fwd(st, ch, 2, Tp, B, h, drop, m->cur_seed, m->exact != 0));
+    auto run_chunk = [&](int l, int t0, int tn, cudaStream_t s, bool project) -> int {
+        LstmChains ch{};
+        const size_t r0 = (size_t)t0 * B;
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            if (project) {
+                const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
+                AST_TRY(gemm_nt(m, s, tn * B, 4 * h, m->in_enc(l), xin + r0 * m->in_enc(l), m->in_enc(l), m->p((ln + "/upward/W").c_str()),
+                                m->in_enc(l), m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
+            }
+            LstmChain& cc = ch.c[d];
+            cc.G = m->Genc[l][d] + r0 * 4 * h; cc.Wl = m->p((ln + "/lateral/W").c_str());
+            cc.Hs = m->Hs[l][d] + r0 * h; cc.Cs = m->Cs[l][d] + r0 * h;
+            if (l == NL - 1) {       // top layer writes enc_states (B,T',H) directly; reverse stack flipped (:231)
+                if (d == 0) { cc.out = m->enc_states + (size_t)t0 * m->H; cc.out_si = m->H; }
+                else { cc.out = m->enc_states + (size_t)(Tp - 1 - t0) * m->H + h; cc.out_si = -(long long)m->H; }
+                cc.out_sb = (long long)Tp * m->H;
+            } else { cc.out = m->Hd[l][d] + r0 * h; cc.out_si = (long long)B * h; cc.out_sb = h; }
+            cc.drop_stream = 1 + 2 * l + d;
+            cc.drop_off = (unsigned)(r0 * h);
+        }
+        return lstm_seq_fwd(s, ch, 2, tn, B, h, drop, m->cur_seed, m->exact != 0);
+    };
+    if (!wave) {
+        for (int l = 0; l < NL; ++l) AST_TRY(run_chunk(l, 0, Tp, st, true));
+    } else {
+        // layer 0: whole-sequence projection (its input is complete), chunked recurrence
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(0, d == 0 ? "enc" : "rev_enc");
+            AST_TRY(gemm_nt(m, st, TB, 4 * h, m->in_enc(0), d == 0 ? m->rnn_in : m->rnn_rev, m->in_enc(0), m->p((ln + "/upward/W").c_str()),
+                            m->in_enc(0), m->Genc[0][d], 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
+        }
+        cudaEvent_t* ev = m->ev_pool;          // ev[l * nch + c]: chunk c of layer l finished; ev[NL * nch]: start
+        AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
+        for (int l = 1; l < NL; ++l) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+        for (int c = 0; c < nch; ++c)
+            for (int l = 0; l < NL; ++l) {     // enqueue order = wavefront order (keeps the host from serialising streams)
+                cudaStream_t s = l == 0 ? st : m->lay[l];
+                const int t0 = c * CH, tn = std::min(CH, Tp - t0);
+                if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(s, ev[(l - 1) * nch + c], 0));
+                AST_TRY(run_chunk(l, t0, tn, s, l > 0));
+                AST_CUDA_OK(cudaEventRecord(ev[l * nch + c], s));
+            }
+        AST_CUDA_OK(cudaStreamWaitEvent(st, ev[(NL - 1) * nch + nch - 1], 0));
     }
     m->have_fwd = false;
     return 0;
@@ -600,35 +639,82 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
         AST_TRY(colsum(sw, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
-    // ---- encoder BPTT, layer-major top-down; both directions per launch ------------------------------
-    for (int l = NL - 1; l >= 0; --l) {
+    // ---- encoder BPTT, top-down; both directions per launch.  Same chunked layer wavefront as the forward pass, in
+    // reverse time: layer l works on chunk c while layer l+1 is already on chunk c-1; the (dh, dc) carry between the
+    // chunks of one layer goes through dh_carry / dc_carry (the kernels' dh0/dc0 outputs).
+    const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
+    const int nch = (Tp + CH - 1) / CH;
+    const bool wave = nch > 1 && NL * nch + 2 <= 128;
+    auto bwd_chunk = [&](int l, int ci, cudaStream_t s) -> int {
+        const int t0 = ci * CH, tn = std::min(CH, Tp - t0);
+        const size_t r0 = (size_t)t0 * B;
+        const bool last_in_time = (ci == nch - 1);
         LstmChains ch{};
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             LstmChain& cc = ch.c[d];
-            cc.G = m->Genc[l][d]; cc.Wl = m->p((ln + "/lateral/W").c_str()); cc.Hs = m->Hs[l][d]; cc.Cs = m->Cs[l][d];
+            cc.G = m->Genc[l][d] + r0 * 4 * h; cc.Wl = m->p((ln + "/lateral/W").c_str());
+            cc.Hs = m->Hs[l][d] + r0 * h; cc.Cs = m->Cs[l][d] + r0 * h;
             if (l == NL - 1) {
-                if (d == 0) { cc.dout = m->d_enc; cc.out_si = H; }
-                else { cc.dout = m->d_enc + (size_t)(Tp - 1) * H + h; cc.out_si = -(long long)H; }
+                if (d == 0) { cc.dout = m->d_enc + (size_t)t0 * H; cc.out_si = H; }
+                else { cc.dout = m->d_enc + (size_t)(Tp - 1 - t0) * H + h; cc.out_si = -(long long)H; }
                 cc.out_sb = (long long)Tp * H;
-            } else { cc.dout = m->dHd[l][d]; cc.out_si = (long long)B * h; cc.out_sb = h; }
-            cc.dh_fin = m->dxh[l] + m->in_dec(l) + d * h; cc.ld_dh_fin = m->in_dec(l) + H;
-            cc.dc_fin = m->dcd[l] + d * h; cc.ld_dc_fin = H;
+            } else { cc.dout = m->dHd[l][d] + r0 * h; cc.out_si = (long long)B * h; cc.out_sb = h; }
+            if (last_in_time) {
+                cc.dh_fin = m->dxh[l] + m->in_dec(l) + d * h; cc.ld_dh_fin = m->in_dec(l) + H;
+                cc.dc_fin = m->dcd[l] + d * h; cc.ld_dc_fin = H;
+            } else {
+                cc.dh_fin = m->dh_carry[l][d]; cc.ld_dh_fin = h;
+                cc.dc_fin = m->dc_carry[l][d]; cc.ld_dc_fin = h;
+            }
+            if (ci > 0) { cc.dh0 = m->dh_carry[l][d]; cc.dc0 = m->dc_carry[l][d]; }
             cc.drop_stream = 1 + 2 * l + d;
+            cc.drop_off = (unsigned)(r0 * h);
         }
-        AST_TRY(lstm_seq_bwd(st, ch, 2, Tp, B, h, dr, m->cur_seed, ex));
-        AST_TRY(fork());
+        AST_TRY(lstm_seq_bwd(s, ch, 2, tn, B, h, dr, m->cur_seed, ex));
+        for (int d = 0; d < 2; ++d) {          // dx = dG . W_up for this chunk's rows (critical path of the layer below)
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            const int in = m->in_enc(l);
+            float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
+            AST_TRY(gemm(m, s, false, false, tn * B, in, 4 * h, m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/W").c_str()), in,
+                         dx + r0 * in, in, nullptr, 0.f, 0, SITE_ENC_DX));
+        }
+        return 0;
+    };
+    auto enc_wgrads = [&](int l) -> int {
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
-            float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
-            const float* Wup = m->p((ln + "/upward/W").c_str());
-            AST_TRY(gemm(m, st, false, false, TB, in, 4 * h, m->Genc[l][d], 4 * h, Wup, in, dx, in, nullptr, 0.f, 0, SITE_ENC_DX));
             AST_TRY(gemm(m, sw, true, false, 4 * h, in, TB, m->Genc[l][d], 4 * h, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_ENC_WGRAD));
             AST_TRY(gemm(m, sw, true, false, 4 * h, h, TB, m->Genc[l][d], 4 * h, m->Hs[l][d], h, m->g((ln + "/lateral/W").c_str()), h, nullptr, 0.f, -1, SITE_ENC_WGRAD));
             AST_TRY(colsum(sw, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
         }
+        return 0;
+    };
+    if (!wave) {
+        for (int l = NL - 1; l >= 0; --l) {
+            AST_TRY(bwd_chunk(l, 0, st));
+            AST_TRY(fork());
+            AST_TRY(enc_wgrads(l));
+        }
+    } else {
+        cudaEvent_t* ev = m->ev_pool;          // ev[l * nch + c]: layer l finished chunk c (recurrence + dx); ev[NL * nch]: start
+        AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
+        for (int l = 0; l < NL - 1; ++l) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+        for (int ci = nch - 1; ci >= 0; --ci)
+            for (int l = NL - 1; l >= 0; --l) {
+                cudaStream_t s = l == NL - 1 ? st : m->lay[l];
+                if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(s, ev[(l + 1) * nch + ci], 0));
+                AST_TRY(bwd_chunk(l, ci, s));
+                AST_CUDA_OK(cudaEventRecord(ev[l * nch + ci], s));
+            }
+        for (int l = NL - 1; l >= 0; --l) {    // weight gradients once the layer's dG is complete, off the critical path
+            if (sw != st) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[l * nch + 0], 0));
+            else AST_CUDA_OK(cudaStreamWaitEvent(st, ev[l * nch + 0], 0));
+            AST_TRY(enc_wgrads(l));
+        }
+        AST_CUDA_OK(cudaStreamWaitEvent(st, ev[0 * nch + 0], 0));
     }
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
@@ -718,6 +804,8 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     AST_CREATE_CHECK(e == cudaSuccess, "cudaStreamCreate: %s", cudaGetErrorString(e));
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->lay[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 128 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
     *out = m;
@@ -730,6 +818,8 @@ int ast_destroy(ast_model* m) {
     for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->side) cudaStreamDestroy(m->side);
+    for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
+    for (int i = 0; i < 128; ++i) if (m->ev_pool[i]) cudaEventDestroy(m->ev_pool[i]);
     delete m;
     return 0;
 }
@@ -777,6 +867,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_fused")) m->dec_fused = value != 0;
     else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
+    else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }

@@ -212,6 +212,34 @@ def test_fused_and_per_step_decoder_paths_agree(dev):
     assert np.abs(out[0][2] - out[1][2]).max() <= 1e-4 * np.abs(out[1][2]).max()
 
 
+@pytest.mark.parametrize("exact", [1, 0])
+def test_encoder_wavefront_and_side_stream_match_serial(dev, exact):
+    """The chunked layer wavefront of the encoder stacks (one stream per layer, link state and (dh, dc) carried across
+    chunks) and the side-stream weight gradients run the same arithmetic as the single-stream, whole-sequence path:
+    bit-identical loss, encoder states and gradients, with dropout on (the dropout counters must line up across chunks)."""
+    cfg = O.default_model_cfg(vocab=200, dropout=(0.3, 0.3, 0.0))
+    P = _perturbed(cfg, 40, 71)
+    X, y, _ = O.synth_batch(21, 300, 40, 200, 4, 9, seed=72, Tmin=260)       # T' = 75: chunks of 16 -> 5 chunks, ragged tail
+    out = []
+    for overlap, chunk in ((0, 0), (1, 16), (1, 7)):
+        e = _engine(cfg, 40, P)
+        e.set_option("exact", exact); e.set_option("tc_gemm", 0 if exact else 1)
+        e.set_option("overlap", overlap); e.set_option("enc_chunk", chunk)
+        e.set_option("seed", 9)
+        loss = float(e.forward_loss(X, y, noise_sigma=0.25))
+        enc = e.enc_states().cpu().numpy().copy()
+        e.backward()
+        torch.cuda.synchronize()
+        out.append((loss, enc, e.grads.cpu().numpy().copy()))
+    for o in out[1:]:
+        assert o[0] == out[0][0]
+        assert np.array_equal(o[1], out[0][1])
+        if exact:
+            assert np.array_equal(o[2], out[0][2])
+        else:       # split-K weight gradients accumulate with atomics: order-dependent fp32 rounding only
+            assert np.abs(o[2] - out[0][2]).max() <= 1e-5 * np.abs(out[0][2]).max()
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_golden_fixtures(dev, name):
     cfg, D, P, z = load_case(name)

@@ -127,3 +127,39 @@ def test_cmvn_coefficients():
     x = (rng.standard_normal((50, 4)) * 3 + 2).astype(np.float32)
     s, o = cmvn_scale_offset(x.astype(np.float64).sum(0), (x.astype(np.float64) ** 2).sum(0), 50)
     assert np.allclose(x * s + o, apply_cmvn(x, x.astype(np.float64).sum(0), (x.astype(np.float64) ** 2).sum(0), 50), atol=1e-6)
+
+
+def test_corpus_bleu_known_answers(tmp_path):
+    """eval.py:29-38 (nltk corpus_bleu + smoothing method2), hand-computed."""
+    import math
+    from ast_b200.eval import Eval, corpus_bleu, brevity_penalty, closest_ref_length, modified_precision
+    # Papineni's clipping example: 'the' x7 against two references -> 2/7
+    hyp = "the the the the the the the".split()
+    refs = ["the cat is on the mat".split(), "there is a cat on the mat".split()]
+    assert modified_precision(refs, hyp, 1) == (2, 7)
+    assert modified_precision(refs, hyp, 2) == (0, 6)
+    assert closest_ref_length(refs, 7) == 7 and closest_ref_length([[0] * 5, [0] * 9], 7) == 5   # tie -> shorter
+    assert brevity_penalty(6, 7) == 1.0 and brevity_penalty(7, 0) == 0.0
+    assert abs(brevity_penalty(9, 6) - math.exp(1 - 9 / 6)) < 1e-15
+    # perfect match of one 5-token sentence: counts 5,4,3,2 -> smoothed p = 6/6, 5/5, ... = 1 -> BLEU 1
+    s = "a b c d e".split()
+    assert abs(corpus_bleu([[s]], [s]) - 1.0) < 1e-12
+    # corpus of two sentences, one reference each
+    r1, h1 = "the quick brown fox jumps".split(), "the quick brown dog jumps".split()
+    r2, h2 = "hello world again".split(), "hello world".split()
+    # unigrams: 4/5 + 2/2 = 6/7 ; bigrams: 2/4 + 1/1 = 3/5 ; trigrams: 1/3 + 0/max(1,0) = 1/4 ; 4-grams: 0/2 + 0/1 = 0/3
+    want_all = math.exp(1 - 8 / 7) * math.exp(0.25 * (math.log(7 / 8) + math.log(4 / 6) + math.log(2 / 5) + math.log(1 / 4)))
+    want_new = math.exp(1 - 8 / 7) * math.exp(0.25 * (math.log(6 / 7) + math.log(4 / 6) + math.log(2 / 5) + math.log(1 / 4)))
+    assert abs(corpus_bleu([[r1], [r2]], [h1, h2]) - want_all) < 1e-12
+    assert abs(corpus_bleu([[r1], [r2]], [h1, h2], smooth_unigram=False) - want_new) < 1e-12
+    assert corpus_bleu([[r1]], ["x y z".split()]) == 0.0            # no unigram match
+    # Eval reads the reference's directory layout (data/fisher/refs/<set>/eval.ids, ref.en0..)
+    (tmp_path / "eval.ids").write_text("u1\nu2\n")
+    (tmp_path / "ref.en0").write_text(" ".join(r1) + "\n" + " ".join(r2) + "\n")
+    (tmp_path / "ref.en1").write_text("a fast brown fox leaps\nhello there world\n")
+    ev = Eval(str(tmp_path), 2)
+    assert len(ev.refs) == 2 and len(ev.refs[0]) == 2
+    b = ev.calc_bleu({"u1": h1, "u2": h2})
+    assert 0.0 < b < 1.0
+    ev.write_to_file({"u1": h1, "u2": h2}, str(tmp_path / "out.txt"))
+    assert (tmp_path / "out.txt").read_text() == "the quick brown dog jumps\nhello world\n"
