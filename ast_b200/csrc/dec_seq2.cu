@@ -1,0 +1,498 @@
+// Decoder-sequence forward, second generation (TF32 training mode, es_en_20h geometry: H = A = 512, E = 128, 3 layers,
+// batch <= 32).  One cooperative launch of 32 clusters x 4 CTAs runs every decoder step of forward_loss
+// (seq2seq.py:423-470).  What changed against dec_seq.cu, and why (tools/dec_phase_times.py: 75 us/step there, every
+// LSTM phase ~11.5 us because 128 CTAs each re-read the whole 147 KB activation operand and 74 KB of weights from L2):
+//
+//  * WEIGHTS STAY ON CHIP FOR THE WHOLE SEQUENCE.  The three LSTM layers' [W_up | W_lat] (26 MB fp32) live in TENSOR
+//    MEMORY: a cluster owns 64 gate rows (16 hidden units) of every layer, each of its 4 CTAs a quarter of K, and each
+//    thread keeps exactly its own mma B-fragments (208 TF32 values) in its TMEM lane, written once with tcgen05.st and
+//    read back with tcgen05.ld every step.  TMEM is used as 256 KB/SM of software-managed operand storage; shared
+//    memory stays free for the activation slice, the context weights and the exchange buffers.
+//  * K IS SPLIT ACROSS THE CLUSTER, so a CTA stages only its 32 x 288 slice of the activations (36 KB instead of
+//    147 KB); the four partial 32 x 64 products are reduce-scattered through distributed shared memory
+//    (st.async + mbarrier complete_tx), and each CTA finishes the LSTM cell for its 4 units x 32 rows.
+//  * ATTENTION IS ONE PHASE: a cluster owns one batch row; score, softmax and context are a single online-softmax
+//    pass over its quarter of T' (scores through the precomputed encW = enc . W_a, so q = W_a h is never formed inside
+//    the loop), merged across warps and across the cluster by (max, sum, partial context) triples.
+//  * THE VOCABULARY PROJECTION LEAVES THE LOOP: logits, softmax-CE and its gradient are one batched tcgen05 GEMM and
+//    one CE launch after the loop.  Only steps whose successor is NOT teacher-forced (scheduled sampling,
+//    seq2seq.py:431-436) compute logits + argmax in-loop, because the next embedding depends on them.
+//  A decoder step is 5 grid barriers (3 LSTM + attention + context) instead of 9.
+#include <cuda_runtime.h>
+#include "cluster_dev.cuh"
+#include "decoder_dev.cuh"
+
+namespace ast {
+
+namespace {
+
+constexpr int D2_THREADS = 256;
+constexpr int D2_CS = 4;                 // CTAs per cluster = K split
+constexpr int D2_NCL = 32;               // clusters
+constexpr int D2_H = 512, D2_E = 128, D2_A = 512;
+constexpr int D2_KQ0 = 320;              // layer-0 K quarter: 32 (emb) + 128 (ht) + 128 (h_prev) = 288, padded to 40 k-steps
+constexpr int D2_KQ = 256;               // layers 1,2 and the context GEMM: 128 + 128
+constexpr int D2_XLD = D2_KQ0 + 4;       // smem row stride of the staged activations (conflict-free A fragments)
+constexpr int D2_WLD = D2_KQ + 4;        // smem row stride of the context weights
+constexpr int D2_TCOL0 = 0, D2_TCOL1 = 80, D2_TCOL2 = 144;   // TMEM column of each layer's fragments (80 + 64 + 64)
+constexpr uint32_t D2_XBYTES = 4 * 32 * 16 * 4;              // GEMM exchange: [src][row][16 cols]
+constexpr uint32_t D2_ABYTES = 4 * 128 * 4 + 4 * 8;          // attention exchange: [src][128 cols] + [src](max, sum)
+
+struct D2Smem {
+    float Xs[32 * D2_XLD];
+    float recv[4 * 32 * 16];
+    float Wcs[64 * D2_WLD];
+    float h2s[D2_H];
+    float cvw[8 * D2_H];
+    float cvx[4 * 128];
+    float statx[4 * 2];
+    float wstat[8 * 2];
+    uint64_t mbar_x, mbar_a;
+    uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ float rtf32(float x) { return __uint_as_float(f2tf32(x)); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// grid barrier on a monotonically increasing global counter (zeroed by the host before the launch)
+__device__ __forceinline__ void grid_barrier2(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long gtimer2() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+
+// One activation segment of the K quarter: W floats per row starting at ptr[row * ld]; 32 rows.  All of a thread's loads
+// are issued before the first store (the serialised load -> convert -> store loop cost ~0.8 us per round trip, measured).
+template <int W>
+__device__ __forceinline__ void seg_load(float4 (&v)[W / 32], const float* ptr, int ld, int B) {
+#pragma unroll
+    for (int i = 0; i < W / 32; ++i) {
+        const int idx = threadIdx.x + i * D2_THREADS, row = idx / (W / 4), k = (idx % (W / 4)) * 4;
+        v[i] = row < B ? __ldcg(reinterpret_cast<const float4*>(ptr + (size_t)row * ld + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int W>
+__device__ __forceinline__ void seg_store(float* Xs_k0, const float4 (&v)[W / 32]) {
+#pragma unroll
+    for (int i = 0; i < W / 32; ++i) {
+        const int idx = threadIdx.x + i * D2_THREADS, row = idx / (W / 4), k = (idx % (W / 4)) * 4;
+        *reinterpret_cast<float4*>(Xs_k0 + row * D2_XLD + k) = make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
+    }
+}
+
+// acc[mt][4] += X(32 x kq) . Wfrag^T for this warp's n-tile; B fragments from TMEM (16 regs per 8 k-steps).
+__device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr, int kq) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int nchunk = kq >> 6;
+    uint32_t bcur[16], bnxt[16];
+    tmem_ld16_nowait(taddr, bcur);
+    tmem_wait_ld();
+    for (int j = 0; j < nchunk; ++j) {
+        if (j + 1 < nchunk) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
+        const float* xr = Xs + g * D2_XLD + j * 64 + q;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const float* x0 = xr + ks * 8;
+            uint32_t a0[4], a1[4];
+            a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * D2_XLD]);
+            a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * D2_XLD + 4]);
+            a1[0] = __float_as_uint(x0[16 * D2_XLD]);     a1[1] = __float_as_uint(x0[24 * D2_XLD]);
+            a1[2] = __float_as_uint(x0[16 * D2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * D2_XLD + 4]);
+            const uint32_t b[2] = {bcur[2 * ks], bcur[2 * ks + 1]};
+            mma_tf32(acc[0], a0, b);
+            mma_tf32(acc[1], a1, b);
+        }
+        if (j + 1 < nchunk) {
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bcur[i] = bnxt[i];
+        }
+    }
+}
+
+// same with B fragments from shared memory (context weights), kq = 256
+__device__ __forceinline__ void mma_from_smem(float (&acc)[2][4], const float* Xs, const float* Ws) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const float* xr = Xs + g * D2_XLD + q;
+    const float* wr = Ws + (8 * w + g) * D2_WLD + q;
+#pragma unroll 8
+    for (int ks = 0; ks < D2_KQ / 8; ++ks) {
+        const float* x0 = xr + ks * 8;
+        uint32_t a0[4], a1[4];
+        a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * D2_XLD]);
+        a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * D2_XLD + 4]);
+        a1[0] = __float_as_uint(x0[16 * D2_XLD]);     a1[1] = __float_as_uint(x0[24 * D2_XLD]);
+        a1[2] = __float_as_uint(x0[16 * D2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * D2_XLD + 4]);
+        const uint32_t b[2] = {__float_as_uint(wr[ks * 8]), __float_as_uint(wr[ks * 8 + 4])};
+        mma_tf32(acc[0], a0, b);
+        mma_tf32(acc[1], a1, b);
+    }
+}
+
+// reduce-scatter of the four K-partial 32 x 64 products: warp w holds n-tile w = columns 8w..8w+7, owned by CTA w/2
+__device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& sm, int rank) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
+    const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = 16 * mt + g;
+        st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
+        st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(D2_THREADS, 1)
+dec_seq2_fwd_kernel(DecSeq p) {
+    extern __shared__ uint8_t smem_raw[];
+    D2Smem& sm = *reinterpret_cast<D2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    __shared__ SkinnySmem ssm;           // in-loop logits of sampled steps (decoder_dev.cuh)
+    __shared__ float scratch[32];
+    __shared__ int iscratch[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int rank = (int)cluster_rank(), cl = blockIdx.x / D2_CS, cta = blockIdx.x, ncta = gridDim.x;
+    const int B = p.B, S = p.S, L = p.L, Tp = p.Tp, Vp = p.Vp;
+    constexpr int H = D2_H, E = D2_E, A = D2_A, ldx0 = D2_E + D2_A;
+    unsigned bar_target = 0;
+    int nprof = 0;
+#define D2_SYNC() do { grid_barrier2(p.bar, bar_target); \
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&sm.tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_lane = sm.tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (w >= 4 ? 256u : 0u);
+
+    // LSTM weights -> TMEM: thread (w, lane) keeps B[k][n] = W[64 cl + 8w + g][kcol(k)] for k = 8 ks + q, 8 ks + q + 4
+    {
+        const int row = 64 * cl + 8 * w + g;
+        for (int l = 0; l < 3; ++l) {
+            const int kq = l == 0 ? D2_KQ0 : D2_KQ;
+            const int in = l == 0 ? ldx0 : H;
+            const float* Wup = p.Wup[l] + (size_t)row * in;
+            const float* Wlat = p.Wlat[l] + (size_t)row * H;
+            const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
+            for (int j = 0; j < (kq >> 6); ++j) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = j * 64 + (i >> 1) * 8 + q + 4 * (i & 1);
+                    float x;
+                    if (l == 0) {
+                        if (k < 32) x = __ldg(Wup + 32 * rank + k);
+                        else if (k < 160) x = __ldg(Wup + E + 128 * rank + (k - 32));
+                        else if (k < 288) x = __ldg(Wlat + 128 * rank + (k - 160));
+                        else x = 0.f;
+                    } else {
+                        x = k < 128 ? __ldg(Wup + 128 * rank + k) : __ldg(Wlat + 128 * rank + (k - 128));
+                    }
+                    v[i] = rtf32(x);
+                }
+                tmem_st16(tmem_lane + tcol + 16 * j, v);
+            }
+        }
+        tmem_wait_st();
+    }
+    // context weights -> smem (clusters 0..7 compute ht): Wcs[j][k] = Wc[64 cl + j][kcol(k)], kcol: cv quarter | h quarter
+    if (cl < A / 64) {
+        for (int idx = tid; idx < 64 * (D2_KQ / 4); idx += D2_THREADS) {
+            const int j = idx / (D2_KQ / 4), k = (idx % (D2_KQ / 4)) * 4;
+            const int kc = k < 128 ? 128 * rank + k : H + 128 * rank + (k - 128);
+            float4 v = __ldg(reinterpret_cast<const float4*>(p.Wc + (size_t)(64 * cl + j) * (2 * H) + kc));
+            v.x = rtf32(v.x); v.y = rtf32(v.y); v.z = rtf32(v.z); v.w = rtf32(v.w);
+            *reinterpret_cast<float4*>(sm.Wcs + j * D2_WLD + k) = v;
+        }
+    }
+    for (int idx = tid; idx < 32 * 32; idx += D2_THREADS) sm.Xs[(idx >> 5) * D2_XLD + 288 + (idx & 31)] = 0.f;      // layer-0 k padding
+    // teacher-forced decoder inputs for every step (sampled steps overwrite theirs in-loop); x0[0][:, E:] = 0
+    for (int i = cta; i < S * B; i += ncta) {
+        const int s = i / B, b = i - s * B;
+        const int word = min(max(p.y[(size_t)b * L + s], 0), p.V - 1);
+        float* dst = p.x0 + (size_t)i * ldx0;
+        if (tid == 0) p.words_used[i] = word;
+        for (int j = tid; j < E; j += D2_THREADS)
+            dst[j] = __ldg(p.emb + (size_t)word * E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * E + j), p.drop_embed);
+        if (s == 0) for (int j = tid; j < A; j += D2_THREADS) dst[E + j] = 0.f;
+    }
+    // cell state of the owned (row, unit) pairs stays in registers
+    const int e_row = tid >> 2, e_ul = tid & 3, e_unit = 16 * cl + 4 * rank + e_ul;
+    float creg[3] = {0.f, 0.f, 0.f};
+    if (tid < 128 && e_row < B)
+        for (int l = 0; l < 3; ++l) creg[l] = p.Cd[l][(size_t)e_row * H + e_unit];
+    uint32_t par_x = 0, par_a = 0;
+    if (tid == 0) { mbar_expect_tx(&sm.mbar_x, D2_XBYTES); mbar_expect_tx(&sm.mbar_a, D2_ABYTES); }
+    if (p.prof && cta == 0 && tid == 0) p.prof[1] = gtimer2();
+    nprof = 1;
+    cluster_sync_all();
+    D2_SYNC();
+
+    const int Tq = (Tp + D2_CS - 1) / D2_CS;
+    for (int s = 0; s < S; ++s) {
+        // ---- LSTM stack (seq2seq.py:375) -----------------------------------------------------------------------
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            int kq; uint32_t tcol;
+            if (l == 0) {
+                const float* x0 = p.x0 + (size_t)s * B * ldx0;
+                float4 v0[1], v1[4], v2[4];
+                seg_load<32>(v0, x0 + 32 * rank, ldx0, B);
+                seg_load<128>(v1, x0 + E + 128 * rank, ldx0, B);
+                seg_load<128>(v2, p.Hd[0] + (size_t)s * B * H + 128 * rank, H, B);
+                seg_store<32>(sm.Xs, v0); seg_store<128>(sm.Xs + 32, v1); seg_store<128>(sm.Xs + 160, v2);
+                kq = D2_KQ0; tcol = D2_TCOL0;
+            } else {
+                float4 v1[4], v2[4];
+                seg_load<128>(v1, p.hdd[l - 1] + (size_t)s * B * H + 128 * rank, H, B);
+                seg_load<128>(v2, p.Hd[l] + (size_t)s * B * H + 128 * rank, H, B);
+                seg_store<128>(sm.Xs, v1); seg_store<128>(sm.Xs + 128, v2);
+                kq = D2_KQ; tcol = l == 1 ? D2_TCOL1 : D2_TCOL2;
+            }
+            __syncthreads();
+            float acc[2][4] = {};
+            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, kq);
+            exchange_send(acc, sm, rank);
+            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
+            if (tid < 128 && e_row < B) {
+                float4 gs = __ldg(reinterpret_cast<const float4*>(p.bup[l] + 4 * e_unit));
+#pragma unroll
+                for (int src = 0; src < 4; ++src) {
+                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + e_row) * 16 + 4 * e_ul);
+                    gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
+                }
+                const float ga = tanhf(gs.x), gi = sigmoidf_(gs.y), gf = sigmoidf_(gs.z), go = sigmoidf_(gs.w);
+                const float c = ga * gi + gf * creg[l];
+                creg[l] = c;
+                const float hv = go * tanhf(c);
+                const size_t e = (size_t)e_row * H + e_unit;
+                *reinterpret_cast<float4*>(p.act[l] + ((size_t)s * B + e_row) * 4 * H + 4 * e_unit) = make_float4(ga, gi, gf, go);
+                p.Cd[l][(size_t)(s + 1) * B * H + e] = c;
+                p.Hd[l][(size_t)(s + 1) * B * H + e] = hv;
+                const float dm = dropout_scale(p.seed, 16 + l, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
+                if (l == 2) p.cvh[((size_t)s * B + e_row) * 2 * H + H + e_unit] = hv * dm;
+                else p.hdd[l][(size_t)s * B * H + e] = hv * dm;
+            }
+            D2_SYNC();
+        }
+        // ---- attention (seq2seq.py:336-358): cluster = batch row, CTA = quarter of T', one online-softmax pass -------
+        if (cl < B) {
+            const int b = cl;
+            const float* cvh_b = p.cvh + ((size_t)s * B + b) * 2 * H;
+            if (tid < H / 4) *reinterpret_cast<float4*>(sm.h2s + 4 * tid) = __ldcg(reinterpret_cast<const float4*>(cvh_b + H + 4 * tid));
+            __syncthreads();
+            const int t_lo = rank * Tq, t_hi = min(Tp, t_lo + Tq);
+            float4 hq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hq[i] = *reinterpret_cast<const float4*>(sm.h2s + 128 * i + 4 * lane);
+            float mw = -INFINITY, sw = 0.f;
+            float4 cv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* sc = sm.recv;     // scores of the local t range (recv is idle during this phase; Tq <= 2048)
+            // rows t, t + 8, ... of this warp; the next row's 4 KB (encW + enc) is in flight while this one is reduced
+            const float* ewb = p.encW + (size_t)b * Tp * H + 4 * lane;
+            const float* enb = p.enc + (size_t)b * Tp * H + 4 * lane;
+            const float* ebb = p.encb + (size_t)b * Tp;
+            float4 a[4], x[4]; float eb = 0.f;
+            int t = t_lo + w;
+            if (t < t_hi) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = __ldg(reinterpret_cast<const float4*>(ewb + (size_t)t * H + 128 * i)); x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i)); }
+                eb = __ldg(ebb + t);
+            }
+            while (t < t_hi) {
+                const int tn = t + 8;
+                float4 an[4], xn[4]; float ebn = 0.f;
+                if (tn < t_hi) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { an[i] = __ldg(reinterpret_cast<const float4*>(ewb + (size_t)tn * H + 128 * i)); xn[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)tn * H + 128 * i)); }
+                    ebn = __ldg(ebb + tn);
+                }
+                float d = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d += a[i].x * hq[i].x + a[i].y * hq[i].y + a[i].z * hq[i].z + a[i].w * hq[i].w;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                d += eb;
+                if (lane == 0) sc[t - t_lo] = d;
+                const float mn = fmaxf(mw, d);
+                const float scale = __expf(mw - mn), pe = __expf(d - mn);
+                sw = sw * scale + pe; mw = mn;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cv[i].x = cv[i].x * scale + pe * x[i].x; cv[i].y = cv[i].y * scale + pe * x[i].y;
+                    cv[i].z = cv[i].z * scale + pe * x[i].z; cv[i].w = cv[i].w * scale + pe * x[i].w;
+                }
+                if (tn < t_hi) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { a[i] = an[i]; x[i] = xn[i]; }
+                    eb = ebn;
+                }
+                t = tn;
+            }
+            if (lane == 0) { sm.wstat[2 * w] = mw; sm.wstat[2 * w + 1] = sw; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sm.cvw + w * H + 128 * i + 4 * lane) = cv[i];
+            __syncthreads();
+            // merge the 8 warps, send column quarter j/128 of the partial context + (max, sum) to every CTA of the cluster
+            float Mr = -INFINITY;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) Mr = fmaxf(Mr, sm.wstat[2 * ww]);
+            float wsc[8], sr = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) { wsc[ww] = (sm.wstat[2 * ww] == -INFINITY) ? 0.f : __expf(sm.wstat[2 * ww] - Mr); sr += wsc[ww] * sm.wstat[2 * ww + 1]; }
+            {
+                float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) {
+                    const float2 c2 = *reinterpret_cast<const float2*>(sm.cvw + ww * H + 2 * tid);
+                    v.x += wsc[ww] * c2.x; v.y += wsc[ww] * c2.y;
+                }
+                const int dst = tid >> 6;                  // columns 2 tid, 2 tid + 1 belong to CTA (2 tid) / 128
+                st_async_v2(mapa(saddr(sm.cvx) + (uint32_t)((rank * 128 + (2 * tid & 127)) * 4), dst), v, mapa(saddr(&sm.mbar_a), dst));
+                if (tid < 4) st_async_v2(mapa(saddr(sm.statx) + (uint32_t)(rank * 8), tid), make_float2(Mr, sr), mapa(saddr(&sm.mbar_a), tid));
+            }
+            mbar_wait(&sm.mbar_a, par_a); par_a ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);
+            float M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) M = fmaxf(M, sm.statx[2 * r]);
+            float wr[4], Z = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { wr[r] = (sm.statx[2 * r] == -INFINITY) ? 0.f : __expf(sm.statx[2 * r] - M); Z += wr[r] * sm.statx[2 * r + 1]; }
+            const float invZ = 1.f / Z;
+            if (tid < 128) {
+                float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v += wr[r] * sm.cvx[r * 128 + tid];
+                p.cvh[((size_t)s * B + b) * 2 * H + 128 * rank + tid] = v * invZ;
+            }
+            float* al = p.alpha + ((size_t)s * B + b) * Tp;
+            for (int t = t_lo + tid; t < t_hi; t += D2_THREADS) al[t] = __expf(sc[t - t_lo] - M) * invZ;
+        }
+        D2_SYNC();
+        // ---- ht = tanh(context([cv ; h]))  (seq2seq.py:386-390), clusters 0..7; also the next step's input feeding ----
+        if (cl < A / 64) {
+            const float* cvh = p.cvh + (size_t)s * B * 2 * H;
+            {
+                float4 v1[4], v2[4];
+                seg_load<128>(v1, cvh + 128 * rank, 2 * H, B);
+                seg_load<128>(v2, cvh + H + 128 * rank, 2 * H, B);
+                seg_store<128>(sm.Xs, v1); seg_store<128>(sm.Xs + 128, v2);
+            }
+            __syncthreads();
+            float acc[2][4] = {};
+            mma_from_smem(acc, sm.Xs, sm.Wcs);
+            exchange_send(acc, sm, rank);
+            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
+            if (tid < 128 && e_row < B) {
+                const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
+                float4 v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
+#pragma unroll
+                for (int src = 0; src < 4; ++src) {
+                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + e_row) * 16 + 4 * e_ul);
+                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                }
+                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+                *reinterpret_cast<float4*>(p.ht + ((size_t)s * B + e_row) * A + n0) = v;
+                if (s + 1 < S) *reinterpret_cast<float4*>(p.x0 + ((size_t)(s + 1) * B + e_row) * ldx0 + E + n0) = v;
+            }
+        }
+        D2_SYNC();
+        // ---- scheduled sampling: the next input is this step's argmax (seq2seq.py:431-436, 448) ----------------------
+        if (s + 1 < S && p.use_true != nullptr && !p.use_true[s + 1]) {
+            float* z = p.logits + (size_t)s * B * Vp;
+            SkinnyArgs a{};
+            a.X[0] = p.ht + (size_t)s * B * A; a.ldx[0] = A; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
+            a.B = B; a.N = p.V; a.epi = EPI_NONE; a.Y = z; a.ldy = Vp;
+            for (int gidx = cta; gidx < (p.V + SK_COLS - 1) / SK_COLS; gidx += ncta) skinny_tile<2, false>(a, gidx * SK_COLS, ssm);
+            D2_SYNC();
+            for (int b = cta; b < B; b += ncta) {
+                const int mi = softmax_ce_row(z + (size_t)b * Vp, Vp, p.V, 0, B, nullptr, 0, scratch, iscratch);
+                const int word = min(max(mi, 0), p.V - 1);
+                float* dst = p.x0 + ((size_t)(s + 1) * B + b) * ldx0;
+                if (tid == 0) p.words_used[(size_t)(s + 1) * B + b] = word;
+                for (int j = tid; j < E; j += D2_THREADS)
+                    dst[j] = __ldg(p.emb + (size_t)word * E + j) * dropout_scale(p.seed, 32, (uint32_t)(((size_t)(s + 1) * B + b) * E + j), p.drop_embed);
+                __syncthreads();
+            }
+            D2_SYNC();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_slot), "n"(512));
+    cluster_sync_all();
+#undef D2_SYNC
+}
+
+bool dec_seq2_supported(const DecSeq& p) {
+    return p.H == D2_H && p.E == D2_E && p.A == D2_A && p.NL == 3 && p.B >= 1 && p.B <= 32 && p.S >= 1 && p.Tp >= 1 &&
+           (p.Tp + D2_CS - 1) / D2_CS <= 4 * 32 * 16 && p.encW != nullptr && p.encb != nullptr && p.bar != nullptr;
+}
+
+int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
+    AST_CHECK(dec_seq2_supported(p), "dec_seq2_fwd: unsupported geometry");
+    const size_t smem = sizeof(D2Smem) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AST_CUDA_OK(cudaFuncSetAttribute(dec_seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    AST_CUDA_OK(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(D2_NCL * D2_CS);
+    cfg.blockDim = dim3(D2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = D2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, dec_seq2_fwd_kernel, p));
+    ++g_kernel_launches;
+    return 0;
+}
+
+}  // namespace ast

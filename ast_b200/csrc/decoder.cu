@@ -158,6 +158,22 @@ int softmax_ce(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, in
     return 0;
 }
 
+// All decoder steps at once: CTA (s, b) handles logits row s*B + b against target y[b][s + 1].
+__global__ void __launch_bounds__(256) softmax_ce_all_kernel(float* __restrict__ z, int ldz, const int* __restrict__ y, int ldy_tok,
+                                                             float* __restrict__ row_loss, int* __restrict__ argmax_out, int B, int V) {
+    __shared__ float scratch[32];
+    __shared__ int iscratch[32];
+    const int row = blockIdx.x, s = row / B, b = row - s * B;
+    const int t = y[(size_t)b * ldy_tok + s + 1];
+    const int mi = softmax_ce_row(z + (size_t)row * ldz, ldz, V, t, B, row_loss + row, 1, scratch, iscratch);
+    if (threadIdx.x == 0 && argmax_out) argmax_out[row] = mi;
+}
+int softmax_ce_all(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, float* row_loss, int* argmax_out, int S, int B, int V) {
+    softmax_ce_all_kernel<<<S * B, 256, 0, st>>>(z, ldz, y, ldy_tok, row_loss, argmax_out, B, V);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 // loss = sum over (steps x B) row losses, fixed order, double accumulation, single CTA.
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int n, float* __restrict__ loss) {
     __shared__ double sh[256];

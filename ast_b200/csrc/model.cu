@@ -62,6 +62,8 @@ struct ast_model {
     double *bnstats, *norm_sq;
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
     float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
+    float *encW, *encb;        // dec_seq2: enc_states . W_a and enc_states . b_a
+    int dec_v2 = 1;
     float *draw1, *dA1, *da0p, *draw0, *dW1p, *dW0pad;
     // decoder (training)
     float *x0, *actd[MAXL], *Hdec[MAXL], *Cdec[MAXL], *hdd[MAXL], *q, *scores, *alpha, *cvh, *ht, *logits, *row_loss;
@@ -188,6 +190,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
         }
     m->enc_states = a.get<float>(TB * H);
     m->d_enc = a.get<float>(TB * H);
+    m->encW = a.get<float>(TB * H);
+    m->encb = a.get<float>(TB);
     m->d_rnn_in = a.get<float>(TB * R); m->d_rnn_rev = a.get<float>(TB * R);
     m->draw1 = a.get<float>(M1 * C1);
     m->dA1 = a.get<float>(M1 * m->K1);
@@ -267,7 +271,7 @@ static int gemm_nt(ast_model* m, cudaStream_t st, int M, int N, int K, const flo
 
 // General GEMM dispatcher (row-major, see gemm_simt.cu for the operand convention).
 enum { SITE_CONV0 = 0, SITE_CONV1 = 1, SITE_ENC_PROJ = 2, SITE_DEC_WGRAD = 3, SITE_ENC_DX = 4, SITE_ENC_WGRAD = 5,
-       SITE_CONV1_WGRAD = 6, SITE_CONV1_DX = 7, SITE_CONV0_WGRAD = 8 };
+       SITE_CONV1_WGRAD = 6, SITE_CONV1_DX = 7, SITE_CONV0_WGRAD = 8, SITE_DEC_PRE = 9 };
 static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
                 int ldb, float* C, int ldc, const float* bias, float beta, int split_k, int site) {
     if (m->tc_gemm && !m->exact && !((m->tc_mask >> site) & 1u)) {
@@ -499,6 +503,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
     p.du = m->du; p.dcvh = m->dcvh; p.dalpha = m->dalpha; p.dq = m->dq; p.demb = m->g("embed_dec/W");
     p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
     p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr;
+    p.encW = m->encW; p.encb = m->encb;
     return p;
 }
 
@@ -519,7 +524,18 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     if (m->dec_fused) {
         DecSeq ds = make_dec_seq(m, y, use_true, true);
         if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof;
-        AST_TRY(dec_seq_fwd(st, ds, m->exact != 0));
+        if (m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds)) {
+            // per-sequence precompute: scores become encW[b,t,:] . h + encb[b,t]  (= enc . (W_a h + b_a), seq2seq.py:341-342)
+            AST_TRY(gemm(m, st, false, false, Tp * B, H, H, m->enc_states, H, m->p("attn_Wa/W"), H, m->encW, H, nullptr, 0.f, 0, SITE_DEC_PRE));
+            AST_TRY(attn_dot(st, m->enc_states, (long long)Tp * H, m->p("attn_Wa/b"), 0, m->encb, B, Tp, H));
+            AST_TRY(dec_seq2_fwd(st, ds));
+            // deferred to after the loop: q (needed by backward), logits, softmax-CE + gradient + argmax for all steps
+            AST_TRY(gemm_nt(m, st, S * B, H, H, m->cvh + H, 2 * H, m->p("attn_Wa/W"), H, m->q, H, m->p("attn_Wa/b"), SITE_DEC_PRE));
+            AST_TRY(gemm_nt(m, st, S * B, m->V, A, m->ht, A, m->p("out/W"), A, m->logits, m->Vp, m->p("out/b"), SITE_DEC_PRE));
+            AST_TRY(softmax_ce_all(st, m->logits, m->Vp, y, L, m->row_loss, m->argmax_steps, S, B, m->V));
+        } else {
+            AST_TRY(dec_seq_fwd(st, ds, m->exact != 0));
+        }
     }
     else for (int s = 0; s < S; ++s) {
         StepIO io{};
@@ -867,6 +883,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_fused")) m->dec_fused = value != 0;
     else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
+    else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }

@@ -16,6 +16,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--T", type=int, default=640)
 ap.add_argument("--L", type=int, default=24)
+ap.add_argument("--ratio", type=float, default=1.0, help="teacher-forcing ratio (1.0: no sampled steps, uniform phases)")
+ap.add_argument("--v1", action="store_true", help="first-generation decoder forward kernel")
 ap.add_argument("--cg", action="store_true", help="use cooperative_groups grid.sync instead of the counter barrier")
 a = ap.parse_args()
 rng = np.random.default_rng(0)
@@ -24,10 +26,11 @@ m.init_params(seed=0)
 e = m._engine
 e.set_option("exact", 0); e.set_option("tc_gemm", 1); e.set_option("dec_prof", 1)
 e.set_option("dec_fast_barrier", 0 if a.cg else 1)
+e.set_option("dec_v2", 0 if a.v1 else 1)
 X = torch.as_tensor(rng.standard_normal((a.B, a.T, 40)).astype(np.float32), device=e.device)
 y = rng.integers(4, 1098, (a.B, a.L)).astype(np.int32); y[:, 0] = 1; y[:, -1] = 2
 y = torch.as_tensor(y, device=e.device)
-bits = torch.as_tensor((rng.random(a.L - 1) < 0.8).astype(np.uint8), device=e.device)
+bits = torch.as_tensor((rng.random(a.L - 1) < a.ratio).astype(np.uint8), device=e.device)
 for it in range(3):
     e.forward_loss(X, y, use_true=bits, noise_sigma=0.25)
     e.backward()
