@@ -465,6 +465,470 @@ dec_seq2_fwd_kernel(DecSeq p) {
 #undef D2_SYNC
 }
 
+
+// ================================================================================================================
+// backward
+// ================================================================================================================
+// Same organisation as the forward kernel (32 clusters x 4 CTAs, K split across the cluster, reduce-scatter through
+// DSMEM, weights resident on chip).  Per step (S-1 .. 0), 6 grid barriers instead of 8:
+//   A  du = (dz.Wo [precomputed for all steps] + dht_feed) * (1 - ht^2)  fused into the operand staging; dcvh = du . Wc
+//   B  attention backward, cluster = batch row, ONE pass over T': with a_t = alpha_t * (enc_t . dcv),
+//        dq = sum_t a_t enc_t - (sum_t a_t) * cv      (cv = the forward context, so enc is read once, not twice)
+//        ds_t = a_t - alpha_t * sum_t a_t  is stored; d_enc = alpha^T dcv + ds^T q becomes ONE batched contraction after
+//        the loop instead of a read-modify-write of the whole (B, T', H) gradient every step
+//   C  dh_top = dcvh[:, H:] + dq . Wa, fused LSTM cell backward of the top layer (dG in place over the saved gates)
+//   D2, D1, D0  [dx | dh_rec] = dG_l . [W_up | W_lat] (K = 2048), fused cell backward of layer l-1 on the dx columns;
+//        the three 2048 x 1024 operands live in TMEM as per-thread mma fragments (192 values per thread).
+// The embedding columns of layer 0 (EmbedID backward) are one batched GEMM + scatter-add after the loop.
+namespace {
+
+constexpr int B2_XLD = 512 + 4;          // staged dG quarter: 32 x 512
+constexpr int B2_WLD = 128 + 4;          // context / attention weight slices: 64 x 128
+
+struct B2Smem {
+    float Xs[32 * B2_XLD];
+    float recv[4 * 32 * 16];
+    float Wcs[64 * B2_WLD];              // Wc^T slice (clusters 0..15)
+    float Was[64 * B2_WLD];              // Wa^T slice (clusters 0..7)
+    float dcvs[D2_H];
+    float cvw[8 * D2_H];
+    float cvx[4 * 128];
+    float statx[4 * 2];
+    float wstat[8];
+    uint64_t mbar_x, mbar_a;
+    uint32_t tmem_slot;
+};
+
+// acc += X(32 x 128, row stride B2_XLD) . Ws^T for this warp's n-tile (weights in smem, row stride B2_WLD)
+__device__ __forceinline__ void mma_k128_smem(float (&acc)[2][4], const float* Xs, const float* Ws) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const float* xr = Xs + g * B2_XLD + q;
+    const float* wr = Ws + (8 * w + g) * B2_WLD + q;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+        const float* x0 = xr + ks * 8;
+        uint32_t a0[4], a1[4];
+        a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * B2_XLD]);
+        a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * B2_XLD + 4]);
+        a1[0] = __float_as_uint(x0[16 * B2_XLD]);     a1[1] = __float_as_uint(x0[24 * B2_XLD]);
+        a1[2] = __float_as_uint(x0[16 * B2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * B2_XLD + 4]);
+        const uint32_t b[2] = {__float_as_uint(wr[ks * 8]), __float_as_uint(wr[ks * 8 + 4])};
+        mma_tf32(acc[0], a0, b);
+        mma_tf32(acc[1], a1, b);
+    }
+}
+
+// acc += X[:, koff : koff + 256] . frag^T, B fragments (64 values) from TMEM
+__device__ __forceinline__ void mma_k256_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    uint32_t bcur[16], bnxt[16];
+    tmem_ld16_nowait(taddr, bcur);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j + 1 < 4) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
+        const float* xr = Xs + g * B2_XLD + j * 64 + q;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const float* x0 = xr + ks * 8;
+            uint32_t a0[4], a1[4];
+            a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * B2_XLD]);
+            a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * B2_XLD + 4]);
+            a1[0] = __float_as_uint(x0[16 * B2_XLD]);     a1[1] = __float_as_uint(x0[24 * B2_XLD]);
+            a1[2] = __float_as_uint(x0[16 * B2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * B2_XLD + 4]);
+            const uint32_t b[2] = {bcur[2 * ks], bcur[2 * ks + 1]};
+            mma_tf32(acc[0], a0, b);
+            mma_tf32(acc[1], a1, b);
+        }
+        if (j + 1 < 4) {
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bcur[i] = bnxt[i];
+        }
+    }
+}
+
+// LSTM cell backward for one (row, unit): dh = d(link output h); returns dG and updates dc
+__device__ __forceinline__ float4 cell_bwd(float dh, const float4 a, float cc, float cp, float& dc) {
+    const float tc = tanhf(cc);
+    const float dct = dc + dh * a.w * (1.f - tc * tc);
+    float4 dg;
+    dg.x = dct * a.y * (1.f - a.x * a.x);
+    dg.y = dct * a.x * a.y * (1.f - a.y);
+    dg.z = dct * cp * a.z * (1.f - a.z);
+    dg.w = dh * tc * a.w * (1.f - a.w);
+    dc = dct * a.z;
+    return dg;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(D2_THREADS, 1)
+dec_seq2_bwd_kernel(DecSeq p) {
+    extern __shared__ uint8_t smem_raw[];
+    B2Smem& sm = *reinterpret_cast<B2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int rank = (int)cluster_rank(), cl = blockIdx.x / D2_CS, cta = blockIdx.x;
+    const int B = p.B, S = p.S, Tp = p.Tp;
+    constexpr int H = D2_H, E = D2_E, A = D2_A;
+    unsigned bar_target = 0;
+    int nprof = 0;
+#define B2_SYNC() do { grid_barrier2(p.bar, bar_target); \
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
+
+    if (tid == 0) {
+        mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&sm.tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_lane = sm.tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (w >= 4 ? 256u : 0u);
+    const int nt = w & 3, kh = w >> 2;       // D phases: warp = (n-tile of the cluster's 32 columns, half of the CTA's K quarter)
+
+    // [W_up | W_lat]^T fragments -> TMEM.  Output column n = 32 cl + 8 nt + g of [dx(512) | dh_rec(512)]; row of WcatT:
+    // dx part -> input column (layer 0: E + n, the ht slot; layers 1,2: n), dh_rec part -> in + (n - 512).
+    {
+        const int n = 32 * cl + 8 * nt + g;
+        for (int l = 0; l < 3; ++l) {
+            const int in = l == 0 ? E + A : H;
+            const int wrow = n < H ? (l == 0 ? E + n : n) : in + (n - H);
+            const float* src = p.WcatT[l] + (size_t)wrow * 4 * H + 512 * rank + 256 * kh;
+            for (int j = 0; j < 4; ++j) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = rtf32(__ldg(src + j * 64 + (i >> 1) * 8 + q + 4 * (i & 1)));
+                tmem_st16(tmem_lane + 64 * l + 16 * j, v);
+            }
+        }
+        tmem_wait_st();
+    }
+    if (cl < 2 * H / 64)
+        for (int idx = tid; idx < 64 * 32; idx += D2_THREADS) {
+            const int j = idx >> 5, k = (idx & 31) * 4;
+            float4 v = __ldg(reinterpret_cast<const float4*>(p.WcT + (size_t)(64 * cl + j) * A + 128 * rank + k));
+            *reinterpret_cast<float4*>(sm.Wcs + j * B2_WLD + k) = make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w));
+        }
+    if (cl < H / 64)
+        for (int idx = tid; idx < 64 * 32; idx += D2_THREADS) {
+            const int j = idx >> 5, k = (idx & 31) * 4;
+            float4 v = __ldg(reinterpret_cast<const float4*>(p.WaT + (size_t)(64 * cl + j) * H + 128 * rank + k));
+            *reinterpret_cast<float4*>(sm.Was + j * B2_WLD + k) = make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w));
+        }
+    uint32_t par_x = 0, par_a = 0;
+    if (tid == 0) { mbar_expect_tx(&sm.mbar_x, D2_XBYTES); mbar_expect_tx(&sm.mbar_a, D2_ABYTES); }
+    if (p.prof && cta == 0 && tid == 0) p.prof[1] = gtimer2();
+    nprof = 1;
+    cluster_sync_all();
+    B2_SYNC();
+
+    const int Tq = (Tp + D2_CS - 1) / D2_CS;
+    const int a_row = tid >> 2, a_c4 = tid & 3;          // phases A, C epilogue: (row, 4 columns of the CTA's 16)
+    const int d_row = tid >> 3, d_c = tid & 7;           // D phases epilogue: (row, 1 column of the CTA's 8)
+    for (int s = S - 1; s >= 0; --s) {
+        const bool last = (s == S - 1);
+        // ---- A: du (fused into the staging), dcvh = du . Wc ---------------------------------------------------------
+        if (cl < 2 * H / 64) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = (tid >> 5) + 8 * i, k = 128 * rank + 4 * lane;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < B) {
+                    const size_t r = (size_t)s * B + row;
+                    float4 d = __ldcg(reinterpret_cast<const float4*>(p.dzw + r * A + k));
+                    const float4 t = __ldcg(reinterpret_cast<const float4*>(p.ht + r * A + k));
+                    if (!last) {
+                        const float4 f = __ldcg(reinterpret_cast<const float4*>(p.dxh[0] + (size_t)row * (E + A + H) + E + k));
+                        d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+                    }
+                    v[i] = make_float4(d.x * (1.f - t.x * t.x), d.y * (1.f - t.y * t.y), d.z * (1.f - t.z * t.z), d.w * (1.f - t.w * t.w));
+                    if (cl == 0) *reinterpret_cast<float4*>(p.du + r * A + k) = v[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(sm.Xs + ((tid >> 5) + 8 * i) * B2_XLD + 4 * lane) =
+                    make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
+            __syncthreads();
+            float acc[2][4] = {};
+            mma_k128_smem(acc, sm.Xs, sm.Wcs);
+            {   // reduce-scatter, forward-style: warp w = n-tile w, owner CTA w/2
+                const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
+                const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = 16 * mt + g;
+                    st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
+                    st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+                }
+            }
+            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
+            if (tid < 128 && a_row < B) {
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int src = 0; src < 4; ++src) {
+                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + a_row) * 16 + 4 * a_c4);
+                    v4.x += r.x; v4.y += r.y; v4.z += r.z; v4.w += r.w;
+                }
+                const int n0 = 64 * cl + 16 * rank + 4 * a_c4;
+                *reinterpret_cast<float4*>(p.dcvh + (size_t)a_row * 2 * H + n0) = v4;
+                if (n0 < H) *reinterpret_cast<float4*>(p.dcv_all + ((size_t)s * B + a_row) * H + n0) = v4;
+            }
+        }
+        B2_SYNC();
+        // ---- B: attention backward, one pass over this CTA's quarter of T' ---------------------------------------------
+        if (cl < B) {
+            const int b = cl;
+            if (tid < H / 4) *reinterpret_cast<float4*>(sm.dcvs + 4 * tid) = __ldcg(reinterpret_cast<const float4*>(p.dcvh + (size_t)b * 2 * H + 4 * tid));
+            __syncthreads();
+            const int t_lo = rank * Tq, t_hi = min(Tp, t_lo + Tq);
+            float4 dq4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dq4[i] = *reinterpret_cast<const float4*>(sm.dcvs + 128 * i + 4 * lane);
+            float4 u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float asum = 0.f;
+            float* av = sm.recv;                 // a_t of the local range (recv is idle during this phase)
+            const float* enb = p.enc + (size_t)b * Tp * H + 4 * lane;
+            const float* alb = p.alpha + ((size_t)s * B + b) * Tp;
+            float4 x[4]; float al = 0.f;
+            int t = t_lo + w;
+            if (t < t_hi) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i));
+                al = __ldcg(alb + t);
+            }
+            while (t < t_hi) {
+                const int tn = t + 8;
+                float4 xn[4]; float aln = 0.f;
+                if (tn < t_hi) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xn[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)tn * H + 128 * i));
+                    aln = __ldcg(alb + tn);
+                }
+                float d = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d += x[i].x * dq4[i].x + x[i].y * dq4[i].y + x[i].z * dq4[i].z + x[i].w * dq4[i].w;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                const float at = al * d;          // alpha_t * dalpha_t
+                if (lane == 0) av[t - t_lo] = at;
+                asum += at;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { u[i].x += at * x[i].x; u[i].y += at * x[i].y; u[i].z += at * x[i].z; u[i].w += at * x[i].w; }
+                if (tn < t_hi) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = xn[i];
+                    al = aln;
+                }
+                t = tn;
+            }
+            if (lane == 0) sm.wstat[w] = asum;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sm.cvw + w * H + 128 * i + 4 * lane) = u[i];
+            __syncthreads();
+            {
+                float2 v = make_float2(0.f, 0.f);
+                float sr = 0.f;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) {
+                    const float2 c2 = *reinterpret_cast<const float2*>(sm.cvw + ww * H + 2 * tid);
+                    v.x += c2.x; v.y += c2.y; sr += sm.wstat[ww];
+                }
+                const int dst = tid >> 6;
+                st_async_v2(mapa(saddr(sm.cvx) + (uint32_t)((rank * 128 + (2 * tid & 127)) * 4), dst), v, mapa(saddr(&sm.mbar_a), dst));
+                if (tid < 4) st_async_v2(mapa(saddr(sm.statx) + (uint32_t)(rank * 8), tid), make_float2(sr, 0.f), mapa(saddr(&sm.mbar_a), tid));
+            }
+            mbar_wait(&sm.mbar_a, par_a); par_a ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);
+            const float dot = sm.statx[0] + sm.statx[2] + sm.statx[4] + sm.statx[6];
+            if (tid < 128) {
+                const float cvj = __ldcg(p.cvh + ((size_t)s * B + b) * 2 * H + 128 * rank + tid);
+                p.dq[((size_t)s * B + b) * H + 128 * rank + tid] = sm.cvx[tid] + sm.cvx[128 + tid] + sm.cvx[256 + tid] + sm.cvx[384 + tid] - dot * cvj;
+            }
+            float* dsb = p.ds_all + ((size_t)s * B + b) * Tp;
+            for (int tt = t_lo + tid; tt < t_hi; tt += D2_THREADS) dsb[tt] = av[tt - t_lo] - __ldcg(alb + tt) * dot;
+        }
+        B2_SYNC();
+        // ---- C: dh_top = dcvh[:, H:] + dq . Wa, fused cell backward of layer 2 ------------------------------------------
+        if (cl < H / 64) {
+            {
+                float4 v[4];
+                seg_load<128>(v, p.dq + (size_t)s * B * H + 128 * rank, H, B);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(sm.Xs + ((tid >> 5) + 8 * i) * B2_XLD + 4 * lane) =
+                        make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
+            }
+            __syncthreads();
+            float acc[2][4] = {};
+            mma_k128_smem(acc, sm.Xs, sm.Was);
+            {
+                const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
+                const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = 16 * mt + g;
+                    st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
+                    st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+                }
+            }
+            // operands of the cell backward are fetched while the exchange is in flight
+            const int n0 = 64 * cl + 16 * rank + 4 * a_c4;
+            const bool act_ok = tid < 128 && a_row < B;
+            float4 addv = make_float4(0.f, 0.f, 0.f, 0.f), rec = addv, ccv = addv, cpv = addv, dcv4 = addv, ga[4];
+            if (act_ok) {
+                const size_t e0 = (size_t)a_row * H + n0;
+                addv = __ldcg(reinterpret_cast<const float4*>(p.dcvh + (size_t)a_row * 2 * H + H + n0));
+                if (!last) rec = __ldcg(reinterpret_cast<const float4*>(p.dxh[2] + (size_t)a_row * 2 * H + H + n0));
+                ccv = __ldcg(reinterpret_cast<const float4*>(p.Cd[2] + (size_t)(s + 1) * B * H + e0));
+                cpv = __ldcg(reinterpret_cast<const float4*>(p.Cd[2] + (size_t)s * B * H + e0));
+                dcv4 = __ldcg(reinterpret_cast<const float4*>(p.dcd[2] + e0));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ga[i] = __ldcg(reinterpret_cast<const float4*>(p.act[2] + ((size_t)s * B + a_row) * 4 * H + 4 * (n0 + i)));
+            }
+            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
+            if (act_ok) {
+                float4 v4 = addv;
+#pragma unroll
+                for (int src = 0; src < 4; ++src) {
+                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + a_row) * 16 + 4 * a_c4);
+                    v4.x += r.x; v4.y += r.y; v4.z += r.z; v4.w += r.w;
+                }
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, rr[4] = {rec.x, rec.y, rec.z, rec.w};
+                const float cc[4] = {ccv.x, ccv.y, ccv.z, ccv.w}, cp[4] = {cpv.x, cpv.y, cpv.z, cpv.w};
+                float dc[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
+                const size_t e0 = (size_t)a_row * H + n0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float dm = dropout_scale(p.seed, 16 + 2, (uint32_t)((size_t)s * B * H + e0 + i), p.drop_rnn);
+                    const float dh = vv[i] * dm + rr[i];
+                    const float4 dg = cell_bwd(dh, ga[i], cc[i], cp[i], dc[i]);
+                    *reinterpret_cast<float4*>(p.act[2] + ((size_t)s * B + a_row) * 4 * H + 4 * (n0 + i)) = dg;
+                }
+                *reinterpret_cast<float4*>(p.dcd[2] + e0) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+            }
+        }
+        B2_SYNC();
+        // ---- D_l: [dx | dh_rec] = dG_l . [W_up | W_lat], fused cell backward of layer l-1 -------------------------------
+#pragma unroll 1
+        for (int l = 2; l >= 0; --l) {
+            const int in = l == 0 ? E + A : H;
+            {
+                const float* src = p.act[l] + (size_t)s * B * 4 * H + 512 * rank;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = tid + (half * 8 + i) * D2_THREADS, row = idx >> 7, k = (idx & 127) * 4;
+                        v[i] = row < B ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)row * 4 * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = tid + (half * 8 + i) * D2_THREADS, row = idx >> 7, k = (idx & 127) * 4;
+                        *reinterpret_cast<float4*>(sm.Xs + row * B2_XLD + k) = make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
+                    }
+                }
+            }
+            __syncthreads();
+            float acc[2][4] = {};
+            mma_k256_tmem(acc, sm.Xs + 256 * kh, tmem_lane + 64 * l);
+            {   // warp (nt, kh) -> owner CTA nt, source slot 2 rank + kh, 8 columns per owner
+                const uint32_t base = mapa(saddr(sm.recv), nt), bar = mapa(saddr(&sm.mbar_x), nt);
+                const int src = 2 * rank + kh;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = 16 * mt + g;
+                    st_async_v2(base + (uint32_t)(((src * 32 + r0) * 8 + 2 * q) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
+                    st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 8 + 2 * q) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+                }
+            }
+            const int n = 32 * cl + 8 * rank + d_c;            // output column of [dx(512) | dh_rec(512)]
+            const bool row_ok = d_row < B;
+            const bool fuse = row_ok && l > 0 && n < H;        // cell backward of layer l-1, unit n
+            float4 gav = make_float4(0.f, 0.f, 0.f, 0.f); float ccv = 0.f, cpv = 0.f, dcv = 0.f, rec = 0.f;
+            const int lb = l - 1, inb = lb == 0 ? E + A : H;
+            const size_t e = (size_t)d_row * H + n;
+            if (fuse) {
+                gav = __ldcg(reinterpret_cast<const float4*>(p.act[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n));
+                ccv = __ldcg(p.Cd[lb] + (size_t)(s + 1) * B * H + e); cpv = __ldcg(p.Cd[lb] + (size_t)s * B * H + e);
+                dcv = __ldcg(p.dcd[lb] + e);
+                if (!last) rec = __ldcg(p.dxh[lb] + (size_t)d_row * (inb + H) + inb + n);
+            }
+            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
+            if (row_ok) {
+                float v = 0.f;
+#pragma unroll
+                for (int src = 0; src < 8; ++src) v += sm.recv[(src * 32 + d_row) * 8 + d_c];
+                if (n >= H) p.dxh[l][(size_t)d_row * (in + H) + in + (n - H)] = v;           // dh_rec of layer l for step s-1
+                else if (l == 0) p.dxh[0][(size_t)d_row * (in + H) + E + n] = v;                // dht_feed for step s-1
+                else {
+                    const float dm = dropout_scale(p.seed, 16 + lb, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
+                    const float dh = v * dm + rec;
+                    const float4 dg = cell_bwd(dh, gav, ccv, cpv, dcv);
+                    *reinterpret_cast<float4*>(p.act[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n) = dg;
+                    p.dcd[lb][e] = dcv;
+                }
+            }
+            B2_SYNC();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_slot), "n"(512));
+    cluster_sync_all();
+#undef B2_SYNC
+}
+
+// d_enc[b][t][:] = sum_s alpha[s][b][t] * dcv[s][b][:] + ds[s][b][t] * q[s][b][:]   (one pass after the loop; replaces the
+// per-step read-modify-write of the whole encoder gradient).  grid (ceil(T'/8), B), 128 threads = 128 float4 columns.
+__global__ void __launch_bounds__(128) attn_denc_kernel(const float* __restrict__ alpha, const float* __restrict__ ds,
+                                                        const float* __restrict__ dcv, const float* __restrict__ qv,
+                                                        float* __restrict__ d_enc, int S, int B, int Tp, int H) {
+    const int b = blockIdx.y, t0 = blockIdx.x * 8, j = threadIdx.x * 4;
+    __shared__ float sa[8], sd[8];
+    float4 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int i = threadIdx.x & 7, t = t0 + i;
+            const float* src = threadIdx.x < 8 ? alpha : ds;
+            const float v = t < Tp ? src[((size_t)s * B + b) * Tp + t] : 0.f;
+            if (threadIdx.x < 8) sa[i] = v; else sd[i] = v;
+        }
+        __syncthreads();
+        const float4 c = *reinterpret_cast<const float4*>(dcv + ((size_t)s * B + b) * H + j);
+        const float4 qq = *reinterpret_cast<const float4*>(qv + ((size_t)s * B + b) * H + j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i].x += sa[i] * c.x + sd[i] * qq.x; acc[i].y += sa[i] * c.y + sd[i] * qq.y;
+            acc[i].z += sa[i] * c.z + sd[i] * qq.z; acc[i].w += sa[i] * c.w + sd[i] * qq.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (t0 + i < Tp) *reinterpret_cast<float4*>(d_enc + ((size_t)b * Tp + t0 + i) * H + j) = acc[i];
+}
+
+int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float* dcv, const float* q, float* d_enc, int S, int B, int Tp, int H) {
+    AST_CHECK(H == 512, "attn_denc: H must be 512");
+    attn_denc_kernel<<<dim3((Tp + 7) / 8, B), 128, 0, st>>>(alpha, ds, dcv, q, d_enc, S, B, Tp, H);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 bool dec_seq2_supported(const DecSeq& p) {
     return p.H == D2_H && p.E == D2_E && p.A == D2_A && p.NL == 3 && p.B >= 1 && p.B <= 32 && p.S >= 1 && p.Tp >= 1 &&
            (p.Tp + D2_CS - 1) / D2_CS <= 4 * 32 * 16 && p.encW != nullptr && p.encb != nullptr && p.bar != nullptr;
@@ -491,6 +955,31 @@ int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
     at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
     AST_CUDA_OK(cudaLaunchKernelEx(&cfg, dec_seq2_fwd_kernel, p));
+    ++g_kernel_launches;
+    return 0;
+}
+
+int dec_seq2_bwd(cudaStream_t st, const DecSeq& p) {
+    AST_CHECK(dec_seq2_supported(p) && p.dzw && p.dcv_all && p.ds_all, "dec_seq2_bwd: unsupported geometry");
+    const size_t smem = sizeof(B2Smem) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AST_CUDA_OK(cudaFuncSetAttribute(dec_seq2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    AST_CUDA_OK(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(D2_NCL * D2_CS);
+    cfg.blockDim = dim3(D2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = D2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, dec_seq2_bwd_kernel, p));
     ++g_kernel_launches;
     return 0;
 }

@@ -98,6 +98,7 @@ struct DecSeq {
     const float* WoT; const float* WcT; const float* WaT; const float* WcatT[AST_MAXL];
     const int* y; const unsigned char* use_true;
     const float* enc; float* d_enc;
+    const float* dzw; float* dcv_all; float* ds_all;   // dec_seq2 backward: dz . Wo for all steps (in); per-step dcv and ds (out)
     const float* encW; const float* encb;   // dec_seq2: enc . W_a (B*T' x H) and enc . b_a (B x T'), precomputed per sequence
     float* x0; float* act[AST_MAXL]; float* Hd[AST_MAXL]; float* Cd[AST_MAXL]; float* hdd[AST_MAXL];
     float* q; float* scores; float* alpha; float* cvh; float* ht; float* logits; float* row_loss;
@@ -112,6 +113,8 @@ int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);
 // second-generation forward (dec_seq2.cu): TMEM-resident weights, cluster K-split, logits deferred to the caller
 bool dec_seq2_supported(const DecSeq& p);
 int dec_seq2_fwd(cudaStream_t st, const DecSeq& p);
+int dec_seq2_bwd(cudaStream_t st, const DecSeq& p);
+int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float* dcv, const float* q, float* d_enc, int S, int B, int Tp, int H);
 // softmax-CE (+ gradient in place, argmax) for every (step, row) of a decoder pass in one launch
 int softmax_ce_all(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, float* row_loss, int* argmax_out, int S, int B, int V);
 int skinny(cudaStream_t st, const SkinnyArgs& p, bool exact);

@@ -63,6 +63,7 @@ struct ast_model {
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
     float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
     float *encW, *encb;        // dec_seq2: enc_states . W_a and enc_states . b_a
+    float *dzw, *dcv_all, *ds_all, *dE;   // dec_seq2 backward
     int dec_v2 = 1;
     float *draw1, *dA1, *da0p, *draw0, *dW1p, *dW0pad;
     // decoder (training)
@@ -222,6 +223,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->dcvh = a.get<float>((size_t)B * 2 * H);
     m->dalpha = a.get<float>((size_t)B * Tp);
     m->dq = a.get<float>(SB * H);
+    m->dzw = a.get<float>(SB * A); m->dcv_all = a.get<float>(SB * H); m->ds_all = a.get<float>(SB * Tp); m->dE = a.get<float>(SB * E);
     m->dhtop = a.get<float>((size_t)B * H);
     m->words_used = a.get<int>(SB);
     m->argmax_steps = a.get<int>(SB);
@@ -503,7 +505,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
     p.du = m->du; p.dcvh = m->dcvh; p.dalpha = m->dalpha; p.dq = m->dq; p.demb = m->g("embed_dec/W");
     p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
     p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr;
-    p.encW = m->encW; p.encb = m->encb;
+    p.encW = m->encW; p.encb = m->encb; p.dzw = m->dzw; p.dcv_all = m->dcv_all; p.ds_all = m->ds_all;
     return p;
 }
 
@@ -582,11 +584,20 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_CUDA_OK(cudaMemsetAsync(m->d_enc, 0, sizeof(float) * (size_t)TB * H, st));
         for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
     }
+    bool dec_bwd_v2 = false;
     // ---- decoder BPTT: data gradients step by step -----------------------------------------------
     if (m->dec_fused) {
         DecSeq ds = make_dec_seq(m, m->y_dev, m->use_true_dev, true);
         if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof + 4096;
-        AST_TRY(dec_seq_bwd(st, ds, ex));
+        dec_bwd_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
+        if (dec_bwd_v2) {
+            // dz . Wo for every step at once (the only place the vocabulary enters the decoder BPTT)
+            AST_TRY(gemm(m, st, false, false, SB, A, V, m->logits, Vp, m->p("out/W"), A, m->dzw, A, nullptr, 0.f, 0, SITE_DEC_PRE));
+            AST_TRY(dec_seq2_bwd(st, ds));
+            AST_TRY(attn_denc(st, m->alpha, m->ds_all, m->dcv_all, m->q, m->d_enc, S, B, Tp, H));
+        } else {
+            AST_TRY(dec_seq_bwd(st, ds, ex));
+        }
     }
     else for (int s = S - 1; s >= 0; --s) {
         const float* dz = m->logits + (size_t)s * B * Vp;
@@ -641,6 +652,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     };
     // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
     AST_TRY(fork());
+    if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
+        AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, m->actd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
+        AST_TRY(embed_scatter(sw, m->g("embed_dec/W"), m->dE, E, m->words_used, SB, E, 0, de, m->cur_seed, 32));
+    }
     AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
     AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, false));
     AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 0.f, -1, SITE_DEC_WGRAD));

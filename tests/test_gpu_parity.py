@@ -262,10 +262,12 @@ def test_encoder_wavefront_and_side_stream_match_serial(dev, exact):
     for o in out[1:]:
         assert o[0] == out[0][0]
         assert np.array_equal(o[1], out[0][1])
-        if exact:
-            assert np.array_equal(o[2], out[0][2])
-        else:       # split-K weight gradients accumulate with atomics: order-dependent fp32 rounding only
-            assert np.abs(o[2] - out[0][2]).max() <= 1e-5 * np.abs(out[0][2]).max()
+        # gradients: float atomics (EmbedID scatter-add, split-K weight gradients) make the summation order, hence the
+        # last bits, run-dependent even on one stream; everything else is the same arithmetic
+        tol = 2e-6 if exact else 2e-5
+        for k, (_, off, shp) in e.info.items():
+            n = int(np.prod(shp))
+            assert _relerr(o[2][off:off + n], out[0][2][off:off + n]) <= tol, k
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
