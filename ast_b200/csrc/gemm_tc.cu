@@ -11,6 +11,10 @@
 // forward tensors in place -- no transposed copies.  Weight gradients have K = T'*B (thousands) and a
 // small output, so they run split-K over blockIdx.z with fp32 red.global.add into a zeroed C.
 //
+// S3 variant ("3xTF32", fp32-faithful): C = x.y + lo(x).y + x.lo(y), lo(v) = v - trunc_tf32(v) precomputed by split_lo();
+// the raw fp32 tiles double as the high parts (the tensor core truncates them itself), so a k-block stages four tiles
+// and issues three MMAs per k-step.  Used for the forward convolutions that feed train-mode BatchNorm.
+//
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
 // (TMEM lane quadrant = warp_id % 4).  Tile 128 x 128 x 32 (one 128-byte swizzle row of fp32 per k-block),
 // 5-stage mbarrier ring (32 KB per stage).
@@ -104,18 +108,22 @@ struct TcParams {
 };
 
 // TA: A operand is M-major (A stored K x M).  NB: B operand is N-major (B stored K x N).
-template <bool TA, bool NB>
+template <bool TA, bool NB, bool S3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapBl, TcParams p) {
+    constexpr int NST = S3 ? 3 : TSTAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + TSTAGES * STAGE_A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TSTAGES * (STAGE_A_BYTES + STAGE_B_BYTES));
-    uint64_t* full = bars;                 // [TSTAGES]
-    uint64_t* empty = bars + TSTAGES;      // [TSTAGES]
-    uint64_t* tmem_full = bars + 2 * TSTAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TSTAGES + 1);
+    uint8_t* sB = smem + NST * STAGE_A_BYTES;
+    uint8_t* sAl = smem + NST * (STAGE_A_BYTES + STAGE_B_BYTES);          // S3 only: low parts
+    uint8_t* sBl = sAl + NST * STAGE_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (S3 ? 2 : 1) * NST * (STAGE_A_BYTES + STAGE_B_BYTES));
+    uint64_t* full = bars;                 // [NST]
+    uint64_t* empty = bars + NST;          // [NST]
+    uint64_t* tmem_full = bars + 2 * NST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
@@ -124,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nkb = min(p.kb_per_split, nkb_total - kb0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -141,10 +149,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ===== TMA producer =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % TSTAGES;
-                const uint32_t ph = (i / TSTAGES) & 1;
+                const int s = i % NST;
+                const uint32_t ph = (i / NST) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], STAGE_A_BYTES + STAGE_B_BYTES);
+                mbar_expect_tx(&full[s], (S3 ? 2 : 1) * (STAGE_A_BYTES + STAGE_B_BYTES));
                 const int k0 = (kb0 + i) * TBK;
                 uint8_t* a = sA + s * STAGE_A_BYTES;
                 uint8_t* b = sB + s * STAGE_B_BYTES;
@@ -156,6 +164,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 else
 #pragma unroll
                     for (int j = 0; j < TBN / 32; ++j) tma_load_2d(&mapB, &full[s], b + j * (TBK * 128), n0 + 32 * j, k0);
+                if (S3) {          // K-major operands only (host enforces)
+                    tma_load_2d(&mapAl, &full[s], sAl + s * STAGE_A_BYTES, k0, m0);
+                    tma_load_2d(&mapBl, &full[s], sBl + s * STAGE_B_BYTES, k0, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -178,10 +190,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint64_t ad0 = a_base + (uint64_t)(s * (STAGE_A_BYTES >> 4));
                 const uint64_t bd0 = b_base + (uint64_t)(s * (STAGE_B_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < TBK / 8; ++k)
+                for (int k = 0; k < TBK / 8; ++k) {
                     umma_tf32(tmem_base, ad0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (S3) {
+                        const uint64_t al0 = ad0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
+                        const uint64_t bl0 = bd0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
+                        umma_tf32(tmem_base, al0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, 1u);
+                        umma_tf32(tmem_base, ad0 + (uint64_t)(k * a_kstep), bl0 + (uint64_t)(k * b_kstep), idesc, 1u);
+                    }
+                }
                 umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
-                if (++s == TSTAGES) { s = 0; ph ^= 1; }
+                if (++s == NST) { s = 0; ph ^= 1; }
             }
             umma_commit(tmem_full);              // accumulator complete
         }
@@ -255,17 +274,54 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
     return r == CUDA_SUCCESS;
 }
 
-template <bool TA, bool NB>
-static int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid) {
-    auto kern = gemm_tc_kernel<TA, NB>;
+template <bool TA, bool NB, bool S3>
+static int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mal, const CUtensorMap& mbl,
+                     const TcParams& p, dim3 grid) {
+    auto kern = gemm_tc_kernel<TA, NB, S3>;
+    constexpr uint32_t smem = S3 ? (2 * 3 * (STAGE_A_BYTES + STAGE_B_BYTES) + 1024 + 256) : TC_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
-        AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, p);
+    kern<<<grid, TC_THREADS, smem, st>>>(ma, mb, mal, mbl, p);
     AST_LAUNCH_OK();
     return 0;
+}
+
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        float4 r;
+        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        reinterpret_cast<float4*>(lo)[i] = r;
+    }
+}
+// lo[i] = x[i] - trunc_tf32(x[i]) (the part of an fp32 value the tensor core drops); n must be a multiple of 4
+int split_lo(cudaStream_t st, const float* x, float* lo, size_t n) {
+    AST_CHECK(n % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)lo % 16 == 0, "split_lo: need 16-byte aligned buffers, n %% 4 == 0");
+    const size_t n4 = n / 4;
+    const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+    split_lo_kernel<<<std::max(blocks, 1), 256, 0, st>>>(x, lo, n4);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// C = A . B^T (+bias) with fp32-faithful 3xTF32 (NT form only).  Alo / Blo = split_lo(A) / split_lo(B), same layouts.
+int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo, int ldb,
+                float* C, int ldc, const float* bias) {
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    CUtensorMap ma, mb, mal, mbl;
+    const bool ok = make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) && make_map(&mal, Alo, (uint64_t)K, (uint64_t)M, lda, TBM, false) &&
+                    make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) && make_map(&mbl, Blo, (uint64_t)K, (uint64_t)N, ldb, TBN, false);
+    if (!ok) return 1;
+    const int nkb = cdiv(K, TBK);
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb};
+    dim3 grid(cdiv(N, TBN), cdiv(M, TBM), 1);
+    return launch_tc<false, false, true>(st, ma, mb, mal, mbl, p, grid);
 }
 
 // General entry: returns 1 when the tensor-core path cannot take the problem (caller falls back to SIMT).
@@ -292,10 +348,10 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
         else if (beta != 1.f) return 1;
     }
     dim3 grid(cdiv(N, TBN), cdiv(M, TBM), splits);
-    if (!ta && tb) return launch_tc<false, false>(st, ma, mb, p, grid);
-    if (!ta && !tb) return launch_tc<false, true>(st, ma, mb, p, grid);
-    if (ta && !tb) return launch_tc<true, true>(st, ma, mb, p, grid);
-    return launch_tc<true, false>(st, ma, mb, p, grid);
+    if (!ta && tb) return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
+    if (!ta && !tb) return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
+    if (ta && !tb) return launch_tc<true, true, false>(st, ma, mb, ma, mb, p, grid);
+    return launch_tc<true, false, false>(st, ma, mb, ma, mb, p, grid);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

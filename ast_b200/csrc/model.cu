@@ -58,6 +58,7 @@ struct ast_model {
     // workspace
     Arena ws; int wsB = 0, wsT = 0, wsL = 0, wsN = 0, wsSteps = 0;
     // ---- buffers (valid after bind_workspace) ----
+    float *a0p_lo, *W1p_lo; int conv3x = 1;   // 3xTF32 operands of the CNN_1 forward GEMM (split_lo)
     float *cols0, *W0pad, *raw0, *a0p, *W1p, *raw1, *mean0, *invstd0, *mean1, *invstd1, *rnn_in, *rnn_rev, *Xn;
     double *bnstats, *norm_sq;
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
@@ -173,6 +174,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->raw0 = a.get<float>(M0 * C0);
     m->a0p = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
     m->W1p = a.get<float>((size_t)C1 * m->K1);
+    m->a0p_lo = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
+    m->W1p_lo = a.get<float>((size_t)C1 * m->K1);
     m->raw1 = a.get<float>(M1 * C1);
     m->bnstats = a.get<double>(2 * (size_t)std::max(C0, C1));
     m->norm_sq = a.get<double>(2);
@@ -290,6 +293,7 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     AST_CUDA_OK(cudaMemsetAsync(m->W0pad, 0, sizeof(float) * m->C0 * m->ld0, st));
     AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
     AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
+    AST_TRY(split_lo(st, m->W1p, m->W1p_lo, (size_t)m->C1 * m->K1));
     AST_CUDA_OK(cudaMemsetAsync(m->WoT, 0, sizeof(float) * m->A * m->Vp, st));
     AST_TRY(transpose(st, m->p("out/W"), m->A, m->WoT, m->Vp, m->V, m->A));
     AST_TRY(transpose(st, m->p("context/W"), 2 * m->H, m->WcT, m->A, m->A, 2 * m->H));
@@ -349,7 +353,17 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
                         B * Fp, T1, S0, c.cnn_ph[1], C0));
     AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
-    AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr, SITE_CONV1));
+    int conv1_done = 0;
+    if (m->tc_gemm && !m->exact && m->conv3x && m->K1 % 4 == 0) {
+        // fp32-faithful on the tensor cores: 3xTF32 (x.y + lo(x).y + x.lo(y)); single-pass TF32 here wrecks the BatchNorm
+        // parameter gradients downstream, the fp32 SIMT kernel was 22 % of the forward pass
+        const size_t n_a0p = (size_t)B * Fp * S0 * C0 + (size_t)(c.cnn_kh[1] + 8) * C0;
+        AST_TRY(split_lo(st, m->a0p, m->a0p_lo, n_a0p));
+        const int r = gemm_tc3_nt(st, M1, C1, m->K1, m->a0p, m->a0p_lo, c.cnn_sh[1] * C0, m->W1p, m->W1p_lo, m->K1, m->raw1, C1, nullptr);
+        if (r < 0) return r;
+        conv1_done = (r == 0);
+    }
+    if (!conv1_done) AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr, SITE_CONV1));
     if (train) {
         AST_TRY(bn_stats(st, m->raw1, m->bnstats, M1, C1, Rs, Tp));
         AST_TRY(bn_finalize(st, m->bnstats, m->mean1, m->invstd1, bn1, bn1 + C1, C1, (double)B * Fp * Tp, BN_EPS, BN_DECAY, true));
@@ -899,6 +913,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
     else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
+    else if (!strcmp(key, "conv3x")) m->conv3x = value != 0;
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
@@ -1138,6 +1153,15 @@ int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const 
         return r;
     }
     return sgemm_simt(S_(stream), ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+}
+int ast_split_lo(const float* x, float* lo, long long n, void* stream) { return split_lo(S_(stream), x, lo, (size_t)n); }
+int ast_gemm3_nt(int M, int N, int K, const float* A, float* Alo, long long a_floats, int lda, const float* B, float* Blo,
+                 long long b_floats, int ldb, float* C, int ldc, const float* bias, void* stream) {
+    AST_TRY(split_lo(S_(stream), A, Alo, (size_t)a_floats));
+    AST_TRY(split_lo(S_(stream), B, Blo, (size_t)b_floats));
+    const int r = gemm_tc3_nt(S_(stream), M, N, K, A, Alo, lda, B, Blo, ldb, C, ldc, bias);
+    AST_CHECK(r <= 0, "3xTF32 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+    return r;
 }
 int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, float* out_or_dout, int T, int B, int h,
                  const float* dh_fin, const float* dc_fin, int exact, void* stream) {

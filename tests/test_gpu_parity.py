@@ -212,6 +212,31 @@ def test_fused_and_per_step_decoder_paths_agree(dev):
     assert np.abs(out[0][2] - out[1][2]).max() <= 1e-4 * np.abs(out[1][2]).max()
 
 
+@pytest.mark.parametrize("M,N,K,lda", [(500, 512, 1152, 256), (300, 200, 120, 120), (4000, 512, 1152, 1152)])
+def test_tcgen05_3xtf32_gemm_is_fp32_faithful(lib, dev, M, N, K, lda):
+    """gemm_tc3 (x.y + lo(x).y + x.lo(y) on tcgen05): error at the fp32 level, ~1000x below single-pass TF32, also on
+    the overlapping-rows operand of the CNN_1 implicit GEMM (lda < K)."""
+    from ast_b200._lib import check, ptr
+    rng = np.random.default_rng(5)
+    buf = rng.standard_normal(M * lda + K).astype(np.float32)
+    nb = (buf.size + 3) // 4 * 4
+    buf = np.concatenate([buf, np.zeros(nb - buf.size, np.float32)])
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    Av = np.lib.stride_tricks.as_strided(buf, (M, K), (lda * 4, 4))
+    want = Av.astype(np.float64) @ W.T.astype(np.float64) + bias
+    dA, dW, db = (torch.as_tensor(x, device=dev) for x in (buf, W, bias))
+    dAl, dWl = torch.empty_like(dA), torch.empty_like(dW)
+    dC = torch.full((M, N), 7.0, device=dev)
+    check(lib.ast_gemm3_nt(M, N, K, ptr(dA), ptr(dAl), dA.numel(), lda, ptr(dW), ptr(dWl), dW.numel(), K, ptr(dC), N, ptr(db), _stream(dev)))
+    torch.cuda.synchronize()
+    err = np.abs(dC.cpu().numpy() - want).max() / np.sqrt(K)
+    assert err < 5e-6, err
+    # and the low parts are what the tensor core drops
+    lo = dAl.cpu().numpy()
+    assert np.array_equal(lo, buf - (buf.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32))
+
+
 @pytest.mark.parametrize("B,T,ss", [(32, 330, True), (19, 140, True), (7, 90, False)])
 def test_decoder_v2_matches_v1_in_tf32_mode(dev, B, T, ss):
     """dec_seq2.cu (TMEM-resident weights, cluster K-split, one-pass attention through enc.W_a, logits/CE deferred to one
