@@ -19,6 +19,7 @@
 //    seq2seq.py:431-436) compute logits + argmax in-loop, because the next embedding depends on them.
 //  A decoder step is 5 grid barriers (3 LSTM + attention + context) instead of 9.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "cluster_dev.cuh"
 #include "decoder_dev.cuh"
 
@@ -934,14 +935,13 @@ bool dec_seq2_supported(const DecSeq& p) {
            (p.Tp + D2_CS - 1) / D2_CS <= 4 * 32 * 16 && p.encW != nullptr && p.encb != nullptr && p.bar != nullptr;
 }
 
-int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
-    AST_CHECK(dec_seq2_supported(p), "dec_seq2_fwd: unsupported geometry");
-    const size_t smem = sizeof(D2Smem) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        AST_CUDA_OK(cudaFuncSetAttribute(dec_seq2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+// 32 clusters x 4 CTAs, one CTA per SM.  The cooperative attribute makes the runtime verify co-residency (the kernels
+// spin on a grid barrier).  Profilers that serialise kernels reject cooperative + cluster launches
+// (cudaErrorInvalidConfiguration under ncu); co-residency still holds there (128 CTAs, 148 SMs, nothing else running), so the
+// launch is retried with the cluster attribute only.
+template <class KernT>
+static int launch_d2(KernT kern, cudaStream_t st, const DecSeq& p, size_t smem) {
+    AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AST_CUDA_OK(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(D2_NCL * D2_CS);
@@ -953,35 +953,31 @@ int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
     at[0].val.clusterDim.x = D2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
-    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, dec_seq2_fwd_kernel, p));
+    // AST_NO_COOP=1 (tools/ncu_capture.sh): ncu aborts on the rejected cooperative launch before the retry below can run
+    static const bool no_coop = getenv("AST_NO_COOP") != nullptr;
+    cfg.attrs = at; cfg.numAttrs = no_coop ? 1 : 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess && !no_coop) {
+        (void)cudaGetLastError();
+        int nclusters = 0;
+        cfg.numAttrs = 1;
+        AST_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+        AST_CHECK(nclusters >= D2_NCL, "decoder-sequence kernel: only %d of %d clusters can be co-resident", nclusters, D2_NCL);
+        e = cudaLaunchKernelEx(&cfg, kern, p);
+    }
+    AST_CUDA_OK(e);
     ++g_kernel_launches;
     return 0;
 }
 
+int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
+    AST_CHECK(dec_seq2_supported(p), "dec_seq2_fwd: unsupported geometry");
+    return launch_d2(dec_seq2_fwd_kernel, st, p, sizeof(D2Smem) + 128);
+}
+
 int dec_seq2_bwd(cudaStream_t st, const DecSeq& p) {
     AST_CHECK(dec_seq2_supported(p) && p.dzw && p.dcv_all && p.ds_all, "dec_seq2_bwd: unsupported geometry");
-    const size_t smem = sizeof(B2Smem) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        AST_CUDA_OK(cudaFuncSetAttribute(dec_seq2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    AST_CUDA_OK(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(D2_NCL * D2_CS);
-    cfg.blockDim = dim3(D2_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = D2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeCooperative;
-    at[1].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
-    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, dec_seq2_bwd_kernel, p));
-    ++g_kernel_launches;
-    return 0;
+    return launch_d2(dec_seq2_bwd_kernel, st, p, sizeof(B2Smem) + 128);
 }
 
 }  // namespace ast

@@ -83,7 +83,7 @@ struct ast_model {
     float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
-    cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr; int overlap = 1;
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr; int overlap = 1; bool tr_pending = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}; cudaEvent_t ev_pool[128] = {}; int enc_chunk = 32;
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
@@ -294,16 +294,24 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
     AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
     AST_TRY(split_lo(st, m->W1p, m->W1p_lo, (size_t)m->C1 * m->K1));
-    AST_CUDA_OK(cudaMemsetAsync(m->WoT, 0, sizeof(float) * m->A * m->Vp, st));
-    AST_TRY(transpose(st, m->p("out/W"), m->A, m->WoT, m->Vp, m->V, m->A));
-    AST_TRY(transpose(st, m->p("context/W"), 2 * m->H, m->WcT, m->A, m->A, 2 * m->H));
-    AST_TRY(transpose(st, m->p("attn_Wa/W"), m->H, m->WaT, m->H, m->H, m->H));
+    // The transposed decoder weights are consumed by backward only: build them on the side stream, concurrently with the
+    // forward pass (backward_impl waits on ev_tr).
+    cudaStream_t ts = m->overlap ? m->side : st;
+    if (ts != st) {
+        AST_CUDA_OK(cudaEventRecord(m->ev_tr, st));
+        AST_CUDA_OK(cudaStreamWaitEvent(ts, m->ev_tr, 0));
+    }
+    AST_CUDA_OK(cudaMemsetAsync(m->WoT, 0, sizeof(float) * m->A * m->Vp, ts));
+    AST_TRY(transpose(ts, m->p("out/W"), m->A, m->WoT, m->Vp, m->V, m->A));
+    AST_TRY(transpose(ts, m->p("context/W"), 2 * m->H, m->WcT, m->A, m->A, 2 * m->H));
+    AST_TRY(transpose(ts, m->p("attn_Wa/W"), m->H, m->WaT, m->H, m->H, m->H));
     for (int l = 0; l < m->NL; ++l) {
         const int in = m->in_dec(l);
-        AST_TRY(transpose(st, m->p((lname(l, "dec") + "/upward/W").c_str()), in, m->WcatT[l], 4 * m->H, 4 * m->H, in));
-        AST_TRY(transpose(st, m->p((lname(l, "dec") + "/lateral/W").c_str()), m->H, m->WcatT[l] + (size_t)in * 4 * m->H,
+        AST_TRY(transpose(ts, m->p((lname(l, "dec") + "/upward/W").c_str()), in, m->WcatT[l], 4 * m->H, 4 * m->H, in));
+        AST_TRY(transpose(ts, m->p((lname(l, "dec") + "/lateral/W").c_str()), m->H, m->WcatT[l] + (size_t)in * 4 * m->H,
                           4 * m->H, 4 * m->H, m->H));
     }
+    if (ts != st) { AST_CUDA_OK(cudaEventRecord(m->ev_tr, ts)); m->tr_pending = true; }
     m->weights_dirty = false;
     return 0;
 }
@@ -430,6 +438,9 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             }
         AST_CUDA_OK(cudaStreamWaitEvent(st, ev[(NL - 1) * nch + nch - 1], 0));
     }
+    // the side-stream weight transposes finished long ago; ordering them before everything that follows on `st` makes a
+    // later parameter write on `st` safe without any host synchronisation
+    if (m->tr_pending) { AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_tr, 0)); m->tr_pending = false; }
     m->have_fwd = false;
     return 0;
 }
@@ -592,6 +603,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     const bool ex = m->exact != 0;
     const float de = c.drop_embed, dr = c.drop_rnn;
     const int SB = S * B, TB = Tp * B;
+    if (m->tr_pending) { AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_tr, 0)); m->tr_pending = false; }
     {   // cleargrads for the accumulate-style outputs
         const ParamInfo* pe = nullptr; for (auto& pi : m->pinfo) if (pi.name == "embed_dec/W") pe = &pi;
         AST_CUDA_OK(cudaMemsetAsync(m->G + pe->off, 0, sizeof(float) * pe->count, st));
@@ -849,6 +861,7 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     AST_CREATE_CHECK(e == cudaSuccess, "cudaStreamCreate: %s", cudaGetErrorString(e));
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_tr, cudaEventDisableTiming);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->lay[i], cudaStreamNonBlocking);
     for (int i = 0; i < 128 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
@@ -862,6 +875,7 @@ int ast_destroy(ast_model* m) {
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
     for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_tr) cudaEventDestroy(m->ev_tr);
     if (m->side) cudaStreamDestroy(m->side);
     for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
     for (int i = 0; i < 128; ++i) if (m->ev_pool[i]) cudaEventDestroy(m->ev_pool[i]);

@@ -73,37 +73,101 @@ def drop_frame_mask(n_frames, drop_rate):
 
 
 class DevicePacker:
-    """Varlen utterances -> padded (B,T,D) batch on the device with one kernel."""
+    """Varlen utterances -> padded (B,T,D) batch on the device: ONE pinned staging buffer, ONE async H2D copy, ONE kernel.
+
+    The host side of `dataloader.py:156-162` (`F.pad_sequence` + `to_gpu`) without its per-batch allocations: features,
+    row offsets, lengths and the frame-keep masks are written straight into a persistent pinned buffer (two slots, so the
+    host can fill batch i+1 while the copy of batch i is in flight), copied with a single `cudaMemcpyAsync`, and expanded
+    on the device by the pack kernel (CMVN, frame zeroing and input noise fused; `csrc/misc.cu::pack_cmvn_kernel`)."""
+
+    SLOTS = 2
 
     def __init__(self, device):
         self.device = device
         self.lib = _lib.load()
+        self._host = [None] * self.SLOTS
+        self._dev = [None] * self.SLOTS
+        self._done = [None] * self.SLOTS
+        self._slot = 0
 
-    def pack(self, utts, max_sp, keep_masks=None, cmvn=None, noise_sigma=0.0, seed=0):
-        utts = [np.ascontiguousarray(u[:max_sp], dtype=np.float32) for u in utts]
+    @staticmethod
+    def _up(n, a=16):
+        return (n + a - 1) // a * a
+
+    def _buffers(self, slot, nbytes):
+        if self._host[slot] is None or self._host[slot].numel() < nbytes:
+            cap = max(nbytes * 3 // 2, 1 << 20)
+            self._host[slot] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self._dev[slot] = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            self._done[slot] = None
+        if self._done[slot] is not None:
+            self._done[slot].synchronize()          # the copy that last used this slot (two batches ago) has finished
+        return self._host[slot], self._dev[slot]
+
+    def pack(self, utts, max_sp, keep_masks=None, cmvn=None, noise_sigma=0.0, seed=0, labels=None, bits=None):
+        """-> X (B,T,D) on the device; with `labels` ((B,L) int32) and optionally `bits` ((L-1,) uint8 scheduled-sampling
+        draws) riding on the same copy: -> (X, y_dev, bits_dev)."""
         B, D = len(utts), utts[0].shape[1]
-        lens = np.asarray([len(u) for u in utts], dtype=np.int32)
+        lens = np.asarray([min(len(u), max_sp) for u in utts], dtype=np.int32)
         T = int(lens.max())
-        off = np.zeros(B, dtype=np.int64)
-        off[1:] = np.cumsum(lens[:-1])
-        raw = torch.from_numpy(np.concatenate(utts, axis=0)).pin_memory().to(self.device, non_blocking=True)
-        d_off = torch.from_numpy(off).to(self.device)
-        d_len = torch.from_numpy(lens).to(self.device)
-        keep = None
+        n_raw = int(lens.sum()) * D * 4
+        o_off = self._up(n_raw)
+        o_len = o_off + self._up(B * 8)
+        o_keep = o_len + self._up(B * 4)
+        o_cmvn = o_keep + (self._up(B * T) if keep_masks is not None else 0)
+        o_lab = o_cmvn + (self._up(2 * B * D * 4) if cmvn is not None else 0)        # per-utterance (speaker) scale / offset
+        n_lab = labels.size * 4 if labels is not None else 0
+        o_bits = o_lab + self._up(n_lab)
+        total = o_bits + (self._up(len(bits)) if bits is not None else 0)
+        slot = self._slot
+        self._slot = (slot + 1) % self.SLOTS
+        host, dev = self._buffers(slot, total)
+        hnp = host.numpy()
+        raw = hnp[:n_raw].view(np.float32).reshape(-1, D)
+        off = hnp[o_off:o_off + B * 8].view(np.int64)
+        r = 0
+        for i, u in enumerate(utts):
+            n = int(lens[i])
+            raw[r:r + n] = u[:n]
+            off[i] = r
+            r += n
+        hnp[o_len:o_len + B * 4].view(np.int32)[:] = lens
         if keep_masks is not None:
-            km = np.zeros((B, T), dtype=np.uint8)
+            km = hnp[o_keep:o_keep + B * T].reshape(B, T)
+            km[:] = 0
             for i, k in enumerate(keep_masks):
-                km[i, :len(k)] = k[:T]
-            keep = torch.from_numpy(km).to(self.device)
+                n = min(len(k), T)
+                km[i, :n] = k[:n]
+        if cmvn is not None:
+            cm = hnp[o_cmvn:o_cmvn + 2 * B * D * 4].view(np.float32).reshape(2, B, D)
+            cm[0] = np.broadcast_to(np.asarray(cmvn[0], dtype=np.float32), (B, D))
+            cm[1] = np.broadcast_to(np.asarray(cmvn[1], dtype=np.float32), (B, D))
+        if labels is not None:
+            hnp[o_lab:o_lab + n_lab].view(np.int32)[:] = np.asarray(labels, dtype=np.int32).ravel()
+        if bits is not None:
+            hnp[o_bits:o_bits + len(bits)] = np.asarray(bits, dtype=np.uint8)
+        dev[:total].copy_(host[:total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._done[slot] = ev
+        d_raw = dev[:n_raw].view(torch.float32)
+        d_off = dev[o_off:o_off + B * 8].view(torch.int64)
+        d_len = dev[o_len:o_len + B * 4].view(torch.int32)
+        keep = dev[o_keep:o_keep + B * T] if keep_masks is not None else None
         scale = offset = None
         if cmvn is not None:
-            scale = torch.from_numpy(np.ascontiguousarray(cmvn[0], dtype=np.float32)).to(self.device)
-            offset = torch.from_numpy(np.ascontiguousarray(cmvn[1], dtype=np.float32)).to(self.device)
+            d_cm = dev[o_cmvn:o_cmvn + 2 * B * D * 4].view(torch.float32)
+            scale, offset = d_cm[:B * D], d_cm[B * D:]
         X = torch.empty(B, T, D, dtype=torch.float32, device=self.device)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self.lib.ast_pack_cmvn(ptr(raw), ptr(d_off), ptr(d_len), ptr(scale), ptr(offset), ptr(keep), None,
+        check(self.lib.ast_pack_cmvn(ptr(d_raw), ptr(d_off), ptr(d_len), ptr(scale), ptr(offset), ptr(keep), None,
                                      float(noise_sigma), int(seed), ptr(X), B, T, D, st), "ast_pack_cmvn")
-        return X
+        if labels is None:
+            return X
+        # the staging slot is recycled two batches later: hand out copies of the (tiny) label / bit tensors
+        y_dev = dev[o_lab:o_lab + n_lab].view(torch.int32).reshape(labels.shape).clone()
+        b_dev = dev[o_bits:o_bits + len(bits)].clone() if bits is not None else None
+        return X, y_dev, b_dev
 
 
 def cmvn_scale_offset(stats_sum, stats_sumsq, count, norm_vars=True):
