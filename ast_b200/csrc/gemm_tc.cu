@@ -11,9 +11,8 @@
 // forward tensors in place -- no transposed copies.  Weight gradients have K = T'*B (thousands) and a
 // small output, so they run split-K over blockIdx.z with fp32 red.global.add into a zeroed C.
 //
-// S3 variant ("3xTF32", fp32-faithful): C = x.y + lo(x).y + x.lo(y), lo(v) = v - trunc_tf32(v) precomputed by split_lo();
-// the raw fp32 tiles double as the high parts (the tensor core truncates them itself), so a k-block stages four tiles
-// and issues three MMAs per k-step.  Used for the forward convolutions that feed train-mode BatchNorm.
+// S3 variant ("3xTF32", fp32-faithful): C = hi(x).hi(y) + lo(x).hi(y) + hi(x).lo(y) with hi = rna_tf32(v),
+// lo = rna_tf32(v - hi) precomputed by split_tf32(); a k-block stages four tiles and issues three MMAs per k-step.  Used for the forward convolutions that feed train-mode BatchNorm.
 //
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
 // (TMEM lane quadrant = warp_id % 4).  Tile 128 x 128 x 32 (one 128-byte swizzle row of fp32 per k-block),
@@ -289,28 +288,35 @@ static int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& 
     return 0;
 }
 
-__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, size_t n4) {
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
-        float4 r;
-        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        reinterpret_cast<float4*>(lo)[i] = r;
+        float4 h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
     }
 }
-// lo[i] = x[i] - trunc_tf32(x[i]) (the part of an fp32 value the tensor core drops); n must be a multiple of 4
-int split_lo(cudaStream_t st, const float* x, float* lo, size_t n) {
-    AST_CHECK(n % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)lo % 16 == 0, "split_lo: need 16-byte aligned buffers, n %% 4 == 0");
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in TF32, so the tensor core's truncation of its
+// fp32 inputs is exact and the remaining error (the dropped lo.lo term and the rounding of lo) is unbiased, ~2^-23.
+// (Feeding raw x and lo = x - trunc(x) instead leaves truncation biases that add up linearly in K: measured 5e-5.)
+int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n) {
+    AST_CHECK(n % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)hi % 16 == 0 && (uintptr_t)lo % 16 == 0,
+              "split_tf32: need 16-byte aligned buffers, n %% 4 == 0");
     const size_t n4 = n / 4;
     const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
-    split_lo_kernel<<<std::max(blocks, 1), 256, 0, st>>>(x, lo, n4);
+    split_tf32_kernel<<<std::max(blocks, 1), 256, 0, st>>>(x, hi, lo, n4);
     AST_LAUNCH_OK();
     return 0;
 }
 
-// C = A . B^T (+bias) with fp32-faithful 3xTF32 (NT form only).  Alo / Blo = split_lo(A) / split_lo(B), same layouts.
+// C = A . B^T (+bias) with fp32-faithful 3xTF32 (NT form only).  (A, Alo) / (B, Blo) = split_tf32 of the operands, same layouts.
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo, int ldb,
                 float* C, int ldc, const float* bias) {
     if (M <= 0 || N <= 0 || K <= 0) return 1;

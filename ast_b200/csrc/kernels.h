@@ -20,8 +20,8 @@ int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, co
 int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
             float* C, int ldc, const float* bias, float beta, int split_k);
 
-// fp32-faithful 3xTF32 NT GEMM (gemm_tc.cu): Alo/Blo = split_lo(A)/split_lo(B); returns 1 if the shape is unsupported
-int split_lo(cudaStream_t st, const float* x, float* lo, size_t n);
+// fp32-faithful 3xTF32 NT GEMM (gemm_tc.cu) on (hi, lo) = split_tf32(operand); returns 1 if the shape is unsupported
+int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo,
                 int ldb, float* C, int ldc, const float* bias);
 

@@ -58,7 +58,7 @@ struct ast_model {
     // workspace
     Arena ws; int wsB = 0, wsT = 0, wsL = 0, wsN = 0, wsSteps = 0;
     // ---- buffers (valid after bind_workspace) ----
-    float *a0p_lo, *W1p_lo; int conv3x = 1;   // 3xTF32 operands of the CNN_1 forward GEMM (split_lo)
+    float *a0p_hi, *a0p_lo, *W1p_hi, *W1p_lo; int conv3x = 1;   // 3xTF32 operands of the CNN_1 forward GEMM (split_tf32)
     float *cols0, *W0pad, *raw0, *a0p, *W1p, *raw1, *mean0, *invstd0, *mean1, *invstd1, *rnn_in, *rnn_rev, *Xn;
     double *bnstats, *norm_sq;
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
@@ -174,7 +174,9 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->raw0 = a.get<float>(M0 * C0);
     m->a0p = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
     m->W1p = a.get<float>((size_t)C1 * m->K1);
+    m->a0p_hi = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
     m->a0p_lo = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
+    m->W1p_hi = a.get<float>((size_t)C1 * m->K1);
     m->W1p_lo = a.get<float>((size_t)C1 * m->K1);
     m->raw1 = a.get<float>(M1 * C1);
     m->bnstats = a.get<double>(2 * (size_t)std::max(C0, C1));
@@ -293,7 +295,7 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     AST_CUDA_OK(cudaMemsetAsync(m->W0pad, 0, sizeof(float) * m->C0 * m->ld0, st));
     AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
     AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
-    AST_TRY(split_lo(st, m->W1p, m->W1p_lo, (size_t)m->C1 * m->K1));
+    AST_TRY(split_tf32(st, m->W1p, m->W1p_hi, m->W1p_lo, (size_t)m->C1 * m->K1));
     // The transposed decoder weights are consumed by backward only: build them on the side stream, concurrently with the
     // forward pass (backward_impl waits on ev_tr).
     cudaStream_t ts = m->overlap ? m->side : st;
@@ -363,11 +365,11 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
     int conv1_done = 0;
     if (m->tc_gemm && !m->exact && m->conv3x && m->K1 % 4 == 0) {
-        // fp32-faithful on the tensor cores: 3xTF32 (x.y + lo(x).y + x.lo(y)); single-pass TF32 here wrecks the BatchNorm
+        // fp32-faithful on the tensor cores: 3xTF32 (hi.hi + lo.hi + hi.lo); single-pass TF32 here wrecks the BatchNorm
         // parameter gradients downstream, the fp32 SIMT kernel was 22 % of the forward pass
         const size_t n_a0p = (size_t)B * Fp * S0 * C0 + (size_t)(c.cnn_kh[1] + 8) * C0;
-        AST_TRY(split_lo(st, m->a0p, m->a0p_lo, n_a0p));
-        const int r = gemm_tc3_nt(st, M1, C1, m->K1, m->a0p, m->a0p_lo, c.cnn_sh[1] * C0, m->W1p, m->W1p_lo, m->K1, m->raw1, C1, nullptr);
+        AST_TRY(split_tf32(st, m->a0p, m->a0p_hi, m->a0p_lo, n_a0p));
+        const int r = gemm_tc3_nt(st, M1, C1, m->K1, m->a0p_hi, m->a0p_lo, c.cnn_sh[1] * C0, m->W1p_hi, m->W1p_lo, m->K1, m->raw1, C1, nullptr);
         if (r < 0) return r;
         conv1_done = (r == 0);
     }
@@ -1168,12 +1170,12 @@ int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const 
     }
     return sgemm_simt(S_(stream), ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
 }
-int ast_split_lo(const float* x, float* lo, long long n, void* stream) { return split_lo(S_(stream), x, lo, (size_t)n); }
-int ast_gemm3_nt(int M, int N, int K, const float* A, float* Alo, long long a_floats, int lda, const float* B, float* Blo,
-                 long long b_floats, int ldb, float* C, int ldc, const float* bias, void* stream) {
-    AST_TRY(split_lo(S_(stream), A, Alo, (size_t)a_floats));
-    AST_TRY(split_lo(S_(stream), B, Blo, (size_t)b_floats));
-    const int r = gemm_tc3_nt(S_(stream), M, N, K, A, Alo, lda, B, Blo, ldb, C, ldc, bias);
+int ast_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) { return split_tf32(S_(stream), x, hi, lo, (size_t)n); }
+int ast_gemm3_nt(int M, int N, int K, const float* A, float* Ahi, float* Alo, long long a_floats, int lda, const float* B, float* Bhi,
+                 float* Blo, long long b_floats, int ldb, float* C, int ldc, const float* bias, void* stream) {
+    AST_TRY(split_tf32(S_(stream), A, Ahi, Alo, (size_t)a_floats));
+    AST_TRY(split_tf32(S_(stream), B, Bhi, Blo, (size_t)b_floats));
+    const int r = gemm_tc3_nt(S_(stream), M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias);
     AST_CHECK(r <= 0, "3xTF32 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
     return r;
 }

@@ -122,11 +122,12 @@ int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V
 int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, void* stream);
 /* fp32-faithful tensor-core GEMM, C = A . B^T + bias (A: M x K, B: N x K, both k-contiguous): 3xTF32 on tcgen05
-   (x.y + lo(x).y + x.lo(y)).  Alo / Blo are scratch buffers of A's / B's size, filled by the call (ast_split_lo).
-   Replaces the cuDNN convolution forward of CNN_1 (seq2seq.py:165) as an implicit GEMM over overlapping rows. */
-int ast_split_lo(const float* x, float* lo, long long n, void* stream);
-int ast_gemm3_nt(int M, int N, int K, const float* A, float* Alo, long long a_floats, int lda, const float* B, float* Blo,
-                 long long b_floats, int ldb, float* C, int ldc, const float* bias, void* stream);
+   (hi.hi + lo.hi + hi.lo with hi = rna_tf32(v), lo = rna_tf32(v - hi)).  Ahi/Alo, Bhi/Blo are scratch buffers of A's / B's
+   size, filled by the call (ast_split_tf32).  Replaces the cuDNN convolution forward of CNN_1 (seq2seq.py:165) as an
+   implicit GEMM over overlapping rows (lda < K). */
+int ast_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+int ast_gemm3_nt(int M, int N, int K, const float* A, float* Ahi, float* Alo, long long a_floats, int lda, const float* B,
+                 float* Bhi, float* Blo, long long b_floats, int ldb, float* C, int ldc, const float* bias, void* stream);
 /* persistent LSTM recurrence over a sequence, one chain (kernel-level test hook) */
 int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, float* out_or_dout, int T, int B, int h,
                  const float* dh_fin, const float* dc_fin, int exact, void* stream);

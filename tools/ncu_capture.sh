@@ -24,5 +24,5 @@ if [ "$what" = all ] || [ "$what" = gemm ]; then
     cap gemm "gemm_tc_kernel" 0 6
     cmd="python tools/profile_step.py --precision tf32 --steps 1 --warmup 1"
 fi
-if [ "$what" = all ] || [ "$what" = mem ]; then cap mem "split_lo|opt_amsgrad|bn_relu_to_rnn|bn_bwd_apply" 8 6; fi
+if [ "$what" = all ] || [ "$what" = mem ]; then cap mem "split_tf32|opt_amsgrad|bn_relu_to_rnn|bn_bwd_apply" 8 6; fi
 du -sh gpurun_out
