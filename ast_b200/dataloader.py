@@ -78,13 +78,18 @@ class DevicePacker:
     The host side of `dataloader.py:156-162` (`F.pad_sequence` + `to_gpu`) without its per-batch allocations: features,
     row offsets, lengths and the frame-keep masks are written straight into a persistent pinned buffer (two slots, so the
     host can fill batch i+1 while the copy of batch i is in flight), copied with a single `cudaMemcpyAsync`, and expanded
-    on the device by the pack kernel (CMVN, frame zeroing and input noise fused; `csrc/misc.cu::pack_cmvn_kernel`)."""
+    on the device by the pack kernel (CMVN, frame zeroing and input noise fused; `csrc/misc.cu::pack_cmvn_kernel`).
+
+    With `async_copy=True` (default) the copy and the pack kernel run on the packer's own stream: a training loop that asks
+    for batch i+1 right after enqueueing step i (the `get_batch` generator does) gets the next batch's H2D transfer and
+    packing overlapped with the running step; the consumer's stream only waits on an event."""
 
     SLOTS = 2
 
-    def __init__(self, device):
+    def __init__(self, device, async_copy=True):
         self.device = device
         self.lib = _lib.load()
+        self.stream = torch.cuda.Stream(device=device) if async_copy else None
         self._host = [None] * self.SLOTS
         self._dev = [None] * self.SLOTS
         self._done = [None] * self.SLOTS
@@ -96,6 +101,8 @@ class DevicePacker:
 
     def _buffers(self, slot, nbytes):
         if self._host[slot] is None or self._host[slot].numel() < nbytes:
+            if self._done[slot] is not None:
+                self._done[slot].synchronize()      # nothing may still read the buffers that are about to be replaced
             cap = max(nbytes * 3 // 2, 1 << 20)
             self._host[slot] = torch.empty(cap, dtype=torch.uint8).pin_memory()
             self._dev[slot] = torch.empty(cap, dtype=torch.uint8, device=self.device)
@@ -146,28 +153,35 @@ class DevicePacker:
             hnp[o_lab:o_lab + n_lab].view(np.int32)[:] = np.asarray(labels, dtype=np.int32).ravel()
         if bits is not None:
             hnp[o_bits:o_bits + len(bits)] = np.asarray(bits, dtype=np.uint8)
-        dev[:total].copy_(host[:total], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+        consumer = torch.cuda.current_stream(self.device)
+        work = self.stream if self.stream is not None else consumer
+        with torch.cuda.stream(work):
+            dev[:total].copy_(host[:total], non_blocking=True)
+            d_raw = dev[:n_raw].view(torch.float32)
+            d_off = dev[o_off:o_off + B * 8].view(torch.int64)
+            d_len = dev[o_len:o_len + B * 4].view(torch.int32)
+            keep = dev[o_keep:o_keep + B * T] if keep_masks is not None else None
+            scale = offset = None
+            if cmvn is not None:
+                d_cm = dev[o_cmvn:o_cmvn + 2 * B * D * 4].view(torch.float32)
+                scale, offset = d_cm[:B * D], d_cm[B * D:]
+            X = torch.empty(B, T, D, dtype=torch.float32, device=self.device)
+            check(self.lib.ast_pack_cmvn(ptr(d_raw), ptr(d_off), ptr(d_len), ptr(scale), ptr(offset), ptr(keep), None,
+                                         float(noise_sigma), int(seed), ptr(X), B, T, D, C.c_void_p(work.cuda_stream)), "ast_pack_cmvn")
+            outs = [X]
+            if labels is not None:
+                # the staging slot is recycled two batches later: hand out copies of the (tiny) label / bit tensors
+                outs.append(dev[o_lab:o_lab + n_lab].view(torch.int32).reshape(labels.shape).clone())
+                outs.append(dev[o_bits:o_bits + len(bits)].clone() if bits is not None else None)
+            ev = torch.cuda.Event()
+            ev.record(work)
         self._done[slot] = ev
-        d_raw = dev[:n_raw].view(torch.float32)
-        d_off = dev[o_off:o_off + B * 8].view(torch.int64)
-        d_len = dev[o_len:o_len + B * 4].view(torch.int32)
-        keep = dev[o_keep:o_keep + B * T] if keep_masks is not None else None
-        scale = offset = None
-        if cmvn is not None:
-            d_cm = dev[o_cmvn:o_cmvn + 2 * B * D * 4].view(torch.float32)
-            scale, offset = d_cm[:B * D], d_cm[B * D:]
-        X = torch.empty(B, T, D, dtype=torch.float32, device=self.device)
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self.lib.ast_pack_cmvn(ptr(d_raw), ptr(d_off), ptr(d_len), ptr(scale), ptr(offset), ptr(keep), None,
-                                     float(noise_sigma), int(seed), ptr(X), B, T, D, st), "ast_pack_cmvn")
-        if labels is None:
-            return X
-        # the staging slot is recycled two batches later: hand out copies of the (tiny) label / bit tensors
-        y_dev = dev[o_lab:o_lab + n_lab].view(torch.int32).reshape(labels.shape).clone()
-        b_dev = dev[o_bits:o_bits + len(bits)].clone() if bits is not None else None
-        return X, y_dev, b_dev
+        if work is not consumer:
+            consumer.wait_event(ev)
+            for t in outs:
+                if t is not None:
+                    t.record_stream(consumer)
+        return X if labels is None else tuple(outs)
 
 
 def cmvn_scale_offset(stats_sum, stats_sumsq, count, norm_vars=True):
@@ -223,7 +237,7 @@ class _BucketedLoader(DataLoader):
             keep = None
             if "train" in set_key and zero_input > 0:                   # dataloader.py:105-106
                 keep = [drop_frame_mask(min(len(f), max_sp), zero_input) for f in feats]
-            batch = {"X": self._packer.pack(feats, max_sp, keep), "utts": list(utts)}
+            batch = {"utts": list(utts)}
             if labels:
                 ys = [np.asarray([SYMBOLS.GO_ID] + self._labels(u, set_key)[:max_pred - 2] + [SYMBOLS.EOS_ID], dtype=np.int32)
                       for u in utts]
@@ -231,7 +245,9 @@ class _BucketedLoader(DataLoader):
                 ypad = np.zeros((len(ys), L), dtype=np.int32)           # PAD_ID = 0
                 for i, v in enumerate(ys):
                     ypad[i, :len(v)] = v
-                batch["y"] = torch.from_numpy(ypad).to(dev)
+                batch["X"], batch["y"], _ = self._packer.pack(feats, max_sp, keep, labels=ypad)   # labels ride the same copy
+            else:
+                batch["X"] = self._packer.pack(feats, max_sp, keep)
             yield batch
 
     def get_hyps(self, preds):
