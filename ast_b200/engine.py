@@ -41,6 +41,36 @@ def config_from_dict(cfg: dict, feat_dim: int) -> AstConfig:
     return c
 
 
+class AsyncScalar:
+    """Device scalar -> host without stalling the stream: `push(t)` enqueues a D2H copy into a pinned slot and records an
+    event right behind it; `pop()` waits for THAT event only.  (`float(t)` one step late is not enough: `.item()` copies
+    on the current stream, i.e. behind everything enqueued since - including the whole next training step.)"""
+
+    def __init__(self, device, depth=4):
+        self.device = device
+        self.buf = torch.zeros(depth, dtype=torch.float32).pin_memory()
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.head = self.tail = 0
+        self.depth = depth
+
+    def __len__(self):
+        return self.head - self.tail
+
+    def push(self, t):
+        assert len(self) < self.depth, "AsyncScalar ring full: pop() before pushing more"
+        i = self.head % self.depth
+        self.buf[i:i + 1].copy_(t.reshape(1), non_blocking=True)
+        self.ev[i].record(torch.cuda.current_stream(self.device))
+        self.head += 1
+
+    def pop(self):
+        assert len(self) > 0
+        i = self.tail % self.depth
+        self.ev[i].synchronize()
+        self.tail += 1
+        return float(self.buf[i])
+
+
 class Engine:
     def __init__(self, cfg: dict, feat_dim: int, device: int = 0):
         if not torch.cuda.is_available():

@@ -205,7 +205,9 @@ class NN:
         random_out = self.cfg.train["extras"]["random_out"]
         add_noise = self.cfg.train["extras"]["speech_noise"]
         teach_ratio = self.cfg.train["extras"]["teach_ratio"]
-        pending = []
+        from .engine import AsyncScalar
+        reader = AsyncScalar(self.model._engine.device)
+        sizes = []
         for batch in self.data_loader.get_batch(batch_size, set_key, train=True, labels=True):
             with using_config("train", True):
                 loss = self.model.forward_loss(X=batch["X"], y=batch["y"], teach_ratio=teach_ratio, random_out=random_out,
@@ -213,15 +215,15 @@ class NN:
                 self.model.cleargrads()
                 loss.backward()
                 self.optimizer.update()
-            pending.append((loss.data, len(batch["y"])))
+            reader.push(loss.data)                 # D2H into pinned memory + event; read back one step late (nn.py:189)
+            sizes.append(len(batch["y"]))
             n_batches += 1
-            if len(pending) > 1:
-                l, n = pending.pop(0)
-                total_loss += float(l) / n
+            if len(reader) > 1:
+                total_loss += reader.pop() / sizes.pop(0)
             if max_batches is not None and n_batches >= max_batches:
                 break
-        for l, n in pending:
-            total_loss += float(l) / n
+        while len(reader):
+            total_loss += reader.pop() / sizes.pop(0)
         return total_loss / max(n_batches, 1)
 
     def predict(self, set_key):

@@ -340,18 +340,20 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    from ast_b200.engine import AsyncScalar
+    reader = AsyncScalar(dev)
     h2d = d2h = 0
     t0 = time.perf_counter()
-    pending = None
     for i in range(W, W + K):
         f, k, y, bits, fr = host[i]
         Xd, yd, bd = packer.pack(f, max_sp, k, labels=y, bits=bits)     # one pinned staging buffer, one H2D copy, one kernel
         loss = step_resident(Xd, yd, bd)
         h2d += sum(x.nbytes for x in f) + sum(m.nbytes for m in k) + y.nbytes + bits.nbytes
-        if pending is not None:
-            float(pending); d2h += 4                        # loss read one step late (asynchronous logging)
-        pending = loss
-    float(pending); d2h += 4
+        reader.push(loss)                                   # D2H of the loss into pinned memory, event behind it
+        if len(reader) > 1:
+            reader.pop(); d2h += 4                          # loss read one step late (asynchronous logging, nn.py:189)
+    while len(reader):
+        reader.pop(); d2h += 4
     torch.cuda.synchronize()
     t_e2e = adist.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = frames_all / t_e2e
