@@ -85,7 +85,7 @@ struct ast_model {
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr; int overlap = 1; bool tr_pending = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
-    cudaStream_t lay[MAXL] = {}; cudaEvent_t ev_pool[128] = {}; int enc_chunk = 32;
+    cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 32;
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -389,22 +389,27 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // 3-layer stack shrinks from 3*T' to about T' + 2*chunk steps.  Link states (Hs/Cs slots) carry across chunks.
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
-    const bool wave = nch > 1 && NL * nch + 2 <= 128;
+    const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
     for (int l = 0; l < NL; ++l)
         for (int d = 0; d < 2; ++d) {
             AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
             AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
         }
-    auto run_chunk = [&](int l, int t0, int tn, cudaStream_t s, bool project) -> int {
+    auto project = [&](int l, int t0, int tn, cudaStream_t s) -> int {
+        const size_t r0 = (size_t)t0 * B;
+        for (int d = 0; d < 2; ++d) {
+            const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+            const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
+            AST_TRY(gemm_nt(m, s, tn * B, 4 * h, m->in_enc(l), xin + r0 * m->in_enc(l), m->in_enc(l), m->p((ln + "/upward/W").c_str()),
+                            m->in_enc(l), m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
+        }
+        return 0;
+    };
+    auto recur = [&](int l, int t0, int tn, cudaStream_t s) -> int {
         LstmChains ch{};
         const size_t r0 = (size_t)t0 * B;
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
-            if (project) {
-                const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
-                AST_TRY(gemm_nt(m, s, tn * B, 4 * h, m->in_enc(l), xin + r0 * m->in_enc(l), m->in_enc(l), m->p((ln + "/upward/W").c_str()),
-                                m->in_enc(l), m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
-            }
             LstmChain& cc = ch.c[d];
             cc.G = m->Genc[l][d] + r0 * 4 * h; cc.Wl = m->p((ln + "/lateral/W").c_str());
             cc.Hs = m->Hs[l][d] + r0 * h; cc.Cs = m->Cs[l][d] + r0 * h;
@@ -419,23 +424,30 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         return lstm_seq_fwd(s, ch, 2, tn, B, h, drop, m->cur_seed, m->exact != 0);
     };
     if (!wave) {
-        for (int l = 0; l < NL; ++l) AST_TRY(run_chunk(l, 0, Tp, st, true));
+        for (int l = 0; l < NL; ++l) { AST_TRY(project(l, 0, Tp, st)); AST_TRY(recur(l, 0, Tp, st)); }
     } else {
-        // layer 0: whole-sequence projection (its input is complete), chunked recurrence
-        for (int d = 0; d < 2; ++d) {
-            const std::string ln = lname(0, d == 0 ? "enc" : "rev_enc");
-            AST_TRY(gemm_nt(m, st, TB, 4 * h, m->in_enc(0), d == 0 ? m->rnn_in : m->rnn_rev, m->in_enc(0), m->p((ln + "/upward/W").c_str()),
-                            m->in_enc(0), m->Genc[0][d], 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
-        }
-        cudaEvent_t* ev = m->ev_pool;          // ev[l * nch + c]: chunk c of layer l finished; ev[NL * nch]: start
+        // layer 0: whole-sequence projection (its input is complete), chunked recurrence.  Layers >= 1: the projection of
+        // chunk c runs on the layer's GEMM stream as soon as layer l-1 has produced chunk c, i.e. while this layer's
+        // recurrence is still on chunk c-1; the recurrence stream only waits for it.
+        AST_TRY(project(0, 0, Tp, st));
+        cudaEvent_t* ev = m->ev_pool;          // ev[l*nch + c]: recurrence of chunk c, layer l done; evg[...]: its projection done
+        cudaEvent_t* evg = m->ev_pool + NL * nch + 1;
         AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
-        for (int l = 1; l < NL; ++l) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+        for (int l = 1; l < NL; ++l) {
+            AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[NL * nch], 0));
+        }
         for (int c = 0; c < nch; ++c)
             for (int l = 0; l < NL; ++l) {     // enqueue order = wavefront order (keeps the host from serialising streams)
                 cudaStream_t s = l == 0 ? st : m->lay[l];
                 const int t0 = c * CH, tn = std::min(CH, Tp - t0);
-                if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(s, ev[(l - 1) * nch + c], 0));
-                AST_TRY(run_chunk(l, t0, tn, s, l > 0));
+                if (l > 0) {
+                    AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[(l - 1) * nch + c], 0));
+                    AST_TRY(project(l, t0, tn, m->layg[l]));
+                    AST_CUDA_OK(cudaEventRecord(evg[l * nch + c], m->layg[l]));
+                    AST_CUDA_OK(cudaStreamWaitEvent(s, evg[l * nch + c], 0));
+                }
+                AST_TRY(recur(l, t0, tn, s));
                 AST_CUDA_OK(cudaEventRecord(ev[l * nch + c], s));
             }
         AST_CUDA_OK(cudaStreamWaitEvent(st, ev[(NL - 1) * nch + nch - 1], 0));
@@ -703,7 +715,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // chunks of one layer goes through dh_carry / dc_carry (the kernels' dh0/dc0 outputs).
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
-    const bool wave = nch > 1 && NL * nch + 2 <= 128;
+    const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
     auto bwd_chunk = [&](int l, int ci, cudaStream_t s) -> int {
         const int t0 = ci * CH, tn = std::min(CH, Tp - t0);
         const size_t r0 = (size_t)t0 * B;
@@ -730,8 +742,12 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             cc.drop_stream = 1 + 2 * l + d;
             cc.drop_off = (unsigned)(r0 * h);
         }
-        AST_TRY(lstm_seq_bwd(s, ch, 2, tn, B, h, dr, m->cur_seed, ex));
-        for (int d = 0; d < 2; ++d) {          // dx = dG . W_up for this chunk's rows (critical path of the layer below)
+        return lstm_seq_bwd(s, ch, 2, tn, B, h, dr, m->cur_seed, ex);
+    };
+    auto bwd_dx = [&](int l, int ci, cudaStream_t s) -> int {   // dx = dG . W_up for this chunk's rows (feeds the layer below)
+        const int t0 = ci * CH, tn = std::min(CH, Tp - t0);
+        const size_t r0 = (size_t)t0 * B;
+        for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
             float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
@@ -754,26 +770,36 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     if (!wave) {
         for (int l = NL - 1; l >= 0; --l) {
             AST_TRY(bwd_chunk(l, 0, st));
+            AST_TRY(bwd_dx(l, 0, st));
             AST_TRY(fork());
             AST_TRY(enc_wgrads(l));
         }
     } else {
-        cudaEvent_t* ev = m->ev_pool;          // ev[l * nch + c]: layer l finished chunk c (recurrence + dx); ev[NL * nch]: start
+        // recurrence of (layer l, chunk c) on the layer's stream; its dx GEMMs on the layer's GEMM stream, so they overlap
+        // the recurrence of chunk c-1; layer l-1 waits for the dx event of its chunk.
+        cudaEvent_t* ev = m->ev_pool;          // ev[l*nch + c]: recurrence done; evg[l*nch + c]: dx of that chunk done
+        cudaEvent_t* evg = m->ev_pool + NL * nch + 1;
         AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
-        for (int l = 0; l < NL - 1; ++l) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+        for (int l = 0; l < NL; ++l) {
+            if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[NL * nch], 0));
+        }
         for (int ci = nch - 1; ci >= 0; --ci)
             for (int l = NL - 1; l >= 0; --l) {
                 cudaStream_t s = l == NL - 1 ? st : m->lay[l];
-                if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(s, ev[(l + 1) * nch + ci], 0));
+                if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(s, evg[(l + 1) * nch + ci], 0));
                 AST_TRY(bwd_chunk(l, ci, s));
                 AST_CUDA_OK(cudaEventRecord(ev[l * nch + ci], s));
+                AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[l * nch + ci], 0));
+                AST_TRY(bwd_dx(l, ci, m->layg[l]));
+                AST_CUDA_OK(cudaEventRecord(evg[l * nch + ci], m->layg[l]));
             }
         for (int l = NL - 1; l >= 0; --l) {    // weight gradients once the layer's dG is complete, off the critical path
-            if (sw != st) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[l * nch + 0], 0));
-            else AST_CUDA_OK(cudaStreamWaitEvent(st, ev[l * nch + 0], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[l * nch + 0], 0));
             AST_TRY(enc_wgrads(l));
         }
-        AST_CUDA_OK(cudaStreamWaitEvent(st, ev[0 * nch + 0], 0));
+        for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, evg[l * nch + 0], 0));     // join every GEMM stream
+        for (int l = 0; l < NL - 1; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, ev[l * nch + 0], 0));
     }
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
@@ -865,7 +891,8 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_tr, cudaEventDisableTiming);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->lay[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 128 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->layg[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
     *out = m;
@@ -880,7 +907,8 @@ int ast_destroy(ast_model* m) {
     if (m->ev_tr) cudaEventDestroy(m->ev_tr);
     if (m->side) cudaStreamDestroy(m->side);
     for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
-    for (int i = 0; i < 128; ++i) if (m->ev_pool[i]) cudaEventDestroy(m->ev_pool[i]);
+    for (int i = 0; i < MAXL; ++i) if (m->layg[i]) cudaStreamDestroy(m->layg[i]);
+    for (int i = 0; i < 256; ++i) if (m->ev_pool[i]) cudaEventDestroy(m->ev_pool[i]);
     delete m;
     return 0;
 }

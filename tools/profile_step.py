@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--precision", default="f32")
 ap.add_argument("--dropout", type=float, default=0.3)
+ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable), e.g. --opt enc_chunk=16")
 a = ap.parse_args()
 
 rng = np.random.default_rng(0)
@@ -29,6 +30,9 @@ m.init_params(seed=0)
 e = m._engine
 e.set_option("exact", 0 if a.precision == "tf32" else 1)
 e.set_option("tc_gemm", 1 if a.precision == "tf32" else 0)
+for kv in a.opt:
+    k, v = kv.split("=")
+    e.set_option(k, float(v))
 X = torch.as_tensor(rng.standard_normal((a.B, a.T, 40)).astype(np.float32), device=e.device)
 y = rng.integers(4, 1098, (a.B, a.L)).astype(np.int32); y[:, 0] = 1; y[:, -1] = 2
 y = torch.as_tensor(y, device=e.device)
