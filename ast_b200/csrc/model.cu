@@ -93,6 +93,15 @@ struct ast_model {
     const int* y_dev = nullptr; const unsigned char* use_true_dev = nullptr;   // of the last forward_loss
     int dec_Bd = 0;
 
+    // optional stage timing (option stage_timing): timed events on the caller's stream at stage boundaries
+    int stage_timing = 0; cudaEvent_t tev[16] = {}; int ntev = 0; const char* tev_name[16] = {};
+    int mark(const char* name, cudaStream_t st) {
+        if (!stage_timing || ntev >= 16) return 0;
+        if (!tev[ntev] && cudaEventCreate(&tev[ntev]) != cudaSuccess) return -1;
+        tev_name[ntev] = name;
+        return cudaEventRecord(tev[ntev++], st) == cudaSuccess ? 0 : -1;
+    }
+
     float* p(const char* name) const {
         for (auto& pi : pinfo) if (pi.name == name) return P + pi.off;
         return nullptr;
@@ -383,6 +392,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     AST_TRY(bn_relu_to_rnn(st, m->raw1, m->rnn_in, m->rnn_rev, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
                            m->p("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
 
+    if (train) m->mark("fwd:cnn_done", st);
     // encoder stacks: one input-projection GEMM per (layer, direction, chunk), then the persistent recurrence for both
     // directions in one launch.  With enc_chunk > 0 the time axis is cut into chunks and the layers run as a wavefront
     // (layer l on chunk c while layer l-1 is on chunk c+1), one stream per layer: the per-step latency chain of a
@@ -555,7 +565,10 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
                              const float* noise, float sigma, float* loss_out, cudaStream_t st) {
     AST_CHECK(L >= 2, "forward_loss: need at least 2 target tokens (got %d)", L);
     AST_CHECK(m->cfg.drop_out == 0.f, "dropout on the output layer is not supported (0 in every shipped config)");
+    m->ntev = 0;
+    m->mark("fwd:start", st);
     AST_TRY(encode_impl(m, X, B, T, 1, noise, sigma, st));
+    m->mark("fwd:encoder_done", st);
     const int H = m->H, E = m->E, A = m->A, NL = m->NL, Tp = m->Tp, S = L - 1;
     m->L = L;
     float* hinit[MAXL]; float* cinit[MAXL];
@@ -601,6 +614,7 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
                            m->V, true));
     }
     AST_TRY(loss_reduce(st, m->row_loss, S * B, m->loss_dev));
+    m->mark("fwd:decoder_done", st);
     if (loss_out) AST_CUDA_OK(cudaMemcpyAsync(loss_out, m->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
     m->have_fwd = true;
     return 0;
@@ -617,6 +631,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     const bool ex = m->exact != 0;
     const float de = c.drop_embed, dr = c.drop_rnn;
     const int SB = S * B, TB = Tp * B;
+    m->mark("bwd:start", st);
     if (m->tr_pending) { AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_tr, 0)); m->tr_pending = false; }
     {   // cleargrads for the accumulate-style outputs
         const ParamInfo* pe = nullptr; for (auto& pi : m->pinfo) if (pi.name == "embed_dec/W") pe = &pi;
@@ -678,6 +693,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(embed_scatter(st, m->g("embed_dec/W"), m->dxh[0], E + A + H, m->words_used + (size_t)s * B, B, E, s, de,
                               m->cur_seed, 32));
     }
+    m->mark("bwd:decoder_done", st);
     // Weight gradients are off the critical path (which is: decoder BPTT -> encoder recurrences top-down, each followed by
     // its dx GEMM -> CNN backward); they run on the side stream, forked after the kernel that produces their operands and
     // joined at the end, so they fill the SMs the latency-bound recurrences leave idle.
@@ -801,6 +817,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, evg[l * nch + 0], 0));     // join every GEMM stream
         for (int l = 0; l < NL - 1; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, ev[l * nch + 0], 0));
     }
+    m->mark("bwd:encoder_done", st);
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
     AST_TRY(bn_bwd_from_rnn(st, m->d_rnn_in, m->d_rnn_rev, m->raw1, m->draw1, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
@@ -815,10 +832,12 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     AST_TRY(gemm(m, st, true, false, C0, m->ld0, M0, m->draw0, C0, m->cols0, m->ld0, m->dW0pad, m->ld0, nullptr, 0.f, -1, SITE_CONV0_WGRAD));
     const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
     AST_TRY(copy2d(st, m->dW0pad, m->ld0, m->g("CNN_0/W"), K0, C0, K0));
+    m->mark("bwd:cnn_done", st);
     if (sw != st) {
         AST_CUDA_OK(cudaEventRecord(m->ev_join, sw));
         AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_join, 0));
     }
+    m->mark("bwd:side_stream_joined", st);
     m->have_fwd = false;
     return 0;
 }
@@ -957,6 +976,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
     else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
+    else if (!strcmp(key, "stage_timing")) m->stage_timing = value != 0;
     else if (!strcmp(key, "conv3x")) m->conv3x = value != 0;
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
@@ -1216,6 +1236,22 @@ int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, 
     c.drop_stream = 0;
     return backward ? lstm_seq_bwd(S_(stream), ch, 1, T, B, h, 0.f, 0, exact != 0)
                     : lstm_seq_fwd(S_(stream), ch, 1, T, B, h, 0.f, 0, exact != 0);
+}
+
+// Stage timing (option stage_timing = 1): names and milliseconds between consecutive marks of the last forward_loss + backward.
+// Synchronises the device.  Returns the number of intervals written (<= cap).
+int ast_stage_times(ast_model* m, float* ms, char* names, int name_stride, int cap) {
+    AST_CUDA_OK(cudaDeviceSynchronize());
+    int n = 0;
+    for (int i = 1; i < m->ntev && n < cap; ++i) {
+        float t = 0.f;
+        if (!strncmp(m->tev_name[i], "bwd:start", 9)) continue;      // the gap between forward and backward is the caller's
+        AST_CUDA_OK(cudaEventElapsedTime(&t, m->tev[i - 1], m->tev[i]));
+        ms[n] = t;
+        snprintf(names + (size_t)n * name_stride, name_stride, "%s", m->tev_name[i]);
+        ++n;
+    }
+    return n;
 }
 
 // Test hook: copy a named internal buffer (device -> caller's device buffer).

@@ -292,6 +292,15 @@ class Engine:
         return dict(n_steps=ns.value, n_hyps=nh.value, hist_parent=hist_parent, hist_tok=hist_tok, scores=scores,
                     alpha_hist=alpha_hist, states=states, attn_v=attn_v)
 
+    def stage_times(self):
+        """[(stage, ms)] of the last forward_loss + backward (needs set_option('stage_timing', 1)); synchronises."""
+        ms = (C.c_float * 16)()
+        names = C.create_string_buffer(16 * 48)
+        n = self.lib.ast_stage_times(self.h, ms, names, 48, 16)
+        if n < 0:
+            raise RuntimeError(self.lib.ast_last_error().decode())
+        return [(names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode(), float(ms[i])) for i in range(n)]
+
     def debug_fetch(self, name):
         n = C.c_longlong(0)
         check(self.lib.ast_debug_fetch(self.h, name.encode(), None, 0, C.byref(n), self.stream()), "ast_debug_fetch")

@@ -46,4 +46,6 @@ for it in range(a.warmup + a.steps):
     torch.cuda.synchronize(); t2 = time.perf_counter()
     e.opt_step(mm, v, vh, it + 1, 1e-3, 1e-4, 2.0)
     torch.cuda.synchronize(); t3 = time.perf_counter()
+    if "stage_timing=1" in a.opt:
+        print("   stages:", ", ".join(f"{n} {ms:.3f}" for n, ms in e.stage_times()), flush=True)
     print(f"step {it}: loss {float(loss):.4f} fwd {1e3*(t1-t0):.2f} ms bwd {1e3*(t2-t1):.2f} ms opt {1e3*(t3-t2):.2f} ms", flush=True)
