@@ -189,6 +189,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[4090] = gtimer2();
     if (tid == 0) {
         mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -577,6 +578,7 @@ dec_seq2_bwd_kernel(DecSeq p) {
 #define B2_SYNC() do { grid_barrier2(p.bar, bar_target); \
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
 
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[4090] = gtimer2();
     if (tid == 0) {
         mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

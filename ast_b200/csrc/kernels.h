@@ -154,6 +154,9 @@ int mul_noise(cudaStream_t st, const float* X, float* Y, const float* noise, flo
 int transpose(cudaStream_t st, const float* src, int ld_src, float* dst, int ld_dst, int R, int C);
 int colsum(cudaStream_t st, const float* x, int ld, float* out, int rows, int C, bool accumulate);
 int copy2d(cudaStream_t st, const float* src, long long ld_src, float* dst, long long ld_dst, int R, int C);
+struct Copy2DJob { const float* src; long long ld_src; float* dst; long long ld_dst; int R, C; };
+struct Copy2DBatch { int n; Copy2DJob job[16]; };
+int copy2d_multi(cudaStream_t st, const Copy2DBatch& b);
 int add_inplace(cudaStream_t st, float* dst, const float* src, size_t n);
 int greedy_track(cudaStream_t st, const int* argmax, int* preds, int* seen, int* done_step, int B, int step, int eos);
 

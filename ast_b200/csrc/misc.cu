@@ -203,6 +203,26 @@ int copy2d(cudaStream_t st, const float* src, long long ld_src, float* dst, long
     return 0;
 }
 
+// Several strided 2-D copies in ONE launch (decoder initial state = 12 slices of the encoder finals, seq2seq.py:318-334).
+__global__ void copy2d_multi_kernel(Copy2DBatch b) {
+    const Copy2DJob j = b.job[blockIdx.y];
+    const size_t total = (size_t)j.R * j.C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % j.C); const size_t r = i / j.C;
+        j.dst[r * j.ld_dst + c] = j.src[r * j.ld_src + c];
+    }
+}
+int copy2d_multi(cudaStream_t st, const Copy2DBatch& b) {
+    if (b.n == 0) return 0;
+    size_t mx = 0;
+    for (int i = 0; i < b.n; ++i) mx = std::max(mx, (size_t)b.job[i].R * b.job[i].C);
+    if (mx == 0) return 0;
+    dim3 grid((unsigned)std::min<size_t>((mx + 255) / 256, 64), b.n);
+    copy2d_multi_kernel<<<grid, 256, 0, st>>>(b);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 // dst[i] += src[i]
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];

@@ -473,14 +473,17 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
 static int init_dec_state(ast_model* m, float* const* dst_h, float* const* dst_c, int Bd, cudaStream_t st) {
     const int B = m->B, h = m->h, H = m->H, Tp = m->Tp;
     AST_CHECK(Bd == B || B == 1, "init_decoder_state: decoder batch %d incompatible with encoder batch %d", Bd, B);
+    Copy2DBatch cb{}; cb.n = 0;
     for (int l = 0; l < m->NL; ++l)
         for (int d = 0; d < 2; ++d) {
             const float* hsrc = m->Hs[l][d] + (size_t)Tp * B * h;
             const float* csrc = m->Cs[l][d] + (size_t)Tp * B * h;
             const long long lds = (Bd == B) ? h : 0;       // broadcast one utterance to all hypotheses
-            AST_TRY(copy2d(st, hsrc, lds, dst_h[l] + d * h, H, Bd, h));
-            AST_TRY(copy2d(st, csrc, lds, dst_c[l] + d * h, H, Bd, h));
+            cb.job[cb.n++] = Copy2DJob{hsrc, lds, dst_h[l] + d * h, H, Bd, h};
+            cb.job[cb.n++] = Copy2DJob{csrc, lds, dst_c[l] + d * h, H, Bd, h};
+            if (cb.n == 16) { AST_TRY(copy2d_multi(st, cb)); cb.n = 0; }
         }
+    AST_TRY(copy2d_multi(st, cb));
     return 0;
 }
 
@@ -584,7 +587,15 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
             AST_TRY(attn_dot(st, m->enc_states, (long long)Tp * H, m->p("attn_Wa/b"), 0, m->encb, B, Tp, H));
             AST_TRY(dec_seq2_fwd(st, ds));
             // deferred to after the loop: q (needed by backward), logits, softmax-CE + gradient + argmax for all steps
-            AST_TRY(gemm_nt(m, st, S * B, H, H, m->cvh + H, 2 * H, m->p("attn_Wa/W"), H, m->q, H, m->p("attn_Wa/b"), SITE_DEC_PRE));
+            if (m->overlap) {      // q is consumed by backward only (d_enc, dW_a): side stream, ordered before backward by ev_tr
+                AST_CUDA_OK(cudaEventRecord(m->ev_fork[7], st));
+                AST_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fork[7], 0));
+                AST_TRY(gemm_nt(m, m->side, S * B, H, H, m->cvh + H, 2 * H, m->p("attn_Wa/W"), H, m->q, H, m->p("attn_Wa/b"), SITE_DEC_PRE));
+                AST_CUDA_OK(cudaEventRecord(m->ev_tr, m->side));
+                m->tr_pending = true;
+            } else {
+                AST_TRY(gemm_nt(m, st, S * B, H, H, m->cvh + H, 2 * H, m->p("attn_Wa/W"), H, m->q, H, m->p("attn_Wa/b"), SITE_DEC_PRE));
+            }
             AST_TRY(gemm_nt(m, st, S * B, m->V, A, m->ht, A, m->p("out/W"), A, m->logits, m->Vp, m->p("out/b"), SITE_DEC_PRE));
             AST_TRY(softmax_ce_all(st, m->logits, m->Vp, y, L, m->row_loss, m->argmax_steps, S, B, m->V));
         } else {

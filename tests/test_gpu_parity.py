@@ -241,6 +241,24 @@ def test_tcgen05_3xtf32_gemm_is_fp32_faithful(lib, dev, M, N, K, lda):
     assert np.abs((hi.astype(np.float64) + lo) - buf).max() <= 2.0 ** -21 * np.abs(buf).max()
 
 
+def test_tf32_training_mode_on_asr_gpfr_shape(dev):
+    """BASELINE config 3 (asr_gpfr: same architecture, 13-dim MFCC input -> F' = 1, character vocabulary): the TF32 training
+    configuration (tcgen05 GEMMs / recurrences, dec_seq2, 3xTF32 convolution, wavefront) against the fp64 oracle."""
+    cfg = O.default_model_cfg(vocab=59)
+    P = O.init_params(cfg, 13, seed=21)
+    X, y, _ = O.synth_batch(9, 420, 13, 59, 10, 30, seed=22, Tmin=300)
+    om = O.OracleModel(cfg, P, dtype=np.float64)
+    loss = float(om.forward_loss(X, y))
+    g = om.backward()
+    e = _engine(cfg, 13, P, exact=0)
+    e.set_option("tc_gemm", 1)
+    got = float(e.forward_loss(X, y))
+    assert abs(got - loss) <= LOSS_RTOL * abs(loss)
+    e.backward()
+    for k in e.info:
+        assert _relerr(e.view(k, grad=True).cpu().numpy(), g[k]) <= GRAD_RTOL, k
+
+
 @pytest.mark.parametrize("B,T,ss", [(32, 330, True), (19, 140, True), (7, 90, False)])
 def test_decoder_v2_matches_v1_in_tf32_mode(dev, B, T, ss):
     """dec_seq2.cu (TMEM-resident weights, cluster K-split, one-pass attention through enc.W_a, logits/CE deferred to one

@@ -40,6 +40,8 @@ S = a.L - 1
 for name, row in (("forward", raw[0]), ("backward", raw[1])):
     n = int(row[0]); ts = row[1:n + 1].astype(np.float64)
     d = np.diff(ts)
+    if row[4090] > 0 and not a.v1:
+        print(f"{name}: kernel entry -> end of setup (TMEM/smem weight fill, prologue) {1e-3 * (row[1] - row[4090]):.1f} us")
     print(f"{name}: {n} stamps, total {1e-3 * (ts[-1] - ts[0]):.1f} us, {1e-3 * (ts[-1] - ts[0]) / S:.2f} us/step")
     per = (n - 1) // S
     head = (n - 1) - per * S
