@@ -172,6 +172,23 @@ __device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& 
 
 }  // namespace
 
+// x0[i][0:E] = Emb[y[b][s]] * dropmask, words_used[i] = token, for row i = s*B + b; (s == 0) x0[i][E:] = 0
+__device__ __forceinline__ void embed_tf_row(const DecSeq& p, int i, int tid, int nthreads) {
+    const int s = i / p.B, b = i - s * p.B, ldx0 = p.E + p.A;
+    const int word = min(max(p.y[(size_t)b * p.L + s], 0), p.V - 1);
+    float* dst = p.x0 + (size_t)i * ldx0;
+    if (tid == 0) p.words_used[i] = word;
+    for (int j = tid; j < p.E; j += nthreads)
+        dst[j] = __ldg(p.emb + (size_t)word * p.E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * p.E + j), p.drop_embed);
+    if (s == 0) for (int j = tid; j < p.A; j += nthreads) dst[p.E + j] = 0.f;
+}
+__global__ void __launch_bounds__(128) embed_all_kernel(DecSeq p) { embed_tf_row(p, blockIdx.x, threadIdx.x, 128); }
+int embed_all(cudaStream_t st, const DecSeq& p) {
+    embed_all_kernel<<<p.S * p.B, 128, 0, st>>>(p);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dec_seq2_fwd_kernel(DecSeq p) {
     extern __shared__ uint8_t smem_raw[];
@@ -244,16 +261,10 @@ dec_seq2_fwd_kernel(DecSeq p) {
         }
     }
     for (int idx = tid; idx < 32 * 32; idx += D2_THREADS) sm.Xs[(idx >> 5) * D2_XLD + 288 + (idx & 31)] = 0.f;      // layer-0 k padding
-    // teacher-forced decoder inputs for every step (sampled steps overwrite theirs in-loop); x0[0][:, E:] = 0
-    for (int i = cta; i < S * B; i += ncta) {
-        const int s = i / B, b = i - s * B;
-        const int word = min(max(p.y[(size_t)b * L + s], 0), p.V - 1);
-        float* dst = p.x0 + (size_t)i * ldx0;
-        if (tid == 0) p.words_used[i] = word;
-        for (int j = tid; j < E; j += D2_THREADS)
-            dst[j] = __ldg(p.emb + (size_t)word * E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * E + j), p.drop_embed);
-        if (s == 0) for (int j = tid; j < A; j += D2_THREADS) dst[E + j] = 0.f;
-    }
+    // teacher-forced decoder inputs for every step (sampled steps overwrite theirs in-loop); x0[0][:, E:] = 0.
+    // Normally done by embed_all() on the side stream while the encoder runs (p.emb_done).
+    if (!p.emb_done)
+        for (int i = cta; i < S * B; i += ncta) embed_tf_row(p, i, tid, D2_THREADS);
     // cell state of the owned (row, unit) pairs stays in registers
     const int e_row = tid >> 2, e_ul = tid & 3, e_unit = 16 * cl + 4 * rank + e_ul;
     float creg[3] = {0.f, 0.f, 0.f};

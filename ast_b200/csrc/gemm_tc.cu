@@ -136,7 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(S3 ? 2 * TBN : TBN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -194,8 +194,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (S3) {
                         const uint64_t al0 = ad0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
                         const uint64_t bl0 = bd0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
-                        umma_tf32(tmem_base, al0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, 1u);
-                        umma_tf32(tmem_base, ad0 + (uint64_t)(k * a_kstep), bl0 + (uint64_t)(k * b_kstep), idesc, 1u);
+                        // the correction terms get their own accumulator (columns TBN..2*TBN-1): the tensor core's fp32
+                        // accumulate truncates, and its error scales with the accumulator's magnitude - the big hi.hi sum
+                        // sees a third of the adds, the 2^-11-sized correction sum contributes nothing measurable
+                        umma_tf32(tmem_base + TBN, al0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base + TBN, ad0 + (uint64_t)(k * a_kstep), bl0 + (uint64_t)(k * b_kstep), idesc, 1u);
                     }
                 }
                 umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
@@ -215,6 +218,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int c = 0; c < TBN / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
+            if (S3) {
+                float v2[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + TBN + c * 32, v2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j];
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
             __syncwarp();
@@ -236,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S3 ? 2 * TBN : TBN));
     }
 }
 

@@ -110,6 +110,7 @@ struct DecSeq {
     int* words_used; int* argmax_steps;
     float* du; float* dcvh; float* dalpha; float* dq; float* dxh[AST_MAXL]; float* dcd[AST_MAXL]; float* demb;
     float drop_embed, drop_rnn; unsigned long long seed;
+    int emb_done;                      // dec_seq2: teacher-forced embedding rows already written by embed_all()
     unsigned* bar;                     // grid-barrier counter (null: cooperative_groups grid.sync)
     unsigned long long* prof;          // optional phase-timing probe: CTA 0 stores %globaltimer after each grid barrier
 };
@@ -119,6 +120,7 @@ int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);
 bool dec_seq2_supported(const DecSeq& p);
 int dec_seq2_fwd(cudaStream_t st, const DecSeq& p);
 int dec_seq2_bwd(cudaStream_t st, const DecSeq& p);
+int embed_all(cudaStream_t st, const DecSeq& p);   // x0[:, :E] / words_used for every step from the ground-truth tokens
 int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float* dcv, const float* q, float* d_enc, int S, int B, int Tp, int H);
 // softmax-CE (+ gradient in place, argmax) for every (step, row) of a decoder pass in one launch
 int softmax_ce_all(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, float* row_loss, int* argmax_out, int S, int B, int V);

@@ -436,27 +436,24 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     if (!wave) {
         for (int l = 0; l < NL; ++l) { AST_TRY(project(l, 0, Tp, st)); AST_TRY(recur(l, 0, Tp, st)); }
     } else {
-        // layer 0: whole-sequence projection (its input is complete), chunked recurrence.  Layers >= 1: the projection of
-        // chunk c runs on the layer's GEMM stream as soon as layer l-1 has produced chunk c, i.e. while this layer's
-        // recurrence is still on chunk c-1; the recurrence stream only waits for it.
-        AST_TRY(project(0, 0, Tp, st));
+        // The projection of (layer l, chunk c) runs on the layer's GEMM stream as soon as its input exists (layer 0: at once;
+        // layer l >= 1: when layer l-1 has produced chunk c), i.e. while this layer's recurrence is still on chunk c-1; the
+        // recurrence stream only waits for it.  Layer 0 is chunked too so its first recurrence starts after one small GEMM.
         cudaEvent_t* ev = m->ev_pool;          // ev[l*nch + c]: recurrence of chunk c, layer l done; evg[...]: its projection done
         cudaEvent_t* evg = m->ev_pool + NL * nch + 1;
         AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
-        for (int l = 1; l < NL; ++l) {
-            AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
+        for (int l = 0; l < NL; ++l) {
+            if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
             AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[NL * nch], 0));
         }
         for (int c = 0; c < nch; ++c)
             for (int l = 0; l < NL; ++l) {     // enqueue order = wavefront order (keeps the host from serialising streams)
                 cudaStream_t s = l == 0 ? st : m->lay[l];
                 const int t0 = c * CH, tn = std::min(CH, Tp - t0);
-                if (l > 0) {
-                    AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[(l - 1) * nch + c], 0));
-                    AST_TRY(project(l, t0, tn, m->layg[l]));
-                    AST_CUDA_OK(cudaEventRecord(evg[l * nch + c], m->layg[l]));
-                    AST_CUDA_OK(cudaStreamWaitEvent(s, evg[l * nch + c], 0));
-                }
+                if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[(l - 1) * nch + c], 0));
+                AST_TRY(project(l, t0, tn, m->layg[l]));
+                AST_CUDA_OK(cudaEventRecord(evg[l * nch + c], m->layg[l]));
+                AST_CUDA_OK(cudaStreamWaitEvent(s, evg[l * nch + c], 0));
                 AST_TRY(recur(l, t0, tn, s));
                 AST_CUDA_OK(cudaEventRecord(ev[l * nch + c], s));
             }
@@ -570,6 +567,7 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     AST_CHECK(m->cfg.drop_out == 0.f, "dropout on the output layer is not supported (0 in every shipped config)");
     m->ntev = 0;
     m->mark("fwd:start", st);
+    if (m->overlap) AST_CUDA_OK(cudaEventRecord(m->ev_fork[6], st));       // inputs (y) are ready on st from here on
     AST_TRY(encode_impl(m, X, B, T, 1, noise, sigma, st));
     m->mark("fwd:encoder_done", st);
     const int H = m->H, E = m->E, A = m->A, NL = m->NL, Tp = m->Tp, S = L - 1;
@@ -581,7 +579,17 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     if (m->dec_fused) {
         DecSeq ds = make_dec_seq(m, y, use_true, true);
         if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof;
-        if (m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds)) {
+        const bool use_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
+        if (use_v2 && m->overlap) {
+            // the teacher-forced embedding rows depend on the targets only: side stream, concurrent with the encoder (the host
+            // is ahead of the device here), joined in front of the decoder kernel
+            AST_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fork[6], 0));
+            AST_TRY(embed_all(m->side, ds));
+            AST_CUDA_OK(cudaEventRecord(m->ev_fork[5], m->side));
+            AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_fork[5], 0));
+            ds.emb_done = 1;
+        }
+        if (use_v2) {
             // per-sequence precompute: scores become encW[b,t,:] . h + encb[b,t]  (= enc . (W_a h + b_a), seq2seq.py:341-342)
             AST_TRY(gemm(m, st, false, false, Tp * B, H, H, m->enc_states, H, m->p("attn_Wa/W"), H, m->encW, H, nullptr, 0.f, 0, SITE_DEC_PRE));
             AST_TRY(attn_dot(st, m->enc_states, (long long)Tp * H, m->p("attn_Wa/b"), 0, m->encb, B, Tp, H));

@@ -234,7 +234,7 @@ def test_tcgen05_3xtf32_gemm_is_fp32_faithful(lib, dev, M, N, K, lda):
                            ptr(dC), N, ptr(db), _stream(dev)))
     torch.cuda.synchronize()
     err = np.abs(dC.cpu().numpy() - want).max() / np.sqrt(K)
-    assert err < 1e-4, err
+    assert err < 3e-5, err
     # the split is exact to 2^-22: hi and lo are TF32-representable (low 13 mantissa bits clear) and hi + lo ~ x
     hi, lo = dAh.cpu().numpy(), dAl.cpu().numpy()
     assert ((hi.view(np.uint32) & np.uint32(0x1FFF)) == 0).all() and ((lo.view(np.uint32) & np.uint32(0x1FFF)) == 0).all()
