@@ -28,7 +28,8 @@ namespace ast {
 constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 5;
 constexpr int TC_THREADS = 192;
 constexpr uint32_t STAGE_A_BYTES = TBM * TBK * 4, STAGE_B_BYTES = TBN * TBK * 4;
-constexpr uint32_t TC_SMEM = TSTAGES * (STAGE_A_BYTES + STAGE_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_STG_BYTES = 4 * 32 * 33 * 4;      // epilogue staging (one 32x33 tile per epilogue warp), outside the ring
+constexpr uint32_t TC_SMEM = TSTAGES * (STAGE_A_BYTES + STAGE_B_BYTES) + TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,40 +104,50 @@ struct TcParams {
     const float* bias;
     float beta;
     int atomic;          // split-K: red.add into C
-    int kb_per_split;    // k-blocks per blockIdx.z
+    int kb_per_split;    // k-blocks per split
+    int splits;          // number of K splits (part of the linearised tile space)
 };
 
 // TA: A operand is M-major (A stored K x M).  NB: B operand is N-major (B stored K x N).
+// PERSISTENT: gridDim.x CTAs walk the linearised (split, m-tile, n-tile) space with stride gridDim.x (n fastest, so
+// concurrently running CTAs share the A row-tile in L2).  The smem ring runs across tile boundaries, and the fp32
+// accumulator is double-buffered in TMEM: while the epilogue warps drain tile i (tcgen05.ld -> smem transpose -> coalesced
+// stores), the MMA warp is already accumulating tile i+1 in the other buffer.  With K of only 256..1536 the prologue and
+// epilogue were ~1/3 of a tile's time in the one-tile-per-CTA version.
 template <bool TA, bool NB, bool S3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapAl, const __grid_constant__ CUtensorMap mapBl, TcParams p) {
     constexpr int NST = S3 ? 3 : TSTAGES;
+    constexpr uint32_t ACC_COLS = S3 ? 2 * TBN : TBN;        // S3: main + correction accumulator
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;             // double-buffered
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + NST * STAGE_A_BYTES;
     uint8_t* sAl = smem + NST * (STAGE_A_BYTES + STAGE_B_BYTES);          // S3 only: low parts
     uint8_t* sBl = sAl + NST * STAGE_A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (S3 ? 2 : 1) * NST * (STAGE_A_BYTES + STAGE_B_BYTES));
+    float* stg_base = reinterpret_cast<float*>(smem + (S3 ? 2 : 1) * NST * (STAGE_A_BYTES + STAGE_B_BYTES));   // 4 x 32 x 33 floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_base) + TC_STG_BYTES);
     uint64_t* full = bars;                 // [NST]
     uint64_t* empty = bars + NST;          // [NST]
-    uint64_t* tmem_full = bars + 2 * NST;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+    uint64_t* tmem_full = bars + 2 * NST;  // [2]
+    uint64_t* tmem_empty = bars + 2 * NST + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
     const int nkb_total = (p.K + TBK - 1) / TBK;
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int nkb = min(p.kb_per_split, nkb_total - kb0);
+    const int tiles_n = (p.N + TBN - 1) / TBN, tiles_m = (p.M + TBM - 1) / TBM;
+    const int tiles_mn = tiles_m * tiles_n;
+    const int ntiles = tiles_mn * p.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(S3 ? 2 * TBN : TBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -147,25 +158,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % NST;
-                const uint32_t ph = (i / NST) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], (S3 ? 2 : 1) * (STAGE_A_BYTES + STAGE_B_BYTES));
-                const int k0 = (kb0 + i) * TBK;
-                uint8_t* a = sA + s * STAGE_A_BYTES;
-                uint8_t* b = sB + s * STAGE_B_BYTES;
-                if (!TA) tma_load_2d(&mapA, &full[s], a, k0, m0);                     // box {32 k, 128 m}
-                else
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int m0 = (mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
+                const int kb0 = z * p.kb_per_split;
+                const int nkb = min(p.kb_per_split, nkb_total - kb0);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (S3 ? 2 : 1) * (STAGE_A_BYTES + STAGE_B_BYTES));
+                    const int k0 = (kb0 + i) * TBK;
+                    uint8_t* a = sA + s * STAGE_A_BYTES;
+                    uint8_t* b = sB + s * STAGE_B_BYTES;
+                    if (!TA) tma_load_2d(&mapA, &full[s], a, k0, m0);                     // box {32 k, 128 m}
+                    else
 #pragma unroll
-                    for (int j = 0; j < TBM / 32; ++j) tma_load_2d(&mapA, &full[s], a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
-                if (!NB) tma_load_2d(&mapB, &full[s], b, k0, n0);
-                else
+                        for (int j = 0; j < TBM / 32; ++j) tma_load_2d(&mapA, &full[s], a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
+                    if (!NB) tma_load_2d(&mapB, &full[s], b, k0, n0);
+                    else
 #pragma unroll
-                    for (int j = 0; j < TBN / 32; ++j) tma_load_2d(&mapB, &full[s], b + j * (TBK * 128), n0 + 32 * j, k0);
-                if (S3) {          // K-major operands only (host enforces)
-                    tma_load_2d(&mapAl, &full[s], sAl + s * STAGE_A_BYTES, k0, m0);
-                    tma_load_2d(&mapBl, &full[s], sBl + s * STAGE_B_BYTES, k0, n0);
+                        for (int j = 0; j < TBN / 32; ++j) tma_load_2d(&mapB, &full[s], b + j * (TBK * 128), n0 + 32 * j, k0);
+                    if (S3) {          // K-major operands only (host enforces)
+                        tma_load_2d(&mapAl, &full[s], sAl + s * STAGE_A_BYTES, k0, m0);
+                        tma_load_2d(&mapBl, &full[s], sBl + s * STAGE_B_BYTES, k0, n0);
+                    }
+                    if (++s == NST) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -183,69 +200,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint64_t b_base = NB ? make_smem_desc(smem_u32(sB), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sB), 16, 1024, 2);
             constexpr uint32_t a_kstep = (TA ? 1024 : 32) >> 4, b_kstep = (NB ? 1024 : 32) >> 4;
             int s = 0; uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&full[s], ph);
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int z = t / tiles_mn;
+                const int nkb = min(p.kb_per_split, nkb_total - z * p.kb_per_split);
+                const int buf = it & 1;
+                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);        // the epilogue has drained this buffer (first use: free)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t ad0 = a_base + (uint64_t)(s * (STAGE_A_BYTES >> 4));
-                const uint64_t bd0 = b_base + (uint64_t)(s * (STAGE_B_BYTES >> 4));
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ad0 = a_base + (uint64_t)(s * (STAGE_A_BYTES >> 4));
+                    const uint64_t bd0 = b_base + (uint64_t)(s * (STAGE_B_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < TBK / 8; ++k) {
-                    umma_tf32(tmem_base, ad0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
-                    if (S3) {
-                        const uint64_t al0 = ad0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
-                        const uint64_t bl0 = bd0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
-                        // the correction terms get their own accumulator (columns TBN..2*TBN-1): the tensor core's fp32
-                        // accumulate truncates, and its error scales with the accumulator's magnitude - the big hi.hi sum
-                        // sees a third of the adds, the 2^-11-sized correction sum contributes nothing measurable
-                        umma_tf32(tmem_base + TBN, al0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_base + TBN, ad0 + (uint64_t)(k * a_kstep), bl0 + (uint64_t)(k * b_kstep), idesc, 1u);
+                    for (int k = 0; k < TBK / 8; ++k) {
+                        umma_tf32(acc, ad0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        if (S3) {
+                            const uint64_t al0 = ad0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
+                            const uint64_t bl0 = bd0 + (uint64_t)((NST * (STAGE_A_BYTES + STAGE_B_BYTES)) >> 4);
+                            // the correction terms get their own accumulator (columns TBN..2*TBN-1): the tensor core's fp32
+                            // accumulate truncates, and its error scales with the accumulator's magnitude - the big hi.hi sum
+                            // sees a third of the adds, the 2^-11-sized correction sum contributes nothing measurable
+                            umma_tf32(acc + TBN, al0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32(acc + TBN, ad0 + (uint64_t)(k * a_kstep), bl0 + (uint64_t)(k * b_kstep), idesc, 1u);
+                        }
                     }
+                    umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+                    if (++s == NST) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&empty[s]);          // frees the smem slot when these MMAs retire
-                if (++s == NST) { s = 0; ph ^= 1; }
+                umma_commit(&tmem_full[buf]);        // accumulator of this tile complete
             }
-            umma_commit(tmem_full);              // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> smem transpose -> global =====
         const int wq = warp & 3;                 // TMEM lane quadrant this warp may access
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // Each thread holds one accumulator ROW (32 columns per tcgen05.ld); a per-warp 32x33 smem transpose (the
-        // pipeline stages are free once tmem_full fired) turns the stores into full 128-byte row segments.
-        float* stg = reinterpret_cast<float*>(sA) + wq * (32 * 33);
+        // Each thread holds one accumulator ROW (32 columns per tcgen05.ld); a per-warp 32x33 smem transpose turns the
+        // stores into full 128-byte row segments.
+        float* stg = stg_base + wq * (32 * 33);
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int z = t / tiles_mn, mn = t - z * tiles_mn;
+            const int m0 = (mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
+            const int nkb = min(p.kb_per_split, nkb_total - z * p.kb_per_split);
+            const int buf = it & 1;
+            const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(wq * 32) << 16);
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c = 0; c < TBN / 32; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + c * 32, v);
-            if (S3) {
-                float v2[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + TBN + c * 32, v2);
+            for (int c = 0; c < TBN / 32; ++c) {
+                float v[32];
+                tmem_ld32(acc + c * 32, v);
+                if (S3) {
+                    float v2[32];
+                    tmem_ld32(acc + TBN + c * 32, v2);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += v2[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-            __syncwarp();
-            const int n = n0 + c * 32 + lane;
-            if (n < p.N && nkb > 0) {
-                const float bv = (p.bias && blockIdx.z == 0) ? p.bias[n] : 0.f;
-                const int mrow0 = m0 + wq * 32;
-                const int rmax = min(32, p.M - mrow0);
-                float* cp = p.C + (size_t)mrow0 * p.ldc + n;
-                for (int r = 0; r < rmax; ++r, cp += p.ldc) {
-                    const float x = stg[r * 33 + lane] + bv;
-                    if (p.atomic) atomicAdd(cp, x);
-                    else *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
+                    for (int j = 0; j < 32; ++j) v[j] += v2[j];
                 }
+                if (c == TBN / 32 - 1) {         // last read of this buffer: hand it back to the MMA warp before the stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int n = n0 + c * 32 + lane;
+                if (n < p.N && nkb > 0) {
+                    const float bv = (p.bias && z == 0) ? p.bias[n] : 0.f;
+                    const int mrow0 = m0 + wq * 32;
+                    const int rmax = min(32, p.M - mrow0);
+                    float* cp = p.C + (size_t)mrow0 * p.ldc + n;
+                    for (int r = 0; r < rmax; ++r, cp += p.ldc) {
+                        const float x = stg[r * 33 + lane] + bv;
+                        if (p.atomic) atomicAdd(cp, x);
+                        else *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S3 ? 2 * TBN : TBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -282,11 +321,20 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
     return r == CUDA_SUCCESS;
 }
 
+static int tc_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
 template <bool TA, bool NB, bool S3>
 static int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mal, const CUtensorMap& mbl,
                      const TcParams& p, dim3 grid) {
     auto kern = gemm_tc_kernel<TA, NB, S3>;
-    constexpr uint32_t smem = S3 ? (2 * 3 * (STAGE_A_BYTES + STAGE_B_BYTES) + 1024 + 256) : TC_SMEM;
+    constexpr uint32_t smem = S3 ? (2 * 3 * (STAGE_A_BYTES + STAGE_B_BYTES) + TC_STG_BYTES + 1024 + 256) : TC_SMEM;
     static bool attr_set = false;
     if (!attr_set) {
         AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -334,8 +382,8 @@ int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const floa
                     make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) && make_map(&mbl, Blo, (uint64_t)K, (uint64_t)N, ldb, TBN, false);
     if (!ok) return 1;
     const int nkb = cdiv(K, TBK);
-    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb};
-    dim3 grid(cdiv(N, TBN), cdiv(M, TBM), 1);
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1};
+    dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM), tc_num_sms()));
     return launch_tc<false, false, true>(st, ma, mb, mal, mbl, p, grid);
 }
 
@@ -357,12 +405,12 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
     }
     const int kbps = cdiv(nkb, splits);
     splits = cdiv(nkb, kbps);
-    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps};
+    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps, splits};
     if (splits > 1) {
         if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
         else if (beta != 1.f) return 1;
     }
-    dim3 grid(cdiv(N, TBN), cdiv(M, TBM), splits);
+    dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM) * splits, tc_num_sms()));
     if (!ta && tb) return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
     if (!ta && !tb) return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
     if (ta && !tb) return launch_tc<true, true, false>(st, ma, mb, ma, mb, p, grid);
