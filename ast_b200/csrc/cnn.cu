@@ -171,35 +171,36 @@ int bn_relu_pad(cudaStream_t st, const float* raw, float* out, const float* mean
 // ---- BN apply + ReLU + relayout for the last CNN layer -------------------------------------
 // raw1 [b][f][Rs][C] (rows t' < Tp valid) -> rnn_in[t'][b][c*Fp+f] and (optionally) the step-ordered
 // copy for the reverse stack rnn_rev[i] = rnn_in[(-i) mod Tp]  (seq2seq.py:219 `X[-i]`).
-__global__ void bn_relu_to_rnn_kernel(const float* __restrict__ raw, float* __restrict__ rnn_in,
+// One CTA per (t', b): reads the F' channel rows of that frame (each C contiguous floats), writes the whole R = C*F' feature
+// row of rnn_in / rnn_rev contiguously through a shared-memory transpose.  (The element-per-thread version wrote with a
+// stride of F' floats between lanes: ncu showed 2.0 TB/s, 31 % of the HBM roofline, for a pure relayout.)
+__global__ void __launch_bounds__(128) bn_relu_to_rnn_kernel(const float* __restrict__ raw, float* __restrict__ rnn_in,
                                       float* __restrict__ rnn_rev, const float* __restrict__ mean,
                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int B, int Fp, int Rs, int Tp, int C) {
-    const size_t total = (size_t)B * Fp * Tp * C;
+    extern __shared__ float row[];          // R floats
+    const int t = blockIdx.x / B, b = blockIdx.x - t * B;
     const int R = C * Fp;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t r = i / C;
-        const int t = (int)(r % Tp); r /= Tp;
-        const int f = (int)(r % Fp);
-        const int b = (int)(r / Fp);
-        const float x = raw[(((size_t)b * Fp + f) * Rs + t) * C + c];
-        const float v = fmaxf(gamma[c] * ((x - mean[c]) * invstd[c]) + beta[c], 0.f);
-        rnn_in[((size_t)t * B + b) * R + c * Fp + f] = v;
-        if (rnn_rev) {
-            const int i_rev = (Tp - t) % Tp;          // step i with (-i) mod Tp == t
-            rnn_rev[((size_t)i_rev * B + b) * R + c * Fp + f] = v;
-        }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float g = gamma[c], mu = mean[c], is = invstd[c], bt = beta[c];
+        for (int f = 0; f < Fp; ++f)        // same expression as the backward mask (g * xhat + beta > 0)
+            row[c * Fp + f] = fmaxf(g * ((raw[(((size_t)b * Fp + f) * Rs + t) * C + c] - mu) * is) + bt, 0.f);
+    }
+    __syncthreads();
+    float4* o1 = reinterpret_cast<float4*>(rnn_in + ((size_t)t * B + b) * R);
+    float4* o2 = rnn_rev ? reinterpret_cast<float4*>(rnn_rev + ((size_t)((Tp - t) % Tp) * B + b) * R) : nullptr;   // step i with (-i) mod Tp == t
+    for (int i = threadIdx.x; i < R / 4; i += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(row)[i];
+        o1[i] = v;
+        if (o2) o2[i] = v;
     }
 }
 
 int bn_relu_to_rnn(cudaStream_t st, const float* raw, float* rnn_in, float* rnn_rev, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, int B, int Fp, int Rs, int Tp,
                    int C) {
-    const size_t total = (size_t)B * Fp * Tp * C;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    bn_relu_to_rnn_kernel<<<grid, 256, 0, st>>>(raw, rnn_in, rnn_rev, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C);
+    AST_CHECK((C * Fp) % 4 == 0, "bn_relu_to_rnn: C*F' must be a multiple of 4");
+    bn_relu_to_rnn_kernel<<<Tp * B, 128, sizeof(float) * C * Fp, st>>>(raw, rnn_in, rnn_rev, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C);
     AST_LAUNCH_OK();
     return 0;
 }
@@ -302,12 +303,107 @@ static int bn_bwd_impl(cudaStream_t st, DY dyf, const float* raw, float* dx, con
     return 0;
 }
 
+// ---- last CNN layer: dy arrives in the RNN feature layout  d_rnn_in[t'][b][c*F'+f] (+ d_rnn_rev[(T'-t')%T'][b][..]) ----
+// Same two passes as bn_bwd_impl, organised per (t', b) feature row so that every global access is contiguous: the row(s)
+// of dy are staged in shared memory (float4 loads), then lane c walks f.
+__global__ void __launch_bounds__(256) bn_bwd_rnn_reduce_kernel(const float* __restrict__ d_in, const float* __restrict__ d_rev,
+                                         const float* __restrict__ raw, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, double* __restrict__ stats, int B, int Fp, int Rs,
+                                         int Tp, int C, int rows_per_block) {
+    extern __shared__ float dyrow[];        // R floats
+    const int R = C * Fp, TB = Tp * B;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(TB, r0 + rows_per_block);
+    constexpr int MAXC = 4;                 // channels per thread (C <= 1024)
+    double db[MAXC], dg[MAXC];
+    float mu[MAXC], is[MAXC], g[MAXC], bt[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        const int c = threadIdx.x + k * 256;
+        db[k] = dg[k] = 0.0;
+        if (c < C) { mu[k] = mean[c]; is[k] = invstd[c]; g[k] = gamma[c]; bt[k] = beta[c]; }
+    }
+    for (int r = r0; r < r1; ++r) {
+        const int t = r / B, b = r - t * B;
+        const float4* s1 = reinterpret_cast<const float4*>(d_in + (size_t)r * R);
+        const float4* s2 = d_rev ? reinterpret_cast<const float4*>(d_rev + ((size_t)((Tp - t) % Tp) * B + b) * R) : nullptr;
+        __syncthreads();
+        for (int i = threadIdx.x; i < R / 4; i += 256) {
+            float4 v = s1[i];
+            if (s2) { const float4 w = s2[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+            reinterpret_cast<float4*>(dyrow)[i] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            const int c = threadIdx.x + k * 256;
+            if (c < C)
+                for (int f = 0; f < Fp; ++f) {
+                    const float xh = (raw[(((size_t)b * Fp + f) * Rs + t) * C + c] - mu[k]) * is[k];
+                    if (g[k] * xh + bt[k] > 0.f) {
+                        const float dy = dyrow[c * Fp + f];
+                        db[k] += dy; dg[k] += (double)dy * xh;
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < C) { atomicAdd(&stats[c], db[k]); atomicAdd(&stats[C + c], dg[k]); }
+    }
+}
+
+// one CTA per (b, t in [0, Rs)): rows t >= T' are the junk rows of the padded segment and get zeros
+__global__ void __launch_bounds__(128) bn_bwd_rnn_apply_kernel(const float* __restrict__ d_in, const float* __restrict__ d_rev,
+                                        const float* __restrict__ raw, float* __restrict__ dx, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const double* __restrict__ stats,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Fp, int Rs, int Tp,
+                                        int C, float inv_m) {
+    extern __shared__ float dyrow[];
+    const int b = blockIdx.x / Rs, t = blockIdx.x - b * Rs;
+    const int R = C * Fp;
+    if (t >= Tp) {
+        for (int f = 0; f < Fp; ++f)
+            for (int c = threadIdx.x; c < C; c += blockDim.x) dx[(((size_t)b * Fp + f) * Rs + t) * C + c] = 0.f;
+        return;
+    }
+    const float4* s1 = reinterpret_cast<const float4*>(d_in + ((size_t)t * B + b) * R);
+    const float4* s2 = d_rev ? reinterpret_cast<const float4*>(d_rev + ((size_t)((Tp - t) % Tp) * B + b) * R) : nullptr;
+    for (int i = threadIdx.x; i < R / 4; i += blockDim.x) {
+        float4 v = s1[i];
+        if (s2) { const float4 w = s2[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+        reinterpret_cast<float4*>(dyrow)[i] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float db = (float)stats[c], dg = (float)stats[C + c];
+        const float is = invstd[c], g = gamma[c], mu = mean[c], bt = beta[c];
+        for (int f = 0; f < Fp; ++f) {
+            const size_t i = (((size_t)b * Fp + f) * Rs + t) * C + c;
+            const float xh = (raw[i] - mu) * is;
+            const float dy = (g * xh + bt > 0.f) ? dyrow[c * Fp + f] : 0.f;
+            dx[i] = g * is * (dy - db * inv_m - xh * (dg * inv_m));
+        }
+        if (blockIdx.x == 0) { dgamma[c] = dg; dbeta[c] = db; }
+    }
+}
+
 int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, const float* raw, float* dx,
                     const float* mean, const float* invstd, const float* gamma, const float* beta,
                     double* stats, float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C) {
-    DyFromRnn f{d_in, d_rev, B, Fp, Rs, Tp, C};
-    return bn_bwd_impl(st, f, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B * Fp * Rs, C, Rs, Tp,
-                       (double)B * Fp * Tp);
+    AST_CHECK((C * Fp) % 4 == 0 && C <= 1024, "bn_bwd_from_rnn: need C*F' %% 4 == 0 and C <= 1024");
+    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+    const int TB = Tp * B;
+    const int rpb = std::max(1, cdiv(TB, 148 * 4));
+    const size_t smem = sizeof(float) * C * Fp;
+    bn_bwd_rnn_reduce_kernel<<<cdiv(TB, rpb), 256, smem, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, stats, B, Fp, Rs, Tp, C, rpb);
+    AST_LAUNCH_OK();
+    bn_bwd_rnn_apply_kernel<<<B * Rs, 128, smem, st>>>(d_in, d_rev, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B, Fp,
+                                                       Rs, Tp, C, (float)(1.0 / ((double)B * Fp * Tp)));
+    AST_LAUNCH_OK();
+    return 0;
 }
 
 int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
