@@ -77,12 +77,28 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     // resident weight slice: smem row p = 32*gate + unit  <-  W_lat row 4*(32*rank + unit) + gate, rounded to TF32
-    for (int idx = tid; idx < 128 * (h / 4); idx += TC_THREADS) {
-        const int p = idx / (h / 4), k4 = idx % (h / 4);
-        const int gate = p >> 5, unit = p & 31;
-        float4 v = *reinterpret_cast<const float4*>(a.Wl + (size_t)(4 * (TU * rank + unit) + gate) * h + k4 * 4);
-        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
-        *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) = v;
+    // 8192 float4 per CTA; loads are issued in batches of 8 per thread before the first store (a load -> round -> store loop
+    // serialises on L2 latency: ~28 round trips, most of the ~17 us fixed cost of a chunk launch)
+    for (int base = 0; base < 128 * (h / 4); base += 8 * TC_THREADS) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            if (idx < 128 * (h / 4)) {
+                const int p = idx / (h / 4), k4 = idx % (h / 4);
+                const int gate = p >> 5, unit = p & 31;
+                v[u] = __ldg(reinterpret_cast<const float4*>(a.Wl + (size_t)(4 * (TU * rank + unit) + gate) * h + k4 * 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            if (idx < 128 * (h / 4)) {
+                const int p = idx / (h / 4), k4 = idx % (h / 4);
+                *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) =
+                    make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
+            }
+        }
     }
     for (int idx = tid; idx < (int)(2 * FW_H_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sH)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
@@ -239,12 +255,25 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 
     // W slice rows p = 4*unit + gate (natural order, = dG's k index), all 256 unit columns n:
     // chunk j = n/32 at j*16 KB, k-row p at p*128 B, 32-byte sub-chunk ((n%32)/8) XOR (p % 4)
-    for (int idx = tid; idx < 128 * (h / 4); idx += TC_THREADS) {
-        const int p = idx / (h / 4), n4 = idx % (h / 4), n = 4 * n4;
-        float4 v = *reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n);
-        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
-        const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
-        *reinterpret_cast<float4*>(sA + off) = v;
+    for (int base = 0; base < 128 * (h / 4); base += 8 * TC_THREADS) {      // batched loads, see the forward kernel
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            if (idx < 128 * (h / 4)) {
+                const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
+                v[u] = __ldg(reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            if (idx < 128 * (h / 4)) {
+                const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
+                const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
+                *reinterpret_cast<float4*>(sA + off) = make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
+            }
+        }
     }
     for (int idx = tid; idx < (int)(BW_G_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sG)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int idx = tid; idx < (int)(2 * BW_R_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(red)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
