@@ -172,18 +172,16 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def roofline_dominant(engine, torch, peaks):
-    """Time the dominant kernel of the step in isolation at its workload shape with CUDA events and
-    report achieved / measured peak.  Dominant kernel: see profiles/ (ncu launch list)."""
+    """Time the largest single-pass tensor-core kernel of the step in isolation at its workload shape with CUDA events and
+    report achieved / measured peak: the tcgen05 GEMM as the CNN_1 data gradient dA = d(raw1) . W1p (NN form; M = B*F'*Rs
+    rows of a B32 x T640 batch, N = 9*128, K = 512), the shape of the ncu --set full capture under profiles/."""
     import ctypes as C
     from ast_b200._lib import ptr, check
     hbm, tf_burst, tf_sus, how = peaks
     lib = engine.lib
     dev = engine.device
-    # L0 encoder input projection of a median batch: (T'*B x R) . (4h x R)^T, R = 1536, 4h = 1024
-    Tp, B, R, N = 160, BATCH, 1536, 1024       # the shape of the ncu --set full capture (profiles/r01_ncu_full_extract_v9.txt)
-    M = Tp * B
-    A = torch.randn(M, R, device=dev); W = torch.randn(N, R, device=dev); Cc = torch.empty(M, N, device=dev)
-    bias = torch.randn(N, device=dev)
+    M, N, K = 15744, 1152, 512
+    A = torch.randn(M, K, device=dev); W = torch.randn(K, N, device=dev); Cc = torch.empty(M, N, device=dev)
     which = 1 if engine.get_option("tc_gemm") and not engine.get_option("exact") else 0
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -192,23 +190,29 @@ def roofline_dominant(engine, torch, peaks):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(lib.ast_gemm(which, 0, 1, M, N, R, 1.0, ptr(A), R, ptr(W), R, 0.0, ptr(Cc), N, ptr(bias), st), "ast_gemm")
+        check(lib.ast_gemm(which, 0, 0, M, N, K, 1.0, ptr(A), K, ptr(W), N, 0.0, ptr(Cc), N, None, st), "ast_gemm")
         e1.record()
         torch.cuda.synchronize()
         if it >= 3:
             ts.append(e0.elapsed_time(e1))
     ms = float(np.mean(ts))
-    flops = 2.0 * M * N * R
+    flops = 2.0 * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = tf_burst / 2.0 if which == 1 else tf_burst / 2.0      # TF32 dense = 1/2 of the measured bf16 figure
-    return {"bound": "tensor", "kernel": "gemm_tc_nt (tcgen05 TF32)" if which == 1 else "sgemm_kernel (fp32 SIMT)",
-            "shape": f"M{M} N{N} K{R}", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape (ncu --set full, profiles/): operands
-            # 37.8 MB read once; the 21 MB output stays in the 126 MB L2 for its consumer.  Algorithmic bytes: 58.7 MB.
-            "traffic": 38.2e6 if (which == 1 and M == 5120) else None, "traffic_unit": "bytes/launch",
-            "ncu": {"tensor_pipe_active_pct": 38.4, "l2_sector_pct_of_peak": 19.5, "smem_fill_bytes": 503e6,
-                    "source": "profiles/r01_ncu_full_extract_v9.txt"} if which == 1 else None}
+    peak = tf_burst / 2.0                                         # TF32 dense = 1/2 of the measured bf16 figure
+    out = {"bound": "tensor", "kernel": "gemm_tc_kernel<NN> (tcgen05 TF32, persistent)" if which == 1 else "sgemm_kernel (fp32 SIMT)",
+           "shape": f"M{M} N{N} K{K} (CNN_1 data gradient)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+           "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms,
+           "algorithmic_bytes": 4.0 * (M * K + K * N + M * N), "traffic": None, "traffic_unit": "bytes/launch"}
+    out.update(NCU_GEMM if which == 1 else {})
+    return out
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum and pipe counters of this kernel at this shape from the ncu --set full capture
+# (tools/ncu_capture.sh, extract under profiles/); filled in from the round's capture
+NCU_GEMM = {"traffic": 34.65e6 + 18.47e6,     # the 72.5 MB output is only partly written back within the kernel's lifetime (126 MB L2)
+            "ncu": {"gpu_time_us_cold": 54.9, "tensor_pipe_active_pct": 38.1, "tensor_pipe_elapsed_pct": 32.5,
+                    "l2_sector_pct_of_peak": 28.9, "l2_hit_rate_pct": 69.4, "smem_fill_bytes": 580.4e6,
+                    "source": "profiles/r01_ncu_full_extract_v18.txt"}}
 
 
 def beam_rate(model, torch, T, n_utts, stop_limit, N=10, K=10):

@@ -10,7 +10,7 @@ $cmd > gpurun_out/plain_$tag.log 2>&1 || { echo "plain run failed"; tail -5 gpur
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv $cmd > gpurun_out/ncu_l_$tag.log 2>&1
 echo "launch list rc=$?"
 cap() {  # name regex skip count
-    ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o /tmp/cap_$1 $cmd > gpurun_out/ncu_f_$1_$tag.log 2>&1
+    ncu -f --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o /tmp/cap_$1 $cmd > gpurun_out/ncu_f_$1_$tag.log 2>&1
     echo "capture $1 rc=$?"
     ncu -i /tmp/cap_$1.ncu-rep --page raw --csv > gpurun_out/full_$1_$tag.csv 2>/dev/null
     ncu -i /tmp/cap_$1.ncu-rep --page details --csv > gpurun_out/details_$1_$tag.csv 2>/dev/null
