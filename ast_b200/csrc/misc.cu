@@ -108,11 +108,56 @@ __global__ void pack_cmvn_kernel(const float* __restrict__ raw, const long long*
         X[i] = v;
     }
 }
+// float4 variant (D % 4 == 0, 16-byte aligned buffers): one thread = 4 consecutive features of one frame, so the raw read,
+// the scale/offset reads and the padded write are all 16-byte accesses; frame index arithmetic once per 4 elements.
+__global__ void pack_cmvn4_kernel(const float* __restrict__ raw, const long long* __restrict__ row_off,
+                                  const int* __restrict__ lens, const float* __restrict__ scale,
+                                  const float* __restrict__ offset, const unsigned char* __restrict__ keep,
+                                  const float* __restrict__ noise, float noise_sigma, unsigned long long seed,
+                                  float* __restrict__ X, int B, int T, int D) {
+    const int D4 = D >> 2;
+    const size_t total4 = (size_t)B * T * D4;
+    for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i4 % D4) * 4;
+        const size_t bt = i4 / D4;
+        const int t = (int)(bt % T);
+        const int b = (int)(bt / T);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < lens[b] && (keep == nullptr || keep[bt])) {
+            v = *reinterpret_cast<const float4*>(raw + (size_t)(row_off[b] + t) * D + d);
+            if (scale) {
+                const float4 sc = *reinterpret_cast<const float4*>(scale + (size_t)b * D + d);
+                const float4 of = *reinterpret_cast<const float4*>(offset + (size_t)b * D + d);
+                v.x = v.x * sc.x + of.x; v.y = v.y * sc.y + of.y; v.z = v.z * sc.z + of.z; v.w = v.w * sc.w + of.w;
+            }
+            const size_t i = bt * D + d;
+            float f[4] = {1.f, 1.f, 1.f, 1.f};
+            if (noise) { const float4 n = *reinterpret_cast<const float4*>(noise + i); f[0] = n.x; f[1] = n.y; f[2] = n.z; f[3] = n.w; }
+            else if (noise_sigma > 0.f) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float u1 = fmaxf(rng_uniform(seed, 0x51u, (uint32_t)(i + j)), 1e-7f);
+                    const float u2 = rng_uniform(seed, 0x52u, (uint32_t)(i + j));
+                    f[j] = 1.f + noise_sigma * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+                }
+            }
+            v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+        }
+        *reinterpret_cast<float4*>(X + bt * D + d) = v;
+    }
+}
 int pack_cmvn(cudaStream_t st, const float* raw, const long long* row_off, const int* lens, const float* scale,
               const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
               unsigned long long seed, float* X, int B, int T, int D) {
     const size_t total = (size_t)B * T * D;
     if (total == 0) return 0;
+    auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (D % 4 == 0 && al16(raw) && al16(X) && al16(scale) && al16(offset) && al16(noise)) {
+        const int grid4 = (int)std::min<size_t>((total / 4 + 255) / 256, 148 * 16);
+        pack_cmvn4_kernel<<<grid4, 256, 0, st>>>(raw, row_off, lens, scale, offset, keep, noise, noise_sigma, seed, X, B, T, D);
+        AST_LAUNCH_OK();
+        return 0;
+    }
     const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     pack_cmvn_kernel<<<grid, 256, 0, st>>>(raw, row_off, lens, scale, offset, keep, noise, noise_sigma, seed, X, B, T, D);
     AST_LAUNCH_OK();

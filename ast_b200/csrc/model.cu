@@ -85,7 +85,7 @@ struct ast_model {
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr; int overlap = 1; bool tr_pending = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
-    cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 32;
+    cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
