@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libast_b200.so")
-SOURCES = ["model.cu", "gemm_simt.cu", "gemm_tc.cu", "cnn.cu", "lstm_seq.cu", "lstm_seq_tc.cu", "decoder.cu", "dec_seq.cu", "dec_seq2.cu", "misc.cu", "beam.cu"]
+SOURCES = ["model.cu", "gemm_simt.cu", "gemm_tc.cu", "cnn.cu", "lstm_seq.cu", "lstm_seq_tc.cu", "decoder.cu", "dec_seq.cu", "dec_seq2.cu", "misc.cu", "beam.cu", "beam_seq.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -33,37 +33,49 @@ __device__ __forceinline__ void skinny_tile(const SkinnyArgs& p, int n0, SkinnyS
 
     const int nch0 = p.K[0] >> 4, nch1 = p.K[1] >> 4;
     const int nn0 = n0 + g, nn1 = n0 + 8 + g;
-#pragma unroll 2
-    for (int c = w; c < nch0 + nch1; c += 8) {
-        const int seg = c < nch0 ? 0 : 1;
-        const int k = ((seg ? c - nch0 : c) << 4) + 4 * q;
-        const float* __restrict__ W = p.W[seg];
-        const float* __restrict__ X = p.X[seg];
-        const int ldw = p.ldw[seg], ldx = p.ldx[seg];
-        float4 wv0 = make_float4(0.f, 0.f, 0.f, 0.f), wv1 = wv0;
-        if (nn0 < p.N) wv0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)nn0 * ldw + k));
-        if (nn1 < p.N) wv1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)nn1 * ldw + k));
-        float4 xv[MT][2];
+    // A warp's chunks are c = w, w + 8, ...; the loads of UB chunks are issued before the first mma of the batch (a
+    // load -> mma loop serialises on L2 latency: a phase of the persistent kernels is a handful of such round trips).
+    constexpr int UB = MT == 1 ? 3 : 2;
+    for (int c0 = w; c0 < nch0 + nch1; c0 += 8 * UB) {
+        float4 wv0[UB], wv1[UB], xv[UB][MT][2];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int u = 0; u < UB; ++u) {
+            const int c = c0 + 8 * u;
+            wv0[u] = wv1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int row = mt * 16 + g + 8 * hf;
-                xv[mt][hf] = make_float4(0.f, 0.f, 0.f, 0.f);
-                // activations may have been written earlier in the same (persistent) kernel: no read-only path
-                if (row < p.B) xv[mt][hf] = __ldcg(reinterpret_cast<const float4*>(X + (size_t)row * ldx + k));
+            for (int mt = 0; mt < MT; ++mt) xv[u][mt][0] = xv[u][mt][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nch0 + nch1) {
+                const int seg = c < nch0 ? 0 : 1;
+                const int k = ((seg ? c - nch0 : c) << 4) + 4 * q;
+                const float* __restrict__ W = p.W[seg];
+                const float* __restrict__ X = p.X[seg];
+                const int ldw = p.ldw[seg], ldx = p.ldx[seg];
+                if (nn0 < p.N) wv0[u] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nn0 * ldw + k));
+                if (nn1 < p.N) wv1[u] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nn1 * ldw + k));
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int row = mt * 16 + g + 8 * hf;
+                        // activations may have been written earlier in the same (persistent) kernel: no read-only path
+                        if (row < p.B) xv[u][mt][hf] = __ldcg(reinterpret_cast<const float4*>(X + (size_t)row * ldx + k));
+                    }
             }
-        // two k-steps; lane q supplies physical k = 4q+{0,1} then 4q+{2,3} for both operands
-        const float b0a[2] = {wv0.x, wv0.y}, b0b[2] = {wv0.z, wv0.w};
-        const float b1a[2] = {wv1.x, wv1.y}, b1b[2] = {wv1.z, wv1.w};
+        }
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const float aa[4] = {xv[mt][0].x, xv[mt][1].x, xv[mt][0].y, xv[mt][1].y};
-            const float ab[4] = {xv[mt][0].z, xv[mt][1].z, xv[mt][0].w, xv[mt][1].w};
-            mma_f32<EXACT>(acc[0][mt], aa, b0a);
-            mma_f32<EXACT>(acc[0][mt], ab, b0b);
-            mma_f32<EXACT>(acc[1][mt], aa, b1a);
-            mma_f32<EXACT>(acc[1][mt], ab, b1b);
+        for (int u = 0; u < UB; ++u) {
+            // two k-steps; lane q supplies physical k = 4q+{0,1} then 4q+{2,3} for both operands (zero chunks add nothing)
+            const float b0a[2] = {wv0[u].x, wv0[u].y}, b0b[2] = {wv0[u].z, wv0[u].w};
+            const float b1a[2] = {wv1[u].x, wv1[u].y}, b1b[2] = {wv1[u].z, wv1[u].w};
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const float aa[4] = {xv[u][mt][0].x, xv[u][mt][1].x, xv[u][mt][0].y, xv[u][mt][1].y};
+                const float ab[4] = {xv[u][mt][0].z, xv[u][mt][1].z, xv[u][mt][0].w, xv[u][mt][1].w};
+                mma_f32<EXACT>(acc[0][mt], aa, b0a);
+                mma_f32<EXACT>(acc[0][mt], ab, b0b);
+                mma_f32<EXACT>(acc[1][mt], aa, b1a);
+                mma_f32<EXACT>(acc[1][mt], ab, b1b);
+            }
         }
     }
     __syncthreads();          // sm may still be read by the previous tile's epilogue

@@ -168,6 +168,19 @@ struct BeamState {
     float* new_score; int* new_parent; int* new_tok; int* new_finished;
 };
 struct BeamGather { int n; const float* cur[8]; const float* post[8]; float* nxt[8]; int width[8]; };
+// Persistent beam search (beam_seq.cu): everything one utterance's search touches.
+struct BeamSeq {
+    int N, K, V, Vp, H, E, A, Tp, NL, stop_limit, eos;
+    const float* emb; const float* Wup[AST_MAXL]; const float* bup[AST_MAXL]; const float* Wlat[AST_MAXL];
+    const float* Wa; const float* ba; const float* Wc; const float* bc; const float* Wo; const float* bo;
+    const float* enc;                                   // (T' x H), one utterance
+    float* h[2][AST_MAXL]; float* c[2][AST_MAXL]; float* ht[2]; int* words[2];     // two state banks (slot r = hypothesis r)
+    float* hpost[AST_MAXL]; float* cpost[AST_MAXL];     // this step's new states before the hand-over
+    float* x0; float* act; float* hd[AST_MAXL]; float* q; float* scores; float* alpha; float* cvh; float* htout; float* logits;
+    BeamState bs; float* cand_lp; int* cand_tok;
+    int* hist_parent; int* hist_tok; float* alpha_hist;
+};
+int beam_seq(cudaStream_t st, const BeamSeq& p);
 int beam_topk(cudaStream_t st, const float* z, int ldz, int V, int K, int N, const BeamState& bs, float* cand_lp, int* cand_tok);
 int beam_prune(cudaStream_t st, const BeamState& bs, const float* cand_lp, const int* cand_tok, int N, int K, int step,
                int eos, int* hist_parent, int* hist_tok);

@@ -65,7 +65,10 @@ struct ast_model {
     float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
     float *encW, *encb;        // dec_seq2: enc_states . W_a and enc_states . b_a
     float *dzw, *dcv_all, *ds_all, *dE;   // dec_seq2 backward
-    int dec_v2 = 1;
+    // beam_fused: the search as one persistent launch (beam_seq.cu).  Measured no faster than the kernel-per-phase loop (159 vs
+    // 146 us per step at N = 10): a step is bound by streaming the 31.6 MB of decoder weights from L2 in 3xTF32 arithmetic,
+    // not by launches, which the stream already pipelines.  Kept as an option (tests run both).
+    int dec_v2 = 1, beam_fused = 0;
     float *draw1, *dA1, *da0p, *draw0, *dW1p, *dW0pad;
     // decoder (training)
     float *x0, *actd[MAXL], *Hdec[MAXL], *Cdec[MAXL], *hdd[MAXL], *q, *scores, *alpha, *cvh, *ht, *logits, *row_loss;
@@ -995,6 +998,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
     else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
+    else if (!strcmp(key, "beam_fused")) m->beam_fused = value != 0;
     else if (!strcmp(key, "stage_timing")) m->stage_timing = value != 0;
     else if (!strcmp(key, "conv3x")) m->conv3x = value != 0;
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
@@ -1179,6 +1183,28 @@ int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, 
     BeamState bs{}; bs.score = m->b_score; bs.finished = finished; bs.n_active = scal; bs.done = scal + 1; bs.steps_done = scal + 2;
     bs.new_score = m->b_new_score; bs.new_parent = new_parent; bs.new_tok = new_tok; bs.new_finished = new_fin;
     int bank = 0;
+    AST_CHECK(alpha_hist != nullptr, "beam_search: alpha_hist buffer required");
+    if (m->beam_fused && N <= 16) {
+        // the whole step loop in ONE cooperative launch (beam_seq.cu)
+        BeamSeq q{};
+        q.N = N; q.K = K; q.V = m->V; q.Vp = m->Vp; q.H = H; q.E = m->E; q.A = A; q.Tp = Tp; q.NL = NL; q.stop_limit = stop_limit; q.eos = eos_token;
+        q.emb = m->p("embed_dec/W");
+        for (int l = 0; l < NL; ++l) {
+            const std::string ln = lname(l, "dec");
+            q.Wup[l] = m->p((ln + "/upward/W").c_str()); q.bup[l] = m->p((ln + "/upward/b").c_str()); q.Wlat[l] = m->p((ln + "/lateral/W").c_str());
+            for (int k = 0; k < 2; ++k) { q.h[k][l] = m->st_h[k][l]; q.c[k][l] = m->st_c[k][l]; }
+            q.hpost[l] = m->st_hpost[l]; q.cpost[l] = m->st_cpost[l]; q.hd[l] = m->s_hd[l];
+        }
+        for (int k = 0; k < 2; ++k) { q.ht[k] = m->st_ht[k]; q.words[k] = m->s_words[k]; }
+        q.Wa = m->p("attn_Wa/W"); q.ba = m->p("attn_Wa/b"); q.Wc = m->p("context/W"); q.bc = m->p("context/b");
+        q.Wo = m->p("out/W"); q.bo = m->p("out/b");
+        q.enc = m->enc_states;
+        q.x0 = m->s_x0; q.act = m->s_act; q.q = m->s_q; q.scores = m->s_scores; q.alpha = m->s_alpha; q.cvh = m->s_cvh;
+        q.htout = m->s_htout; q.logits = m->s_logits;
+        q.bs = bs; q.cand_lp = m->b_cand_lp; q.cand_tok = m->b_cand_tok;
+        q.hist_parent = hist_parent; q.hist_tok = hist_tok; q.alpha_hist = alpha_hist;
+        AST_TRY(beam_seq(st, q));
+    } else
     for (int s = 0; s < stop_limit; ++s) {
         AST_TRY(decode_bank_step(m, bank, N, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st));
         AST_TRY(beam_topk(st, m->s_logits, m->Vp, m->V, K, N, bs, m->b_cand_lp, m->b_cand_tok));

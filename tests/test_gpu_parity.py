@@ -355,10 +355,12 @@ def test_greedy_and_beam_hypotheses_identical(dev):
         from ast_b200.nn import beam_result_to_entries
         for (N, K) in [(4, 3), (10, 10), (1, 1), (3, 5)]:
             nb = om.decode_beam(X[:1, :lens[0]], stop, N, K)
-            ent = beam_result_to_entries(e.beam_search(X[:1, :lens[0]], stop, N, K))
-            assert [a["hyp"] for a in ent] == [b["hyp"] for b in nb], (boost, N, K)
-            assert np.allclose([float(a["score"]) for a in ent], [float(b["score"]) for b in nb], rtol=1e-4)
-            assert _relerr(np.stack(ent[0]["attn_history"]), np.stack(nb[0]["attn_history"])) < 1e-3
+            for fused in (0, 1):       # kernel-per-phase search and the single-launch persistent kernel (beam_seq.cu)
+                e.set_option("beam_fused", fused)
+                ent = beam_result_to_entries(e.beam_search(X[:1, :lens[0]], stop, N, K))
+                assert [a["hyp"] for a in ent] == [b["hyp"] for b in nb], (boost, N, K, fused)
+                assert np.allclose([float(a["score"]) for a in ent], [float(b["score"]) for b in nb], rtol=1e-4)
+                assert _relerr(np.stack(ent[0]["attn_history"]), np.stack(nb[0]["attn_history"])) < 1e-3
 
 
 def test_eval_mode_uses_running_statistics(dev):
