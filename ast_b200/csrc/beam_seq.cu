@@ -3,7 +3,7 @@
 // utterance.  The N live hypotheses are the decoder batch.  A step is 12 phases separated by grid barriers instead of 13
 // kernel launches (the per-launch version in model.cu::ast_beam_search spends ~140 us per step, mostly launch and drain
 // latency around 5-10 us kernels).  Arithmetic is the fp32-faithful path of the decode_step protocol (3xTF32-split mma.sync,
-// accurate transcendental functions), so hypotheses stay identical to the fp32 oracle; every phase body is the same device
+// accurate transcendental functions), so hypotheses stay identical to the fp32 reference arithmetic; every phase body is the same device
 // function the per-step kernels run (decoder_dev.cuh, beam_dev.cuh).
 #include <cooperative_groups.h>
 #include "beam_dev.cuh"

@@ -21,6 +21,10 @@
 
 namespace ast {
 
+// optional cycle probe (tools/lstm_step_probe.py): CTA 0 stores clock64() stamps of steps 8..23 of the forward kernel
+static unsigned long long* g_lstm_prof = nullptr;
+void lstm_tc_set_prof(unsigned long long* p) { g_lstm_prof = p; }
+
 constexpr int TNC = 8;           // CTAs per cluster
 constexpr int TH = 256;          // per-direction hidden size handled by this kernel
 constexpr int TU = TH / TNC;     // 32 hidden units per CTA
@@ -31,6 +35,26 @@ constexpr int TC_THREADS = TC_EPI + 32;
 __device__ __forceinline__ float rnd_tf32(float x) { return __uint_as_float(f2tf32(x)); }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+// D[tmem] (+)= A[tmem, lane = row m, column = k] . B[smem]: the weight operand read from TENSOR MEMORY instead of shared memory
+// (cute::SM100_MMA_TF32_TS).  With the weight on the M side (swap-AB) every step re-reads the whole 128 KB slice; from shared
+// memory that alone was ~1900 cycles of a 4740-cycle step (tools/lstm_step_probe.py).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
 }
@@ -55,12 +79,17 @@ __device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows_per_bloc
 // forward
 // ================================================================================================
 constexpr uint32_t FW_A_BYTES = 8 * 128 * 128;          // W slice: 8 k-blocks x 128 gate rows x 128 B
+constexpr uint32_t FW_TMEM_D = 0;                       // accumulator column
+constexpr uint32_t FW_TMEM_COLS = 32;
 constexpr uint32_t FW_H_BYTES = 8 * TROWS * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B
 constexpr uint32_t FW_XG_BYTES = 4 * TROWS * TU * 4;    // gate exchange [gate][batch][unit]
-constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + 64 + 1024;
+constexpr uint32_t FW_STG_BYTES = 2 * TROWS * 128;      // [2] staging of this CTA's h slice (= one k-block of the operand layout)
+constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_BYTES + 64 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed) {
+lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, unsigned long long* prof) {
+    const bool probe = prof != nullptr && blockIdx.x == 0;
+#define PROBE(slot) do { if (probe && i >= 8 && i < 24) prof[(i - 8) * 8 + (slot)] = clock64(); } while (0)
     const int rank = (int)cluster_rank();
     const LstmChain a = ch.c[blockIdx.x / TNC];
     constexpr int h = TH, H4 = 4 * TH;
@@ -70,15 +99,30 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     uint8_t* sA = sm;                                  // resident W slice, rows p = 32*gate + unit
     uint8_t* sH = sm + FW_A_BYTES;                     // [2] h buffers (UMMA B operand)
     float* xg = reinterpret_cast<float*>(sm + FW_A_BYTES + 2 * FW_H_BYTES);
-    uint64_t* mbar_h = reinterpret_cast<uint64_t*>(sm + FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES);   // [2]
+    uint8_t* sStg = sm + FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES;
+    uint64_t* mbar_h = reinterpret_cast<uint64_t*>(sm + FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_BYTES);   // [2]
     uint64_t* mbar_mma = mbar_h + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_h + 3);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
-    // resident weight slice: smem row p = 32*gate + unit  <-  W_lat row 4*(32*rank + unit) + gate, rounded to TF32
-    // 8192 float4 per CTA; loads are issued in batches of 8 per thread before the first store (a load -> round -> store loop
-    // serialises on L2 latency: ~28 round trips, most of the ~17 us fixed cost of a chunk launch)
+    for (int idx = tid; idx < (int)(2 * FW_H_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sH)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&mbar_h[0], 1); mbar_init(&mbar_h[1], 1); mbar_init(mbar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(tmem_slot)), "n"(FW_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // Resident weight slice in shared memory: row p = 32*gate + unit  <-  W_lat row 4*(32*rank + unit) + gate, rounded to TF32.
+    // (The operand was also tried in TENSOR MEMORY - umma_tf32_ts, A read from TMEM lanes: numerically identical, but the
+    // issue cost of the 32 small MMAs stayed at ~56 cycles each, and a 512-column allocation made co-resident GEMM CTAs
+    // stall in tcgen05.alloc for the length of a chunk.)  Loads are issued in batches of 8 per thread before the first
+    // store: a load -> round -> store loop serialises on L2 latency.
     for (int base = 0; base < 128 * (h / 4); base += 8 * TC_THREADS) {
         float4 v[8];
 #pragma unroll
@@ -100,16 +144,6 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             }
         }
     }
-    for (int idx = tid; idx < (int)(2 * FW_H_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sH)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) {
-        mbar_init(&mbar_h[0], 1); mbar_init(&mbar_h[1], 1); mbar_init(mbar_mma, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (w == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(tmem_slot)), "n"(32));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    __syncthreads();
     for (int idx = tid; idx < nb * (h / 4); idx += TC_THREADS) {          // h_{-1} (slot 0 of Hs) into buffer 0
         const int m = idx / (h / 4), k4 = idx % (h / 4);
         float4 v = *reinterpret_cast<const float4*>(a.Hs + (size_t)(b0 + m) * h + k4 * 4);
@@ -121,19 +155,20 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t sA_addr = saddr(sA), sH_addr = saddr(sH);
+    const uint32_t sH_addr = saddr(sH);
     cluster_sync_all();                   // all CTAs have initialised buffers / barriers before any remote store
 
     if (w == 8) {
         // ===== MMA issuer: one thread, nothing else on its plate =====
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(128, TROWS, false, false);
-            const uint64_t a0 = umma_smem_desc(sA_addr, 16, 1024, 2);
+            const uint64_t a0 = umma_smem_desc(saddr(sA), 16, 1024, 2);
             const uint64_t b0d = umma_smem_desc(sH_addr, 16, 1024, 2);
             for (int i = 0; i < T; ++i) {
                 const int cur = i & 1;
                 if (i + 1 < T) mbar_expect_tx(&mbar_h[cur ^ 1], FW_H_BYTES);    // arm the buffer this step fills
                 if (i > 0) mbar_wait(&mbar_h[cur], ((i - 1) >> 1) & 1);         // all 8 slices of h_{i-1} have landed
+                PROBE(0);
                 fence_proxy_async();
                 tc_fence_after();
                 const uint64_t bcur = b0d + (uint64_t)((cur * FW_H_BYTES) >> 4);
@@ -144,6 +179,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                         umma_tf32_ss(tmem_base, a0 + (uint64_t)((kb * 16384 + ks * 32) >> 4),
                                      bcur + (uint64_t)((kb * (TROWS * 128) + ks * 32) >> 4), idesc, (kb | ks) ? 1u : 0u);
                 umma_commit_arrive(mbar_mma);
+                PROBE(1);
             }
         }
     } else {
@@ -161,15 +197,17 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         for (int i = 0; i < T; ++i) {
             const int nxt = (i & 1) ^ 1;
             mbar_wait(mbar_mma, i & 1);
+            if (tid == 0) PROBE(2);
             tc_fence_after();
             {
                 float v[8];
-                tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + 8 * bh, v);
+                tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + 8 * bh, v);
                 tc_fence_before();
 #pragma unroll
                 for (int b = 0; b < 8; ++b) xg[(gate * TROWS + 8 * bh + b) * TU + lane] = v[b];
             }
             epi_barrier();
+            if (tid == 0) PROBE(3);
             float4 actv[2]; float cv[2], hv[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -183,28 +221,28 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 actv[j] = make_float4(ga, gi, gf, go); cv[j] = c; hv[j] = hval;
                 if (b < nb) creg[j] = c;
             }
+            if (tid == 0) PROBE(4);
             if (i + 1 < T) {
-                // quad of lanes = 4 consecutive units x 2 batch rows = two 16-byte chunks; lane l sends chunk (l & 1)
-                // to CTAs 4*((l >> 1) & 1) .. +3  (TF32-rounded: this copy is the next step's MMA operand)
-                const int qb = lane & ~3;
-                float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+                // This CTA's 32 units are exactly k-block `rank` of the next step's K-major operand: a contiguous 2 KB block
+                // [16 rows][128 B, 16-byte chunks XOR-ed with row % 8].  Stage it locally (TF32-rounded) and push it to all 8
+                // CTAs with ONE bulk copy each (cp.async.bulk smem -> dsmem, completing bytes on the receiver's mbarrier)
+                // instead of 4 st.async + 8 mapa per thread (measured: the send section was 1340 of a step's 4500 cycles).
+                uint8_t* stg = sStg + nxt * (TROWS * 128);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const float r = rnd_tf32(hv[j]);
-                    float4 t;
-                    t.x = __shfl_sync(0xffffffffu, r, qb + 0);
-                    t.y = __shfl_sync(0xffffffffu, r, qb + 1);
-                    t.z = __shfl_sync(0xffffffffu, r, qb + 2);
-                    t.w = __shfl_sync(0xffffffffu, r, qb + 3);
-                    if ((lane & 1) == j) mine = t;
+                    const int b = 2 * w + j;
+                    *reinterpret_cast<float*>(stg + b * 128 + ((((lane >> 2) ^ (b & 7))) << 4) + ((lane & 3) << 2)) = rnd_tf32(hv[j]);
                 }
-                const int b = 2 * w + (lane & 1);
-                const uint32_t dst = sH_addr + nxt * FW_H_BYTES + kmajor_off(b, TU * rank + 4 * (lane >> 2), TROWS);
-                const uint32_t bar = saddr(&mbar_h[nxt]);
-                const int d0 = 4 * ((lane >> 1) & 1);
-#pragma unroll
-                for (int d = 0; d < 4; ++d) st_async_v4(mapa(dst, d0 + d), mine, mapa(bar, d0 + d));
+                fence_proxy_async();
+                epi_barrier();
+                if (tid < TNC) {
+                    const uint32_t dst = mapa(sH_addr + nxt * FW_H_BYTES + (uint32_t)rank * (TROWS * 128), tid);
+                    const uint32_t bar = mapa(saddr(&mbar_h[nxt]), tid);
+                    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "r"(saddr(stg)), "r"((uint32_t)(TROWS * 128)), "r"(bar) : "memory");
+                }
             }
+            if (tid == 0) PROBE(5);
             // bookkeeping: overlaps the other CTAs' sends and the next step's MMA
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -219,11 +257,13 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     if (i + 1 < T) gx[j] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);
                 }
             }
+            if (tid == 0) PROBE(6);
         }
     }
+#undef PROBE
     tc_fence_before();
     __syncthreads();
-    if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32));
+    if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(FW_TMEM_COLS));
     cluster_sync_all();
 }
 
@@ -233,7 +273,8 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 constexpr uint32_t BW_A_BYTES = 8 * 128 * 128;          // W slice as M-major operand: 8 unit-chunks x 128 gate rows x 128 B
 constexpr uint32_t BW_G_BYTES = 4 * TROWS * 128;        // dG: 4 k-blocks x 16 batch rows x 128 B (K-major)
 constexpr uint32_t BW_R_BYTES = TNC * TU * TROWS * 4;   // one reduce buffer [src][unit][batch]
-constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + 64 + 1024;
+constexpr uint32_t BW_STG_BYTES = 2 * TNC * TU * TROWS * 4;   // [2][owner] staging of the partial dh blocks (2 KB per owner)
+constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES + 64 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed) {
@@ -246,7 +287,8 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     uint8_t* sA = sm;                                   // A[m = unit][k = gate row p] (M-major, SWIZZLE_128B_BASE32B)
     uint8_t* sG = sm + BW_A_BYTES;                      // B[n = batch][k = gate row p] (K-major, SWIZZLE_128B)
     float* red = reinterpret_cast<float*>(sm + BW_A_BYTES + BW_G_BYTES);     // [2][src][unit][batch]
-    uint64_t* mbar_r = reinterpret_cast<uint64_t*>(sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES);   // [2]
+    uint8_t* sStg = sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES;
+    uint64_t* mbar_r = reinterpret_cast<uint64_t*>(sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES);   // [2]
     uint64_t* mbar_mma = mbar_r + 2;
     uint64_t* mbar_g = mbar_r + 3;                      // dG operand written by all 256 epilogue threads
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_r + 4);
@@ -398,11 +440,20 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (w >> 2) * TROWS, v);
                 tc_fence_before();
+                // warp w holds exactly the block owner CTA w needs ([32 units][16 batch] partials = 2 KB contiguous at the
+                // receiver): stage it and push it with ONE bulk copy per warp instead of 4 st.async per lane
                 const int owner = (w >> 2) * 4 + (w & 3);
-                const uint32_t dst = mapa(red_addr + (uint32_t)(((buf * TNC + rank) * TU + lane) * TROWS * 4), owner);
-                const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
+                float* stg = reinterpret_cast<float*>(sStg + (size_t)(buf * TNC + owner) * (TU * TROWS * 4)) + lane * TROWS;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) st_async_v4(dst + 16 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), bar);
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stg + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t dst = mapa(red_addr + (uint32_t)(((buf * TNC + rank) * TU) * TROWS * 4), owner);
+                    const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
+                    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "r"(saddr(stg)), "r"((uint32_t)(TU * TROWS * 4)), "r"(bar) : "memory");
+                }
             }
         }
         // gradients w.r.t. the initial state (slot 0): the carry into the previous chunk of a longer sequence
@@ -447,10 +498,25 @@ static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, cons
     ++g_kernel_launches;
     return 0;
 }
+static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B, float drop, unsigned long long seed) {
+    AST_CUDA_OK(cudaFuncSetAttribute(lstm_seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nchains * TNC);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TNC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_seq_fwd_tc_kernel, ch, T, B, drop, seed, g_lstm_prof));
+    ++g_kernel_launches;
+    return 0;
+}
 
 // `ch` already holds 16-row chains (lstm_seq.cu::expand_chains).  Preconditions checked by the caller: h == 256.
 int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {
-    return launch_tc(lstm_seq_fwd_tc_kernel, st, nchains, FW_SMEM, ch, T, B, drop, seed);
+    return launch_tc_fwd(st, nchains, FW_SMEM, ch, T, B, drop, seed);
 }
 int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {
     return launch_tc(lstm_seq_bwd_tc_kernel, st, nchains, BW_SMEM, ch, T, B, drop, seed);

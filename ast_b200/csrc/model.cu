@@ -1283,6 +1283,8 @@ int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, 
                     : lstm_seq_fwd(S_(stream), ch, 1, T, B, h, 0.f, 0, exact != 0);
 }
 
+int ast_lstm_probe(unsigned long long* dev_buf) { lstm_tc_set_prof(dev_buf); return 0; }
+
 // Stage timing (option stage_timing = 1): names and milliseconds between consecutive marks of the last forward_loss + backward.
 // Synchronises the device.  Returns the number of intervals written (<= cap).
 int ast_stage_times(ast_model* m, float* ms, char* names, int name_stride, int cap) {
