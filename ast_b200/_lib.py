@@ -50,6 +50,9 @@ SIGNATURES = {
     "ast_get_enc_states": (_I, [_P, _P, _P]),
     "ast_forward_loss": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _F, _P, _P]),
     "ast_backward": (_I, [_P, _P]),
+    "ast_grad_bucket_count": (_I, [_P]),
+    "ast_grad_bucket_range": (_I, [_P, _I, C.POINTER(_LL), C.POINTER(_LL)]),
+    "ast_grad_bucket_wait": (_I, [_P, _I, _P]),
     "ast_get_step_argmax": (_I, [_P, _P, _P]),
     "ast_opt_step": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, C.POINTER(_I), _I, _P]),
     "ast_last_grad_norm": (C.c_double, [_P, _P]),

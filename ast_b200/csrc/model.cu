@@ -86,7 +86,7 @@ struct ast_model {
     float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
-    cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr; int overlap = 1; bool tr_pending = false;
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
@@ -748,6 +748,9 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
         AST_TRY(colsum(sw, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
+    // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
+    // starts its all-reduce now (ast_grad_bucket_wait) and overlaps it with the encoder + CNN backward below
+    AST_CUDA_OK(cudaEventRecord(m->ev_bucket[0], sw));
     // ---- encoder BPTT, top-down; both directions per launch.  Same chunked layer wavefront as the forward pass, in
     // reverse time: layer l works on chunk c while layer l+1 is already on chunk c-1; the (dh, dc) carry between the
     // chunks of one layer goes through dh_carry / dc_carry (the kernels' dh0/dc0 outputs).
@@ -839,6 +842,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, evg[l * nch + 0], 0));     // join every GEMM stream
         for (int l = 0; l < NL - 1; ++l) AST_CUDA_OK(cudaStreamWaitEvent(st, ev[l * nch + 0], 0));
     }
+    AST_CUDA_OK(cudaEventRecord(m->ev_bucket[1], sw));      // bucket 1: every encoder weight gradient is enqueued on sw by now
     m->mark("bwd:encoder_done", st);
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
@@ -860,6 +864,8 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_join, 0));
     }
     m->mark("bwd:side_stream_joined", st);
+    AST_CUDA_OK(cudaEventRecord(m->ev_bucket[2], st));      // bucket 2: CNN gradients (and everything else)
+    m->buckets_valid = true;
     m->have_fwd = false;
     return 0;
 }
@@ -931,6 +937,7 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_tr, cudaEventDisableTiming);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_bucket[i], cudaEventDisableTiming);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->lay[i], cudaStreamNonBlocking);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->layg[i], cudaStreamNonBlocking);
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
@@ -946,6 +953,7 @@ int ast_destroy(ast_model* m) {
     for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->ev_tr) cudaEventDestroy(m->ev_tr);
+    for (int i = 0; i < 3; ++i) if (m->ev_bucket[i]) cudaEventDestroy(m->ev_bucket[i]);
     if (m->side) cudaStreamDestroy(m->side);
     for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
     for (int i = 0; i < MAXL; ++i) if (m->layg[i]) cudaStreamDestroy(m->layg[i]);
@@ -1033,6 +1041,31 @@ int ast_forward_loss(ast_model* m, const float* X, const int* y, int B, int T, i
     return forward_loss_impl(m, X, y, B, T, L, use_true, noise, noise_sigma, loss_out, S_(stream));
 }
 int ast_backward(ast_model* m, void* stream) { return backward_impl(m, S_(stream)); }
+
+// Gradient buckets for a data-parallel caller, in the order backward completes them.  The flat buffer is laid out
+// CNN | encoder | decoder (build_param_table), so each bucket is one contiguous range.
+static void bucket_bounds(const ast_model* m, long long* b) {
+    long long enc0 = m->nfloats, dec0 = m->nfloats;
+    for (const auto& pi : m->pinfo) {
+        if (pi.name == "L0_enc/upward/W") enc0 = (long long)pi.off;
+        if (pi.name == "attn_Wa/W") dec0 = (long long)pi.off;
+    }
+    b[0] = 0; b[1] = enc0; b[2] = dec0; b[3] = m->nfloats;
+}
+int ast_grad_bucket_count(const ast_model*) { return 3; }
+int ast_grad_bucket_range(const ast_model* m, int bucket, long long* offset, long long* count) {
+    AST_CHECK(bucket >= 0 && bucket < 3 && offset && count, "ast_grad_bucket_range: bad argument");
+    long long b[4]; bucket_bounds(m, b);
+    const int r = 2 - bucket;            // bucket 0 = decoder (last range), 1 = encoder, 2 = CNN
+    *offset = b[r]; *count = b[r + 1] - b[r];
+    return 0;
+}
+int ast_grad_bucket_wait(ast_model* m, int bucket, void* stream) {
+    AST_CHECK(bucket >= 0 && bucket < 3, "ast_grad_bucket_wait: bucket %d out of range", bucket);
+    AST_CHECK(m->buckets_valid, "ast_grad_bucket_wait: no ast_backward has been enqueued");
+    AST_CUDA_OK(cudaStreamWaitEvent(S_(stream), m->ev_bucket[bucket], 0));
+    return 0;
+}
 int ast_get_step_argmax(ast_model* m, int* out, void* stream) {
     AST_CHECK(m->L >= 2, "no forward_loss yet");
     AST_CUDA_OK(cudaMemcpyAsync(out, m->argmax_steps, sizeof(int) * (size_t)(m->L - 1) * m->B, cudaMemcpyDeviceToDevice, S_(stream)));

@@ -208,6 +208,19 @@ class Engine:
     def backward(self):
         check(self.lib.ast_backward(self.h, self.stream()), "ast_backward")
 
+    def grad_buckets(self):
+        """[(offset, count)] in floats: contiguous ranges of ``grads`` in the order backward completes them."""
+        out = []
+        for i in range(self.lib.ast_grad_bucket_count(self.h)):
+            off, cnt = C.c_longlong(), C.c_longlong()
+            check(self.lib.ast_grad_bucket_range(self.h, i, C.byref(off), C.byref(cnt)), "ast_grad_bucket_range")
+            out.append((off.value, cnt.value))
+        return out
+
+    def grad_bucket_wait(self, bucket, stream):
+        """Make ``stream`` (torch.cuda.Stream) wait until bucket ``bucket`` of the last enqueued backward is final."""
+        check(self.lib.ast_grad_bucket_wait(self.h, int(bucket), C.c_void_p(stream.cuda_stream)), "ast_grad_bucket_wait")
+
     def step_argmax(self):
         out = torch.empty(self.L - 1, self.B, dtype=torch.int32, device=self.device)
         check(self.lib.ast_get_step_argmax(self.h, ptr(out), self.stream()))

@@ -280,7 +280,7 @@ def run_ours(args):
     opt = Adam(alpha=OPT_CFG["lr"]).setup(model)
     opt.add_hook(WeightDecay(OPT_CFG["l2"]))
     opt.add_hook(GradientClipping(OPT_CFG["grad_clip"]))
-    adist.GradAllReduce(e, opt, world)
+    adist.GradAllReduce(e, opt, world, overlap=not args.no_allreduce_overlap)
     packer = DevicePacker(dev)
     train_config.train = True
     lib = _lib.load()
@@ -377,7 +377,7 @@ def run_ours(args):
         "config": {"workload": "es_en_20h bucketed training steps (configs[1]): B=32/GPU, Fisher-shaped lengths (20x80-frame buckets, "
                                "truncated at 1680), D=40 fbank, V=1098, 2xCNN + 2x3-layer LSTM encoder + 3-layer attention decoder; "
                                "fwd + bwd + WD/clip/AMSGrad; dropout .3/.3, speech_noise .25, teach_ratio .8, zero_input .1",
-                   "global_batch": BATCH * world, "parallelism": f"dp{world}", "l2_flush_between_steps": True,
+                   "global_batch": BATCH * world, "parallelism": f"dp{world}", "grad_allreduce": ("3 buckets overlapped with backward" if not args.no_allreduce_overlap else "3 buckets after backward") if world > 1 else "none", "l2_flush_between_steps": True,
                    "frames_counted": "true (unpadded, post-truncation) input frames",
                    "wall_ms_per_step_incl_flush": 1e3 * t_wall / K},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K},
@@ -418,6 +418,8 @@ def main():
                          "tolerances); f32: fp32-faithful everywhere (the decode / hypothesis-identity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true")
+    ap.add_argument("--no-allreduce-overlap", action="store_true",
+                    help="N>1: all-reduce the gradient buckets on the compute stream after backward instead of overlapped with it")
     args = ap.parse_args()
     # keep stdout clean for the ONE JSON line: library banners (e.g. NCCL's version line) go to stderr
     global _REAL_STDOUT

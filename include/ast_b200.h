@@ -76,6 +76,13 @@ int ast_forward_loss(ast_model* m, const float* X, const int* y, int B, int T, i
                      void* stream);
 /* loss.backward() (nn.py:181) after cleargrads (:180): fills the bound grads buffer. */
 int ast_backward(ast_model* m, void* stream);
+/* Data-parallel hook (no reference counterpart: the reference is single-GPU).  backward completes the flat
+ * gradient buffer in three contiguous buckets - 0: decoder (attn_Wa .. out), 1: encoder stacks, 2: CNN - and records an
+ * event as each one becomes final.  ast_grad_bucket_wait makes `stream` wait for that event of the LAST enqueued
+ * ast_backward, so a caller can all-reduce bucket 0 while the encoder/CNN backward still runs.  range: in floats. */
+int ast_grad_bucket_count(const ast_model* m);
+int ast_grad_bucket_range(const ast_model* m, int bucket, long long* offset, long long* count);
+int ast_grad_bucket_wait(ast_model* m, int bucket, void* stream);
 /* per-step argmax tokens of the last forward_loss: (L-1, B) int32 */
 int ast_get_step_argmax(ast_model* m, int* out, void* stream);
 

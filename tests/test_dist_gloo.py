@@ -29,9 +29,25 @@ def _worker(rank, world, port, out):
     g = torch.tensor(rng.standard_normal(1000), dtype=torch.float32)
     local = g.clone()
     adist.allreduce_sum_(g)
+    # the bucketed hook (same ranges the library reports on the GPU: CNN | encoder | decoder, reduced decoder-first)
+    class _Opt:
+        grad_scale = 1.0
+        pre_update = None
+
+    class _Eng:
+        grads = torch.tensor(np.random.default_rng(10 + rank).standard_normal(1000), dtype=torch.float32)
+
+        def grad_buckets(self):
+            return [(600, 400), (100, 500), (0, 100)]
+
+    eng, opt = _Eng(), _Opt()
+    blocal = eng.grads.clone()
+    hook = adist.GradAllReduce(eng, opt, world)
+    assert opt.pre_update is hook and opt.grad_scale == 1.0 / world and not hook.overlap
+    hook()
     tmax = adist.max_over_ranks(float(rank + 1), torch.device("cpu"))
     tsum = adist.sum_over_ranks(float(rank + 1), torch.device("cpu"))
-    torch.save({"plan": plan, "mine": mine, "local": local, "reduced": g, "tmax": tmax, "tsum": tsum}, out + f".{rank}")
+    torch.save({"plan": plan, "mine": mine, "local": local, "reduced": g, "blocal": blocal, "breduced": eng.grads, "tmax": tmax, "tsum": tsum}, out + f".{rank}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,4 +66,6 @@ def test_dp_host_logic_world2(tmp_path):
         assert len(s0) >= 1 and len(s1) >= 1
     want = res[0]["local"] + res[1]["local"]
     assert torch.allclose(res[0]["reduced"], want) and torch.allclose(res[1]["reduced"], want)
+    bwant = res[0]["blocal"] + res[1]["blocal"]
+    assert torch.allclose(res[0]["breduced"], bwant) and torch.allclose(res[1]["breduced"], bwant)
     assert res[0]["tmax"] == 2.0 and res[1]["tsum"] == 3.0

@@ -317,6 +317,41 @@ def test_encoder_wavefront_and_side_stream_match_serial(dev, exact):
             assert _relerr(o[2][off:off + n], out[0][2][off:off + n]) <= tol, k
 
 
+@pytest.mark.parametrize("overlap", [1, 0])
+def test_gradient_buckets_are_final_at_their_events(dev, overlap):
+    """Data-parallel hook (ast_grad_bucket_*): the three buckets tile the flat gradient buffer in backward order
+    (decoder, encoder, CNN), and a stream that waits on a bucket's event sees that bucket's FINAL gradients - a copy
+    taken on a side stream right after the event equals the gradients after the whole backward has drained, while the
+    encoder / CNN backward is still in flight."""
+    cfg = O.default_model_cfg(vocab=200, dropout=(0.3, 0.3, 0.0))
+    P = _perturbed(cfg, 40, 81)
+    X, y, _ = O.synth_batch(32, 640, 40, 200, 10, 24, seed=82, Tmin=600)
+    e = _engine(cfg, 40, P)
+    e.set_option("exact", 0); e.set_option("tc_gemm", 1); e.set_option("overlap", overlap)
+    b = e.grad_buckets()
+    assert len(b) == 3 and sorted(b)[0][0] == 0 and sum(c for _, c in b) == e.grads.numel()
+    srt = sorted(b)
+    assert all(a[0] + a[1] == n[0] for a, n in zip(srt, srt[1:]))
+    names = {i: [k for k, (_, off, _s) in e.info.items() if o <= off < o + c] for i, (o, c) in enumerate(b)}
+    assert "out/W" in names[0] and "L0_dec/upward/W" in names[0] and "embed_dec/W" in names[0] and "attn_Wa/W" in names[0]
+    assert "L0_enc/upward/W" in names[1] and "L2_rev_enc/lateral/W" in names[1]
+    assert "CNN_0/W" in names[2] and "CNN_1_bn/beta" in names[2]
+    side = torch.cuda.Stream(device=e.device)
+    for it in range(3):
+        e.grads.fill_(float("nan"))
+        float(e.forward_loss(X, y, noise_sigma=0.25))
+        e.backward()
+        snaps = []
+        with torch.cuda.stream(side):
+            for i, (o, c) in enumerate(b):
+                e.grad_bucket_wait(i, side)
+                snaps.append(e.grads[o:o + c].clone())
+        torch.cuda.synchronize()
+        for i, (o, c) in enumerate(b):
+            assert torch.isfinite(snaps[i]).all(), i
+            assert torch.equal(snaps[i], e.grads[o:o + c]), i
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_golden_fixtures(dev, name):
     cfg, D, P, z = load_case(name)
