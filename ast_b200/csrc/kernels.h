@@ -65,6 +65,13 @@ struct LstmChain {
     int b0, nb;          // batch rows [b0, b0+nb) of the B-row buffers handled by this chain (nb = 0: all B rows)
 };
 struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
+// Chunk gating for a recurrence kernel that covers a whole sequence while its inputs are still being produced (the
+// persistent encoder wavefront, model.cu): steps are numbered in PROCESSING order k (forward: k = t, backward: k = T-1-t).
+//   ready: device word = number of leading steps whose inputs (forward: x-projection rows of G; backward: dout rows) have been
+//          written; the kernel spins (ld.acquire.sys) before it first touches step k until *ready > k.  null: everything is ready.
+//   done : per-chunk counters; every CTA adds 1 to done[k / chunk] (after a fence) once its outputs of that chunk are in
+//          global memory, so a stream can wait (cuStreamWaitValue32 GEQ #CTAs) and launch the consumer GEMM.  null: no signal.
+struct LstmGate { const unsigned* ready; unsigned* done; int chunk; };
 int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact);
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
@@ -73,6 +80,14 @@ int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
 int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);
 void lstm_tc_set_prof(unsigned long long* p);   // diagnostics: device buffer of >= 128 u64 for the forward kernel's cycle probe
 int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);
+// gated whole-sequence launches (TF32 tcgen05 kernels only: h == 256, !exact); *ncta = CTAs that will arrive on each done counter
+bool lstm_seq_gated_supported(int h, bool exact);
+int lstm_seq_fwd_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop, unsigned long long seed,
+                       const LstmGate& gate, int* ncta);
+int lstm_seq_bwd_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop, unsigned long long seed,
+                       const LstmGate& gate, int* ncta);
+int lstm_seq_fwd_tc_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed, const LstmGate& gate);
+int lstm_seq_bwd_tc_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed, const LstmGate& gate);
 
 // ---- decoder step kernels ------------------------------------------------------------------------
 enum { EPI_NONE = 0, EPI_TANH = 1, EPI_LSTM = 2, EPI_TANHBWD = 3, EPI_CELLBWD = 4 };

@@ -437,6 +437,24 @@ int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
                  : launch_cluster(lstm_seq_fwd_kernel<false>, st, n, smem, ex, T, B, h, drop, seed);
 }
 
+bool lstm_seq_gated_supported(int h, bool exact) { return !exact && h == 256; }
+int lstm_seq_fwd_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop, unsigned long long seed,
+                       const LstmGate& gate, int* ncta) {
+    AST_CHECK(lstm_seq_gated_supported(h, false), "lstm_seq_fwd_gated: only the tcgen05 recurrence (h == 256) can be gated");
+    LstmChains ex{}; int n = 0;
+    AST_TRY(expand_chains("lstm_seq_fwd_gated", ch, nchains, T, B, h, ex, n));
+    if (ncta) *ncta = n * 8;
+    return lstm_seq_fwd_tc_gated(st, ex, n, T, B, drop, seed, gate);
+}
+int lstm_seq_bwd_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop, unsigned long long seed,
+                       const LstmGate& gate, int* ncta) {
+    AST_CHECK(lstm_seq_gated_supported(h, false), "lstm_seq_bwd_gated: only the tcgen05 recurrence (h == 256) can be gated");
+    LstmChains ex{}; int n = 0;
+    AST_TRY(expand_chains("lstm_seq_bwd_gated", ch, nchains, T, B, h, ex, n));
+    if (ncta) *ncta = n * 8;
+    return lstm_seq_bwd_tc_gated(st, ex, n, T, B, drop, seed, gate);
+}
+
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact) {
     LstmChains ex{}; int n = 0;

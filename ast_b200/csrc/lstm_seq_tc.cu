@@ -68,6 +68,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// chunk gating (kernels.h::LstmGate): spin until the producer has published more than k ready steps
+__device__ __forceinline__ void gate_wait(const unsigned* ready, unsigned& cached, unsigned k) {
+    while (cached <= k) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cached) : "l"(ready) : "memory");
+}
+// all epilogue threads: this CTA's global stores of the chunk are visible device-wide, then one arrival on the chunk's counter
+__device__ __forceinline__ void gate_signal(unsigned* counter, int tid) {
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory");
+    if (tid == 0) { __threadfence(); atomicAdd(counter, 1u); }
+}
+
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B operand made of k-blocks of 32 floats:
 // [kb][rows][128 B], 16-byte chunks XOR-ed with (row % 8)
 __device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows_per_block) {
@@ -87,7 +98,7 @@ constexpr uint32_t FW_STG_BYTES = 2 * TROWS * 128;      // [2] staging of this C
 constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_BYTES + 64 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, unsigned long long* prof) {
+lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, unsigned long long* prof, LstmGate gt) {
     const bool probe = prof != nullptr && blockIdx.x == 0;
 #define PROBE(slot) do { if (probe && i >= 8 && i < 24) prof[(i - 8) * 8 + (slot)] = clock64(); } while (0)
     const int rank = (int)cluster_rank();
@@ -187,11 +198,13 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         const int ju = TU * rank + lane;
         float creg[2];
         float4 gx[2];
+        unsigned ready_seen = gt.ready ? 0u : 0xffffffffu;
+        gate_wait(gt.ready, ready_seen, 0u);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int b = 2 * w + j;
             creg[j] = b < nb ? a.Cs[(size_t)(b0 + b) * h + ju] : 0.f;
-            gx[j] = b < nb ? *reinterpret_cast<const float4*>(a.G + (size_t)(b0 + b) * H4 + 4 * ju) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gx[j] = b < nb ? __ldcg(reinterpret_cast<const float4*>(a.G + (size_t)(b0 + b) * H4 + 4 * ju)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const int gate = w & 3, bh = w >> 2;          // TMEM quadrant = gate; this warp reads batch columns 8*bh..+7
         for (int i = 0; i < T; ++i) {
@@ -244,6 +257,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             }
             if (tid == 0) PROBE(5);
             // bookkeeping: overlaps the other CTAs' sends and the next step's MMA
+            if (i + 1 < T) gate_wait(gt.ready, ready_seen, (unsigned)(i + 1));      // x-projection of step i+1 published?
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int b = 2 * w + j;
@@ -254,9 +268,10 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     a.Hs[(r + B) * h + ju] = hv[j];
                     const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
                     a.out[(long long)i * a.out_si + (long long)(b0 + b) * a.out_sb + ju] = hv[j] * dm;
-                    if (i + 1 < T) gx[j] = *reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju);
+                    if (i + 1 < T) gx[j] = __ldcg(reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju));
                 }
             }
+            if (gt.done && ((i + 1) % gt.chunk == 0 || i + 1 == T)) gate_signal(gt.done + i / gt.chunk, tid);
             if (tid == 0) PROBE(6);
         }
     }
@@ -277,7 +292,7 @@ constexpr uint32_t BW_STG_BYTES = 2 * TNC * TU * TROWS * 4;   // [2][owner] stag
 constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES + 64 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed) {
+lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, LstmGate gt) {
     const int rank = (int)cluster_rank();
     const LstmChain a = ch.c[blockIdx.x / TNC];
     constexpr int h = TH, H4 = 4 * TH;
@@ -361,6 +376,8 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         // ===== epilogue / elementwise: pair e -> batch row m = idx % 16, unit ul = idx / 16 =====
         float dc[2];
         float4 p_act[2]; float p_c[2], p_cp[2], p_dout[2];
+        unsigned ready_seen = gt.ready ? 0u : 0xffffffffu;
+        gate_wait(gt.ready, ready_seen, 0u);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int idx = tid + e * TC_EPI;
@@ -371,7 +388,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 const size_t r = (size_t)(T - 1) * B + b0 + m;
                 p_act[e] = *reinterpret_cast<const float4*>(a.G + r * H4 + 4 * ju);
                 p_c[e] = a.Cs[(r + B) * h + ju]; p_cp[e] = a.Cs[r * h + ju];
-                p_dout[e] = a.dout[(long long)(T - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
+                p_dout[e] = __ldcg(a.dout + (long long)(T - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju);
             } else { p_act[e] = make_float4(0.f, 0.f, 0.f, 0.f); p_c[e] = p_cp[e] = p_dout[e] = 0.f; }
         }
         int step = 0;
@@ -418,6 +435,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 mbar_arrive(mbar_g);              // hand the operand to the issuer warp
             }
             // 2. bookkeeping while the tensor core works: write dG_t in place, prefetch step i-1
+            if (i > 0) gate_wait(gt.ready, ready_seen, (unsigned)(T - i));        // dout of step i-1 (processing index T-i) published?
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int idx = tid + e * TC_EPI;
@@ -429,10 +447,11 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                         const size_t rp = r - B;
                         p_act[e] = *reinterpret_cast<const float4*>(a.G + rp * H4 + 4 * ju);
                         p_c[e] = p_cp[e]; p_cp[e] = a.Cs[rp * h + ju];
-                        p_dout[e] = a.dout[(long long)(i - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju];
+                        p_dout[e] = __ldcg(a.dout + (long long)(i - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju);
                     }
                 }
             }
+            if (gt.done && ((T - i) % gt.chunk == 0 || i == 0)) gate_signal(gt.done + (T - 1 - i) / gt.chunk, tid);
             if (send) {
                 // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
                 mbar_wait(mbar_mma, step & 1);
@@ -483,7 +502,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 
 template <class KernT>
 static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B,
-                     float drop, unsigned long long seed) {
+                     float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, nullptr, 1}) {
     AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);
@@ -494,11 +513,12 @@ static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, cons
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = TNC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ch, T, B, drop, seed));
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ch, T, B, drop, seed, gate));
     ++g_kernel_launches;
     return 0;
 }
-static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B, float drop, unsigned long long seed) {
+static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B, float drop, unsigned long long seed,
+                         LstmGate gate = LstmGate{nullptr, nullptr, 1}) {
     AST_CUDA_OK(cudaFuncSetAttribute(lstm_seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);
@@ -509,7 +529,7 @@ static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmCh
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = TNC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_seq_fwd_tc_kernel, ch, T, B, drop, seed, g_lstm_prof));
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_seq_fwd_tc_kernel, ch, T, B, drop, seed, g_lstm_prof, gate));
     ++g_kernel_launches;
     return 0;
 }
@@ -520,6 +540,14 @@ int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, i
 }
 int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {
     return launch_tc(lstm_seq_bwd_tc_kernel, st, nchains, BW_SMEM, ch, T, B, drop, seed);
+}
+int lstm_seq_fwd_tc_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed, const LstmGate& gate) {
+    AST_CHECK(gate.chunk >= 1, "lstm_seq_fwd_tc_gated: chunk must be >= 1");
+    return launch_tc_fwd(st, nchains, FW_SMEM, ch, T, B, drop, seed, gate);
+}
+int lstm_seq_bwd_tc_gated(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed, const LstmGate& gate) {
+    AST_CHECK(gate.chunk >= 1, "lstm_seq_bwd_tc_gated: chunk must be >= 1");
+    return launch_tc(lstm_seq_bwd_tc_kernel, st, nchains, BW_SMEM, ch, T, B, drop, seed, gate);
 }
 
 }  // namespace ast

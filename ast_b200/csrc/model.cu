@@ -4,6 +4,8 @@
 // only enqueue kernels; nothing in the training step synchronises with the host.
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
+#include <cuda.h>
 #include <string>
 #include <vector>
 #include "../../include/ast_b200.h"
@@ -21,6 +23,8 @@ unsigned long long g_kernel_launches = 0;
 
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
+
+constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 
 struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
 
@@ -89,6 +93,7 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
+    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0;     // persistent wavefront: ready[MAXL] then done[MAXL][MAXQ]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -178,6 +183,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs);
     const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, H = m->H, h = m->h, E = m->E, A = m->A, Vp = m->Vp, R = m->R, NL = m->NL;
     const size_t M0 = (size_t)B * Fp * T1, M1 = (size_t)B * Fp * Rs, TB = (size_t)Tp * B;
+    m->enc_flags = a.get<unsigned>((size_t)MAXL * (1 + MAXQ) + 64);
     const int S = std::max(L - 1, 1);
     const int Bd = std::max(std::max(B, N), 1);
     m->Xn = a.get<float>((size_t)B * T * m->D);
@@ -339,6 +345,36 @@ static int require_ready(ast_model* m, int B, int T, int L, int N, int steps) {
     return 0;
 }
 
+// Stream memory operations (driver API): the persistent encoder wavefront orders GEMM launches against kernels that are
+// still running, which events cannot express.
+// (Entry points through cudaGetDriverEntryPoint: the library must load on a machine without libcuda.so.1.)
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamValue32Fn driver_fn(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<StreamValue32Fn>(p);
+}
+static StreamValue32Fn fn_write32() { static StreamValue32Fn f = driver_fn("cuStreamWriteValue32"); return f; }
+static StreamValue32Fn fn_wait32() { static StreamValue32Fn f = driver_fn("cuStreamWaitValue32"); return f; }
+static int stream_write32(cudaStream_t s, unsigned* addr, unsigned value) {
+    const CUresult r = fn_write32()((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    AST_CHECK(r == CUDA_SUCCESS, "cuStreamWriteValue32 failed (%d)", (int)r);
+    return 0;
+}
+static int stream_wait_geq32(cudaStream_t s, unsigned* addr, unsigned value) {
+    const CUresult r = fn_wait32()((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+    AST_CHECK(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed (%d)", (int)r);
+    return 0;
+}
+// A profiler that serialises kernels (ncu) would deadlock kernels that wait for one another: the same switch that turns the
+// cooperative decoder launch off (tools/ncu_capture.sh) selects the per-chunk launches.
+static bool persist_allowed() {
+    static const bool off = getenv("AST_NO_COOP") != nullptr || getenv("AST_NO_PERSIST") != nullptr ||
+                            getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
+    return !off && fn_write32() && fn_wait32();
+}
+
 // ------------------------------------------------------------------------------------------------
 // encoder forward (seq2seq.py:293-315)
 // ------------------------------------------------------------------------------------------------
@@ -418,7 +454,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         }
         return 0;
     };
-    auto recur = [&](int l, int t0, int tn, cudaStream_t s) -> int {
+    auto fwd_chains = [&](int l, int t0) -> LstmChains {
         LstmChains ch{};
         const size_t r0 = (size_t)t0 * B;
         for (int d = 0; d < 2; ++d) {
@@ -434,10 +470,69 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             cc.drop_stream = 1 + 2 * l + d;
             cc.drop_off = (unsigned)(r0 * h);
         }
-        return lstm_seq_fwd(s, ch, 2, tn, B, h, drop, m->cur_seed, m->exact != 0);
+        return ch;
     };
+    auto recur = [&](int l, int t0, int tn, cudaStream_t s) -> int {
+        return lstm_seq_fwd(s, fwd_chains(l, t0), 2, tn, B, h, drop, m->cur_seed, m->exact != 0);
+    };
+    const int PCH = std::max(4, m->enc_pchunk);
+    const int nq = (Tp + PCH - 1) / PCH;
+    // warm_fwd: CUDA loads a kernel lazily at its first launch, and that load can wait for running kernels to finish - a
+    // first-time launch submitted while the recurrence kernels spin on flags only this host thread can advance would hang.
+    // The first pass of a model (and the first after an option change) therefore runs the per-chunk path, which launches the
+    // same kernels.
+    const bool persist = wave && m->enc_persist && persist_allowed() && lstm_seq_gated_supported(h, m->exact != 0) && Tp >= 48 &&
+                         nq <= MAXQ && m->enc_flags && m->warm_fwd > 0;
     if (!wave) {
         for (int l = 0; l < NL; ++l) { AST_TRY(project(l, 0, Tp, st)); AST_TRY(recur(l, 0, Tp, st)); }
+    } else if (persist) {
+        // PERSISTENT wavefront: one whole-sequence recurrence launch per layer, all three resident at once (96 CTAs); the chunk
+        // hand-offs are device flags instead of kernel boundaries.  layer l's kernel spins until its GEMM stream has published
+        // the x-projection of the steps it is about to touch (`ready`, a step count written with cuStreamWriteValue32 after each
+        // projection GEMM); the GEMM stream of layer l+1 waits (cuStreamWaitValue32) for all CTAs of layer l to have counted
+        // themselves into `done[chunk]`.  Against the per-chunk launches this removes ~17 us of kernel prologue (1 MB of W_h
+        // into shared memory, TMEM allocation, cluster launch) per chunk and lets the chunks shrink: the pipeline fill between
+        // layers is 2 x PCH steps instead of 2 x 24..32.
+        // SUBMISSION ORDER matters: streams can share a hardware queue, and an operation that blocks its queue (a value wait,
+        // or anything ordered after a spinning kernel) must never be submitted ahead of work that kernel needs.  So: kernels
+        // first, then the GEMMs in wavefront order (a valid serial schedule), and only then the joins.
+        unsigned* ready = m->enc_flags;
+        unsigned* done = m->enc_flags + MAXL;
+        cudaEvent_t* ev = m->ev_pool;
+        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ((size_t)MAXL * (1 + MAXQ)), st));
+        AST_CUDA_OK(cudaEventRecord(ev[0], st));
+        for (int l = 0; l < NL; ++l) {
+            if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0));
+        }
+        int ncta = 0;
+        for (int l = 0; l < NL; ++l) {
+            const LstmGate gate{ready + l, l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            AST_TRY(lstm_seq_fwd_gated(l == 0 ? st : m->lay[l], fwd_chains(l, 0), 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
+        }
+        // layer 0 depends on nothing: a small first projection so the recurrence starts at once, then doubling slices (bigger
+        // GEMMs run closer to the tensor-core rate and stay ahead of the recurrence)
+        for (int t0 = 0, sz = PCH; t0 < Tp; sz = std::min(2 * sz, 64)) {
+            const int tn = std::min(sz, Tp - t0);
+            AST_TRY(project(0, t0, tn, m->layg[0]));
+            t0 += tn;
+            AST_TRY(stream_write32(m->layg[0], ready, (unsigned)t0));
+        }
+        for (int q = 0; q < nq; ++q)
+            for (int l = 1; l < NL; ++l) {
+                const int t0 = q * PCH, tn = std::min(PCH, Tp - t0);
+                AST_TRY(stream_wait_geq32(m->layg[l], done + (size_t)(l - 1) * MAXQ + q, (unsigned)ncta));
+                AST_TRY(project(l, t0, tn, m->layg[l]));
+                AST_TRY(stream_write32(m->layg[l], ready + l, (unsigned)(t0 + tn)));
+            }
+        for (int l = 1; l < NL; ++l) {
+            AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
+            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
+        }
+        for (int l = 0; l < NL; ++l) {
+            AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
+            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
+        }
     } else {
         // The projection of (layer l, chunk c) runs on the layer's GEMM stream as soon as its input exists (layer 0: at once;
         // layer l >= 1: when layer l-1 has produced chunk c), i.e. while this layer's recurrence is still on chunk c-1; the
@@ -466,6 +561,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // later parameter write on `st` safe without any host synchronisation
     if (m->tr_pending) { AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_tr, 0)); m->tr_pending = false; }
     m->have_fwd = false;
+    ++m->warm_fwd;
     return 0;
 }
 
@@ -757,10 +853,8 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
     const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
-    auto bwd_chunk = [&](int l, int ci, cudaStream_t s) -> int {
-        const int t0 = ci * CH, tn = std::min(CH, Tp - t0);
+    auto bwd_chains = [&](int l, int t0, bool last_in_time, bool carry_out) -> LstmChains {
         const size_t r0 = (size_t)t0 * B;
-        const bool last_in_time = (ci == nch - 1);
         LstmChains ch{};
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
@@ -779,14 +873,17 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                 cc.dh_fin = m->dh_carry[l][d]; cc.ld_dh_fin = h;
                 cc.dc_fin = m->dc_carry[l][d]; cc.ld_dc_fin = h;
             }
-            if (ci > 0) { cc.dh0 = m->dh_carry[l][d]; cc.dc0 = m->dc_carry[l][d]; }
+            if (carry_out) { cc.dh0 = m->dh_carry[l][d]; cc.dc0 = m->dc_carry[l][d]; }
             cc.drop_stream = 1 + 2 * l + d;
             cc.drop_off = (unsigned)(r0 * h);
         }
-        return lstm_seq_bwd(s, ch, 2, tn, B, h, dr, m->cur_seed, ex);
+        return ch;
     };
-    auto bwd_dx = [&](int l, int ci, cudaStream_t s) -> int {   // dx = dG . W_up for this chunk's rows (feeds the layer below)
+    auto bwd_chunk = [&](int l, int ci, cudaStream_t s) -> int {
         const int t0 = ci * CH, tn = std::min(CH, Tp - t0);
+        return lstm_seq_bwd(s, bwd_chains(l, t0, ci == nch - 1, ci > 0), 2, tn, B, h, dr, m->cur_seed, ex);
+    };
+    auto bwd_dx_rows = [&](int l, int t0, int tn, cudaStream_t s) -> int {   // dx = dG . W_up for rows of steps [t0, t0+tn) (feeds the layer below)
         const size_t r0 = (size_t)t0 * B;
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
@@ -797,6 +894,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         }
         return 0;
     };
+    auto bwd_dx = [&](int l, int ci, cudaStream_t s) -> int { return bwd_dx_rows(l, ci * CH, std::min(CH, Tp - ci * CH), s); };
     auto enc_wgrads = [&](int l) -> int {
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
@@ -808,11 +906,56 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         }
         return 0;
     };
+    const int PCH = std::max(4, m->enc_pchunk);
+    const int nq = (Tp + PCH - 1) / PCH;
+    const bool persist = wave && m->enc_persist && persist_allowed() && lstm_seq_gated_supported(h, ex) && Tp >= 48 && nq <= MAXQ &&
+                         m->enc_flags && m->warm_bwd > 0;
     if (!wave) {
         for (int l = NL - 1; l >= 0; --l) {
             AST_TRY(bwd_chunk(l, 0, st));
             AST_TRY(bwd_dx(l, 0, st));
             AST_TRY(fork());
+            AST_TRY(enc_wgrads(l));
+        }
+    } else if (persist) {
+        // persistent wavefront in reverse time (see encode_impl): one whole-sequence launch per layer, chunks counted from the
+        // END of the sequence (processing order).  `ready[l]` = steps of dout published for layer l (written after layer l+1's dx
+        // GEMM of the chunk), `done[l][q]` = CTAs of layer l that have written dG of chunk q.  Submission order: kernels, GEMMs
+        // in wavefront order, joins last.
+        unsigned* ready = m->enc_flags;
+        unsigned* done = m->enc_flags + MAXL;
+        cudaEvent_t* ev = m->ev_pool;
+        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ((size_t)MAXL * (1 + MAXQ)), st));
+        AST_CUDA_OK(cudaEventRecord(ev[0], st));
+        for (int l = 0; l < NL; ++l) {
+            if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0));
+        }
+        int ncta = 0;
+        for (int l = NL - 1; l >= 0; --l) {
+            const LstmGate gate{l < NL - 1 ? ready + l : nullptr, done + (size_t)l * MAXQ, PCH};
+            AST_TRY(lstm_seq_bwd_gated(l == NL - 1 ? st : m->lay[l], bwd_chains(l, 0, true, false), 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
+        }
+        for (int q = 0; q < nq; ++q)
+            for (int l = NL - 1; l >= 0; --l) {
+                const int t_hi = Tp - q * PCH, t_lo = std::max(t_hi - PCH, 0);
+                AST_TRY(stream_wait_geq32(m->layg[l], done + (size_t)l * MAXQ + q, (unsigned)ncta));
+                AST_TRY(bwd_dx_rows(l, t_lo, t_hi - t_lo, m->layg[l]));
+                if (l > 0) AST_TRY(stream_write32(m->layg[l], ready + (l - 1), (unsigned)(Tp - t_lo)));
+            }
+        for (int l = NL - 1; l >= 0; --l) {    // joins: recurrence kernels, GEMM streams; weight gradients once a layer's dG is complete
+            if (l < NL - 1) {
+                AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
+                AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
+            }
+            AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
+            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
+        }
+        for (int l = NL - 1; l >= 0; --l) {
+            if (sw != st) {
+                if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + l], 0));
+                else { AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL], st)); AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + 2 * MAXL], 0)); }
+            }
             AST_TRY(enc_wgrads(l));
         }
     } else {
@@ -866,6 +1009,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     m->mark("bwd:side_stream_joined", st);
     AST_CUDA_OK(cudaEventRecord(m->ev_bucket[2], st));      // bucket 2: CNN gradients (and everything else)
     m->buckets_valid = true;
+    ++m->warm_bwd;
     m->have_fwd = false;
     return 0;
 }
@@ -999,6 +1143,7 @@ int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, in
 }
 
 int ast_set_option(ast_model* m, const char* key, double value) {
+    if (strcmp(key, "seed") && strncmp(key, "enc_", 4) && strcmp(key, "stage_timing")) m->warm_fwd = m->warm_bwd = 0;   // other kernels may run now
     if (!strcmp(key, "exact")) m->exact = value != 0;
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
     else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
@@ -1010,6 +1155,8 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "stage_timing")) m->stage_timing = value != 0;
     else if (!strcmp(key, "conv3x")) m->conv3x = value != 0;
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
+    else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
+    else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
@@ -1356,6 +1503,7 @@ int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_fl
     else if (s == "ht") { src = m->ht; n = (size_t)(m->L - 1) * B * m->A; }
     else if (s == "row_loss") { src = m->row_loss; n = (size_t)(m->L - 1) * B; }
     else if (s == "W1p") { src = m->W1p; n = (size_t)m->C1 * m->K1; }
+    else if (s == "enc_flags") { src = reinterpret_cast<const float*>(m->enc_flags); n = (size_t)MAXL * (1 + MAXQ); }
     else if (s == "dec_prof") { src = reinterpret_cast<const float*>(m->dec_prof); n = 2 * 2 * 4096; }
     else if (s.size() == 4 && (s[0] == 'G' || s[0] == 'H' || s[0] == 'C' || s[0] == 'O') && s[1] == '_') {
         const int l = s[2] - '0', d = s[3] - '0';

@@ -276,6 +276,9 @@ def run_ours(args):
     e = model._engine
     e.set_option("exact", 0 if args.precision == "tf32" else 1)
     e.set_option("tc_gemm", 1 if args.precision == "tf32" else 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        e.set_option(k, float(v))
     adist.broadcast_params_(e)
     opt = Adam(alpha=OPT_CFG["lr"]).setup(model)
     opt.add_hook(WeightDecay(OPT_CFG["l2"]))
@@ -418,6 +421,7 @@ def main():
                          "tolerances); f32: fp32-faithful everywhere (the decode / hypothesis-identity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable; experiments), e.g. --opt enc_pchunk=8")
     ap.add_argument("--no-allreduce-overlap", action="store_true",
                     help="N>1: all-reduce the gradient buckets on the compute stream after backward instead of overlapped with it")
     args = ap.parse_args()

@@ -295,17 +295,28 @@ def test_encoder_wavefront_and_side_stream_match_serial(dev, exact):
     cfg = O.default_model_cfg(vocab=200, dropout=(0.3, 0.3, 0.0))
     P = _perturbed(cfg, 40, 71)
     X, y, _ = O.synth_batch(21, 300, 40, 200, 4, 9, seed=72, Tmin=260)       # T' = 75: chunks of 16 -> 5 chunks, ragged tail
-    out = []
-    for overlap, chunk in ((0, 0), (1, 16), (1, 7)):
+    out, launches = [], []
+    # (overlap, chunk, persistent wavefront, its chunk): the persistent variant (one gated whole-sequence launch per layer,
+    # device flags instead of kernel boundaries; TF32 mode only) must reproduce the same bits, ragged last chunk included
+    for overlap, chunk, persist, pchunk in ((0, 0, 0, 16), (1, 16, 0, 16), (1, 7, 0, 16), (1, 16, 1, 8), (1, 16, 1, 5), (1, 16, 1, 16)):
         e = _engine(cfg, 40, P)
         e.set_option("exact", exact); e.set_option("tc_gemm", 0 if exact else 1)
         e.set_option("overlap", overlap); e.set_option("enc_chunk", chunk)
+        e.set_option("enc_persist", persist); e.set_option("enc_pchunk", pchunk)
+        # the persistent wavefront only engages once a model has completed one pass (lazy kernel loading must not happen
+        # while kernels wait for one another): a throw-away step first, then the seed (and its step counter) again
+        float(e.forward_loss(X, y, noise_sigma=0.25)); e.backward()
+        from ast_b200 import _lib
+        _lib.load().ast_launch_count(1)
         e.set_option("seed", 9)
         loss = float(e.forward_loss(X, y, noise_sigma=0.25))
         enc = e.enc_states().cpu().numpy().copy()
         e.backward()
         torch.cuda.synchronize()
         out.append((loss, enc, e.grads.cpu().numpy().copy()))
+        launches.append(_lib.load().ast_launch_count(1))
+    if not exact:        # the persistent variant really ran: 3 recurrence launches per pass instead of 3 per chunk
+        assert launches[5] < launches[1] - 20, launches
     for o in out[1:]:
         assert o[0] == out[0][0]
         assert np.array_equal(o[1], out[0][1])
