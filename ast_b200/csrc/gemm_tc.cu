@@ -106,6 +106,9 @@ struct TcParams {
     int atomic;          // split-K: red.add into C
     int kb_per_split;    // k-blocks per split
     int splits;          // number of K splits (part of the linearised tile space)
+    // optional gating (persistent encoder wavefront; kernels.h::TcGate): the A rows of chunk q = row / gate_rows exist once
+    // gate_wait[q] >= gate_target; every epilogue warp adds 1 to gate_done[m-tile] after its stores of a tile are visible
+    const unsigned* gate_wait; unsigned gate_target; int gate_rows; unsigned* gate_done;
 };
 
 // TA: A operand is M-major (A stored K x M).  NB: B operand is N-major (B stored K x N).
@@ -164,6 +167,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int m0 = (mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
                 const int kb0 = z * p.kb_per_split;
                 const int nkb = min(p.kb_per_split, nkb_total - kb0);
+                if (p.gate_wait) {       // the producer kernel is still running: spin until it has published this tile's last row
+                    const unsigned* f = p.gate_wait + (min(m0 + TBM, p.M) - 1) / p.gate_rows;
+                    unsigned v;
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < p.gate_target);
+                    asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes (other SMs) -> this thread's TMA reads
+                }
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (S3 ? 2 : 1) * (STAGE_A_BYTES + STAGE_B_BYTES));
@@ -279,6 +288,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 __syncwarp();
             }
+            if (p.gate_done) {           // this warp's 32 rows of the tile are in global memory
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.gate_done + m0 / TBM, 1u);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -382,7 +396,7 @@ int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const floa
                     make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) && make_map(&mbl, Blo, (uint64_t)K, (uint64_t)N, ldb, TBN, false);
     if (!ok) return 1;
     const int nkb = cdiv(K, TBK);
-    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1};
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1, nullptr, 0u, 1, nullptr};
     dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM), tc_num_sms()));
     return launch_tc<false, false, true>(st, ma, mb, mal, mbl, p, grid);
 }
@@ -405,7 +419,7 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
     }
     const int kbps = cdiv(nkb, splits);
     splits = cdiv(nkb, kbps);
-    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps, splits};
+    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps, splits, nullptr, 0u, 1, nullptr};
     if (splits > 1) {
         if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
         else if (beta != 1.f) return 1;
@@ -415,6 +429,21 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
     if (!ta && !tb) return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
     if (ta && !tb) return launch_tc<true, true, false>(st, ma, mb, ma, mb, p, grid);
     return launch_tc<true, false, false>(st, ma, mb, ma, mb, p, grid);
+}
+
+// C = A . B^T + bias as ONE small persistent launch (`ctas` CTAs) that runs beside the kernel PRODUCING A: tiles are walked in
+// row order, the TMA warp waits for gate.wait[row chunk] >= gate.target before it reads a tile's rows, and each finished tile
+// counts 4 (epilogue warps) into gate.done[m-tile]; the consumer waits for 4 * tiles_per_row() there.  Returns 1 if the TMA path
+// cannot take the operands (the caller must then not use the gated scheme).
+int gemm_tc_tiles_per_row(int N) { return cdiv(N, TBN); }
+int gemm_tc_nt_gated(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     const float* bias, const TcGate& gate, int ctas) {
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false)) return 1;
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, cdiv(K, TBK), 1, gate.wait, gate.target, gate.rows, gate.done};
+    dim3 grid(std::max(1, std::min(cdiv(N, TBN) * cdiv(M, TBM), ctas)));
+    return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

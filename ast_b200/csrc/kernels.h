@@ -20,6 +20,12 @@ int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, co
 int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
             float* C, int ldc, const float* bias, float beta, int split_k);
 
+// gated variant for the persistent encoder wavefront (gemm_tc.cu): wait[q] >= target before rows of chunk q = row / rows are read;
+// done[m-tile of 128 rows] += 4 per finished tile
+struct TcGate { const unsigned* wait; unsigned target; int rows; unsigned* done; };
+int gemm_tc_tiles_per_row(int N);
+int gemm_tc_nt_gated(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                     const float* bias, const TcGate& gate, int ctas);
 // fp32-faithful 3xTF32 NT GEMM (gemm_tc.cu) on (hi, lo) = split_tf32(operand); returns 1 if the shape is unsupported
 int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo,
@@ -63,6 +69,9 @@ struct LstmChain {
     unsigned drop_stream;
     unsigned drop_off;   // added to the dropout counter: (t0 * B * h) when this launch covers steps [t0, t0+T) of a longer sequence
     int b0, nb;          // batch rows [b0, b0+nb) of the B-row buffers handled by this chain (nb = 0: all B rows)
+    // forward, optional: the x-projection G is being written by a gated GEMM (TcGate) while this kernel runs - 128-row tile
+    // m of G is complete once tile_ready[m] >= tile_target.  null: G is complete at launch.
+    const unsigned* tile_ready; unsigned tile_target;
 };
 struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
 // Chunk gating for a recurrence kernel that covers a whole sequence while its inputs are still being produced (the

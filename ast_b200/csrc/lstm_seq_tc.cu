@@ -200,6 +200,12 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         float4 gx[2];
         unsigned ready_seen = gt.ready ? 0u : 0xffffffffu;
         gate_wait(gt.ready, ready_seen, 0u);
+        int tiles_ok = 0;          // leading 128-row tiles of G known complete (a.tile_ready gating)
+        // rows of step i handled here: [i*B + b0, i*B + b0 + nb) -> needs every tile up to the one holding the last row
+#define TILE_WAIT(step) do { if (a.tile_ready) { const int need = ((step) * B + b0 + nb - 1) >> 7; \
+            while (tiles_ok <= need) { unsigned v; do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tile_ready + tiles_ok) : "memory"); } \
+                                       while (v < a.tile_target); ++tiles_ok; } } } while (0)
+        TILE_WAIT(0);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int b = 2 * w + j;
@@ -257,7 +263,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             }
             if (tid == 0) PROBE(5);
             // bookkeeping: overlaps the other CTAs' sends and the next step's MMA
-            if (i + 1 < T) gate_wait(gt.ready, ready_seen, (unsigned)(i + 1));      // x-projection of step i+1 published?
+            if (i + 1 < T) { gate_wait(gt.ready, ready_seen, (unsigned)(i + 1)); TILE_WAIT(i + 1); }      // x-projection of step i+1 published?
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int b = 2 * w + j;
@@ -276,6 +282,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         }
     }
 #undef PROBE
+#undef TILE_WAIT
     tc_fence_before();
     __syncthreads();
     if (w == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(FW_TMEM_COLS));

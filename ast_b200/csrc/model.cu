@@ -25,6 +25,8 @@ constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
 
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
+constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
+constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + MAXL + 64;   // done | tiles | ready (backward)
 
 struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
 
@@ -92,8 +94,8 @@ struct ast_model {
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
-    cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0;     // persistent wavefront: ready[MAXL] then done[MAXL][MAXQ]
+    cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
+    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_defer_l0dx = 0, enc_wseg = 1, enc_gemm_ctas = 8;     // persistent wavefront: ready[MAXL] then done[MAXL][MAXQ]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -183,7 +185,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs);
     const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, H = m->H, h = m->h, E = m->E, A = m->A, Vp = m->Vp, R = m->R, NL = m->NL;
     const size_t M0 = (size_t)B * Fp * T1, M1 = (size_t)B * Fp * Rs, TB = (size_t)Tp * B;
-    m->enc_flags = a.get<unsigned>((size_t)MAXL * (1 + MAXQ) + 64);
+    m->enc_flags = a.get<unsigned>(ENC_FLAG_WORDS);
     const int S = std::max(L - 1, 1);
     const int Bd = std::max(std::max(B, N), 1);
     m->Xn = a.get<float>((size_t)B * T * m->D);
@@ -481,57 +483,56 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // first-time launch submitted while the recurrence kernels spin on flags only this host thread can advance would hang.
     // The first pass of a model (and the first after an option change) therefore runs the per-chunk path, which launches the
     // same kernels.
-    const bool persist = wave && m->enc_persist && persist_allowed() && lstm_seq_gated_supported(h, m->exact != 0) && Tp >= 48 &&
-                         nq <= MAXQ && m->enc_flags && m->warm_fwd > 0;
+    const bool persist = wave && (m->enc_persist & 1) && persist_allowed() && lstm_seq_gated_supported(h, m->exact != 0) && Tp >= 48 &&
+                         nq <= MAXQ && (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->warm_fwd > 0 && m->tc_gemm;
     if (!wave) {
         for (int l = 0; l < NL; ++l) { AST_TRY(project(l, 0, Tp, st)); AST_TRY(recur(l, 0, Tp, st)); }
     } else if (persist) {
-        // PERSISTENT wavefront: one whole-sequence recurrence launch per layer, all three resident at once (96 CTAs); the chunk
-        // hand-offs are device flags instead of kernel boundaries.  layer l's kernel spins until its GEMM stream has published
-        // the x-projection of the steps it is about to touch (`ready`, a step count written with cuStreamWriteValue32 after each
-        // projection GEMM); the GEMM stream of layer l+1 waits (cuStreamWaitValue32) for all CTAs of layer l to have counted
-        // themselves into `done[chunk]`.  Against the per-chunk launches this removes ~17 us of kernel prologue (1 MB of W_h
-        // into shared memory, TMEM allocation, cluster launch) per chunk and lets the chunks shrink: the pipeline fill between
-        // layers is 2 x PCH steps instead of 2 x 24..32.
-        // SUBMISSION ORDER matters: streams can share a hardware queue, and an operation that blocks its queue (a value wait,
-        // or anything ordered after a spinning kernel) must never be submitted ahead of work that kernel needs.  So: kernels
-        // first, then the GEMMs in wavefront order (a valid serial schedule), and only then the joins.
-        unsigned* ready = m->enc_flags;
-        unsigned* done = m->enc_flags + MAXL;
+        // PERSISTENT wavefront: ONE whole-sequence recurrence launch per layer, all three resident at once (96 CTAs), and for the
+        // layers above the first ONE small persistent projection GEMM per (layer, direction) (8 CTAs each) that runs beside
+        // them.  Hand-offs are device counters instead of kernel boundaries: every CTA of layer l-1 counts itself into
+        // done[l-1][chunk] when its outputs of a chunk of PCH steps are in global memory; the GEMM's TMA warp spins on that
+        // counter before it loads a tile's rows, and its epilogue warps count finished tiles into tiles[l][d][m-tile]; the
+        // recurrence of layer l spins on the tile that holds the gate pre-activations of its next step.  Against the per-chunk
+        // launches (one recurrence launch + two GEMM launches + events per chunk and layer: ~70 us of hand-off per layer)
+        // the lag between layers is one chunk plus a few microseconds.  The layer-0 projection (K = 1536, 3/4 of the encoder's
+        // GEMM FLOPs) runs first as one GEMM per direction on the whole GPU.
+        unsigned* done = m->enc_flags;
+        unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         cudaEvent_t* ev = m->ev_pool;
-        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ((size_t)MAXL * (1 + MAXQ)), st));
+        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
+        AST_TRY(project(0, 0, Tp, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
-        for (int l = 0; l < NL; ++l) {
-            if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
+        for (int l = 1; l < NL; ++l) {
+            AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
             AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0));
         }
         int ncta = 0;
+        const unsigned tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(4 * h);
         for (int l = 0; l < NL; ++l) {
-            const LstmGate gate{ready + l, l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
-            AST_TRY(lstm_seq_fwd_gated(l == 0 ? st : m->lay[l], fwd_chains(l, 0), 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
+            LstmChains ch = fwd_chains(l, 0);
+            if (l > 0)
+                for (int d = 0; d < 2; ++d) { ch.c[d].tile_ready = tiles + (size_t)(l * 2 + d) * MAXT; ch.c[d].tile_target = tile_target; }
+            const LstmGate gate{nullptr, l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            AST_TRY(lstm_seq_fwd_gated(l == 0 ? st : m->lay[l], ch, 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
         }
-        // layer 0 depends on nothing: a small first projection so the recurrence starts at once, then doubling slices (bigger
-        // GEMMs run closer to the tensor-core rate and stay ahead of the recurrence)
-        for (int t0 = 0, sz = PCH; t0 < Tp; sz = std::min(2 * sz, 64)) {
-            const int tn = std::min(sz, Tp - t0);
-            AST_TRY(project(0, t0, tn, m->layg[0]));
-            t0 += tn;
-            AST_TRY(stream_write32(m->layg[0], ready, (unsigned)t0));
-        }
-        for (int q = 0; q < nq; ++q)
-            for (int l = 1; l < NL; ++l) {
-                const int t0 = q * PCH, tn = std::min(PCH, Tp - t0);
-                AST_TRY(stream_wait_geq32(m->layg[l], done + (size_t)(l - 1) * MAXQ + q, (unsigned)ncta));
-                AST_TRY(project(l, t0, tn, m->layg[l]));
-                AST_TRY(stream_write32(m->layg[l], ready + l, (unsigned)(t0 + tn)));
+        for (int l = 1; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) {
+                const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+                const TcGate tg{done + (size_t)(l - 1) * MAXQ, (unsigned)ncta, PCH * B, tiles + (size_t)(l * 2 + d) * MAXT};
+                const int r = gemm_tc_nt_gated(d == 0 ? m->layg[l] : m->layh[l], Tp * B, 4 * h, m->in_enc(l), m->Hd[l - 1][d], m->in_enc(l),
+                                               m->p((ln + "/upward/W").c_str()), m->in_enc(l), m->Genc[l][d], 4 * h,
+                                               m->p((ln + "/upward/b").c_str()), tg, m->enc_gemm_ctas);
+                AST_CHECK(r == 0, "persistent wavefront: the gated projection GEMM rejected its operands");
             }
         for (int l = 1; l < NL; ++l) {
             AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
-        }
-        for (int l = 0; l < NL; ++l) {
             AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
+            AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL + l], m->layh[l]));
+            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + 2 * MAXL + l], 0));
         }
     } else {
         // The projection of (layer l, chunk c) runs on the layer's GEMM stream as soon as its input exists (layer 0: at once;
@@ -539,6 +540,11 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         // recurrence stream only waits for it.  Layer 0 is chunked too so its first recurrence starts after one small GEMM.
         cudaEvent_t* ev = m->ev_pool;          // ev[l*nch + c]: recurrence of chunk c, layer l done; evg[...]: its projection done
         cudaEvent_t* evg = m->ev_pool + NL * nch + 1;
+        // the layer-0 projection (K = 1536: 3/4 of the encoder's GEMM work) as ONE GEMM per direction on the whole GPU before the
+        // recurrence kernels take their SMs: chunked beside the recurrences it ran on the ~50 SMs they leave free and was the
+        // bottleneck of the forward pass (0.77 -> 0.68 ms at B32 x T640)
+        const bool l0_whole = m->enc_l0_pre > 0;      // measured: no gain on this path (the hand-offs dominate), off by default
+        if (l0_whole) AST_TRY(project(0, 0, Tp, st));
         AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
         for (int l = 0; l < NL; ++l) {
             if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[NL * nch], 0));
@@ -548,6 +554,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             for (int l = 0; l < NL; ++l) {     // enqueue order = wavefront order (keeps the host from serialising streams)
                 cudaStream_t s = l == 0 ? st : m->lay[l];
                 const int t0 = c * CH, tn = std::min(CH, Tp - t0);
+                if (l == 0 && l0_whole) { AST_TRY(recur(l, t0, tn, s)); AST_CUDA_OK(cudaEventRecord(ev[l * nch + c], s)); continue; }
                 if (l > 0) AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[(l - 1) * nch + c], 0));
                 AST_TRY(project(l, t0, tn, m->layg[l]));
                 AST_CUDA_OK(cudaEventRecord(evg[l * nch + c], m->layg[l]));
@@ -895,20 +902,25 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         return 0;
     };
     auto bwd_dx = [&](int l, int ci, cudaStream_t s) -> int { return bwd_dx_rows(l, ci * CH, std::min(CH, Tp - ci * CH), s); };
-    auto enc_wgrads = [&](int l) -> int {
+    // weight gradients of layer l from the steps [t0, t0+tn) (first: overwrite, else accumulate)
+    auto enc_wgrads_range = [&](int l, int t0, int tn, bool first) -> int {
+        const size_t r0 = (size_t)t0 * B;
+        const float beta = first ? 0.f : 1.f;
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
-            AST_TRY(gemm(m, sw, true, false, 4 * h, in, TB, m->Genc[l][d], 4 * h, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_ENC_WGRAD));
-            AST_TRY(gemm(m, sw, true, false, 4 * h, h, TB, m->Genc[l][d], 4 * h, m->Hs[l][d], h, m->g((ln + "/lateral/W").c_str()), h, nullptr, 0.f, -1, SITE_ENC_WGRAD));
-            AST_TRY(colsum(sw, m->Genc[l][d], 4 * h, m->g((ln + "/upward/b").c_str()), TB, 4 * h, false));
+            const float* dG = m->Genc[l][d] + r0 * 4 * h;
+            AST_TRY(gemm(m, sw, true, false, 4 * h, in, tn * B, dG, 4 * h, xin + r0 * in, in, m->g((ln + "/upward/W").c_str()), in, nullptr, beta, -1, SITE_ENC_WGRAD));
+            AST_TRY(gemm(m, sw, true, false, 4 * h, h, tn * B, dG, 4 * h, m->Hs[l][d] + r0 * h, h, m->g((ln + "/lateral/W").c_str()), h, nullptr, beta, -1, SITE_ENC_WGRAD));
+            AST_TRY(colsum(sw, dG, 4 * h, m->g((ln + "/upward/b").c_str()), tn * B, 4 * h, !first));
         }
         return 0;
     };
+    auto enc_wgrads = [&](int l) -> int { return enc_wgrads_range(l, 0, Tp, true); };
     const int PCH = std::max(4, m->enc_pchunk);
     const int nq = (Tp + PCH - 1) / PCH;
-    const bool persist = wave && m->enc_persist && persist_allowed() && lstm_seq_gated_supported(h, ex) && Tp >= 48 && nq <= MAXQ &&
+    const bool persist = wave && (m->enc_persist & 2) && persist_allowed() && lstm_seq_gated_supported(h, ex) && Tp >= 48 && nq <= MAXQ &&
                          m->enc_flags && m->warm_bwd > 0;
     if (!wave) {
         for (int l = NL - 1; l >= 0; --l) {
@@ -922,10 +934,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         // END of the sequence (processing order).  `ready[l]` = steps of dout published for layer l (written after layer l+1's dx
         // GEMM of the chunk), `done[l][q]` = CTAs of layer l that have written dG of chunk q.  Submission order: kernels, GEMMs
         // in wavefront order, joins last.
-        unsigned* ready = m->enc_flags;
-        unsigned* done = m->enc_flags + MAXL;
+        unsigned* done = m->enc_flags;
+        unsigned* ready = m->enc_flags + (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT;
         cudaEvent_t* ev = m->ev_pool;
-        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ((size_t)MAXL * (1 + MAXQ)), st));
+        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int l = 0; l < NL; ++l) {
             if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
@@ -936,13 +948,28 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             const LstmGate gate{l < NL - 1 ? ready + l : nullptr, done + (size_t)l * MAXQ, PCH};
             AST_TRY(lstm_seq_bwd_gated(l == NL - 1 ? st : m->lay[l], bwd_chains(l, 0, true, false), 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
         }
-        for (int q = 0; q < nq; ++q)
+        // The weight gradients (side stream, lowest priority) are cut into `nw` time segments that start as soon as every layer
+        // has written dG for the segment, so most of them run beside the recurrences instead of after them.
+        const int nw = (sw != st) ? std::max(1, std::min(m->enc_wseg, nq)) : 1;
+        int seg = 0, seg_q0 = 0;
+        for (int q = 0; q < nq; ++q) {
             for (int l = NL - 1; l >= 0; --l) {
                 const int t_hi = Tp - q * PCH, t_lo = std::max(t_hi - PCH, 0);
+                if (l == 0 && m->enc_defer_l0dx) continue;       // not needed by any recurrence: after them, on the whole GPU
                 AST_TRY(stream_wait_geq32(m->layg[l], done + (size_t)l * MAXQ + q, (unsigned)ncta));
                 AST_TRY(bwd_dx_rows(l, t_lo, t_hi - t_lo, m->layg[l]));
                 if (l > 0) AST_TRY(stream_write32(m->layg[l], ready + (l - 1), (unsigned)(Tp - t_lo)));
             }
+            if (nw > 1 && seg < nw - 1 && q + 1 == ((seg + 1) * nq) / nw) {       // segment `seg` = chunks [seg_q0, q]; the last one follows the joins
+                const int t_hi = Tp - seg_q0 * PCH, t_lo = std::max(Tp - (q + 1) * PCH, 0);
+                for (int l = NL - 1; l >= 0; --l) {
+                    AST_TRY(stream_wait_geq32(sw, done + (size_t)l * MAXQ + q, (unsigned)ncta));
+                    AST_TRY(enc_wgrads_range(l, t_lo, t_hi - t_lo, seg == 0));
+                }
+                ++seg; seg_q0 = q + 1;
+            }
+        }
+        const int last_t_hi = Tp - seg_q0 * PCH;       // steps [0, last_t_hi) remain for the weight gradients
         for (int l = NL - 1; l >= 0; --l) {    // joins: recurrence kernels, GEMM streams; weight gradients once a layer's dG is complete
             if (l < NL - 1) {
                 AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
@@ -951,12 +978,13 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
         }
+        if (m->enc_defer_l0dx) AST_TRY(bwd_dx_rows(0, 0, Tp, st));
         for (int l = NL - 1; l >= 0; --l) {
             if (sw != st) {
                 if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + l], 0));
                 else { AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL], st)); AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + 2 * MAXL], 0)); }
             }
-            AST_TRY(enc_wgrads(l));
+            AST_TRY(enc_wgrads_range(l, 0, last_t_hi, seg == 0));
         }
     } else {
         // recurrence of (layer l, chunk c) on the layer's stream; its dx GEMMs on the layer's GEMM stream, so they overlap
@@ -1076,14 +1104,20 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     AST_CREATE_CHECK(e == cudaSuccess, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     e = cudaMallocHost(&m->h_pinned, 64 * sizeof(int));
     AST_CREATE_CHECK(e == cudaSuccess, "cudaMallocHost: %s", cudaGetErrorString(e));
-    e = cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking);
+    // priorities: the GEMMs the recurrences wait for (projection / dx chunks) are dispatched ahead of the weight-gradient GEMMs
+    // of the side stream when both compete for the SMs the recurrence kernels leave free
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (getenv("AST_NO_PRIO")) prio_lo = prio_hi = 0;
+    e = cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, prio_lo);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaStreamCreate: %s", cudaGetErrorString(e));
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_tr, cudaEventDisableTiming);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_bucket[i], cudaEventDisableTiming);
-    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->lay[i], cudaStreamNonBlocking);
-    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&m->layg[i], cudaStreamNonBlocking);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->lay[i], cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layg[i], cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layh[i], cudaStreamNonBlocking, prio_hi);
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
@@ -1101,6 +1135,7 @@ int ast_destroy(ast_model* m) {
     if (m->side) cudaStreamDestroy(m->side);
     for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
     for (int i = 0; i < MAXL; ++i) if (m->layg[i]) cudaStreamDestroy(m->layg[i]);
+    for (int i = 0; i < MAXL; ++i) if (m->layh[i]) cudaStreamDestroy(m->layh[i]);
     for (int i = 0; i < 256; ++i) if (m->ev_pool[i]) cudaEventDestroy(m->ev_pool[i]);
     delete m;
     return 0;
@@ -1157,6 +1192,10 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
+    else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
+    else if (!strcmp(key, "enc_wseg")) m->enc_wseg = (int)value;
+    else if (!strcmp(key, "enc_gemm_ctas")) m->enc_gemm_ctas = (int)value;
+    else if (!strcmp(key, "enc_defer_l0dx")) m->enc_defer_l0dx = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
@@ -1503,7 +1542,7 @@ int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_fl
     else if (s == "ht") { src = m->ht; n = (size_t)(m->L - 1) * B * m->A; }
     else if (s == "row_loss") { src = m->row_loss; n = (size_t)(m->L - 1) * B; }
     else if (s == "W1p") { src = m->W1p; n = (size_t)m->C1 * m->K1; }
-    else if (s == "enc_flags") { src = reinterpret_cast<const float*>(m->enc_flags); n = (size_t)MAXL * (1 + MAXQ); }
+    else if (s == "enc_flags") { src = reinterpret_cast<const float*>(m->enc_flags); n = ENC_FLAG_WORDS; }
     else if (s == "dec_prof") { src = reinterpret_cast<const float*>(m->dec_prof); n = 2 * 2 * 4096; }
     else if (s.size() == 4 && (s[0] == 'G' || s[0] == 'H' || s[0] == 'C' || s[0] == 'O') && s[1] == '_') {
         const int l = s[2] - '0', d = s[3] - '0';

@@ -298,7 +298,7 @@ def test_encoder_wavefront_and_side_stream_match_serial(dev, exact):
     out, launches = [], []
     # (overlap, chunk, persistent wavefront, its chunk): the persistent variant (one gated whole-sequence launch per layer,
     # device flags instead of kernel boundaries; TF32 mode only) must reproduce the same bits, ragged last chunk included
-    for overlap, chunk, persist, pchunk in ((0, 0, 0, 16), (1, 16, 0, 16), (1, 7, 0, 16), (1, 16, 1, 8), (1, 16, 1, 5), (1, 16, 1, 16)):
+    for overlap, chunk, persist, pchunk in ((0, 0, 0, 16), (1, 16, 0, 16), (1, 7, 0, 16), (1, 16, 1, 8), (1, 16, 3, 5), (1, 16, 3, 16)):
         e = _engine(cfg, 40, P)
         e.set_option("exact", exact); e.set_option("tc_gemm", 0 if exact else 1)
         e.set_option("overlap", overlap); e.set_option("enc_chunk", chunk)

@@ -1,4 +1,11 @@
-for o in "enc_persist=0" "enc_pchunk=8" "enc_pchunk=12" "enc_pchunk=16" "enc_pchunk=24" "enc_pchunk=32"; do
-  echo "== $o"; timeout -s KILL 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-beam --opt $o 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'])"
-done
-for o in "enc_persist=0" "enc_pchunk=8" "enc_pchunk=16"; do echo "== stage $o"; timeout -s KILL 100 python tools/profile_step.py --precision tf32 --steps 3 --opt stage_timing=1 --opt $o 2>&1 | tail -12; done
+run() { echo "== $*"; timeout -s KILL 40 python tools/persist_debug.py "$@" 2>&1 | tail -14; }
+run --T 640 --steps 3 --sync 1
+run --T 300 1680 640 200 --steps 8 --sync 0
+timeout -s KILL 120 python -m pytest tests -m gpu -x -q -k "wavefront or bucket" 2>&1 | tail -5
+st() { echo "== stage $*"; timeout -s KILL 40 python tools/profile_step.py --precision tf32 --steps 3 --opt stage_timing=1 "$@" 2>&1 | tail -2; }
+st --opt enc_persist=0
+st --opt enc_pchunk=16
+st --opt enc_pchunk=8
+st --opt enc_pchunk=4
+st --opt enc_pchunk=8 --opt enc_gemm_ctas=4
+st --opt enc_pchunk=8 --opt enc_gemm_ctas=12
