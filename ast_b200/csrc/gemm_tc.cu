@@ -108,7 +108,7 @@ struct TcParams {
     int splits;          // number of K splits (part of the linearised tile space)
     // optional gating (persistent encoder wavefront; kernels.h::TcGate): the A rows of chunk q = row / gate_rows exist once
     // gate_wait[q] >= gate_target; every epilogue warp adds 1 to gate_done[m-tile] after its stores of a tile are visible
-    const unsigned* gate_wait; unsigned gate_target; int gate_rows; unsigned* gate_done;
+    const unsigned* gate_wait; unsigned gate_target; int gate_B, gate_chunk, gate_T, gate_rev; unsigned* gate_done;
 };
 
 // TA: A operand is M-major (A stored K x M).  NB: B operand is N-major (B stored K x N).
@@ -164,11 +164,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int z = t / tiles_mn, mn = t - z * tiles_mn;
-                const int m0 = (mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
+                const int m0 = (p.gate_rev ? tiles_m - 1 - mn / tiles_n : mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
                 const int kb0 = z * p.kb_per_split;
                 const int nkb = min(p.kb_per_split, nkb_total - kb0);
                 if (p.gate_wait) {       // the producer kernel is still running: spin until it has published this tile's last row
-                    const unsigned* f = p.gate_wait + (min(m0 + TBM, p.M) - 1) / p.gate_rows;
+                    // rows are (step, batch) pairs; the producer counts chunks of gate_chunk steps in ITS processing order
+                    // (forward in time, or - gate_rev - backward from step gate_T - 1)
+                    const int q = p.gate_rev ? (p.gate_T - 1 - m0 / p.gate_B) / p.gate_chunk
+                                             : ((min(m0 + TBM, p.M) - 1) / p.gate_B) / p.gate_chunk;
+                    const unsigned* f = p.gate_wait + q;
                     unsigned v;
                     do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < p.gate_target);
                     asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes (other SMs) -> this thread's TMA reads
@@ -250,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
-            const int m0 = (mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
+            const int m0 = (p.gate_rev ? tiles_m - 1 - mn / tiles_n : mn / tiles_n) * TBM, n0 = (mn % tiles_n) * TBN;
             const int nkb = min(p.kb_per_split, nkb_total - z * p.kb_per_split);
             const int buf = it & 1;
             const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(wq * 32) << 16);
@@ -335,6 +339,11 @@ static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_
     return r == CUDA_SUCCESS;
 }
 
+// Grid cap for gemm_tc launches (0 = none): GEMMs that are off the critical path and run beside the persistent encoder wavefront
+// must leave the recurrence clusters their SMs - a 148-CTA grid of single CTAs re-takes every SM that frees up and starves the
+// 8-CTA cluster launches (stream priorities do not reserve SMs for a pending cluster).
+static int g_tc_cta_cap = 0;
+void gemm_tc_set_cta_cap(int cap) { g_tc_cta_cap = cap; }
 static int tc_num_sms() {
     static int sms = 0;
     if (!sms) {
@@ -396,7 +405,7 @@ int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const floa
                     make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) && make_map(&mbl, Blo, (uint64_t)K, (uint64_t)N, ldb, TBN, false);
     if (!ok) return 1;
     const int nkb = cdiv(K, TBK);
-    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1, nullptr, 0u, 1, nullptr};
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
     dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM), tc_num_sms()));
     return launch_tc<false, false, true>(st, ma, mb, mal, mbl, p, grid);
 }
@@ -419,31 +428,33 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
     }
     const int kbps = cdiv(nkb, splits);
     splits = cdiv(nkb, kbps);
-    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps, splits, nullptr, 0u, 1, nullptr};
+    TcParams p{M, N, K, C, ldc, bias, beta, splits > 1 ? 1 : 0, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
     if (splits > 1) {
         if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
         else if (beta != 1.f) return 1;
     }
-    dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM) * splits, tc_num_sms()));
+    dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM) * splits, g_tc_cta_cap > 0 ? std::min(g_tc_cta_cap, tc_num_sms()) : tc_num_sms()));
     if (!ta && tb) return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
     if (!ta && !tb) return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
     if (ta && !tb) return launch_tc<true, true, false>(st, ma, mb, ma, mb, p, grid);
     return launch_tc<true, false, false>(st, ma, mb, ma, mb, p, grid);
 }
 
-// C = A . B^T + bias as ONE small persistent launch (`ctas` CTAs) that runs beside the kernel PRODUCING A: tiles are walked in
+// C = A . op(B) + bias (tb: B^T, K-major weight; !tb: N-major weight) as ONE small persistent launch (`ctas` CTAs) that runs beside the kernel PRODUCING A: tiles are walked in
 // row order, the TMA warp waits for gate.wait[row chunk] >= gate.target before it reads a tile's rows, and each finished tile
 // counts 4 (epilogue warps) into gate.done[m-tile]; the consumer waits for 4 * tiles_per_row() there.  Returns 1 if the TMA path
 // cannot take the operands (the caller must then not use the gated scheme).
 int gemm_tc_tiles_per_row(int N) { return cdiv(N, TBN); }
-int gemm_tc_nt_gated(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                     const float* bias, const TcGate& gate, int ctas) {
+int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                  const float* bias, const TcGate& gate, int ctas) {
     if (M <= 0 || N <= 0 || K <= 0) return 1;
     CUtensorMap ma, mb;
-    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false)) return 1;
-    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, cdiv(K, TBK), 1, gate.wait, gate.target, gate.rows, gate.done};
+    const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !okB) return 1;
+    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, cdiv(K, TBK), 1, gate.wait, gate.target, gate.B, gate.chunk, gate.T, gate.rev ? 1 : 0, gate.done};
     dim3 grid(std::max(1, std::min(cdiv(N, TBN) * cdiv(M, TBM), ctas)));
-    return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
+    if (tb) return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
+    return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -20,12 +20,15 @@ int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, co
 int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
             float* C, int ldc, const float* bias, float beta, int split_k);
 
-// gated variant for the persistent encoder wavefront (gemm_tc.cu): wait[q] >= target before rows of chunk q = row / rows are read;
-// done[m-tile of 128 rows] += 4 per finished tile
-struct TcGate { const unsigned* wait; unsigned target; int rows; unsigned* done; };
+// gated variant for the persistent encoder wavefront (gemm_tc.cu).  Rows of A are (step, batch) pairs, B batch rows per step; the
+// kernel producing A counts its CTAs into wait[chunk] per chunk of `chunk` steps in its processing order (rev: from step T-1
+// down, and the m-tiles are then walked from the last one).  A tile's rows are read once wait[its chunk] >= target; every
+// finished tile adds 4 to done[m-tile of 128 rows].
+void gemm_tc_set_cta_cap(int cap);   // 0 = no cap; applies to gemm_tc() launches issued afterwards by this thread's caller
+struct TcGate { const unsigned* wait; unsigned target; int B, chunk, T; bool rev; unsigned* done; };
 int gemm_tc_tiles_per_row(int N);
-int gemm_tc_nt_gated(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                     const float* bias, const TcGate& gate, int ctas);
+int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                  const float* bias, const TcGate& gate, int ctas);
 // fp32-faithful 3xTF32 NT GEMM (gemm_tc.cu) on (hi, lo) = split_tf32(operand); returns 1 if the shape is unsupported
 int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo,
@@ -69,18 +72,16 @@ struct LstmChain {
     unsigned drop_stream;
     unsigned drop_off;   // added to the dropout counter: (t0 * B * h) when this launch covers steps [t0, t0+T) of a longer sequence
     int b0, nb;          // batch rows [b0, b0+nb) of the B-row buffers handled by this chain (nb = 0: all B rows)
-    // forward, optional: the x-projection G is being written by a gated GEMM (TcGate) while this kernel runs - 128-row tile
-    // m of G is complete once tile_ready[m] >= tile_target.  null: G is complete at launch.
+    // optional: the kernel's per-step input (forward: the x-projection G; backward: dout) is being written by a gated GEMM
+    // (TcGate) while this kernel runs - its 128-row tile m is complete once tile_ready[m] >= tile_target.  null: complete at launch.
     const unsigned* tile_ready; unsigned tile_target;
 };
 struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
-// Chunk gating for a recurrence kernel that covers a whole sequence while its inputs are still being produced (the
-// persistent encoder wavefront, model.cu): steps are numbered in PROCESSING order k (forward: k = t, backward: k = T-1-t).
-//   ready: device word = number of leading steps whose inputs (forward: x-projection rows of G; backward: dout rows) have been
-//          written; the kernel spins (ld.acquire.sys) before it first touches step k until *ready > k.  null: everything is ready.
-//   done : per-chunk counters; every CTA adds 1 to done[k / chunk] (after a fence) once its outputs of that chunk are in
-//          global memory, so a stream can wait (cuStreamWaitValue32 GEQ #CTAs) and launch the consumer GEMM.  null: no signal.
-struct LstmGate { const unsigned* ready; unsigned* done; int chunk; };
+// Chunk signalling of a recurrence kernel that covers a whole sequence while its consumers are already running (the persistent
+// encoder wavefront, model.cu).  Steps are numbered in PROCESSING order k (forward: k = t, backward: k = T-1-t); every CTA adds 1
+// to done[k / chunk] (after a fence) once its outputs of that chunk are in global memory, and a gated GEMM (TcGate) waits for all
+// CTAs of the launch.  null: no signalling.  (The kernel's own inputs are gated per 128-row tile: LstmChain::tile_ready.)
+struct LstmGate { unsigned* done; int chunk; };
 int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact);
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,

@@ -68,10 +68,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// chunk gating (kernels.h::LstmGate): spin until the producer has published more than k ready steps
-__device__ __forceinline__ void gate_wait(const unsigned* ready, unsigned& cached, unsigned k) {
-    while (cached <= k) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cached) : "l"(ready) : "memory");
-}
 // all epilogue threads: this CTA's global stores of the chunk are visible device-wide, then one arrival on the chunk's counter
 __device__ __forceinline__ void gate_signal(unsigned* counter, int tid) {
     __threadfence();
@@ -198,8 +194,6 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         const int ju = TU * rank + lane;
         float creg[2];
         float4 gx[2];
-        unsigned ready_seen = gt.ready ? 0u : 0xffffffffu;
-        gate_wait(gt.ready, ready_seen, 0u);
         int tiles_ok = 0;          // leading 128-row tiles of G known complete (a.tile_ready gating)
         // rows of step i handled here: [i*B + b0, i*B + b0 + nb) -> needs every tile up to the one holding the last row
 #define TILE_WAIT(step) do { if (a.tile_ready) { const int need = ((step) * B + b0 + nb - 1) >> 7; \
@@ -263,7 +257,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             }
             if (tid == 0) PROBE(5);
             // bookkeeping: overlaps the other CTAs' sends and the next step's MMA
-            if (i + 1 < T) { gate_wait(gt.ready, ready_seen, (unsigned)(i + 1)); TILE_WAIT(i + 1); }      // x-projection of step i+1 published?
+            if (i + 1 < T) TILE_WAIT(i + 1);      // x-projection of step i+1 published?
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int b = 2 * w + j;
@@ -383,8 +377,11 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         // ===== epilogue / elementwise: pair e -> batch row m = idx % 16, unit ul = idx / 16 =====
         float dc[2];
         float4 p_act[2]; float p_c[2], p_cp[2], p_dout[2];
-        unsigned ready_seen = gt.ready ? 0u : 0xffffffffu;
-        gate_wait(gt.ready, ready_seen, 0u);
+        int tile_next = (T * B - 1) >> 7;          // a.tile_ready gating: tiles above this one are known complete (dout arrives last tile first)
+#define TILE_WAIT_REV(step) do { if (a.tile_ready) { const int need = ((step) * B + b0) >> 7; \
+            while (tile_next >= need) { unsigned v; do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tile_ready + tile_next) : "memory"); } \
+                                        while (v < a.tile_target); --tile_next; } } } while (0)
+        TILE_WAIT_REV(T - 1);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int idx = tid + e * TC_EPI;
@@ -442,7 +439,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 mbar_arrive(mbar_g);              // hand the operand to the issuer warp
             }
             // 2. bookkeeping while the tensor core works: write dG_t in place, prefetch step i-1
-            if (i > 0) gate_wait(gt.ready, ready_seen, (unsigned)(T - i));        // dout of step i-1 (processing index T-i) published?
+            if (i > 0) TILE_WAIT_REV(i - 1);       // dout of step i-1 published?
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int idx = tid + e * TC_EPI;
@@ -509,7 +506,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 
 template <class KernT>
 static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B,
-                     float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, nullptr, 1}) {
+                     float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, 1}) {
     AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);
@@ -525,7 +522,7 @@ static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, cons
     return 0;
 }
 static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B, float drop, unsigned long long seed,
-                         LstmGate gate = LstmGate{nullptr, nullptr, 1}) {
+                         LstmGate gate = LstmGate{nullptr, 1}) {
     AST_CUDA_OK(cudaFuncSetAttribute(lstm_seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);

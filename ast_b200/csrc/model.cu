@@ -5,7 +5,6 @@
 #include <cstdarg>
 #include <cstring>
 #include <cstdlib>
-#include <cuda.h>
 #include <string>
 #include <vector>
 #include "../../include/ast_b200.h"
@@ -26,7 +25,7 @@ constexpr int MAXL = 4;
 
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
-constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + MAXL + 64;   // done | tiles | ready (backward)
+constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + 64;   // done | tiles
 
 struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
 
@@ -95,7 +94,7 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_defer_l0dx = 0, enc_wseg = 1, enc_gemm_ctas = 8;     // persistent wavefront: ready[MAXL] then done[MAXL][MAXQ]
+    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -347,34 +346,12 @@ static int require_ready(ast_model* m, int B, int T, int L, int N, int steps) {
     return 0;
 }
 
-// Stream memory operations (driver API): the persistent encoder wavefront orders GEMM launches against kernels that are
-// still running, which events cannot express.
-// (Entry points through cudaGetDriverEntryPoint: the library must load on a machine without libcuda.so.1.)
-typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-static StreamValue32Fn driver_fn(const char* name) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-    return reinterpret_cast<StreamValue32Fn>(p);
-}
-static StreamValue32Fn fn_write32() { static StreamValue32Fn f = driver_fn("cuStreamWriteValue32"); return f; }
-static StreamValue32Fn fn_wait32() { static StreamValue32Fn f = driver_fn("cuStreamWaitValue32"); return f; }
-static int stream_write32(cudaStream_t s, unsigned* addr, unsigned value) {
-    const CUresult r = fn_write32()((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WRITE_VALUE_DEFAULT);
-    AST_CHECK(r == CUDA_SUCCESS, "cuStreamWriteValue32 failed (%d)", (int)r);
-    return 0;
-}
-static int stream_wait_geq32(cudaStream_t s, unsigned* addr, unsigned value) {
-    const CUresult r = fn_wait32()((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
-    AST_CHECK(r == CUDA_SUCCESS, "cuStreamWaitValue32 failed (%d)", (int)r);
-    return 0;
-}
 // A profiler that serialises kernels (ncu) would deadlock kernels that wait for one another: the same switch that turns the
 // cooperative decoder launch off (tools/ncu_capture.sh) selects the per-chunk launches.
 static bool persist_allowed() {
     static const bool off = getenv("AST_NO_COOP") != nullptr || getenv("AST_NO_PERSIST") != nullptr ||
                             getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
-    return !off && fn_write32() && fn_wait32();
+    return !off;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,10 +480,9 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         AST_TRY(project(0, 0, Tp, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
-        for (int l = 1; l < NL; ++l) {
+        for (int l = 0; l < NL; ++l) {       // every recurrence on a high-priority stream: the caller's stream has the priority of the side stream
             AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
-            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0));
-            AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0));
+            if (l > 0) { AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0)); AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0)); }
         }
         int ncta = 0;
         const unsigned tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(4 * h);
@@ -514,21 +490,22 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             LstmChains ch = fwd_chains(l, 0);
             if (l > 0)
                 for (int d = 0; d < 2; ++d) { ch.c[d].tile_ready = tiles + (size_t)(l * 2 + d) * MAXT; ch.c[d].tile_target = tile_target; }
-            const LstmGate gate{nullptr, l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
-            AST_TRY(lstm_seq_fwd_gated(l == 0 ? st : m->lay[l], ch, 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
+            const LstmGate gate{l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            AST_TRY(lstm_seq_fwd_gated(m->lay[l], ch, 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
         }
         for (int l = 1; l < NL; ++l)
             for (int d = 0; d < 2; ++d) {
                 const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
-                const TcGate tg{done + (size_t)(l - 1) * MAXQ, (unsigned)ncta, PCH * B, tiles + (size_t)(l * 2 + d) * MAXT};
-                const int r = gemm_tc_nt_gated(d == 0 ? m->layg[l] : m->layh[l], Tp * B, 4 * h, m->in_enc(l), m->Hd[l - 1][d], m->in_enc(l),
+                const TcGate tg{done + (size_t)(l - 1) * MAXQ, (unsigned)ncta, B, PCH, Tp, false, tiles + (size_t)(l * 2 + d) * MAXT};
+                const int r = gemm_tc_gated(d == 0 ? m->layg[l] : m->layh[l], true, Tp * B, 4 * h, m->in_enc(l), m->Hd[l - 1][d], m->in_enc(l),
                                                m->p((ln + "/upward/W").c_str()), m->in_enc(l), m->Genc[l][d], 4 * h,
                                                m->p((ln + "/upward/b").c_str()), tg, m->enc_gemm_ctas);
                 AST_CHECK(r == 0, "persistent wavefront: the gated projection GEMM rejected its operands");
             }
-        for (int l = 1; l < NL; ++l) {
+        for (int l = 0; l < NL; ++l) {
             AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
+            if (l == 0) continue;
             AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
             AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL + l], m->layh[l]));
@@ -748,6 +725,18 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
 // ------------------------------------------------------------------------------------------------
 // backward (nn.py:180-181)
 // ------------------------------------------------------------------------------------------------
+// the persistent (gated, whole-sequence) encoder backward applies to this pass (see backward_impl / encode_impl)
+static bool bwd_will_persist(const ast_model* m) {
+    const int Tp = m->Tp, B = m->B, NL = m->NL;
+    const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
+    const int nch = (Tp + CH - 1) / CH;
+    const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
+    const int PCH = std::max(4, m->enc_pchunk);
+    const int nq = (Tp + PCH - 1) / PCH;
+    return wave && (m->enc_persist & 2) && persist_allowed() && lstm_seq_gated_supported(m->h, m->exact != 0) && Tp >= 48 && nq <= MAXQ &&
+           (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->warm_bwd > 0 && m->tc_gemm;
+}
+
 static int backward_impl(ast_model* m, cudaStream_t st) {
     AST_CHECK(m->have_fwd, "backward: no forward_loss to differentiate");
     const ast_config& c = m->cfg;
@@ -832,6 +821,9 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         return 0;
     };
     // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
+    // With the persistent encoder wavefront below they run beside the recurrence clusters and are capped to a few CTAs.
+    const bool will_persist = bwd_will_persist(m);
+    if (will_persist && sw != st) gemm_tc_set_cta_cap(m->enc_side_ctas);
     AST_TRY(fork());
     if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
         AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, m->actd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
@@ -851,6 +843,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
         AST_TRY(colsum(sw, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
+    gemm_tc_set_cta_cap(0);
     // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
     // starts its all-reduce now (ast_grad_bucket_wait) and overlaps it with the encoder + CNN backward below
     AST_CUDA_OK(cudaEventRecord(m->ev_bucket[0], sw));
@@ -920,8 +913,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     auto enc_wgrads = [&](int l) -> int { return enc_wgrads_range(l, 0, Tp, true); };
     const int PCH = std::max(4, m->enc_pchunk);
     const int nq = (Tp + PCH - 1) / PCH;
-    const bool persist = wave && (m->enc_persist & 2) && persist_allowed() && lstm_seq_gated_supported(h, ex) && Tp >= 48 && nq <= MAXQ &&
-                         m->enc_flags && m->warm_bwd > 0;
+    const bool persist = will_persist;
     if (!wave) {
         for (int l = NL - 1; l >= 0; --l) {
             AST_TRY(bwd_chunk(l, 0, st));
@@ -930,61 +922,55 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             AST_TRY(enc_wgrads(l));
         }
     } else if (persist) {
-        // persistent wavefront in reverse time (see encode_impl): one whole-sequence launch per layer, chunks counted from the
-        // END of the sequence (processing order).  `ready[l]` = steps of dout published for layer l (written after layer l+1's dx
-        // GEMM of the chunk), `done[l][q]` = CTAs of layer l that have written dG of chunk q.  Submission order: kernels, GEMMs
-        // in wavefront order, joins last.
+        // persistent wavefront in reverse time (see encode_impl): one whole-sequence recurrence launch per layer plus one small
+        // gated dx GEMM (dHd[l-1] = dG_l . W_up, tiles walked from the last row block down) per (layer >= 1, direction).  Every CTA
+        // of layer l counts itself into done[l][chunk] (chunks of PCH steps from the END of the sequence) when its dG rows are in
+        // global memory; the GEMM counts finished tiles into tiles[l][d][m-tile]; layer l-1 spins on the tile holding dout of its
+        // next step.  Layer 0's dx (N = 1536, not needed by any recurrence) follows as one GEMM per direction on the whole GPU,
+        // the weight gradients of a layer start on the side stream when that layer's kernel has finished.
         unsigned* done = m->enc_flags;
-        unsigned* ready = m->enc_flags + (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT;
+        unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         cudaEvent_t* ev = m->ev_pool;
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int l = 0; l < NL; ++l) {
-            if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
-            AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0));
+            AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
+            if (l > 0) { AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0)); AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0)); }
         }
         int ncta = 0;
         for (int l = NL - 1; l >= 0; --l) {
-            const LstmGate gate{l < NL - 1 ? ready + l : nullptr, done + (size_t)l * MAXQ, PCH};
-            AST_TRY(lstm_seq_bwd_gated(l == NL - 1 ? st : m->lay[l], bwd_chains(l, 0, true, false), 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
-        }
-        // The weight gradients (side stream, lowest priority) are cut into `nw` time segments that start as soon as every layer
-        // has written dG for the segment, so most of them run beside the recurrences instead of after them.
-        const int nw = (sw != st) ? std::max(1, std::min(m->enc_wseg, nq)) : 1;
-        int seg = 0, seg_q0 = 0;
-        for (int q = 0; q < nq; ++q) {
-            for (int l = NL - 1; l >= 0; --l) {
-                const int t_hi = Tp - q * PCH, t_lo = std::max(t_hi - PCH, 0);
-                if (l == 0 && m->enc_defer_l0dx) continue;       // not needed by any recurrence: after them, on the whole GPU
-                AST_TRY(stream_wait_geq32(m->layg[l], done + (size_t)l * MAXQ + q, (unsigned)ncta));
-                AST_TRY(bwd_dx_rows(l, t_lo, t_hi - t_lo, m->layg[l]));
-                if (l > 0) AST_TRY(stream_write32(m->layg[l], ready + (l - 1), (unsigned)(Tp - t_lo)));
-            }
-            if (nw > 1 && seg < nw - 1 && q + 1 == ((seg + 1) * nq) / nw) {       // segment `seg` = chunks [seg_q0, q]; the last one follows the joins
-                const int t_hi = Tp - seg_q0 * PCH, t_lo = std::max(Tp - (q + 1) * PCH, 0);
-                for (int l = NL - 1; l >= 0; --l) {
-                    AST_TRY(stream_wait_geq32(sw, done + (size_t)l * MAXQ + q, (unsigned)ncta));
-                    AST_TRY(enc_wgrads_range(l, t_lo, t_hi - t_lo, seg == 0));
+            LstmChains ch = bwd_chains(l, 0, true, false);
+            if (l < NL - 1)
+                for (int d = 0; d < 2; ++d) {
+                    ch.c[d].tile_ready = tiles + (size_t)((l + 1) * 2 + d) * MAXT;
+                    ch.c[d].tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(m->in_enc(l + 1));
                 }
-                ++seg; seg_q0 = q + 1;
-            }
+            const LstmGate gate{l > 0 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            AST_TRY(lstm_seq_bwd_gated(m->lay[l], ch, 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
+            AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));       // layer l's dG complete
         }
-        const int last_t_hi = Tp - seg_q0 * PCH;       // steps [0, last_t_hi) remain for the weight gradients
-        for (int l = NL - 1; l >= 0; --l) {    // joins: recurrence kernels, GEMM streams; weight gradients once a layer's dG is complete
-            if (l < NL - 1) {
-                AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));
-                AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
+        for (int l = NL - 1; l >= 1; --l)
+            for (int d = 0; d < 2; ++d) {
+                const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+                const int in = m->in_enc(l);
+                const TcGate tg{done + (size_t)l * MAXQ, (unsigned)ncta, B, PCH, Tp, true, tiles + (size_t)(l * 2 + d) * MAXT};
+                const int r = gemm_tc_gated(d == 0 ? m->layg[l] : m->layh[l], false, Tp * B, in, 4 * h, m->Genc[l][d], 4 * h,
+                                            m->p((ln + "/upward/W").c_str()), in, m->dHd[l - 1][d], in, nullptr, tg, m->enc_gemm_ctas_bwd);
+                AST_CHECK(r == 0, "persistent wavefront: the gated dx GEMM rejected its operands");
             }
-            AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
-            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
-        }
-        if (m->enc_defer_l0dx) AST_TRY(bwd_dx_rows(0, 0, Tp, st));
         for (int l = NL - 1; l >= 0; --l) {
-            if (sw != st) {
-                if (l < NL - 1) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + l], 0));
-                else { AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL], st)); AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + 2 * MAXL], 0)); }
+            AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
+            if (l > 0) {
+                AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
+                AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
+                AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL + l], m->layh[l]));
+                AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + 2 * MAXL + l], 0));
             }
-            AST_TRY(enc_wgrads_range(l, 0, last_t_hi, seg == 0));
+        }
+        AST_TRY(bwd_dx_rows(0, 0, Tp, st));
+        for (int l = NL - 1; l >= 0; --l) {
+            if (sw != st) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + l], 0));
+            AST_TRY(enc_wgrads(l));
         }
     } else {
         // recurrence of (layer l, chunk c) on the layer's stream; its dx GEMMs on the layer's GEMM stream, so they overlap
@@ -1193,9 +1179,9 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
-    else if (!strcmp(key, "enc_wseg")) m->enc_wseg = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas")) m->enc_gemm_ctas = (int)value;
-    else if (!strcmp(key, "enc_defer_l0dx")) m->enc_defer_l0dx = (int)value;
+    else if (!strcmp(key, "enc_gemm_ctas_bwd")) m->enc_gemm_ctas_bwd = (int)value;
+    else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
