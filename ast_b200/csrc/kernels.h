@@ -81,7 +81,7 @@ struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
 // encoder wavefront, model.cu).  Steps are numbered in PROCESSING order k (forward: k = t, backward: k = T-1-t); every CTA adds 1
 // to done[k / chunk] (after a fence) once its outputs of that chunk are in global memory, and a gated GEMM (TcGate) waits for all
 // CTAs of the launch.  null: no signalling.  (The kernel's own inputs are gated per 128-row tile: LstmChain::tile_ready.)
-struct LstmGate { unsigned* done; int chunk; };
+struct LstmGate { unsigned* done; int chunk; unsigned long long* ts; };   // ts (diagnostics, may be null): %globaltimer of block 0 at each chunk signal
 int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact);
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,

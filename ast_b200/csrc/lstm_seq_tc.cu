@@ -271,7 +271,10 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     if (i + 1 < T) gx[j] = __ldcg(reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju));
                 }
             }
-            if (gt.done && ((i + 1) % gt.chunk == 0 || i + 1 == T)) gate_signal(gt.done + i / gt.chunk, tid);
+            if ((i + 1) % gt.chunk == 0 || i + 1 == T) {
+                if (gt.ts && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gt.ts[i / gt.chunk] = t; }
+                if (gt.done) gate_signal(gt.done + i / gt.chunk, tid);
+            }
             if (tid == 0) PROBE(6);
         }
     }
@@ -455,7 +458,10 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     }
                 }
             }
-            if (gt.done && ((T - i) % gt.chunk == 0 || i == 0)) gate_signal(gt.done + (T - 1 - i) / gt.chunk, tid);
+            if ((T - i) % gt.chunk == 0 || i == 0) {
+                if (gt.ts && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gt.ts[(T - 1 - i) / gt.chunk] = t; }
+                if (gt.done) gate_signal(gt.done + (T - 1 - i) / gt.chunk, tid);
+            }
             if (send) {
                 // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
                 mbar_wait(mbar_mma, step & 1);
@@ -506,7 +512,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 
 template <class KernT>
 static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B,
-                     float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, 1}) {
+                     float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, 1, nullptr}) {
     AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);
@@ -522,7 +528,7 @@ static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, cons
     return 0;
 }
 static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B, float drop, unsigned long long seed,
-                         LstmGate gate = LstmGate{nullptr, 1}) {
+                         LstmGate gate = LstmGate{nullptr, 1, nullptr}) {
     AST_CUDA_OK(cudaFuncSetAttribute(lstm_seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);

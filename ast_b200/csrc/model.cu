@@ -26,6 +26,7 @@ constexpr int MAXL = 4;
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
 constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + 64;   // done | tiles
+constexpr size_t ENC_TS_WORDS = (size_t)2 * MAXL * MAXQ;     // diagnostics: [pass][layer][chunk] %globaltimer stamps
 
 struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
 
@@ -94,7 +95,8 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned* enc_flags = nullptr; int enc_persist = 1, enc_pchunk = 16; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
+    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0;
+    unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -185,6 +187,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, H = m->H, h = m->h, E = m->E, A = m->A, Vp = m->Vp, R = m->R, NL = m->NL;
     const size_t M0 = (size_t)B * Fp * T1, M1 = (size_t)B * Fp * Rs, TB = (size_t)Tp * B;
     m->enc_flags = a.get<unsigned>(ENC_FLAG_WORDS);
+    m->enc_ts = a.get<unsigned long long>(ENC_TS_WORDS);
     const int S = std::max(L - 1, 1);
     const int Bd = std::max(std::max(B, N), 1);
     m->Xn = a.get<float>((size_t)B * T * m->D);
@@ -490,7 +493,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             LstmChains ch = fwd_chains(l, 0);
             if (l > 0)
                 for (int d = 0; d < 2; ++d) { ch.c[d].tile_ready = tiles + (size_t)(l * 2 + d) * MAXT; ch.c[d].tile_target = tile_target; }
-            const LstmGate gate{l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            const LstmGate gate{l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)l * MAXQ : nullptr};
             AST_TRY(lstm_seq_fwd_gated(m->lay[l], ch, 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
         }
         for (int l = 1; l < NL; ++l)
@@ -945,7 +948,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                     ch.c[d].tile_ready = tiles + (size_t)((l + 1) * 2 + d) * MAXT;
                     ch.c[d].tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(m->in_enc(l + 1));
                 }
-            const LstmGate gate{l > 0 ? done + (size_t)l * MAXQ : nullptr, PCH};
+            const LstmGate gate{l > 0 ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)(MAXL + l) * MAXQ : nullptr};
             AST_TRY(lstm_seq_bwd_gated(m->lay[l], ch, 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
             AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));       // layer l's dG complete
         }
@@ -1179,6 +1182,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
+    else if (!strcmp(key, "enc_ts")) m->enc_ts_on = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas")) m->enc_gemm_ctas = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas_bwd")) m->enc_gemm_ctas_bwd = (int)value;
     else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
@@ -1528,6 +1532,7 @@ int ast_debug_fetch(ast_model* m, const char* name, float* out, long long max_fl
     else if (s == "ht") { src = m->ht; n = (size_t)(m->L - 1) * B * m->A; }
     else if (s == "row_loss") { src = m->row_loss; n = (size_t)(m->L - 1) * B; }
     else if (s == "W1p") { src = m->W1p; n = (size_t)m->C1 * m->K1; }
+    else if (s == "enc_ts") { src = reinterpret_cast<const float*>(m->enc_ts); n = 2 * ENC_TS_WORDS; }
     else if (s == "enc_flags") { src = reinterpret_cast<const float*>(m->enc_flags); n = ENC_FLAG_WORDS; }
     else if (s == "dec_prof") { src = reinterpret_cast<const float*>(m->dec_prof); n = 2 * 2 * 4096; }
     else if (s.size() == 4 && (s[0] == 'G' || s[0] == 'H' || s[0] == 'C' || s[0] == 'O') && s[1] == '_') {
