@@ -306,6 +306,184 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// =================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA PAIR (cluster of 2, two SMs of one TPC) computes a 256 x 256 tile.  Each CTA stages
+// its own 128 rows of A and its own 128 columns of B (32 KB per k-block instead of 32 KB for a 128 x 128 tile: twice the
+// FLOPs per byte moved into and read out of shared memory, which is what bounds the fp32-operand 1-CTA kernel), the leader
+// CTA's elected thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 8) for both tensor cores, and each CTA keeps
+// its 128 x 256 half of the fp32 accumulator in its own TMEM (double-buffered: all 512 columns).
+//   barriers:  full[s]       leader only; 1 arrival (the leader's expect_tx of BOTH CTAs' bytes), both CTAs' TMA complete on it
+//              empty[s]      per CTA; tcgen05.commit multicast to both CTAs when the MMAs that read the slot have retired
+//              tmem_full[b]  per CTA; commit multicast when a tile's accumulator is complete
+//              tmem_empty[b] leader only; 8 arrivals (4 epilogue warps x 2 CTAs, the peer's through mapa)
+// K-major or N-major B, K-major A; no split-K, no 3xTF32 (the 1-CTA kernel keeps those).
+constexpr int T2_BN = 256, T2_STAGES = 6;
+constexpr uint32_t T2_STAGE_BYTES = STAGE_A_BYTES + (T2_BN / 2) * TBK * 4;       // per CTA: 16 KB of A + 16 KB of B
+constexpr uint32_t T2_SMEM = T2_STAGES * T2_STAGE_BYTES + TC_STG_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync2() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair into its OWN shared memory, completing bytes on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <bool NB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + T2_STAGES * STAGE_A_BYTES;
+    float* stg_base = reinterpret_cast<float*>(smem + T2_STAGES * T2_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg_base) + TC_STG_BYTES);
+    uint64_t* full = bars;                       // [T2_STAGES]
+    uint64_t* empty = bars + T2_STAGES;          // [T2_STAGES]
+    uint64_t* tmem_full = bars + 2 * T2_STAGES;  // [2]
+    uint64_t* tmem_empty = bars + 2 * T2_STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int nkb = (p.K + TBK - 1) / TBK;
+    const int tiles_n = (p.N + T2_BN - 1) / T2_BN, tiles_m = (p.M + 2 * TBM - 1) / (2 * TBM);
+    const int ntiles = tiles_m * tiles_n;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {         // collective over the pair: warp 1 of both CTAs, same slot offset
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync2();         // both CTAs' barriers exist before any remote completion / arrival
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own 128 columns of B =====
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = pair; t < ntiles; t += npairs) {
+                const int m0 = (t / tiles_n) * (2 * TBM) + (int)rank * TBM;
+                const int n0 = (t % tiles_n) * T2_BN + (int)rank * (T2_BN / 2);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (leader) mbar_expect_tx(&full[s], 2 * T2_STAGE_BYTES);
+                    const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
+                    const int k0 = i * TBK;
+                    uint8_t* a = sA + s * STAGE_A_BYTES;
+                    uint8_t* b = sB + s * ((T2_BN / 2) * TBK * 4);
+                    tma_load_2d_pair(&mapA, lbar, a, k0, m0);                         // box {32 k, 128 m}
+                    if (!NB) tma_load_2d_pair(&mapB, lbar, b, k0, n0);                // box {32 k, 128 n}
+                    else
+#pragma unroll
+                        for (int j = 0; j < T2_BN / 2 / 32; ++j) tma_load_2d_pair(&mapB, lbar, b + j * (TBK * 128), n0 + 32 * j, k0);   // box {32 n, 32 k}
+                    if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's elected thread drives both tensor cores =====
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB ? 1u : 0u) << 16) |
+                                   ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)((2 * TBM) >> 4) << 24);
+            const uint64_t a_base = make_smem_desc(smem_u32(sA), 16, 1024, 2);
+            const uint64_t b_base = NB ? make_smem_desc(smem_u32(sB), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sB), 16, 1024, 2);
+            constexpr uint32_t a_kstep = 32 >> 4, b_kstep = (NB ? 1024 : 32) >> 4;
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int t = pair; t < ntiles; t += npairs, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc = tmem_base + buf * T2_BN;
+                mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ad0 = a_base + (uint64_t)(s * (STAGE_A_BYTES >> 4));
+                    const uint64_t bd0 = b_base + (uint64_t)(s * (((T2_BN / 2) * TBK * 4) >> 4));
+#pragma unroll
+                    for (int k = 0; k < TBK / 8; ++k)
+                        umma_tf32_pair(acc, ad0 + (uint64_t)(k * a_kstep), bd0 + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_pair(&empty[s]);
+                    if (++s == T2_STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_pair(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows x 256 columns =====
+        const int wq = warp & 3;
+        float* stg = stg_base + wq * (32 * 33);
+        int it = 0;
+        for (int t = pair; t < ntiles; t += npairs, ++it) {
+            const int m0 = (t / tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (t % tiles_n) * T2_BN;
+            const int buf = it & 1;
+            const uint32_t acc = tmem_base + buf * T2_BN + ((uint32_t)(wq * 32) << 16);
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < T2_BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(acc + c * 32, v);
+                if (c == T2_BN / 32 - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(smem_u32(&tmem_empty[buf]), 0)) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int n = n0 + c * 32 + lane;
+                if (n < p.N) {
+                    const float bv = p.bias ? p.bias[n] : 0.f;
+                    const int mrow0 = m0 + wq * 32;
+                    const int rmax = min(32, p.M - mrow0);
+                    float* cp = p.C + (size_t)mrow0 * p.ldc + n;
+                    for (int r = 0; r < rmax; ++r, cp += p.ldc) {
+                        const float x = stg[r * 33 + lane] + bv;
+                        *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync2();         // the peer may still be reading its accumulator / our barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -455,6 +633,38 @@ int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A,
     dim3 grid(std::max(1, std::min(cdiv(N, TBN) * cdiv(M, TBM), ctas)));
     if (tb) return launch_tc<false, false, false>(st, ma, mb, ma, mb, p, grid);
     return launch_tc<false, true, false>(st, ma, mb, ma, mb, p, grid);
+}
+
+// 2-CTA launch: returns 1 when the pair kernel does not apply (the caller then uses the 1-CTA kernel).
+template <bool NB>
+static int launch_tc2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int pairs) {
+    auto kern = gemm_tc2_kernel<NB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = T2_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+    ++g_kernel_launches;
+    return 0;
+}
+int gemm_tc2(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const float* bias, float beta) {
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    CUtensorMap ma, mb;
+    const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !okB) return 1;
+    TcParams p{M, N, K, C, ldc, bias, beta, 0, cdiv(K, TBK), 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    int cap = tc_num_sms() / 2;
+    if (g_tc_cta_cap > 0) cap = std::max(1, std::min(cap, g_tc_cta_cap / 2));
+    const int pairs = std::min(cdiv(M, 2 * TBM) * cdiv(N, T2_BN), cap);
+    return tb ? launch_tc2<false>(st, ma, mb, p, pairs) : launch_tc2<true>(st, ma, mb, p, pairs);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -1463,6 +1463,12 @@ int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V
 }
 int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
              float beta, float* C, int ldc, const float* bias, void* stream) {
+    if (which == -2) {  // the 2-CTA (cta_group::2) kernel
+        AST_CHECK(alpha == 1.f && ta == 0, "2-CTA tcgen05 GEMM: alpha = 1, K-major A only");
+        const int r = gemm_tc2(S_(stream), tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+        AST_CHECK(r <= 0, "2-CTA tcgen05 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+        return r;
+    }
     if (which >= 1) {   // 1: tcgen05 TF32, no split-K ; 2: automatic split-K ; >2: that many splits
         AST_CHECK(alpha == 1.f, "tcgen05 GEMM supports alpha = 1 only");
         const int r = gemm_tc(S_(stream), ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta,

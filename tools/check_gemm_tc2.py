@@ -1,0 +1,54 @@
+"""2-CTA (cta_group::2) tcgen05 TF32 GEMM vs fp64 reference and vs the 1-CTA kernel (time).  Usage: python tools/check_gemm_tc2.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ast_b200 import _lib                      # noqa: E402
+from ast_b200._lib import ptr                  # noqa: E402
+
+dev = torch.device("cuda", 0)
+lib = _lib.load()
+st = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+rng = np.random.default_rng(0)
+bad = 0
+for (tb, M, N, K) in [(1, 256, 256, 32), (1, 256, 256, 64), (1, 512, 512, 256), (1, 300, 200, 120), (1, 1000, 1024, 1536), (1, 5120, 1024, 1536),
+                      (0, 256, 256, 64), (0, 130, 260, 72), (0, 4000, 1536, 1024), (0, 1500, 1152, 512)]:
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    want = A.astype(np.float64) @ (B.T if tb else B).astype(np.float64) + bias
+    dA, dB, db = (torch.as_tensor(x, device=dev) for x in (A, B, bias))
+    dC = torch.full((M, N), 7.0, device=dev)
+    rc = lib.ast_gemm(-2, 0, tb, M, N, K, 1.0, ptr(dA), K, ptr(dB), B.shape[1], 0.0, ptr(dC), N, ptr(db), st())
+    torch.cuda.synchronize()
+    if rc != 0:
+        print(f"[FAIL] tb={tb} {M}x{N}x{K}: rc={rc} {lib.ast_last_error().decode()}"); bad += 1; continue
+    got = dC.cpu().numpy()
+    err = np.abs(got - want).max() / np.sqrt(K)
+    ok = err < 6e-3
+    bad += (not ok)
+    print(f"[{'ok' if ok else 'FAIL'}] 2-CTA gemm tb={tb} {M}x{N}x{K}: max err / sqrt(K) = {err:.2e}", flush=True)
+    if not ok:
+        d = np.abs(got - want)
+        print("     row-block errs", [float(d[r:r + 32].max()) for r in range(0, min(M, 512), 32)])
+        print("     col-block errs", [float(d[:, c:c + 32].max()) for c in range(0, min(N, 512), 32)])
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for (tb, M, N, K) in [(1, 5120, 1024, 1536), (0, 5120, 1536, 1024), (0, 15744, 1152, 512), (1, 8192, 4096, 4096)]:
+    A = torch.randn(M, K, device=dev); B = torch.randn((N, K) if tb else (K, N), device=dev)
+    Cc = torch.zeros(M, N, device=dev)
+    for w in (-2, 1):
+        ts = []
+        for it in range(8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lib.ast_gemm(w, 0, tb, M, N, K, 1.0, ptr(A), K, ptr(B), B.shape[1], 0.0, ptr(Cc), N, None, st())
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts[3:]))
+        print(f"  time tb={tb} {M}x{N}x{K} {'2-CTA' if w == -2 else '1-CTA'}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+print("FAILED" if bad else "ALL OK", bad)
