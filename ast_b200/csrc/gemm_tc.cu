@@ -464,7 +464,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
                 __syncwarp();
                 const int n = n0 + c * 32 + lane;
-                if (n < p.N) {
+                if (n < p.N && p.atomic != 2) {
                     const float bv = p.bias ? p.bias[n] : 0.f;
                     const int mrow0 = m0 + wq * 32;
                     const int rmax = min(32, p.M - mrow0);
@@ -660,7 +660,7 @@ int gemm_tc2(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int 
     CUtensorMap ma, mb;
     const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
     if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !okB) return 1;
-    TcParams p{M, N, K, C, ldc, bias, beta, 0, cdiv(K, TBK), 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    TcParams p{M, N, K, C, ldc, bias, beta, getenv("AST_TC2_NOSTORE") ? 2 : 0, cdiv(K, TBK), 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
     int cap = tc_num_sms() / 2;
     if (g_tc_cta_cap > 0) cap = std::max(1, std::min(cap, g_tc_cta_cap / 2));
     const int pairs = std::min(cdiv(M, 2 * TBM) * cdiv(N, T2_BN), cap);

@@ -95,7 +95,7 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0;
+    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 1;
     unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
@@ -304,6 +304,11 @@ enum { SITE_CONV0 = 0, SITE_CONV1 = 1, SITE_ENC_PROJ = 2, SITE_DEC_WGRAD = 3, SI
 static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
                 int ldb, float* C, int ldc, const float* bias, float beta, int split_k, int site) {
     if (m->tc_gemm && !m->exact && !((m->tc_mask >> site) & 1u)) {
+        // large K-major-A problems whose 256 x 256 pair tiles fill the GPU go to the 2-CTA kernel (layer-0 projection and data gradient)
+        if (m->tc2 && !ta && split_k == 0 && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= 60) {
+            const int r2 = gemm_tc2(st, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+            if (r2 <= 0) return r2;
+        }
         const int r = gemm_tc(st, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, split_k);
         if (r <= 0) return r;
     }
@@ -1183,6 +1188,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
     else if (!strcmp(key, "enc_ts")) m->enc_ts_on = (int)value;
+    else if (!strcmp(key, "tc2")) m->tc2 = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas")) m->enc_gemm_ctas = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas_bwd")) m->enc_gemm_ctas_bwd = (int)value;
     else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
