@@ -204,15 +204,44 @@ def roofline_dominant(engine, torch, peaks):
            "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms,
            "algorithmic_bytes": 4.0 * (M * K + K * N + M * N), "traffic": None, "traffic_unit": "bytes/launch"}
     out.update(NCU_GEMM if which == 1 else {})
+    if which == 1:
+        # the 2-CTA (cta_group::2, 256 x 256 pair tiles) kernel the library uses for the layer-0 projection / data gradient, at that
+        # shape and at a shape large enough to fill its pipeline: same measurement, same peak
+        others = []
+        for (tb, M2, N2, K2, what) in ((0, 5120, 1536, 1024, "encoder layer-0 data gradient (B32 x T640)"),
+                                       (1, 5120, 1024, 1536, "encoder layer-0 input projection (B32 x T640)"),
+                                       (1, 8192, 4096, 4096, "kernel ceiling: a GEMM large enough to fill the pipeline")):
+            A2 = torch.randn(M2, K2, device=dev); W2 = torch.randn((N2, K2) if tb else (K2, N2), device=dev); C2 = torch.empty(M2, N2, device=dev)
+            t2 = []
+            for it in range(7):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                check(lib.ast_gemm(-2, 0, tb, M2, N2, K2, 1.0, ptr(A2), K2, ptr(W2), W2.shape[1], 0.0, ptr(C2), N2, None, st), "ast_gemm 2-CTA")
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    t2.append(e0.elapsed_time(e1))
+            ms2 = float(np.mean(t2))
+            ach = 2.0 * M2 * N2 * K2 / (ms2 * 1e-3) / 1e12
+            others.append({"kernel": "gemm_tc2_kernel (tcgen05 TF32, cta_group::2)", "shape": f"M{M2} N{N2} K{K2} ({'NT' if tb else 'NN'}): {what}",
+                           "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "ms_per_launch": ms2})
+        out["other_kernels"] = others
+        out["other_kernels_ncu"] = NCU_GEMM2
     return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum and pipe counters of this kernel at this shape from the ncu --set full capture
 # (tools/ncu_capture.sh, extract under profiles/); filled in from the round's capture
-NCU_GEMM = {"traffic": 34.65e6 + 18.47e6,     # the 72.5 MB output is only partly written back within the kernel's lifetime (126 MB L2)
-            "ncu": {"gpu_time_us_cold": 54.9, "tensor_pipe_active_pct": 38.1, "tensor_pipe_elapsed_pct": 32.5,
-                    "l2_sector_pct_of_peak": 28.9, "l2_hit_rate_pct": 69.4, "smem_fill_bytes": 580.4e6,
-                    "source": "profiles/r01_ncu_full_extract_v18.txt"}}
+NCU_GEMM = {"traffic": 34.64e6 + 18.55e6,     # the 72.5 MB output is only partly written back within the kernel's lifetime (126 MB L2)
+            "ncu": {"gpu_time_us_cold": 56.5, "tensor_pipe_active_pct": 37.6, "tensor_pipe_elapsed_pct": 31.3,
+                    "l2_sector_pct_of_peak": 27.8, "l2_hit_rate_pct": 70.5, "smem_fill_bytes": 580.4e6,
+                    "source": "profiles/r01_ncu_full_extract_v26_gemm.txt"}}
+
+
+NCU_GEMM2 = {"M5120_N1536_K1024": {"gpu_time_us_cold": 36.3, "tensor_pipe_active_pct": 54.9, "tensor_pipe_elapsed_pct": 41.8, "dram_bytes": 27.3e6 + 0.5e6},
+             "M8192_N4096_K4096": {"gpu_time_us_cold": 346.2, "tensor_pipe_active_pct": 95.2, "tensor_pipe_elapsed_pct": 88.8, "dram_bytes": 623.3e6 + 117.7e6},
+             "source": "profiles/r01_ncu_full_extract_v26_gemm.txt"}
 
 
 def beam_rate(model, torch, T, n_utts, stop_limit, N=10, K=10):
