@@ -9,6 +9,10 @@ namespace ast {
 // ---- error plumbing (never throw across the C ABI) ------------------------------------
 void set_last_error(const char* fmt, ...);
 const char* get_last_error();
+// true when a tool that SERIALISES kernel execution is attached (Nsight Compute / compute-sanitizer found in /proc/self/maps, or
+// AST_NO_COOP / AST_NO_PERSIST set): kernels that wait for one another (persistent encoder wavefront) would deadlock, and ncu
+// rejects cooperative + cluster launches, so both fall back to their per-chunk / non-cooperative launch structure.
+bool kernels_are_serialised();
 extern unsigned long long g_kernel_launches;   // every kernel this library enqueues (bench.py gpu_launches)
 
 #define AST_CUDA_OK(expr)                                                                   \

@@ -966,8 +966,8 @@ static int launch_d2(KernT kern, cudaStream_t st, const DecSeq& p, size_t smem) 
     at[0].val.clusterDim.x = D2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
-    // AST_NO_COOP=1 (tools/ncu_capture.sh): ncu aborts on the rejected cooperative launch before the retry below can run
-    static const bool no_coop = getenv("AST_NO_COOP") != nullptr;
+    // under ncu (detected, or AST_NO_COOP=1): it aborts on the rejected cooperative launch before the retry below can run
+    static const bool no_coop = kernels_are_serialised();
     cfg.attrs = at; cfg.numAttrs = no_coop ? 1 : 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess && !no_coop) {

@@ -18,6 +18,22 @@ void set_last_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+bool kernels_are_serialised() {
+    static int state = -1;
+    if (state < 0) {
+        state = (getenv("AST_NO_COOP") != nullptr || getenv("AST_NO_PERSIST") != nullptr) ? 1 : 0;
+        if (!state) {
+            if (FILE* f = fopen("/proc/self/maps", "r")) {
+                char line[1024];
+                while (!state && fgets(line, sizeof line, f))
+                    if (strstr(line, "nsight-compute") || strstr(line, "libnvperf_target") || strstr(line, "compute-sanitizer") ||
+                        strstr(line, "libsanitizer-collection")) state = 1;
+                fclose(f);
+            }
+        }
+    }
+    return state == 1;
+}
 unsigned long long g_kernel_launches = 0;
 
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
@@ -354,13 +370,7 @@ static int require_ready(ast_model* m, int B, int T, int L, int N, int steps) {
     return 0;
 }
 
-// A profiler that serialises kernels (ncu) would deadlock kernels that wait for one another: the same switch that turns the
-// cooperative decoder launch off (tools/ncu_capture.sh) selects the per-chunk launches.
-static bool persist_allowed() {
-    static const bool off = getenv("AST_NO_COOP") != nullptr || getenv("AST_NO_PERSIST") != nullptr ||
-                            getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
-    return !off;
-}
+static bool persist_allowed() { return !kernels_are_serialised(); }
 
 // ------------------------------------------------------------------------------------------------
 // encoder forward (seq2seq.py:293-315)
