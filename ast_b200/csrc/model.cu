@@ -1211,6 +1211,8 @@ double ast_get_option(const ast_model* m, const char* key) {
     if (!strcmp(key, "exact")) return m->exact;
     if (!strcmp(key, "tc_gemm")) return m->tc_gemm;
     if (!strcmp(key, "dec_fused")) return m->dec_fused;
+    if (!strcmp(key, "beam_fused")) return m->beam_fused;
+    if (!strcmp(key, "enc_persist")) return m->enc_persist;
     if (!strcmp(key, "seed")) return (double)m->seed;
     return -1;
 }

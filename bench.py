@@ -267,6 +267,22 @@ def beam_rate(model, torch, T, n_utts, stop_limit, N=10, K=10):
             "N": N, "K": K, "us_per_beam_step": 1e6 * dt / max(steps, 1)}
 
 
+def beam_rate_pool(model, torch, T, n_utts, stop_limit, n_streams, N=10, K=10):
+    """Throughput mode: the same searches, `n_streams` independent utterances in flight (ast_b200.beam.BeamPool)."""
+    from ast_b200.beam import BeamPool
+    from ast_b200.nn import beam_result_to_entries
+    pool = BeamPool(model._engine, n=n_streams)
+    rng = np.random.default_rng(7)
+    utts = [rng.standard_normal((1, T, D), dtype=np.float32) for _ in range(n_utts)]
+    pool.decode(utts[:n_streams], stop_limit, N, K, convert=beam_result_to_entries)      # warm every replica
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = pool.decode(utts, stop_limit, N, K, convert=beam_result_to_entries)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert all(r is not None for r in res)
+    return {"utts_per_s": n_utts / dt, "T": T, "stop_limit": stop_limit, "n_utts": n_utts, "N": N, "K": K, "utterances_in_flight": n_streams}
+
+
 def beam_cpu_rate(T, stop_limit, n_utts=1, N=10, K=10):
     """The reference's beam search (nn.py:235-322 restated in the numpy oracle) on the host cores, same inputs."""
     from oracle import ast_oracle as O
@@ -429,7 +445,12 @@ def run_ours(args):
                         "random-init weights: every search runs stop_limit steps",
                         "T1000_175steps_worst_case": beam_rate(model, torch, 1000, 4, 175),
                         "T1000_40steps": beam_rate(model, torch, 1000, 12, 40),
-                        "T3000_40steps": beam_rate(model, torch, 3000, 6, 40)}
+                        "T3000_40steps": beam_rate(model, torch, 3000, 6, 40),
+                        "T1000_175steps_8_in_flight": beam_rate_pool(model, torch, 1000, 24, 175, 8),
+                        "T1000_40steps_8_in_flight": beam_rate_pool(model, torch, 1000, 32, 40, 8),
+                        "T3000_40steps_8_in_flight": beam_rate_pool(model, torch, 3000, 24, 40, 8),
+                        "in_flight_note": "ast_b200.beam.BeamPool: independent utterances decoded concurrently by engine replicas "
+                                          "(own streams / host threads), hypotheses identical to the sequential loop"}
         if not args.no_cpu_baseline:
             line["beam"]["cpu_baseline_T1000_40steps"] = beam_cpu_rate(1000, 40, 2)
     if cpu_rate is not None:

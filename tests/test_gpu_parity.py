@@ -413,6 +413,30 @@ def test_greedy_and_beam_hypotheses_identical(dev):
                 assert _relerr(np.stack(ent[0]["attn_history"]), np.stack(nb[0]["attn_history"])) < 1e-3
 
 
+def test_beam_pool_matches_sequential_decoding(dev):
+    """BeamPool (independent utterances decoded concurrently by engine replicas on their own streams / host threads) returns,
+    utterance by utterance, exactly what the sequential decode_beam loop returns - and that equals the oracle's search."""
+    from ast_b200.beam import BeamPool
+    from ast_b200.nn import beam_result_to_entries
+    cfg = O.default_model_cfg(vocab=200)
+    D = 40
+    P = O.init_params(cfg, D, seed=31)
+    P["out/b"][O.EOS_ID] += 1.2
+    rng = np.random.default_rng(32)
+    utts = [rng.standard_normal((1, int(T), D)).astype(np.float32) for T in (150, 97, 230, 64, 181, 120, 75)]
+    e = _engine(cfg, D, P)
+    seq = [beam_result_to_entries(e.beam_search(x, 25, 6, 5)) for x in utts]
+    pool = BeamPool(e, n=3)
+    for rep in range(2):
+        par = pool.decode(utts, 25, 6, 5, convert=beam_result_to_entries)
+        for a, b in zip(seq, par):
+            assert [h["hyp"] for h in a] == [h["hyp"] for h in b]
+            assert [float(h["score"]) for h in a] == [float(h["score"]) for h in b]
+    om = O.OracleModel(cfg, P, dtype=np.float32)
+    nb = om.decode_beam(utts[1], 25, 6, 5)
+    assert [h["hyp"] for h in par[1]] == [h["hyp"] for h in nb]
+
+
 def test_eval_mode_uses_running_statistics(dev):
     cfg = O.default_model_cfg(vocab=64)
     P = _perturbed(cfg, 40, 31)
