@@ -93,13 +93,16 @@ class BeamPool:
                         try:
                             i, x = jobs.get_nowait()
                         except queue.Empty:
-                            return
+                            break
                         r = e.beam_search(x, int(stop_limit), int(N), int(K), go, eos)
                         out[i] = convert(r) if convert else r
                     st.synchronize()
             except Exception as ex:     # surface in the caller
                 errs.append(ex)
 
+        # the utterances may still be in flight on other streams (e.g. the loader's pack stream): the workers' streams do not
+        # know about them
+        torch.cuda.synchronize(self.engines[0].device)
         ts = [threading.Thread(target=worker, args=(e, st)) for e, st in zip(self.engines, self.streams)]
         for t in ts:
             t.start()

@@ -623,6 +623,14 @@ def test_nn_runtime_trains_on_synthetic_corpus(dev, tmp_path):
     nb = nn.decode_beam(batch["X"], stop_limit=12, N=5, K=5)
     assert 1 <= len(nb) <= 5 and nb[0]["hyp"][0] == 1 and set(nb[0]) == {"hyp", "score", "dec_state", "attn_v", "attn_history"}
     assert all(nb[i]["score"] >= nb[i + 1]["score"] for i in range(len(nb) - 1))
+    # beam.py:105-124 over the whole set: sequential loop == 4 utterances in flight (BeamPool), then the rerank (beam.py:30-42)
+    from ast_b200.beam import decode_set, get_best_hyps
+    data_cfg["zero_input"] = 0          # the random frame dropping follows the SET NAME (dataloader.py:105-106), not the train flag
+    b1 = decode_set(nn, "fisher_train", 5, 5, stop_limit=12)
+    b4 = decode_set(nn, "fisher_train", 5, 5, stop_limit=12, in_flight=4)
+    assert b1.keys() == b4.keys() and len(b1) == 48
+    assert all([h[0] for h in b1[u]] == [h[0] for h in b4[u]] for u in b1)
+    assert get_best_hyps(b1, 0.6) == get_best_hyps(b4, 0.6)
     serializers.save_npz(str(tmp_path / "seq2seq_7.model"), nn.model)
     nn2 = NN(str(tmp_path), feat_dim=40, data_loader=loader, cfg=Cfg)
     assert nn2.max_epoch == 7 and torch.equal(nn2.model.out.W.data, nn.model.out.W.data)
