@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) bn_bwd_rnn_reduce_kernel(const float* __r
                                          const float* __restrict__ raw, const float* __restrict__ mean,
                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, double* __restrict__ stats, int B, int Fp, int Rs,
-                                         int Tp, int C, int rows_per_block) {
+                                         int Tp, int C, int rows_per_block, double* __restrict__ partials) {
     extern __shared__ float dyrow[];        // R floats
     const int R = C * Fp, TB = Tp * B;
     const int r0 = blockIdx.x * rows_per_block, r1 = min(TB, r0 + rows_per_block);
@@ -350,8 +350,25 @@ __global__ void __launch_bounds__(256) bn_bwd_rnn_reduce_kernel(const float* __r
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) {
         const int c = threadIdx.x + k * 256;
-        if (c < C) { atomicAdd(&stats[c], db[k]); atomicAdd(&stats[C + c], dg[k]); }
+        if (c < C) {
+            // 569 blocks x 2C double atomics onto 2C addresses serialised in L2 (most of this kernel's 83 us): per-block partial sums
+            // (coalesced stores) and one small summation kernel instead
+            if (partials) { partials[(size_t)blockIdx.x * 2 * C + c] = db[k]; partials[(size_t)blockIdx.x * 2 * C + C + c] = dg[k]; }
+            else { atomicAdd(&stats[c], db[k]); atomicAdd(&stats[C + c], dg[k]); }
+        }
     }
+}
+__global__ void bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nblocks; b += 4) {
+        s0 += partials[(size_t)b * n + i]; s1 += partials[(size_t)(b + 1) * n + i];
+        s2 += partials[(size_t)(b + 2) * n + i]; s3 += partials[(size_t)(b + 3) * n + i];
+    }
+    for (; b < nblocks; ++b) s0 += partials[(size_t)b * n + i];
+    stats[i] = (s0 + s1) + (s2 + s3);
 }
 
 // one CTA per (b, t in [0, Rs)): rows t >= T' are the junk rows of the padded segment and get zeros
@@ -392,14 +409,21 @@ __global__ void __launch_bounds__(128) bn_bwd_rnn_apply_kernel(const float* __re
 
 int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, const float* raw, float* dx,
                     const float* mean, const float* invstd, const float* gamma, const float* beta,
-                    double* stats, float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C) {
+                    double* stats, float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C, double* partials,
+                    int partial_blocks) {
     AST_CHECK((C * Fp) % 4 == 0 && C <= 1024, "bn_bwd_from_rnn: need C*F' %% 4 == 0 and C <= 1024");
-    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
     const int TB = Tp * B;
     const int rpb = std::max(1, cdiv(TB, 148 * 4));
+    const int nblk = cdiv(TB, rpb);
+    if (partials && nblk > partial_blocks) partials = nullptr;
+    if (!partials) AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
     const size_t smem = sizeof(float) * C * Fp;
-    bn_bwd_rnn_reduce_kernel<<<cdiv(TB, rpb), 256, smem, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, stats, B, Fp, Rs, Tp, C, rpb);
+    bn_bwd_rnn_reduce_kernel<<<nblk, 256, smem, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, stats, B, Fp, Rs, Tp, C, rpb, partials);
     AST_LAUNCH_OK();
+    if (partials) {
+        bn_partials_sum_kernel<<<cdiv(2 * C, 128), 128, 0, st>>>(partials, nblk, 2 * C, stats);
+        AST_LAUNCH_OK();
+    }
     bn_bwd_rnn_apply_kernel<<<B * Rs, 128, smem, st>>>(d_in, d_rev, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B, Fp,
                                                        Rs, Tp, C, (float)(1.0 / ((double)B * Fp * Tp)));
     AST_LAUNCH_OK();

@@ -51,7 +51,7 @@ int bn_relu_to_rnn(cudaStream_t st, const float* raw, float* rnn_in, float* rnn_
                    const float* invstd, const float* gamma, const float* beta, int B, int Fp, int Rs, int Tp, int C);
 int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, const float* raw, float* dx,
                     const float* mean, const float* invstd, const float* gamma, const float* beta, double* stats,
-                    float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C);
+                    float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C, double* partials, int partial_blocks);
 int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
                        const float* invstd, const float* gamma, const float* beta, double* stats, float* dgamma,
                        float* dbeta, int nseg, int T1, int S0, int pad, int C);

@@ -39,6 +39,7 @@ unsigned long long g_kernel_launches = 0;
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
 
+constexpr int BN_PART_BLOCKS = 640;   // per-block partial sums of bn_bwd_rnn_reduce (<= 148 * 4 + slack blocks)
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
 constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + 64;   // done | tiles
@@ -82,7 +83,7 @@ struct ast_model {
     // ---- buffers (valid after bind_workspace) ----
     float *a0p_hi, *a0p_lo, *W1p_hi, *W1p_lo; int conv3x = 1;   // 3xTF32 operands of the CNN_1 forward GEMM (split_tf32)
     float *cols0, *W0pad, *raw0, *a0p, *W1p, *raw1, *mean0, *invstd0, *mean1, *invstd1, *rnn_in, *rnn_rev, *Xn;
-    double *bnstats, *norm_sq;
+    double *bnstats, *norm_sq, *bnpart;
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
     float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
     float *encW, *encb;        // dec_seq2: enc_states . W_a and enc_states . b_a
@@ -218,6 +219,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->W1p_lo = a.get<float>((size_t)C1 * m->K1);
     m->raw1 = a.get<float>(M1 * C1);
     m->bnstats = a.get<double>(2 * (size_t)std::max(C0, C1));
+    m->bnpart = a.get<double>((size_t)BN_PART_BLOCKS * 2 * C1);
     m->norm_sq = a.get<double>(2);
     m->mean0 = a.get<float>(C0); m->invstd0 = a.get<float>(C0);
     m->mean1 = a.get<float>(C1); m->invstd1 = a.get<float>(C1);
@@ -1022,7 +1024,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // ---- CNN backward ------------------------------------------------------------------------------------
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs;
     AST_TRY(bn_bwd_from_rnn(st, m->d_rnn_in, m->d_rnn_rev, m->raw1, m->draw1, m->mean1, m->invstd1, m->p("CNN_1_bn/gamma"),
-                            m->p("CNN_1_bn/beta"), m->bnstats, m->g("CNN_1_bn/gamma"), m->g("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1));
+                            m->p("CNN_1_bn/beta"), m->bnstats, m->g("CNN_1_bn/gamma"), m->g("CNN_1_bn/beta"), B, Fp, Rs, Tp, C1, m->bnpart, BN_PART_BLOCKS));
     AST_TRY(fork());
     AST_TRY(gemm(m, sw, true, false, C1, m->K1, M1, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, m->dW1p, m->K1, nullptr, 0.f, -1, SITE_CONV1_WGRAD));
     AST_TRY(permute_w1(sw, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
