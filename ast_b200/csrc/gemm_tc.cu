@@ -316,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //              empty[s]      per CTA; tcgen05.commit multicast to both CTAs when the MMAs that read the slot have retired
 //              tmem_full[b]  per CTA; commit multicast when a tile's accumulator is complete
 //              tmem_empty[b] leader only; 8 arrivals (4 epilogue warps x 2 CTAs, the peer's through mapa)
-// K-major or N-major B, K-major A; no split-K, no 3xTF32 (the 1-CTA kernel keeps those).
+// All operand majors, split-K (weight gradients); no 3xTF32 (the 1-CTA kernel keeps that).
 constexpr int T2_BN = 256, T2_STAGES = 6;
 constexpr uint32_t T2_STAGE_BYTES = STAGE_A_BYTES + (T2_BN / 2) * TBK * 4;       // per CTA: 16 KB of A + 16 KB of B
 constexpr uint32_t T2_SMEM = T2_STAGES * T2_STAGE_BYTES + TC_STG_BYTES + 1024 + 256;
@@ -350,7 +350,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrive
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
-template <bool NB>
+template <bool TA, bool NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -368,9 +368,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int nkb = (p.K + TBK - 1) / TBK;
+    const int nkb_total = (p.K + TBK - 1) / TBK;
     const int tiles_n = (p.N + T2_BN - 1) / T2_BN, tiles_m = (p.M + 2 * TBM - 1) / (2 * TBM);
-    const int ntiles = tiles_m * tiles_n;
+    const int tiles_mn = tiles_m * tiles_n;
+    const int ntiles = tiles_mn * p.splits;      // split-K: (split, m-tile, n-tile), fp32 red.add into a zeroed C
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -393,16 +394,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int t = pair; t < ntiles; t += npairs) {
-                const int m0 = (t / tiles_n) * (2 * TBM) + (int)rank * TBM;
-                const int n0 = (t % tiles_n) * T2_BN + (int)rank * (T2_BN / 2);
+                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int m0 = (mn / tiles_n) * (2 * TBM) + (int)rank * TBM;
+                const int n0 = (mn % tiles_n) * T2_BN + (int)rank * (T2_BN / 2);
+                const int kb0 = z * p.kb_per_split;
+                const int nkb = min(p.kb_per_split, nkb_total - kb0);
                 for (int i = 0; i < nkb; ++i) {
                     mbar_wait(&empty[s], ph ^ 1);
                     if (leader) mbar_expect_tx(&full[s], 2 * T2_STAGE_BYTES);
                     const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
-                    const int k0 = i * TBK;
+                    const int k0 = (kb0 + i) * TBK;
                     uint8_t* a = sA + s * STAGE_A_BYTES;
                     uint8_t* b = sB + s * ((T2_BN / 2) * TBK * 4);
-                    tma_load_2d_pair(&mapA, lbar, a, k0, m0);                         // box {32 k, 128 m}
+                    if (!TA) tma_load_2d_pair(&mapA, lbar, a, k0, m0);                // box {32 k, 128 m}
+                    else
+#pragma unroll
+                        for (int j = 0; j < TBM / 32; ++j) tma_load_2d_pair(&mapA, lbar, a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
                     if (!NB) tma_load_2d_pair(&mapB, lbar, b, k0, n0);                // box {32 k, 128 n}
                     else
 #pragma unroll
@@ -414,14 +421,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer: the leader's elected thread drives both tensor cores =====
         if (leader && lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((NB ? 1u : 0u) << 16) |
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((NB ? 1u : 0u) << 16) |
                                    ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)((2 * TBM) >> 4) << 24);
-            const uint64_t a_base = make_smem_desc(smem_u32(sA), 16, 1024, 2);
+            const uint64_t a_base = TA ? make_smem_desc(smem_u32(sA), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sA), 16, 1024, 2);
             const uint64_t b_base = NB ? make_smem_desc(smem_u32(sB), TBK * 128, 512, 1) : make_smem_desc(smem_u32(sB), 16, 1024, 2);
-            constexpr uint32_t a_kstep = 32 >> 4, b_kstep = (NB ? 1024 : 32) >> 4;
+            constexpr uint32_t a_kstep = (TA ? 1024 : 32) >> 4, b_kstep = (NB ? 1024 : 32) >> 4;
             int s = 0; uint32_t ph = 0;
             int it = 0;
             for (int t = pair; t < ntiles; t += npairs, ++it) {
+                const int z = t / tiles_mn;
+                const int nkb = min(p.kb_per_split, nkb_total - z * p.kb_per_split);
                 const int buf = it & 1;
                 const uint32_t acc = tmem_base + buf * T2_BN;
                 mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -446,7 +455,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         float* stg = stg_base + wq * (32 * 33);
         int it = 0;
         for (int t = pair; t < ntiles; t += npairs, ++it) {
-            const int m0 = (t / tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (t % tiles_n) * T2_BN;
+            const int z = t / tiles_mn, mn = t - z * tiles_mn;
+            const int m0 = (mn / tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (mn % tiles_n) * T2_BN;
             const int buf = it & 1;
             const uint32_t acc = tmem_base + buf * T2_BN + ((uint32_t)(wq * 32) << 16);
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
@@ -465,13 +475,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
                 const int n = n0 + c * 32 + lane;
                 if (n < p.N && p.atomic != 2) {
-                    const float bv = p.bias ? p.bias[n] : 0.f;
+                    const float bv = (p.bias && z == 0) ? p.bias[n] : 0.f;
                     const int mrow0 = m0 + wq * 32;
                     const int rmax = min(32, p.M - mrow0);
                     float* cp = p.C + (size_t)mrow0 * p.ldc + n;
                     for (int r = 0; r < rmax; ++r, cp += p.ldc) {
                         const float x = stg[r * 33 + lane] + bv;
-                        *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
+                        if (p.atomic == 1) atomicAdd(cp, x);
+                        else *cp = (p.beta != 0.f) ? x + p.beta * (*cp) : x;
                     }
                 }
                 __syncwarp();
@@ -636,9 +647,9 @@ int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A,
 }
 
 // 2-CTA launch: returns 1 when the pair kernel does not apply (the caller then uses the 1-CTA kernel).
-template <bool NB>
+template <bool TA, bool NB>
 static int launch_tc2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int pairs) {
-    auto kern = gemm_tc2_kernel<NB>;
+    auto kern = gemm_tc2_kernel<TA, NB>;
     static bool attr_set = false;
     if (!attr_set) {
         AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
@@ -654,17 +665,37 @@ static int launch_tc2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
     ++g_kernel_launches;
     return 0;
 }
-int gemm_tc2(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-             const float* bias, float beta) {
+// split_k: 0 = none, -1 = automatic (one wave of CTA pairs, >= 8 k-blocks per split), > 0 = that many
+int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const float* bias, float beta, int split_k) {
     if (M <= 0 || N <= 0 || K <= 0) return 1;
     CUtensorMap ma, mb;
+    const bool okA = ta ? make_map(&ma, A, (uint64_t)M, (uint64_t)K, lda, 32, true) : make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false);
     const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
-    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) || !okB) return 1;
-    TcParams p{M, N, K, C, ldc, bias, beta, getenv("AST_TC2_NOSTORE") ? 2 : 0, cdiv(K, TBK), 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    if (!okA || !okB) return 1;
     int cap = tc_num_sms() / 2;
     if (g_tc_cta_cap > 0) cap = std::max(1, std::min(cap, g_tc_cta_cap / 2));
-    const int pairs = std::min(cdiv(M, 2 * TBM) * cdiv(N, T2_BN), cap);
-    return tb ? launch_tc2<false>(st, ma, mb, p, pairs) : launch_tc2<true>(st, ma, mb, p, pairs);
+    const int nkb = cdiv(K, TBK);
+    const int tiles = cdiv(M, 2 * TBM) * cdiv(N, T2_BN);
+    int splits = 1;
+    if (split_k != 0) {
+        splits = split_k > 0 ? split_k : std::max(1, std::min(nkb / 8, (tc_num_sms() / 2) / std::max(tiles, 1)));
+        splits = std::max(1, std::min(splits, nkb));
+    }
+    const int kbps = cdiv(nkb, splits);
+    splits = cdiv(nkb, kbps);
+    if (splits > 1) {
+        if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+        else if (beta != 1.f) return 1;
+    }
+    static const bool nostore = getenv("AST_TC2_NOSTORE") != nullptr;      // diagnostics: epilogue without its global stores
+    const int atomic = nostore ? 2 : (splits > 1 ? 1 : 0);
+    TcParams p{M, N, K, C, ldc, bias, beta, atomic, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    const int pairs = std::min(tiles * splits, cap);
+    if (!ta && tb) return launch_tc2<false, false>(st, ma, mb, p, pairs);
+    if (!ta && !tb) return launch_tc2<false, true>(st, ma, mb, p, pairs);
+    if (ta && !tb) return launch_tc2<true, true>(st, ma, mb, p, pairs);
+    return launch_tc2<true, false>(st, ma, mb, p, pairs);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -24,9 +24,9 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
 // kernel producing A counts its CTAs into wait[chunk] per chunk of `chunk` steps in its processing order (rev: from step T-1
 // down, and the m-tiles are then walked from the last one).  A tile's rows are read once wait[its chunk] >= target; every
 // finished tile adds 4 to done[m-tile of 128 rows].
-// 2-CTA (cta_group::2) 256 x 256 tiles, K-major A, no split-K: C = A . op(B) (+bias, + beta*C); returns 1 if it cannot take the operands
-int gemm_tc2(cudaStream_t st, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-             const float* bias, float beta);
+// 2-CTA (cta_group::2) 256 x 256 tiles, all operand majors, optional split-K (0 none, -1 automatic, > 0 count): C = A . op(B) (+bias, + beta*C); returns 1 if it cannot take the operands
+int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const float* bias, float beta, int split_k);
 void gemm_tc_set_cta_cap(int cap);   // 0 = no cap; applies to gemm_tc() launches issued afterwards by this thread's caller
 struct TcGate { const unsigned* wait; unsigned target; int B, chunk, T; bool rev; unsigned* done; };
 int gemm_tc_tiles_per_row(int N);

@@ -112,7 +112,7 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 1;
+    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 3;
     unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
@@ -324,7 +324,13 @@ static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, i
     if (m->tc_gemm && !m->exact && !((m->tc_mask >> site) & 1u)) {
         // large K-major-A problems whose 256 x 256 pair tiles fill the GPU go to the 2-CTA kernel (layer-0 projection and data gradient)
         if (m->tc2 && !ta && split_k == 0 && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= 60) {
-            const int r2 = gemm_tc2(st, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+            const int r2 = gemm_tc2(st, false, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, 0);
+            if (r2 <= 0) return r2;
+        }
+        // weight gradients (M-major A, huge K, small output): 256 x 256 pair tiles halve the operand traffic per FLOP and need a
+        // third of the split-K atomic passes of the 128 x 128 kernel
+        if ((m->tc2 & 2) && ta && split_k == -1 && M % 256 == 0 && N % 256 == 0 && K >= 1024) {
+            const int r2 = gemm_tc2(st, true, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, -1);
             if (r2 <= 0) return r2;
         }
         const int r = gemm_tc(st, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, split_k);
@@ -1483,9 +1489,15 @@ int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V
 }
 int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
              float beta, float* C, int ldc, const float* bias, void* stream) {
+    if (which == -3) {  // the 2-CTA kernel with automatic split-K
+        AST_CHECK(alpha == 1.f, "2-CTA tcgen05 GEMM supports alpha = 1 only");
+        const int r = gemm_tc2(S_(stream), ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, -1);
+        AST_CHECK(r <= 0, "2-CTA tcgen05 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
+        return r;
+    }
     if (which == -2) {  // the 2-CTA (cta_group::2) kernel
-        AST_CHECK(alpha == 1.f && ta == 0, "2-CTA tcgen05 GEMM: alpha = 1, K-major A only");
-        const int r = gemm_tc2(S_(stream), tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta);
+        AST_CHECK(alpha == 1.f, "2-CTA tcgen05 GEMM supports alpha = 1 only");
+        const int r = gemm_tc2(S_(stream), ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, 0);
         AST_CHECK(r <= 0, "2-CTA tcgen05 GEMM: unsupported problem M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
         return r;
     }

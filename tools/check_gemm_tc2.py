@@ -36,7 +36,36 @@ for (tb, M, N, K) in [(1, 256, 256, 32), (1, 256, 256, 64), (1, 512, 512, 256), 
         d = np.abs(got - want)
         print("     row-block errs", [float(d[r:r + 32].max()) for r in range(0, min(M, 512), 32)])
         print("     col-block errs", [float(d[:, c:c + 32].max()) for c in range(0, min(N, 512), 32)])
+# M-major A (weight-gradient form) and split-K
+for (tb, M, N, K, which) in [(0, 256, 256, 64, -2), (0, 512, 256, 1000, -2), (1, 256, 128, 64, -2), (0, 1024, 1536, 4000, -3), (0, 1024, 256, 5120, -3),
+                             (0, 1100, 520, 2000, -3), (1, 512, 512, 3000, -3)]:
+    A = rng.standard_normal((K, M)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    want = A.T.astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+    dA, dB = (torch.as_tensor(x, device=dev) for x in (A, B))
+    dC = torch.full((M, N), 7.0, device=dev)
+    rc = lib.ast_gemm(which, 1, tb, M, N, K, 1.0, ptr(dA), M, ptr(dB), B.shape[1], 0.0, ptr(dC), N, None, st())
+    torch.cuda.synchronize()
+    if rc != 0:
+        print(f"[FAIL] ta=1 tb={tb} {M}x{N}x{K}: rc={rc} {lib.ast_last_error().decode()}"); bad += 1; continue
+    err = np.abs(dC.cpu().numpy() - want).max() / np.sqrt(K)
+    ok = err < 6e-3
+    bad += (not ok)
+    print(f"[{'ok' if ok else 'FAIL'}] 2-CTA gemm ta=1 tb={tb} {M}x{N}x{K} {'split-K' if which == -3 else ''}: max err / sqrt(K) = {err:.2e}", flush=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for (M, N, K) in [(1024, 1536, 5120), (1024, 256, 5120), (512, 1152, 15744)]:
+    A = torch.randn(K, M, device=dev); B = torch.randn(K, N, device=dev); Cc = torch.zeros(M, N, device=dev)
+    for w in (-3, 2):
+        ts = []
+        for it in range(8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lib.ast_gemm(w, 1, 0, M, N, K, 1.0, ptr(A), M, ptr(B), N, 0.0, ptr(Cc), N, None, st())
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts[3:]))
+        print(f"  time TN split-K {M}x{N}x{K} {'2-CTA' if w == -3 else '1-CTA'}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 for (tb, M, N, K) in [(1, 5120, 1024, 1536), (0, 5120, 1536, 1024), (0, 15744, 1152, 512), (1, 8192, 4096, 4096)]:
     A = torch.randn(M, K, device=dev); B = torch.randn((N, K) if tb else (K, N), device=dev)
     Cc = torch.zeros(M, N, device=dev)
