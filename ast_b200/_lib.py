@@ -66,6 +66,7 @@ SIGNATURES = {
     "ast_pack_cmvn": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _ULL, _P, _I, _I, _I, _P]),
     "ast_softmax_ce": (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     "ast_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _P]),
+    "ast_gemm_grouped": (_I, [_I, _I, _I, _I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _LL, _I, _I, _P]),
     "ast_lstm_probe": (_I, [_P]),
     "ast_stage_times": (_I, [_P, _P, _P, _I, _I]),
     "ast_split_tf32": (_I, [_P, _P, _P, _LL, _P]),

@@ -350,9 +350,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrive
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// Up to T2_MAXG same-shape problems in one launch ("grouped"): the tile space becomes (problem, split, m-tile, n-tile).  The encoder's
+// ten 1024 x 256 x (T'B) weight gradients have four 256 x 256 tiles each: alone they need ~18 K-splits to fill the GPU (9 k-blocks
+// per CTA, 18 atomic passes over the output); four at a time need 4-5.
+constexpr int T2_MAXG = 4;
+struct Tc2Maps { CUtensorMap a[T2_MAXG]; CUtensorMap b[T2_MAXG]; };
+struct Tc2Group { int n; float* C[T2_MAXG]; };
+
 template <bool TA, bool NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, TcParams p, Tc2Group grp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -371,7 +378,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int nkb_total = (p.K + TBK - 1) / TBK;
     const int tiles_n = (p.N + T2_BN - 1) / T2_BN, tiles_m = (p.M + 2 * TBM - 1) / (2 * TBM);
     const int tiles_mn = tiles_m * tiles_n;
-    const int ntiles = tiles_mn * p.splits;      // split-K: (split, m-tile, n-tile), fp32 red.add into a zeroed C
+    const int tiles_p = tiles_mn * p.splits;     // split-K: (split, m-tile, n-tile), fp32 red.add into a zeroed C
+    const int ntiles = tiles_p * grp.n;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -394,7 +402,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int t = pair; t < ntiles; t += npairs) {
-                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int g = t / tiles_p, tp = t - g * tiles_p;
+                const CUtensorMap* mapA = &maps.a[g];
+                const CUtensorMap* mapB = &maps.b[g];
+                const int z = tp / tiles_mn, mn = tp - z * tiles_mn;
                 const int m0 = (mn / tiles_n) * (2 * TBM) + (int)rank * TBM;
                 const int n0 = (mn % tiles_n) * T2_BN + (int)rank * (T2_BN / 2);
                 const int kb0 = z * p.kb_per_split;
@@ -406,14 +417,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const int k0 = (kb0 + i) * TBK;
                     uint8_t* a = sA + s * STAGE_A_BYTES;
                     uint8_t* b = sB + s * ((T2_BN / 2) * TBK * 4);
-                    if (!TA) tma_load_2d_pair(&mapA, lbar, a, k0, m0);                // box {32 k, 128 m}
+                    if (!TA) tma_load_2d_pair(mapA, lbar, a, k0, m0);                // box {32 k, 128 m}
                     else
 #pragma unroll
-                        for (int j = 0; j < TBM / 32; ++j) tma_load_2d_pair(&mapA, lbar, a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
-                    if (!NB) tma_load_2d_pair(&mapB, lbar, b, k0, n0);                // box {32 k, 128 n}
+                        for (int j = 0; j < TBM / 32; ++j) tma_load_2d_pair(mapA, lbar, a + j * (TBK * 128), m0 + 32 * j, k0);   // box {32 m, 32 k}
+                    if (!NB) tma_load_2d_pair(mapB, lbar, b, k0, n0);                // box {32 k, 128 n}
                     else
 #pragma unroll
-                        for (int j = 0; j < T2_BN / 2 / 32; ++j) tma_load_2d_pair(&mapB, lbar, b + j * (TBK * 128), n0 + 32 * j, k0);   // box {32 n, 32 k}
+                        for (int j = 0; j < T2_BN / 2 / 32; ++j) tma_load_2d_pair(mapB, lbar, b + j * (TBK * 128), n0 + 32 * j, k0);   // box {32 n, 32 k}
                     if (++s == T2_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -429,7 +440,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int s = 0; uint32_t ph = 0;
             int it = 0;
             for (int t = pair; t < ntiles; t += npairs, ++it) {
-                const int z = t / tiles_mn;
+                const int z = (t % tiles_p) / tiles_mn;
                 const int nkb = min(p.kb_per_split, nkb_total - z * p.kb_per_split);
                 const int buf = it & 1;
                 const uint32_t acc = tmem_base + buf * T2_BN;
@@ -455,7 +466,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         float* stg = stg_base + wq * (32 * 33);
         int it = 0;
         for (int t = pair; t < ntiles; t += npairs, ++it) {
-            const int z = t / tiles_mn, mn = t - z * tiles_mn;
+            const int g = t / tiles_p, tp = t - g * tiles_p;
+            float* Cg = grp.C[g];
+            const int z = tp / tiles_mn, mn = tp - z * tiles_mn;
             const int m0 = (mn / tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (mn % tiles_n) * T2_BN;
             const int buf = it & 1;
             const uint32_t acc = tmem_base + buf * T2_BN + ((uint32_t)(wq * 32) << 16);
@@ -478,7 +491,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const float bv = (p.bias && z == 0) ? p.bias[n] : 0.f;
                     const int mrow0 = m0 + wq * 32;
                     const int rmax = min(32, p.M - mrow0);
-                    float* cp = p.C + (size_t)mrow0 * p.ldc + n;
+                    float* cp = Cg + (size_t)mrow0 * p.ldc + n;
                     for (int r = 0; r < rmax; ++r, cp += p.ldc) {
                         const float x = stg[r * 33 + lane] + bv;
                         if (p.atomic == 1) atomicAdd(cp, x);
@@ -648,7 +661,7 @@ int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A,
 
 // 2-CTA launch: returns 1 when the pair kernel does not apply (the caller then uses the 1-CTA kernel).
 template <bool TA, bool NB>
-static int launch_tc2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int pairs) {
+static int launch_tc2(cudaStream_t st, const Tc2Maps& maps, const TcParams& p, const Tc2Group& grp, int pairs) {
     auto kern = gemm_tc2_kernel<TA, NB>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -661,41 +674,52 @@ static int launch_tc2(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap&
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+    AST_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, p, grp));
     ++g_kernel_launches;
     return 0;
 }
-// split_k: 0 = none, -1 = automatic (one wave of CTA pairs, >= 8 k-blocks per split), > 0 = that many
-int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-             const float* bias, float beta, int split_k) {
-    if (M <= 0 || N <= 0 || K <= 0) return 1;
-    CUtensorMap ma, mb;
-    const bool okA = ta ? make_map(&ma, A, (uint64_t)M, (uint64_t)K, lda, 32, true) : make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false);
-    const bool okB = tb ? make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&mb, B, (uint64_t)N, (uint64_t)K, ldb, 32, true);
-    if (!okA || !okB) return 1;
+// n same-shape problems C[g] = op(A[g]) . op(B[g]) in one launch (n = 1: the plain GEMM).  split_k: 0 = none, -1 = automatic (one
+// wave of CTA pairs, >= 8 k-blocks per split), > 0 = that many.  bias applies to every problem.
+int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int K, const float* const* A, int lda, const float* const* B, int ldb,
+                     float* const* C, int ldc, const float* bias, float beta, int split_k) {
+    if (M <= 0 || N <= 0 || K <= 0 || n < 1 || n > T2_MAXG) return 1;
+    Tc2Maps maps;
+    Tc2Group grp{};
+    grp.n = n;
+    for (int g = 0; g < T2_MAXG; ++g) {
+        const int q = g < n ? g : 0;
+        const bool okA = ta ? make_map(&maps.a[g], A[q], (uint64_t)M, (uint64_t)K, lda, 32, true) : make_map(&maps.a[g], A[q], (uint64_t)K, (uint64_t)M, lda, TBM, false);
+        const bool okB = tb ? make_map(&maps.b[g], B[q], (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&maps.b[g], B[q], (uint64_t)N, (uint64_t)K, ldb, 32, true);
+        if (!okA || !okB) return 1;
+        grp.C[g] = C[q];
+    }
     int cap = tc_num_sms() / 2;
     if (g_tc_cta_cap > 0) cap = std::max(1, std::min(cap, g_tc_cta_cap / 2));
     const int nkb = cdiv(K, TBK);
     const int tiles = cdiv(M, 2 * TBM) * cdiv(N, T2_BN);
     int splits = 1;
     if (split_k != 0) {
-        splits = split_k > 0 ? split_k : std::max(1, std::min(nkb / 8, (tc_num_sms() / 2) / std::max(tiles, 1)));
+        splits = split_k > 0 ? split_k : std::max(1, std::min(nkb / 8, (tc_num_sms() / 2) / std::max(tiles * n, 1)));
         splits = std::max(1, std::min(splits, nkb));
     }
     const int kbps = cdiv(nkb, splits);
     splits = cdiv(nkb, kbps);
     if (splits > 1) {
-        if (beta == 0.f) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+        if (beta == 0.f) { for (int g = 0; g < n; ++g) AST_CUDA_OK(cudaMemset2DAsync(C[g], sizeof(float) * ldc, 0, sizeof(float) * N, M, st)); }
         else if (beta != 1.f) return 1;
     }
     static const bool nostore = getenv("AST_TC2_NOSTORE") != nullptr;      // diagnostics: epilogue without its global stores
     const int atomic = nostore ? 2 : (splits > 1 ? 1 : 0);
-    TcParams p{M, N, K, C, ldc, bias, beta, atomic, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
-    const int pairs = std::min(tiles * splits, cap);
-    if (!ta && tb) return launch_tc2<false, false>(st, ma, mb, p, pairs);
-    if (!ta && !tb) return launch_tc2<false, true>(st, ma, mb, p, pairs);
-    if (ta && !tb) return launch_tc2<true, true>(st, ma, mb, p, pairs);
-    return launch_tc2<true, false>(st, ma, mb, p, pairs);
+    TcParams p{M, N, K, C[0], ldc, bias, beta, atomic, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    const int pairs = std::min(tiles * splits * n, cap);
+    if (!ta && tb) return launch_tc2<false, false>(st, maps, p, grp, pairs);
+    if (!ta && !tb) return launch_tc2<false, true>(st, maps, p, grp, pairs);
+    if (ta && !tb) return launch_tc2<true, true>(st, maps, p, grp, pairs);
+    return launch_tc2<true, false>(st, maps, p, grp, pairs);
+}
+int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const float* bias, float beta, int split_k) {
+    return gemm_tc2_grouped(st, 1, ta, tb, M, N, K, &A, lda, &B, ldb, &C, ldc, bias, beta, split_k);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -27,6 +27,9 @@ int gemm_tc(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float*
 // 2-CTA (cta_group::2) 256 x 256 tiles, all operand majors, optional split-K (0 none, -1 automatic, > 0 count): C = A . op(B) (+bias, + beta*C); returns 1 if it cannot take the operands
 int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, float beta, int split_k);
+// up to 4 same-shape problems in one 2-CTA launch (tile space: problem x split x m x n)
+int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int K, const float* const* A, int lda, const float* const* B, int ldb,
+                     float* const* C, int ldc, const float* bias, float beta, int split_k);
 void gemm_tc_set_cta_cap(int cap);   // 0 = no cap; applies to gemm_tc() launches issued afterwards by this thread's caller
 struct TcGate { const unsigned* wait; unsigned target; int B, chunk, T; bool rev; unsigned* done; };
 int gemm_tc_tiles_per_row(int N);

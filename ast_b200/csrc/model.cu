@@ -112,7 +112,7 @@ struct ast_model {
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
-    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 3;
+    unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 7;      // bit 0: 2-CTA GEMM for large K-major-A problems, 1: for weight gradients, 2: grouped weight gradients
     unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
@@ -329,7 +329,7 @@ static int gemm(ast_model* m, cudaStream_t st, bool ta, bool tb, int M, int N, i
         }
         // weight gradients (M-major A, huge K, small output): 256 x 256 pair tiles halve the operand traffic per FLOP and need a
         // third of the split-K atomic passes of the 128 x 128 kernel
-        if ((m->tc2 & 2) && ta && split_k == -1 && M % 256 == 0 && N % 256 == 0 && K >= 1024) {
+        if ((m->tc2 & 2) && ta && split_k == -1 && M % 256 == 0 && (N % 256 == 0 || N >= 1024) && K >= 1024) {
             const int r2 = gemm_tc2(st, true, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, beta, -1);
             if (r2 <= 0) return r2;
         }
@@ -925,13 +925,29 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     auto enc_wgrads_range = [&](int l, int t0, int tn, bool first) -> int {
         const size_t r0 = (size_t)t0 * B;
         const float beta = first ? 0.f : 1.f;
+        // the 1024 x 256 x (T'B) problems of a layer (lateral both directions; upward too above layer 0) as ONE grouped 2-CTA launch
+        bool grouped_lat = false, grouped_up = false;
+        if (m->tc_gemm && !m->exact && (m->tc2 & 4) && !((m->tc_mask >> SITE_ENC_WGRAD) & 1u) && (4 * h) % 256 == 0 && h % 256 == 0 && tn * B >= 1024) {
+            const float* Ag[4]; const float* Bg[4]; float* Cg[4];
+            int n = 0;
+            const bool with_up = l > 0 && m->in_enc(l) == h;
+            for (int d = 0; d < 2; ++d) {
+                const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+                const float* dG = m->Genc[l][d] + r0 * 4 * h;
+                Ag[n] = dG; Bg[n] = m->Hs[l][d] + r0 * h; Cg[n] = m->g((ln + "/lateral/W").c_str()); ++n;
+                if (with_up) { Ag[n] = dG; Bg[n] = m->Hd[l - 1][d] + r0 * h; Cg[n] = m->g((ln + "/upward/W").c_str()); ++n; }
+            }
+            const int r = gemm_tc2_grouped(sw, n, true, false, 4 * h, h, tn * B, Ag, 4 * h, Bg, h, Cg, h, nullptr, beta, -1);
+            if (r < 0) return r;
+            if (r == 0) { grouped_lat = true; grouped_up = with_up; }
+        }
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
             const float* dG = m->Genc[l][d] + r0 * 4 * h;
-            AST_TRY(gemm(m, sw, true, false, 4 * h, in, tn * B, dG, 4 * h, xin + r0 * in, in, m->g((ln + "/upward/W").c_str()), in, nullptr, beta, -1, SITE_ENC_WGRAD));
-            AST_TRY(gemm(m, sw, true, false, 4 * h, h, tn * B, dG, 4 * h, m->Hs[l][d] + r0 * h, h, m->g((ln + "/lateral/W").c_str()), h, nullptr, beta, -1, SITE_ENC_WGRAD));
+            if (!grouped_up) AST_TRY(gemm(m, sw, true, false, 4 * h, in, tn * B, dG, 4 * h, xin + r0 * in, in, m->g((ln + "/upward/W").c_str()), in, nullptr, beta, -1, SITE_ENC_WGRAD));
+            if (!grouped_lat) AST_TRY(gemm(m, sw, true, false, 4 * h, h, tn * B, dG, 4 * h, m->Hs[l][d] + r0 * h, h, m->g((ln + "/lateral/W").c_str()), h, nullptr, beta, -1, SITE_ENC_WGRAD));
             AST_TRY(colsum(sw, dG, 4 * h, m->g((ln + "/upward/b").c_str()), tn * B, 4 * h, !first));
         }
         return 0;
@@ -1509,6 +1525,15 @@ int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const 
         return r;
     }
     return sgemm_simt(S_(stream), ta != 0, tb != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+}
+int ast_gemm_grouped(int n, int ta, int tb, int M, int N, int K, const float* A, long long strideA, int lda, const float* B, long long strideB,
+                     int ldb, float* C, long long strideC, int ldc, int split_k, void* stream) {
+    AST_CHECK(n >= 1 && n <= 4, "ast_gemm_grouped: 1..4 problems");
+    const float* Ag[4]; const float* Bg[4]; float* Cg[4];
+    for (int g = 0; g < n; ++g) { Ag[g] = A + g * strideA; Bg[g] = B + g * strideB; Cg[g] = C + g * strideC; }
+    const int r = gemm_tc2_grouped(S_(stream), n, ta != 0, tb != 0, M, N, K, Ag, lda, Bg, ldb, Cg, ldc, nullptr, 0.f, split_k);
+    AST_CHECK(r <= 0, "grouped 2-CTA GEMM: unsupported problem M=%d N=%d K=%d", M, N, K);
+    return r;
 }
 int ast_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) { return split_tf32(S_(stream), x, hi, lo, (size_t)n); }
 int ast_gemm3_nt(int M, int N, int K, const float* A, float* Ahi, float* Alo, long long a_floats, int lda, const float* B, float* Bhi,

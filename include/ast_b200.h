@@ -128,6 +128,10 @@ int ast_softmax_ce(float* logits_inout, int ld, const int* targets, int B, int V
 /* C = alpha*op(A)op(B) + beta*C + bias ; which: 0 = fp32 SIMT, 1 = tcgen05 TF32 (NT only) */
 int ast_gemm(int which, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
              int ldb, float beta, float* C, int ldc, const float* bias, void* stream);
+/* test hook: n (1..4) same-shape problems in one 2-CTA launch; problem g uses A + g*strideA, B + g*strideB, C + g*strideC;
+ * split_k: 0 none, -1 automatic, > 0 count */
+int ast_gemm_grouped(int n, int ta, int tb, int M, int N, int K, const float* A, long long strideA, int lda, const float* B,
+                     long long strideB, int ldb, float* C, long long strideC, int ldc, int split_k, void* stream);
 /* fp32-faithful tensor-core GEMM, C = A . B^T + bias (A: M x K, B: N x K, both k-contiguous): 3xTF32 on tcgen05
    (hi.hi + lo.hi + hi.lo with hi = rna_tf32(v), lo = rna_tf32(v - hi)).  Ahi/Alo, Bhi/Blo are scratch buffers of A's / B's
    size, filled by the call (ast_split_tf32).  Replaces the cuDNN convolution forward of CNN_1 (seq2seq.py:165) as an

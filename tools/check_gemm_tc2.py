@@ -52,7 +52,34 @@ for (tb, M, N, K, which) in [(0, 256, 256, 64, -2), (0, 512, 256, 1000, -2), (1,
     ok = err < 6e-3
     bad += (not ok)
     print(f"[{'ok' if ok else 'FAIL'}] 2-CTA gemm ta=1 tb={tb} {M}x{N}x{K} {'split-K' if which == -3 else ''}: max err / sqrt(K) = {err:.2e}", flush=True)
+# grouped: n same-shape problems in one launch
+for (n, ta, tb, M, N, K, sk) in [(4, 1, 0, 1024, 256, 5120, -1), (2, 1, 0, 1024, 256, 3000, -1), (3, 0, 1, 512, 256, 640, 0), (4, 1, 0, 512, 256, 2048, 3)]:
+    A = rng.standard_normal((n, K, M) if ta else (n, M, K)).astype(np.float32)
+    B = rng.standard_normal((n, N, K) if tb else (n, K, N)).astype(np.float32)
+    want = np.stack([(A[g].T if ta else A[g]).astype(np.float64) @ (B[g].T if tb else B[g]).astype(np.float64) for g in range(n)])
+    dA, dB = torch.as_tensor(A, device=dev), torch.as_tensor(B, device=dev)
+    dC = torch.full((n, M, N), 7.0, device=dev)
+    rc = lib.ast_gemm_grouped(n, ta, tb, M, N, K, ptr(dA), A[0].size, A.shape[2], ptr(dB), B[0].size, B.shape[2], ptr(dC), M * N, N, sk, st())
+    torch.cuda.synchronize()
+    if rc != 0:
+        print(f"[FAIL] grouped n={n}: rc={rc} {lib.ast_last_error().decode()}"); bad += 1; continue
+    err = np.abs(dC.cpu().numpy() - want).max() / np.sqrt(K)
+    ok = err < 6e-3
+    bad += (not ok)
+    print(f"[{'ok' if ok else 'FAIL'}] grouped 2-CTA gemm n={n} ta={ta} tb={tb} {M}x{N}x{K} split_k={sk}: max err / sqrt(K) = {err:.2e}", flush=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+A4 = torch.randn(4, 5120, 1024, device=dev); B4 = torch.randn(4, 5120, 256, device=dev); C4 = torch.zeros(4, 1024, 256, device=dev)
+for n in (4, 2):
+    ts = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.ast_gemm_grouped(n, 1, 0, 1024, 256, 5120, ptr(A4), 5120 * 1024, 1024, ptr(B4), 5120 * 256, 256, ptr(C4), 1024 * 256, 256, -1, st())
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts[3:]))
+    print(f"  time grouped TN split-K {n} x 1024x256x5120: {ms*1e3:.1f} us  {n*2.0*1024*256*5120/ms/1e9:.1f} TFLOP/s ({ms*1e3/n:.1f} us per problem)", flush=True)
 for (M, N, K) in [(1024, 1536, 5120), (1024, 256, 5120), (512, 1152, 15744)]:
     A = torch.randn(K, M, device=dev); B = torch.randn(K, N, device=dev); Cc = torch.zeros(M, N, device=dev)
     for w in (-3, 2):
