@@ -355,7 +355,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrive
 // per CTA, 18 atomic passes over the output); four at a time need 4-5.
 constexpr int T2_MAXG = 4;
 struct Tc2Maps { CUtensorMap a[T2_MAXG]; CUtensorMap b[T2_MAXG]; };
-struct Tc2Group { int n; float* C[T2_MAXG]; };
+struct Tc2Group { int n; float* C[T2_MAXG]; const float* bias[T2_MAXG]; };
 
 template <bool TA, bool NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -468,6 +468,7 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, TcParams p, Tc2Group grp) 
         for (int t = pair; t < ntiles; t += npairs, ++it) {
             const int g = t / tiles_p, tp = t - g * tiles_p;
             float* Cg = grp.C[g];
+            const float* biasg = grp.bias[g];
             const int z = tp / tiles_mn, mn = tp - z * tiles_mn;
             const int m0 = (mn / tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (mn % tiles_n) * T2_BN;
             const int buf = it & 1;
@@ -488,7 +489,7 @@ gemm_tc2_kernel(const __grid_constant__ Tc2Maps maps, TcParams p, Tc2Group grp) 
                 __syncwarp();
                 const int n = n0 + c * 32 + lane;
                 if (n < p.N && p.atomic != 2) {
-                    const float bv = (p.bias && z == 0) ? p.bias[n] : 0.f;
+                    const float bv = (biasg && z == 0) ? biasg[n] : 0.f;
                     const int mrow0 = m0 + wq * 32;
                     const int rmax = min(32, p.M - mrow0);
                     float* cp = Cg + (size_t)mrow0 * p.ldc + n;
@@ -679,9 +680,9 @@ static int launch_tc2(cudaStream_t st, const Tc2Maps& maps, const TcParams& p, c
     return 0;
 }
 // n same-shape problems C[g] = op(A[g]) . op(B[g]) in one launch (n = 1: the plain GEMM).  split_k: 0 = none, -1 = automatic (one
-// wave of CTA pairs, >= 8 k-blocks per split), > 0 = that many.  bias applies to every problem.
+// wave of CTA pairs, >= 8 k-blocks per split), > 0 = that many.  bias[g] (or null) per problem.
 int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int K, const float* const* A, int lda, const float* const* B, int ldb,
-                     float* const* C, int ldc, const float* bias, float beta, int split_k) {
+                     float* const* C, int ldc, const float* const* bias, float beta, int split_k) {
     if (M <= 0 || N <= 0 || K <= 0 || n < 1 || n > T2_MAXG) return 1;
     Tc2Maps maps;
     Tc2Group grp{};
@@ -692,6 +693,7 @@ int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int
         const bool okB = tb ? make_map(&maps.b[g], B[q], (uint64_t)K, (uint64_t)N, ldb, T2_BN / 2, false) : make_map(&maps.b[g], B[q], (uint64_t)N, (uint64_t)K, ldb, 32, true);
         if (!okA || !okB) return 1;
         grp.C[g] = C[q];
+        grp.bias[g] = bias ? bias[q] : nullptr;
     }
     int cap = tc_num_sms() / 2;
     if (g_tc_cta_cap > 0) cap = std::max(1, std::min(cap, g_tc_cta_cap / 2));
@@ -710,7 +712,7 @@ int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int
     }
     static const bool nostore = getenv("AST_TC2_NOSTORE") != nullptr;      // diagnostics: epilogue without its global stores
     const int atomic = nostore ? 2 : (splits > 1 ? 1 : 0);
-    TcParams p{M, N, K, C[0], ldc, bias, beta, atomic, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    TcParams p{M, N, K, C[0], ldc, nullptr, beta, atomic, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
     const int pairs = std::min(tiles * splits * n, cap);
     if (!ta && tb) return launch_tc2<false, false>(st, maps, p, grp, pairs);
     if (!ta && !tb) return launch_tc2<false, true>(st, maps, p, grp, pairs);
@@ -719,7 +721,7 @@ int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int
 }
 int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, float beta, int split_k) {
-    return gemm_tc2_grouped(st, 1, ta, tb, M, N, K, &A, lda, &B, ldb, &C, ldc, bias, beta, split_k);
+    return gemm_tc2_grouped(st, 1, ta, tb, M, N, K, &A, lda, &B, ldb, &C, ldc, bias ? &bias : nullptr, beta, split_k);
 }
 
 int gemm_tc_nt(cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,

@@ -29,7 +29,7 @@ int gemm_tc2(cudaStream_t st, bool ta, bool tb, int M, int N, int K, const float
              const float* bias, float beta, int split_k);
 // up to 4 same-shape problems in one 2-CTA launch (tile space: problem x split x m x n)
 int gemm_tc2_grouped(cudaStream_t st, int n, bool ta, bool tb, int M, int N, int K, const float* const* A, int lda, const float* const* B, int ldb,
-                     float* const* C, int ldc, const float* bias, float beta, int split_k);
+                     float* const* C, int ldc, const float* const* bias, float beta, int split_k);
 void gemm_tc_set_cta_cap(int cap);   // 0 = no cap; applies to gemm_tc() launches issued afterwards by this thread's caller
 struct TcGate { const unsigned* wait; unsigned target; int B, chunk, T; bool rev; unsigned* done; };
 int gemm_tc_tiles_per_row(int N);

@@ -504,7 +504,17 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         cudaEvent_t* ev = m->ev_pool;
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
-        AST_TRY(project(0, 0, Tp, st));
+        {   // both directions in one grouped 2-CTA launch: 2 x 80 pair tiles are 3 waves of 74 pairs, two separate launches are 4
+            const float* Ag[2] = {m->rnn_in, m->rnn_rev};
+            const float* Bg[2] = {m->p("L0_enc/upward/W"), m->p("L0_rev_enc/upward/W")};
+            const float* bg[2] = {m->p("L0_enc/upward/b"), m->p("L0_rev_enc/upward/b")};
+            float* Cg[2] = {m->Genc[0][0], m->Genc[0][1]};
+            int r = 1;
+            if ((m->tc2 & 1) && (4 * h) % 256 == 0 && !((m->tc_mask >> SITE_ENC_PROJ) & 1u))
+                r = gemm_tc2_grouped(st, 2, false, true, Tp * B, 4 * h, m->in_enc(0), Ag, m->in_enc(0), Bg, m->in_enc(0), Cg, 4 * h, bg, 0.f, 0);
+            if (r < 0) return r;
+            if (r > 0) AST_TRY(project(0, 0, Tp, st));
+        }
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int l = 0; l < NL; ++l) {       // every recurrence on a high-priority stream: the caller's stream has the priority of the side stream
             AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
