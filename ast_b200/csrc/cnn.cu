@@ -483,6 +483,26 @@ __global__ void permute_w1_kernel(const float* __restrict__ src, float* __restri
         if (to_p) dst[i] = src[j]; else dst[j] = src[i];
     }
 }
+// Weights of CNN_1's data gradient as a TRANSPOSED convolution over time (stride 2): the padded-input rows of parity p receive
+// the taps kt = p, p+2, ... from the output rows r = j - u, u = (kt - p) / 2.  Reading d(raw1) as an overlapping-rows matrix
+// (row j = rows j-U .. j of d(raw1), U = ntaps_p - 1) makes the whole gradient two plain GEMMs straight into da0p - no
+// (M1 x 9*C0) im2col-gradient buffer, no col2im pass.  Wt_p[(u' * Co + co) * Ci + ci] = W1p[co][kt = 2 (U - u') + p][ci].
+__global__ void build_w1t_kernel(const float* __restrict__ W1p, float* __restrict__ Wt, int Co, int Ci, int Kt, int p, int ntaps) {
+    const int total = ntaps * Co * Ci;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Ci; const int co = (i / Ci) % Co; const int up = i / (Ci * Co);
+        const int kt = 2 * (ntaps - 1 - up) + p;
+        Wt[i] = W1p[((size_t)co * Kt + kt) * Ci + ci];
+    }
+}
+int build_w1t(cudaStream_t st, const float* W1p, float* Wt, int Co, int Ci, int Kt, int p) {
+    const int ntaps = (Kt - p + 1) / 2;
+    if (ntaps <= 0) return 0;
+    build_w1t_kernel<<<std::min(cdiv(ntaps * Co * Ci, 256), 148 * 8), 256, 0, st>>>(W1p, Wt, Co, Ci, Kt, p, ntaps);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 int permute_w1(cudaStream_t st, const float* src, float* dst, int Co, int Ci, int Kt, bool to_p) {
     permute_w1_kernel<<<std::min(cdiv(Co * Ci * Kt, 256), 148 * 8), 256, 0, st>>>(src, dst, Co, Ci, Kt, to_p ? 1 : 0);
     AST_LAUNCH_OK();

@@ -60,6 +60,7 @@ int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, flo
                        float* dbeta, int nseg, int T1, int S0, int pad, int C);
 int col2im1(cudaStream_t st, const float* dA, float* da0p, int nseg, int S0, int Rs, int Tp, int C0, int kh, int sh);
 int permute_w1(cudaStream_t st, const float* src, float* dst, int Co, int Ci, int Kt, bool to_p);
+int build_w1t(cudaStream_t st, const float* W1p, float* Wt, int Co, int Ci, int Kt, int p);   // transposed-convolution weights, parity p
 
 // ---- persistent LSTM recurrence ----------------------------------------------------------------
 struct LstmChain {

@@ -39,6 +39,7 @@ unsigned long long g_kernel_launches = 0;
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
 
+constexpr int DRAW1_PAD_ROWS = 8;     // zero rows in front of d(raw1): the transposed convolution reads up to (kh-1)/2 rows back
 constexpr int BN_PART_BLOCKS = 640;   // per-block partial sums of bn_bwd_rnn_reduce (<= 148 * 4 + slack blocks)
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
@@ -93,6 +94,7 @@ struct ast_model {
     // not by launches, which the stream already pipelines.  Kept as an option (tests run both).
     int dec_v2 = 1, beam_fused = 0;
     float *draw1, *dA1, *da0p, *draw0, *dW1p, *dW0pad;
+    float* W1t[2] = {nullptr, nullptr}; int conv1_dx_fused = 1;      // CNN_1 data gradient as a transposed convolution (two overlapping-rows GEMMs)
     // decoder (training)
     float *x0, *actd[MAXL], *Hdec[MAXL], *Cdec[MAXL], *hdd[MAXL], *q, *scores, *alpha, *cvh, *ht, *logits, *row_loss;
     float *du, *dcvh, *dalpha, *dq, *dhtop, *dxh[MAXL], *dcd[MAXL];
@@ -239,7 +241,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->encW = a.get<float>(TB * H);
     m->encb = a.get<float>(TB);
     m->d_rnn_in = a.get<float>(TB * R); m->d_rnn_rev = a.get<float>(TB * R);
-    m->draw1 = a.get<float>(M1 * C1);
+    m->draw1 = a.get<float>(M1 * C1 + (size_t)DRAW1_PAD_ROWS * C1) + (a.dry ? 0 : (size_t)DRAW1_PAD_ROWS * C1);      // zero rows in front (transposed convolution)
+    for (int p = 0; p < 2; ++p) m->W1t[p] = a.get<float>((size_t)((m->cfg.cnn_kh[1] - p + 1) / 2) * C1 * C0);
     m->dA1 = a.get<float>(M1 * m->K1);
     m->da0p = a.get<float>((size_t)B * Fp * S0 * C0);
     m->draw0 = a.get<float>(M0 * C0);
@@ -347,6 +350,7 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
     AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
     AST_TRY(split_tf32(st, m->W1p, m->W1p_hi, m->W1p_lo, (size_t)m->C1 * m->K1));
+    for (int p = 0; p < 2; ++p) AST_TRY(build_w1t(st, m->W1p, m->W1t[p], m->C1, m->C0, c.cnn_kh[1], p));
     // The transposed decoder weights are consumed by backward only: build them on the side stream, concurrently with the
     // forward pass (backward_impl waits on ev_tr).
     cudaStream_t ts = m->overlap ? m->side : st;
@@ -1060,8 +1064,22 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     AST_TRY(fork());
     AST_TRY(gemm(m, sw, true, false, C1, m->K1, M1, m->draw1, C1, m->a0p, c.cnn_sh[1] * C0, m->dW1p, m->K1, nullptr, 0.f, -1, SITE_CONV1_WGRAD));
     AST_TRY(permute_w1(sw, m->dW1p, m->g("CNN_1/W"), C1, C0, c.cnn_kh[1], false));
-    AST_TRY(gemm(m, st, false, false, M1, m->K1, C1, m->draw1, C1, m->W1p, m->K1, m->dA1, m->K1, nullptr, 0.f, 0, SITE_CONV1_DX));
-    AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
+    const int U0 = (c.cnn_kh[1] + 1) / 2 - 1;       // rows the even-parity taps reach back
+    if (m->conv1_dx_fused && c.cnn_sh[1] == 2 && S0 == 2 * Rs && Rs - Tp >= U0 && U0 <= DRAW1_PAD_ROWS) {
+        // transposed convolution: da0p[seg][2j+p][:] = sum_{u'} d(raw1)[seg*Rs + j - U_p + u'][:] . Wt_p[u'] - the rows before a
+        // segment are the previous segment's junk rows (>= T', written as zeros by the BN backward) or the zero pad in front of the
+        // buffer, so row R = seg*Rs + j of the overlapping-rows operand simply starts U_p rows before d(raw1)[R]; the output row
+        // is da0p row 2R + p.  Two GEMMs (K = 5*C1 and 4*C1), no d(im2col) buffer (72.5 MB at B32 x T640), no col2im pass.
+        AST_CUDA_OK(cudaMemsetAsync(m->draw1 - (size_t)DRAW1_PAD_ROWS * C1, 0, sizeof(float) * DRAW1_PAD_ROWS * C1, st));
+        for (int p = 0; p < 2; ++p) {
+            const int ntaps = (c.cnn_kh[1] - p + 1) / 2, U = ntaps - 1;
+            AST_TRY(gemm(m, st, false, false, M1, C0, ntaps * C1, m->draw1 - (size_t)U * C1, C1, m->W1t[p], C0, m->da0p + (size_t)p * C0, 2 * C0,
+                         nullptr, 0.f, 0, SITE_CONV1_DX));
+        }
+    } else {
+        AST_TRY(gemm(m, st, false, false, M1, m->K1, C1, m->draw1, C1, m->W1p, m->K1, m->dA1, m->K1, nullptr, 0.f, 0, SITE_CONV1_DX));
+        AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
+    }
     AST_TRY(bn_bwd_from_padded(st, m->da0p, m->raw0, m->draw0, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
                                m->bnstats, m->g("CNN_0_bn/gamma"), m->g("CNN_0_bn/beta"), B * Fp, T1, S0, c.cnn_ph[1], C0));
     AST_TRY(gemm(m, st, true, false, C0, m->ld0, M0, m->draw0, C0, m->cols0, m->ld0, m->dW0pad, m->ld0, nullptr, 0.f, -1, SITE_CONV0_WGRAD));
@@ -1233,6 +1251,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
     else if (!strcmp(key, "enc_ts")) m->enc_ts_on = (int)value;
     else if (!strcmp(key, "tc2")) m->tc2 = (int)value;
+    else if (!strcmp(key, "conv1_dx_fused")) m->conv1_dx_fused = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas")) m->enc_gemm_ctas = (int)value;
     else if (!strcmp(key, "enc_gemm_ctas_bwd")) m->enc_gemm_ctas_bwd = (int)value;
     else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
