@@ -172,76 +172,84 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def roofline_dominant(engine, torch, peaks):
-    """Time the largest single-pass tensor-core kernel of the step in isolation at its workload shape with CUDA events and
-    report achieved / measured peak: the tcgen05 GEMM as the CNN_1 data gradient dA = d(raw1) . W1p (NN form; M = B*F'*Rs
-    rows of a B32 x T640 batch, N = 9*128, K = 512), the shape of the ncu --set full capture under profiles/."""
+    """Time the largest single-pass tensor-core launch of the step in isolation at its workload shape with CUDA events and
+    report achieved / measured peak: the grouped 2-CTA tcgen05 GEMM that computes the two layer-0 input projections of the
+    encoder (2 problems of M = T'B = 5120 rows of a B32 x T640 batch, N = 4h = 1024, K = 1536) - the shape of the ncu
+    --set full capture under profiles/.  `other_kernels` carries the rest of the GEMM family at the step's other large shapes."""
     import ctypes as C
     from ast_b200._lib import ptr, check
     hbm, tf_burst, tf_sus, how = peaks
     lib = engine.lib
     dev = engine.device
-    M, N, K = 15744, 1152, 512
-    A = torch.randn(M, K, device=dev); W = torch.randn(K, N, device=dev); Cc = torch.empty(M, N, device=dev)
-    which = 1 if engine.get_option("tc_gemm") and not engine.get_option("exact") else 0
+    peak = tf_burst / 2.0                                         # TF32 dense = 1/2 of the measured bf16 figure
+    tc = bool(engine.get_option("tc_gemm")) and not engine.get_option("exact")
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ts = []
-    for it in range(8):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(lib.ast_gemm(which, 0, 0, M, N, K, 1.0, ptr(A), K, ptr(W), N, 0.0, ptr(Cc), N, None, st), "ast_gemm")
-        e1.record()
-        torch.cuda.synchronize()
-        if it >= 3:
-            ts.append(e0.elapsed_time(e1))
-    ms = float(np.mean(ts))
-    flops = 2.0 * M * N * K
+
+    def timed(fn, n=8, skip=3):
+        ts = []
+        for it in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= skip:
+                ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts))
+
+    if not tc:
+        M, N, K = 5120, 1024, 1536
+        A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); Cc = torch.empty(M, N, device=dev)
+        ms = timed(lambda: check(lib.ast_gemm(0, 0, 1, M, N, K, 1.0, ptr(A), K, ptr(W), K, 0.0, ptr(Cc), N, None, st), "ast_gemm"))
+        ach = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "sgemm_kernel (fp32 SIMT)", "shape": f"M{M} N{N} K{K}", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "ms_per_launch": ms, "algorithmic_bytes": 4.0 * (M * K + K * N + M * N), "traffic": None}
+    G, M, N, K = 2, 5120, 1024, 1536
+    A = torch.randn(G, M, K, device=dev); W = torch.randn(G, N, K, device=dev); Cc = torch.empty(G, M, N, device=dev)
+    ms = timed(lambda: check(lib.ast_gemm_grouped(G, 0, 1, M, N, K, ptr(A), M * K, K, ptr(W), N * K, K, ptr(Cc), M * N, N, 0, st), "ast_gemm_grouped"))
+    flops = 2.0 * G * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = tf_burst / 2.0                                         # TF32 dense = 1/2 of the measured bf16 figure
-    out = {"bound": "tensor", "kernel": "gemm_tc_kernel<NN> (tcgen05 TF32, persistent)" if which == 1 else "sgemm_kernel (fp32 SIMT)",
-           "shape": f"M{M} N{N} K{K} (CNN_1 data gradient)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-           "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms,
-           "algorithmic_bytes": 4.0 * (M * K + K * N + M * N), "traffic": None, "traffic_unit": "bytes/launch"}
-    out.update(NCU_GEMM if which == 1 else {})
-    if which == 1:
-        # the 2-CTA (cta_group::2, 256 x 256 pair tiles) kernel the library uses for the layer-0 projection / data gradient, at that
-        # shape and at a shape large enough to fill its pipeline: same measurement, same peak
-        others = []
-        for (tb, M2, N2, K2, what) in ((0, 5120, 1536, 1024, "encoder layer-0 data gradient (B32 x T640)"),
-                                       (1, 5120, 1024, 1536, "encoder layer-0 input projection (B32 x T640)"),
-                                       (1, 8192, 4096, 4096, "kernel ceiling: a GEMM large enough to fill the pipeline")):
-            A2 = torch.randn(M2, K2, device=dev); W2 = torch.randn((N2, K2) if tb else (K2, N2), device=dev); C2 = torch.empty(M2, N2, device=dev)
-            t2 = []
-            for it in range(7):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                check(lib.ast_gemm(-2, 0, tb, M2, N2, K2, 1.0, ptr(A2), K2, ptr(W2), W2.shape[1], 0.0, ptr(C2), N2, None, st), "ast_gemm 2-CTA")
-                e1.record()
-                torch.cuda.synchronize()
-                if it >= 3:
-                    t2.append(e0.elapsed_time(e1))
-            ms2 = float(np.mean(t2))
-            ach = 2.0 * M2 * N2 * K2 / (ms2 * 1e-3) / 1e12
-            others.append({"kernel": "gemm_tc2_kernel (tcgen05 TF32, cta_group::2)", "shape": f"M{M2} N{N2} K{K2} ({'NT' if tb else 'NN'}): {what}",
-                           "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "ms_per_launch": ms2})
-        out["other_kernels"] = others
-        out["other_kernels_ncu"] = NCU_GEMM2
+    out = {"bound": "tensor", "kernel": "gemm_tc2_kernel<NT> (tcgen05 TF32, cta_group::2, grouped launch of 2 problems)",
+           "shape": f"2 x (M{M} N{N} K{K}): the two encoder layer-0 input projections of a B32 x T640 batch", "achieved": achieved, "peak": peak,
+           "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": f"{how} bf16 burst / 2 (TF32 dense is half of bf16)", "ms_per_launch": ms,
+           "algorithmic_bytes": 4.0 * G * (M * K + K * N + M * N), "traffic": None, "traffic_unit": "bytes/launch"}
+    out.update(NCU_GEMM)
+    others = []
+    for (kind, ta, tb, M2, N2, K2, what) in (("2cta", 0, 0, 5120, 1536, 1024, "encoder layer-0 data gradient (one direction)"),
+                                             ("2cta_splitk", 1, 0, 1024, 1536, 5120, "encoder layer-0 upward weight gradient (split-K)"),
+                                             ("1cta", 0, 0, 15744, 128, 2560, "CNN_1 data gradient, even rows (transposed convolution, overlapping-rows operand)"),
+                                             ("1cta", 0, 0, 15744, 1152, 512, "CNN_1 data gradient in its former im2col-gradient form"),
+                                             ("2cta", 0, 1, 8192, 4096, 4096, "kernel ceiling: a GEMM large enough to fill the pipeline")):
+        A2 = torch.randn((K2, M2) if ta else (M2, K2), device=dev); W2 = torch.randn((N2, K2) if tb else (K2, N2), device=dev)
+        C2 = torch.empty(M2, N2, device=dev)
+        which = {"2cta": -2, "2cta_splitk": -3, "1cta": 1}[kind]
+        ms2 = timed(lambda: check(lib.ast_gemm(which, ta, tb, M2, N2, K2, 1.0, ptr(A2), A2.shape[1], ptr(W2), W2.shape[1], 0.0, ptr(C2), N2, None, st),
+                                  "ast_gemm"), n=7)
+        ach = 2.0 * M2 * N2 * K2 / (ms2 * 1e-3) / 1e12
+        others.append({"kernel": {"2cta": "gemm_tc2_kernel (cta_group::2)", "2cta_splitk": "gemm_tc2_kernel (cta_group::2, split-K)",
+                                  "1cta": "gemm_tc_kernel (1-CTA persistent)"}[kind],
+                       "shape": f"M{M2} N{N2} K{K2} ({'T' if ta else 'N'}{'T' if tb else 'N'}): {what}",
+                       "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "ms_per_launch": ms2})
+    out["other_kernels"] = others
+    out["other_kernels_ncu"] = NCU_GEMM2
     return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum and pipe counters of this kernel at this shape from the ncu --set full capture
-# (tools/ncu_capture.sh, extract under profiles/); filled in from the round's capture
-NCU_GEMM = {"traffic": 34.64e6 + 18.55e6,     # the 72.5 MB output is only partly written back within the kernel's lifetime (126 MB L2)
-            "ncu": {"gpu_time_us_cold": 56.5, "tensor_pipe_active_pct": 37.6, "tensor_pipe_elapsed_pct": 31.3,
-                    "l2_sector_pct_of_peak": 27.8, "l2_hit_rate_pct": 70.5, "smem_fill_bytes": 580.4e6,
-                    "source": "profiles/r01_ncu_full_extract_v26_gemm.txt"}}
+# (tools/ncu_capture_roofline.sh, extract under profiles/); filled in from the round's capture
+NCU_GEMM = {"traffic": 76.01e6 + 9.36e6,     # the 42 MB output is only partly written back within the kernel's lifetime (126 MB L2)
+            "ncu": {"gpu_time_us_cold": 63.4, "tensor_pipe_active_pct": 68.6, "tensor_pipe_elapsed_pct": 49.9,
+                    "l2_sector_pct_of_peak": 29.5, "l2_hit_rate_pct": 68.4, "smem_fill_bytes": 503.7e6,
+                    "source": "profiles/r01_ncu_full_extract_v28_roofline.txt"}}
 
 
 NCU_GEMM2 = {"M5120_N1536_K1024": {"gpu_time_us_cold": 36.3, "tensor_pipe_active_pct": 54.9, "tensor_pipe_elapsed_pct": 41.8, "dram_bytes": 27.3e6 + 0.5e6},
              "M8192_N4096_K4096": {"gpu_time_us_cold": 346.2, "tensor_pipe_active_pct": 95.2, "tensor_pipe_elapsed_pct": 88.8, "dram_bytes": 623.3e6 + 117.7e6},
-             "source": "profiles/r01_ncu_full_extract_v26_gemm.txt"}
+             "M15744_N128_K2560_1cta": {"gpu_time_us_cold": 32.4, "tensor_pipe_active_pct": 42.7, "tensor_pipe_elapsed_pct": 30.1, "dram_bytes": 33.6e6 + 0.01e6},
+             "M15744_N1152_K512_1cta": {"gpu_time_us_cold": 56.5, "tensor_pipe_active_pct": 37.6, "tensor_pipe_elapsed_pct": 31.3, "dram_bytes": 34.64e6 + 18.55e6},
+             "source": "profiles/r01_ncu_full_extract_v26_gemm.txt, profiles/r01_ncu_full_extract_v28_roofline.txt"}
 
 
 def beam_rate(model, torch, T, n_utts, stop_limit, N=10, K=10):
