@@ -222,7 +222,9 @@ def roofline_dominant(engine, torch, peaks):
                                              ("1cta", 0, 0, 15744, 128, 2560, "CNN_1 data gradient, even rows (transposed convolution, overlapping-rows operand)"),
                                              ("1cta", 0, 0, 15744, 1152, 512, "CNN_1 data gradient in its former im2col-gradient form"),
                                              ("2cta", 0, 1, 8192, 4096, 4096, "kernel ceiling: a GEMM large enough to fill the pipeline")):
-        A2 = torch.randn((K2, M2) if ta else (M2, K2), device=dev); W2 = torch.randn((N2, K2) if tb else (K2, N2), device=dev)
+        overlap = "overlapping-rows" in what        # row j of the operand = rows j .. j+4 of a (M2 + 8) x 512 buffer: lda = 512 < K
+        A2 = torch.randn(M2 + 8, 512, device=dev) if overlap else torch.randn((K2, M2) if ta else (M2, K2), device=dev)
+        W2 = torch.randn((N2, K2) if tb else (K2, N2), device=dev)
         C2 = torch.empty(M2, N2, device=dev)
         which = {"2cta": -2, "2cta_splitk": -3, "1cta": 1}[kind]
         ms2 = timed(lambda: check(lib.ast_gemm(which, ta, tb, M2, N2, K2, 1.0, ptr(A2), A2.shape[1], ptr(W2), W2.shape[1], 0.0, ptr(C2), N2, None, st),
