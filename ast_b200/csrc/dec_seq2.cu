@@ -229,23 +229,35 @@ dec_seq2_fwd_kernel(DecSeq p) {
             const float* Wup = p.Wup[l] + (size_t)row * in;
             const float* Wlat = p.Wlat[l] + (size_t)row * H;
             const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
-            for (int j = 0; j < (kq >> 6); ++j) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = j * 64 + (i >> 1) * 8 + q + 4 * (i & 1);
-                    float x;
-                    if (l == 0) {
-                        if (k < 32) x = __ldg(Wup + 32 * rank + k);
-                        else if (k < 160) x = __ldg(Wup + E + 128 * rank + (k - 32));
-                        else if (k < 288) x = __ldg(Wlat + 128 * rank + (k - 160));
-                        else x = 0.f;
-                    } else {
-                        x = k < 128 ? __ldg(Wup + 128 * rank + k) : __ldg(Wlat + 128 * rank + (k - 128));
-                    }
-                    v[i] = rtf32(x);
+            // two 16-value fragments per round: 32 scattered 4-byte loads in flight before the first tcgen05.st (one fragment at a
+            // time serialised 13 L2 round trips per thread: 47 us of kernel prologue)
+            auto wload = [&](int k) -> float {
+                if (l == 0) {
+                    if (k < 32) return __ldg(Wup + 32 * rank + k);
+                    if (k < 160) return __ldg(Wup + E + 128 * rank + (k - 32));
+                    if (k < 288) return __ldg(Wlat + 128 * rank + (k - 160));
+                    return 0.f;
                 }
-                tmem_st16(tmem_lane + tcol + 16 * j, v);
+                return k < 128 ? __ldg(Wup + 128 * rank + k) : __ldg(Wlat + 128 * rank + (k - 128));
+            };
+            const int nj = kq >> 6;
+            for (int j = 0; j < nj; j += 2) {
+                float v0[16], v1[16];
+                const bool two = j + 1 < nj;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v0[i] = wload(j * 64 + (i >> 1) * 8 + q + 4 * (i & 1));
+                if (two) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v1[i] = wload((j + 1) * 64 + (i >> 1) * 8 + q + 4 * (i & 1));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v0[i] = rtf32(v0[i]);
+                tmem_st16(tmem_lane + tcol + 16 * j, v0);
+                if (two) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v1[i] = rtf32(v1[i]);
+                    tmem_st16(tmem_lane + tcol + 16 * (j + 1), v1);
+                }
             }
         }
         tmem_wait_st();

@@ -82,7 +82,8 @@ struct ast_model {
     // workspace
     Arena ws; int wsB = 0, wsT = 0, wsL = 0, wsN = 0, wsSteps = 0;
     // ---- buffers (valid after bind_workspace) ----
-    float *a0p_hi, *a0p_lo, *W1p_hi, *W1p_lo; int conv3x = 1;   // 3xTF32 operands of the CNN_1 forward GEMM (split_tf32)
+    float *cols0_hi, *cols0_lo, *W0_hi, *W0_lo;       // 3xTF32 operands of the CNN_0 forward GEMM
+    float *a0p_hi, *a0p_lo, *W1p_hi, *W1p_lo; int conv3x = 3;   // 3xTF32 operands of the CNN_1 forward GEMM (split_tf32)
     float *cols0, *W0pad, *raw0, *a0p, *W1p, *raw1, *mean0, *invstd0, *mean1, *invstd1, *rnn_in, *rnn_rev, *Xn;
     double *bnstats, *norm_sq, *bnpart;
     float *Genc[MAXL][2], *Hs[MAXL][2], *Cs[MAXL][2], *Hd[MAXL][2], *dHd[MAXL][2];
@@ -212,6 +213,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->Xn = a.get<float>((size_t)B * T * m->D);
     m->cols0 = a.get<float>(M0 * m->ld0);
     m->W0pad = a.get<float>((size_t)C0 * m->ld0);
+    m->W0_hi = a.get<float>((size_t)C0 * m->ld0); m->W0_lo = a.get<float>((size_t)C0 * m->ld0);
+    m->cols0_hi = a.get<float>(M0 * m->ld0); m->cols0_lo = a.get<float>(M0 * m->ld0);
     m->raw0 = a.get<float>(M0 * C0);
     m->a0p = a.get<float>((size_t)B * Fp * S0 * C0 + (size_t)(m->cfg.cnn_kh[1] + 8) * C0);
     m->W1p = a.get<float>((size_t)C1 * m->K1);
@@ -348,6 +351,7 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
     AST_CUDA_OK(cudaMemsetAsync(m->W0pad, 0, sizeof(float) * m->C0 * m->ld0, st));
     AST_TRY(copy2d(st, m->p("CNN_0/W"), K0, m->W0pad, m->ld0, m->C0, K0));
+    if (((size_t)m->C0 * m->ld0) % 4 == 0) AST_TRY(split_tf32(st, m->W0pad, m->W0_hi, m->W0_lo, (size_t)m->C0 * m->ld0));
     AST_TRY(permute_w1(st, m->p("CNN_1/W"), m->W1p, m->C1, m->C0, c.cnn_kh[1], true));
     AST_TRY(split_tf32(st, m->W1p, m->W1p_hi, m->W1p_lo, (size_t)m->C1 * m->K1));
     for (int p = 0; p < 2; ++p) AST_TRY(build_w1t(st, m->W1p, m->W1t[p], m->C1, m->C0, c.cnn_kh[1], p));
@@ -408,7 +412,15 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     }
     // CNN_0: im2col + GEMM, BN statistics, BN+ReLU into the padded layout
     AST_TRY(im2col0(st, Xin, m->cols0, B, T, m->D, Fp, T1, c.cnn_kh[0], c.cnn_kw[0], c.cnn_sh[0], c.cnn_sw[0], c.cnn_ph[0], m->ld0));
-    AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr, SITE_CONV0));
+    int conv0_done = 0;
+    if (m->tc_gemm && !m->exact && (m->conv3x & 2) && ((size_t)M0 * m->ld0) % 4 == 0) {
+        // fp32-faithful 3xTF32 on the tensor cores, as for CNN_1 below (K = 117 padded to 120: the fp32 SIMT GEMM took 38 us)
+        AST_TRY(split_tf32(st, m->cols0, m->cols0_hi, m->cols0_lo, (size_t)M0 * m->ld0));
+        const int r = gemm_tc3_nt(st, M0, C0, m->ld0, m->cols0_hi, m->cols0_lo, m->ld0, m->W0_hi, m->W0_lo, m->ld0, m->raw0, C0, nullptr);
+        if (r < 0) return r;
+        conv0_done = (r == 0);
+    }
+    if (!conv0_done) AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr, SITE_CONV0));
     float* bn0 = m->bn_state; float* bn1 = m->bn_state + 2 * C0;
     if (train) {
         AST_TRY(bn_stats(st, m->raw0, m->bnstats, M0, C0, T1, T1));
@@ -421,7 +433,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
     int conv1_done = 0;
-    if (m->tc_gemm && !m->exact && m->conv3x && m->K1 % 4 == 0) {
+    if (m->tc_gemm && !m->exact && (m->conv3x & 1) && m->K1 % 4 == 0) {
         // fp32-faithful on the tensor cores: 3xTF32 (hi.hi + lo.hi + hi.lo); single-pass TF32 here wrecks the BatchNorm
         // parameter gradients downstream, the fp32 SIMT kernel was 22 % of the forward pass
         const size_t n_a0p = (size_t)B * Fp * S0 * C0 + (size_t)(c.cnn_kh[1] + 8) * C0;
@@ -1244,7 +1256,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
     else if (!strcmp(key, "beam_fused")) m->beam_fused = value != 0;
     else if (!strcmp(key, "stage_timing")) m->stage_timing = value != 0;
-    else if (!strcmp(key, "conv3x")) m->conv3x = value != 0;
+    else if (!strcmp(key, "conv3x")) m->conv3x = (int)value;      // bit 0: CNN_1, bit 1: CNN_0 forward convolution as 3xTF32
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
