@@ -358,17 +358,23 @@ __global__ void __launch_bounds__(256) bn_bwd_rnn_reduce_kernel(const float* __r
         }
     }
 }
-__global__ void bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < nblocks; b += 4) {
-        s0 += partials[(size_t)b * n + i]; s1 += partials[(size_t)(b + 1) * n + i];
-        s2 += partials[(size_t)(b + 2) * n + i]; s3 += partials[(size_t)(b + 3) * n + i];
+// stats[i] = sum over blocks of partials[b][i]: one CTA per 32 columns, 32 x 32 threads (thread (y, x) sums blocks y, y+32, ... of
+// column x: coalesced 256-byte rows), then a shared-memory tree over y.  (A single thread per column walking all ~570 blocks was a
+// 81 us serial chain of dependent L2 loads.)
+__global__ void __launch_bounds__(1024) bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats) {
+    __shared__ double red[32][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
+    double s = 0.0;
+    if (i < n)
+        for (int b = y; b < nblocks; b += 32) s += partials[(size_t)b * n + i];
+    red[y][x] = s;
+    __syncthreads();
+    for (int h = 16; h > 0; h >>= 1) {
+        if (y < h) red[y][x] += red[y + h][x];
+        __syncthreads();
     }
-    for (; b < nblocks; ++b) s0 += partials[(size_t)b * n + i];
-    stats[i] = (s0 + s1) + (s2 + s3);
+    if (y == 0 && i < n) stats[i] = red[0][x];
 }
 
 // one CTA per (b, t in [0, Rs)): rows t >= T' are the junk rows of the padded segment and get zeros
@@ -421,7 +427,7 @@ int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, cons
     bn_bwd_rnn_reduce_kernel<<<nblk, 256, smem, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, stats, B, Fp, Rs, Tp, C, rpb, partials);
     AST_LAUNCH_OK();
     if (partials) {
-        bn_partials_sum_kernel<<<cdiv(2 * C, 128), 128, 0, st>>>(partials, nblk, 2 * C, stats);
+        bn_partials_sum_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partials, nblk, 2 * C, stats);
         AST_LAUNCH_OK();
     }
     bn_bwd_rnn_apply_kernel<<<B * Rs, 128, smem, st>>>(d_in, d_rev, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B, Fp,
