@@ -875,6 +875,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // ---- decoder weight gradients: one batched GEMM per tensor over all steps ----------------------
     // With the persistent encoder wavefront below they run beside the recurrence clusters and are capped to a few CTAs.
     const bool will_persist = bwd_will_persist(m);
+    struct CapGuard { ~CapGuard() { gemm_tc_set_cta_cap(0); } } cap_guard;      // an early error return must not leave the cap behind
     if (will_persist && sw != st) gemm_tc_set_cta_cap(m->enc_side_ctas);
     AST_TRY(fork());
     if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
