@@ -7,6 +7,7 @@ import random
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -163,3 +164,38 @@ def test_corpus_bleu_known_answers(tmp_path):
     assert 0.0 < b < 1.0
     ev.write_to_file({"u1": h1, "u2": h2}, str(tmp_path / "out.txt"))
     assert (tmp_path / "out.txt").read_text() == "the quick brown dog jumps\nhello world\n"
+
+
+def test_grad_allreduce_rejects_buckets_that_do_not_tile_the_buffer():
+    """GradAllReduce (data-parallel hook): the gradient buckets an engine reports must tile the flat buffer exactly - a gap
+    would leave gradients unreduced, an overlap would reduce them twice."""
+    import torch
+    from ast_b200 import dist as adist
+
+    class _Opt:
+        grad_scale = 1.0
+        pre_update = None
+
+    class _Eng:
+        grads = torch.zeros(1000)
+
+        def __init__(self, buckets):
+            self._b = buckets
+
+        def grad_buckets(self):
+            return self._b
+
+    ok = adist.GradAllReduce(_Eng([(600, 400), (100, 500), (0, 100)]), _Opt(), world=1)
+    assert ok.buckets[0] == (600, 400) and not ok.overlap
+    for bad in ([(600, 400), (0, 100)], [(500, 500), (100, 500), (0, 100)], [(0, 999)]):
+        with pytest.raises(AssertionError):
+            adist.GradAllReduce(_Eng(bad), _Opt(), world=1)
+
+
+def test_declared_c_abi_covers_the_data_parallel_and_grouped_entry_points(lib):
+    """The round-1 additions are part of the C ABI (include/ast_b200.h) and of the ctypes table."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "ast_b200.h")).read()
+    for sym in ("ast_grad_bucket_count", "ast_grad_bucket_range", "ast_grad_bucket_wait", "ast_gemm_grouped"):
+        assert re.search(r"\b%s\s*\(" % sym, hdr), sym
+        assert hasattr(lib, sym), sym
