@@ -220,14 +220,28 @@ class _BucketedLoader(DataLoader):
     def _load_utt(self, utt, set_key):
         raise NotImplementedError
 
+    @property
+    def feat_dim(self):
+        """Feature dimension D of the corpus, read from one utterance (the reference shapes its first layers lazily at
+        the first batch: `in_channels: null`, `L.LSTM(None, ...)`; NN needs D to build the engine up front)."""
+        if getattr(self, "_feat_dim", None) is None:
+            for set_key in self.buckets:
+                for bucket in self.buckets[set_key]["buckets"]:
+                    if bucket:
+                        self._feat_dim = int(np.asarray(self._load_utt(bucket[0], set_key)).shape[-1])
+                        return self._feat_dim
+            raise RuntimeError("empty corpus: cannot infer the feature dimension")
+        return self._feat_dim
+
     def _labels(self, utt, set_key):
         dec_key = self.data_cfg["dec_key"]
         return [self.vocab[dec_key]["w2i"].get(w, SYMBOLS.UNK_ID) for w in self.map[set_key][utt][dec_key]]
 
-    def get_batch(self, batch_size, set_key, train, labels=False):
-        dev = torch.device("cuda", self.gpuid if self.gpuid is not None and self.gpuid >= 0 else 0)
-        if self._packer is None:
-            self._packer = DevicePacker(dev)
+    def host_batches(self, batch_size, set_key, train, labels=False):
+        """The host half of dataloader.py:111-164 (pure numpy, no device): batch plan with the reference's `random` draw
+        order, per-utterance load, frame-zeroing masks drawn from numpy's global RNG in load order (:83-93,105-106), labels
+        [GO] + ids[:max_pred-2] + [EOS] zero-padded to the batch maximum (:149-150,160).
+        Yields (utts, feats [list of (T_i, D)], keep [list of uint8 masks] | None, y (B, L) int32 | None, max_sp)."""
         num_b, width_b = self.buckets[set_key]["num_b"], self.buckets[set_key]["width_b"]
         max_sp = (num_b + 1) * width_b                                  # dataloader.py:118
         max_pred = self.data_cfg["max_pred"]
@@ -237,7 +251,7 @@ class _BucketedLoader(DataLoader):
             keep = None
             if "train" in set_key and zero_input > 0:                   # dataloader.py:105-106
                 keep = [drop_frame_mask(min(len(f), max_sp), zero_input) for f in feats]
-            batch = {"utts": list(utts)}
+            ypad = None
             if labels:
                 ys = [np.asarray([SYMBOLS.GO_ID] + self._labels(u, set_key)[:max_pred - 2] + [SYMBOLS.EOS_ID], dtype=np.int32)
                       for u in utts]
@@ -245,6 +259,15 @@ class _BucketedLoader(DataLoader):
                 ypad = np.zeros((len(ys), L), dtype=np.int32)           # PAD_ID = 0
                 for i, v in enumerate(ys):
                     ypad[i, :len(v)] = v
+            yield list(utts), feats, keep, ypad, max_sp
+
+    def get_batch(self, batch_size, set_key, train, labels=False):
+        dev = torch.device("cuda", self.gpuid if self.gpuid is not None and self.gpuid >= 0 else 0)
+        if self._packer is None:
+            self._packer = DevicePacker(dev)
+        for utts, feats, keep, ypad, max_sp in self.host_batches(batch_size, set_key, train, labels):
+            batch = {"utts": utts}
+            if labels:
                 batch["X"], batch["y"], _ = self._packer.pack(feats, max_sp, keep, labels=ypad)   # labels ride the same copy
             else:
                 batch["X"] = self._packer.pack(feats, max_sp, keep)
@@ -315,7 +338,7 @@ class SyntheticDataLoader(_BucketedLoader):
 
     def __init__(self, data_cfg, model_dir, gpuid, feat_dim, vocab_size, lengths, target_lengths, seed=0, set_key="fisher_train"):
         super().__init__()
-        self.feat_dim, self.vocab_size = feat_dim, vocab_size
+        self._feat_dim, self.vocab_size = feat_dim, vocab_size
         rng = np.random.default_rng(seed)
         self._seed = seed
         names = ["utt{0:06d}".format(i) for i in range(len(lengths))]
@@ -340,7 +363,7 @@ class SyntheticDataLoader(_BucketedLoader):
     def _load_utt(self, utt, set_key):
         n = self.lengths[utt]
         rng = np.random.default_rng(zlib.crc32(utt.encode()) ^ self._seed)
-        return rng.standard_normal((n, self.feat_dim), dtype=np.float32)
+        return rng.standard_normal((n, self._feat_dim), dtype=np.float32)
 
     def _labels(self, utt, set_key):
         return self._labels_cache[utt]
