@@ -55,12 +55,15 @@ SIGNATURES = {
     "ast_grad_bucket_wait": (_I, [_P, _I, _P]),
     "ast_get_step_argmax": (_I, [_P, _P, _P]),
     "ast_opt_step": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, C.POINTER(_I), _I, _P]),
+    "ast_grad_buckets_mark": (_I, [_P, _P]),
+    "ast_scale_grads": (_I, [_P, _F, _P]),
     "ast_last_grad_norm": (C.c_double, [_P, _P]),
     "ast_init_decoder_state": (_I, [_P, _I, _P]),
     "ast_get_encoder_states": (_I, [_P, _P, _P]),
     "ast_get_decoder_states": (_I, [_P, _P, _I, _P]),
     "ast_set_decoder_states": (_I, [_P, _P, _I, _P]),
     "ast_decode_step": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    "ast_attention": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "ast_predict": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
     "ast_beam_search": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P, _P, _P, _P]),
     "ast_pack_cmvn": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _ULL, _P, _I, _I, _I, _P]),

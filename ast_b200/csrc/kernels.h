@@ -177,7 +177,7 @@ int lstm_cell_bwd(cudaStream_t st, float* act, const float* c, const float* c_pr
                   unsigned long long seed, unsigned drop_stream);
 
 // ---- optimizer / data / misc -----------------------------------------------------------------------
-struct FrozenRanges { int n; size_t begin[8]; size_t end[8]; };
+struct FrozenRanges { int n; size_t begin[24]; size_t end[24]; };   // merged [begin, end) float ranges, ascending
 int opt_sqnorm(cudaStream_t st, const float* g, const float* p, size_t n, float gscale, float wd, double* norm_sq);
 int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, float* vhat, size_t n, float gscale,
                 float wd, float clip, const double* norm_sq, float alpha_t, float beta1, float beta2, float eps,
@@ -185,6 +185,7 @@ int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, f
 int pack_cmvn(cudaStream_t st, const float* raw, const long long* row_off, const int* lens, const float* scale,
               const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
               unsigned long long seed, float* X, int B, int T, int D);
+int scale_inplace(cudaStream_t st, float* x, float a, size_t n);
 int mul_noise(cudaStream_t st, const float* X, float* Y, const float* noise, float sigma, unsigned long long seed, size_t n);
 int transpose(cudaStream_t st, const float* src, int ld_src, float* dst, int ld_dst, int R, int C);
 int colsum(cudaStream_t st, const float* x, int ld, float* out, int rows, int C, bool accumulate);

@@ -80,6 +80,19 @@ int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, f
     return 0;
 }
 
+// x *= a over a flat float buffer (data-parallel tail batches: a rank's gradient is weighted by its share of the global batch
+// before the all-reduce; a == 0 writes exact zeros whatever x held)
+__global__ void scale_kernel(float* __restrict__ x, float a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] = a == 0.f ? 0.f : x[i] * a;
+}
+int scale_inplace(cudaStream_t st, float* x, float a, size_t n) {
+    if (n == 0) return 0;
+    scale_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(x, a, n);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 // ---- pack + CMVN (+ frame drop + multiplicative noise) ---------------------------------------
 // raw: concatenated utterances (sum_len x D); X[b][t][d] = t < len_b ? (raw*scale[b][d]+offset[b][d]) * keep * noise : 0
 // Box-Muller normal from the counter RNG when noise_sigma > 0 and no explicit noise tensor is given.

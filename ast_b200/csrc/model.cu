@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <utility>
 #include "../../include/ast_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -1326,6 +1328,11 @@ int ast_grad_bucket_wait(ast_model* m, int bucket, void* stream) {
     AST_CUDA_OK(cudaStreamWaitEvent(S_(stream), m->ev_bucket[bucket], 0));
     return 0;
 }
+int ast_grad_buckets_mark(ast_model* m, void* stream) {
+    for (int i = 0; i < 3; ++i) AST_CUDA_OK(cudaEventRecord(m->ev_bucket[i], S_(stream)));
+    m->buckets_valid = true;
+    return 0;
+}
 int ast_get_step_argmax(ast_model* m, int* out, void* stream) {
     AST_CHECK(m->L >= 2, "no forward_loss yet");
     AST_CUDA_OK(cudaMemcpyAsync(out, m->argmax_steps, sizeof(int) * (size_t)(m->L - 1) * m->B, cudaMemcpyDeviceToDevice, S_(stream)));
@@ -1336,12 +1343,20 @@ int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr
                  float beta2, float eps, float grad_scale, const int* frozen_idx, int n_frozen, void* stream) {
     AST_CHECK(m->P && m->G && !m->ws.dry, "opt_step: params/workspace not bound");
     AST_CHECK(t >= 1, "opt_step: t is 1-based");
-    AST_CHECK(n_frozen <= 8, "opt_step: at most 8 frozen tensors");
-    FrozenRanges fr{}; fr.n = 0;
+    // disable_update() on a link freezes all its tensors (nn.py:113-118): a link's tensors are adjacent in the flat layout, so
+    // the sorted ranges merge (an LSTM link = 1 range; the whole model is 14 links + 4 BN/CNN pairs)
+    std::vector<std::pair<size_t, size_t>> rng;
     for (int i = 0; i < n_frozen; ++i) {
         AST_CHECK(frozen_idx[i] >= 0 && frozen_idx[i] < (int)m->pinfo.size(), "opt_step: bad frozen index");
         const ParamInfo& pi = m->pinfo[frozen_idx[i]];
-        fr.begin[fr.n] = (size_t)pi.off; fr.end[fr.n] = align_up((size_t)(pi.off + pi.count), 64); ++fr.n;
+        rng.emplace_back((size_t)pi.off, align_up((size_t)(pi.off + pi.count), 64));
+    }
+    std::sort(rng.begin(), rng.end());
+    FrozenRanges fr{}; fr.n = 0;
+    for (const auto& r : rng) {
+        if (fr.n > 0 && r.first <= fr.end[fr.n - 1]) { fr.end[fr.n - 1] = std::max(fr.end[fr.n - 1], r.second); continue; }
+        AST_CHECK(fr.n < 24, "opt_step: more than 24 disjoint frozen ranges");
+        fr.begin[fr.n] = r.first; fr.end[fr.n] = r.second; ++fr.n;
     }
     const double fix1 = 1.0 - pow((double)beta1, t), fix2 = 1.0 - pow((double)beta2, t);
     const float alpha_t = (float)(lr * sqrt(fix2) / fix1);
@@ -1350,6 +1365,10 @@ int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr
     AST_TRY(opt_amsgrad(st, m->P, m->G, m1, v, vhat, (size_t)m->nfloats, grad_scale, l2, clip, m->norm_sq, alpha_t, beta1, beta2, eps, fr));
     m->weights_dirty = true;
     return 0;
+}
+int ast_scale_grads(ast_model* m, float weight, void* stream) {
+    AST_CHECK(m->G, "scale_grads: params not bound");
+    return scale_inplace(S_(stream), m->G, weight, (size_t)m->nfloats);
 }
 double ast_last_grad_norm(ast_model* m, void* stream) {
     double v = 0;
@@ -1405,6 +1424,26 @@ int ast_decode_step(ast_model* m, const int* word, const float* ht_in, int Bd, f
     }
     AST_TRY(copy2d(st, m->s_logits, m->Vp, logits, m->V, Bd, m->V));
     AST_CUDA_OK(cudaMemcpyAsync(ht_out, m->s_htout, sizeof(float) * Bd * m->A, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// compute_context_vector (seq2seq.py:336-358): q = Wa.h + ba; s = enc.q; alpha = softmax over T' (no mask); cv = sum_t alpha_t enc_t
+int ast_attention(ast_model* m, const float* dec_h, int Bd, const float* Wa, const float* ba, float* cv, float* alphas,
+                  void* stream) {
+    AST_TRY(require_ready(m, 0, 0, 0, Bd, 0));
+    AST_CHECK(m->Tp > 0, "attention: encode first");
+    AST_CHECK(Bd == m->B || m->B == 1, "attention: batch %d incompatible with encoder batch %d", Bd, m->B);
+    AST_CHECK(dec_h && cv, "attention: null argument");
+    AST_CHECK((Wa == nullptr) == (ba == nullptr), "attention: pass both W and b of the attention link, or neither");
+    cudaStream_t st = S_(stream);
+    if (m->weights_dirty) AST_TRY(refresh_weights(m, st));
+    const int H = m->H;
+    SkinnyArgs s{}; s.X[0] = dec_h; s.ldx[0] = H; s.K[0] = H; s.W[0] = Wa ? Wa : m->p("attn_Wa/W"); s.ldw[0] = H;
+    s.bias = ba ? ba : m->p("attn_Wa/b"); s.B = Bd; s.N = H; s.epi = EPI_NONE; s.Y = m->s_q; s.ldy = H;
+    AST_TRY(skinny(st, s, true));
+    const long long ebs = (m->B == Bd) ? (long long)m->Tp * H : 0;
+    AST_TRY(attn_dot(st, m->enc_states, ebs, m->s_q, H, m->s_scores, Bd, m->Tp, H));
+    AST_TRY(attn_ctx(st, m->enc_states, ebs, m->s_scores, alphas ? alphas : m->s_alpha, cv, H, Bd, m->Tp, H));
     return 0;
 }
 

@@ -50,16 +50,19 @@ def buckets_main(save_path, num_b, width_b, key, scale=1, seed="haha", info_path
     return bucket_dict
 
 
-def plan_batches(buckets, batch_size):
+def plan_batches(buckets, batch_size, rng=None):
     """dataloader.py:125-135: shuffle inside each bucket, slice by batch_size, shuffle the batches.
-    Draws from Python's global `random` in the reference's order."""
+    Draws from Python's global `random` in the reference's order; `rng` (a random.Random) replaces it under data
+    parallelism, where every rank must draw the SAME plan although their global streams have diverged (each rank's
+    forward_loss draws a rank-local number of scheduled-sampling values, seq2seq.py:432)."""
+    rng = random if rng is None else rng
     batches = []
     width_b = buckets["width_b"]
     for b, bucket in enumerate(buckets["buckets"]):
-        random.shuffle(bucket)
+        rng.shuffle(bucket)
         for i in range(0, len(bucket), batch_size):
             batches.append((bucket[i:i + batch_size], (b + 1) * width_b))
-    random.shuffle(batches)
+    rng.shuffle(batches)
     return batches
 
 
@@ -237,16 +240,25 @@ class _BucketedLoader(DataLoader):
         dec_key = self.data_cfg["dec_key"]
         return [self.vocab[dec_key]["w2i"].get(w, SYMBOLS.UNK_ID) for w in self.map[set_key][utt][dec_key]]
 
-    def host_batches(self, batch_size, set_key, train, labels=False):
+    def host_batches(self, batch_size, set_key, train, labels=False, rank=0, world=1, plan_rng=None):
         """The host half of dataloader.py:111-164 (pure numpy, no device): batch plan with the reference's `random` draw
         order, per-utterance load, frame-zeroing masks drawn from numpy's global RNG in load order (:83-93,105-106), labels
         [GO] + ids[:max_pred-2] + [EOS] zero-padded to the batch maximum (:149-150,160).
-        Yields (utts, feats [list of (T_i, D)], keep [list of uint8 masks] | None, y (B, L) int32 | None, max_sp)."""
+        Yields (utts, feats [list of (T_i, D)], keep [list of uint8 masks] | None, y (B, L) int32 | None, max_sp).
+        Data parallel (`world` > 1): the plan is drawn for the GLOBAL batch (batch_size * world, from `plan_rng`,
+        identical on every rank) and rank r takes utterances r::world of each global batch - same bucket on every rank, so
+        padded lengths stay balanced.  A tail batch smaller than the world leaves some ranks with an EMPTY shard (utts == []):
+        they still take part in the gradient all-reduce with a zero contribution (NN.train_epoch)."""
         num_b, width_b = self.buckets[set_key]["num_b"], self.buckets[set_key]["width_b"]
         max_sp = (num_b + 1) * width_b                                  # dataloader.py:118
         max_pred = self.data_cfg["max_pred"]
         zero_input = self.data_cfg.get("zero_input", 0)
-        for utts, _ in plan_batches(self.buckets[set_key], batch_size):
+        for gutts, _ in plan_batches(self.buckets[set_key], batch_size * world, plan_rng):
+            utts = list(gutts[rank::world]) if world > 1 else gutts
+            self.last_global_batch = len(gutts)
+            if not utts:
+                yield [], [], None, None, max_sp
+                continue
             feats = [self._load_utt(u, set_key) for u in utts]
             keep = None
             if "train" in set_key and zero_input > 0:                   # dataloader.py:105-106
@@ -261,12 +273,16 @@ class _BucketedLoader(DataLoader):
                     ypad[i, :len(v)] = v
             yield list(utts), feats, keep, ypad, max_sp
 
-    def get_batch(self, batch_size, set_key, train, labels=False):
+    def get_batch(self, batch_size, set_key, train, labels=False, rank=0, world=1, plan_rng=None):
         dev = torch.device("cuda", self.gpuid if self.gpuid is not None and self.gpuid >= 0 else 0)
         if self._packer is None:
             self._packer = DevicePacker(dev)
-        for utts, feats, keep, ypad, max_sp in self.host_batches(batch_size, set_key, train, labels):
-            batch = {"utts": utts}
+        for utts, feats, keep, ypad, max_sp in self.host_batches(batch_size, set_key, train, labels, rank, world, plan_rng):
+            batch = {"utts": utts, "global_batch": self.last_global_batch}
+            if not utts:                       # empty data-parallel shard of a tail batch
+                batch["X"] = batch["y"] = None
+                yield batch
+                continue
             if labels:
                 batch["X"], batch["y"], _ = self._packer.pack(feats, max_sp, keep, labels=ypad)   # labels ride the same copy
             else:

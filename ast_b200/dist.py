@@ -40,15 +40,19 @@ def shard_utterances(utts, rank, world):
 
 
 def shard_batch_plan(batches, rank, world):
-    """Global batch plan [(utts, width)] built with batch_size*world -> this rank's plan.  All ranks must
-    have seeded Python's `random` identically so the plans agree (nn.py:54)."""
-    out = []
-    for utts, width in batches:
-        mine = shard_utterances(utts, rank, world)
-        if len(mine) == 0:           # tail batch smaller than the world: every rank still needs a step
-            mine = [utts[rank % len(utts)]]
-        out.append((mine, width))
-    return out
+    """Global batch plan [(utts, width)] built with batch_size*world -> this rank's plan [(utts, width, n_global)].
+    Every rank must have drawn the same plan: use a dedicated `random.Random` (dataloader.plan_batches(rng=)), the global
+    `random` streams of the ranks diverge after one step.  A tail batch smaller than the world leaves ranks with an EMPTY
+    shard; they still join the all-reduce with weight 0 (`shard_weight`) - no utterance is ever counted twice."""
+    return [(shard_utterances(utts, rank, world), width, len(utts)) for utts, width in batches]
+
+
+def shard_weight(n_local, n_global, world):
+    """Factor a rank applies to its local gradient BEFORE the sum all-reduce so that the reduced gradient, multiplied by
+    the optimizer's grad_scale = 1/world, is the gradient of the global-batch mean loss: each replica's loss is a mean
+    over its OWN n_local utterances (seq2seq.py:468, divisor = local batch), so the global mean is
+    sum_r (n_r / n_global) g_r = (1/world) sum_r w_r g_r with w_r = n_r * world / n_global (1 for equal shards)."""
+    return float(n_local) * world / float(n_global) if n_global else 0.0
 
 
 def allreduce_sum_(flat, group=None):

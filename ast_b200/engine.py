@@ -233,6 +233,14 @@ class Engine:
         check(self.lib.ast_opt_step(self.h, ptr(m), ptr(v), ptr(vhat), int(t), lr, l2, clip, beta1, beta2, eps, grad_scale,
                                     arr, len(idx), self.stream()), "ast_opt_step")
 
+    def scale_grads(self, weight):
+        """grads *= weight, then re-arm the bucket events so a gated all-reduce sees the scaled values."""
+        check(self.lib.ast_scale_grads(self.h, float(weight), self.stream()), "ast_scale_grads")
+        self.mark_grads_final()
+
+    def mark_grads_final(self):
+        check(self.lib.ast_grad_buckets_mark(self.h, self.stream()), "ast_grad_buckets_mark")
+
     def last_grad_norm(self):
         return float(self.lib.ast_last_grad_norm(self.h, self.stream()))
 
@@ -272,6 +280,21 @@ class Engine:
               "ast_decode_step")
         self._keep_step = (word, ht)
         return logits, ht_out, alphas
+
+    def attention(self, dec_h, W=None, b=None):
+        """compute_context_vector (seq2seq.py:336-358): dec_h (Bd,H) -> (cv (Bd,H), alphas (Bd,T'))."""
+        dec_h = self._as_f32(dec_h)
+        Bd = dec_h.shape[0]
+        assert dec_h.shape[1] == self.H
+        self.ensure_workspace(B=Bd, N=Bd)
+        if W is not None:
+            W, b = self._as_f32(W), self._as_f32(b)
+            assert tuple(W.shape) == (self.H, self.H) and tuple(b.shape) == (self.H,)
+        cv = torch.empty(Bd, self.H, dtype=torch.float32, device=self.device)
+        alphas = torch.empty(Bd, self.Tp, dtype=torch.float32, device=self.device)
+        check(self.lib.ast_attention(self.h, ptr(dec_h), Bd, ptr(W), ptr(b), ptr(cv), ptr(alphas), self.stream()), "ast_attention")
+        self._keep_attn = (dec_h, W, b)
+        return cv, alphas
 
     def predict(self, X, start_token, end_token, stop_limit):
         X = self._as_f32(X)

@@ -140,11 +140,24 @@ def beam_result_to_entries(r, go_id=SYMBOLS.GO_ID, model=None):
 class NN:
     def __init__(self, cfg_path, feat_dim=None, data_loader=None, cfg=None):
         """nn.py:43-79.  ``feat_dim`` / ``data_loader`` / ``cfg`` are optional injection points (synthetic
-        benchmarks, tests); with only ``cfg_path`` this behaves like the reference."""
+        benchmarks, tests); with only ``cfg_path`` this behaves like the reference.
+
+        Launched under torchrun (WORLD_SIZE > 1) the same object trains data-parallel (new work, SURVEY 8e / BASELINE config
+        4; the reference is single-GPU): one process per GPU, the device is LOCAL_RANK (train_cfg's ``gpuid`` is ignored),
+        rank 0's parameters are broadcast, every global batch of batch_size * world utterances is split r::world, and the
+        flat gradient is sum-all-reduced over NCCL in buckets overlapped with backward (dist.GradAllReduce)."""
+        from . import dist as adist
         self.cfg = cfg if cfg is not None else Config(cfg_path)
         self.model_dir = self.cfg.model["model_dir"]
+        self.rank, local_rank, self.world = adist.env_rank()
+        if self.world > 1:
+            adist.init_process_group()
+            self.cfg.train["gpuid"] = local_rank
         self.gpuid = self.cfg.train["gpuid"]
         random.seed(self.cfg.train["seed"])
+        # data-parallel batch plans come from their own generator: identical on every rank in every epoch, whatever each
+        # rank's global `random` stream has consumed for scheduled sampling meanwhile
+        self._plan_rng = random.Random(f"{self.cfg.train['seed']}/plan") if self.world > 1 else None
         if data_loader is not None:
             self.data_loader = data_loader
         elif self.cfg.train["data"].get("dataloader") == "globalphone":
@@ -156,6 +169,7 @@ class NN:
         self._feat_dim = feat_dim
         self.get_model()
         self.init_optimizer(self.cfg.train["optimizer"])
+        self._allreduce = None
         self.train_log = os.path.join(self.model_dir, "train.log")
         self.dev_log = os.path.join(self.model_dir, "dev.log")
 
@@ -172,9 +186,9 @@ class NN:
         if opt_cfg["grad_noise_eta"] > 0:
             self.optimizer.add_hook(GradientNoise(eta=opt_cfg["grad_noise_eta"]))
         for l in opt_cfg["freeze"]:
-            if l in self.model.__dict__:
+            if l in self.model.link_names:          # known before the lazy build (`l in self.model.__dict__`, nn.py:114)
                 print("freezing: {0:s}".format(l))
-                self.model[l].disable_update()
+                self.model.disable_update(l)
             else:
                 print("layer {0:s} not in model".format(l))
 
@@ -197,34 +211,63 @@ class NN:
         else:
             print("model not found")
 
+    def _dp_setup(self, engine):
+        """First data-parallel step: same start on every rank, then the bucketed all-reduce hook (dist.GradAllReduce)."""
+        from . import dist as adist
+        adist.broadcast_params_(engine)
+        self._allreduce = adist.GradAllReduce(engine, self.optimizer, self.world)
+
     def train_epoch(self, set_key, max_batches=None):
         """nn.py:158-200.  The per-batch loss read-back is one step late (pinned, asynchronous) so the
         training loop never blocks on the device; the returned average is the same quantity."""
+        from .engine import AsyncScalar
+        from . import dist as adist
         total_loss, n_batches = 0.0, 0
         batch_size = self.cfg.train["batch_size"]
         random_out = self.cfg.train["extras"]["random_out"]
         add_noise = self.cfg.train["extras"]["speech_noise"]
         teach_ratio = self.cfg.train["extras"]["teach_ratio"]
-        from .engine import AsyncScalar
-        reader = AsyncScalar(self.model._engine.device)
+        reader = None            # needs the device, i.e. the (possibly lazily built) engine: created after the first forward
         sizes = []
-        for batch in self.data_loader.get_batch(batch_size, set_key, train=True, labels=True):
+        kw = dict(rank=self.rank, world=self.world, plan_rng=self._plan_rng) if self.world > 1 else {}
+        for batch in self.data_loader.get_batch(batch_size, set_key, train=True, labels=True, **kw):
+            weight = 1.0
             with using_config("train", True):
-                loss = self.model.forward_loss(X=batch["X"], y=batch["y"], teach_ratio=teach_ratio, random_out=random_out,
-                                               add_noise=add_noise)
-                self.model.cleargrads()
-                loss.backward()
+                if batch["X"] is None:
+                    # empty shard of a data-parallel tail batch: contribute exact zeros to the all-reduce
+                    e = self.model._require()
+                    if self._allreduce is None:
+                        self._dp_setup(e)
+                    e.scale_grads(0.0)
+                    loss = None
+                else:
+                    loss = self.model.forward_loss(X=batch["X"], y=batch["y"], teach_ratio=teach_ratio, random_out=random_out,
+                                                   add_noise=add_noise)
+                    if self.world > 1 and self._allreduce is None:
+                        self._dp_setup(self.model._engine)
+                    self.model.cleargrads()
+                    loss.backward()
+                    if self.world > 1:
+                        weight = adist.shard_weight(len(batch["y"]), batch["global_batch"], self.world)
+                        if weight != 1.0:
+                            self.model._engine.scale_grads(weight)
                 self.optimizer.update()
-            reader.push(loss.data)                 # D2H into pinned memory + event; read back one step late (nn.py:189)
-            sizes.append(len(batch["y"]))
             n_batches += 1
-            if len(reader) > 1:
-                total_loss += reader.pop() / sizes.pop(0)
+            if loss is not None:
+                if reader is None:
+                    reader = AsyncScalar(self.model._engine.device)
+                reader.push(loss.data)             # D2H into pinned memory + event; read back one step late (nn.py:189)
+                sizes.append(len(batch["y"]))
+                if len(reader) > 1:
+                    total_loss += reader.pop() / sizes.pop(0)
             if max_batches is not None and n_batches >= max_batches:
                 break
-        while len(reader):
+        while reader is not None and len(reader):
             total_loss += reader.pop() / sizes.pop(0)
-        return total_loss / max(n_batches, 1)
+        avg = total_loss / max(n_batches, 1)
+        if self.world > 1:       # the epoch loss every rank logs is the mean over ranks of the per-replica averages
+            avg = adist.sum_over_ranks(avg, self.model._engine.device) / self.world
+        return avg
 
     def predict(self, set_key):
         """nn.py:202-233"""

@@ -188,15 +188,34 @@ class SpeechEncoderDecoder:
         self.rnn_rev_enc = [f"L{i}_rev_enc" for i in range(nl)] if self.bi_rnn else []
         self.rnn_dec = [f"L{i}_dec" for i in range(r["dec_layers"])]
         self._pending_state = {}
+        self._pending_frozen = set()
+        self._provisional_dim = False
         self._seed = None
         if feat_dim is not None:
             self._build(feat_dim)
 
+    @property
+    def link_names(self):
+        """Names of the child links (what `l in model.__dict__` tests in nn.py:114), known before the lazy build."""
+        return ([n for c in self.cnns for n in (c, c + "_bn")] + self.rnn_enc + self.rnn_rev_enc
+                + ["attn_Wa", "context", "embed_dec"] + self.rnn_dec + ["out"])
+
+    def disable_update(self, name):
+        """`model[name].disable_update()` (nn.py:116) that also works while the model is still unshaped."""
+        if name not in self.link_names:
+            raise KeyError(name)
+        if self._engine is None:
+            self._pending_frozen.add(name)
+        else:
+            self._links[name].disable_update()
+
     # ---- construction ---------------------------------------------------------------------------
-    def _build(self, feat_dim):
+    def _build(self, feat_dim, provisional=False):
         dev = self.gpuid if self.gpuid is not None and self.gpuid >= 0 else 0
+        old = self._engine
+        frozen = {n for n, l in self._links.items() if not l.update_enabled} | set(self._pending_frozen)
         e = Engine(self.cfg, feat_dim, dev)
-        self._engine, self._feat_dim = e, feat_dim
+        self._engine, self._feat_dim, self._provisional_dim = e, feat_dim, provisional
         links = {}
         for c in self.cnns:
             links[c] = Link(e, c, params=("W",))
@@ -212,7 +231,19 @@ class SpeechEncoderDecoder:
             object.__setattr__(self, k, v)
         self.mask_pad_id = torch.ones(e.V, dtype=torch.float32, device=e.device)   # seq2seq.py:152-156
         self.mask_pad_id[0] = 0
-        self.init_params(seed=self._seed)
+        if old is not None:
+            # re-shaped for another feature dimension with the same number of CNN frequency positions: no parameter shape
+            # depends on D itself (CNN_0/W is (C0,1,kh,kw); the RNN input width is C1*F'), so everything carries over
+            assert old.nfloats == e.nfloats, "parameter layout changed with the feature dimension"
+            e.params.copy_(old.params)
+            e.bn_state.copy_(old.bn_state)
+            e.bn_N = list(old.bn_N)
+            e.weights_changed()
+        else:
+            self.init_params(seed=self._seed)
+        for n in frozen:
+            links[n].disable_update()
+        self._pending_frozen = set()
 
     def _require(self, X=None):
         if self._engine is None:
@@ -220,6 +251,17 @@ class SpeechEncoderDecoder:
                 raise RuntimeError("model parameters are shaped at the first encode() (lazy in_channels); "
                                    "pass feat_dim= or call encode first")
             self._build(int(X.shape[-1]))
+        elif X is not None and self._provisional_dim and int(X.shape[-1]) != self._feat_dim:
+            # shaped from a checkpoint, which fixes only the number of frequency positions F' (serializers.load_npz)
+            D = int(X.shape[-1])
+            l0 = self.cfg["cnn_config"]["cnn_layers"][0]
+            fp = (D + 2 * l0["pad"][1] - l0["ksize"][1]) // l0["stride"][1] + 1
+            if fp * self.cfg["cnn_config"]["cnn_layers"][-1]["out_channels"] != self._engine.info["L0_enc/upward/W"][2][1]:
+                raise ValueError(f"feature dimension {D} does not fit the loaded parameters "
+                                 f"(L0_enc input width {self._engine.info['L0_enc/upward/W'][2][1]})")
+            self._build(D)
+        if X is not None:
+            self._provisional_dim = False
         return self._engine
 
     def init_params(self, seed=None):
@@ -341,8 +383,15 @@ class SpeechEncoderDecoder:
     forward_dec = decode_step
 
     def compute_context_vector(self, dec_h, attn_Wa=None):
-        raise NotImplementedError("attention is fused into decode_step on the CUDA path (seq2seq.py:336-358 "
-                                  "is not called by nn.py / beam.py)")
+        """seq2seq.py:336-358 -> (cv (B,H), alphas (B,T',1)) over the encoder states of the last encode(): q = attn_Wa(dec_h),
+        scores = enc_states . q, softmax over T' with NO length mask (:344-347), cv = sum_t alpha_t enc_states[:, t].
+        `attn_Wa`: an attention link (`model.attn_Wa`, also of another model) or None for this model's own."""
+        dec_h = dec_h.data if isinstance(dec_h, Variable) else dec_h
+        W = b = None
+        if attn_Wa is not None and attn_Wa is not self._links.get("attn_Wa"):
+            W, b = attn_Wa.W.data, attn_Wa.b.data
+        cv, alphas = self._engine.attention(dec_h, W, b)
+        return Variable(cv), Variable(alphas.unsqueeze(2))
 
     attention = compute_context_vector
 

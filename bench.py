@@ -346,7 +346,7 @@ def run_ours(args):
     # ---- host batches (features, masks, labels, scheduled-sampling bits) -----------------------------
     random.seed(1000 + rank)
     host = []
-    for utts, _ in plan:
+    for utts, _, _ in plan:
         feats, keep, y, frames = host_batch(loader, utts)
         bits = np.asarray(draw_use_true(y.shape[1], TRAIN_EXTRAS["teach_ratio"]), dtype=np.uint8)
         host.append((feats, keep, y, bits, frames))

@@ -92,6 +92,12 @@ int ast_get_step_argmax(ast_model* m, int* out, void* stream);
 int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr, float l2, float clip,
                  float beta1, float beta2, float eps, float grad_scale, const int* frozen_idx, int n_frozen,
                  void* stream);
+/* re-record all bucket events on `stream`: the gradients were modified after ast_backward (ast_scale_grads) or no backward ran this
+ * step (empty shard), so a collective gated on ast_grad_bucket_wait must wait for work enqueued on `stream` up to here */
+int ast_grad_buckets_mark(ast_model* m, void* stream);
+/* data parallelism (new work): grads *= weight in place before the all-reduce - a rank whose shard of a tail batch is
+ * smaller than the others' weights its replica-mean gradient by n_local * world / n_global (0 for an empty shard: exact zeros) */
+int ast_scale_grads(ast_model* m, float weight, void* stream);
 double ast_last_grad_norm(ast_model* m, void* stream);   /* synchronises; for logging / tests */
 
 /* decode_step / get|set_decoder_states / get_encoder_states (seq2seq.py:361-396, 529-569; nn.py:238-274).
@@ -103,6 +109,12 @@ int ast_set_decoder_states(ast_model* m, const float* states, int Bd, void* stre
 /* word (Bd) int32, ht_in (Bd,A) -> logits (Bd,V), ht_out (Bd,A), alphas (Bd,T'). Eval mode. */
 int ast_decode_step(ast_model* m, const int* word, const float* ht_in, int Bd, float* logits, float* ht_out,
                     float* alphas, void* stream);
+
+/* compute_context_vector(dec_h, attn_Wa) (seq2seq.py:336-358; called by decode_step :379,382): dec_h (Bd,H) -> cv (Bd,H),
+ * alphas (Bd,T') (may be NULL) over the encoder states of the last encode.  Wa (H,H) / ba (H): device pointers to the attention
+ * link's W and b (the `attn_Wa` argument of the reference), both NULL = the model's own attn_Wa. */
+int ast_attention(ast_model* m, const float* dec_h, int Bd, const float* Wa, const float* ba, float* cv, float* alphas,
+                  void* stream);
 
 /* predict (seq2seq.py:475-527; nn.py:217-220): greedy batched decode; preds (stop_limit,B) int32 device,
  * n_steps (host) = rows actually produced (not cut at EOS per row, as the reference). */

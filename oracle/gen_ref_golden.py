@@ -13,6 +13,7 @@ stand-in because the library is absent.
 The fixtures travel to the GPU box; /root/reference does not.  tests/test_ref_golden.py checks oracle == fixture (CPU) and
 tests/test_gpu_parity.py checks CUDA path == fixture (GPU).
 """
+import json
 import os
 import random
 import shutil
@@ -117,7 +118,7 @@ class Recorder:
         return False
 
 
-def synth_xy(rng, B, T, D, L, lens=None, ylens=None):
+def synth_xy(rng, B, T, D, L, lens=None, ylens=None, V=V):
     lens = lens if lens is not None else [T] + [int(v) for v in rng.integers(max(T - 15, 9), T, size=B - 1)]
     X = np.zeros((B, T, D), dtype=np.float32)
     for b, n in enumerate(lens):
@@ -125,21 +126,25 @@ def synth_xy(rng, B, T, D, L, lens=None, ylens=None):
     ylens = ylens if ylens is not None else [L] + [int(v) for v in rng.integers(3, L + 1, size=B - 1)]
     y = np.zeros((B, L), dtype=np.int32)
     for b, n in enumerate(ylens):
-        y[b, :n] = [SYMBOLS.GO_ID] + [int(v) for v in rng.integers(4, V, size=n - 2)] + [SYMBOLS.EOS_ID]
+        y[b, :n] = [SYMBOLS.GO_ID] + [int(v) for v in rng.integers(4, V, size=n - 2)] + [SYMBOLS.EOS_ID]   # noqa
     return X, y
 
 
-def fresh_nn(root, cfg, D, P, dropout=(0.0, 0.0, 0.0), eos_boost=0.0, **kw):
+def fresh_nn(root, cfg, D, P, dropout=(0.0, 0.0, 0.0), eos_boost=0.0, mc=None, vocab_words=VOCAB_WORDS, **kw):
     """A new experiment directory + checkpoint -> the reference's NN(cfg_path) (resumes from seq2seq_0.model, nn.py:142-152)."""
     if os.path.isdir(root):
         shutil.rmtree(root)
     os.makedirs(root)
-    mc = SC.small_model_cfg(hidden=128, embed=16, attn=128, c0=8, c1=16, dropout=dropout)
+    if mc is None:
+        mc = SC.small_model_cfg(hidden=128, embed=16, attn=128, c0=8, c1=16, dropout=dropout)
+    else:
+        mc = json.loads(json.dumps(mc))
+        mc["dropout"] = {"embed": dropout[0], "rnn": dropout[1], "out": dropout[2]}
     assert mc["rnn_config"] == {k: v for k, v in cfg["rnn_config"].items() if k != "dec_vocab_size"}
-    exp = SC.write_experiment(root, mc, feat_dim=D, vocab_words=VOCAB_WORDS, **kw)
+    exp = SC.write_experiment(root, mc, feat_dim=D, vocab_words=vocab_words, **kw)
     write_checkpoint(exp, P, 0, eos_boost)
     n = ref_nn.NN(exp)
-    assert n.max_epoch == 0 and n.model.cfg["rnn_config"]["dec_vocab_size"] == V
+    assert n.max_epoch == 0 and n.model.cfg["rnn_config"]["dec_vocab_size"] == vocab_words + 4
     return n
 
 
@@ -319,8 +324,85 @@ def gen_epoch_case(name, D, seed, globalphone=False, freeze=()):
     print(f"{name}: {out['n_batches']} batches, avg loss {avg:.6f} -> {path} ({os.path.getsize(path) / 1024:.0f} KB)")
 
 
+def gen_full_case(name, seed=505, B=4, T=120, L=10, stride=97, eos_boost=1.4):
+    """The SHIPPED geometry (the reference's own experiments/es_en_20h/model_cfg.json: H=512, E=128, A=512, CNN 128/512,
+    dropout .3/.3) with the BPE vocabulary size of data/fisher/fisher.vocab (1098), D=40, and the shipped training extras
+    (speech_noise .25, teach_ratio .8): the configuration bench.py measures, on a batch small enough for a fixture.  This
+    is the geometry the tcgen05 recurrences and the TMEM-resident decoder kernels are specialised for."""
+    with open(os.path.join(REF, "experiments", "es_en_20h", "model_cfg.json")) as f:
+        mc = json.load(f)
+    D, Vf = 40, 1098
+    cfg = json.loads(json.dumps(mc))
+    cfg["rnn_config"]["dec_vocab_size"] = Vf
+    drop = (mc["dropout"]["embed"], mc["dropout"]["rnn"], mc["dropout"]["out"])
+    assert drop == (0.3, 0.3, 0)
+    P = golden_params(cfg, D, seed)
+    rng = np.random.default_rng(seed + 1)
+    X, y = synth_xy(rng, B, T, D, L, V=Vf)
+    out = {"D": D, "seed": seed, "V": Vf, "X": X, "y": y, "param_checksum": param_checksum(P), "sample": stride,
+           "model_cfg_json": json.dumps(mc, sort_keys=True)}
+    tmp = tempfile.mkdtemp(prefix="ast_ref_")
+    try:
+        n = fresh_nn(os.path.join(tmp, "f"), cfg, D, P, dropout=drop, mc=mc, vocab_words=Vf - 4)
+        m = n.model
+        Tp = O.cnn_shapes(cfg, T, D)[-1][10]
+        masks = R.training_masks(DROP_SEED, 1, B, Tp, L - 1, 256, 512, 128, 3, 0.3, 0.3)
+        order = R.reference_call_order(Tp, L - 1, 3, 0.3, 0.3)
+        calls = []
+
+        def hook(shape, ratio):
+            k = order[len(calls)]
+            calls.append(k)
+            assert tuple(masks[k].shape) == tuple(shape), (k, shape)
+            return masks[k].astype(np.float64)
+        F.dropout_hook = hook
+        random.seed(779)
+        np.random.seed(31338)
+        try:
+            with Recorder() as rec, chainer.using_config("train", True):
+                loss = m.forward_loss(X=chainer.Variable(X), y=chainer.Variable(y), teach_ratio=0.8, add_noise=0.25)
+                m.cleargrads()
+                loss.backward()
+        finally:
+            F.dropout_hook = None
+        assert len(calls) == len(order) and len(rec.noise) == 1
+        random.seed(779)
+        out["do_bits"] = np.asarray([True if not (0 < i < L - 2) else (random.random() < 0.8) for i in range(L - 1)])
+        out["do_noise"] = rec.noise[0].astype(np.float32)
+        out["do_seed"] = DROP_SEED
+        out["do_loss"] = float(loss.data)
+        out["do_step_losses"] = np.asarray(rec.step_losses)
+        out["do_enc_states"] = np.asarray(m.enc_states.data).astype(np.float32)
+        out["do_logits"] = np.stack(rec.logits).astype(np.float32)
+        pack_tensors(out, "do_grad", model_grads(m), stride=stride)
+        n.optimizer.update()
+        out["do_grad_norm"] = n.optimizer.last_grad_norm
+        pack_tensors(out, "do_param_after1", model_params(m), stride=stride)
+        for k, v in bn_state(m).items():
+            out["do_bn/" + k] = v
+        # decoding at float32 after that one training step: batched greedy + beam-10 that runs 40 steps
+        chainer.config.dtype = np.float32
+        try:
+            n32 = fresh_nn(os.path.join(tmp, "g"), cfg, D, P, dropout=drop, mc=mc, vocab_words=Vf - 4, eos_boost=eos_boost)
+            with chainer.using_config("train", False):
+                out["greedy_f32"] = np.asarray(n32.model.predict(chainer.Variable(X), SYMBOLS.GO_ID, SYMBOLS.EOS_ID, 20), dtype=np.int32)
+                nb = n32.decode_beam(chainer.Variable(X[0:1]), stop_limit=40, N=10, K=10)
+            for k, v in beam_to_arrays(nb).items():
+                out[f"beam_N10K10/{k}"] = v
+            out["eos_boost"] = eos_boost
+        finally:
+            chainer.config.dtype = np.float64
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: do_loss {out['do_loss']:.6f} greedy {out['greedy_f32'].shape} beam lens {out['beam_N10K10/beam_hyp_lens'].tolist()} "
+          f"-> {path} ({os.path.getsize(path) / 1024:.0f} KB)")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    gen_full_case("ref_full_es_en_20h")
     gen_model_case("ref_model_d13", D=13, seed=101)
     gen_model_case("ref_model_d40", D=40, seed=202)
     gen_epoch_case("ref_epoch_fisher_d13", D=13, seed=303)

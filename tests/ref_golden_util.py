@@ -32,6 +32,19 @@ def load_model_case(name, dropout=(0.0, 0.0, 0.0), eos_boost=False):
     return cfg, D, P, z
 
 
+def load_full_case(name="ref_full_es_en_20h", eos_boost=False):
+    """The shipped es_en_20h geometry (model_cfg.json as the reference ships it, stored in the fixture) at V=1098, D=40."""
+    import json
+    z = load(name)
+    cfg = json.loads(str(z["model_cfg_json"]))
+    cfg["rnn_config"]["dec_vocab_size"] = int(z["V"])
+    D, P = _params(z, cfg)
+    if eos_boost:
+        P["out/b"] = P["out/b"].copy()
+        P["out/b"][O.EOS_ID] += float(z["eos_boost"])
+    return cfg, D, P, z
+
+
 def epoch_case_model(z):
     cfg = C.model_cfg()
     D, P = _params(z, cfg)
@@ -61,7 +74,7 @@ def tensor_errors(z, prefix, tensors):
         want = z[key].astype(np.float64)
         got = np.asarray(tensors[k], dtype=np.float64)
         if want.shape != got.shape:
-            got = got.ravel()[::C.SAMPLE]
+            got = got.ravel()[::int(z["sample"]) if "sample" in z.files else C.SAMPLE]
         assert got.shape == want.shape, (k, got.shape, want.shape)
         out[k] = (float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30)),
                   float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30)))

@@ -120,6 +120,37 @@ def test_oracle_matches_reference_greedy_and_beam(name):
     assert lens.min() < lens.max()                                            # finished hypotheses were carried along
 
 
+def test_oracle_matches_reference_at_the_shipped_geometry():
+    """experiments/es_en_20h/model_cfg.json as shipped (H=512, dropout .3/.3), V=1098, D=40, speech_noise .25,
+    teach_ratio .8 - the configuration bench.py measures - then decoding at float32: greedy and a 40-step beam-10."""
+    cfg, D, P, z = G.load_full_case()
+    assert (cfg["dropout"]["embed"], cfg["dropout"]["rnn"], cfg["rnn_config"]["hidden_units"]) == (0.3, 0.3, 512)
+    B, L = z["y"].shape
+    Tp = O.cnn_shapes(cfg, z["X"].shape[1], D)[-1][10]
+    om = O.OracleModel(cfg, P, dtype=np.float64)
+    om.dropout_masks = {k: v.astype(np.float64) for k, v in
+                        R.training_masks(int(z["do_seed"]), 1, B, Tp, L - 1, 256, 512, 128, 3, 0.3, 0.3).items()}
+    loss = float(om.forward_loss(z["X"], z["y"], tf_bits=[bool(b) for b in z["do_bits"]], noise=z["do_noise"]))
+    assert abs(loss - float(z["do_loss"])) <= 1e-11 * abs(loss)
+    np.testing.assert_allclose(om.step_losses, z["do_step_losses"], rtol=1e-11)
+    np.testing.assert_allclose(om.enc_states, z["do_enc_states"], rtol=0, atol=2e-7)
+    g = om.backward()
+    G.assert_tensors_match(z, "do_grad", g, rel=1e-9)
+    opt = O.OracleAMSGrad(om.p)
+    opt.update(om.p, g)
+    assert abs(opt.last_norm - float(z["do_grad_norm"])) <= 1e-10 * opt.last_norm
+    G.assert_tensors_match(z, "do_param_after1", {k: v for k, v in om.p.items() if k in g}, rel=1e-10)
+    cfg, D, P, z = G.load_full_case(eos_boost=True)
+    om = O.OracleModel(cfg, P, dtype=np.float32)
+    pred = om.predict(z["X"], O.GO_ID, O.EOS_ID, 20)
+    assert pred.shape == z["greedy_f32"].shape and (pred == z["greedy_f32"]).all()
+    nb = om.decode_beam(z["X"][0:1], 40, 10, 10)
+    hyps, scores, attn = G.beam_from_fixture(z, 10, 10)
+    assert [list(map(int, e["hyp"])) for e in nb] == hyps
+    assert max(len(h) for h in hyps) == 41 and min(len(h) for h in hyps) == 2      # 40-step hypotheses next to finished ones
+    np.testing.assert_allclose([float(e["score"]) for e in nb], scores, rtol=2e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize("name", EPOCH_CASES)
 def test_host_loader_and_oracle_reproduce_reference_training_epoch(name, tmp_path):
     """train.py:56 -> nn.py:158-200 on an on-disk corpus: the repo's loaders (bucket plan, per-speaker sub-directories / one
