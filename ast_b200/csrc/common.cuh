@@ -140,6 +140,27 @@ __device__ __forceinline__ void mma_f32(float (&c)[4], const float (&a)[4], cons
     }
 }
 
+// ---- bounded spin on a flag another LAUNCH publishes (persistent-wavefront hand-offs) -----------------
+// CUDA gives no forward-progress guarantee between separate launches: if the producer never becomes resident (another tenant
+// holds the SMs, a stream got serialised behind the waiter) an unbounded spin hangs the GPU until the watchdog / the operator
+// kills the process.  After SPIN_TIMEOUT_NS of %globaltimer the waiter traps instead: the launch fails loudly
+// (cudaErrorLaunchFailure at the next synchronisation) and the host reports it.  The clock is read every 1024 polls only.
+constexpr unsigned long long SPIN_TIMEOUT_NS = 4000000000ULL;
+__device__ __forceinline__ void spin_until_ge(const unsigned* flag, unsigned target) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= target) return;
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned polls = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((++polls & 1023u) == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > SPIN_TIMEOUT_NS) __trap();
+        }
+    } while (v < target);
+}
+
 // ---- counter-based RNG for dropout / noise (stateless: mask is re-derivable in backward) ---
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;

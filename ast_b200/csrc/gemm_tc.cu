@@ -172,9 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     // (forward in time, or - gate_rev - backward from step gate_T - 1)
                     const int q = p.gate_rev ? (p.gate_T - 1 - m0 / p.gate_B) / p.gate_chunk
                                              : ((min(m0 + TBM, p.M) - 1) / p.gate_B) / p.gate_chunk;
-                    const unsigned* f = p.gate_wait + q;
-                    unsigned v;
-                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < p.gate_target);
+                    spin_until_ge(p.gate_wait + q, p.gate_target);
                     asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes (other SMs) -> this thread's TMA reads
                 }
                 for (int i = 0; i < nkb; ++i) {

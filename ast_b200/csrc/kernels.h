@@ -94,6 +94,8 @@ int lstm_seq_fwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int 
 int lstm_seq_bwd(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, int h, float drop,
                  unsigned long long seed, bool exact);
 // tcgen05 versions (lstm_seq_tc.cu): TF32 mode, h == 256, chains already split into 16-row slices
+int lstm_seq_tc_max_clusters(bool backward);     // cudaOccupancyMaxActiveClusters of the tcgen05 recurrence kernels (cached)
+int lstm_seq_tc_cluster_size();
 int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);
 void lstm_tc_set_prof(unsigned long long* p);   // diagnostics: device buffer of >= 128 u64 for the forward kernel's cycle probe
 int lstm_seq_bwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed);

@@ -197,8 +197,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         int tiles_ok = 0;          // leading 128-row tiles of G known complete (a.tile_ready gating)
         // rows of step i handled here: [i*B + b0, i*B + b0 + nb) -> needs every tile up to the one holding the last row
 #define TILE_WAIT(step) do { if (a.tile_ready) { const int need = ((step) * B + b0 + nb - 1) >> 7; \
-            while (tiles_ok <= need) { unsigned v; do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tile_ready + tiles_ok) : "memory"); } \
-                                       while (v < a.tile_target); ++tiles_ok; } } } while (0)
+            while (tiles_ok <= need) { spin_until_ge(a.tile_ready + tiles_ok, a.tile_target); ++tiles_ok; } } } while (0)
         TILE_WAIT(0);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -382,8 +381,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         float4 p_act[2]; float p_c[2], p_cp[2], p_dout[2];
         int tile_next = (T * B - 1) >> 7;          // a.tile_ready gating: tiles above this one are known complete (dout arrives last tile first)
 #define TILE_WAIT_REV(step) do { if (a.tile_ready) { const int need = ((step) * B + b0) >> 7; \
-            while (tile_next >= need) { unsigned v; do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tile_ready + tile_next) : "memory"); } \
-                                        while (v < a.tile_target); --tile_next; } } } while (0)
+            while (tile_next >= need) { spin_until_ge(a.tile_ready + tile_next, a.tile_target); --tile_next; } } } while (0)
         TILE_WAIT_REV(T - 1);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -543,6 +541,36 @@ static int launch_tc_fwd(cudaStream_t st, int nchains, size_t smem, const LstmCh
     ++g_kernel_launches;
     return 0;
 }
+
+// How many 8-CTA clusters of the recurrence kernels the device can hold at once (cudaOccupancyMaxActiveClusters): the
+// persistent encoder wavefront needs every cluster of all layers co-resident, its caller checks that before choosing it.
+int lstm_seq_tc_max_clusters(bool backward) {
+    static int cached[2] = {-1, -1};
+    int& c = cached[backward ? 1 : 0];
+    if (c >= 0) return c;
+    const size_t smem = backward ? BW_SMEM : FW_SMEM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(TNC * 64);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = TNC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e;
+    if (backward) {
+        e = cudaFuncSetAttribute(lstm_seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, lstm_seq_bwd_tc_kernel, &cfg);
+    } else {
+        e = cudaFuncSetAttribute(lstm_seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, lstm_seq_fwd_tc_kernel, &cfg);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    c = n;
+    return c;
+}
+int lstm_seq_tc_cluster_size() { return TNC; }
 
 // `ch` already holds 16-row chains (lstm_seq.cu::expand_chains).  Preconditions checked by the caller: h == 256.
 int lstm_seq_fwd_tc(cudaStream_t st, const LstmChains& ch, int nchains, int T, int B, float drop, unsigned long long seed) {

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <cuda.h>
 #include <utility>
 #include "../../include/ast_b200.h"
 #include "common.cuh"
@@ -37,6 +39,8 @@ bool kernels_are_serialised() {
     return state == 1;
 }
 unsigned long long g_kernel_launches = 0;
+// live ast_model objects per device in this process: the spin-wait encoder schedule assumes this engine owns the GPU
+static std::atomic<int> g_live_models[64];
 
 constexpr float BN_EPS = 2e-5f, BN_DECAY = 0.9f;
 constexpr int MAXL = 4;
@@ -118,6 +122,7 @@ struct ast_model {
     // encoder layer wavefront: layer l runs chunk c of the time axis while layer l-1 runs chunk c+1 (one stream per layer)
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
     unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 7;      // bit 0: 2-CTA GEMM for large K-major-A problems, 1: for weight gradients, 2: grouped weight gradients
+    bool queues_ok = false, eager_loading = false, last_fwd_persistent = false; int num_sms = 0;     // residency guards of the spin-wait schedule (persist_allowed)
     unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
@@ -388,7 +393,30 @@ static int require_ready(ast_model* m, int B, int T, int L, int N, int steps) {
     return 0;
 }
 
-static bool persist_allowed() { return !kernels_are_serialised(); }
+// The persistent encoder wavefront launches kernels that WAIT FOR EACH OTHER through device flags (three cluster recurrences + four
+// gated GEMMs, on different streams).  CUDA does not promise that separate launches are co-resident, so the schedule is chosen only
+// when that can be established, and the per-chunk schedule (ordinary stream dependencies) runs otherwise:
+//   * no tool serialises kernels (Nsight Compute / compute-sanitizer / AST_NO_PERSIST);
+//   * this is the only live engine on the device in this process (BeamPool replicas, a second model, ... share the SMs);
+//   * the streams really map to distinct hardware queues (CUDA_DEVICE_MAX_CONNECTIONS as seen at ast_create >= 16);
+//   * kernels are loaded eagerly, or this model has completed one pass on the per-chunk path (a first-time load can wait for
+//     running kernels, which wait for flags only the blocked host thread can cause to be written);
+//   * every CTA that spins plus every CTA it waits for fits on the device at once: clusters by cudaOccupancyMaxActiveClusters,
+//     total CTAs against the SM count (each takes a whole SM's shared memory).
+// A producer that still fails to show up trips the bounded spin (common.cuh::spin_until_ge): an error, not a hang.
+static bool persist_allowed(const ast_model* m, bool backward, int B, int warm) {
+    if (kernels_are_serialised()) return false;
+    if (g_live_models[m->device & 63].load() != 1) return false;
+    if (!m->queues_ok) return false;
+    if (!m->eager_loading && warm <= 0) return false;
+    const int csz = lstm_seq_tc_cluster_size();
+    const int clusters_per_layer = 2 * ((B + 15) / 16);
+    const int spin_ctas = m->NL * clusters_per_layer * csz;
+    const int gemm_ctas = 2 * (m->NL - 1) * (backward ? m->enc_gemm_ctas_bwd : m->enc_gemm_ctas);
+    if (lstm_seq_tc_max_clusters(backward) < m->NL * clusters_per_layer) return false;
+    if (spin_ctas + gemm_ctas > m->num_sms) return false;
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------
 // encoder forward (seq2seq.py:293-315)
@@ -504,8 +532,9 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // first-time launch submitted while the recurrence kernels spin on flags only this host thread can advance would hang.
     // The first pass of a model (and the first after an option change) therefore runs the per-chunk path, which launches the
     // same kernels.
-    const bool persist = wave && (m->enc_persist & 1) && persist_allowed() && lstm_seq_gated_supported(h, m->exact != 0) && Tp >= 48 &&
-                         nq <= MAXQ && (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->warm_fwd > 0 && m->tc_gemm;
+    const bool persist = wave && (m->enc_persist & 1) && lstm_seq_gated_supported(h, m->exact != 0) && Tp >= 48 &&
+                         nq <= MAXQ && (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->tc_gemm && persist_allowed(m, false, B, m->warm_fwd);
+    m->last_fwd_persistent = persist;
     if (!wave) {
         for (int l = 0; l < NL; ++l) { AST_TRY(project(l, 0, Tp, st)); AST_TRY(recur(l, 0, Tp, st)); }
     } else if (persist) {
@@ -787,8 +816,8 @@ static bool bwd_will_persist(const ast_model* m) {
     const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
     const int PCH = std::max(4, m->enc_pchunk);
     const int nq = (Tp + PCH - 1) / PCH;
-    return wave && (m->enc_persist & 2) && persist_allowed() && lstm_seq_gated_supported(m->h, m->exact != 0) && Tp >= 48 && nq <= MAXQ &&
-           (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->warm_bwd > 0 && m->tc_gemm;
+    return wave && (m->enc_persist & 2) && lstm_seq_gated_supported(m->h, m->exact != 0) && Tp >= 48 && nq <= MAXQ &&
+           (Tp * B + 127) / 128 <= MAXT && m->enc_flags && m->tc_gemm && persist_allowed(m, true, m->B, m->warm_bwd);
 }
 
 static int backward_impl(ast_model* m, cudaStream_t st) {
@@ -1173,6 +1202,19 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     build_param_table(m);
     cudaError_t e = cudaSetDevice(device);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    {   // what the spin-wait schedule may rely on (persist_allowed)
+        cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
+        const char* mc = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        m->queues_ok = mc && atoi(mc) >= 16;          // 11 library streams + the caller's; the default (8) aliases them
+        cudaFree(0);                                  // make sure the context exists before asking the driver
+        // through the runtime's entry-point query: the library must load (and export its symbols) on hosts without libcuda.so.1
+        typedef CUresult (*LoadingModeFn)(CUmoduleLoadingMode*);
+        void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+        CUmoduleLoadingMode mode = CU_MODULE_LAZY_LOADING;
+        if (cudaGetDriverEntryPoint("cuModuleGetLoadingMode", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && fp)
+            m->eager_loading = reinterpret_cast<LoadingModeFn>(fp)(&mode) == CUDA_SUCCESS && mode == CU_MODULE_EAGER_LOADING;
+        cudaGetLastError();
+    }
     e = cudaMallocHost(&m->h_pinned, 64 * sizeof(int));
     AST_CREATE_CHECK(e == cudaSuccess, "cudaMallocHost: %s", cudaGetErrorString(e));
     // priorities: the GEMMs the recurrences wait for (projection / dx chunks) are dispatched ahead of the weight-gradient GEMMs
@@ -1192,12 +1234,14 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
+    ++g_live_models[device & 63];
     *out = m;
     return 0;
 }
 
 int ast_destroy(ast_model* m) {
     if (!m) return 0;
+    --g_live_models[m->device & 63];
     if (m->h_pinned) cudaFreeHost(m->h_pinned);
     for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -1281,6 +1325,10 @@ double ast_get_option(const ast_model* m, const char* key) {
     if (!strcmp(key, "dec_fused")) return m->dec_fused;
     if (!strcmp(key, "beam_fused")) return m->beam_fused;
     if (!strcmp(key, "enc_persist")) return m->enc_persist;
+    if (!strcmp(key, "enc_persist_active")) return m->last_fwd_persistent ? 1 : 0;       // did the last training forward use the spin-wait schedule?
+    if (!strcmp(key, "eager_loading")) return m->eager_loading ? 1 : 0;
+    if (!strcmp(key, "queues_ok")) return m->queues_ok ? 1 : 0;
+    if (!strcmp(key, "live_models")) return g_live_models[m->device & 63].load();
     if (!strcmp(key, "seed")) return (double)m->seed;
     return -1;
 }

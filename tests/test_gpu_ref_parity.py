@@ -1,0 +1,397 @@
+"""GPU parity against the REFERENCE-generated fixtures (tests/golden/ref_*.npz, produced by the unmodified
+/root/reference source on the Chainer stand-in, oracle/gen_ref_golden.py) and against the oracle on the configuration
+bench.py measures (dropout .3/.3, speech_noise .25, teach_ratio .8) at the benchmarked sizes, with the device's own
+dropout masks replicated on the host (oracle/device_rng.py) and injected into the oracle.
+
+Tolerances (BASELINE.json north_star): loss 1e-3 relative, gradients 1e-2 relative (max-norm per tensor; the L2-relative
+figure is asserted beside it), greedy / beam hypotheses identical at fp32 (exact mode).
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ast_oracle as O
+from oracle import device_rng as R
+import ref_golden_util as G
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-3
+GRAD_RTOL = 1e-2
+MODES = [("exact", 1, 0), ("tf32", 0, 1)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _engine(cfg, D, P, exact=1, tc=0, seed=None):
+    from ast_b200.engine import Engine
+    e = Engine(cfg, D, 0)
+    for k in e.info:
+        e.view(k).copy_(torch.as_tensor(np.asarray(P[k], dtype=np.float32), device=e.device))
+    for k in ("CNN_0_bn/avg_mean", "CNN_0_bn/avg_var", "CNN_1_bn/avg_mean", "CNN_1_bn/avg_var"):
+        e.bn_view(k).copy_(torch.as_tensor(np.asarray(P[k], dtype=np.float32), device=e.device))
+    e.weights_changed()
+    e.set_option("exact", exact)
+    e.set_option("tc_gemm", tc)
+    if seed is not None:
+        e.set_option("seed", seed)
+    return e
+
+
+def _grads(e):
+    return {k: e.view(k, grad=True).cpu().numpy() for k in e.info}
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _l2err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _assert_grads(z, prefix, e, what):
+    errs = G.tensor_errors(z, prefix, _grads(e))
+    worst = max(errs.items(), key=lambda kv: kv[1][0])
+    for k, (emax, el2) in errs.items():
+        assert emax <= GRAD_RTOL, (what, k, "max-norm", emax)
+        assert el2 <= 2 * GRAD_RTOL, (what, k, "l2", el2)
+    return worst
+
+
+def _step_losses(e, L, B):
+    return e.debug_fetch("row_loss").cpu().numpy().reshape(L - 1, B).sum(1)
+
+
+# ---- the device RNG replica ------------------------------------------------------------------------------------------------
+def test_device_dropout_masks_match_the_host_replica(dev):
+    """oracle/device_rng.py == csrc/common.cuh: the encoder's post-dropout outputs equal its pre-dropout link states times
+    the replicated masks, for every layer, direction and step (chunked launches included)."""
+    cfg = O.default_model_cfg(vocab=64, dropout=(0.3, 0.3, 0.0))
+    P = O.init_params(cfg, 40, seed=5)
+    X, y, _ = O.synth_batch(5, 170, 40, 64, 4, 6, seed=6, Tmin=150)
+    for exact, tc in ((1, 0), (0, 1)):
+        e = _engine(cfg, 40, P, exact, tc, seed=1234)
+        float(e.forward_loss(X, y))
+        B, Tp, h = 5, e.Tp, 256
+        masks = R.training_masks(1234, 1, B, Tp, y.shape[1] - 1, h, 512, 128, 3, 0.3, 0.3)
+        for l in range(3):
+            for d, stack in enumerate(("enc", "rev_enc")):
+                Hs = e.debug_fetch(f"H_{l}{d}").cpu().numpy().reshape(Tp + 1, B, h)[1:]
+                Od = e.debug_fetch(f"O_{l}{d}").cpu().numpy().reshape(Tp, B, h)
+                m = np.stack([masks[(f"L{l}_{stack}", i)] for i in range(Tp)])
+                if l < 2:        # the top layer writes enc_states directly (no separate post-dropout buffer)
+                    np.testing.assert_allclose(Od, Hs * m, rtol=1e-6, atol=1e-7, err_msg=f"layer {l} dir {d}")
+        # top layer through enc_states: fwd half is step-ordered, rev half is flipped (seq2seq.py:231)
+        enc = e.enc_states().cpu().numpy()
+        Hf = e.debug_fetch("H_20").cpu().numpy().reshape(Tp + 1, B, h)[1:]
+        Hr = e.debug_fetch("H_21").cpu().numpy().reshape(Tp + 1, B, h)[1:]
+        mf = np.stack([masks[("L2_enc", i)] for i in range(Tp)])
+        mr = np.stack([masks[("L2_rev_enc", i)] for i in range(Tp)])
+        np.testing.assert_allclose(enc[:, :, :h], (Hf * mf).transpose(1, 0, 2), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(enc[:, :, h:], (Hr * mr)[::-1].transpose(1, 0, 2), rtol=1e-6, atol=1e-7)
+
+
+# ---- reference fixtures, toy geometry -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,exact,tc", MODES)
+@pytest.mark.parametrize("name", ["ref_model_d13", "ref_model_d40"])
+def test_cuda_matches_reference_teacher_forced_and_sampled_steps(dev, name, mode, exact, tc):
+    cfg, D, P, z = G.load_model_case(name)
+    X, y = z["X"], z["y"]
+    B, L = y.shape
+    e = _engine(cfg, D, P, exact, tc)
+    loss = float(e.forward_loss(X, y))
+    assert abs(loss - float(z["tf_loss"])) <= LOSS_RTOL * abs(float(z["tf_loss"]))
+    np.testing.assert_allclose(_step_losses(e, L, B), z["tf_step_losses"], rtol=LOSS_RTOL, atol=1e-6)
+    tol = 1e-4 if exact else 5e-3
+    assert _relerr(e.enc_states().cpu().numpy(), z["tf_enc_states"]) < tol
+    Vp = (cfg["rnn_config"]["dec_vocab_size"] + 15) // 16 * 16
+    logits = e.debug_fetch("logits").cpu().numpy().reshape(L - 1, B, Vp)[:, :, :int(z["V"])]
+    e.backward()
+    _assert_grads(z, "tf_grad", e, (name, mode, "tf"))
+    # NOTE: `logits` were fetched before backward (the buffer is reused for dlogits in place)
+    assert _relerr(logits, z["tf_logits"]) < (1e-4 if exact else 1e-2)
+    bn = np.concatenate([z[f"tf_bn/CNN_{i}_bn/{k}"] for i in (0, 1) for k in ("avg_mean", "avg_var")])
+    assert _relerr(e.bn_state.cpu().numpy(), bn) < (1e-4 if exact else 2e-3)
+    # scheduled sampling (seq2seq.py:431-436) with the reference's draws
+    from ast_b200.seq2seq import draw_use_true
+    random.seed(int(z["ss_seed"]))
+    bits = draw_use_true(L, 0.5)
+    assert bits == [bool(b) for b in z["ss_bits"]]
+    e = _engine(cfg, D, P, exact, tc)
+    loss = float(e.forward_loss(X, y, use_true=bits))
+    assert abs(loss - float(z["ss_loss"])) <= LOSS_RTOL * abs(float(z["ss_loss"]))
+    if exact:
+        assert (e.step_argmax().cpu().numpy() == z["ss_argmax"]).all()
+    e.backward()
+    _assert_grads(z, "ss_grad", e, (name, mode, "ss"))
+
+
+@pytest.mark.parametrize("mode,exact,tc", MODES)
+@pytest.mark.parametrize("name", ["ref_model_d13", "ref_model_d40"])
+def test_cuda_matches_reference_with_dropout_noise_and_sampling(dev, name, mode, exact, tc):
+    """The reference ran with THIS library's dropout masks (counter RNG at the fixture's seed) and its own recorded input
+    noise: set the same seed, pass the same noise tensor and scheduled-sampling bits, compare directly."""
+    cfg, D, P, z = G.load_model_case(name, dropout=(0.3, 0.3, 0.0))
+    B, L = z["y"].shape
+    e = _engine(cfg, D, P, exact, tc, seed=int(z["do_seed"]))
+    loss = float(e.forward_loss(z["X"], z["y"], use_true=[bool(b) for b in z["do_bits"]], noise=z["do_noise"]))
+    assert abs(loss - float(z["do_loss"])) <= LOSS_RTOL * abs(float(z["do_loss"]))
+    np.testing.assert_allclose(_step_losses(e, L, B), z["do_step_losses"], rtol=LOSS_RTOL, atol=1e-6)
+    assert _relerr(e.enc_states().cpu().numpy(), z["do_enc_states"]) < (1e-4 if exact else 5e-3)
+    e.backward()
+    _assert_grads(z, "do_grad", e, (name, mode, "dropout"))
+
+
+@pytest.mark.parametrize("name", ["ref_model_d13", "ref_model_d40"])
+def test_cuda_matches_reference_optimizer_greedy_and_beam(dev, name):
+    cfg, D, P, z = G.load_model_case(name)
+    e = _engine(cfg, D, P)
+    m, v, vh = (torch.zeros_like(e.params) for _ in range(3))
+    float(e.forward_loss(z["X"], z["y"]))
+    e.backward()
+    e.opt_step(m, v, vh, 1, 1e-3, 1e-4, 2.0)
+    assert abs(e.last_grad_norm() - float(z["tf_grad_norm1"])) <= 1e-4 * float(z["tf_grad_norm1"])
+    loss2 = float(e.forward_loss(z["X"], z["y"]))
+    assert abs(loss2 - float(z["tf_loss2"])) <= LOSS_RTOL * abs(float(z["tf_loss2"]))
+    e.backward()
+    e.opt_step(m, v, vh, 2, 1e-3, 1e-4, 2.0)
+    # AMSGrad's first steps move every weight by ~lr * sign(g): elements whose gradient is at round-off level may go the
+    # other way, so the bound is 2 steps * lr (+ slack) per element and a tight mean
+    after = {k: e.view(k).cpu().numpy() for k in e.info}
+    for k, (emax, el2) in G.tensor_errors(z, "tf_param_after2", after).items():
+        want = z[f"tf_param_after2/{k}"]
+        got = after[k].ravel()[::G.C.SAMPLE] if after[k].shape != want.shape else after[k]
+        d = np.abs(got.astype(np.float64) - want)
+        assert d.max() <= 4.5e-3 and d.mean() <= 2e-5, (k, d.max(), d.mean())
+    # decoding: fresh model with the EOS-boosted bias, exactly one training-mode forward, then eval
+    cfg, D, P, z = G.load_model_case(name, eos_boost=True)
+    e = _engine(cfg, D, P)
+    float(e.forward_loss(z["X"], z["y"]))
+    pred = e.predict(z["X"], O.GO_ID, O.EOS_ID, 12).cpu().numpy()
+    assert pred.shape == z["greedy_f32"].shape and (pred == z["greedy_f32"]).all()
+    from ast_b200.nn import beam_result_to_entries
+    for (N, K, stop) in ((4, 3, 12), (10, 10, 12), (1, 1, 6), (3, 5, 10)):
+        nb = beam_result_to_entries(e.beam_search(z["X"][0:1], stop, N, K, O.GO_ID, O.EOS_ID))
+        hyps, scores, attn = G.beam_from_fixture(z, N, K)
+        assert [h["hyp"] for h in nb] == hyps, (N, K)
+        np.testing.assert_allclose([float(h["score"]) for h in nb], scores, rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(np.stack([h["attn_history"][-1] for h in nb]), attn, rtol=0, atol=1e-5)
+
+
+# ---- reference fixture, shipped geometry: the kernels bench.py times ---------------------------------------------------------
+@pytest.mark.parametrize("mode,exact,tc", MODES)
+def test_cuda_matches_reference_at_the_shipped_geometry(dev, mode, exact, tc):
+    """experiments/es_en_20h/model_cfg.json as shipped (H=512/E=128/A=512, CNN 128/512, dropout .3/.3), V=1098, D=40,
+    speech_noise .25, teach_ratio .8: tcgen05 recurrences + TMEM-resident decoder (tf32 mode) against what the reference's own
+    source computed with the same masks / noise / draws."""
+    cfg, D, P, z = G.load_full_case()
+    B, L = z["y"].shape
+    e = _engine(cfg, D, P, exact, tc, seed=int(z["do_seed"]))
+    loss = float(e.forward_loss(z["X"], z["y"], use_true=[bool(b) for b in z["do_bits"]], noise=z["do_noise"]))
+    assert abs(loss - float(z["do_loss"])) <= LOSS_RTOL * abs(float(z["do_loss"]))
+    np.testing.assert_allclose(_step_losses(e, L, B), z["do_step_losses"], rtol=LOSS_RTOL, atol=1e-6)
+    assert _relerr(e.enc_states().cpu().numpy(), z["do_enc_states"]) < (1e-4 if exact else 5e-3)
+    e.backward()
+    worst = _assert_grads(z, "do_grad", e, ("full", mode))
+    print(f"[{mode}] loss rel {abs(loss - float(z['do_loss'])) / float(z['do_loss']):.2e}; worst gradient {worst[0]}: "
+          f"max-norm {worst[1][0]:.2e}, l2 {worst[1][1]:.2e}")
+    if exact:
+        cfg, D, P, z = G.load_full_case(eos_boost=True)
+        e = _engine(cfg, D, P)
+        pred = e.predict(z["X"], O.GO_ID, O.EOS_ID, 20).cpu().numpy()
+        assert pred.shape == z["greedy_f32"].shape and (pred == z["greedy_f32"]).all()
+        from ast_b200.nn import beam_result_to_entries
+        nb = beam_result_to_entries(e.beam_search(z["X"][0:1], 40, 10, 10, O.GO_ID, O.EOS_ID))
+        hyps, scores, _ = G.beam_from_fixture(z, 10, 10)
+        assert [h["hyp"] for h in nb] == hyps
+        np.testing.assert_allclose([float(h["score"]) for h in nb], scores, rtol=1e-4, atol=1e-4)
+
+
+# ---- the benchmarked configuration at the benchmarked sizes, against the oracle ---------------------------------------------------
+@pytest.mark.parametrize("B,T,Lmin,Lmax,tag", [(16, 1000, 20, 40, "C1"), (32, 1680, 50, 66, "largest C2 bucket")])
+def test_benchmarked_configuration_matches_oracle_at_full_size(dev, B, T, Lmin, Lmax, tag):
+    """bench.py's configuration (TF32 training mode, dropout .3/.3, speech_noise .25 as an explicit tensor, teach_ratio .8)
+    at C1 (B16 x T1000) and at the largest es_en_20h bucket (B32 x T1680 x L66), against the float64 oracle fed the device's
+    own dropout masks: loss 1e-3, every gradient 1e-2 (max-norm and L2)."""
+    cfg = O.default_model_cfg(vocab=1098, dropout=(0.3, 0.3, 0.0))
+    D = 40
+    P = O.init_params(cfg, D, seed=31)
+    X, y, _ = O.synth_batch(B, T, D, 1098, Lmin, Lmax, seed=32, Tmin=T - 79)
+    L = y.shape[1]
+    rng = np.random.default_rng(33)
+    noise = rng.normal(1.0, 0.25, size=X.shape).astype(np.float32)
+    bits = [True if not (0 < i < L - 2) else bool(rng.random() < 0.8) for i in range(L - 1)]
+    e = _engine(cfg, D, P, 0, 1, seed=77)
+    loss = float(e.forward_loss(X, y, use_true=bits, noise=noise))
+    am = e.step_argmax().cpu().numpy()
+    e.backward()
+    torch.cuda.synchronize()
+    g_dev = _grads(e)
+    Tp = e.Tp
+    om = O.OracleModel(cfg, P, dtype=np.float64)
+    om.dropout_masks = {k: v.astype(np.float64) for k, v in R.training_masks(77, 1, B, Tp, L - 1, 256, 512, 128, 3, 0.3, 0.3).items()}
+    want = float(om.forward_loss(X, y, tf_bits=bits, noise=noise))
+    g = om.backward()
+    assert abs(loss - want) <= LOSS_RTOL * abs(want), (tag, loss, want)
+    worst = ("", 0.0, 0.0)
+    for k in e.info:
+        emax, el2 = _relerr(g_dev[k], g[k]), _l2err(g_dev[k], g[k])
+        assert emax <= GRAD_RTOL and el2 <= 2 * GRAD_RTOL, (tag, k, emax, el2)
+        if emax > worst[1]:
+            worst = (k, emax, el2)
+    flips = float((am != np.stack(om.step_argmax)).mean())
+    print(f"[{tag}] loss rel {abs(loss - want) / abs(want):.2e}; worst gradient {worst[0]}: max-norm {worst[1]:.2e}, l2 {worst[2]:.2e}; "
+          f"argmax flips {flips:.4f}")
+    assert flips <= 0.02            # TF32 training does not reproduce every near-tie of scheduled sampling
+
+
+# ---- A2: multiplicative input noise ---------------------------------------------------------------------------------------------------
+def test_input_noise_explicit_tensor_and_device_rng(dev):
+    """seq2seq.py:297-305: X * N(1, sigma).  An explicit tensor reproduces the oracle's `noise=` path exactly; the device
+    generator (Box-Muller on the counter RNG) has mean 1, std sigma, is a function of (seed, step) only and is off in eval."""
+    from ast_b200._lib import check, load, ptr
+    import ctypes as C
+    cfg = O.default_model_cfg(vocab=64)
+    P = O.init_params(cfg, 40, seed=8)
+    X, y, _ = O.synth_batch(3, 120, 40, 64, 4, 6, seed=9, Tmin=100)
+    noise = np.random.default_rng(10).normal(1.0, 0.25, X.shape).astype(np.float32)
+    om = O.OracleModel(cfg, P, dtype=np.float64)
+    want = float(om.forward_loss(X, y, noise=noise))
+    plain = float(O.OracleModel(cfg, P, dtype=np.float64).forward_loss(X, y))
+    e = _engine(cfg, 40, P)
+    got = float(e.forward_loss(X, y, noise=noise))
+    assert abs(got - want) <= 1e-5 * abs(want) and abs(want - plain) > 1e-4
+    assert _relerr(e.enc_states().cpu().numpy(), om.enc_states) < 1e-4
+    e.backward()
+    g = om.backward()
+    for k in e.info:
+        assert _relerr(e.view(k, grad=True).cpu().numpy(), g[k]) <= GRAD_RTOL, k
+    # the generator itself, through the pack kernel on a tensor of ones
+    lib = load()
+    B, T, D = 8, 1000, 40
+    raw = torch.ones(B * T, D, device=dev)
+    off = torch.arange(B, dtype=torch.int64, device=dev) * T
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    outs = []
+    for seed in (42, 42, 43):
+        Xn = torch.empty(B, T, D, device=dev)
+        check(lib.ast_pack_cmvn(ptr(raw), ptr(off), ptr(lens), None, None, None, None, 0.25, seed, ptr(Xn), B, T, D,
+                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        outs.append(Xn.cpu().numpy().astype(np.float64))
+    a = outs[0].ravel()
+    assert abs(a.mean() - 1.0) < 2e-3 and abs(a.std() - 0.25) < 2e-3
+    assert abs(((a - 1) ** 3).mean()) < 1e-3 and abs(((a - 1) / 0.25) ** 4).mean() - 3.0 < 0.1      # symmetric, Gaussian kurtosis
+    assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
+    # eval mode: no noise (chainer.config.train is False, seq2seq.py:297)
+    e2 = _engine(cfg, 40, P)
+    e2.encode(X, train=False, noise_sigma=0.25)
+    e3 = _engine(cfg, 40, P)
+    e3.encode(X, train=False)
+    assert np.array_equal(e2.enc_states().cpu().numpy(), e3.enc_states().cpu().numpy())
+
+
+# ---- C5: beam-10 on long utterances --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,stop", [(1000, 60), (3000, 45)])
+def test_beam10_long_utterances_match_oracle(dev, T, stop):
+    """BASELINE config 5: T up to 3000 frames (T' = 750), V = 1098, N = K = 10, >= 40 steps; the EOS bias is raised so that
+    some hypotheses finish and are carried along (nn.py:317-318) while others run to the limit."""
+    from ast_b200.nn import beam_result_to_entries
+    cfg = O.default_model_cfg(vocab=1098)
+    P = O.init_params(cfg, 40, seed=41)
+    P["out/W"] = P["out/W"] * 3.0
+    P["out/b"] = P["out/b"].copy()
+    P["out/b"][O.EOS_ID] += 1.4
+    X = np.random.default_rng(42 + T).standard_normal((1, T, 40)).astype(np.float32)
+    om = O.OracleModel(cfg, P, dtype=np.float32)
+    want = om.decode_beam(X, stop, 10, 10)
+    e = _engine(cfg, 40, P)
+    got = beam_result_to_entries(e.beam_search(X, stop, 10, 10, O.GO_ID, O.EOS_ID))
+    assert [h["hyp"] for h in got] == [list(map(int, h["hyp"])) for h in want]
+    np.testing.assert_allclose([float(h["score"]) for h in got], [float(h["score"]) for h in want], rtol=1e-4, atol=1e-4)
+    lens = [len(h["hyp"]) for h in got]
+    assert max(lens) >= 41, lens
+    np.testing.assert_allclose(np.stack([h["attn_history"][-1] for h in got]), np.stack([h["attn_history"][-1] for h in want]),
+                               rtol=0, atol=1e-5)
+
+
+# ---- runtime level: the reference's NN.train_epoch / predict on an on-disk corpus ------------------------------------------------------
+@pytest.mark.parametrize("name", ["ref_epoch_fisher_d13", "ref_epoch_gp_d40_freeze"])
+def test_nn_train_epoch_and_predict_match_reference(dev, name, tmp_path):
+    """ast_b200.nn.NN(cfg_path) on the experiment directory the reference trained on (rebuilt from the fixture's arguments):
+    resume from seq2seq_0.model with a lazily shaped model, bucketed epoch with frame zeroing + scheduled sampling + frozen links,
+    dev-set greedy prediction, ids -> text, save_npz key set - against what the reference's own train_epoch / predict produced."""
+    from ast_b200.nn import NN
+    from ast_b200 import serializers
+    z = G.load(name)
+    exp = G.rebuild_epoch_corpus(z, str(tmp_path))
+    np.random.seed(int(z["np_seed"]))
+    nn = NN(exp)
+    assert nn.max_epoch == 0 and nn.model._engine is not None and nn.model._feat_dim == int(z["D"])
+    P0 = {k: nn.model._engine.view(k).cpu().numpy().copy() for k in nn.model._engine.info}
+    avg = nn.train_epoch("fisher_train")
+    assert abs(avg - float(z["epoch_avg_loss"])) <= LOSS_RTOL * abs(float(z["epoch_avg_loss"]))
+    after = {k: nn.model._engine.view(k).cpu().numpy() for k in nn.model._engine.info}
+    freeze = [str(s) for s in z["freeze"]]
+    for k in after:
+        want = z[f"param_after/{k}"]
+        got = after[k].ravel()[::G.C.SAMPLE]
+        d = np.abs(got.astype(np.float64) - want)
+        assert d.max() <= 3 * 1.5e-3 and d.mean() <= 3e-5, (k, d.max(), d.mean())
+        if any(k.startswith(f + "/") for f in freeze):
+            assert np.array_equal(after[k], P0[k]), k                # disable_update(): bit-identical
+        else:
+            assert not np.array_equal(after[k], P0[k]), k
+    preds = nn.predict("fisher_dev")
+    assert [u for u, _ in preds] == [str(u) for u in z["pred_utts"]]
+    assert [t for _, p in preds for t in p] == z["pred_tokens"].tolist()
+    hyps = nn.data_loader.get_hyps(preds)
+    assert [" ".join(hyps[u]) for u, _ in preds] == [str(t) for t in z["pred_text"]]
+    ck = os.path.join(str(tmp_path), "saved.model")
+    serializers.save_npz(ck, nn.model)
+    with np.load(ck) as f:
+        assert sorted(f.files) == [str(k) for k in z["npz_keys"]]
+
+
+def test_compute_context_vector_matches_oracle(dev):
+    """seq2seq.py:336-358 through the drop-in's public method (and its legacy alias `attention`)."""
+    from ast_b200.seq2seq import SpeechEncoderDecoder, config as train_config
+    cfg = O.default_model_cfg(vocab=64)
+    P = O.init_params(cfg, 40, seed=51)
+    P["attn_Wa/b"] = np.random.default_rng(1).standard_normal(512).astype(np.float32) * 0.1
+    X, _, _ = O.synth_batch(4, 130, 40, 64, 4, 6, seed=52, Tmin=100)
+    m = SpeechEncoderDecoder(0, cfg, feat_dim=40)
+    m.load_state(P)
+    train_config.train = False
+    try:
+        m.encode(X)
+        om = O.OracleModel(cfg, P, dtype=np.float64)
+        om.train = False
+        om.encode(X)
+        h = np.random.default_rng(2).standard_normal((4, 512)).astype(np.float32)
+        cv, al, _ = om.compute_context_vector(h.astype(np.float64))
+        got_cv, got_al = m.compute_context_vector(h, m.attn_Wa)
+        assert tuple(got_al.shape) == (4, om.enc_states.shape[1], 1)
+        assert _relerr(got_cv.data.cpu().numpy(), cv) < 1e-5 and _relerr(got_al.data.cpu().numpy()[:, :, 0], al) < 1e-5
+        got2, _ = m.attention(h)
+        assert np.array_equal(got2.data.cpu().numpy(), got_cv.data.cpu().numpy())
+        # a foreign attention link (another model's attn_Wa, as decode_step does for n_attn > 1: seq2seq.py:381-383)
+        other = SpeechEncoderDecoder(0, cfg, feat_dim=40)
+        Q = dict(P)
+        Q["attn_Wa/W"] = (P["attn_Wa/W"] * -0.5).astype(np.float32)
+        other.load_state(Q)
+        om.p["attn_Wa/W"] = Q["attn_Wa/W"].astype(np.float64)
+        cv3, al3, _ = om.compute_context_vector(h.astype(np.float64))
+        got3, gal3 = m.compute_context_vector(h, other.attn_Wa)
+        assert _relerr(got3.data.cpu().numpy(), cv3) < 1e-5 and _relerr(gal3.data.cpu().numpy()[:, :, 0], al3) < 1e-5
+    finally:
+        train_config.train = True
