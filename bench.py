@@ -453,8 +453,8 @@ def parity_block(torch, precision):
     from oracle import device_rng as R
     cfg = model_cfg()
     B, T, Lmin, Lmax, seed = 6, 200, 8, 12, 4321
-    P = O.init_params(cfg, D, seed=3)
-    P["out/W"] = P["out/W"] * 3.0
+    from oracle.ref_golden_common import golden_params
+    P = {k: (v.astype(np.float32) if v.dtype.kind == "f" else v) for k, v in golden_params(cfg, D, 3).items()}
     X, y, _ = O.synth_batch(B, T, D, V, Lmin, Lmax, seed=5, Tmin=T - 60)
     L = y.shape[1]
     rng = np.random.default_rng(6)
@@ -502,13 +502,18 @@ def parity_block(torch, precision):
     nb_w = om32.decode_beam(X[0:1], 24, 10, 10)
     nb_g = beam_result_to_entries(e.beam_search(X[0:1], 24, 10, 10, O.GO_ID, O.EOS_ID))
     beam_ok = [list(map(int, h["hyp"])) for h in nb_w] == [h["hyp"] for h in nb_g]
-    score_err = float(max(abs(float(a["score"]) - float(b["score"])) for a, b in zip(nb_w, nb_g))) if beam_ok else None
+    score_err = float(max(abs(float(a["score"]) - float(b["score"])) for a, b in zip(nb_w, nb_g)))
+    beam_detail = None
+    if not beam_ok:      # say what differs: a permutation among (near-)equal scores, or different token sequences
+        sw, sg = sorted(tuple(map(int, h["hyp"])) for h in nb_w), sorted(tuple(h["hyp"]) for h in nb_g)
+        beam_detail = {"same_set_of_hypotheses": sw == sg, "oracle_scores": [float(h["score"]) for h in nb_w],
+                       "device_scores": [float(h["score"]) for h in nb_g]}
     return {"against": "numpy restatement of the reference (oracle/, pinned to the reference's own source by tests/golden/ref_*.npz)",
             "config": f"shipped geometry, B{B} x T{T} x L{L}, dropout .3/.3 (device masks injected into the oracle), speech_noise .25, "
                       f"teach_ratio .8, {precision} training mode; decode in the fp32-faithful mode",
             "loss_rel": abs(loss - want) / abs(want), "grad_rel_max": gmax, "grad_rel_max_tensor": worst, "grad_l2_rel_max": gl2,
             "greedy_identical": greedy_ok, "beam_identical": bool(beam_ok), "beam_score_abs_err": score_err,
-            "beam_hyp_lens": [len(h["hyp"]) for h in nb_g],
+            "beam_hyp_lens": [len(h["hyp"]) for h in nb_g], "beam_detail": beam_detail,
             "tolerances": {"loss_rel": 1e-3, "grad_rel": 1e-2}}
 
 

@@ -496,9 +496,12 @@ class OracleModel:
         return logits, ht_new, alpha[:, :, None]
 
     # ---- loss: seq2seq.py:399-473 -----------------------------------------------------
-    def forward_loss(self, X, y, tf_bits: Optional[Sequence[bool]] = None, noise=None):
+    def forward_loss(self, X, y, tf_bits: Optional[Sequence[bool]] = None, noise=None, feedback=None):
         """Sum over decode steps of the batch-mean, PAD-weighted CE.  ``tf_bits`` are the
-        scheduled-sampling draws (see teacher_forcing_bits); None == teach_ratio 1."""
+        scheduled-sampling draws (see teacher_forcing_bits); None == teach_ratio 1.
+        ``feedback`` ((L-1, B) ints, test hook): tokens fed back at sampled steps INSTEAD of this model's own argmax -
+        lets a gradient comparison against an implementation in lower precision (whose argmax may flip on a near-tie
+        and then follows a different, equally valid, trajectory) be made along the same token path."""
         X = np.asarray(X, dtype=self.dtype)
         y = np.asarray(y)
         B, L = y.shape
@@ -521,6 +524,8 @@ class OracleModel:
             loss = loss + li
             self.step_losses.append(float(li))
             self.step_argmax.append(decoder_input.copy())
+            if feedback is not None:
+                decoder_input = np.asarray(feedback[i]).astype(np.int64)
             self._dec_cache.append(self._last_dec + (dz,))
         self.loss = loss
         return loss

@@ -114,12 +114,13 @@ def test_cuda_matches_reference_teacher_forced_and_sampled_steps(dev, name, mode
     np.testing.assert_allclose(_step_losses(e, L, B), z["tf_step_losses"], rtol=LOSS_RTOL, atol=1e-6)
     tol = 1e-4 if exact else 5e-3
     assert _relerr(e.enc_states().cpu().numpy(), z["tf_enc_states"]) < tol
-    Vp = (cfg["rnn_config"]["dec_vocab_size"] + 15) // 16 * 16
-    logits = e.debug_fetch("logits").cpu().numpy().reshape(L - 1, B, Vp)[:, :, :int(z["V"])]
+    # per-step logits = out(ht) (seq2seq.py:394): the library's logits buffer already holds d(logits) (the CE kernel works in
+    # place), so take the attentional states it kept for backward and apply the output layer here
+    ht = e.debug_fetch("ht").cpu().numpy().reshape(L - 1, B, -1).astype(np.float64)
+    logits = ht @ np.asarray(P["out/W"], np.float64).T + np.asarray(P["out/b"], np.float64)
+    assert _relerr(logits, z["tf_logits"]) < (1e-4 if exact else 1e-2)
     e.backward()
     _assert_grads(z, "tf_grad", e, (name, mode, "tf"))
-    # NOTE: `logits` were fetched before backward (the buffer is reused for dlogits in place)
-    assert _relerr(logits, z["tf_logits"]) < (1e-4 if exact else 1e-2)
     bn = np.concatenate([z[f"tf_bn/CNN_{i}_bn/{k}"] for i in (0, 1) for k in ("avg_mean", "avg_var")])
     assert _relerr(e.bn_state.cpu().numpy(), bn) < (1e-4 if exact else 2e-3)
     # scheduled sampling (seq2seq.py:431-436) with the reference's draws
@@ -238,21 +239,31 @@ def test_benchmarked_configuration_matches_oracle_at_full_size(dev, B, T, Lmin, 
     torch.cuda.synchronize()
     g_dev = _grads(e)
     Tp = e.Tp
+    masks = {k: v.astype(np.float64) for k, v in R.training_masks(77, 1, B, Tp, L - 1, 256, 512, 128, 3, 0.3, 0.3).items()}
     om = O.OracleModel(cfg, P, dtype=np.float64)
-    om.dropout_masks = {k: v.astype(np.float64) for k, v in R.training_masks(77, 1, B, Tp, L - 1, 256, 512, 128, 3, 0.3, 0.3).items()}
-    want = float(om.forward_loss(X, y, tf_bits=bits, noise=noise))
+    om.dropout_masks = masks
+    own = float(om.forward_loss(X, y, tf_bits=bits, noise=noise))
+    flips = float((am != np.stack(om.step_argmax)).mean())
+    # TF32 arithmetic may flip an argmax on a near-tie; a flipped token at a sampled step then feeds a different (equally
+    # valid) trajectory, which is a property of scheduled sampling, not a gradient error: the gradient comparison runs the
+    # oracle along the device's token path (`feedback`), the flip rate and the loss along the oracle's OWN path are asserted too
+    assert flips <= 0.02, flips
+    assert abs(loss - own) <= 5 * LOSS_RTOL * abs(own), (tag, loss, own)
+    om = O.OracleModel(cfg, P, dtype=np.float64)
+    om.dropout_masks = masks
+    want = float(om.forward_loss(X, y, tf_bits=bits, noise=noise, feedback=am))
     g = om.backward()
     assert abs(loss - want) <= LOSS_RTOL * abs(want), (tag, loss, want)
     worst = ("", 0.0, 0.0)
     for k in e.info:
         emax, el2 = _relerr(g_dev[k], g[k]), _l2err(g_dev[k], g[k])
-        assert emax <= GRAD_RTOL and el2 <= 2 * GRAD_RTOL, (tag, k, emax, el2)
         if emax > worst[1]:
             worst = (k, emax, el2)
-    flips = float((am != np.stack(om.step_argmax)).mean())
-    print(f"[{tag}] loss rel {abs(loss - want) / abs(want):.2e}; worst gradient {worst[0]}: max-norm {worst[1]:.2e}, l2 {worst[2]:.2e}; "
-          f"argmax flips {flips:.4f}")
-    assert flips <= 0.02            # TF32 training does not reproduce every near-tie of scheduled sampling
+    print(f"[{tag}] loss rel {abs(loss - want) / abs(want):.2e} (own path {abs(loss - own) / abs(own):.2e}); worst gradient {worst[0]}: "
+          f"max-norm {worst[1]:.2e}, l2 {worst[2]:.2e}; argmax flips {flips:.4f}")
+    for k in e.info:
+        emax, el2 = _relerr(g_dev[k], g[k]), _l2err(g_dev[k], g[k])
+        assert emax <= GRAD_RTOL and el2 <= 2 * GRAD_RTOL, (tag, k, emax, el2)
 
 
 # ---- A2: multiplicative input noise ---------------------------------------------------------------------------------------------------
