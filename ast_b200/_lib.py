@@ -66,6 +66,8 @@ SIGNATURES = {
     "ast_attention": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "ast_predict": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(_I), _P]),
     "ast_beam_search": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P, _P, _P, _P]),
+    "ast_beam_search_batch": (_I, [_P, _P, C.POINTER(_I), _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P,
+                                   _I, _P, _P, _P]),
     "ast_pack_cmvn": (_I, [_P, _P, _P, _P, _P, _P, _P, _F, _ULL, _P, _I, _I, _I, _P]),
     "ast_softmax_ce": (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     "ast_gemm": (_I, [_I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _P]),

@@ -22,11 +22,27 @@ def get_best_hyps(utts_beam, W):
     return preds
 
 
-def decode_set(nn, set_key, N, K, stop_limit=None, in_flight=1):
+def decode_set(nn, set_key, N, K, stop_limit=None, in_flight=1, batch=0):
     """beam.py:105-124: per-utterance decode_beam over a data set -> {utt: [(hyp, score, attn_history)]}.
-    in_flight > 1 decodes that many utterances concurrently (BeamPool): same hypotheses, ~4x the utterances/s at 8."""
+    batch > 1 searches that many utterances in lock-step on the device (NN.decode_beam_batch: one pass over the decoder weights
+    per step for all of them); in_flight > 1 decodes that many utterances concurrently on engine replicas (BeamPool).
+    Either way every utterance gets the hypotheses of the sequential loop."""
     stop_limit = nn.cfg.train["data"]["max_pred"] if stop_limit is None else stop_limit
     beam = {}
+    if batch > 1:
+        pend = []
+
+        def flush():
+            for b, n_best in zip(pend, nn.decode_beam_batch([b["X"] for b in pend], stop_limit, N, K)):
+                beam[b["utts"][0]] = [(e["hyp"], e["score"], e["attn_history"]) for e in n_best]
+            pend.clear()
+        for utt in nn.data_loader.get_batch(1, set_key, train=False, labels=False):
+            pend.append(utt)
+            if len(pend) == min(batch, 32):
+                flush()
+        if pend:
+            flush()
+        return beam
     if in_flight > 1:
         from .nn import beam_result_to_entries, using_config
         batches = list(nn.data_loader.get_batch(1, set_key, train=False, labels=False))

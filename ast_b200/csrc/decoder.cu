@@ -16,16 +16,39 @@ template <int MT, bool EXACT>
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_kernel(SkinnyArgs p) {
     __shared__ SkinnySmem sm;
+    if (blockIdx.y > 0) {
+        // more than 32 rows (beam search batched over utterances: rows = utterances x hypotheses): this CTA's 32-row block.
+        // Rows are independent, so a block is the same problem with every per-row pointer moved down by r0 rows.
+        const size_t r0 = (size_t)blockIdx.y * 32;
+        p.B = min(32, p.B - (int)r0);
+        p.X[0] += r0 * p.ldx[0];
+        if (p.K[1] > 0) p.X[1] += r0 * p.ldx[1];
+        if (p.Y) p.Y += r0 * p.ldy;
+        if (p.Y2) p.Y2 += r0 * p.ldy2;
+        if (p.add) p.add += r0 * p.ld_add;
+        if (p.aux) p.aux += r0 * p.ld_aux;
+        if (p.epi == EPI_LSTM) {
+            const size_t Hh = (size_t)(p.N >> 2);
+            p.c_prev += r0 * Hh; p.c_out += r0 * Hh; p.h_out += r0 * Hh; p.hd_out += r0 * p.ld_hd;
+            p.drop_base += r0 * Hh;
+        }
+    } else if (p.B > 32) {
+        p.B = 32;
+    }
     skinny_tile<MT, EXACT>(p, blockIdx.x * SK_COLS, sm);
 }
 
 int skinny(cudaStream_t st, const SkinnyArgs& p, bool exact) {
-    AST_CHECK(p.B >= 1 && p.B <= 32, "skinny: batch %d unsupported (1..32)", p.B);
+    AST_CHECK(p.B >= 1, "skinny: batch %d unsupported", p.B);
+    if (p.B > 32) {
+        AST_CHECK(p.epi == EPI_NONE || p.epi == EPI_TANH || p.epi == EPI_LSTM, "skinny: more than 32 rows only for the forward epilogues");
+        AST_CHECK(!p.sc_demb, "skinny: more than 32 rows not supported with the embedding scatter");
+    }
     AST_CHECK(p.K[0] % 16 == 0 && p.K[1] % 16 == 0, "skinny: K (%d,%d) must be multiples of 16", p.K[0], p.K[1]);
     AST_CHECK(p.ldx[0] % 4 == 0 && p.ldw[0] % 4 == 0 && (p.K[1] == 0 || (p.ldx[1] % 4 == 0 && p.ldw[1] % 4 == 0)),
               "skinny: leading dims must be multiples of 4");
     if (p.epi == EPI_LSTM) AST_CHECK(p.N % 16 == 0, "skinny: LSTM epilogue needs N %% 16 == 0");
-    const int grid = cdiv(p.N, SK_COLS);
+    const dim3 grid(cdiv(p.N, SK_COLS), cdiv(p.B, 32));
     if (p.B <= 16) {
         if (exact) skinny_kernel<1, true><<<grid, SK_THREADS, 0, st>>>(p);
         else skinny_kernel<1, false><<<grid, SK_THREADS, 0, st>>>(p);
@@ -114,6 +137,40 @@ int attn_ctx(cudaStream_t st, const float* enc, long long enc_bs, const float* s
     AST_CHECK(H % 4 == 0 && ld_cv % 4 == 0, "attn_ctx: H/ld must be multiples of 4");
     dim3 grid(cdiv(H, 128), B);
     attn_ctx_kernel<<<grid, 256, sizeof(float) * (Tp + 4 + 8 * 128), st>>>(enc, enc_bs, s, alpha, cv, ld_cv, Tp, H);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// Grouped attention (beam search batched over utterances): row b attends over the encoder states of utterance b / rows_per_enc,
+// which has its OWN length lens[g] <= Tp_ld (utterances of different lengths share one launch; scores / alpha rows are Tp_ld apart
+// and the tail [lens[g], Tp_ld) of alpha is zeroed).  Same arithmetic per row as attn_dot / attn_ctx on that utterance alone.
+__global__ void __launch_bounds__(256) attn_dot_grouped_kernel(const float* __restrict__ enc, long long enc_bs, int rows_per_enc,
+                                                               const int* __restrict__ lens, const float* v, int ldv, float* s,
+                                                               int Tp_ld, int H) {
+    const int b = blockIdx.y, g = b / rows_per_enc;
+    const int Tg = lens[g];
+    if ((int)blockIdx.x * 8 >= Tg) return;
+    attn_dot_block(enc + (size_t)g * enc_bs, 0, v + (size_t)b * ldv, ldv, s + (size_t)b * Tp_ld, Tg, H, 0, blockIdx.x);
+}
+__global__ void __launch_bounds__(256) attn_ctx_grouped_kernel(const float* __restrict__ enc, long long enc_bs, int rows_per_enc,
+                                                               const int* __restrict__ lens, const float* s, float* alpha, float* cv,
+                                                               int ld_cv, int Tp_ld, int H) {
+    extern __shared__ float dsm[];
+    __shared__ float scratch[32];
+    const int b = blockIdx.y, g = b / rows_per_enc;
+    const int Tg = lens[g];
+    attn_ctx_block(enc + (size_t)g * enc_bs, 0, s + (size_t)b * Tp_ld, alpha + (size_t)b * Tp_ld, cv + (size_t)b * ld_cv, ld_cv, Tg, H, 0,
+                   blockIdx.x, dsm, dsm + ((Tg + 3) & ~3), scratch);
+    if (blockIdx.x == 0)
+        for (int t = Tg + threadIdx.x; t < Tp_ld; t += blockDim.x) alpha[(size_t)b * Tp_ld + t] = 0.f;
+}
+int attn_grouped(cudaStream_t st, const float* enc, long long enc_bs, int rows_per_enc, const int* lens, const float* q, int ldq,
+                 float* scores, float* alpha, float* cv, int ld_cv, int rows, int Tp_ld, int H) {
+    AST_CHECK(H % 4 == 0 && ldq % 4 == 0 && ld_cv % 4 == 0, "attn_grouped: H/ld must be multiples of 4");
+    attn_dot_grouped_kernel<<<dim3(cdiv(Tp_ld, 8), rows), 256, 0, st>>>(enc, enc_bs, rows_per_enc, lens, q, ldq, scores, Tp_ld, H);
+    AST_LAUNCH_OK();
+    attn_ctx_grouped_kernel<<<dim3(cdiv(H, 128), rows), 256, sizeof(float) * (Tp_ld + 4 + 8 * 128), st>>>(enc, enc_bs, rows_per_enc, lens,
+                                                                                                      scores, alpha, cv, ld_cv, Tp_ld, H);
     AST_LAUNCH_OK();
     return 0;
 }

@@ -167,6 +167,8 @@ int embed_concat(cudaStream_t st, const float* emb, const int* y, int ldy_tok, c
 int embed_scatter(cudaStream_t st, float* demb, const float* dx0, int ld_dx, const int* words, int B, int E, int step,
                   float drop, unsigned long long seed, unsigned drop_stream);
 int attn_dot(cudaStream_t st, const float* enc, long long enc_bs, const float* v, int ldv, float* s, int B, int Tp, int H);
+int attn_grouped(cudaStream_t st, const float* enc, long long enc_bs, int rows_per_enc, const int* lens, const float* q, int ldq,
+                 float* scores, float* alpha, float* cv, int ld_cv, int rows, int Tp_ld, int H);
 int attn_ctx(cudaStream_t st, const float* enc, long long enc_bs, const float* s, float* alpha, float* cv, int ld_cv,
              int B, int Tp, int H);
 int attn_bwd(cudaStream_t st, const float* enc, float* d_enc, long long enc_bs, const float* alpha, const float* dalpha,
@@ -217,6 +219,10 @@ struct BeamSeq {
     int* hist_parent; int* hist_tok; float* alpha_hist;
 };
 int beam_seq(cudaStream_t st, const BeamSeq& p);
+int beam_step_batch(cudaStream_t st, int G, const float* z, int ldz, int V, int K, int N, const BeamState& bs, float* cand_lp,
+                    int* cand_tok, int step, int eos, int stop_limit, int* hist_parent, int* hist_tok, const BeamGather& gd, int Tp_ld,
+                    const float* alpha_step, float* alpha_hist, const int* last_tok_prev, int* last_tok_next);
+int beam_all_done(cudaStream_t st, const int* done, int G, int* all_done);
 int beam_topk(cudaStream_t st, const float* z, int ldz, int V, int K, int N, const BeamState& bs, float* cand_lp, int* cand_tok);
 int beam_prune(cudaStream_t st, const BeamState& bs, const float* cand_lp, const int* cand_tok, int N, int K, int step,
                int eos, int* hist_parent, int* hist_tok);

@@ -116,6 +116,7 @@ struct ast_model {
     float *s_x0, *s_act, *s_hd[MAXL], *s_q, *s_scores, *s_alpha, *s_cvh, *s_htout, *s_logits;
     int *s_words[2], *s_argmax, *g_preds, *g_seen, *g_done;
     float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
+    float* bb_enc = nullptr; int* bb_ints = nullptr; int bb_G = 0, wsTp = 0;      // batched beam search (ast_beam_search_batch)
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
@@ -317,6 +318,10 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->b_cand_tok = a.get<int>((size_t)Bd * 64);
     m->b_score = a.get<float>(Bd); m->b_new_score = a.get<float>(Bd);
     m->b_ints = a.get<int>((size_t)4 * Bd + 8);
+    // beam search batched over utterances: encoder-state bank [min(Bd, 32)][T'][H], per-utterance lengths and scalars
+    m->bb_G = std::min(Bd, 32); m->wsTp = Tp;
+    m->bb_enc = a.get<float>((size_t)m->bb_G * Tp * H);
+    m->bb_ints = a.get<int>((size_t)m->bb_G * 4 + 8);
 }
 
 static cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -658,6 +663,8 @@ struct StepIO {
     float* act[MAXL]; const float* h_prev[MAXL]; const float* c_prev[MAXL]; float* h_out[MAXL]; float* c_out[MAXL];
     float* hd[MAXL]; int ld_hd[MAXL];       // post-dropout outputs; top layer -> cvh[:, H:]
     float* q; float* scores; float* alpha; float* cvh; float* ht_out; float* logits;
+    // beam search batched over utterances: row b attends over enc_bank[b / rows_per_enc] (length enc_lens[b / rows_per_enc] <= Tp_ld)
+    const float* enc_bank = nullptr; const int* enc_lens = nullptr; int rows_per_enc = 0; int Tp_ld = 0;
 };
 
 static int dec_step_fwd(ast_model* m, const StepIO& io, cudaStream_t st) {
@@ -685,9 +692,14 @@ static int dec_step_fwd(ast_model* m, const StepIO& io, cudaStream_t st) {
         s.bias = m->p("attn_Wa/b"); s.B = Bd; s.N = H; s.epi = EPI_NONE; s.Y = io.q; s.ldy = H;
         AST_TRY(skinny(st, s, ex));
     }
-    const long long ebs = (m->B == Bd) ? (long long)m->Tp * H : 0;
-    AST_TRY(attn_dot(st, m->enc_states, ebs, io.q, H, io.scores, Bd, m->Tp, H));
-    AST_TRY(attn_ctx(st, m->enc_states, ebs, io.scores, io.alpha, io.cvh, 2 * H, Bd, m->Tp, H));
+    if (io.enc_bank) {
+        AST_TRY(attn_grouped(st, io.enc_bank, (long long)io.Tp_ld * H, io.rows_per_enc, io.enc_lens, io.q, H, io.scores, io.alpha, io.cvh,
+                             2 * H, Bd, io.Tp_ld, H));
+    } else {
+        const long long ebs = (m->B == Bd) ? (long long)m->Tp * H : 0;
+        AST_TRY(attn_dot(st, m->enc_states, ebs, io.q, H, io.scores, Bd, m->Tp, H));
+        AST_TRY(attn_ctx(st, m->enc_states, ebs, io.scores, io.alpha, io.cvh, 2 * H, Bd, m->Tp, H));
+    }
     {   // ht = tanh(context([cv;h]))  (:386-390)
         SkinnyArgs s{}; s.X[0] = io.cvh; s.ldx[0] = 2 * H; s.K[0] = 2 * H; s.W[0] = m->p("context/W"); s.ldw[0] = 2 * H;
         s.bias = m->p("context/b"); s.B = Bd; s.N = A; s.epi = EPI_TANH; s.Y = io.ht_out; s.ldy = A;
@@ -1146,8 +1158,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
 // decode-time helpers: one step on the model's own state banks
 // ------------------------------------------------------------------------------------------------
 static int decode_bank_step(ast_model* m, int bank, int Bd, const int* words, const float* ht_in, float* logits_out,
-                            float* ht_out, float* alpha_out, bool to_post, cudaStream_t st) {
+                            float* ht_out, float* alpha_out, bool to_post, cudaStream_t st, const float* enc_bank = nullptr,
+                            const int* enc_lens = nullptr, int rows_per_enc = 0, int Tp_ld = 0) {
     StepIO io{};
+    io.enc_bank = enc_bank; io.enc_lens = enc_lens; io.rows_per_enc = rows_per_enc; io.Tp_ld = Tp_ld;
     io.Bd = Bd; io.step = 0; io.train = false; io.forced_words = words; io.ht_prev = ht_in;
     io.x0 = m->s_x0;
     for (int l = 0; l < m->NL; ++l) {
@@ -1624,6 +1638,115 @@ int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, 
 }
 
 // ---- stateless kernels ------------------------------------------------------------------------------------
+// decode_beam for G utterances in lock-step (beam.py:110-124 runs them one after the other; nn.py:299-322 per utterance).
+// Every search is the same arithmetic as ast_beam_search on that utterance alone - rows of different utterances never mix:
+// the decoder step runs over rows = G x N (one pass over the 31.6 MB of decoder weights serves every in-flight search), attention
+// is grouped (each row attends over its own utterance's encoder states and length), top-K / prune / gather run per utterance.
+// Utterances of EQUAL length that are adjacent in the input are encoded as one batch (eval mode: BatchNorm uses running
+// statistics, rows are independent), others one by one; an utterance is never padded (the reference encodes it alone).
+int ast_beam_search_batch(ast_model* m, const float* X, const int* lens, int G, int stop_limit, int N, int K, int go_token,
+                          int eos_token, int* n_steps, int* n_hyps, int* enc_lens_out, int* hist_parent, int* hist_tok, float* scores,
+                          float* alpha_hist, int Tp_ld, float* final_states, float* final_attn_v, void* stream) {
+    AST_CHECK(G >= 1 && lens && X, "beam_search_batch: bad arguments");
+    int Tmax = 0; for (int g = 0; g < G; ++g) { AST_CHECK(lens[g] >= 1, "beam_search_batch: empty utterance %d", g); Tmax = std::max(Tmax, lens[g]); }
+    const int R = G * N;
+    AST_TRY(require_ready(m, 1, Tmax, 0, R, stop_limit));
+    AST_CHECK(N >= 1 && N <= 32 && K >= 1 && K <= 64 && K <= m->V, "beam_search_batch: need 1<=N<=32, 1<=K<=min(64,V)");
+    AST_CHECK(G <= m->bb_G && G <= 32, "beam_search_batch: at most %d utterances per call with this workspace", std::min(m->bb_G, 32));
+    AST_CHECK(hist_parent && hist_tok && scores && alpha_hist && n_steps && n_hyps, "beam_search_batch: null output");
+    cudaStream_t st = S_(stream);
+    const int H = m->H, A = m->A, NL = m->NL;
+    int T1, TpMax, S0, Rs; shapes_for(m, Tmax, T1, TpMax, S0, Rs);
+    AST_CHECK(Tp_ld >= TpMax, "beam_search_batch: alpha_hist row length %d < T' = %d", Tp_ld, TpMax);
+    AST_CHECK((size_t)G * Tp_ld <= (size_t)m->bb_G * m->wsTp, "beam_search_batch: encoder bank too small (G=%d, T'=%d)", G, Tp_ld);
+    for (int k = 0; k < 2; ++k) {
+        for (int l = 0; l < NL; ++l) {
+            AST_CUDA_OK(cudaMemsetAsync(m->st_h[k][l], 0, sizeof(float) * R * H, st));
+            AST_CUDA_OK(cudaMemsetAsync(m->st_c[k][l], 0, sizeof(float) * R * H, st));
+        }
+        AST_CUDA_OK(cudaMemsetAsync(m->st_ht[k], 0, sizeof(float) * R * A, st));
+    }
+    // ---- encoders: runs of equal length as one batch ------------------------------------------------------------------
+    std::vector<int> tps(G, 0);
+    size_t xoff = 0;
+    for (int g0 = 0; g0 < G;) {
+        int g1 = g0 + 1;
+        while (g1 < G && lens[g1] == lens[g0] && g1 - g0 < 32) ++g1;
+        const int Be = g1 - g0, T = lens[g0];
+        AST_TRY(require_ready(m, Be, T, 0, R, stop_limit));
+        AST_TRY(encode_impl(m, X + xoff, Be, T, 0, nullptr, 0.f, st));
+        const int Tp = m->Tp;
+        for (int e = 0; e < Be; ++e) {
+            tps[g0 + e] = Tp;
+            AST_CUDA_OK(cudaMemcpyAsync(m->bb_enc + (size_t)(g0 + e) * Tp_ld * H, m->enc_states + (size_t)e * Tp * H, sizeof(float) * (size_t)Tp * H,
+                                        cudaMemcpyDeviceToDevice, st));
+        }
+        // slot 0 of every utterance <- its encoder finals (init_decoder_state, seq2seq.py:318-334); rows are N apart
+        Copy2DBatch cb{}; cb.n = 0;
+        const int h = m->h;
+        for (int l = 0; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) {
+                const float* hsrc = m->Hs[l][d] + (size_t)Tp * Be * h;
+                const float* csrc = m->Cs[l][d] + (size_t)Tp * Be * h;
+                cb.job[cb.n++] = Copy2DJob{hsrc, h, m->st_h[0][l] + (size_t)g0 * N * H + d * h, (long long)N * H, Be, h};
+                cb.job[cb.n++] = Copy2DJob{csrc, h, m->st_c[0][l] + (size_t)g0 * N * H + d * h, (long long)N * H, Be, h};
+                if (cb.n == 16) { AST_TRY(copy2d_multi(st, cb)); cb.n = 0; }
+            }
+        AST_TRY(copy2d_multi(st, cb));
+        xoff += (size_t)Be * T * m->D;
+        g0 = g1;
+    }
+    m->dec_Bd = R;
+    // ---- bookkeeping state: b_ints = [finished R][new_parent R][new_tok R][new_finished R]; bb_ints = [n_active G][done G][steps G][lens G][all_done]
+    int* finished = m->b_ints; int* new_parent = finished + R; int* new_tok = new_parent + R; int* new_fin = new_tok + R;
+    int* n_active = m->bb_ints; int* done = n_active + G; int* steps_done = done + G; int* d_lens = steps_done + G; int* all_done = d_lens + G;
+    std::vector<int> init(4 * G + 1, 0);
+    for (int g = 0; g < G; ++g) { init[g] = 1; init[3 * G + g] = tps[g]; }
+    std::vector<int> w0(R, go_token);
+    AST_CUDA_OK(cudaMemsetAsync(m->b_ints, 0, sizeof(int) * (size_t)4 * R, st));
+    AST_CUDA_OK(cudaMemcpyAsync(m->bb_ints, init.data(), sizeof(int) * (4 * G + 1), cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaMemcpyAsync(m->s_words[0], w0.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaMemcpyAsync(m->s_words[1], w0.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    AST_CUDA_OK(cudaStreamSynchronize(st));
+    AST_CUDA_OK(cudaMemsetAsync(m->b_score, 0, sizeof(float) * R, st));
+    AST_CUDA_OK(cudaMemsetAsync(hist_parent, 0, sizeof(int) * (size_t)G * stop_limit * N, st));
+    AST_CUDA_OK(cudaMemsetAsync(hist_tok, 0xff, sizeof(int) * (size_t)G * stop_limit * N, st));
+    BeamState bs{}; bs.score = m->b_score; bs.finished = finished; bs.n_active = n_active; bs.done = done; bs.steps_done = steps_done;
+    bs.new_score = m->b_new_score; bs.new_parent = new_parent; bs.new_tok = new_tok; bs.new_finished = new_fin;
+    int bank = 0;
+    for (int s = 0; s < stop_limit; ++s) {
+        AST_TRY(decode_bank_step(m, bank, R, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st, m->bb_enc,
+                                 d_lens, N, Tp_ld));
+        BeamGather gd{}; gd.n = 0;
+        for (int l = 0; l < NL; ++l) {
+            gd.cur[gd.n] = m->st_h[bank][l]; gd.post[gd.n] = m->st_hpost[l]; gd.nxt[gd.n] = m->st_h[bank ^ 1][l]; gd.width[gd.n++] = H;
+            gd.cur[gd.n] = m->st_c[bank][l]; gd.post[gd.n] = m->st_cpost[l]; gd.nxt[gd.n] = m->st_c[bank ^ 1][l]; gd.width[gd.n++] = H;
+        }
+        gd.cur[gd.n] = m->st_ht[bank]; gd.post[gd.n] = m->s_htout; gd.nxt[gd.n] = m->st_ht[bank ^ 1]; gd.width[gd.n++] = A;
+        AST_TRY(beam_step_batch(st, G, m->s_logits, m->Vp, m->V, K, N, bs, m->b_cand_lp, m->b_cand_tok, s, eos_token, stop_limit, hist_parent,
+                                hist_tok, gd, Tp_ld, m->s_alpha, alpha_hist, m->s_words[bank], m->s_words[bank ^ 1]));
+        bank ^= 1;
+        if ((s & 15) == 15 || s == stop_limit - 1) {
+            AST_TRY(beam_all_done(st, done, G, all_done));
+            AST_CUDA_OK(cudaMemcpyAsync(m->h_pinned, all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            AST_CUDA_OK(cudaStreamSynchronize(st));
+            if (m->h_pinned[0]) break;
+        }
+    }
+    std::vector<int> host(3 * G);
+    AST_CUDA_OK(cudaMemcpyAsync(host.data(), m->bb_ints, sizeof(int) * 3 * G, cudaMemcpyDeviceToHost, st));
+    AST_CUDA_OK(cudaStreamSynchronize(st));
+    for (int g = 0; g < G; ++g) { n_hyps[g] = host[g]; n_steps[g] = host[2 * G + g]; if (enc_lens_out) enc_lens_out[g] = tps[g]; }
+    AST_CUDA_OK(cudaMemcpyAsync(scores, m->b_score, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
+    if (final_states)
+        for (int l = 0; l < NL; ++l) {
+            AST_CUDA_OK(cudaMemcpyAsync(final_states + (size_t)(2 * l) * R * H, m->st_c[bank][l], sizeof(float) * R * H, cudaMemcpyDeviceToDevice, st));
+            AST_CUDA_OK(cudaMemcpyAsync(final_states + (size_t)(2 * l + 1) * R * H, m->st_h[bank][l], sizeof(float) * R * H, cudaMemcpyDeviceToDevice, st));
+        }
+    if (final_attn_v) AST_CUDA_OK(cudaMemcpyAsync(final_attn_v, m->st_ht[bank], sizeof(float) * R * A, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 int ast_pack_cmvn(const float* raw, const long long* row_off, const int* lens, const float* scale, const float* offset,
                   const unsigned char* keep, const float* noise, float noise_sigma, unsigned long long seed, float* X, int B,
                   int T, int D, void* stream) {

@@ -296,6 +296,17 @@ class Engine:
         self._keep_attn = (dec_h, W, b)
         return cv, alphas
 
+    def softmax_ce(self, logits, targets):
+        """F.softmax_cross_entropy(class_weight=mask_pad_id) + argmax for one step (seq2seq.py:448,468): logits (B,V), targets (B,)
+        -> (row_loss (B,) already divided by B and PAD-weighted, argmax (B,) int32).  The kernel works in place: a copy is passed."""
+        z = self._as_f32(logits).clone()
+        t = self._as_i32(targets).reshape(-1)
+        B, Vv = z.shape
+        row_loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        am = torch.empty(B, dtype=torch.int32, device=self.device)
+        check(self.lib.ast_softmax_ce(ptr(z), Vv, ptr(t), B, Vv, ptr(row_loss), ptr(am), self.stream()), "ast_softmax_ce")
+        return row_loss, am
+
     def predict(self, X, start_token, end_token, stop_limit):
         X = self._as_f32(X)
         B, T, _ = X.shape
@@ -327,6 +338,46 @@ class Engine:
         self.B, self.T, self.Tp = 1, T, Tp
         return dict(n_steps=ns.value, n_hyps=nh.value, hist_parent=hist_parent, hist_tok=hist_tok, scores=scores,
                     alpha_hist=alpha_hist, states=states, attn_v=attn_v)
+
+    def beam_search_batch(self, Xs, stop_limit, N, K, go=1, eos=2):
+        """decode_beam for up to 32 utterances in lock-step (ast_beam_search_batch): Xs = list of (1, T_g, D) / (T_g, D) arrays or
+        tensors of ANY lengths -> list of per-utterance result dicts in the same order, each with the fields of `beam_search`
+        (so nn.beam_result_to_entries applies).  Utterances are sorted by length internally so equal lengths share an encoder
+        batch; every utterance's hypotheses, scores and attention history equal those of `beam_search` on it alone."""
+        G = len(Xs)
+        assert 1 <= G <= 32, "1..32 utterances per call"
+        feats = []
+        for x in Xs:
+            t = self._as_f32(x)
+            t = t.reshape(-1, t.shape[-1])
+            assert t.shape[1] == self.feat_dim
+            feats.append(t)
+        order = sorted(range(G), key=lambda i: feats[i].shape[0])
+        lens = [int(feats[i].shape[0]) for i in order]
+        run = max(sum(1 for _ in grp) for _, grp in __import__("itertools").groupby(lens))
+        Tmax = max(lens)
+        self.ensure_workspace(B=min(run, 32), T=Tmax, N=G * N, steps=stop_limit)
+        Tp_ld = self.enc_len(Tmax)
+        dev = self.device
+        X = torch.cat([feats[i] for i in order], dim=0).contiguous()
+        hist_parent = torch.zeros(G, stop_limit, N, dtype=torch.int32, device=dev)
+        hist_tok = torch.zeros(G, stop_limit, N, dtype=torch.int32, device=dev)
+        scores = torch.zeros(G, N, dtype=torch.float32, device=dev)
+        alpha_hist = torch.zeros(G, stop_limit, N, Tp_ld, dtype=torch.float32, device=dev)
+        states = torch.zeros(self.NL, 2, G * N, self.H, dtype=torch.float32, device=dev)
+        attn_v = torch.zeros(G * N, self.A, dtype=torch.float32, device=dev)
+        IntG = C.c_int * G
+        c_lens, ns, nh, tp = IntG(*lens), IntG(), IntG(), IntG()
+        check(self.lib.ast_beam_search_batch(self.h, ptr(X), c_lens, G, int(stop_limit), int(N), int(K), go, eos, ns, nh, tp,
+                                             ptr(hist_parent), ptr(hist_tok), ptr(scores), ptr(alpha_hist), Tp_ld, ptr(states),
+                                             ptr(attn_v), self.stream()), "ast_beam_search_batch")
+        self._keep = (X,)
+        out = [None] * G
+        for j, i in enumerate(order):
+            out[i] = dict(n_steps=ns[j], n_hyps=nh[j], hist_parent=hist_parent[j], hist_tok=hist_tok[j], scores=scores[j],
+                          alpha_hist=alpha_hist[j][:, :, :tp[j]], states=states[:, :, j * N:(j + 1) * N, :],
+                          attn_v=attn_v[j * N:(j + 1) * N])
+        return out
 
     def stage_times(self):
         """[(stage, ms)] of the last forward_loss + backward (needs set_option('stage_timing', 1)); synchronises."""

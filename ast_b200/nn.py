@@ -307,6 +307,17 @@ class NN:
                             "attn_history": decode_entry["attn_history"] + [alphas.data[0, :, 0].cpu().numpy()]})
             return out
 
+    def decode_beam_batch(self, Xs, stop_limit, N, K):
+        """Throughput form of decode_beam: up to 32 utterances (any lengths) searched in lock-step on the device - one pass over
+        the decoder weights per step serves every in-flight search.  Returns one n_best list per utterance, each identical to
+        decode_beam(X) on that utterance alone (nn.py:299-322)."""
+        Xs = [x.data if isinstance(x, Variable) else x for x in Xs]
+        with using_config("train", False):
+            e = self.model._require(Xs[0])
+            res = e.beam_search_batch(Xs, int(stop_limit), int(N), int(K), SYMBOLS.GO_ID, SYMBOLS.EOS_ID)
+            self.model.enc_states = None
+            return [beam_result_to_entries(r, SYMBOLS.GO_ID) if r["n_steps"] > 0 else [self.init_hyp()] for r in res]
+
     def decode_beam(self, X, stop_limit, N, K):
         """nn.py:299-322 with the search loop, top-K, pruning and state gather on the device."""
         X = X.data if isinstance(X, Variable) else X

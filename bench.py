@@ -348,6 +348,30 @@ def beam_rate_pool(model, torch, T, n_utts, stop_limit, n_streams, N=10, K=10):
             "roofline": beam_roofline(n_utts * stop_limit, dt)}
 
 
+def beam_rate_batch(model, torch, T, n_utts, stop_limit, G, N=10, K=10):
+    """Throughput mode, second generation: G utterances searched in LOCK-STEP by one engine (ast_beam_search_batch): one pass over
+    the decoder weights per step serves all G x N rows, equal-length utterances share an encoder batch.  Host feature buffers in,
+    hypotheses (host lists) out."""
+    from ast_b200.nn import beam_result_to_entries
+    e = model._engine
+    rng = np.random.default_rng(7)
+    utts = [rng.standard_normal((1, T, D), dtype=np.float32) for _ in range(n_utts)]
+    e.beam_search_batch(utts[:G], stop_limit, N, K)                                  # warm (workspace, kernels)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    steps = 0
+    for i in range(0, n_utts, G):
+        res = e.beam_search_batch(utts[i:i + G], stop_limit, N, K)
+        ent = [beam_result_to_entries(r) for r in res]
+        steps += sum(r["n_steps"] for r in res)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    passes = steps / G                                                               # decoder-weight passes actually made
+    return {"utts_per_s": n_utts / dt, "T": T, "stop_limit": stop_limit, "n_utts": n_utts, "N": N, "K": K, "utterances_per_search": G,
+            "us_per_lockstep_step": 1e6 * dt / max(passes, 1), "roofline": beam_roofline(steps, dt),
+            "roofline_note": "achieved = (utterance-steps x 33 MB) / time as SURVEY 8(d) defines it; the lock-step search reads the weights "
+                             "once per step for all utterances, so figures above the HBM peak are possible and mean reuse, not bandwidth"}
+
+
 def beam_cpu_rate(T, stop_limit, n_utts=1, N=10, K=10):
     """The reference's beam search (nn.py:235-322 restated in the numpy oracle) on the host cores, same inputs."""
     from oracle import ast_oracle as O
@@ -752,6 +776,9 @@ def run_ours(args):
                         "T1000_175steps_8_in_flight": beam_rate_pool(model, torch, 1000, 24, 175, 8),
                         "T1000_40steps_8_in_flight": beam_rate_pool(model, torch, 1000, 32, 40, 8),
                         "T3000_40steps_8_in_flight": beam_rate_pool(model, torch, 3000, 24, 40, 8),
+                        "T1000_175steps_lockstep32": beam_rate_batch(model, torch, 1000, 64, 175, 32),
+                        "T1000_40steps_lockstep32": beam_rate_batch(model, torch, 1000, 96, 40, 32),
+                        "T3000_40steps_lockstep32": beam_rate_batch(model, torch, 3000, 64, 40, 32),
                         "in_flight_note": "ast_b200.beam.BeamPool: independent utterances decoded concurrently by engine replicas "
                                           "(own streams / host threads), hypotheses identical to the sequential loop"}
         if not args.no_cpu_baseline:

@@ -129,6 +129,17 @@ int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, 
                     int* n_steps, int* n_hyps, int* hist_parent, int* hist_tok, float* scores, float* alpha_hist,
                     float* final_states, float* final_attn_v, void* stream);
 
+/* The beam.py:110-124 loop over utterances as ONE lock-step search (throughput mode; new work - the reference decodes one utterance
+ * at a time): G <= 32 utterances, X = their features back to back (sum of lens[g] x D floats, device), lens (host) in frames.
+ * Same hypotheses, scores and attention history per utterance as ast_beam_search on it alone; rows of different utterances never mix
+ * (one decoder pass over rows = G x N, grouped attention with per-utterance length, per-utterance top-K / prune / gather).
+ * Outputs are utterance-major: n_steps / n_hyps / enc_lens_out (host, G), hist_parent / hist_tok (G, stop_limit, N), scores (G, N),
+ * alpha_hist (G, stop_limit, N, Tp_ld) with Tp_ld >= the largest T', final_states (2*layers, G*N, H) and final_attn_v (G*N, A) or NULL.
+ * Workspace: ast_bind_workspace with B >= the largest equal-length run (or 1), T >= max lens, N >= G * N, steps >= stop_limit. */
+int ast_beam_search_batch(ast_model* m, const float* X, const int* lens, int G, int stop_limit, int N, int K, int go_token,
+                          int eos_token, int* n_steps, int* n_hyps, int* enc_lens_out, int* hist_parent, int* hist_tok, float* scores,
+                          float* alpha_hist, int Tp_ld, float* final_states, float* final_attn_v, void* stream);
+
 /* ---- stateless kernels (unit-testable pieces; also what a foreign host would call directly) ---- */
 /* Kaldi apply-cmvn + dataloader.py:103,156 pad_sequence (+ :83-93 frame zeroing, seq2seq.py:300 noise) */
 int ast_pack_cmvn(const float* raw, const long long* row_off, const int* lens, const float* scale,
