@@ -284,4 +284,63 @@ int lstm_cell_bwd(cudaStream_t st, float* act, const float* c, const float* c_pr
     return 0;
 }
 
+// =========================================================================================
+// pieces of the tensor-core decode step (beam search: rows = utterances x hypotheses, fp32-faithful 3xTF32 tcgen05 GEMMs)
+// =========================================================================================
+// out[r][0:w0] = src0[r][0:w0], out[r][w0:w0+w1] = src1[r][0:w1], written as the (hi, lo) TF32 split the 3xTF32 GEMM consumes
+// (hi = rna_tf32(x), lo = rna_tf32(x - hi), same rounding as split_tf32).  One float4 per thread; widths are multiples of 4.
+__global__ void split_concat2_kernel(const float* __restrict__ src0, int ld0, int w0, const float* __restrict__ src1, int ld1, int w1,
+                                     float* __restrict__ hi, float* __restrict__ lo, int ldo, int R) {
+    const int w4 = (w0 + w1) >> 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < R * w4; idx += gridDim.x * blockDim.x) {
+        const int r = idx / w4, k = (idx - r * w4) << 2;
+        const float4 v = k < w0 ? __ldcg(reinterpret_cast<const float4*>(src0 + (size_t)r * ld0 + k))
+                                : __ldcg(reinterpret_cast<const float4*>(src1 + (size_t)r * ld1 + (k - w0)));
+        float4 h, l;
+        h.x = __uint_as_float(f2tf32(v.x)); h.y = __uint_as_float(f2tf32(v.y)); h.z = __uint_as_float(f2tf32(v.z)); h.w = __uint_as_float(f2tf32(v.w));
+        l.x = __uint_as_float(f2tf32(v.x - h.x)); l.y = __uint_as_float(f2tf32(v.y - h.y));
+        l.z = __uint_as_float(f2tf32(v.z - h.z)); l.w = __uint_as_float(f2tf32(v.w - h.w));
+        *reinterpret_cast<float4*>(hi + (size_t)r * ldo + k) = h;
+        *reinterpret_cast<float4*>(lo + (size_t)r * ldo + k) = l;
+    }
+}
+int split_concat2(cudaStream_t st, const float* src0, int ld0, int w0, const float* src1, int ld1, int w1, float* hi, float* lo, int ldo, int R) {
+    AST_CHECK(w0 % 4 == 0 && w1 % 4 == 0 && ld0 % 4 == 0 && (w1 == 0 || ld1 % 4 == 0) && ldo % 4 == 0, "split_concat2: widths / strides must be multiples of 4");
+    const int n4 = R * ((w0 + w1) >> 2);
+    split_concat2_kernel<<<std::max(1, std::min(cdiv(n4, 256), 148 * 8)), 256, 0, st>>>(src0, ld0, w0, src1, ld1, w1, hi, lo, ldo, R);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// F.lstm on pre-activations that already include the bias (Appendix A.3, interleaved gates): act <- (a, i, f, o) in place,
+// c = a i + f c_prev, h = o tanh(c); eval mode (no dropout): hd = h
+__global__ void lstm_cell_rows_kernel(float* __restrict__ act, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                      float* __restrict__ h_out, float* __restrict__ hd_out, int ld_hd, int R, int H) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * H) return;
+    const int r = idx / H, j = idx - r * H;
+    const float4 g = __ldcg(reinterpret_cast<const float4*>(act + ((size_t)r * H + j) * 4));
+    const float ga = tanhf(g.x), gi = sigmoidf_(g.y), gf = sigmoidf_(g.z), go = sigmoidf_(g.w);
+    const float c = ga * gi + gf * __ldcg(c_prev + (size_t)r * H + j);
+    const float hv = go * tanhf(c);
+    *reinterpret_cast<float4*>(act + ((size_t)r * H + j) * 4) = make_float4(ga, gi, gf, go);
+    c_out[(size_t)r * H + j] = c;
+    h_out[(size_t)r * H + j] = hv;
+    hd_out[(size_t)r * ld_hd + j] = hv;
+}
+int lstm_cell_rows(cudaStream_t st, float* act, const float* c_prev, float* c_out, float* h_out, float* hd_out, int ld_hd, int R, int H) {
+    lstm_cell_rows_kernel<<<cdiv(R * H, 256), 256, 0, st>>>(act, c_prev, c_out, h_out, hd_out, ld_hd, R, H);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void tanh_rows_kernel(float* __restrict__ x, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = tanhf(x[i]);
+}
+int tanh_rows(cudaStream_t st, float* x, size_t n) {
+    tanh_rows_kernel<<<(int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 8)), 256, 0, st>>>(x, n);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace ast

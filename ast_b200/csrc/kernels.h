@@ -176,6 +176,9 @@ int attn_bwd(cudaStream_t st, const float* enc, float* d_enc, long long enc_bs, 
 int softmax_ce(cudaStream_t st, float* z, int ldz, const int* y, int ldy_tok, int step_next, float* row_loss,
                int* argmax_out, int B, int V, bool write_grad);
 int loss_reduce(cudaStream_t st, const float* row_loss, int n, float* loss);
+int split_concat2(cudaStream_t st, const float* src0, int ld0, int w0, const float* src1, int ld1, int w1, float* hi, float* lo, int ldo, int R);
+int lstm_cell_rows(cudaStream_t st, float* act, const float* c_prev, float* c_out, float* h_out, float* hd_out, int ld_hd, int R, int H);
+int tanh_rows(cudaStream_t st, float* x, size_t n);
 int lstm_cell_bwd(cudaStream_t st, float* act, const float* c, const float* c_prev, const float* d_out, int ld_dout,
                   const float* dh_rec, int ld_dhrec, float* dc, int B, int H, int step_row0, float drop,
                   unsigned long long seed, unsigned drop_stream);

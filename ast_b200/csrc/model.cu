@@ -116,7 +116,12 @@ struct ast_model {
     float *s_x0, *s_act, *s_hd[MAXL], *s_q, *s_scores, *s_alpha, *s_cvh, *s_htout, *s_logits;
     int *s_words[2], *s_argmax, *g_preds, *g_seen, *g_done;
     float *b_cand_lp; int *b_cand_tok; float *b_score, *b_new_score; int *b_ints;
-    float* bb_enc = nullptr; int* bb_ints = nullptr; int bb_G = 0, wsTp = 0;      // batched beam search (ast_beam_search_batch)
+    float* bb_enc = nullptr; int* bb_ints = nullptr; int bb_G = 0, wsTp = 0;
+    // tensor-core decode step (beam search): (hi, lo) TF32 splits of the decoder weights, [W_up | W_lat] concatenated per layer, and of
+    // the step's activations; built lazily (tb_ready) after every weight change
+    float *tb_Wcat_hi[MAXL] = {}, *tb_Wcat_lo[MAXL] = {}, *tb_Wa_hi = nullptr, *tb_Wa_lo = nullptr, *tb_Wc_hi = nullptr, *tb_Wc_lo = nullptr,
+          *tb_Wo_hi = nullptr, *tb_Wo_lo = nullptr, *tb_x_hi = nullptr, *tb_x_lo = nullptr;
+    bool tb_ready = false; int beam_tc = 1;      // batched beam search (ast_beam_search_batch)
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
@@ -319,6 +324,17 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->b_score = a.get<float>(Bd); m->b_new_score = a.get<float>(Bd);
     m->b_ints = a.get<int>((size_t)4 * Bd + 8);
     // beam search batched over utterances: encoder-state bank [min(Bd, 32)][T'][H], per-utterance lengths and scalars
+    for (int l = 0; l < NL; ++l) {
+        m->tb_Wcat_hi[l] = a.get<float>((size_t)4 * H * (m->in_dec(l) + H)); m->tb_Wcat_lo[l] = a.get<float>((size_t)4 * H * (m->in_dec(l) + H));
+    }
+    m->tb_Wa_hi = a.get<float>((size_t)H * H); m->tb_Wa_lo = a.get<float>((size_t)H * H);
+    m->tb_Wc_hi = a.get<float>((size_t)A * 2 * H); m->tb_Wc_lo = a.get<float>((size_t)A * 2 * H);
+    m->tb_Wo_hi = a.get<float>((size_t)m->V * A); m->tb_Wo_lo = a.get<float>((size_t)m->V * A);
+    {
+        const size_t kmax = (size_t)std::max(std::max(E + A + H, 2 * H), A);
+        m->tb_x_hi = a.get<float>((size_t)Bd * kmax); m->tb_x_lo = a.get<float>((size_t)Bd * kmax);
+    }
+    m->tb_ready = false;
     m->bb_G = std::min(Bd, 32); m->wsTp = Tp;
     m->bb_enc = a.get<float>((size_t)m->bb_G * Tp * H);
     m->bb_ints = a.get<int>((size_t)m->bb_G * 4 + 8);
@@ -386,6 +402,25 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     }
     if (ts != st) { AST_CUDA_OK(cudaEventRecord(m->ev_tr, ts)); m->tr_pending = true; }
     m->weights_dirty = false;
+    m->tb_ready = false;
+    return 0;
+}
+
+// (hi, lo) splits of the decoder weights for the tensor-core decode step: [W_up | W_lat] per layer (the step's operand is [x ; h_prev]),
+// attn_Wa, context, out.  Copy into the hi buffer, split in place (element-wise kernel: reads x, writes hi and lo of the same element).
+static int build_beam_weights(ast_model* m, cudaStream_t st) {
+    const int H = m->H, A = m->A;
+    for (int l = 0; l < m->NL; ++l) {
+        const int in = m->in_dec(l), Kl = in + H;
+        const std::string ln = lname(l, "dec");
+        AST_TRY(copy2d(st, m->p((ln + "/upward/W").c_str()), in, m->tb_Wcat_hi[l], Kl, 4 * H, in));
+        AST_TRY(copy2d(st, m->p((ln + "/lateral/W").c_str()), H, m->tb_Wcat_hi[l] + in, Kl, 4 * H, H));
+        AST_TRY(split_tf32(st, m->tb_Wcat_hi[l], m->tb_Wcat_hi[l], m->tb_Wcat_lo[l], (size_t)4 * H * Kl));
+    }
+    AST_TRY(split_tf32(st, m->p("attn_Wa/W"), m->tb_Wa_hi, m->tb_Wa_lo, (size_t)H * H));
+    AST_TRY(split_tf32(st, m->p("context/W"), m->tb_Wc_hi, m->tb_Wc_lo, (size_t)A * 2 * H));
+    AST_TRY(split_tf32(st, m->p("out/W"), m->tb_Wo_hi, m->tb_Wo_lo, (size_t)m->V * A));
+    m->tb_ready = true;
     return 0;
 }
 
@@ -709,6 +744,54 @@ static int dec_step_fwd(ast_model* m, const StepIO& io, cudaStream_t st) {
         SkinnyArgs s{}; s.X[0] = io.ht_out; s.ldx[0] = A; s.K[0] = A; s.W[0] = m->p("out/W"); s.ldw[0] = A;
         s.bias = m->p("out/b"); s.B = Bd; s.N = m->V; s.epi = EPI_NONE; s.Y = io.logits; s.ldy = m->Vp;
         AST_TRY(skinny(st, s, ex));
+    }
+    return 0;
+}
+
+// The same decoder step (eval mode) with every contraction on the tensor cores: fp32-faithful 3xTF32 tcgen05 GEMMs (gemm_tc3_nt: the
+// error of hi.hi + lo.hi + hi.lo is at fp32 round-off level) over ALL rows at once - beam search with rows = hypotheses (x utterances).
+// The skinny path above re-reads every weight row once per 32-row block; here one pass over the 31.6 MB serves every row.
+// Per-row results do not depend on how many rows share the launch, so a batched search equals the per-utterance search bit for bit.
+static bool dec_step_tc_supported(const ast_model* m) {
+    return m->beam_tc && m->tb_Wo_hi && (m->E + m->A) % 4 == 0 && m->H % 4 == 0 && m->A % 4 == 0 && ((size_t)m->V * m->A) % 4 == 0;
+}
+static int dec_step_fwd_tc(ast_model* m, const StepIO& io, cudaStream_t st) {
+    const int R = io.Bd, H = m->H, E = m->E, A = m->A, NL = m->NL;
+    if (!m->tb_ready) AST_TRY(build_beam_weights(m, st));
+    AST_TRY(embed_concat(st, m->p("embed_dec/W"), io.y, io.ldy, io.use_true, io.prev_argmax, io.forced_words, io.ht_prev, A,
+                         io.x0, io.words_used, R, E, A, m->V, io.step, 0.f, m->cur_seed, 32));
+    for (int l = 0; l < NL; ++l) {
+        const int in = m->in_dec(l), Kl = in + H;
+        const std::string ln = lname(l, "dec");
+        AST_TRY(split_concat2(st, l == 0 ? io.x0 : io.hd[l - 1], l == 0 ? E + A : io.ld_hd[l - 1], in, io.h_prev[l], H, H, m->tb_x_hi, m->tb_x_lo, Kl, R));
+        const int r = gemm_tc3_nt(st, R, 4 * H, Kl, m->tb_x_hi, m->tb_x_lo, Kl, m->tb_Wcat_hi[l], m->tb_Wcat_lo[l], Kl, io.act[l], 4 * H,
+                                  m->p((ln + "/upward/b").c_str()));
+        AST_CHECK(r == 0, "tensor-core decode step: the LSTM GEMM of layer %d rejected its operands", l);
+        AST_TRY(lstm_cell_rows(st, io.act[l], io.c_prev[l], io.c_out[l], io.h_out[l], io.hd[l], io.ld_hd[l], R, H));
+    }
+    {   // q = attn_Wa(h)  (:341)
+        AST_TRY(split_concat2(st, io.hd[NL - 1], io.ld_hd[NL - 1], H, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, H, R));
+        const int r = gemm_tc3_nt(st, R, H, H, m->tb_x_hi, m->tb_x_lo, H, m->tb_Wa_hi, m->tb_Wa_lo, H, io.q, H, m->p("attn_Wa/b"));
+        AST_CHECK(r == 0, "tensor-core decode step: the attention GEMM rejected its operands");
+    }
+    if (io.enc_bank) {
+        AST_TRY(attn_grouped(st, io.enc_bank, (long long)io.Tp_ld * H, io.rows_per_enc, io.enc_lens, io.q, H, io.scores, io.alpha, io.cvh,
+                             2 * H, R, io.Tp_ld, H));
+    } else {
+        const long long ebs = (m->B == R) ? (long long)m->Tp * H : 0;
+        AST_TRY(attn_dot(st, m->enc_states, ebs, io.q, H, io.scores, R, m->Tp, H));
+        AST_TRY(attn_ctx(st, m->enc_states, ebs, io.scores, io.alpha, io.cvh, 2 * H, R, m->Tp, H));
+    }
+    {   // ht = tanh(context([cv;h]))  (:386-390)
+        AST_TRY(split_concat2(st, io.cvh, 2 * H, 2 * H, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, 2 * H, R));
+        const int r = gemm_tc3_nt(st, R, A, 2 * H, m->tb_x_hi, m->tb_x_lo, 2 * H, m->tb_Wc_hi, m->tb_Wc_lo, 2 * H, io.ht_out, A, m->p("context/b"));
+        AST_CHECK(r == 0, "tensor-core decode step: the context GEMM rejected its operands");
+        AST_TRY(tanh_rows(st, io.ht_out, (size_t)R * A));
+    }
+    {   // logits = out(ht)  (:394)
+        AST_TRY(split_concat2(st, io.ht_out, A, A, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, A, R));
+        const int r = gemm_tc3_nt(st, R, m->V, A, m->tb_x_hi, m->tb_x_lo, A, m->tb_Wo_hi, m->tb_Wo_lo, A, io.logits, m->Vp, m->p("out/b"));
+        AST_CHECK(r == 0, "tensor-core decode step: the output GEMM rejected its operands");
     }
     return 0;
 }
@@ -1159,7 +1242,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 static int decode_bank_step(ast_model* m, int bank, int Bd, const int* words, const float* ht_in, float* logits_out,
                             float* ht_out, float* alpha_out, bool to_post, cudaStream_t st, const float* enc_bank = nullptr,
-                            const int* enc_lens = nullptr, int rows_per_enc = 0, int Tp_ld = 0) {
+                            const int* enc_lens = nullptr, int rows_per_enc = 0, int Tp_ld = 0, bool use_tc = false) {
     StepIO io{};
     io.enc_bank = enc_bank; io.enc_lens = enc_lens; io.rows_per_enc = rows_per_enc; io.Tp_ld = Tp_ld;
     io.Bd = Bd; io.step = 0; io.train = false; io.forced_words = words; io.ht_prev = ht_in;
@@ -1173,6 +1256,7 @@ static int decode_bank_step(ast_model* m, int bank, int Bd, const int* words, co
     }
     io.q = m->s_q; io.scores = m->s_scores; io.alpha = alpha_out ? alpha_out : m->s_alpha; io.cvh = m->s_cvh;
     io.ht_out = ht_out; io.logits = logits_out;
+    if (use_tc && dec_step_tc_supported(m)) return dec_step_fwd_tc(m, io, st);
     return dec_step_fwd(m, io, st);
 }
 
@@ -1248,6 +1332,7 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
+    if (const char* v = getenv("AST_BEAM_TC")) m->beam_tc = atoi(v);      // experiments: 0 skinny everywhere, 1 batched search on tcgen05, 3 both
     ++g_live_models[device & 63];
     *out = m;
     return 0;
@@ -1320,6 +1405,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "conv3x")) m->conv3x = (int)value;      // bit 0: CNN_1, bit 1: CNN_0 forward convolution as 3xTF32
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
+    else if (!strcmp(key, "beam_tc")) m->beam_tc = (int)value;
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
     else if (!strcmp(key, "enc_ts")) m->enc_ts_on = (int)value;
@@ -1339,6 +1425,7 @@ double ast_get_option(const ast_model* m, const char* key) {
     if (!strcmp(key, "dec_fused")) return m->dec_fused;
     if (!strcmp(key, "beam_fused")) return m->beam_fused;
     if (!strcmp(key, "enc_persist")) return m->enc_persist;
+    if (!strcmp(key, "beam_tc")) return m->beam_tc;
     if (!strcmp(key, "enc_persist_active")) return m->last_fwd_persistent ? 1 : 0;       // did the last training forward use the spin-wait schedule?
     if (!strcmp(key, "eager_loading")) return m->eager_loading ? 1 : 0;
     if (!strcmp(key, "queues_ok")) return m->queues_ok ? 1 : 0;
@@ -1600,7 +1687,8 @@ int ast_beam_search(ast_model* m, const float* X, int T, int stop_limit, int N, 
         AST_TRY(beam_seq(st, q));
     } else
     for (int s = 0; s < stop_limit; ++s) {
-        AST_TRY(decode_bank_step(m, bank, N, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st));
+        AST_TRY(decode_bank_step(m, bank, N, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st, nullptr, nullptr,
+                                 0, 0, (m->beam_tc & 2) != 0));
         AST_TRY(beam_topk(st, m->s_logits, m->Vp, m->V, K, N, bs, m->b_cand_lp, m->b_cand_tok));
         AST_TRY(beam_prune(st, bs, m->b_cand_lp, m->b_cand_tok, N, K, s, eos_token, hist_parent, hist_tok));
         BeamGather gd{}; gd.n = 0;
@@ -1716,7 +1804,7 @@ int ast_beam_search_batch(ast_model* m, const float* X, const int* lens, int G, 
     int bank = 0;
     for (int s = 0; s < stop_limit; ++s) {
         AST_TRY(decode_bank_step(m, bank, R, m->s_words[bank], m->st_ht[bank], m->s_logits, m->s_htout, m->s_alpha, true, st, m->bb_enc,
-                                 d_lens, N, Tp_ld));
+                                 d_lens, N, Tp_ld, (m->beam_tc & 1) != 0));
         BeamGather gd{}; gd.n = 0;
         for (int l = 0; l < NL; ++l) {
             gd.cur[gd.n] = m->st_h[bank][l]; gd.post[gd.n] = m->st_hpost[l]; gd.nxt[gd.n] = m->st_h[bank ^ 1][l]; gd.width[gd.n++] = H;
