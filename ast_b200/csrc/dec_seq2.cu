@@ -17,7 +17,14 @@
 //  * THE VOCABULARY PROJECTION LEAVES THE LOOP: logits, softmax-CE and its gradient are one batched tcgen05 GEMM and
 //    one CE launch after the loop.  Only steps whose successor is NOT teacher-forced (scheduled sampling,
 //    seq2seq.py:431-436) compute logits + argmax in-loop, because the next embedding depends on them.
-//  A decoder step is 5 grid barriers (3 LSTM + attention + context) instead of 9.
+//  * NO GRID BARRIERS BETWEEN PHASES.  A decoder step is 5 dependent phases (3 LSTM + attention + context); each needs the
+//    previous phase's output from CTAs all over the GPU.  The hand-off arrays (h, dropped-out h, [cv ; h2], the input-feeding
+//    slot of x0) have one slot per step and are filled with a sentinel (0xFFFFFFFF, a NaN no arithmetic produces) before the
+//    launch; a producer simply stores its values, a consumer re-reads its operand slice until no word is the sentinel
+//    (ld.relaxed.gpu: one L2 round trip when the data is already there).  Against a counter barrier this removes the
+//    release fence, the atomic and one L2 round trip from every phase, and CTAs no longer wait for the slowest one.  The
+//    operands that are a step old (own recurrent state, embedding) are staged and multiplied BEFORE the poll on the operand
+//    the previous phase has just produced.  Grid barriers remain only around the in-loop logits/argmax of sampled steps.
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "cluster_dev.cuh"
@@ -41,7 +48,8 @@ constexpr uint32_t D2_ABYTES = 4 * 128 * 4 + 4 * 8;          // attention exchan
 
 struct D2Smem {
     float Xs[32 * D2_XLD];
-    float recv[4 * 32 * 16];
+    float recv[2][4 * 32 * 16];          // ring of 2: a peer may send exchange k+1 while this CTA still reads exchange k
+    float sc[4 * 32 * 16];               // attention scores of the local t range (T'/4 <= 2048)
     float Wcs[64 * D2_WLD];
     float h2s[D2_H];
     float cvw[8 * D2_H];
@@ -73,6 +81,10 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long gtimer2() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+
 // grid barrier on a monotonically increasing global counter (zeroed by the host before the launch)
 __device__ __forceinline__ void grid_barrier2(unsigned* counter, unsigned& target) {
     __syncthreads();
@@ -85,8 +97,73 @@ __device__ __forceinline__ void grid_barrier2(unsigned* counter, unsigned& targe
     __syncthreads();
 }
 
-__device__ __forceinline__ unsigned long long gtimer2() {
-    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+
+// ---- sentinel hand-off ------------------------------------------------------------------------------------------------
+constexpr uint32_t D2_SENT = 0xFFFFFFFFu;            // "not written yet" (cudaMemsetAsync 0xFF / fill kernel before the launch)
+__device__ __forceinline__ float4 ld_pub4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_pub1(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool unwritten(float v) { return __float_as_uint(v) == D2_SENT; }
+__device__ __forceinline__ bool unwritten(const float4& v) { return unwritten(v.x) | unwritten(v.y) | unwritten(v.z) | unwritten(v.w); }
+// a value that happens to carry the sentinel's bits (only a copied NaN payload could) is stored as the canonical NaN
+__device__ __forceinline__ float pubval(float v) { return unwritten(v) ? __uint_as_float(0x7FFFFFFFu) : v; }
+__device__ __forceinline__ void st_pub4(float* p, float4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(pubval(v.x)), "f"(pubval(v.y)), "f"(pubval(v.z)), "f"(pubval(v.w)) : "memory");
+}
+__device__ __forceinline__ void st_pub1(float* p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(pubval(v)) : "memory");
+}
+// bounded like common.cuh::spin_until_ge: a producer that never shows up is a failed launch, not a hung GPU
+struct PollClock {
+    unsigned long long t0 = 0; unsigned polls = 0;
+    __device__ __forceinline__ void tick() {
+        if ((++polls & 1023u) == 0) {
+            const unsigned long long t = gtimer2();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > SPIN_TIMEOUT_NS) __trap();
+        }
+    }
+};
+__device__ __forceinline__ float4 poll4(const float* p) {
+    float4 v = ld_pub4(p);
+    PollClock pc;
+    while (unwritten(v)) { pc.tick(); v = ld_pub4(p); }
+    return v;
+}
+__device__ __forceinline__ float poll1(const float* p) {
+    float v = ld_pub1(p);
+    PollClock pc;
+    while (unwritten(v)) { pc.tick(); v = ld_pub1(p); }
+    return v;
+}
+// seg_load for an operand another CTA publishes during this launch: all loads in flight first, then only the float4s that
+// still hold a sentinel word are re-read
+template <int W>
+__device__ __forceinline__ void seg_poll(float4 (&v)[W / 32], const float* ptr, int ld, int B) {
+    const float* a[W / 32];
+#pragma unroll
+    for (int i = 0; i < W / 32; ++i) {
+        const int idx = threadIdx.x + i * D2_THREADS, row = idx / (W / 4), k = (idx % (W / 4)) * 4;
+        a[i] = row < B ? ptr + (size_t)row * ld + k : nullptr;
+        v[i] = a[i] ? ld_pub4(a[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    PollClock pc;
+    for (;;) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < W / 32; ++i) bad |= unwritten(v[i]);
+        if (!bad) break;
+        pc.tick();
+#pragma unroll
+        for (int i = 0; i < W / 32; ++i) if (unwritten(v[i])) v[i] = ld_pub4(a[i]);
+    }
 }
 
 // One activation segment of the K quarter: W floats per row starting at ptr[row * ld]; 32 rows.  All of a thread's loads
@@ -108,15 +185,14 @@ __device__ __forceinline__ void seg_store(float* Xs_k0, const float4 (&v)[W / 32
     }
 }
 
-// acc[mt][4] += X(32 x kq) . Wfrag^T for this warp's n-tile; B fragments from TMEM (16 regs per 8 k-steps).
-__device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr, int kq) {
+// acc[mt][4] += X[:, 64 j0 : 64 j1] . Wfrag^T for this warp's n-tile; B fragments from TMEM (16 regs per 8 k-steps).
+__device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr, int j0, int j1) {
     const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int nchunk = kq >> 6;
     uint32_t bcur[16], bnxt[16];
-    tmem_ld16_nowait(taddr, bcur);
+    tmem_ld16_nowait(taddr + 16 * j0, bcur);
     tmem_wait_ld();
-    for (int j = 0; j < nchunk; ++j) {
-        if (j + 1 < nchunk) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
+    for (int j = j0; j < j1; ++j) {
+        if (j + 1 < j1) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
         const float* xr = Xs + g * D2_XLD + j * 64 + q;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -130,7 +206,7 @@ __device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* X
             mma_tf32(acc[0], a0, b);
             mma_tf32(acc[1], a1, b);
         }
-        if (j + 1 < nchunk) {
+        if (j + 1 < j1) {
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) bcur[i] = bnxt[i];
@@ -138,13 +214,13 @@ __device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* X
     }
 }
 
-// same with B fragments from shared memory (context weights), kq = 256
-__device__ __forceinline__ void mma_from_smem(float (&acc)[2][4], const float* Xs, const float* Ws) {
+// same with B fragments from shared memory (context weights), k-steps ks0 .. ks0 + 15 of the 32
+__device__ __forceinline__ void mma_from_smem(float (&acc)[2][4], const float* Xs, const float* Ws, int ks0) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const float* xr = Xs + g * D2_XLD + q;
     const float* wr = Ws + (8 * w + g) * D2_WLD + q;
 #pragma unroll 8
-    for (int ks = 0; ks < D2_KQ / 8; ++ks) {
+    for (int ks = ks0; ks < ks0 + D2_KQ / 16; ++ks) {
         const float* x0 = xr + ks * 8;
         uint32_t a0[4], a1[4];
         a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * D2_XLD]);
@@ -158,10 +234,10 @@ __device__ __forceinline__ void mma_from_smem(float (&acc)[2][4], const float* X
 }
 
 // reduce-scatter of the four K-partial 32 x 64 products: warp w holds n-tile w = columns 8w..8w+7, owned by CTA w/2
-__device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& sm, int rank) {
+__device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& sm, int rank, int buf) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
-    const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
+    const uint32_t base = mapa(saddr(sm.recv[buf]), dst), bar = mapa(saddr(&sm.mbar_x), dst);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         const int r0 = 16 * mt + g;
@@ -172,7 +248,8 @@ __device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& 
 
 }  // namespace
 
-// x0[i][0:E] = Emb[y[b][s]] * dropmask, words_used[i] = token, for row i = s*B + b; (s == 0) x0[i][E:] = 0
+// x0[i][0:E] = Emb[y[b][s]] * dropmask, words_used[i] = token, for row i = s*B + b; x0[i][E:] = 0 (s == 0) or the hand-off
+// sentinel (s > 0: the input-feeding slot the decoder kernel fills at step s - 1 and polls at step s)
 __device__ __forceinline__ void embed_tf_row(const DecSeq& p, int i, int tid, int nthreads) {
     const int s = i / p.B, b = i - s * p.B, ldx0 = p.E + p.A;
     const int word = min(max(p.y[(size_t)b * p.L + s], 0), p.V - 1);
@@ -180,7 +257,8 @@ __device__ __forceinline__ void embed_tf_row(const DecSeq& p, int i, int tid, in
     if (tid == 0) p.words_used[i] = word;
     for (int j = tid; j < p.E; j += nthreads)
         dst[j] = __ldg(p.emb + (size_t)word * p.E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * p.E + j), p.drop_embed);
-    if (s == 0) for (int j = tid; j < p.A; j += nthreads) dst[p.E + j] = 0.f;
+    const float fill = s == 0 ? 0.f : __uint_as_float(0xFFFFFFFFu);
+    for (int j = tid; j < p.A; j += nthreads) dst[p.E + j] = fill;
 }
 __global__ void __launch_bounds__(128) embed_all_kernel(DecSeq p) { embed_tf_row(p, blockIdx.x, threadIdx.x, 128); }
 int embed_all(cudaStream_t st, const DecSeq& p) {
@@ -202,7 +280,10 @@ dec_seq2_fwd_kernel(DecSeq p) {
     constexpr int H = D2_H, E = D2_E, A = D2_A, ldx0 = D2_E + D2_A;
     unsigned bar_target = 0;
     int nprof = 0;
-#define D2_SYNC() do { grid_barrier2(p.bar, bar_target); \
+#define D2_SYNC() grid_barrier2(p.bar, bar_target)
+    // phase boundary: nothing to wait for (consumers poll the hand-off slots); option dec_sync puts the grid barrier back
+    // (bisecting), option dec_prof stamps the time CTA 0 gets here
+#define D2_PHASE_END() do { if (p.sync_all) D2_SYNC(); \
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
 
     // ---- one-time setup ------------------------------------------------------------------------------------------
@@ -232,9 +313,9 @@ dec_seq2_fwd_kernel(DecSeq p) {
             // two 16-value fragments per round: 32 scattered 4-byte loads in flight before the first tcgen05.st (one fragment at a
             // time serialised 13 L2 round trips per thread: 47 us of kernel prologue)
             auto wload = [&](int k) -> float {
-                if (l == 0) {
-                    if (k < 32) return __ldg(Wup + 32 * rank + k);
-                    if (k < 160) return __ldg(Wup + E + 128 * rank + (k - 32));
+                if (l == 0) {           // K order [ht 128 | emb 32 | h_prev 128 | pad 32]: the just-produced operand first
+                    if (k < 128) return __ldg(Wup + E + 128 * rank + k);
+                    if (k < 160) return __ldg(Wup + 32 * rank + (k - 128));
                     if (k < 288) return __ldg(Wlat + 128 * rank + (k - 160));
                     return 0.f;
                 }
@@ -290,69 +371,76 @@ dec_seq2_fwd_kernel(DecSeq p) {
     D2_SYNC();
 
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
+    int xbuf = 0;
     for (int s = 0; s < S; ++s) {
         // ---- LSTM stack (seq2seq.py:375) -----------------------------------------------------------------------
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
-            int kq; uint32_t tcol;
-            if (l == 0) {
-                const float* x0 = p.x0 + (size_t)s * B * ldx0;
-                float4 v0[1], v1[4], v2[4];
-                seg_load<32>(v0, x0 + 32 * rank, ldx0, B);
-                seg_load<128>(v1, x0 + E + 128 * rank, ldx0, B);
-                seg_load<128>(v2, p.Hd[0] + (size_t)s * B * H + 128 * rank, H, B);
-                seg_store<32>(sm.Xs, v0); seg_store<128>(sm.Xs + 32, v1); seg_store<128>(sm.Xs + 160, v2);
-                kq = D2_KQ0; tcol = D2_TCOL0;
-            } else {
-                float4 v1[4], v2[4];
-                seg_load<128>(v1, p.hdd[l - 1] + (size_t)s * B * H + 128 * rank, H, B);
-                seg_load<128>(v2, p.Hd[l] + (size_t)s * B * H + 128 * rank, H, B);
-                seg_store<128>(sm.Xs, v1); seg_store<128>(sm.Xs + 128, v2);
-                kq = D2_KQ; tcol = l == 1 ? D2_TCOL1 : D2_TCOL2;
+            const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
+            const float* x0 = p.x0 + (size_t)s * B * ldx0;
+            // (1) operands that are a step old: own recurrent state (layer 0: + the embedding rows)
+            {
+                float4 v2[4];
+                seg_poll<128>(v2, p.Hd[l] + (size_t)s * B * H + 128 * rank, H, B);
+                if (l == 0) {
+                    float4 v0[1];
+                    seg_load<32>(v0, x0 + 32 * rank, ldx0, B);
+                    seg_store<32>(sm.Xs + 128, v0); seg_store<128>(sm.Xs + 160, v2);
+                } else {
+                    seg_store<128>(sm.Xs + 128, v2);
+                }
             }
             __syncthreads();
             float acc[2][4] = {};
-            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, kq);
-            exchange_send(acc, sm, rank);
+            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, 2, l == 0 ? 5 : 4);
+            // (2) the operand the previous phase has just produced: ht of step s-1 (input feeding) / the layer below
+            {
+                float4 v1[4];
+                if (l == 0) seg_poll<128>(v1, x0 + E + 128 * rank, ldx0, B);
+                else seg_poll<128>(v1, p.hdd[l - 1] + (size_t)s * B * H + 128 * rank, H, B);
+                seg_store<128>(sm.Xs, v1);
+            }
+            __syncthreads();
+            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, 0, 2);
+            exchange_send(acc, sm, rank, xbuf);
+            const bool own = tid < 128 && e_row < B;
+            const size_t e = (size_t)e_row * H + e_unit;
+            float4 gs = make_float4(0.f, 0.f, 0.f, 0.f); float dm = 1.f;
+            if (own) {     // while the exchange is in flight
+                gs = __ldg(reinterpret_cast<const float4*>(p.bup[l] + 4 * e_unit));
+                dm = dropout_scale(p.seed, 16 + l, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
+            }
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
-            if (tid < 128 && e_row < B) {
-                float4 gs = __ldg(reinterpret_cast<const float4*>(p.bup[l] + 4 * e_unit));
+            if (own) {
+                const float* rv = sm.recv[xbuf];
 #pragma unroll
                 for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + e_row) * 16 + 4 * e_ul);
+                    const float4 r = *reinterpret_cast<const float4*>(rv + (src * 32 + e_row) * 16 + 4 * e_ul);
                     gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
                 }
                 const float ga = tanhf(gs.x), gi = sigmoidf_(gs.y), gf = sigmoidf_(gs.z), go = sigmoidf_(gs.w);
                 const float c = ga * gi + gf * creg[l];
                 creg[l] = c;
                 const float hv = go * tanhf(c);
-                const size_t e = (size_t)e_row * H + e_unit;
+                // published values first (the next phase / the next step polls them), then what only backward reads
+                if (l == 2) st_pub1(p.cvh + ((size_t)s * B + e_row) * 2 * H + H + e_unit, hv * dm);
+                else st_pub1(p.hdd[l] + (size_t)s * B * H + e, hv * dm);
+                st_pub1(p.Hd[l] + (size_t)(s + 1) * B * H + e, hv);
                 *reinterpret_cast<float4*>(p.act[l] + ((size_t)s * B + e_row) * 4 * H + 4 * e_unit) = make_float4(ga, gi, gf, go);
                 p.Cd[l][(size_t)(s + 1) * B * H + e] = c;
-                p.Hd[l][(size_t)(s + 1) * B * H + e] = hv;
-                const float dm = dropout_scale(p.seed, 16 + l, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
-                if (l == 2) p.cvh[((size_t)s * B + e_row) * 2 * H + H + e_unit] = hv * dm;
-                else p.hdd[l][(size_t)s * B * H + e] = hv * dm;
             }
-            D2_SYNC();
+            xbuf ^= 1;
+            __syncthreads();        // every warp is done with Xs and recv before the next phase restages them
+            D2_PHASE_END();
         }
         // ---- attention (seq2seq.py:336-358): cluster = batch row, CTA = quarter of T', one online-softmax pass -------
         if (cl < B) {
             const int b = cl;
             const float* cvh_b = p.cvh + ((size_t)s * B + b) * 2 * H;
-            if (tid < H / 4) *reinterpret_cast<float4*>(sm.h2s + 4 * tid) = __ldcg(reinterpret_cast<const float4*>(cvh_b + H + 4 * tid));
-            __syncthreads();
             const int t_lo = rank * Tq, t_hi = min(Tp, t_lo + Tq);
-            float4 hq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hq[i] = *reinterpret_cast<const float4*>(sm.h2s + 128 * i + 4 * lane);
-            float mw = -INFINITY, sw = 0.f;
-            float4 cv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float* sc = sm.recv;     // scores of the local t range (recv is idle during this phase; Tq <= 2048)
-            // rows t, t + 8, ... of this warp; the next row's 4 KB (encW + enc) is in flight while this one is reduced
+            // rows t, t + 8, ... of this warp; the next row's 4 KB (encW + enc) is in flight while this one is reduced.  The
+            // first row is requested before the poll on h2.
             const float* ewb = p.encW + (size_t)b * Tp * H + 4 * lane;
             const float* enb = p.enc + (size_t)b * Tp * H + 4 * lane;
             const float* ebb = p.encb + (size_t)b * Tp;
@@ -363,6 +451,16 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 for (int i = 0; i < 4; ++i) { a[i] = __ldg(reinterpret_cast<const float4*>(ewb + (size_t)t * H + 128 * i)); x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i)); }
                 eb = __ldg(ebb + t);
             }
+            if (tid < H / 4) *reinterpret_cast<float4*>(sm.h2s + 4 * tid) = poll4(cvh_b + H + 4 * tid);
+            __syncthreads();
+            float4 hq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hq[i] = *reinterpret_cast<const float4*>(sm.h2s + 128 * i + 4 * lane);
+            float mw = -INFINITY, sw = 0.f;
+            float4 cv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* sc = sm.sc;
             while (t < t_hi) {
                 const int tn = t + 8;
                 float4 an[4], xn[4]; float ebn = 0.f;
@@ -428,43 +526,58 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 float v = 0.f;
 #pragma unroll
                 for (int r = 0; r < 4; ++r) v += wr[r] * sm.cvx[r * 128 + tid];
-                p.cvh[((size_t)s * B + b) * 2 * H + 128 * rank + tid] = v * invZ;
+                st_pub1(p.cvh + ((size_t)s * B + b) * 2 * H + 128 * rank + tid, v * invZ);
             }
             float* al = p.alpha + ((size_t)s * B + b) * Tp;
-            for (int t = t_lo + tid; t < t_hi; t += D2_THREADS) al[t] = __expf(sc[t - t_lo] - M) * invZ;
+            for (int tt = t_lo + tid; tt < t_hi; tt += D2_THREADS) al[tt] = __expf(sc[tt - t_lo] - M) * invZ;
+            __syncthreads();        // cvw / cvx / sc are reused by the next step's attention only, Xs by the next phase
         }
-        D2_SYNC();
+        D2_PHASE_END();
         // ---- ht = tanh(context([cv ; h]))  (seq2seq.py:386-390), clusters 0..7; also the next step's input feeding ----
         if (cl < A / 64) {
             const float* cvh = p.cvh + (size_t)s * B * 2 * H;
-            {
-                float4 v1[4], v2[4];
-                seg_load<128>(v1, cvh + 128 * rank, 2 * H, B);
-                seg_load<128>(v2, cvh + H + 128 * rank, 2 * H, B);
-                seg_store<128>(sm.Xs, v1); seg_store<128>(sm.Xs + 128, v2);
+            {   // h2 (published one phase ago) first, then the context vector the attention phase has just produced
+                float4 v2[4];
+                seg_poll<128>(v2, cvh + H + 128 * rank, 2 * H, B);
+                seg_store<128>(sm.Xs + 128, v2);
             }
             __syncthreads();
             float acc[2][4] = {};
-            mma_from_smem(acc, sm.Xs, sm.Wcs);
-            exchange_send(acc, sm, rank);
+            mma_from_smem(acc, sm.Xs, sm.Wcs, 16);
+            {
+                float4 v1[4];
+                seg_poll<128>(v1, cvh + 128 * rank, 2 * H, B);
+                seg_store<128>(sm.Xs, v1);
+            }
+            __syncthreads();
+            mma_from_smem(acc, sm.Xs, sm.Wcs, 0);
+            exchange_send(acc, sm, rank, xbuf);
+            const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
+            const bool own = tid < 128 && e_row < B;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (own) v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
-            if (tid < 128 && e_row < B) {
-                const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
-                float4 v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
+            if (own) {
+                const float* rv = sm.recv[xbuf];
 #pragma unroll
                 for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + e_row) * 16 + 4 * e_ul);
+                    const float4 r = *reinterpret_cast<const float4*>(rv + (src * 32 + e_row) * 16 + 4 * e_ul);
                     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
                 }
                 v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+                if (s + 1 < S) st_pub4(p.x0 + ((size_t)(s + 1) * B + e_row) * ldx0 + E + n0, v);
                 *reinterpret_cast<float4*>(p.ht + ((size_t)s * B + e_row) * A + n0) = v;
-                if (s + 1 < S) *reinterpret_cast<float4*>(p.x0 + ((size_t)(s + 1) * B + e_row) * ldx0 + E + n0) = v;
             }
+            xbuf ^= 1;
+            __syncthreads();
         }
-        D2_SYNC();
+        D2_PHASE_END();
         // ---- scheduled sampling: the next input is this step's argmax (seq2seq.py:431-436, 448) ----------------------
+        // The only place grid barriers remain: logits need every column of ht, the argmax every logit, and the embedding
+        // row of step s+1 (already holding the teacher-forced token's) is overwritten before anyone may stage it.
         if (s + 1 < S && p.use_true != nullptr && !p.use_true[s + 1]) {
+            D2_SYNC();
             float* z = p.logits + (size_t)s * B * Vp;
             SkinnyArgs a{};
             a.X[0] = p.ht + (size_t)s * B * A; a.ldx[0] = A; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
@@ -488,6 +601,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_slot), "n"(512));
     cluster_sync_all();
 #undef D2_SYNC
+#undef D2_PHASE_END
 }
 
 
@@ -953,6 +1067,40 @@ int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float*
     attn_denc_kernel<<<dim3((Tp + 7) / 8, B), 128, 0, st>>>(alpha, ds, dcv, q, d_enc, S, B, Tp, H);
     AST_LAUNCH_OK();
     return 0;
+}
+
+// Sentinel fill of the hand-off slots of one launch (one kernel for all ranges).  Must be ordered before anything that writes
+// real values into them (init_dec_state writes slot 0 of Hd, which is therefore not part of the range).
+namespace {
+struct FillRanges { int n; uint4* ptr[12]; size_t n4[12]; };
+__global__ void __launch_bounds__(256) fill_sentinel_kernel(FillRanges r) {
+    const uint4 v = make_uint4(D2_SENT, D2_SENT, D2_SENT, D2_SENT);
+    for (int i = 0; i < r.n; ++i)
+        for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < r.n4[i]; j += (size_t)gridDim.x * blockDim.x) r.ptr[i][j] = v;
+}
+int fill_ranges(cudaStream_t st, const FillRanges& r) {
+    fill_sentinel_kernel<<<148 * 2, 256, 0, st>>>(r);
+    AST_LAUNCH_OK();
+    return 0;
+}
+}  // namespace
+
+int dec_seq2_prepare_fwd(cudaStream_t st, const DecSeq& p) {
+    FillRanges r{};
+    const size_t SBH = (size_t)p.S * p.B * p.H;
+    auto add = [&](float* ptr, size_t words) { r.ptr[r.n] = reinterpret_cast<uint4*>(ptr); r.n4[r.n] = words / 4; ++r.n; };
+    for (int l = 0; l < 3; ++l) add(p.Hd[l] + (size_t)p.B * p.H, SBH);
+    add(p.hdd[0], SBH); add(p.hdd[1], SBH); add(p.cvh, 2 * SBH);
+    return fill_ranges(st, r);
+}
+
+int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p) {
+    FillRanges r{};
+    const size_t SBH = (size_t)p.S * p.B * p.H;
+    auto add = [&](float* ptr, size_t words) { r.ptr[r.n] = reinterpret_cast<uint4*>(ptr); r.n4[r.n] = words / 4; ++r.n; };
+    add(p.dcv_all, SBH); add(p.dhh_all, SBH); add(p.dq, SBH); add(p.dfeed, (size_t)p.S * p.B * p.A);
+    for (int l = 0; l < 3; ++l) { add(p.dxr[l], SBH); add(p.dgd[l], 4 * SBH); }
+    return fill_ranges(st, r);
 }
 
 bool dec_seq2_supported(const DecSeq& p) {

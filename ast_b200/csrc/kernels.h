@@ -147,6 +147,10 @@ struct DecSeq {
     float drop_embed, drop_rnn; unsigned long long seed;
     int emb_done;                      // dec_seq2: teacher-forced embedding rows already written by embed_all()
     unsigned* bar;                     // grid-barrier counter (null: cooperative_groups grid.sync)
+    int sync_all;                      // dec_seq2: grid barrier after every phase as well (debugging; the hand-off is by sentinel polling)
+    // dec_seq2 backward hand-off slots, one per step, sentinel-filled before the launch: dG of every layer (the forward gates in
+    // act[] stay intact), dh_rec of layer l produced at step s (consumed at s-1), d(ht) fed back into layer 0, h-half of du.Wc
+    float* dgd[AST_MAXL]; float* dxr[AST_MAXL]; float* dfeed; float* dhh_all;
     unsigned long long* prof;          // optional phase-timing probe: CTA 0 stores %globaltimer after each grid barrier
 };
 int dec_seq_fwd(cudaStream_t st, const DecSeq& p, bool exact);
@@ -155,6 +159,9 @@ int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);
 bool dec_seq2_supported(const DecSeq& p);
 int dec_seq2_fwd(cudaStream_t st, const DecSeq& p);
 int dec_seq2_bwd(cudaStream_t st, const DecSeq& p);
+// sentinel fill of the per-step hand-off slots the dec_seq2 kernels poll; ordered before init_dec_state / the kernel
+int dec_seq2_prepare_fwd(cudaStream_t st, const DecSeq& p);
+int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p);
 int embed_all(cudaStream_t st, const DecSeq& p);   // x0[:, :E] / words_used for every step from the ground-truth tokens
 int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float* dcv, const float* q, float* d_enc, int S, int B, int Tp, int H);
 // softmax-CE (+ gradient in place, argmax) for every (step, row) of a decoder pass in one launch

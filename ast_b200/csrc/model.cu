@@ -109,7 +109,7 @@ struct ast_model {
     float *WoT, *WcT, *WaT, *WcatT[MAXL];
     float *loss_dev;
     unsigned long long *dec_prof;      // [2][4096] phase-timing probe of the decoder-sequence kernels (option dec_prof)
-    int dec_prof_on = 0, dec_fast_barrier = 1;
+    int dec_prof_on = 0, dec_fast_barrier = 1, dec_sync = 0;      // dec_sync: grid barrier after every phase of dec_seq2 (debugging)
     unsigned* dec_bar;
     // decode-time state (greedy / beam / decode_step): two banks
     float *st_h[2][MAXL], *st_c[2][MAXL], *st_ht[2], *st_hpost[MAXL], *st_cpost[MAXL];
@@ -814,7 +814,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
     p.row_loss = m->row_loss; p.words_used = m->words_used; p.argmax_steps = m->argmax_steps;
     p.du = m->du; p.dcvh = m->dcvh; p.dalpha = m->dalpha; p.dq = m->dq; p.demb = m->g("embed_dec/W");
     p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
-    p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr;
+    p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr; p.sync_all = m->dec_sync;
     p.encW = m->encW; p.encb = m->encb; p.dzw = m->dzw; p.dcv_all = m->dcv_all; p.ds_all = m->ds_all;
     return p;
 }
@@ -835,21 +835,31 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     m->L = L;
     float* hinit[MAXL]; float* cinit[MAXL];
     for (int l = 0; l < NL; ++l) { hinit[l] = m->Hdec[l]; cinit[l] = m->Cdec[l]; }
-    AST_TRY(init_dec_state(m, hinit, cinit, B, st));
     m->y_dev = y; m->use_true_dev = use_true;
+    DecSeq ds{};
+    bool use_v2 = false;
     if (m->dec_fused) {
-        DecSeq ds = make_dec_seq(m, y, use_true, true);
+        ds = make_dec_seq(m, y, use_true, true);
         if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof;
-        const bool use_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
-        if (use_v2 && m->overlap) {
-            // the teacher-forced embedding rows depend on the targets only: side stream, concurrent with the encoder (the host
-            // is ahead of the device here), joined in front of the decoder kernel
+        use_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
+    }
+    if (use_v2) {
+        // hand-off slots of this launch <- sentinel (dec_seq2.cu), before init_dec_state writes slot 0 of the state arrays
+        if (m->overlap) {
+            // this and the teacher-forced embedding rows depend on the targets only: side stream, concurrent with the encoder
+            // (the host is ahead of the device here), joined in front of init_dec_state / the decoder kernel
             AST_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fork[6], 0));
+            AST_TRY(dec_seq2_prepare_fwd(m->side, ds));
             AST_TRY(embed_all(m->side, ds));
             AST_CUDA_OK(cudaEventRecord(m->ev_fork[5], m->side));
             AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_fork[5], 0));
             ds.emb_done = 1;
+        } else {
+            AST_TRY(dec_seq2_prepare_fwd(st, ds));
         }
+    }
+    AST_TRY(init_dec_state(m, hinit, cinit, B, st));
+    if (m->dec_fused) {
         if (use_v2) {
             // per-sequence precompute: scores become encW[b,t,:] . h + encb[b,t]  (= enc . (W_a h + b_a), seq2seq.py:341-342)
             AST_TRY(gemm(m, st, false, false, Tp * B, H, H, m->enc_states, H, m->p("attn_Wa/W"), H, m->encW, H, nullptr, 0.f, 0, SITE_DEC_PRE));
@@ -1415,6 +1425,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_gemm_ctas_bwd")) m->enc_gemm_ctas_bwd = (int)value;
     else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
+    else if (!strcmp(key, "dec_sync")) m->dec_sync = value != 0;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
     return 0;
