@@ -1,30 +1,36 @@
-// Decoder-sequence forward, second generation (TF32 training mode, es_en_20h geometry: H = A = 512, E = 128, 3 layers,
+// Decoder-sequence kernels, second generation (TF32 training mode, es_en_20h geometry: H = A = 512, E = 128, 3 layers,
 // batch <= 32).  One cooperative launch of 32 clusters x 4 CTAs runs every decoder step of forward_loss
-// (seq2seq.py:423-470).  What changed against dec_seq.cu, and why (tools/dec_phase_times.py: 75 us/step there, every
-// LSTM phase ~11.5 us because 128 CTAs each re-read the whole 147 KB activation operand and 74 KB of weights from L2):
+// (seq2seq.py:423-470); a second one runs the decoder BPTT.  What changed against dec_seq.cu, and why
+// (tools/dec_phase_times.py: 75 us/step there, every LSTM phase ~11.5 us because 128 CTAs each re-read the whole 147 KB
+// activation operand and 74 KB of weights from L2):
 //
 //  * WEIGHTS STAY ON CHIP FOR THE WHOLE SEQUENCE.  The three LSTM layers' [W_up | W_lat] (26 MB fp32) live in TENSOR
 //    MEMORY: a cluster owns 64 gate rows (16 hidden units) of every layer, each of its 4 CTAs a quarter of K, and each
 //    thread keeps exactly its own mma B-fragments (208 TF32 values) in its TMEM lane, written once with tcgen05.st and
 //    read back with tcgen05.ld every step.  TMEM is used as 256 KB/SM of software-managed operand storage; shared
 //    memory stays free for the activation slice, the context weights and the exchange buffers.
-//  * K IS SPLIT ACROSS THE CLUSTER, so a CTA stages only its 32 x 288 slice of the activations (36 KB instead of
-//    147 KB); the four partial 32 x 64 products are reduce-scattered through distributed shared memory
-//    (st.async + mbarrier complete_tx), and each CTA finishes the LSTM cell for its 4 units x 32 rows.
+//  * K IS SPLIT ACROSS THE CLUSTER AND, INSIDE A CTA, ACROSS THE WARPS.  A CTA stages only its 32 x 288 slice of the
+//    activations.  Warp (kh, nh) multiplies a quarter of that slice (16-wide k blocks) with four n-tiles (32 of the
+//    cluster's 64 gate columns): the activation operand is read from shared memory twice per CTA instead of eight times (the
+//    first cut, one n-tile x the whole K quarter per warp, was bound by shared-memory bandwidth: 2048 cycles of A-fragment
+//    loads per phase), with ld.shared.v4 (k is permuted inside a 16-block so that one 128-bit load feeds two k-steps; the
+//    weight fragments are stored in the same permutation), and a warp has eight independent accumulator chains.  The
+//    16 partial 32 x 64 products of a cluster (4 CTAs x 4 k-slices) are reduce-scattered through distributed shared
+//    memory (st.async + mbarrier complete_tx); each CTA finishes the LSTM cell for its 4 units x 32 rows.
 //  * ATTENTION IS ONE PHASE: a cluster owns one batch row; score, softmax and context are a single online-softmax
 //    pass over its quarter of T' (scores through the precomputed encW = enc . W_a, so q = W_a h is never formed inside
 //    the loop), merged across warps and across the cluster by (max, sum, partial context) triples.
 //  * THE VOCABULARY PROJECTION LEAVES THE LOOP: logits, softmax-CE and its gradient are one batched tcgen05 GEMM and
 //    one CE launch after the loop.  Only steps whose successor is NOT teacher-forced (scheduled sampling,
 //    seq2seq.py:431-436) compute logits + argmax in-loop, because the next embedding depends on them.
-//  * NO GRID BARRIERS BETWEEN PHASES.  A decoder step is 5 dependent phases (3 LSTM + attention + context); each needs the
-//    previous phase's output from CTAs all over the GPU.  The hand-off arrays (h, dropped-out h, [cv ; h2], the input-feeding
-//    slot of x0) have one slot per step and are filled with a sentinel (0xFFFFFFFF, a NaN no arithmetic produces) before the
-//    launch; a producer simply stores its values, a consumer re-reads its operand slice until no word is the sentinel
-//    (ld.relaxed.gpu: one L2 round trip when the data is already there).  Against a counter barrier this removes the
-//    release fence, the atomic and one L2 round trip from every phase, and CTAs no longer wait for the slowest one.  The
-//    operands that are a step old (own recurrent state, embedding) are staged and multiplied BEFORE the poll on the operand
-//    the previous phase has just produced.  Grid barriers remain only around the in-loop logits/argmax of sampled steps.
+//  * NO GRID BARRIERS BETWEEN PHASES.  A decoder step is 5 dependent phases (3 LSTM + attention + context), a BPTT step 6;
+//    each needs the previous phase's output from CTAs all over the GPU.  The hand-off arrays have one slot per step and are
+//    filled with a sentinel (0xFFFFFFFF, a NaN no arithmetic produces) before the launch; a producer simply stores its
+//    values, a consumer re-reads its operand slice until no word is the sentinel (ld.relaxed.gpu: one L2 round trip when
+//    the data is already there).  Against a counter barrier this removes the release fence, the atomic and one L2 round
+//    trip from every phase, and CTAs no longer wait for the slowest one.  Operands that are a step old (own recurrent
+//    state, embedding) are staged and multiplied BEFORE the poll on the operand the previous phase has just produced.
+//    Grid barriers remain only around the in-loop logits/argmax of sampled steps.
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "cluster_dev.cuh"
@@ -38,18 +44,18 @@ constexpr int D2_THREADS = 256;
 constexpr int D2_CS = 4;                 // CTAs per cluster = K split
 constexpr int D2_NCL = 32;               // clusters
 constexpr int D2_H = 512, D2_E = 128, D2_A = 512;
-constexpr int D2_KQ0 = 320;              // layer-0 K quarter: 32 (emb) + 128 (ht) + 128 (h_prev) = 288, padded to 40 k-steps
-constexpr int D2_KQ = 256;               // layers 1,2 and the context GEMM: 128 + 128
-constexpr int D2_XLD = D2_KQ0 + 4;       // smem row stride of the staged activations (conflict-free A fragments)
-constexpr int D2_WLD = D2_KQ + 4;        // smem row stride of the context weights
-constexpr int D2_TCOL0 = 0, D2_TCOL1 = 80, D2_TCOL2 = 144;   // TMEM column of each layer's fragments (80 + 64 + 64)
-constexpr uint32_t D2_XBYTES = 4 * 32 * 16 * 4;              // GEMM exchange: [src][row][16 cols]
+// Forward K quarter of a CTA, physical column order: [fresh operand 128 | step-old operands].  Layer 0: ht 128 | emb 32 |
+// h_prev 128 | zero pad 32 (= 20 blocks of 16); layers 1, 2 and the context GEMM: 128 | 128 (16 blocks).
+constexpr int D2_XLD = 320 + 16;         // smem row stride of the staged activations (= 16 mod 32: conflict-free ld.shared.v4)
+constexpr int D2_WLD = 256 + 16;         // smem row stride of the context weights
+constexpr int D2_TCOL0 = 0, D2_TCOL1 = 80, D2_TCOL2 = 144;   // TMEM column of each layer's fragments (5 + 4 + 4 blocks of 16)
+constexpr int D2_RECV = 16 * 32 * 16;                        // floats of one exchange buffer: [src 16][row 32][16 cols] (backward D: [32][32][8])
+constexpr uint32_t D2_XBYTES = D2_RECV * 4;
 constexpr uint32_t D2_ABYTES = 4 * 128 * 4 + 4 * 8;          // attention exchange: [src][128 cols] + [src](max, sum)
 
 struct D2Smem {
-    float Xs[32 * D2_XLD];
-    float recv[2][4 * 32 * 16];          // ring of 2: a peer may send exchange k+1 while this CTA still reads exchange k
-    float sc[4 * 32 * 16];               // attention scores of the local t range (T'/4 <= 2048)
+    float Xs[32 * D2_XLD];               // staged operand; during the attention phase: scores of the local t range (T'/4 <= 2048)
+    float recv[2][D2_RECV];              // ring of 2: a peer may send exchange k+1 while this CTA still reads exchange k
     float Wcs[64 * D2_WLD];
     float h2s[D2_H];
     float cvw[8 * D2_H];
@@ -61,6 +67,10 @@ struct D2Smem {
 };
 
 __device__ __forceinline__ float rtf32(float x) { return __uint_as_float(f2tf32(x)); }
+// gate nonlinearities of the training kernels: ex2.approx-based, absolute error ~1e-7 (the operands are TF32-rounded anyway);
+// the libm versions were ~0.3 us of every phase's critical path
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 2.f * fsig(2.f * x) - 1.f; }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
@@ -97,9 +107,8 @@ __device__ __forceinline__ void grid_barrier2(unsigned* counter, unsigned& targe
     __syncthreads();
 }
 
-
 // ---- sentinel hand-off ------------------------------------------------------------------------------------------------
-constexpr uint32_t D2_SENT = 0xFFFFFFFFu;            // "not written yet" (cudaMemsetAsync 0xFF / fill kernel before the launch)
+constexpr uint32_t D2_SENT = 0xFFFFFFFFu;            // "not written yet" (fill_sentinel_kernel before the launch)
 __device__ __forceinline__ float4 ld_pub4(const float* p) {
     float4 v;
     asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -143,8 +152,24 @@ __device__ __forceinline__ float poll1(const float* p) {
     while (unwritten(v)) { pc.tick(); v = ld_pub1(p); }
     return v;
 }
-// seg_load for an operand another CTA publishes during this launch: all loads in flight first, then only the float4s that
-// still hold a sentinel word are re-read
+// N float4 per thread of an operand other CTAs publish during this launch: all loads in flight first, then only the float4s
+// that still hold a sentinel word are re-read.  a[i] == nullptr: a row beyond the batch (zeros).
+template <int N>
+__device__ __forceinline__ void poll_many(float4 (&v)[N], const float* const (&a)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = a[i] ? ld_pub4(a[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    PollClock pc;
+    for (;;) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) bad |= unwritten(v[i]);
+        if (!bad) break;
+        pc.tick();
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (unwritten(v[i])) v[i] = ld_pub4(a[i]);
+    }
+}
+// One activation segment of the K quarter: W floats per row starting at ptr[row * ld]; 32 rows
 template <int W>
 __device__ __forceinline__ void seg_poll(float4 (&v)[W / 32], const float* ptr, int ld, int B) {
     const float* a[W / 32];
@@ -152,22 +177,10 @@ __device__ __forceinline__ void seg_poll(float4 (&v)[W / 32], const float* ptr, 
     for (int i = 0; i < W / 32; ++i) {
         const int idx = threadIdx.x + i * D2_THREADS, row = idx / (W / 4), k = (idx % (W / 4)) * 4;
         a[i] = row < B ? ptr + (size_t)row * ld + k : nullptr;
-        v[i] = a[i] ? ld_pub4(a[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    PollClock pc;
-    for (;;) {
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < W / 32; ++i) bad |= unwritten(v[i]);
-        if (!bad) break;
-        pc.tick();
-#pragma unroll
-        for (int i = 0; i < W / 32; ++i) if (unwritten(v[i])) v[i] = ld_pub4(a[i]);
-    }
+    poll_many<W / 32>(v, a);
 }
-
-// One activation segment of the K quarter: W floats per row starting at ptr[row * ld]; 32 rows.  All of a thread's loads
-// are issued before the first store (the serialised load -> convert -> store loop cost ~0.8 us per round trip, measured).
+// the same for data that was complete before the launch (or is ordered by a grid barrier)
 template <int W>
 __device__ __forceinline__ void seg_load(float4 (&v)[W / 32], const float* ptr, int ld, int B) {
 #pragma unroll
@@ -176,74 +189,106 @@ __device__ __forceinline__ void seg_load(float4 (&v)[W / 32], const float* ptr, 
         v[i] = row < B ? __ldcg(reinterpret_cast<const float4*>(ptr + (size_t)row * ld + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-template <int W>
+template <int W, int LD>
 __device__ __forceinline__ void seg_store(float* Xs_k0, const float4 (&v)[W / 32]) {
 #pragma unroll
     for (int i = 0; i < W / 32; ++i) {
         const int idx = threadIdx.x + i * D2_THREADS, row = idx / (W / 4), k = (idx % (W / 4)) * 4;
-        *reinterpret_cast<float4*>(Xs_k0 + row * D2_XLD + k) = make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
+        *reinterpret_cast<float4*>(Xs_k0 + row * LD + k) = make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
     }
 }
 
-// acc[mt][4] += X[:, 64 j0 : 64 j1] . Wfrag^T for this warp's n-tile; B fragments from TMEM (16 regs per 8 k-steps).
-__device__ __forceinline__ void mma_from_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr, int j0, int j1) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    uint32_t bcur[16], bnxt[16];
-    tmem_ld16_nowait(taddr + 16 * j0, bcur);
-    tmem_wait_ld();
-    for (int j = j0; j < j1; ++j) {
-        if (j + 1 < j1) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
-        const float* xr = Xs + g * D2_XLD + j * 64 + q;
+// ---- tensor-core core: one 16-wide k block, 32 rows x 4 n-tiles per warp ---------------------------------------------------
+// The struct pointers derive from an aligned-up uintptr, so the compiler no longer knows they are shared memory and emits
+// generic loads; explicit ld.shared keeps the operand path on LDS.128.
+__device__ __forceinline__ float4 lds128(uint32_t sa) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t fu(float x) { return __float_as_uint(x); }
+// Physical k = 16 blk + 4 q + 2 ksub + i  <->  logical (k-step ksub of the block, fragment column q + 4 i): thread (g, q)
+// reads X[row][16 blk + 4 q .. + 3] of rows g, g+8, g+16, g+24 with four 128-bit loads and has the A fragments of two
+// k-steps x two m-tiles.  b[(ksub * 4 + nt) * 2 + i] = W[n-tile nt, column g][16 blk + 4 q + 2 ksub + i].
+__device__ __forceinline__ void mma_blk(float (&acc)[2][4][4], uint32_t xa, uint32_t xrow8, const uint32_t (&b)[16]) {
+    const float4 x0 = lds128(xa), x1 = lds128(xa + xrow8), x2 = lds128(xa + 2 * xrow8), x3 = lds128(xa + 3 * xrow8);
+    {
+        const uint32_t a0[4] = {fu(x0.x), fu(x1.x), fu(x0.y), fu(x1.y)}, a1[4] = {fu(x2.x), fu(x3.x), fu(x2.y), fu(x3.y)};
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            const float* x0 = xr + ks * 8;
-            uint32_t a0[4], a1[4];
-            a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * D2_XLD]);
-            a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * D2_XLD + 4]);
-            a1[0] = __float_as_uint(x0[16 * D2_XLD]);     a1[1] = __float_as_uint(x0[24 * D2_XLD]);
-            a1[2] = __float_as_uint(x0[16 * D2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * D2_XLD + 4]);
-            const uint32_t b[2] = {bcur[2 * ks], bcur[2 * ks + 1]};
-            mma_tf32(acc[0], a0, b);
-            mma_tf32(acc[1], a1, b);
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint32_t bb[2] = {b[2 * nt], b[2 * nt + 1]};
+            mma_tf32(acc[0][nt], a0, bb);
+            mma_tf32(acc[1][nt], a1, bb);
         }
-        if (j + 1 < j1) {
+    }
+    {
+        const uint32_t a0[4] = {fu(x0.z), fu(x1.z), fu(x0.w), fu(x1.w)}, a1[4] = {fu(x2.z), fu(x3.z), fu(x2.w), fu(x3.w)};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint32_t bb[2] = {b[8 + 2 * nt], b[8 + 2 * nt + 1]};
+            mma_tf32(acc[0][nt], a0, bb);
+            mma_tf32(acc[1][nt], a1, bb);
+        }
+    }
+}
+// NB consecutive blocks of X against NB consecutive 16-register fragment blocks in TMEM.  The caller has already issued the
+// tcgen05.ld of the first block into bcur (so its latency hides behind the operand staging).
+template <int NB>
+__device__ __forceinline__ void mma_run_tmem(float (&acc)[2][4][4], uint32_t xa, uint32_t xrow8, uint32_t taddr, uint32_t (&bcur)[16]) {
+    uint32_t bnxt[16];
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i + 1 < NB) tmem_ld16_nowait(taddr + 16 * (i + 1), bnxt);
+        mma_blk(acc, xa + 64 * i, xrow8, bcur);
+        if (i + 1 < NB) {
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) bcur[i] = bnxt[i];
+            for (int j = 0; j < 16; ++j) bcur[j] = bnxt[j];
         }
     }
 }
-
-// same with B fragments from shared memory (context weights), k-steps ks0 .. ks0 + 15 of the 32
-__device__ __forceinline__ void mma_from_smem(float (&acc)[2][4], const float* Xs, const float* Ws, int ks0) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const float* xr = Xs + g * D2_XLD + q;
-    const float* wr = Ws + (8 * w + g) * D2_WLD + q;
-#pragma unroll 8
-    for (int ks = ks0; ks < ks0 + D2_KQ / 16; ++ks) {
-        const float* x0 = xr + ks * 8;
-        uint32_t a0[4], a1[4];
-        a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * D2_XLD]);
-        a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * D2_XLD + 4]);
-        a1[0] = __float_as_uint(x0[16 * D2_XLD]);     a1[1] = __float_as_uint(x0[24 * D2_XLD]);
-        a1[2] = __float_as_uint(x0[16 * D2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * D2_XLD + 4]);
-        const uint32_t b[2] = {__float_as_uint(wr[ks * 8]), __float_as_uint(wr[ks * 8 + 4])};
-        mma_tf32(acc[0], a0, b);
-        mma_tf32(acc[1], a1, b);
+// the same with the weight operand in shared memory, row-major [n][k] in the same physical k order: wa = address of
+// W[first n-tile's row g][16 blk + 4 q], wrow8 = bytes of 8 rows; one 128-bit load per n-tile feeds both k-steps
+template <int NB>
+__device__ __forceinline__ void mma_run_smem(float (&acc)[2][4][4], uint32_t xa, uint32_t xrow8, uint32_t wa, uint32_t wrow8) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        uint32_t b[16];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float4 w4 = lds128(wa + 64 * i + nt * wrow8);
+            b[2 * nt] = fu(w4.x); b[2 * nt + 1] = fu(w4.y); b[8 + 2 * nt] = fu(w4.z); b[8 + 2 * nt + 1] = fu(w4.w);
+        }
+        mma_blk(acc, xa + 64 * i, xrow8, b);
     }
 }
 
-// reduce-scatter of the four K-partial 32 x 64 products: warp w holds n-tile w = columns 8w..8w+7, owned by CTA w/2
-__device__ __forceinline__ void exchange_send(const float (&acc)[2][4], D2Smem& sm, int rank, int buf) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
-    const uint32_t base = mapa(saddr(sm.recv[buf]), dst), bar = mapa(saddr(&sm.mbar_x), dst);
+// reduce-scatter of the 16 K-partial 32 x 64 products of a cluster (4 CTAs x 4 k-slices): warp (kh, nh) holds n-tiles
+// 4 nh .. 4 nh + 3; n-tile j belongs to CTA j / 2.  Receiver layout [src = 4 rank + kh][row][16 cols].
+__device__ __forceinline__ void exchange16(const float (&acc)[2][4][4], uint32_t recv_sa, uint32_t mbar_sa, int rank, int kh, int nh) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int src = 4 * rank + kh;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const int r0 = 16 * mt + g;
-        st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
-        st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+    for (int nt = 0; nt < 4; ++nt) {
+        const int gnt = 4 * nh + nt, dst = gnt >> 1, col = 8 * (gnt & 1) + 2 * q;
+        const uint32_t base = mapa(recv_sa, dst), bar = mapa(mbar_sa, dst);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = 16 * mt + g;
+            st_async_v2(base + (uint32_t)(((src * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][nt][0], acc[mt][nt][1]), bar);
+            st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][nt][2], acc[mt][nt][3]), bar);
+        }
     }
+}
+// sum of the 16 partial float4s of (row, 4 columns c4)
+__device__ __forceinline__ float4 recv_sum16(uint32_t recv_sa, int row, int c4, float4 v) {
+#pragma unroll
+    for (int src = 0; src < 16; ++src) {
+        const float4 r = lds128(recv_sa + (uint32_t)(((src * 32 + row) * 16 + 4 * c4) * 4));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    return v;
 }
 
 }  // namespace
@@ -275,12 +320,15 @@ dec_seq2_fwd_kernel(DecSeq p) {
     __shared__ float scratch[32];
     __shared__ int iscratch[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int kh = w & 3, nh = w >> 2;       // warp = (k slice of the CTA's K quarter, 32-column half of the cluster's 64 columns)
     const int rank = (int)cluster_rank(), cl = blockIdx.x / D2_CS, cta = blockIdx.x, ncta = gridDim.x;
-    const int B = p.B, S = p.S, L = p.L, Tp = p.Tp, Vp = p.Vp;
+    const int B = p.B, S = p.S, Tp = p.Tp, Vp = p.Vp;
     constexpr int H = D2_H, E = D2_E, A = D2_A, ldx0 = D2_E + D2_A;
     unsigned bar_target = 0;
-    int nprof = 0;
+    int nprof = 0, nfine = 0;
 #define D2_SYNC() grid_barrier2(p.bar, bar_target)
+    // option dec_prof = 2 + c: thread 0 of CTA c stamps clock64 inside the phases of step 6 (tools/dec_phase_times.py --fine)
+#define D2_FINE(s_) do { if (p.prof_fine && (s_) == 6 && blockIdx.x == p.prof_fine - 1 && threadIdx.x == 0 && nfine < 64) p.prof[3000 + nfine++] = (unsigned long long)clock64(); } while (0)
     // phase boundary: nothing to wait for (consumers poll the hand-off slots); option dec_sync puts the grid barrier back
     // (bisecting), option dec_prof stamps the time CTA 0 gets here
 #define D2_PHASE_END() do { if (p.sync_all) D2_SYNC(); \
@@ -301,52 +349,50 @@ dec_seq2_fwd_kernel(DecSeq p) {
     tc_fence_after();
     const uint32_t tmem_lane = sm.tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (w >= 4 ? 256u : 0u);
 
-    // LSTM weights -> TMEM: thread (w, lane) keeps B[k][n] = W[64 cl + 8w + g][kcol(k)] for k = 8 ks + q, 8 ks + q + 4
-    {
-        const int row = 64 * cl + 8 * w + g;
-        for (int l = 0; l < 3; ++l) {
-            const int kq = l == 0 ? D2_KQ0 : D2_KQ;
-            const int in = l == 0 ? ldx0 : H;
-            const float* Wup = p.Wup[l] + (size_t)row * in;
-            const float* Wlat = p.Wlat[l] + (size_t)row * H;
-            const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
-            // two 16-value fragments per round: 32 scattered 4-byte loads in flight before the first tcgen05.st (one fragment at a
-            // time serialised 13 L2 round trips per thread: 47 us of kernel prologue)
-            auto wload = [&](int k) -> float {
-                if (l == 0) {           // K order [ht 128 | emb 32 | h_prev 128 | pad 32]: the just-produced operand first
-                    if (k < 128) return __ldg(Wup + E + 128 * rank + k);
-                    if (k < 160) return __ldg(Wup + 32 * rank + (k - 128));
-                    if (k < 288) return __ldg(Wlat + 128 * rank + (k - 160));
-                    return 0.f;
+    // LSTM weights -> TMEM.  Fragment block i of layer l (16 values per thread) covers the 16 physical k of X block
+    // xb(i): the warp's step-old blocks first (8 + nnc kh + i), then its two fresh blocks (2 kh + ...).
+    for (int l = 0; l < 3; ++l) {
+        const int nnc = l == 0 ? 3 : 2, nblk = nnc + 2;
+        const int in = l == 0 ? ldx0 : H;
+        const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
+        float4 v[5][4];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i >= nblk) break;
+            const int xb = i < nnc ? 8 + nnc * kh + i : 2 * kh + (i - nnc);
+            const int kc = 16 * xb + 4 * q;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int row = 64 * cl + 8 * (4 * nh + nt) + g;
+                const float* src;
+                if (l == 0) {           // K order [ht 128 | emb 32 | h_prev 128 | pad 32]
+                    if (kc < 128) src = p.Wup[0] + (size_t)row * in + E + 128 * rank + kc;
+                    else if (kc < 160) src = p.Wup[0] + (size_t)row * in + 32 * rank + (kc - 128);
+                    else if (kc < 288) src = p.Wlat[0] + (size_t)row * H + 128 * rank + (kc - 160);
+                    else src = nullptr;
+                } else {
+                    src = kc < 128 ? p.Wup[l] + (size_t)row * in + 128 * rank + kc : p.Wlat[l] + (size_t)row * H + 128 * rank + (kc - 128);
                 }
-                return k < 128 ? __ldg(Wup + 128 * rank + k) : __ldg(Wlat + 128 * rank + (k - 128));
-            };
-            const int nj = kq >> 6;
-            for (int j = 0; j < nj; j += 2) {
-                float v0[16], v1[16];
-                const bool two = j + 1 < nj;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v0[i] = wload(j * 64 + (i >> 1) * 8 + q + 4 * (i & 1));
-                if (two) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v1[i] = wload((j + 1) * 64 + (i >> 1) * 8 + q + 4 * (i & 1));
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v0[i] = rtf32(v0[i]);
-                tmem_st16(tmem_lane + tcol + 16 * j, v0);
-                if (two) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v1[i] = rtf32(v1[i]);
-                    tmem_st16(tmem_lane + tcol + 16 * (j + 1), v1);
-                }
+                v[i][nt] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        tmem_wait_st();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i >= nblk) break;
+            float f[16];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                f[2 * nt] = rtf32(v[i][nt].x); f[2 * nt + 1] = rtf32(v[i][nt].y);
+                f[8 + 2 * nt] = rtf32(v[i][nt].z); f[8 + 2 * nt + 1] = rtf32(v[i][nt].w);
+            }
+            tmem_st16(tmem_lane + tcol + 16 * i, f);
+        }
     }
+    tmem_wait_st();
     // context weights -> smem (clusters 0..7 compute ht): Wcs[j][k] = Wc[64 cl + j][kcol(k)], kcol: cv quarter | h quarter
     if (cl < A / 64) {
-        for (int idx = tid; idx < 64 * (D2_KQ / 4); idx += D2_THREADS) {
-            const int j = idx / (D2_KQ / 4), k = (idx % (D2_KQ / 4)) * 4;
+        for (int idx = tid; idx < 64 * 64; idx += D2_THREADS) {
+            const int j = idx >> 6, k = (idx & 63) * 4;
             const int kc = k < 128 ? 128 * rank + k : H + 128 * rank + (k - 128);
             float4 v = __ldg(reinterpret_cast<const float4*>(p.Wc + (size_t)(64 * cl + j) * (2 * H) + kc));
             v.x = rtf32(v.x); v.y = rtf32(v.y); v.z = rtf32(v.z); v.w = rtf32(v.w);
@@ -360,9 +406,11 @@ dec_seq2_fwd_kernel(DecSeq p) {
         for (int i = cta; i < S * B; i += ncta) embed_tf_row(p, i, tid, D2_THREADS);
     // cell state of the owned (row, unit) pairs stays in registers
     const int e_row = tid >> 2, e_ul = tid & 3, e_unit = 16 * cl + 4 * rank + e_ul;
-    float creg[3] = {0.f, 0.f, 0.f};
-    if (tid < 128 && e_row < B)
-        for (int l = 0; l < 3; ++l) creg[l] = p.Cd[l][(size_t)e_row * H + e_unit];
+    const bool own = tid < 128 && e_row < B;
+    float creg0 = 0.f, creg1 = 0.f, creg2 = 0.f;
+    if (own) {
+        creg0 = p.Cd[0][(size_t)e_row * H + e_unit]; creg1 = p.Cd[1][(size_t)e_row * H + e_unit]; creg2 = p.Cd[2][(size_t)e_row * H + e_unit];
+    }
     uint32_t par_x = 0, par_a = 0;
     if (tid == 0) { mbar_expect_tx(&sm.mbar_x, D2_XBYTES); mbar_expect_tx(&sm.mbar_a, D2_ABYTES); }
     if (p.prof && cta == 0 && tid == 0) p.prof[1] = gtimer2();
@@ -370,6 +418,12 @@ dec_seq2_fwd_kernel(DecSeq p) {
     cluster_sync_all();
     D2_SYNC();
 
+    const uint32_t xrow8 = 8 * D2_XLD * 4, wrow8 = 8 * D2_WLD * 4;
+    const uint32_t xa_g = saddr(sm.Xs) + (uint32_t)((g * D2_XLD + 4 * q) * 4);                 // + 64 * block
+    const uint32_t wa_g = saddr(sm.Wcs) + (uint32_t)(((8 * 4 * nh + g) * D2_WLD + 4 * q) * 4);
+    const uint32_t recv_sa0 = saddr(sm.recv[0]);
+#define RECV_SA(b_) (recv_sa0 + (uint32_t)(b_) * D2_XBYTES)
+    const uint32_t mbx_sa = saddr(&sm.mbar_x);
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
     int xbuf = 0;
     for (int s = 0; s < S; ++s) {
@@ -377,7 +431,11 @@ dec_seq2_fwd_kernel(DecSeq p) {
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const uint32_t tcol = l == 0 ? D2_TCOL0 : (l == 1 ? D2_TCOL1 : D2_TCOL2);
+            const int nnc = l == 0 ? 3 : 2;
             const float* x0 = p.x0 + (size_t)s * B * ldx0;
+            D2_FINE(s);
+            uint32_t bfr[16];
+            tmem_ld16_nowait(tmem_lane + tcol, bfr);
             // (1) operands that are a step old: own recurrent state (layer 0: + the embedding rows)
             {
                 float4 v2[4];
@@ -385,25 +443,30 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 if (l == 0) {
                     float4 v0[1];
                     seg_load<32>(v0, x0 + 32 * rank, ldx0, B);
-                    seg_store<32>(sm.Xs + 128, v0); seg_store<128>(sm.Xs + 160, v2);
+                    seg_store<32, D2_XLD>(sm.Xs + 128, v0); seg_store<128, D2_XLD>(sm.Xs + 160, v2);
                 } else {
-                    seg_store<128>(sm.Xs + 128, v2);
+                    seg_store<128, D2_XLD>(sm.Xs + 128, v2);
                 }
             }
             __syncthreads();
-            float acc[2][4] = {};
-            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, 2, l == 0 ? 5 : 4);
+            D2_FINE(s);
+            float acc[2][4][4] = {};
+            if (l == 0) mma_run_tmem<3>(acc, xa_g + 64 * (8 + 3 * kh), xrow8, tmem_lane + tcol, bfr);
+            else mma_run_tmem<2>(acc, xa_g + 64 * (8 + 2 * kh), xrow8, tmem_lane + tcol, bfr);
+            D2_FINE(s);
+            tmem_ld16_nowait(tmem_lane + tcol + 16 * nnc, bfr);
             // (2) the operand the previous phase has just produced: ht of step s-1 (input feeding) / the layer below
             {
                 float4 v1[4];
                 if (l == 0) seg_poll<128>(v1, x0 + E + 128 * rank, ldx0, B);
                 else seg_poll<128>(v1, p.hdd[l - 1] + (size_t)s * B * H + 128 * rank, H, B);
-                seg_store<128>(sm.Xs, v1);
+                D2_FINE(s);
+                seg_store<128, D2_XLD>(sm.Xs, v1);
             }
             __syncthreads();
-            mma_from_tmem(acc, sm.Xs, tmem_lane + tcol, 0, 2);
-            exchange_send(acc, sm, rank, xbuf);
-            const bool own = tid < 128 && e_row < B;
+            mma_run_tmem<2>(acc, xa_g + 64 * (2 * kh), xrow8, tmem_lane + tcol + 16 * nnc, bfr);
+            D2_FINE(s);
+            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
             const size_t e = (size_t)e_row * H + e_unit;
             float4 gs = make_float4(0.f, 0.f, 0.f, 0.f); float dm = 1.f;
             if (own) {     // while the exchange is in flight
@@ -411,18 +474,14 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 dm = dropout_scale(p.seed, 16 + l, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
             }
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            D2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (own) {
-                const float* rv = sm.recv[xbuf];
-#pragma unroll
-                for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(rv + (src * 32 + e_row) * 16 + 4 * e_ul);
-                    gs.x += r.x; gs.y += r.y; gs.z += r.z; gs.w += r.w;
-                }
-                const float ga = tanhf(gs.x), gi = sigmoidf_(gs.y), gf = sigmoidf_(gs.z), go = sigmoidf_(gs.w);
-                const float c = ga * gi + gf * creg[l];
-                creg[l] = c;
-                const float hv = go * tanhf(c);
+                gs = recv_sum16(RECV_SA(xbuf), e_row, e_ul, gs);
+                const float ga = ftanh(gs.x), gi = fsig(gs.y), gf = fsig(gs.z), go = fsig(gs.w);
+                const float c = ga * gi + gf * (l == 0 ? creg0 : (l == 1 ? creg1 : creg2));
+                if (l == 0) creg0 = c; else if (l == 1) creg1 = c; else creg2 = c;
+                const float hv = go * ftanh(c);
                 // published values first (the next phase / the next step polls them), then what only backward reads
                 if (l == 2) st_pub1(p.cvh + ((size_t)s * B + e_row) * 2 * H + H + e_unit, hv * dm);
                 else st_pub1(p.hdd[l] + (size_t)s * B * H + e, hv * dm);
@@ -431,6 +490,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 p.Cd[l][(size_t)(s + 1) * B * H + e] = c;
             }
             xbuf ^= 1;
+            D2_FINE(s);
             __syncthreads();        // every warp is done with Xs and recv before the next phase restages them
             D2_PHASE_END();
         }
@@ -451,7 +511,9 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 for (int i = 0; i < 4; ++i) { a[i] = __ldg(reinterpret_cast<const float4*>(ewb + (size_t)t * H + 128 * i)); x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i)); }
                 eb = __ldg(ebb + t);
             }
+            D2_FINE(s);
             if (tid < H / 4) *reinterpret_cast<float4*>(sm.h2s + 4 * tid) = poll4(cvh_b + H + 4 * tid);
+            D2_FINE(s);
             __syncthreads();
             float4 hq[4];
 #pragma unroll
@@ -460,7 +522,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
             float4 cv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) cv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float* sc = sm.sc;
+            float* sc = sm.Xs;       // scores of the local t range (Xs is idle during this phase)
             while (t < t_hi) {
                 const int tn = t + 8;
                 float4 an[4], xn[4]; float ebn = 0.f;
@@ -491,6 +553,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 }
                 t = tn;
             }
+            D2_FINE(s);
             if (lane == 0) { sm.wstat[2 * w] = mw; sm.wstat[2 * w + 1] = sw; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sm.cvw + w * H + 128 * i + 4 * lane) = cv[i];
@@ -513,7 +576,9 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 st_async_v2(mapa(saddr(sm.cvx) + (uint32_t)((rank * 128 + (2 * tid & 127)) * 4), dst), v, mapa(saddr(&sm.mbar_a), dst));
                 if (tid < 4) st_async_v2(mapa(saddr(sm.statx) + (uint32_t)(rank * 8), tid), make_float2(Mr, sr), mapa(saddr(&sm.mbar_a), tid));
             }
+            D2_FINE(s);
             mbar_wait(&sm.mbar_a, par_a); par_a ^= 1;
+            D2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);
             float M = -INFINITY;
 #pragma unroll
@@ -530,46 +595,47 @@ dec_seq2_fwd_kernel(DecSeq p) {
             }
             float* al = p.alpha + ((size_t)s * B + b) * Tp;
             for (int tt = t_lo + tid; tt < t_hi; tt += D2_THREADS) al[tt] = __expf(sc[tt - t_lo] - M) * invZ;
-            __syncthreads();        // cvw / cvx / sc are reused by the next step's attention only, Xs by the next phase
+            D2_FINE(s);
+            __syncthreads();        // cvw / cvx are reused by the next step's attention only, Xs (scores) by the next phase
         }
         D2_PHASE_END();
         // ---- ht = tanh(context([cv ; h]))  (seq2seq.py:386-390), clusters 0..7; also the next step's input feeding ----
         if (cl < A / 64) {
             const float* cvh = p.cvh + (size_t)s * B * 2 * H;
+            D2_FINE(s);
             {   // h2 (published one phase ago) first, then the context vector the attention phase has just produced
                 float4 v2[4];
                 seg_poll<128>(v2, cvh + H + 128 * rank, 2 * H, B);
-                seg_store<128>(sm.Xs + 128, v2);
+                seg_store<128, D2_XLD>(sm.Xs + 128, v2);
             }
             __syncthreads();
-            float acc[2][4] = {};
-            mma_from_smem(acc, sm.Xs, sm.Wcs, 16);
+            float acc[2][4][4] = {};
+            mma_run_smem<2>(acc, xa_g + 64 * (8 + 2 * kh), xrow8, wa_g + 64 * (8 + 2 * kh), wrow8);
             {
                 float4 v1[4];
+                D2_FINE(s);
                 seg_poll<128>(v1, cvh + 128 * rank, 2 * H, B);
-                seg_store<128>(sm.Xs, v1);
+                D2_FINE(s);
+                seg_store<128, D2_XLD>(sm.Xs, v1);
             }
             __syncthreads();
-            mma_from_smem(acc, sm.Xs, sm.Wcs, 0);
-            exchange_send(acc, sm, rank, xbuf);
+            mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, wa_g + 64 * (2 * kh), wrow8);
+            D2_FINE(s);
+            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
             const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
-            const bool own = tid < 128 && e_row < B;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (own) v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            D2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (own) {
-                const float* rv = sm.recv[xbuf];
-#pragma unroll
-                for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(rv + (src * 32 + e_row) * 16 + 4 * e_ul);
-                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-                }
-                v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+                v = recv_sum16(RECV_SA(xbuf), e_row, e_ul, v);
+                v.x = ftanh(v.x); v.y = ftanh(v.y); v.z = ftanh(v.z); v.w = ftanh(v.w);
                 if (s + 1 < S) st_pub4(p.x0 + ((size_t)(s + 1) * B + e_row) * ldx0 + E + n0, v);
                 *reinterpret_cast<float4*>(p.ht + ((size_t)s * B + e_row) * A + n0) = v;
             }
             xbuf ^= 1;
+            D2_FINE(s);
             __syncthreads();
         }
         D2_PHASE_END();
@@ -602,31 +668,36 @@ dec_seq2_fwd_kernel(DecSeq p) {
     cluster_sync_all();
 #undef D2_SYNC
 #undef D2_PHASE_END
+#undef D2_FINE
+#undef RECV_SA
 }
 
 
 // ================================================================================================================
 // backward
 // ================================================================================================================
-// Same organisation as the forward kernel (32 clusters x 4 CTAs, K split across the cluster, reduce-scatter through
-// DSMEM, weights resident on chip).  Per step (S-1 .. 0), 6 grid barriers instead of 8:
+// Same organisation as the forward kernel (32 clusters x 4 CTAs, K split across the cluster and the warps, reduce-scatter
+// through DSMEM, weights resident on chip, sentinel-polled hand-off slots).  Per step (S-1 .. 0), 6 phases:
 //   A  du = (dz.Wo [precomputed for all steps] + dht_feed) * (1 - ht^2)  fused into the operand staging; dcvh = du . Wc
 //   B  attention backward, cluster = batch row, ONE pass over T': with a_t = alpha_t * (enc_t . dcv),
 //        dq = sum_t a_t enc_t - (sum_t a_t) * cv      (cv = the forward context, so enc is read once, not twice)
 //        ds_t = a_t - alpha_t * sum_t a_t  is stored; d_enc = alpha^T dcv + ds^T q becomes ONE batched contraction after
 //        the loop instead of a read-modify-write of the whole (B, T', H) gradient every step
-//   C  dh_top = dcvh[:, H:] + dq . Wa, fused LSTM cell backward of the top layer (dG in place over the saved gates)
+//   C  dh_top = dcvh[:, H:] + dq . Wa, fused LSTM cell backward of the top layer
 //   D2, D1, D0  [dx | dh_rec] = dG_l . [W_up | W_lat] (K = 2048), fused cell backward of layer l-1 on the dx columns;
 //        the three 2048 x 1024 operands live in TMEM as per-thread mma fragments (192 values per thread).
+// Hand-off slots (one per step, DecSeq): dcv_all / dhh_all (the two halves of du . Wc), dq, dgd[l] (dG of layer l; the forward
+// gates in act[] stay intact), dxr[l] (dh_rec of layer l: produced at step s, consumed at s-1), dfeed (d ht fed back through
+// layer 0's input).  The cell-state gradient of an owned (row, unit) stays in registers across steps.
 // The embedding columns of layer 0 (EmbedID backward) are one batched GEMM + scatter-add after the loop.
 namespace {
 
-constexpr int B2_XLD = 512 + 4;          // staged dG quarter: 32 x 512
-constexpr int B2_WLD = 128 + 4;          // context / attention weight slices: 64 x 128
+constexpr int B2_XLD = 512 + 16;         // staged dG quarter: 32 x 512
+constexpr int B2_WLD = 128 + 16;         // context / attention weight slices: 64 x 128
 
 struct B2Smem {
-    float Xs[32 * B2_XLD];
-    float recv[4 * 32 * 16];
+    float Xs[32 * B2_XLD];               // staged operand; during the attention phase: a_t of the local t range
+    float recv[2][D2_RECV];
     float Wcs[64 * B2_WLD];              // Wc^T slice (clusters 0..15)
     float Was[64 * B2_WLD];              // Wa^T slice (clusters 0..7)
     float dcvs[D2_H];
@@ -638,58 +709,9 @@ struct B2Smem {
     uint32_t tmem_slot;
 };
 
-// acc += X(32 x 128, row stride B2_XLD) . Ws^T for this warp's n-tile (weights in smem, row stride B2_WLD)
-__device__ __forceinline__ void mma_k128_smem(float (&acc)[2][4], const float* Xs, const float* Ws) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const float* xr = Xs + g * B2_XLD + q;
-    const float* wr = Ws + (8 * w + g) * B2_WLD + q;
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {
-        const float* x0 = xr + ks * 8;
-        uint32_t a0[4], a1[4];
-        a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * B2_XLD]);
-        a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * B2_XLD + 4]);
-        a1[0] = __float_as_uint(x0[16 * B2_XLD]);     a1[1] = __float_as_uint(x0[24 * B2_XLD]);
-        a1[2] = __float_as_uint(x0[16 * B2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * B2_XLD + 4]);
-        const uint32_t b[2] = {__float_as_uint(wr[ks * 8]), __float_as_uint(wr[ks * 8 + 4])};
-        mma_tf32(acc[0], a0, b);
-        mma_tf32(acc[1], a1, b);
-    }
-}
-
-// acc += X[:, koff : koff + 256] . frag^T, B fragments (64 values) from TMEM
-__device__ __forceinline__ void mma_k256_tmem(float (&acc)[2][4], const float* Xs, uint32_t taddr) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    uint32_t bcur[16], bnxt[16];
-    tmem_ld16_nowait(taddr, bcur);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j + 1 < 4) tmem_ld16_nowait(taddr + 16 * (j + 1), bnxt);
-        const float* xr = Xs + g * B2_XLD + j * 64 + q;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            const float* x0 = xr + ks * 8;
-            uint32_t a0[4], a1[4];
-            a0[0] = __float_as_uint(x0[0]);               a0[1] = __float_as_uint(x0[8 * B2_XLD]);
-            a0[2] = __float_as_uint(x0[4]);               a0[3] = __float_as_uint(x0[8 * B2_XLD + 4]);
-            a1[0] = __float_as_uint(x0[16 * B2_XLD]);     a1[1] = __float_as_uint(x0[24 * B2_XLD]);
-            a1[2] = __float_as_uint(x0[16 * B2_XLD + 4]); a1[3] = __float_as_uint(x0[24 * B2_XLD + 4]);
-            const uint32_t b[2] = {bcur[2 * ks], bcur[2 * ks + 1]};
-            mma_tf32(acc[0], a0, b);
-            mma_tf32(acc[1], a1, b);
-        }
-        if (j + 1 < 4) {
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) bcur[i] = bnxt[i];
-        }
-    }
-}
-
 // LSTM cell backward for one (row, unit): dh = d(link output h); returns dG and updates dc
 __device__ __forceinline__ float4 cell_bwd(float dh, const float4 a, float cc, float cp, float& dc) {
-    const float tc = tanhf(cc);
+    const float tc = ftanh(cc);
     const float dct = dc + dh * a.w * (1.f - tc * tc);
     float4 dg;
     dg.x = dct * a.y * (1.f - a.x * a.x);
@@ -707,12 +729,15 @@ dec_seq2_bwd_kernel(DecSeq p) {
     extern __shared__ uint8_t smem_raw[];
     B2Smem& sm = *reinterpret_cast<B2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int kh = w & 3, nh = w >> 2;       // phases A, C: warp = (k slice, 32-column half)
     const int rank = (int)cluster_rank(), cl = blockIdx.x / D2_CS, cta = blockIdx.x;
     const int B = p.B, S = p.S, Tp = p.Tp;
     constexpr int H = D2_H, E = D2_E, A = D2_A;
     unsigned bar_target = 0;
-    int nprof = 0;
-#define B2_SYNC() do { grid_barrier2(p.bar, bar_target); \
+    int nprof = 0, nfine = 0;
+#define B2_SYNC() grid_barrier2(p.bar, bar_target)
+#define B2_FINE(s_) do { if (p.prof_fine && (s_) == 6 && blockIdx.x == p.prof_fine - 1 && threadIdx.x == 0 && nfine < 64) p.prof[3000 + nfine++] = (unsigned long long)clock64(); } while (0)
+#define B2_PHASE_END() do { if (p.sync_all) B2_SYNC(); \
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { p.prof[++nprof] = gtimer2(); p.prof[0] = (unsigned long long)nprof; } } while (0)
 
     if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[4090] = gtimer2();
@@ -728,25 +753,33 @@ dec_seq2_bwd_kernel(DecSeq p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_lane = sm.tmem_slot + ((uint32_t)(32 * (w & 3)) << 16) + (w >= 4 ? 256u : 0u);
-    const int nt = w & 3, kh = w >> 2;       // D phases: warp = (n-tile of the cluster's 32 columns, half of the CTA's K quarter)
 
-    // [W_up | W_lat]^T fragments -> TMEM.  Output column n = 32 cl + 8 nt + g of [dx(512) | dh_rec(512)]; row of WcatT:
+    // [W_up | W_lat]^T fragments -> TMEM.  D phases: warp w owns the 16-blocks 4w .. 4w+3 of the CTA's 512 dG columns and all
+    // four n-tiles of the cluster's 32 output columns n = 32 cl + 8 nt + g of [dx(512) | dh_rec(512)]; row of WcatT:
     // dx part -> input column (layer 0: E + n, the ht slot; layers 1,2: n), dh_rec part -> in + (n - 512).
-    {
-        const int n = 32 * cl + 8 * nt + g;
-        for (int l = 0; l < 3; ++l) {
-            const int in = l == 0 ? E + A : H;
-            const int wrow = n < H ? (l == 0 ? E + n : n) : in + (n - H);
-            const float* src = p.WcatT[l] + (size_t)wrow * 4 * H + 512 * rank + 256 * kh;
-            for (int j = 0; j < 4; ++j) {
-                float v[16];
+    for (int l = 0; l < 3; ++l) {
+        const int in = l == 0 ? E + A : H;
+        float4 v[4][4];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = rtf32(__ldg(src + j * 64 + (i >> 1) * 8 + q + 4 * (i & 1)));
-                tmem_st16(tmem_lane + 64 * l + 16 * j, v);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n = 32 * cl + 8 * nt + g;
+                const int wrow = n < H ? (l == 0 ? E + n : n) : in + (n - H);
+                v[i][nt] = __ldg(reinterpret_cast<const float4*>(p.WcatT[l] + (size_t)wrow * 4 * H + 512 * rank + 16 * (4 * w + i) + 4 * q));
             }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float f[16];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                f[2 * nt] = rtf32(v[i][nt].x); f[2 * nt + 1] = rtf32(v[i][nt].y);
+                f[8 + 2 * nt] = rtf32(v[i][nt].z); f[8 + 2 * nt + 1] = rtf32(v[i][nt].w);
+            }
+            tmem_st16(tmem_lane + 64 * l + 16 * i, f);
         }
-        tmem_wait_st();
     }
+    tmem_wait_st();
     if (cl < 2 * H / 64)
         for (int idx = tid; idx < 64 * 32; idx += D2_THREADS) {
             const int j = idx >> 5, k = (idx & 31) * 4;
@@ -766,28 +799,49 @@ dec_seq2_bwd_kernel(DecSeq p) {
     cluster_sync_all();
     B2_SYNC();
 
+    const uint32_t xrow8 = 8 * B2_XLD * 4, wrow8 = 8 * B2_WLD * 4;
+    const uint32_t xa_g = saddr(sm.Xs) + (uint32_t)((g * B2_XLD + 4 * q) * 4);
+    const uint32_t wca_g = saddr(sm.Wcs) + (uint32_t)(((8 * 4 * nh + g) * B2_WLD + 4 * q) * 4);
+    const uint32_t waa_g = saddr(sm.Was) + (uint32_t)(((8 * 4 * nh + g) * B2_WLD + 4 * q) * 4);
+    const uint32_t recv_sa0 = saddr(sm.recv[0]);
+#define RECV_SA(b_) (recv_sa0 + (uint32_t)(b_) * D2_XBYTES)
+    const uint32_t mbx_sa = saddr(&sm.mbar_x);
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
     const int a_row = tid >> 2, a_c4 = tid & 3;          // phases A, C epilogue: (row, 4 columns of the CTA's 16)
     const int d_row = tid >> 3, d_c = tid & 7;           // D phases epilogue: (row, 1 column of the CTA's 8)
+    const bool a_ok = tid < 128 && a_row < B, d_ok = d_row < B;
+    float4 dcC = make_float4(0.f, 0.f, 0.f, 0.f);        // d(cell state) of the owned (row, 4 units) of layer 2 (phase C)
+    float dcD0 = 0.f, dcD1 = 0.f;                        // of the owned (row, unit) of layers 0, 1 (phases D1, D2)
+    int xbuf = 0;
     for (int s = S - 1; s >= 0; --s) {
         const bool last = (s == S - 1);
         // ---- A: du (fused into the staging), dcvh = du . Wc ---------------------------------------------------------
         if (cl < 2 * H / 64) {
             float4 v[4];
+            {
+                float4 d[4], t[4], f[4];
+                const float* fa[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = (tid >> 5) + 8 * i, k = 128 * rank + 4 * lane;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < B) {
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (tid >> 5) + 8 * i, k = 128 * rank + 4 * lane;
                     const size_t r = (size_t)s * B + row;
-                    float4 d = __ldcg(reinterpret_cast<const float4*>(p.dzw + r * A + k));
-                    const float4 t = __ldcg(reinterpret_cast<const float4*>(p.ht + r * A + k));
-                    if (!last) {
-                        const float4 f = __ldcg(reinterpret_cast<const float4*>(p.dxh[0] + (size_t)row * (E + A + H) + E + k));
-                        d.x += f.x; d.y += f.y; d.z += f.z; d.w += f.w;
+                    d[i] = t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    fa[i] = nullptr;
+                    if (row < B) {
+                        d[i] = __ldcg(reinterpret_cast<const float4*>(p.dzw + r * A + k));
+                        t[i] = __ldcg(reinterpret_cast<const float4*>(p.ht + r * A + k));
+                        if (!last) fa[i] = p.dfeed + ((size_t)(s + 1) * B + row) * A + k;
                     }
-                    v[i] = make_float4(d.x * (1.f - t.x * t.x), d.y * (1.f - t.y * t.y), d.z * (1.f - t.z * t.z), d.w * (1.f - t.w * t.w));
-                    if (cl == 0) *reinterpret_cast<float4*>(p.du + r * A + k) = v[i];
+                }
+                B2_FINE(s);
+                poll_many<4>(f, fa);
+                B2_FINE(s);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (tid >> 5) + 8 * i, k = 128 * rank + 4 * lane;
+                    const float dx = d[i].x + f[i].x, dy = d[i].y + f[i].y, dz = d[i].z + f[i].z, dw = d[i].w + f[i].w;
+                    v[i] = make_float4(dx * (1.f - t[i].x * t[i].x), dy * (1.f - t[i].y * t[i].y), dz * (1.f - t[i].z * t[i].z), dw * (1.f - t[i].w * t[i].w));
+                    if (cl == 0 && row < B) *reinterpret_cast<float4*>(p.du + ((size_t)s * B + row) * A + k) = v[i];
                 }
             }
 #pragma unroll
@@ -795,39 +849,42 @@ dec_seq2_bwd_kernel(DecSeq p) {
                 *reinterpret_cast<float4*>(sm.Xs + ((tid >> 5) + 8 * i) * B2_XLD + 4 * lane) =
                     make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
             __syncthreads();
-            float acc[2][4] = {};
-            mma_k128_smem(acc, sm.Xs, sm.Wcs);
-            {   // reduce-scatter, forward-style: warp w = n-tile w, owner CTA w/2
-                const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
-                const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = 16 * mt + g;
-                    st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
-                    st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
-                }
-            }
+            float acc[2][4][4] = {};
+            mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, wca_g + 64 * (2 * kh), wrow8);
+            B2_FINE(s);
+            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            B2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
-            if (tid < 128 && a_row < B) {
-                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + a_row) * 16 + 4 * a_c4);
-                    v4.x += r.x; v4.y += r.y; v4.z += r.z; v4.w += r.w;
-                }
+            if (a_ok) {
+                const float4 v4 = recv_sum16(RECV_SA(xbuf), a_row, a_c4, make_float4(0.f, 0.f, 0.f, 0.f));
                 const int n0 = 64 * cl + 16 * rank + 4 * a_c4;
-                *reinterpret_cast<float4*>(p.dcvh + (size_t)a_row * 2 * H + n0) = v4;
-                if (n0 < H) *reinterpret_cast<float4*>(p.dcv_all + ((size_t)s * B + a_row) * H + n0) = v4;
+                if (n0 < H) st_pub4(p.dcv_all + ((size_t)s * B + a_row) * H + n0, v4);
+                else st_pub4(p.dhh_all + ((size_t)s * B + a_row) * H + (n0 - H), v4);
             }
+            xbuf ^= 1;
+            B2_FINE(s);
+            __syncthreads();
         }
-        B2_SYNC();
+        B2_PHASE_END();
         // ---- B: attention backward, one pass over this CTA's quarter of T' ---------------------------------------------
         if (cl < B) {
             const int b = cl;
-            if (tid < H / 4) *reinterpret_cast<float4*>(sm.dcvs + 4 * tid) = __ldcg(reinterpret_cast<const float4*>(p.dcvh + (size_t)b * 2 * H + 4 * tid));
-            __syncthreads();
             const int t_lo = rank * Tq, t_hi = min(Tp, t_lo + Tq);
+            float* av = sm.Xs;                   // a_t of the local range (Xs is idle during this phase)
+            const float* enb = p.enc + (size_t)b * Tp * H + 4 * lane;
+            const float* alb = p.alpha + ((size_t)s * B + b) * Tp;
+            float4 x[4]; float al = 0.f;
+            int t = t_lo + w;
+            if (t < t_hi) {      // first row requested before the poll
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i));
+                al = __ldcg(alb + t);
+            }
+            B2_FINE(s);
+            if (tid < H / 4) *reinterpret_cast<float4*>(sm.dcvs + 4 * tid) = poll4(p.dcv_all + ((size_t)s * B + b) * H + 4 * tid);
+            B2_FINE(s);
+            __syncthreads();
             float4 dq4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) dq4[i] = *reinterpret_cast<const float4*>(sm.dcvs + 128 * i + 4 * lane);
@@ -835,16 +892,6 @@ dec_seq2_bwd_kernel(DecSeq p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             float asum = 0.f;
-            float* av = sm.recv;                 // a_t of the local range (recv is idle during this phase)
-            const float* enb = p.enc + (size_t)b * Tp * H + 4 * lane;
-            const float* alb = p.alpha + ((size_t)s * B + b) * Tp;
-            float4 x[4]; float al = 0.f;
-            int t = t_lo + w;
-            if (t < t_hi) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(enb + (size_t)t * H + 128 * i));
-                al = __ldcg(alb + t);
-            }
             while (t < t_hi) {
                 const int tn = t + 8;
                 float4 xn[4]; float aln = 0.f;
@@ -870,6 +917,7 @@ dec_seq2_bwd_kernel(DecSeq p) {
                 }
                 t = tn;
             }
+            B2_FINE(s);
             if (lane == 0) sm.wstat[w] = asum;
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sm.cvw + w * H + 128 * i + 4 * lane) = u[i];
@@ -886,92 +934,104 @@ dec_seq2_bwd_kernel(DecSeq p) {
                 st_async_v2(mapa(saddr(sm.cvx) + (uint32_t)((rank * 128 + (2 * tid & 127)) * 4), dst), v, mapa(saddr(&sm.mbar_a), dst));
                 if (tid < 4) st_async_v2(mapa(saddr(sm.statx) + (uint32_t)(rank * 8), tid), make_float2(sr, 0.f), mapa(saddr(&sm.mbar_a), tid));
             }
+            float cvj = 0.f;
+            if (tid < 128) cvj = __ldcg(p.cvh + ((size_t)s * B + b) * 2 * H + 128 * rank + tid);
             mbar_wait(&sm.mbar_a, par_a); par_a ^= 1;
+            B2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);
             const float dot = sm.statx[0] + sm.statx[2] + sm.statx[4] + sm.statx[6];
-            if (tid < 128) {
-                const float cvj = __ldcg(p.cvh + ((size_t)s * B + b) * 2 * H + 128 * rank + tid);
-                p.dq[((size_t)s * B + b) * H + 128 * rank + tid] = sm.cvx[tid] + sm.cvx[128 + tid] + sm.cvx[256 + tid] + sm.cvx[384 + tid] - dot * cvj;
-            }
+            if (tid < 128)
+                st_pub1(p.dq + ((size_t)s * B + b) * H + 128 * rank + tid, sm.cvx[tid] + sm.cvx[128 + tid] + sm.cvx[256 + tid] + sm.cvx[384 + tid] - dot * cvj);
             float* dsb = p.ds_all + ((size_t)s * B + b) * Tp;
             for (int tt = t_lo + tid; tt < t_hi; tt += D2_THREADS) dsb[tt] = av[tt - t_lo] - __ldcg(alb + tt) * dot;
+            B2_FINE(s);
+            __syncthreads();
         }
-        B2_SYNC();
+        B2_PHASE_END();
         // ---- C: dh_top = dcvh[:, H:] + dq . Wa, fused cell backward of layer 2 ------------------------------------------
         if (cl < H / 64) {
-            {
-                float4 v[4];
-                seg_load<128>(v, p.dq + (size_t)s * B * H + 128 * rank, H, B);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4*>(sm.Xs + ((tid >> 5) + 8 * i) * B2_XLD + 4 * lane) =
-                        make_float4(rtf32(v[i].x), rtf32(v[i].y), rtf32(v[i].z), rtf32(v[i].w));
-            }
-            __syncthreads();
-            float acc[2][4] = {};
-            mma_k128_smem(acc, sm.Xs, sm.Was);
-            {
-                const int dst = w >> 1, col = 8 * (w & 1) + 2 * q;
-                const uint32_t base = mapa(saddr(sm.recv), dst), bar = mapa(saddr(&sm.mbar_x), dst);
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = 16 * mt + g;
-                    st_async_v2(base + (uint32_t)(((rank * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
-                    st_async_v2(base + (uint32_t)(((rank * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
-                }
-            }
-            // operands of the cell backward are fetched while the exchange is in flight
             const int n0 = 64 * cl + 16 * rank + 4 * a_c4;
-            const bool act_ok = tid < 128 && a_row < B;
-            float4 addv = make_float4(0.f, 0.f, 0.f, 0.f), rec = addv, ccv = addv, cpv = addv, dcv4 = addv, ga[4];
-            if (act_ok) {
-                const size_t e0 = (size_t)a_row * H + n0;
-                addv = __ldcg(reinterpret_cast<const float4*>(p.dcvh + (size_t)a_row * 2 * H + H + n0));
-                if (!last) rec = __ldcg(reinterpret_cast<const float4*>(p.dxh[2] + (size_t)a_row * 2 * H + H + n0));
+            const size_t e0 = (size_t)a_row * H + n0;
+            // forward-pass operands of the cell backward: requested before the poll
+            float4 ccv = make_float4(0.f, 0.f, 0.f, 0.f), cpv = ccv, ga[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ga[i] = ccv;
+            if (a_ok) {
                 ccv = __ldcg(reinterpret_cast<const float4*>(p.Cd[2] + (size_t)(s + 1) * B * H + e0));
                 cpv = __ldcg(reinterpret_cast<const float4*>(p.Cd[2] + (size_t)s * B * H + e0));
-                dcv4 = __ldcg(reinterpret_cast<const float4*>(p.dcd[2] + e0));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) ga[i] = __ldcg(reinterpret_cast<const float4*>(p.act[2] + ((size_t)s * B + a_row) * 4 * H + 4 * (n0 + i)));
             }
+            B2_FINE(s);
+            {
+                float4 v[4];
+                seg_poll<128>(v, p.dq + (size_t)s * B * H + 128 * rank, H, B);
+                B2_FINE(s);
+                seg_store<128, B2_XLD>(sm.Xs, v);
+            }
+            __syncthreads();
+            float acc[2][4][4] = {};
+            mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, waa_g + 64 * (2 * kh), wrow8);
+            B2_FINE(s);
+            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
+            // the other addends (published two and several phases ago) while the exchange is in flight
+            float4 addv = make_float4(0.f, 0.f, 0.f, 0.f), rec = addv;
+            if (a_ok) {
+                addv = poll4(p.dhh_all + ((size_t)s * B + a_row) * H + n0);
+                if (!last) rec = poll4(p.dxr[2] + ((size_t)(s + 1) * B + a_row) * H + n0);
+            }
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            B2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
-            if (act_ok) {
-                float4 v4 = addv;
-#pragma unroll
-                for (int src = 0; src < 4; ++src) {
-                    const float4 r = *reinterpret_cast<const float4*>(sm.recv + (src * 32 + a_row) * 16 + 4 * a_c4);
-                    v4.x += r.x; v4.y += r.y; v4.z += r.z; v4.w += r.w;
-                }
+            if (a_ok) {
+                const float4 v4 = recv_sum16(RECV_SA(xbuf), a_row, a_c4, addv);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, rr[4] = {rec.x, rec.y, rec.z, rec.w};
                 const float cc[4] = {ccv.x, ccv.y, ccv.z, ccv.w}, cp[4] = {cpv.x, cpv.y, cpv.z, cpv.w};
-                float dc[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
-                const size_t e0 = (size_t)a_row * H + n0;
+                float dc[4] = {dcC.x, dcC.y, dcC.z, dcC.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float dm = dropout_scale(p.seed, 16 + 2, (uint32_t)((size_t)s * B * H + e0 + i), p.drop_rnn);
                     const float dh = vv[i] * dm + rr[i];
                     const float4 dg = cell_bwd(dh, ga[i], cc[i], cp[i], dc[i]);
-                    *reinterpret_cast<float4*>(p.act[2] + ((size_t)s * B + a_row) * 4 * H + 4 * (n0 + i)) = dg;
+                    st_pub4(p.dgd[2] + ((size_t)s * B + a_row) * 4 * H + 4 * (n0 + i), dg);
                 }
-                *reinterpret_cast<float4*>(p.dcd[2] + e0) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+                dcC = make_float4(dc[0], dc[1], dc[2], dc[3]);
+                if (s == 0) *reinterpret_cast<float4*>(p.dcd[2] + e0) = dcC;
             }
+            xbuf ^= 1;
+            B2_FINE(s);
+            __syncthreads();
         }
-        B2_SYNC();
+        B2_PHASE_END();
         // ---- D_l: [dx | dh_rec] = dG_l . [W_up | W_lat], fused cell backward of layer l-1 -------------------------------
 #pragma unroll 1
         for (int l = 2; l >= 0; --l) {
             const int in = l == 0 ? E + A : H;
+            const int n = 32 * cl + 8 * rank + d_c;            // output column of [dx(512) | dh_rec(512)]
+            const bool fuse = d_ok && l > 0 && n < H;          // cell backward of layer l-1, unit n
+            const int lb = l > 0 ? l - 1 : 0;
+            const size_t e = (size_t)d_row * H + n;
+            B2_FINE(s);
+            uint32_t bfr[16];
+            tmem_ld16_nowait(tmem_lane + 64 * l, bfr);
+            // forward-pass operands of the fused cell backward: requested before the poll
+            float4 gav = make_float4(0.f, 0.f, 0.f, 0.f); float ccv = 0.f, cpv = 0.f;
+            if (fuse) {
+                gav = __ldcg(reinterpret_cast<const float4*>(p.act[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n));
+                ccv = __ldcg(p.Cd[lb] + (size_t)(s + 1) * B * H + e); cpv = __ldcg(p.Cd[lb] + (size_t)s * B * H + e);
+            }
             {
-                const float* src = p.act[l] + (size_t)s * B * 4 * H + 512 * rank;
+                const float* src = p.dgd[l] + (size_t)s * B * 4 * H + 512 * rank;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float4 v[8];
+                    const float* a[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int idx = tid + (half * 8 + i) * D2_THREADS, row = idx >> 7, k = (idx & 127) * 4;
-                        v[i] = row < B ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)row * 4 * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a[i] = row < B ? src + (size_t)row * 4 * H + k : nullptr;
                     }
+                    poll_many<8>(v, a);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int idx = tid + (half * 8 + i) * D2_THREADS, row = idx >> 7, k = (idx & 127) * 4;
@@ -979,48 +1039,55 @@ dec_seq2_bwd_kernel(DecSeq p) {
                     }
                 }
             }
+            B2_FINE(s);
             __syncthreads();
-            float acc[2][4] = {};
-            mma_k256_tmem(acc, sm.Xs + 256 * kh, tmem_lane + 64 * l);
-            {   // warp (nt, kh) -> owner CTA nt, source slot 2 rank + kh, 8 columns per owner
-                const uint32_t base = mapa(saddr(sm.recv), nt), bar = mapa(saddr(&sm.mbar_x), nt);
-                const int src = 2 * rank + kh;
+            float acc[2][4][4] = {};
+            mma_run_tmem<4>(acc, xa_g + 64 * (4 * w), xrow8, tmem_lane + 64 * l, bfr);
+            B2_FINE(s);
+            {   // 32 partial products (4 CTAs x 8 k-slices); n-tile nt belongs to CTA nt.  Receiver layout [src = 8 rank + w][row][8 cols]
+                const int src = 8 * rank + w;
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = 16 * mt + g;
-                    st_async_v2(base + (uint32_t)(((src * 32 + r0) * 8 + 2 * q) * 4), make_float2(acc[mt][0], acc[mt][1]), bar);
-                    st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 8 + 2 * q) * 4), make_float2(acc[mt][2], acc[mt][3]), bar);
+                for (int nt = 0; nt < 4; ++nt) {
+                    const uint32_t base = mapa(RECV_SA(xbuf), nt), bar = mapa(mbx_sa, nt);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int r0 = 16 * mt + g;
+                        st_async_v2(base + (uint32_t)(((src * 32 + r0) * 8 + 2 * q) * 4), make_float2(acc[mt][nt][0], acc[mt][nt][1]), bar);
+                        st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 8 + 2 * q) * 4), make_float2(acc[mt][nt][2], acc[mt][nt][3]), bar);
+                    }
                 }
             }
-            const int n = 32 * cl + 8 * rank + d_c;            // output column of [dx(512) | dh_rec(512)]
-            const bool row_ok = d_row < B;
-            const bool fuse = row_ok && l > 0 && n < H;        // cell backward of layer l-1, unit n
-            float4 gav = make_float4(0.f, 0.f, 0.f, 0.f); float ccv = 0.f, cpv = 0.f, dcv = 0.f, rec = 0.f;
-            const int lb = l - 1, inb = lb == 0 ? E + A : H;
-            const size_t e = (size_t)d_row * H + n;
+            float rec = 0.f, dm = 1.f;
             if (fuse) {
-                gav = __ldcg(reinterpret_cast<const float4*>(p.act[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n));
-                ccv = __ldcg(p.Cd[lb] + (size_t)(s + 1) * B * H + e); cpv = __ldcg(p.Cd[lb] + (size_t)s * B * H + e);
-                dcv = __ldcg(p.dcd[lb] + e);
-                if (!last) rec = __ldcg(p.dxh[lb] + (size_t)d_row * (inb + H) + inb + n);
+                dm = dropout_scale(p.seed, 16 + lb, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
+                if (!last) rec = poll1(p.dxr[lb] + ((size_t)(s + 1) * B + d_row) * H + n);
             }
             mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            B2_FINE(s);
             if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
-            if (row_ok) {
+            if (d_ok) {
                 float v = 0.f;
+                const float* rv = sm.recv[xbuf];
 #pragma unroll
-                for (int src = 0; src < 8; ++src) v += sm.recv[(src * 32 + d_row) * 8 + d_c];
-                if (n >= H) p.dxh[l][(size_t)d_row * (in + H) + in + (n - H)] = v;           // dh_rec of layer l for step s-1
-                else if (l == 0) p.dxh[0][(size_t)d_row * (in + H) + E + n] = v;                // dht_feed for step s-1
-                else {
-                    const float dm = dropout_scale(p.seed, 16 + lb, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
+                for (int src = 0; src < 32; ++src) v += rv[(src * 32 + d_row) * 8 + d_c];
+                if (n >= H) {                                  // dh_rec of layer l for step s-1
+                    st_pub1(p.dxr[l] + ((size_t)s * B + d_row) * H + (n - H), v);
+                    if (s == 0) p.dxh[l][(size_t)d_row * (in + H) + in + (n - H)] = v;     // gradient of the decoder's initial state
+                } else if (l == 0) {                           // dht_feed for step s-1
+                    st_pub1(p.dfeed + ((size_t)s * B + d_row) * A + n, v);
+                } else {
                     const float dh = v * dm + rec;
-                    const float4 dg = cell_bwd(dh, gav, ccv, cpv, dcv);
-                    *reinterpret_cast<float4*>(p.act[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n) = dg;
-                    p.dcd[lb][e] = dcv;
+                    float dcl = lb == 0 ? dcD0 : dcD1;
+                    const float4 dg = cell_bwd(dh, gav, ccv, cpv, dcl);
+                    if (lb == 0) dcD0 = dcl; else dcD1 = dcl;
+                    st_pub4(p.dgd[lb] + ((size_t)s * B + d_row) * 4 * H + 4 * n, dg);
+                    if (s == 0) p.dcd[lb][e] = dcl;
                 }
             }
-            B2_SYNC();
+            xbuf ^= 1;
+            B2_FINE(s);
+            __syncthreads();
+            B2_PHASE_END();
         }
     }
     tc_fence_before();
@@ -1028,6 +1095,9 @@ dec_seq2_bwd_kernel(DecSeq p) {
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_slot), "n"(512));
     cluster_sync_all();
 #undef B2_SYNC
+#undef B2_PHASE_END
+#undef B2_FINE
+#undef RECV_SA
 }
 
 // d_enc[b][t][:] = sum_s alpha[s][b][t] * dcv[s][b][:] + ds[s][b][t] * q[s][b][:]   (one pass after the loop; replaces the
@@ -1105,11 +1175,11 @@ int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p) {
 
 bool dec_seq2_supported(const DecSeq& p) {
     return p.H == D2_H && p.E == D2_E && p.A == D2_A && p.NL == 3 && p.B >= 1 && p.B <= 32 && p.S >= 1 && p.Tp >= 1 &&
-           (p.Tp + D2_CS - 1) / D2_CS <= 4 * 32 * 16 && p.encW != nullptr && p.encb != nullptr && p.bar != nullptr;
+           (p.Tp + D2_CS - 1) / D2_CS <= 2048 && p.encW != nullptr && p.encb != nullptr && p.bar != nullptr;
 }
 
 // 32 clusters x 4 CTAs, one CTA per SM.  The cooperative attribute makes the runtime verify co-residency (the kernels
-// spin on a grid barrier).  Profilers that serialise kernels reject cooperative + cluster launches
+// poll each other's output).  Profilers that serialise kernels reject cooperative + cluster launches
 // (cudaErrorInvalidConfiguration under ncu); co-residency still holds there (128 CTAs, 148 SMs, nothing else running), so the
 // launch is retried with the cluster attribute only.
 template <class KernT>
@@ -1149,7 +1219,8 @@ int dec_seq2_fwd(cudaStream_t st, const DecSeq& p) {
 }
 
 int dec_seq2_bwd(cudaStream_t st, const DecSeq& p) {
-    AST_CHECK(dec_seq2_supported(p) && p.dzw && p.dcv_all && p.ds_all, "dec_seq2_bwd: unsupported geometry");
+    AST_CHECK(dec_seq2_supported(p) && p.dzw && p.dcv_all && p.ds_all && p.dhh_all && p.dfeed && p.dgd[0] && p.dxr[0],
+              "dec_seq2_bwd: unsupported geometry");
     return launch_d2(dec_seq2_bwd_kernel, st, p, sizeof(B2Smem) + 128);
 }
 

@@ -151,7 +151,8 @@ struct DecSeq {
     // dec_seq2 backward hand-off slots, one per step, sentinel-filled before the launch: dG of every layer (the forward gates in
     // act[] stay intact), dh_rec of layer l produced at step s (consumed at s-1), d(ht) fed back into layer 0, h-half of du.Wc
     float* dgd[AST_MAXL]; float* dxr[AST_MAXL]; float* dfeed; float* dhh_all;
-    unsigned long long* prof;          // optional phase-timing probe: CTA 0 stores %globaltimer after each grid barrier
+    unsigned long long* prof;          // optional phase-timing probe: CTA 0 stores %globaltimer at the end of each phase
+    int prof_fine;                     // 1 + index of the CTA whose thread 0 stamps clock64 inside the phases of step 6 (0: off)
 };
 int dec_seq_fwd(cudaStream_t st, const DecSeq& p, bool exact);
 int dec_seq_bwd(cudaStream_t st, const DecSeq& p, bool exact);

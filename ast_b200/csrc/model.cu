@@ -96,6 +96,8 @@ struct ast_model {
     float *enc_states, *d_enc, *d_rnn_in, *d_rnn_rev;
     float *encW, *encb;        // dec_seq2: enc_states . W_a and enc_states . b_a
     float *dzw, *dcv_all, *ds_all, *dE;   // dec_seq2 backward
+    float *dgd[MAXL], *dxr[MAXL], *dfeed, *dhh_all;   // dec_seq2 backward: per-step hand-off slots (dec_seq2.cu)
+    cudaEvent_t ev_fill[2] = {};
     // beam_fused: the search as one persistent launch (beam_seq.cu).  Measured no faster than the kernel-per-phase loop (159 vs
     // 146 us per step at N = 10): a step is bound by streaming the 31.6 MB of decoder weights from L2 in 3xTF32 arithmetic,
     // not by launches, which the stream already pipelines.  Kept as an option (tests run both).
@@ -288,6 +290,8 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->dalpha = a.get<float>((size_t)B * Tp);
     m->dq = a.get<float>(SB * H);
     m->dzw = a.get<float>(SB * A); m->dcv_all = a.get<float>(SB * H); m->ds_all = a.get<float>(SB * Tp); m->dE = a.get<float>(SB * E);
+    for (int l = 0; l < NL; ++l) { m->dgd[l] = a.get<float>(SB * 4 * H); m->dxr[l] = a.get<float>(SB * H); }
+    m->dfeed = a.get<float>(SB * A); m->dhh_all = a.get<float>(SB * H);
     m->dhtop = a.get<float>((size_t)B * H);
     m->words_used = a.get<int>(SB);
     m->argmax_steps = a.get<int>(SB);
@@ -805,7 +809,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
         const std::string ln = lname(l, "dec");
         p.Wup[l] = m->p((ln + "/upward/W").c_str()); p.bup[l] = m->p((ln + "/upward/b").c_str()); p.Wlat[l] = m->p((ln + "/lateral/W").c_str());
         p.WcatT[l] = m->WcatT[l]; p.act[l] = m->actd[l]; p.Hd[l] = m->Hdec[l]; p.Cd[l] = m->Cdec[l]; p.hdd[l] = m->hdd[l];
-        p.dxh[l] = m->dxh[l]; p.dcd[l] = m->dcd[l];
+        p.dxh[l] = m->dxh[l]; p.dcd[l] = m->dcd[l]; p.dgd[l] = m->dgd[l]; p.dxr[l] = m->dxr[l];
     }
     p.Wa = m->p("attn_Wa/W"); p.ba = m->p("attn_Wa/b"); p.Wc = m->p("context/W"); p.bc = m->p("context/b");
     p.Wo = m->p("out/W"); p.bo = m->p("out/b"); p.WoT = m->WoT; p.WcT = m->WcT; p.WaT = m->WaT;
@@ -816,6 +820,7 @@ static DecSeq make_dec_seq(ast_model* m, const int* y, const unsigned char* use_
     p.drop_embed = train ? m->cfg.drop_embed : 0.f; p.drop_rnn = train ? m->cfg.drop_rnn : 0.f; p.seed = m->cur_seed;
     p.prof = nullptr; p.bar = m->dec_fast_barrier ? m->dec_bar : nullptr; p.sync_all = m->dec_sync;
     p.encW = m->encW; p.encb = m->encb; p.dzw = m->dzw; p.dcv_all = m->dcv_all; p.ds_all = m->ds_all;
+    p.dfeed = m->dfeed; p.dhh_all = m->dhh_all;
     return p;
 }
 
@@ -840,7 +845,7 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
     bool use_v2 = false;
     if (m->dec_fused) {
         ds = make_dec_seq(m, y, use_true, true);
-        if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof;
+        if (m->dec_prof_on && (size_t)S * 12 + 16 < 3000) { ds.prof = m->dec_prof; ds.prof_fine = m->dec_prof_on >= 2 ? m->dec_prof_on - 1 : 0; }
         use_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
     }
     if (use_v2) {
@@ -945,11 +950,21 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // ---- decoder BPTT: data gradients step by step -----------------------------------------------
     if (m->dec_fused) {
         DecSeq ds = make_dec_seq(m, m->y_dev, m->use_true_dev, true);
-        if (m->dec_prof_on && (size_t)S * 12 + 16 < 4096) ds.prof = m->dec_prof + 4096;
+        if (m->dec_prof_on && (size_t)S * 12 + 16 < 3000) { ds.prof = m->dec_prof + 4096; ds.prof_fine = m->dec_prof_on >= 2 ? m->dec_prof_on - 1 : 0; }
         dec_bwd_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
         if (dec_bwd_v2) {
+            // hand-off slots of this launch <- sentinel, beside the dz . Wo GEMM
+            if (m->overlap) {
+                AST_CUDA_OK(cudaEventRecord(m->ev_fill[0], st));
+                AST_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fill[0], 0));
+                AST_TRY(dec_seq2_prepare_bwd(m->side, ds));
+                AST_CUDA_OK(cudaEventRecord(m->ev_fill[1], m->side));
+            } else {
+                AST_TRY(dec_seq2_prepare_bwd(st, ds));
+            }
             // dz . Wo for every step at once (the only place the vocabulary enters the decoder BPTT)
             AST_TRY(gemm(m, st, false, false, SB, A, V, m->logits, Vp, m->p("out/W"), A, m->dzw, A, nullptr, 0.f, 0, SITE_DEC_PRE));
+            if (m->overlap) AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_fill[1], 0));
             AST_TRY(dec_seq2_bwd(st, ds));
             AST_TRY(attn_denc(st, m->alpha, m->ds_all, m->dcv_all, m->q, m->d_enc, S, B, Tp, H));
         } else {
@@ -1014,8 +1029,11 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     struct CapGuard { ~CapGuard() { gemm_tc_set_cta_cap(0); } } cap_guard;      // an early error return must not leave the cap behind
     if (will_persist && sw != st) gemm_tc_set_cta_cap(m->enc_side_ctas);
     AST_TRY(fork());
+    // dG of the decoder layers: dec_seq2 keeps the forward gates intact and writes dG to its own per-step slots
+    float* dGd[MAXL];
+    for (int l = 0; l < NL; ++l) dGd[l] = dec_bwd_v2 ? m->dgd[l] : m->actd[l];
     if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
-        AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, m->actd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
+        AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, dGd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
         AST_TRY(embed_scatter(sw, m->g("embed_dec/W"), m->dE, E, m->words_used, SB, E, 0, de, m->cur_seed, 32));
     }
     AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
@@ -1028,9 +1046,9 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         const std::string ln = lname(l, "dec");
         const int in = m->in_dec(l);
         const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
-        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, m->actd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, m->actd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(colsum(sw, m->actd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, dGd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, dGd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, dGd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
     }
     gemm_tc_set_cta_cap(0);
     // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
@@ -1335,6 +1353,7 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_tr, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fill[i], cudaEventDisableTiming);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_bucket[i], cudaEventDisableTiming);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->lay[i], cudaStreamNonBlocking, prio_hi);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layg[i], cudaStreamNonBlocking, prio_hi);
@@ -1355,6 +1374,7 @@ int ast_destroy(ast_model* m) {
     for (int i = 0; i < 8; ++i) if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->ev_tr) cudaEventDestroy(m->ev_tr);
+    for (int i = 0; i < 2; ++i) if (m->ev_fill[i]) cudaEventDestroy(m->ev_fill[i]);
     for (int i = 0; i < 3; ++i) if (m->ev_bucket[i]) cudaEventDestroy(m->ev_bucket[i]);
     if (m->side) cudaStreamDestroy(m->side);
     for (int i = 0; i < MAXL; ++i) if (m->lay[i]) cudaStreamDestroy(m->lay[i]);
@@ -1407,7 +1427,7 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
     else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
     else if (!strcmp(key, "dec_fused")) m->dec_fused = value != 0;
-    else if (!strcmp(key, "dec_prof")) m->dec_prof_on = value != 0;
+    else if (!strcmp(key, "dec_prof")) m->dec_prof_on = (int)value;      // 1: phase stamps of CTA 0; 2 + c: also clock64 stamps inside the phases by CTA c
     else if (!strcmp(key, "overlap")) m->overlap = value != 0;
     else if (!strcmp(key, "dec_v2")) m->dec_v2 = value != 0;
     else if (!strcmp(key, "beam_fused")) m->beam_fused = value != 0;
