@@ -294,14 +294,17 @@ __device__ __forceinline__ float4 recv_sum16(uint32_t recv_sa, int row, int c4, 
 }  // namespace
 
 // x0[i][0:E] = Emb[y[b][s]] * dropmask, words_used[i] = token, for row i = s*B + b; x0[i][E:] = 0 (s == 0) or the hand-off
-// sentinel (s > 0: the input-feeding slot the decoder kernel fills at step s - 1 and polls at step s)
+// sentinel (s > 0: the input-feeding slot the decoder kernel fills at step s - 1 and polls at step s).  A step whose input is
+// the previous step's argmax (scheduled sampling) gets the sentinel in the embedding columns as well.
 __device__ __forceinline__ void embed_tf_row(const DecSeq& p, int i, int tid, int nthreads) {
     const int s = i / p.B, b = i - s * p.B, ldx0 = p.E + p.A;
     const int word = min(max(p.y[(size_t)b * p.L + s], 0), p.V - 1);
     float* dst = p.x0 + (size_t)i * ldx0;
+    const bool sampled = s > 0 && p.use_true != nullptr && !p.use_true[s];      // the kernel embeds step s-1's argmax in-loop
     if (tid == 0) p.words_used[i] = word;
     for (int j = tid; j < p.E; j += nthreads)
-        dst[j] = __ldg(p.emb + (size_t)word * p.E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * p.E + j), p.drop_embed);
+        dst[j] = sampled ? __uint_as_float(0xFFFFFFFFu)
+                         : __ldg(p.emb + (size_t)word * p.E + j) * dropout_scale(p.seed, 32, (uint32_t)((size_t)i * p.E + j), p.drop_embed);
     const float fill = s == 0 ? 0.f : __uint_as_float(0xFFFFFFFFu);
     for (int j = tid; j < p.A; j += nthreads) dst[p.E + j] = fill;
 }
@@ -442,7 +445,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 seg_poll<128>(v2, p.Hd[l] + (size_t)s * B * H + 128 * rank, H, B);
                 if (l == 0) {
                     float4 v0[1];
-                    seg_load<32>(v0, x0 + 32 * rank, ldx0, B);
+                    seg_poll<32>(v0, x0 + 32 * rank, ldx0, B);
                     seg_store<32, D2_XLD>(sm.Xs + 128, v0); seg_store<128, D2_XLD>(sm.Xs + 160, v2);
                 } else {
                     seg_store<128, D2_XLD>(sm.Xs + 128, v2);
@@ -640,26 +643,46 @@ dec_seq2_fwd_kernel(DecSeq p) {
         }
         D2_PHASE_END();
         // ---- scheduled sampling: the next input is this step's argmax (seq2seq.py:431-436, 448) ----------------------
-        // The only place grid barriers remain: logits need every column of ht, the argmax every logit, and the embedding
-        // row of step s+1 (already holding the teacher-forced token's) is overwritten before anyone may stage it.
+        // Hand-off by polling like everything else: the logits tiles wait for ht (its copy in the input-feeding slot of step
+        // s+1), the argmax CTAs for the logits row (sentinel-filled before the launch), layer 0 of step s+1 for the
+        // embedding columns.  CTAs from the end of the grid (clusters that have no context phase) do this work.
         if (s + 1 < S && p.use_true != nullptr && !p.use_true[s + 1]) {
-            D2_SYNC();
             float* z = p.logits + (size_t)s * B * Vp;
-            SkinnyArgs a{};
-            a.X[0] = p.ht + (size_t)s * B * A; a.ldx[0] = A; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
-            a.B = B; a.N = p.V; a.epi = EPI_NONE; a.Y = z; a.ldy = Vp;
-            for (int gidx = cta; gidx < (p.V + SK_COLS - 1) / SK_COLS; gidx += ncta) skinny_tile<2, false>(a, gidx * SK_COLS, ssm);
-            D2_SYNC();
-            for (int b = cta; b < B; b += ncta) {
-                const int mi = softmax_ce_row(z + (size_t)b * Vp, Vp, p.V, 0, B, nullptr, 0, scratch, iscratch);
+            const float* feed = p.x0 + (size_t)(s + 1) * B * ldx0 + E;
+            const int ntiles = (p.V + SK_COLS - 1) / SK_COLS;
+            const int tile = cta - 32;                            // CTAs 32 .. 32 + ntiles - 1
+            if (tile >= 0 && tile < ntiles) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {            // wait until every word of ht is visible in L2
+                    float4 v[8]; const float* a8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = tid + (half * 8 + i) * D2_THREADS, row = idx >> 7, k = (idx & 127) * 4;
+                        a8[i] = row < B ? feed + (size_t)row * ldx0 + k : nullptr;
+                    }
+                    poll_many<8>(v, a8);
+                }
+                __syncthreads();
+                SkinnyArgs a{};
+                a.X[0] = feed; a.ldx[0] = ldx0; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
+                a.B = B; a.N = p.V; a.epi = EPI_NONE; a.Y = z; a.ldy = Vp;
+                skinny_tile<2, false>(a, tile * SK_COLS, ssm);
+            }
+            const int b = ncta - 1 - cta;                         // CTAs 127, 126, ... take rows 0, 1, ...
+            if (b < B) {
+                float* zr = z + (size_t)b * Vp;
+                PollClock pc;
+                for (int n = tid; n < p.V; n += D2_THREADS)
+                    while (unwritten(ld_pub1(zr + n))) pc.tick();
+                __syncthreads();
+                const int mi = softmax_ce_row(zr, Vp, p.V, 0, B, nullptr, 0, scratch, iscratch);
                 const int word = min(max(mi, 0), p.V - 1);
                 float* dst = p.x0 + ((size_t)(s + 1) * B + b) * ldx0;
                 if (tid == 0) p.words_used[(size_t)(s + 1) * B + b] = word;
                 for (int j = tid; j < E; j += D2_THREADS)
-                    dst[j] = __ldg(p.emb + (size_t)word * E + j) * dropout_scale(p.seed, 32, (uint32_t)(((size_t)(s + 1) * B + b) * E + j), p.drop_embed);
+                    st_pub1(dst + j, __ldg(p.emb + (size_t)word * E + j) * dropout_scale(p.seed, 32, (uint32_t)(((size_t)(s + 1) * B + b) * E + j), p.drop_embed));
                 __syncthreads();
             }
-            D2_SYNC();
         }
     }
     tc_fence_before();
@@ -1161,6 +1184,7 @@ int dec_seq2_prepare_fwd(cudaStream_t st, const DecSeq& p) {
     auto add = [&](float* ptr, size_t words) { r.ptr[r.n] = reinterpret_cast<uint4*>(ptr); r.n4[r.n] = words / 4; ++r.n; };
     for (int l = 0; l < 3; ++l) add(p.Hd[l] + (size_t)p.B * p.H, SBH);
     add(p.hdd[0], SBH); add(p.hdd[1], SBH); add(p.cvh, 2 * SBH);
+    if (p.use_true != nullptr) add(p.logits, (size_t)p.S * p.B * p.Vp);      // in-loop logits of sampled steps (the batched GEMM after the loop rewrites them all)
     return fill_ranges(st, r);
 }
 
