@@ -225,77 +225,116 @@ struct DyFromPadded {       // layer 0: dy = da0p[seg][pad + t1][c]
         const int t1 = r % T1; const int seg = r / T1;
         return d[((size_t)seg * S0 + pad + t1) * C + c];
     }
+    __device__ __forceinline__ float4 vec4(int r, int c) const {        // c % 4 == 0
+        const int t1 = r % T1; const int seg = r / T1;
+        return *reinterpret_cast<const float4*>(d + ((size_t)seg * S0 + pad + t1) * C + c);
+    }
 };
 
+__global__ void bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats);
+
+// Both passes walk rows of C contiguous floats with float4 channel vectors: lane x of a (32, 8) block owns channels
+// 4 (32 bx + x) .. + 3, row lane y strides the block's rows, so a warp reads 512 contiguous bytes per row.  The first pass
+// accumulates in fp32 per thread (a few dozen terms), reduces the 8 row lanes in double and writes per-block partial sums
+// (bn_partials_sum adds them up; double atomics onto 2C addresses serialised in L2: 47 us for 32 MB at C = 128).
 template <class DY>
-__global__ void bn_bwd_reduce_kernel(DY dyf, const float* __restrict__ raw, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(DY dyf, const float* __restrict__ raw, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, double* __restrict__ stats, int rows, int C,
+                                     const float* __restrict__ beta, double* __restrict__ partials, int rows, int C,
                                      int seg_rows, int seg_valid, int rows_per_block) {
-    __shared__ double sb[8][33], sg[8][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    __shared__ double sb[8][32][4], sg[8][32][4];
+    const int c = 4 * (blockIdx.x * 32 + threadIdx.x);
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(rows, r0 + rows_per_block);
-    double db = 0.0, dg = 0.0;
+    float db[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
-        const float mu = mean[c], is = invstd[c], g = gamma[c], bt = beta[c];
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+#pragma unroll 4
         for (int r = r0 + threadIdx.y; r < r1; r += 8) {
             if ((r % seg_rows) < seg_valid) {
-                const float xh = (raw[(size_t)r * C + c] - mu) * is;
-                if (g * xh + bt > 0.f) {
-                    const float dy = dyf(r, c);
-                    db += dy; dg += (double)dy * xh;
-                }
+                const float4 x = *reinterpret_cast<const float4*>(raw + (size_t)r * C + c);
+                const float4 dy = dyf.vec4(r, c);
+                const float xh[4] = {(x.x - mu.x) * is.x, (x.y - mu.y) * is.y, (x.z - mu.z) * is.z, (x.w - mu.w) * is.w};
+                const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w}, dd[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (gg[k] * xh[k] + bb[k] > 0.f) { db[k] += dd[k]; dg[k] += dd[k] * xh[k]; }
             }
         }
     }
-    sb[threadIdx.y][threadIdx.x] = db;
-    sg[threadIdx.y][threadIdx.x] = dg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sb[threadIdx.y][threadIdx.x][k] = db[k]; sg[threadIdx.y][threadIdx.x][k] = dg[k]; }
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
+        double* out = partials + (size_t)blockIdx.y * 2 * C;
 #pragma unroll
-        for (int j = 1; j < 8; ++j) { db += sb[j][threadIdx.x]; dg += sg[j][threadIdx.x]; }
-        atomicAdd(&stats[c], db);
-        atomicAdd(&stats[C + c], dg);
+        for (int k = 0; k < 4; ++k) {
+            double b = 0.0, gq = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { b += sb[j][threadIdx.x][k]; gq += sg[j][threadIdx.x][k]; }
+            out[c + k] = b; out[C + c + k] = gq;
+        }
     }
 }
 
 template <class DY>
-__global__ void bn_bwd_apply_kernel(DY dyf, const float* __restrict__ raw, float* __restrict__ dx,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DY dyf, const float* __restrict__ raw, float* __restrict__ dx,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const double* __restrict__ stats, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int rows, int C, int seg_rows, int seg_valid,
                                     double m) {
-    const size_t total = (size_t)rows * C;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const int r = (int)(i / C);
-        float o = 0.f;
-        const float db = (float)stats[c], dg = (float)stats[C + c];
+    const int C4 = C >> 2;
+    const size_t total = (size_t)rows * C4;
+    const float inv_m = (float)(1.0 / m);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = 4 * (int)(i % C4);
+        const int r = (int)(i / C4);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float db[4] = {(float)stats[c], (float)stats[c + 1], (float)stats[c + 2], (float)stats[c + 3]};
+        const float dg[4] = {(float)stats[C + c], (float)stats[C + c + 1], (float)stats[C + c + 2], (float)stats[C + c + 3]};
         if ((r % seg_rows) < seg_valid) {
-            const float is = invstd[c], g = gamma[c];
-            const float xh = (raw[i] - mean[c]) * is;
-            const float dy = (g * xh + beta[c] > 0.f) ? dyf(r, c) : 0.f;
-            o = g * is * (dy - db / (float)m - xh * (dg / (float)m));
+            const float4 x = *reinterpret_cast<const float4*>(raw + (size_t)r * C + c);
+            const float4 dy = dyf.vec4(r, c);
+            const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+            const float4 g = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+            const float xv[4] = {x.x, x.y, x.z, x.w}, dd[4] = {dy.x, dy.y, dy.z, dy.w}, mm[4] = {mu.x, mu.y, mu.z, mu.w};
+            const float ii[4] = {is.x, is.y, is.z, is.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+            float ov[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xh = (xv[k] - mm[k]) * ii[k];
+                const float d = (gg[k] * xh + bb[k] > 0.f) ? dd[k] : 0.f;
+                ov[k] = gg[k] * ii[k] * (d - db[k] * inv_m - xh * (dg[k] * inv_m));
+            }
+            o = make_float4(ov[0], ov[1], ov[2], ov[3]);
         }
-        dx[i] = o;
-        if (r == 0) { dgamma[c] = dg; dbeta[c] = db; }
+        *reinterpret_cast<float4*>(dx + (size_t)r * C + c) = o;
+        if (r == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { dgamma[c + k] = dg[k]; dbeta[c + k] = db[k]; }
+        }
     }
 }
 
 template <class DY>
 static int bn_bwd_impl(cudaStream_t st, DY dyf, const float* raw, float* dx, const float* mean,
                        const float* invstd, const float* gamma, const float* beta, double* stats,
-                       float* dgamma, float* dbeta, int rows, int C, int seg_rows, int seg_valid, double m) {
-    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-    const int rpb = std::max(64, cdiv(rows, 148 * 4 / std::max(1, cdiv(C, 32))));
-    dim3 grid(cdiv(C, 32), cdiv(rows, rpb)), block(32, 8);
-    bn_bwd_reduce_kernel<DY><<<grid, block, 0, st>>>(dyf, raw, mean, invstd, gamma, beta, stats, rows, C,
+                       float* dgamma, float* dbeta, int rows, int C, int seg_rows, int seg_valid, double m,
+                       double* partials, int partial_blocks) {
+    AST_CHECK(C % 4 == 0, "bn_bwd: C %% 4 != 0");
+    const int gx = cdiv(C, 128);
+    int rpb = std::max(64, cdiv(rows, std::max(1, 148 * 4 / gx)));
+    rpb = std::max(rpb, cdiv(rows, partial_blocks));
+    const int gy = cdiv(rows, rpb);
+    dim3 grid(gx, gy), block(32, 8);
+    bn_bwd_reduce_kernel<DY><<<grid, block, 0, st>>>(dyf, raw, mean, invstd, gamma, beta, partials, rows, C,
                                                       seg_rows, seg_valid, rpb);
     AST_LAUNCH_OK();
-    const size_t total = (size_t)rows * C;
+    bn_partials_sum_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partials, gy, 2 * C, stats);
+    AST_LAUNCH_OK();
+    const size_t total = (size_t)rows * (C / 4);
     const int g2 = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     bn_bwd_apply_kernel<DY><<<g2, 256, 0, st>>>(dyf, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta,
                                                  rows, C, seg_rows, seg_valid, m);
@@ -306,56 +345,67 @@ static int bn_bwd_impl(cudaStream_t st, DY dyf, const float* raw, float* dx, con
 // ---- last CNN layer: dy arrives in the RNN feature layout  d_rnn_in[t'][b][c*F'+f] (+ d_rnn_rev[(T'-t')%T'][b][..]) ----
 // Same two passes as bn_bwd_impl, organised per (t', b) feature row so that every global access is contiguous: the row(s)
 // of dy are staged in shared memory (float4 loads), then lane c walks f.
-__global__ void __launch_bounds__(256) bn_bwd_rnn_reduce_kernel(const float* __restrict__ d_in, const float* __restrict__ d_rev,
+// Thread x of a (R/4, 2) block owns four consecutive elements j = c F' + f of the R-float feature row: dy (and the reverse
+// stack's) is one 128-bit load per row, perfectly coalesced; the four raw values are a gather inside three 128-byte lines per
+// warp (channel c = j / F', plane f = j % F').  No shared-memory staging and no barrier inside the row loop (the staged
+// version ran at 1.1 TB/s, 17 % of the HBM roofline: two barriers per row, one row in flight per block).  fp32 accumulation
+// per thread (a few dozen terms); the F' planes and the 2 row lanes of a channel are added in double; per-block partial sums,
+// bn_partials_sum adds them up (deterministic).
+template <int FP>
+__global__ void __launch_bounds__(768) bn_bwd_rnn_reduce_kernel(const float* __restrict__ d_in, const float* __restrict__ d_rev,
                                          const float* __restrict__ raw, const float* __restrict__ mean,
                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, double* __restrict__ stats, int B, int Fp, int Rs,
+                                         const float* __restrict__ beta, int B, int Fp_rt, int Rs,
                                          int Tp, int C, int rows_per_block, double* __restrict__ partials) {
-    extern __shared__ float dyrow[];        // R floats
+    extern __shared__ float sm_bn[];        // params [4][C] | sums [2 (db, dg)][2 (row lane)][R]
+    const int Fp = FP > 0 ? FP : Fp_rt;
     const int R = C * Fp, TB = Tp * B;
+    float* prm = sm_bn; float* sums = sm_bn + 4 * C;
+    const int x = threadIdx.x, y = threadIdx.y, nx = blockDim.x;
+    for (int c = y * nx + x; c < C; c += 2 * nx) { prm[c] = mean[c]; prm[C + c] = invstd[c]; prm[2 * C + c] = gamma[c]; prm[3 * C + c] = beta[c]; }
+    __syncthreads();
     const int r0 = blockIdx.x * rows_per_block, r1 = min(TB, r0 + rows_per_block);
-    constexpr int MAXC = 4;                 // channels per thread (C <= 1024)
-    double db[MAXC], dg[MAXC];
-    float mu[MAXC], is[MAXC], g[MAXC], bt[MAXC];
+    constexpr int MAXK = 2;                 // R <= 4 * blockDim.x * MAXK
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-        const int c = threadIdx.x + k * 256;
-        db[k] = dg[k] = 0.0;
-        if (c < C) { mu[k] = mean[c]; is[k] = invstd[c]; g[k] = gamma[c]; bt[k] = beta[c]; }
+    for (int k = 0; k < MAXK; ++k) {
+        const int j0 = 4 * (x + k * nx);
+        if (j0 >= R) break;
+        int off[4]; float mu[4], is[4], g[4], bt[4], db[4], dg[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j0 + i, c = j / Fp, f = j - c * Fp;
+            off[i] = f * Rs * C + c;
+            mu[i] = prm[c]; is[i] = prm[C + c]; g[i] = prm[2 * C + c]; bt[i] = prm[3 * C + c];
+            db[i] = dg[i] = 0.f;
+        }
+#pragma unroll 2
+        for (int r = r0 + y; r < r1; r += 2) {
+            const int t = r / B, b = r - t * B;
+            float4 dy = *reinterpret_cast<const float4*>(d_in + (size_t)r * R + j0);
+            if (d_rev) {
+                const float4 w = *reinterpret_cast<const float4*>(d_rev + ((size_t)((Tp - t) % Tp) * B + b) * R + j0);
+                dy.x += w.x; dy.y += w.y; dy.z += w.z; dy.w += w.w;
+            }
+            const float* rw = raw + ((size_t)b * Fp * Rs + t) * C;
+            const float dd[4] = {dy.x, dy.y, dy.z, dy.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float xh = (rw[off[i]] - mu[i]) * is[i];
+                if (g[i] * xh + bt[i] > 0.f) { db[i] += dd[i]; dg[i] += dd[i] * xh; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sums[y * R + j0 + i] = db[i]; sums[(2 + y) * R + j0 + i] = dg[i]; }
     }
-    for (int r = r0; r < r1; ++r) {
-        const int t = r / B, b = r - t * B;
-        const float4* s1 = reinterpret_cast<const float4*>(d_in + (size_t)r * R);
-        const float4* s2 = d_rev ? reinterpret_cast<const float4*>(d_rev + ((size_t)((Tp - t) % Tp) * B + b) * R) : nullptr;
-        __syncthreads();
-        for (int i = threadIdx.x; i < R / 4; i += 256) {
-            float4 v = s1[i];
-            if (s2) { const float4 w = s2[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
-            reinterpret_cast<float4*>(dyrow)[i] = v;
+    __syncthreads();
+    double* out = partials + (size_t)blockIdx.x * 2 * C;
+    for (int c = y * nx + x; c < C; c += 2 * nx) {
+        double b2 = 0.0, g2 = 0.0;
+        for (int f = 0; f < Fp; ++f) {
+            b2 += (double)sums[c * Fp + f] + (double)sums[R + c * Fp + f];
+            g2 += (double)sums[2 * R + c * Fp + f] + (double)sums[3 * R + c * Fp + f];
         }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < MAXC; ++k) {
-            const int c = threadIdx.x + k * 256;
-            if (c < C)
-                for (int f = 0; f < Fp; ++f) {
-                    const float xh = (raw[(((size_t)b * Fp + f) * Rs + t) * C + c] - mu[k]) * is[k];
-                    if (g[k] * xh + bt[k] > 0.f) {
-                        const float dy = dyrow[c * Fp + f];
-                        db[k] += dy; dg[k] += (double)dy * xh;
-                    }
-                }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-        const int c = threadIdx.x + k * 256;
-        if (c < C) {
-            // 569 blocks x 2C double atomics onto 2C addresses serialised in L2 (most of this kernel's 83 us): per-block partial sums
-            // (coalesced stores) and one small summation kernel instead
-            if (partials) { partials[(size_t)blockIdx.x * 2 * C + c] = db[k]; partials[(size_t)blockIdx.x * 2 * C + C + c] = dg[k]; }
-            else { atomicAdd(&stats[c], db[k]); atomicAdd(&stats[C + c], dg[k]); }
-        }
+        out[c] = b2; out[C + c] = g2;
     }
 }
 // stats[i] = sum over blocks of partials[b][i]: one CTA per 32 columns, 32 x 32 threads (thread (y, x) sums blocks y, y+32, ... of
@@ -419,29 +469,33 @@ int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, cons
                     int partial_blocks) {
     AST_CHECK((C * Fp) % 4 == 0 && C <= 1024, "bn_bwd_from_rnn: need C*F' %% 4 == 0 and C <= 1024");
     const int TB = Tp * B;
-    const int rpb = std::max(1, cdiv(TB, 148 * 4));
+    AST_CHECK(partials != nullptr && partial_blocks >= 1, "bn_bwd_from_rnn: no buffer for the per-block partial sums");
+    const int R = C * Fp;
+    const int nx = std::min(384, R / 4);
+    AST_CHECK(R <= 4 * nx * 2, "bn_bwd_from_rnn: feature row of %d floats too long", R);
+    int rpb = 2 * std::max(1, cdiv(TB, 2 * 148 * 2));
+    rpb = std::max(rpb, cdiv(TB, partial_blocks));
     const int nblk = cdiv(TB, rpb);
-    if (partials && nblk > partial_blocks) partials = nullptr;
-    if (!partials) AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-    const size_t smem = sizeof(float) * C * Fp;
-    bn_bwd_rnn_reduce_kernel<<<nblk, 256, smem, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, stats, B, Fp, Rs, Tp, C, rpb, partials);
+    const size_t smem_r = sizeof(float) * (4 * (size_t)C + 4 * (size_t)R);
+    if (Fp == 3) bn_bwd_rnn_reduce_kernel<3><<<nblk, dim3(nx, 2), smem_r, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C, rpb, partials);
+    else if (Fp == 1) bn_bwd_rnn_reduce_kernel<1><<<nblk, dim3(nx, 2), smem_r, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C, rpb, partials);
+    else bn_bwd_rnn_reduce_kernel<0><<<nblk, dim3(nx, 2), smem_r, st>>>(d_in, d_rev, raw, mean, invstd, gamma, beta, B, Fp, Rs, Tp, C, rpb, partials);
     AST_LAUNCH_OK();
-    if (partials) {
-        bn_partials_sum_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partials, nblk, 2 * C, stats);
-        AST_LAUNCH_OK();
-    }
-    bn_bwd_rnn_apply_kernel<<<B * Rs, 128, smem, st>>>(d_in, d_rev, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B, Fp,
-                                                       Rs, Tp, C, (float)(1.0 / ((double)B * Fp * Tp)));
+    bn_partials_sum_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partials, nblk, 2 * C, stats);
+    AST_LAUNCH_OK();
+    bn_bwd_rnn_apply_kernel<<<B * Rs, 128, sizeof(float) * C * Fp, st>>>(d_in, d_rev, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, B, Fp,
+                                                                       Rs, Tp, C, (float)(1.0 / ((double)B * Fp * Tp)));
     AST_LAUNCH_OK();
     return 0;
 }
 
 int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
                        const float* invstd, const float* gamma, const float* beta, double* stats,
-                       float* dgamma, float* dbeta, int nseg, int T1, int S0, int pad, int C) {
+                       float* dgamma, float* dbeta, int nseg, int T1, int S0, int pad, int C, double* partials,
+                       int partial_blocks) {
     DyFromPadded f{da0p, T1, S0, pad, C};
     return bn_bwd_impl(st, f, raw, dx, mean, invstd, gamma, beta, stats, dgamma, dbeta, nseg * T1, C, T1, T1,
-                       (double)nseg * T1);
+                       (double)nseg * T1, partials, partial_blocks);
 }
 
 // ---- col2im gather for CNN_1's data gradient ------------------------------------------------

@@ -56,8 +56,9 @@ int bn_bwd_from_rnn(cudaStream_t st, const float* d_in, const float* d_rev, cons
                     const float* mean, const float* invstd, const float* gamma, const float* beta, double* stats,
                     float* dgamma, float* dbeta, int B, int Fp, int Rs, int Tp, int C, double* partials, int partial_blocks);
 int bn_bwd_from_padded(cudaStream_t st, const float* da0p, const float* raw, float* dx, const float* mean,
-                       const float* invstd, const float* gamma, const float* beta, double* stats, float* dgamma,
-                       float* dbeta, int nseg, int T1, int S0, int pad, int C);
+                       const float* invstd, const float* gamma, const float* beta, double* stats,
+                       float* dgamma, float* dbeta, int nseg, int T1, int S0, int pad, int C, double* partials,
+                       int partial_blocks);
 int col2im1(cudaStream_t st, const float* dA, float* da0p, int nseg, int S0, int Rs, int Tp, int C0, int kh, int sh);
 int permute_w1(cudaStream_t st, const float* src, float* dst, int Co, int Ci, int Kt, bool to_p);
 int build_w1t(cudaStream_t st, const float* W1p, float* Wt, int Co, int Ci, int Kt, int p);   // transposed-convolution weights, parity p
@@ -207,6 +208,8 @@ int colsum(cudaStream_t st, const float* x, int ld, float* out, int rows, int C,
 int copy2d(cudaStream_t st, const float* src, long long ld_src, float* dst, long long ld_dst, int R, int C);
 struct Copy2DJob { const float* src; long long ld_src; float* dst; long long ld_dst; int R, C; };
 struct Copy2DBatch { int n; Copy2DJob job[16]; };
+struct ZeroBatch { int n; float* ptr[16]; size_t count[16]; };
+int zero_multi(cudaStream_t st, const ZeroBatch& b);   // zero up to 16 float ranges (counts % 4 == 0) in one launch
 int copy2d_multi(cudaStream_t st, const Copy2DBatch& b);
 int add_inplace(cudaStream_t st, float* dst, const float* src, size_t n);
 int greedy_track(cudaStream_t st, const int* argmax, int* preds, int* seen, int* done_step, int B, int step, int eos);

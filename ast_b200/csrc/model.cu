@@ -239,7 +239,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     m->W1p_lo = a.get<float>((size_t)C1 * m->K1);
     m->raw1 = a.get<float>(M1 * C1);
     m->bnstats = a.get<double>(2 * (size_t)std::max(C0, C1));
-    m->bnpart = a.get<double>((size_t)BN_PART_BLOCKS * 2 * C1);
+    m->bnpart = a.get<double>((size_t)BN_PART_BLOCKS * 2 * std::max(C0, C1));
     m->norm_sq = a.get<double>(2);
     m->mean0 = a.get<float>(C0); m->invstd0 = a.get<float>(C0);
     m->mean1 = a.get<float>(C1); m->invstd1 = a.get<float>(C1);
@@ -534,11 +534,21 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
     const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
-    for (int l = 0; l < NL; ++l)
-        for (int d = 0; d < 2; ++d) {
-            AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
-            AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
-        }
+    if ((B * h) % 4 == 0 && 4 * NL <= 16) {      // initial link states: one launch
+        ZeroBatch zb{};
+        for (int l = 0; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) {
+                zb.ptr[zb.n] = m->Hs[l][d]; zb.count[zb.n++] = (size_t)B * h;
+                zb.ptr[zb.n] = m->Cs[l][d]; zb.count[zb.n++] = (size_t)B * h;
+            }
+        AST_TRY(zero_multi(st, zb));
+    } else {
+        for (int l = 0; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) {
+                AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
+                AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
+            }
+    }
     auto project = [&](int l, int t0, int tn, cudaStream_t s) -> int {
         const size_t r0 = (size_t)t0 * B;
         for (int d = 0; d < 2; ++d) {
@@ -940,28 +950,31 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     const int SB = S * B, TB = Tp * B;
     m->mark("bwd:start", st);
     if (m->tr_pending) { AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_tr, 0)); m->tr_pending = false; }
-    {   // cleargrads for the accumulate-style outputs
-        const ParamInfo* pe = nullptr; for (auto& pi : m->pinfo) if (pi.name == "embed_dec/W") pe = &pi;
-        AST_CUDA_OK(cudaMemsetAsync(m->G + pe->off, 0, sizeof(float) * pe->count, st));
-        AST_CUDA_OK(cudaMemsetAsync(m->d_enc, 0, sizeof(float) * (size_t)TB * H, st));
-        for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
-    }
     bool dec_bwd_v2 = false;
-    // ---- decoder BPTT: data gradients step by step -----------------------------------------------
+    DecSeq ds{};
     if (m->dec_fused) {
-        DecSeq ds = make_dec_seq(m, m->y_dev, m->use_true_dev, true);
+        ds = make_dec_seq(m, m->y_dev, m->use_true_dev, true);
         if (m->dec_prof_on && (size_t)S * 12 + 16 < 3000) { ds.prof = m->dec_prof + 4096; ds.prof_fine = m->dec_prof_on >= 2 ? m->dec_prof_on - 1 : 0; }
         dec_bwd_v2 = m->dec_v2 && !m->exact && m->tc_gemm && ds.bar && dec_seq2_supported(ds);
+    }
+    {   // cleargrads (nn.py:180): the whole flat gradient buffer once; every weight-gradient kernel below accumulates into it
+        // (one memset instead of one in front of each split-K GEMM / column sum on the side stream's critical tail).  With the
+        // dec_seq2 kernels the first gradient write is after the decoder BPTT: the memset and the sentinel fill of that kernel's
+        // hand-off slots run on the side stream beside the dz . Wo GEMM.
+        cudaStream_t zs = (m->overlap && dec_bwd_v2) ? m->side : st;
+        if (zs != st) {
+            AST_CUDA_OK(cudaEventRecord(m->ev_fill[0], st));
+            AST_CUDA_OK(cudaStreamWaitEvent(zs, m->ev_fill[0], 0));
+        }
+        AST_CUDA_OK(cudaMemsetAsync(m->G, 0, sizeof(float) * (size_t)m->nfloats, zs));
+        if (dec_bwd_v2) AST_TRY(dec_seq2_prepare_bwd(zs, ds));
+        if (zs != st) AST_CUDA_OK(cudaEventRecord(m->ev_fill[1], zs));
+        if (!dec_bwd_v2) AST_CUDA_OK(cudaMemsetAsync(m->d_enc, 0, sizeof(float) * (size_t)TB * H, st));      // accumulated step by step
+        for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
+    }
+    // ---- decoder BPTT: data gradients step by step -----------------------------------------------
+    if (m->dec_fused) {
         if (dec_bwd_v2) {
-            // hand-off slots of this launch <- sentinel, beside the dz . Wo GEMM
-            if (m->overlap) {
-                AST_CUDA_OK(cudaEventRecord(m->ev_fill[0], st));
-                AST_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fill[0], 0));
-                AST_TRY(dec_seq2_prepare_bwd(m->side, ds));
-                AST_CUDA_OK(cudaEventRecord(m->ev_fill[1], m->side));
-            } else {
-                AST_TRY(dec_seq2_prepare_bwd(st, ds));
-            }
             // dz . Wo for every step at once (the only place the vocabulary enters the decoder BPTT)
             AST_TRY(gemm(m, st, false, false, SB, A, V, m->logits, Vp, m->p("out/W"), A, m->dzw, A, nullptr, 0.f, 0, SITE_DEC_PRE));
             if (m->overlap) AST_CUDA_OK(cudaStreamWaitEvent(st, m->ev_fill[1], 0));
@@ -1036,19 +1049,19 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, dGd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
         AST_TRY(embed_scatter(sw, m->g("embed_dec/W"), m->dE, E, m->words_used, SB, E, 0, de, m->cur_seed, 32));
     }
-    AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, false));
-    AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->du, A, m->g("context/b"), SB, A, false));
-    AST_TRY(gemm(m, sw, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->dq, H, m->g("attn_Wa/b"), SB, H, false));
+    AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, true));
+    AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->du, A, m->g("context/b"), SB, A, true));
+    AST_TRY(gemm(m, sw, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+    AST_TRY(colsum(sw, m->dq, H, m->g("attn_Wa/b"), SB, H, true));
     for (int l = 0; l < NL; ++l) {
         const std::string ln = lname(l, "dec");
         const int in = m->in_dec(l);
         const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
-        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, dGd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, dGd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 0.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(colsum(sw, dGd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, false));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, dGd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, dGd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, dGd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, true));
     }
     gemm_tc_set_cta_cap(0);
     // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
@@ -1102,10 +1115,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         return 0;
     };
     auto bwd_dx = [&](int l, int ci, cudaStream_t s) -> int { return bwd_dx_rows(l, ci * CH, std::min(CH, Tp - ci * CH), s); };
-    // weight gradients of layer l from the steps [t0, t0+tn) (first: overwrite, else accumulate)
+    // weight gradients of layer l from the steps [t0, t0+tn), accumulated into the gradient buffer (zeroed at the start of backward)
     auto enc_wgrads_range = [&](int l, int t0, int tn, bool first) -> int {
         const size_t r0 = (size_t)t0 * B;
-        const float beta = first ? 0.f : 1.f;
+        const float beta = 1.f; (void)first;
         // the 1024 x 256 x (T'B) problems of a layer (lateral both directions; upward too above layer 0) as ONE grouped 2-CTA launch
         bool grouped_lat = false, grouped_up = false;
         if (m->tc_gemm && !m->exact && (m->tc2 & 4) && !((m->tc_mask >> SITE_ENC_WGRAD) & 1u) && (4 * h) % 256 == 0 && h % 256 == 0 && tn * B >= 1024) {
@@ -1129,7 +1142,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
             const float* dG = m->Genc[l][d] + r0 * 4 * h;
             if (!grouped_up) AST_TRY(gemm(m, sw, true, false, 4 * h, in, tn * B, dG, 4 * h, xin + r0 * in, in, m->g((ln + "/upward/W").c_str()), in, nullptr, beta, -1, SITE_ENC_WGRAD));
             if (!grouped_lat) AST_TRY(gemm(m, sw, true, false, 4 * h, h, tn * B, dG, 4 * h, m->Hs[l][d] + r0 * h, h, m->g((ln + "/lateral/W").c_str()), h, nullptr, beta, -1, SITE_ENC_WGRAD));
-            AST_TRY(colsum(sw, dG, 4 * h, m->g((ln + "/upward/b").c_str()), tn * B, 4 * h, !first));
+            AST_TRY(colsum(sw, dG, 4 * h, m->g((ln + "/upward/b").c_str()), tn * B, 4 * h, true));
         }
         return 0;
     };
@@ -1248,7 +1261,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         AST_TRY(col2im1(st, m->dA1, m->da0p, B * Fp, S0, Rs, Tp, C0, c.cnn_kh[1], c.cnn_sh[1]));
     }
     AST_TRY(bn_bwd_from_padded(st, m->da0p, m->raw0, m->draw0, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
-                               m->bnstats, m->g("CNN_0_bn/gamma"), m->g("CNN_0_bn/beta"), B * Fp, T1, S0, c.cnn_ph[1], C0));
+                               m->bnstats, m->g("CNN_0_bn/gamma"), m->g("CNN_0_bn/beta"), B * Fp, T1, S0, c.cnn_ph[1], C0, m->bnpart, BN_PART_BLOCKS));
     AST_TRY(gemm(m, st, true, false, C0, m->ld0, M0, m->draw0, C0, m->cols0, m->ld0, m->dW0pad, m->ld0, nullptr, 0.f, -1, SITE_CONV0_WGRAD));
     const int K0 = c.cnn_kh[0] * c.cnn_kw[0];
     AST_TRY(copy2d(st, m->dW0pad, m->ld0, m->g("CNN_0/W"), K0, C0, K0));

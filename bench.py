@@ -668,6 +668,9 @@ def run_ours(args):
         torch.distributed.barrier()
     clk = clocks.stop() if rank == 0 else None
     ms_dev = sum(a.elapsed_time(b) for a, b in evs)
+    if rank == 0 and os.environ.get("AST_BENCH_VERBOSE"):
+        for (a, b), x in zip(evs, resident[W:W + K]):
+            print(f"  step B{x[0].shape[0]} x T{x[0].shape[1]} x L{x[1].shape[1]}: {a.elapsed_time(b):.3f} ms", file=sys.stderr)
     frames = sum(x[3] for x in resident[W:W + K])
     t_max = adist.max_over_ranks(ms_dev * 1e-3, dev)
     frames_all = adist.sum_over_ranks(frames, dev)

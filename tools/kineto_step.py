@@ -19,6 +19,7 @@ ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--T", type=int, default=640)
 ap.add_argument("--L", type=int, default=24)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--timeline", action="store_true", help="also print every device record of the last step in start order (us since its first record, duration, stream, name)")
 a = ap.parse_args()
 rng = np.random.default_rng(0)
 m = SpeechEncoderDecoder(0, es_en_20h_model_cfg(dropout=(0.3, 0.3, 0.0)), feat_dim=40)
@@ -58,3 +59,18 @@ print(f"{len(ev)} kernel records over {a.steps} steps, wall span {(t_hi - t_lo) 
 print(f"{'kernel':70s} {'count':>6s} {'total us':>10s} {'avg us':>9s}")
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:70s} {n:6d} {us:10.1f} {us / n:9.2f}")
+
+if a.timeline:
+    allev = sorted((x for x in prof.events() if x.device_type == torch.autograd.DeviceType.CUDA), key=lambda x: x.time_range.start)
+    # the last step starts at the last mul_noise / im2col0 kernel
+    starts = [x.time_range.start for x in allev if "mul_noise" in x.name]
+    t0 = starts[-1] if starts else allev[0].time_range.start
+    print("timeline of the last step: start us | dur us | stream | name")
+    for x in allev:
+        if x.time_range.start < t0:
+            continue
+        try:
+            sid = x.device_resource_id
+        except Exception:
+            sid = -1
+        print(f"{x.time_range.start - t0:9.1f} {x.time_range.end - x.time_range.start:8.1f} {sid:4d}  {x.name.split('(')[0][:90]}")
