@@ -601,15 +601,25 @@ int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n) 
 
 // C = A . B^T (+bias) with fp32-faithful 3xTF32 (NT form only).  (A, Alo) / (B, Blo) = split_tf32 of the operands, same layouts.
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo, int ldb,
-                float* C, int ldc, const float* bias) {
+                float* C, int ldc, const float* bias, bool allow_split) {
     if (M <= 0 || N <= 0 || K <= 0) return 1;
     CUtensorMap ma, mb, mal, mbl;
     const bool ok = make_map(&ma, A, (uint64_t)K, (uint64_t)M, lda, TBM, false) && make_map(&mal, Alo, (uint64_t)K, (uint64_t)M, lda, TBM, false) &&
                     make_map(&mb, B, (uint64_t)K, (uint64_t)N, ldb, TBN, false) && make_map(&mbl, Blo, (uint64_t)K, (uint64_t)N, ldb, TBN, false);
     if (!ok) return 1;
     const int nkb = cdiv(K, TBK);
-    TcParams p{M, N, K, C, ldc, bias, 0.f, 0, nkb, 1, nullptr, 0u, 1, 1, 0, 0, nullptr};
-    dim3 grid(std::min(cdiv(N, TBN) * cdiv(M, TBM), tc_num_sms()));
+    // few output tiles (a decode step: M = utterances x hypotheses <= 320 rows): split K so that about one wave of CTAs shares the
+    // operand traffic (a 48-tile launch with K = 1152 was bound by each CTA's own 2.3 MB of TMA loads: 23 us), partial sums by
+    // red.add onto a zeroed C, the bias added by split 0
+    const int tiles = cdiv(N, TBN) * cdiv(M, TBM);
+    int splits = 1;
+    static const bool no_split = getenv("AST_TC3_NOSPLIT") != nullptr;      // diagnostics
+    if (allow_split && !no_split && tiles * 2 <= tc_num_sms()) splits = std::max(1, std::min(nkb / 4, tc_num_sms() / tiles));
+    const int kbps = cdiv(nkb, splits);
+    splits = cdiv(nkb, kbps);
+    if (splits > 1) AST_CUDA_OK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+    TcParams p{M, N, K, C, ldc, bias, 0.f, splits > 1 ? 1 : 0, kbps, splits, nullptr, 0u, 1, 1, 0, 0, nullptr};
+    dim3 grid(std::min(tiles * splits, tc_num_sms()));
     return launch_tc<false, false, true>(st, ma, mb, mal, mbl, p, grid);
 }
 

@@ -38,7 +38,7 @@ int gemm_tc_gated(cudaStream_t st, bool tb, int M, int N, int K, const float* A,
 // fp32-faithful 3xTF32 NT GEMM (gemm_tc.cu) on (hi, lo) = split_tf32(operand); returns 1 if the shape is unsupported
 int split_tf32(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
 int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const float* Alo, int lda, const float* B, const float* Blo,
-                int ldb, float* C, int ldc, const float* bias);
+                int ldb, float* C, int ldc, const float* bias, bool allow_split = false);
 
 // ---- CNN front-end ---------------------------------------------------------------------------
 int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, int Fp, int T1, int kh, int kw, int sh,

@@ -124,6 +124,9 @@ struct ast_model {
     float *tb_Wcat_hi[MAXL] = {}, *tb_Wcat_lo[MAXL] = {}, *tb_Wa_hi = nullptr, *tb_Wa_lo = nullptr, *tb_Wc_hi = nullptr, *tb_Wc_lo = nullptr,
           *tb_Wo_hi = nullptr, *tb_Wo_lo = nullptr, *tb_x_hi = nullptr, *tb_x_lo = nullptr;
     bool tb_ready = false; int beam_tc = 1;      // batched beam search (ast_beam_search_batch)
+    // fp32-faithful encoder on the tensor cores (decode-time encode of the beam searches that use the tensor-core decode step):
+    // 3xTF32 input projections and convolutions in EXACT mode.  (hi, lo) splits of the encoder's upward weights, built lazily.
+    float *enc_Wup_hi[MAXL][2] = {}, *enc_Wup_lo[MAXL][2] = {}; bool enc_split_ready = false; int enc_tc3 = 0; size_t cap_TB = 0;      // cap_TB: rows the planned T' x B buffers hold
     int *h_pinned = nullptr;   // small pinned host mailbox
     // side stream: weight-gradient GEMMs run here, off the backward critical path (recurrences + dx GEMMs)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork[8] = {}, ev_join = nullptr, ev_tr = nullptr, ev_bucket[3] = {}; int overlap = 1; bool tr_pending = false; bool buckets_valid = false;
@@ -221,6 +224,7 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
     int T1, Tp, S0, Rs; shapes_for(m, T, T1, Tp, S0, Rs);
     const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, H = m->H, h = m->h, E = m->E, A = m->A, Vp = m->Vp, R = m->R, NL = m->NL;
     const size_t M0 = (size_t)B * Fp * T1, M1 = (size_t)B * Fp * Rs, TB = (size_t)Tp * B;
+    m->cap_TB = TB;
     m->enc_flags = a.get<unsigned>(ENC_FLAG_WORDS);
     m->enc_ts = a.get<unsigned long long>(ENC_TS_WORDS);
     const int S = std::max(L - 1, 1);
@@ -338,6 +342,11 @@ static void plan(ast_model* m, Arena& a, int B, int T, int L, int N, int steps) 
         const size_t kmax = (size_t)std::max(std::max(E + A + H, 2 * H), A);
         m->tb_x_hi = a.get<float>((size_t)Bd * kmax); m->tb_x_lo = a.get<float>((size_t)Bd * kmax);
     }
+    for (int l = 0; l < NL; ++l)
+        for (int d = 0; d < 2; ++d) {
+            m->enc_Wup_hi[l][d] = a.get<float>((size_t)4 * h * m->in_enc(l)); m->enc_Wup_lo[l][d] = a.get<float>((size_t)4 * h * m->in_enc(l));
+        }
+    m->enc_split_ready = false;
     m->tb_ready = false;
     m->bb_G = std::min(Bd, 32); m->wsTp = Tp;
     m->bb_enc = a.get<float>((size_t)m->bb_G * Tp * H);
@@ -407,6 +416,19 @@ static int refresh_weights(ast_model* m, cudaStream_t st) {
     if (ts != st) { AST_CUDA_OK(cudaEventRecord(m->ev_tr, ts)); m->tr_pending = true; }
     m->weights_dirty = false;
     m->tb_ready = false;
+    m->enc_split_ready = false;
+    return 0;
+}
+
+// (hi, lo) splits of the encoder's upward weights for the decode-time 3xTF32 input projections
+static int build_enc_splits(ast_model* m, cudaStream_t st) {
+    for (int l = 0; l < m->NL; ++l)
+        for (int d = 0; d < 2; ++d) {
+            const size_t n = (size_t)4 * m->h * m->in_enc(l);
+            AST_CHECK(n % 4 == 0, "encoder weight split: size not a multiple of 4");
+            AST_TRY(split_tf32(st, m->p((lname(l, d == 0 ? "enc" : "rev_enc") + "/upward/W").c_str()), m->enc_Wup_hi[l][d], m->enc_Wup_lo[l][d], n));
+        }
+    m->enc_split_ready = true;
     return 0;
 }
 
@@ -487,7 +509,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     // CNN_0: im2col + GEMM, BN statistics, BN+ReLU into the padded layout
     AST_TRY(im2col0(st, Xin, m->cols0, B, T, m->D, Fp, T1, c.cnn_kh[0], c.cnn_kw[0], c.cnn_sh[0], c.cnn_sw[0], c.cnn_ph[0], m->ld0));
     int conv0_done = 0;
-    if (m->tc_gemm && !m->exact && (m->conv3x & 2) && ((size_t)M0 * m->ld0) % 4 == 0) {
+    if (((m->tc_gemm && !m->exact) || m->enc_tc3) && (m->conv3x & 2) && ((size_t)M0 * m->ld0) % 4 == 0) {
         // fp32-faithful 3xTF32 on the tensor cores, as for CNN_1 below (K = 117 padded to 120: the fp32 SIMT GEMM took 38 us)
         AST_TRY(split_tf32(st, m->cols0, m->cols0_hi, m->cols0_lo, (size_t)M0 * m->ld0));
         const int r = gemm_tc3_nt(st, M0, C0, m->ld0, m->cols0_hi, m->cols0_lo, m->ld0, m->W0_hi, m->W0_lo, m->ld0, m->raw0, C0, nullptr);
@@ -507,7 +529,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
     int conv1_done = 0;
-    if (m->tc_gemm && !m->exact && (m->conv3x & 1) && m->K1 % 4 == 0) {
+    if (((m->tc_gemm && !m->exact) || m->enc_tc3) && (m->conv3x & 1) && m->K1 % 4 == 0) {
         // fp32-faithful on the tensor cores: 3xTF32 (hi.hi + lo.hi + hi.lo); single-pass TF32 here wrecks the BatchNorm
         // parameter gradients downstream, the fp32 SIMT kernel was 22 % of the forward pass
         const size_t n_a0p = (size_t)B * Fp * S0 * C0 + (size_t)(c.cnn_kh[1] + 8) * C0;
@@ -554,8 +576,22 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const float* xin = l == 0 ? (d == 0 ? m->rnn_in : m->rnn_rev) : m->Hd[l - 1][d];
-            AST_TRY(gemm_nt(m, s, tn * B, 4 * h, m->in_enc(l), xin + r0 * m->in_enc(l), m->in_enc(l), m->p((ln + "/upward/W").c_str()),
-                            m->in_enc(l), m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
+            const int in = m->in_enc(l);
+            if (m->enc_tc3 && !train && in % 4 == 0 && (l == 0 ? 2 * TB * (size_t)R <= (size_t)B * Fp * Rs * m->K1 : l <= 2)) {
+                // decode-time projection in fp32-faithful 3xTF32 on tcgen05 (the fp32 SIMT GEMMs were 2/3 of a group's encode).
+                // The weight's (hi, lo) split is cached; the activations are split into buffers only backward uses, one pair
+                // per (layer, direction) because the layers' chunks run concurrently on their own streams.
+                float *xh, *xl;
+                if (l == 0) { xh = d == 0 ? m->d_rnn_in : m->dA1; xl = d == 0 ? m->d_rnn_rev : m->dA1 + TB * (size_t)R; }
+                else { xh = m->dHd[l][d]; xl = l == 1 ? m->dHd[0][d] : m->d_enc + (size_t)d * TB * h; }
+                AST_TRY(split_tf32(s, xin + r0 * in, xh + r0 * in, xl + r0 * in, (size_t)tn * B * in));
+                const int r = gemm_tc3_nt(s, tn * B, 4 * h, in, xh + r0 * in, xl + r0 * in, in, m->enc_Wup_hi[l][d], m->enc_Wup_lo[l][d], in,
+                                          m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()));
+                if (r < 0) return r;
+                if (r == 0) continue;
+            }
+            AST_TRY(gemm_nt(m, s, tn * B, 4 * h, in, xin + r0 * in, in, m->p((ln + "/upward/W").c_str()),
+                            in, m->Genc[l][d] + r0 * 4 * h, 4 * h, m->p((ln + "/upward/b").c_str()), SITE_ENC_PROJ));
         }
         return 0;
     };
@@ -779,13 +815,13 @@ static int dec_step_fwd_tc(ast_model* m, const StepIO& io, cudaStream_t st) {
         const std::string ln = lname(l, "dec");
         AST_TRY(split_concat2(st, l == 0 ? io.x0 : io.hd[l - 1], l == 0 ? E + A : io.ld_hd[l - 1], in, io.h_prev[l], H, H, m->tb_x_hi, m->tb_x_lo, Kl, R));
         const int r = gemm_tc3_nt(st, R, 4 * H, Kl, m->tb_x_hi, m->tb_x_lo, Kl, m->tb_Wcat_hi[l], m->tb_Wcat_lo[l], Kl, io.act[l], 4 * H,
-                                  m->p((ln + "/upward/b").c_str()));
+                                  m->p((ln + "/upward/b").c_str()), true);
         AST_CHECK(r == 0, "tensor-core decode step: the LSTM GEMM of layer %d rejected its operands", l);
         AST_TRY(lstm_cell_rows(st, io.act[l], io.c_prev[l], io.c_out[l], io.h_out[l], io.hd[l], io.ld_hd[l], R, H));
     }
     {   // q = attn_Wa(h)  (:341)
         AST_TRY(split_concat2(st, io.hd[NL - 1], io.ld_hd[NL - 1], H, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, H, R));
-        const int r = gemm_tc3_nt(st, R, H, H, m->tb_x_hi, m->tb_x_lo, H, m->tb_Wa_hi, m->tb_Wa_lo, H, io.q, H, m->p("attn_Wa/b"));
+        const int r = gemm_tc3_nt(st, R, H, H, m->tb_x_hi, m->tb_x_lo, H, m->tb_Wa_hi, m->tb_Wa_lo, H, io.q, H, m->p("attn_Wa/b"), true);
         AST_CHECK(r == 0, "tensor-core decode step: the attention GEMM rejected its operands");
     }
     if (io.enc_bank) {
@@ -798,13 +834,13 @@ static int dec_step_fwd_tc(ast_model* m, const StepIO& io, cudaStream_t st) {
     }
     {   // ht = tanh(context([cv;h]))  (:386-390)
         AST_TRY(split_concat2(st, io.cvh, 2 * H, 2 * H, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, 2 * H, R));
-        const int r = gemm_tc3_nt(st, R, A, 2 * H, m->tb_x_hi, m->tb_x_lo, 2 * H, m->tb_Wc_hi, m->tb_Wc_lo, 2 * H, io.ht_out, A, m->p("context/b"));
+        const int r = gemm_tc3_nt(st, R, A, 2 * H, m->tb_x_hi, m->tb_x_lo, 2 * H, m->tb_Wc_hi, m->tb_Wc_lo, 2 * H, io.ht_out, A, m->p("context/b"), true);
         AST_CHECK(r == 0, "tensor-core decode step: the context GEMM rejected its operands");
         AST_TRY(tanh_rows(st, io.ht_out, (size_t)R * A));
     }
     {   // logits = out(ht)  (:394)
         AST_TRY(split_concat2(st, io.ht_out, A, A, nullptr, 0, 0, m->tb_x_hi, m->tb_x_lo, A, R));
-        const int r = gemm_tc3_nt(st, R, m->V, A, m->tb_x_hi, m->tb_x_lo, A, m->tb_Wo_hi, m->tb_Wo_lo, A, io.logits, m->Vp, m->p("out/b"));
+        const int r = gemm_tc3_nt(st, R, m->V, A, m->tb_x_hi, m->tb_x_lo, A, m->tb_Wo_hi, m->tb_Wo_lo, A, io.logits, m->Vp, m->p("out/b"), true);
         AST_CHECK(r == 0, "tensor-core decode step: the output GEMM rejected its operands");
     }
     return 0;
@@ -1449,6 +1485,10 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_chunk")) m->enc_chunk = (int)value;
     else if (!strcmp(key, "enc_persist")) m->enc_persist = (int)value;
     else if (!strcmp(key, "beam_tc")) m->beam_tc = (int)value;
+    else if (!strcmp(key, "enc_tc3")) {       // diagnostics: decode-time encodes with the 3xTF32 tensor-core projections / convolutions
+        if (value != 0 && !m->enc_split_ready) { if (m->weights_dirty) AST_TRY(refresh_weights(m, nullptr)); AST_TRY(build_enc_splits(m, nullptr)); AST_CUDA_OK(cudaStreamSynchronize(nullptr)); }
+        m->enc_tc3 = value != 0;
+    }
     else if (!strcmp(key, "enc_pchunk")) m->enc_pchunk = (int)value;
     else if (!strcmp(key, "enc_l0_pre")) m->enc_l0_pre = (int)value;
     else if (!strcmp(key, "enc_ts")) m->enc_ts_on = (int)value;
@@ -1806,7 +1846,15 @@ int ast_beam_search_batch(ast_model* m, const float* X, const int* lens, int G, 
         while (g1 < G && lens[g1] == lens[g0] && g1 - g0 < 32) ++g1;
         const int Be = g1 - g0, T = lens[g0];
         AST_TRY(require_ready(m, Be, T, 0, R, stop_limit));
-        AST_TRY(encode_impl(m, X + xoff, Be, T, 0, nullptr, 0.f, st));
+        if (m->weights_dirty) AST_TRY(refresh_weights(m, st));
+        static const bool no_enc_tc3 = getenv("AST_NO_ENC_TC3") != nullptr;      // diagnostics
+        const bool tc3 = !no_enc_tc3 && (m->beam_tc & 1) && m->exact && m->in_enc(0) % 4 == 0 && m->h % 4 == 0;      // same arithmetic class as the tensor-core decode step
+        if (tc3 && !m->enc_split_ready) AST_TRY(build_enc_splits(m, st));
+        const int enc_tc3_was = m->enc_tc3;
+        m->enc_tc3 = tc3 ? 1 : 0;
+        const int enc_rc = encode_impl(m, X + xoff, Be, T, 0, nullptr, 0.f, st);
+        m->enc_tc3 = enc_tc3_was;
+        if (enc_rc) return enc_rc;
         const int Tp = m->Tp;
         for (int e = 0; e < Be; ++e) {
             tps[g0 + e] = Tp;

@@ -346,20 +346,31 @@ class Engine:
         batch; every utterance's hypotheses, scores and attention history equal those of `beam_search` on it alone."""
         G = len(Xs)
         assert 1 <= G <= 32, "1..32 utterances per call"
-        feats = []
-        for x in Xs:
-            t = self._as_f32(x)
-            t = t.reshape(-1, t.shape[-1])
-            assert t.shape[1] == self.feat_dim
-            feats.append(t)
-        order = sorted(range(G), key=lambda i: feats[i].shape[0])
-        lens = [int(feats[i].shape[0]) for i in order]
+        dev = self.device
+        if all(not isinstance(x, torch.Tensor) for x in Xs):
+            # host features: one pinned staging buffer, ONE host-to-device copy for the whole group (32 pageable copies + a
+            # device concatenation were a millisecond of the call)
+            arrs = [np.asarray(x, dtype=np.float32).reshape(-1, np.shape(x)[-1]) for x in Xs]
+            assert all(a.shape[1] == self.feat_dim for a in arrs)
+            order = sorted(range(G), key=lambda i: arrs[i].shape[0])
+            lens = [int(arrs[i].shape[0]) for i in order]
+            stage = self._pinned("beam_X", (sum(lens), self.feat_dim), torch.float32)
+            np.concatenate([arrs[i] for i in order], axis=0, out=stage.numpy())
+            X = stage.to(dev, non_blocking=True)
+        else:
+            feats = []
+            for x in Xs:
+                t = self._as_f32(x)
+                t = t.reshape(-1, t.shape[-1])
+                assert t.shape[1] == self.feat_dim
+                feats.append(t)
+            order = sorted(range(G), key=lambda i: feats[i].shape[0])
+            lens = [int(feats[i].shape[0]) for i in order]
+            X = torch.cat([feats[i] for i in order], dim=0).contiguous()
         run = max(sum(1 for _ in grp) for _, grp in __import__("itertools").groupby(lens))
         Tmax = max(lens)
         self.ensure_workspace(B=min(run, 32), T=Tmax, N=G * N, steps=stop_limit)
         Tp_ld = self.enc_len(Tmax)
-        dev = self.device
-        X = torch.cat([feats[i] for i in order], dim=0).contiguous()
         hist_parent = torch.zeros(G, stop_limit, N, dtype=torch.int32, device=dev)
         hist_tok = torch.zeros(G, stop_limit, N, dtype=torch.int32, device=dev)
         scores = torch.zeros(G, N, dtype=torch.float32, device=dev)
@@ -372,12 +383,38 @@ class Engine:
                                              ptr(hist_parent), ptr(hist_tok), ptr(scores), ptr(alpha_hist), Tp_ld, ptr(states),
                                              ptr(attn_v), self.stream()), "ast_beam_search_batch")
         self._keep = (X,)
+        # the group's buffers, shared by the per-utterance result dicts: nn.beam_result_to_entries copies them to the host once per
+        # group (pinned) and backtracks all utterances together
+        shared = dict(engine=self, hist_parent=hist_parent, hist_tok=hist_tok, scores=scores, alpha_hist=alpha_hist,
+                      n_steps=[int(v) for v in ns], n_hyps=[int(v) for v in nh], tp=[int(v) for v in tp], host=None)
         out = [None] * G
         for j, i in enumerate(order):
             out[i] = dict(n_steps=ns[j], n_hyps=nh[j], hist_parent=hist_parent[j], hist_tok=hist_tok[j], scores=scores[j],
                           alpha_hist=alpha_hist[j][:, :, :tp[j]], states=states[:, :, j * N:(j + 1) * N, :],
-                          attn_v=attn_v[j * N:(j + 1) * N])
+                          attn_v=attn_v[j * N:(j + 1) * N], _group=shared, _slot=j)
         return out
+
+    def _pinned(self, key, shape, dtype):
+        """Cached page-locked staging tensor (cudaHostAlloc costs milliseconds: one buffer per use, grown on demand)."""
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        n = int(np.prod(shape))
+        buf = cache.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+            cache[key] = buf
+        return buf[:n].view(*shape)
+
+    def fetch_host(self, tensors):
+        """Device tensors -> numpy VIEWS of cached pinned buffers: all copies asynchronous, one synchronisation.  The views are
+        valid until the next fetch_host (``self.fetch_gen`` counts them: a holder compares the value it saw)."""
+        outs = []
+        for i, t in enumerate(tensors):
+            h = self._pinned(f"fetch{i}", tuple(t.shape), t.dtype)
+            h.copy_(t, non_blocking=True)
+            outs.append(h)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.fetch_gen = getattr(self, "fetch_gen", 0) + 1
+        return [h.numpy() for h in outs]
 
     def stage_times(self):
         """[(stage, ms)] of the last forward_loss + backward (needs set_option('stage_timing', 1)); synchronises."""

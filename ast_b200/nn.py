@@ -112,29 +112,67 @@ class SGD:
         raise NotImplementedError("optimizer.type=1 (SGD) is outside the hot path; every shipped config uses Adam (type 0)")
 
 
+def _backtrack(hp, hk, ns):
+    """Parent-pointer walk for a whole group at once.  hp, hk: (G, S, N) int arrays, ns: (G,) steps made per utterance ->
+    toks, slots (G, S, N): final hypothesis j of utterance g emitted toks[g, s, j] at step s (-1: none: finished earlier) from
+    beam slot slots[g, s, j]."""
+    G, S, N = hp.shape
+    slot = np.tile(np.arange(N), (G, 1))
+    toks = np.full((G, S, N), -1, dtype=np.int64)
+    slots = np.zeros((G, S, N), dtype=np.int64)
+    gi = np.arange(G)[:, None]
+    ns = np.asarray(ns)
+    for s in range(int(ns.max()) - 1, -1, -1):
+        act = (s < ns)[:, None]
+        toks[:, s] = np.where(act, hk[gi, s, slot], -1)
+        slots[:, s] = slot
+        slot = np.where(act, hp[gi, s, slot], slot)
+    return toks, slots
+
+
+def _entries(toks, slots, ah, sc, ns, nh, r, go_id):
+    """One utterance's hypothesis dicts.  ``attn_history`` is a (tokens, T') array: indexing, iteration and len() behave like the
+    reference's list of per-step attention vectors (one list of 175 small arrays per hypothesis was most of the conversion time).
+    The device views of the decoder state are cut with a handful of split/unbind calls per utterance, not seven slices per
+    hypothesis."""
+    st = r["states"]                                                        # (NL, 2, N, H)
+    per_layer = [[part.split(1, 0) for part in layer.unbind(0)] for layer in st.unbind(0)]      # [l][c|h][j] -> (1, H)
+    av = r["attn_v"].split(1, 0)
+    out = []
+    for j in range(nh):
+        idx = np.nonzero(toks[:, j] >= 0)[0]
+        out.append({"hyp": [go_id] + toks[idx, j].tolist(), "score": np.float32(sc[j]) if ns > 0 else 0,
+                    "dec_state": {"c": [Variable(pl[0][j]) for pl in per_layer],
+                                  "h": [Variable(pl[1][j]) for pl in per_layer]},
+                    "attn_v": Variable(av[j]),
+                    "attn_history": ah[idx, slots[idx, j]]})
+    return out
+
+
 def beam_result_to_entries(r, go_id=SYMBOLS.GO_ID, model=None):
-    """Device beam-search buffers -> the reference's list of hypothesis dicts (nn.py:286-294)."""
+    """Device beam-search buffers -> the reference's list of hypothesis dicts (nn.py:286-294).  Results of a lock-step group
+    (Engine.beam_search_batch) are copied to the host (pinned, one synchronisation) and backtracked together when the first
+    of them is converted; the host copy is re-fetched if another group was fetched in between."""
+    grp = r.get("_group")
+    if grp is not None:
+        eng = grp["engine"]
+        if grp["host"] is None or grp["host"][0] != eng.fetch_gen:
+            hp, hk, sc, ah = eng.fetch_host([grp["hist_parent"], grp["hist_tok"], grp["scores"], grp["alpha_hist"]])
+            toks, slots = _backtrack(hp, hk, grp["n_steps"])
+            grp["host"] = (eng.fetch_gen, toks, slots, sc.copy(), ah)
+        _, toks, slots, sc, ah = grp["host"]
+        g = r["_slot"]
+        ns, nh = grp["n_steps"][g], grp["n_hyps"][g]
+        return _entries(toks[g, :ns], slots[g, :ns], ah[g, :ns, :, :grp["tp"][g]], sc[g], ns, nh, r, go_id)
     ns, nh = r["n_steps"], r["n_hyps"]
     hp = r["hist_parent"][:ns].cpu().numpy()
     hk = r["hist_tok"][:ns].cpu().numpy()
     ah = r["alpha_hist"][:ns].cpu().numpy()
     sc = r["scores"].cpu().numpy()
-    out = []
-    for j in range(nh):
-        toks, als = [], []
-        slot = j
-        for s in range(ns - 1, -1, -1):
-            if hk[s, slot] >= 0:
-                toks.append(int(hk[s, slot]))
-                als.append(ah[s, slot].copy())
-            slot = int(hp[s, slot])
-        st = r["states"][:, :, j:j + 1, :]
-        out.append({"hyp": [go_id] + toks[::-1], "score": np.float32(sc[j]) if ns > 0 else 0,
-                    "dec_state": {"c": [Variable(st[l, 0]) for l in range(st.shape[0])],
-                                  "h": [Variable(st[l, 1]) for l in range(st.shape[0])]},
-                    "attn_v": Variable(r["attn_v"][j:j + 1]),
-                    "attn_history": als[::-1]})
-    return out
+    if ns == 0:
+        return _entries(np.zeros((0, max(nh, 1)), np.int64), np.zeros((0, max(nh, 1)), np.int64), ah, sc, ns, nh, r, go_id)
+    toks, slots = _backtrack(hp[None], hk[None], [ns])
+    return _entries(toks[0], slots[0], ah, sc, ns, nh, r, go_id)
 
 
 class NN:
@@ -304,7 +342,7 @@ class NN:
                 out.append({"hyp": decode_entry["hyp"] + [int(pi)],
                             "score": np.float32(np.float32(decode_entry["score"]) + lp[pi]),
                             "dec_state": st, "attn_v": ht,
-                            "attn_history": decode_entry["attn_history"] + [alphas.data[0, :, 0].cpu().numpy()]})
+                            "attn_history": list(decode_entry["attn_history"]) + [alphas.data[0, :, 0].cpu().numpy()]})
             return out
 
     def decode_beam_batch(self, Xs, stop_limit, N, K):
