@@ -49,29 +49,40 @@ int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, i
 // ---- BN statistics: per-channel sum / sum-of-squares over valid rows (double accumulation) ---
 // x: rows x C (ld = C).  Row r is valid iff (r % seg_rows) < seg_valid.  stats[0..C) += sum,
 // stats[C..2C) += sumsq.  blockDim = (32, 8): x = channel lane, y = row lane.
-__global__ void bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int rows, int C,
+__global__ void bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats);
+
+// float4 channel vectors: lane x of a (32, 8) block owns channels 4 (32 bx + x) .. + 3 (a warp reads 512 contiguous bytes per row),
+// row lane y strides the block's rows.  fp32 accumulation per thread (a few dozen rows), the 8 row lanes are added in double, one
+// partial sum per block (bn_partials_sum adds them: deterministic, no double atomics; the scalar version ran at 1.2 TB/s).
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partials, int rows, int C,
                                 int seg_rows, int seg_valid, int rows_per_block) {
-    __shared__ double ssum[8][33], ssq[8][33];
-    const int c = blockIdx.x * 32 + threadIdx.x;
+    __shared__ double ssum[8][32][4], ssq[8][32][4];
+    const int c = 4 * (blockIdx.x * 32 + threadIdx.x);
     const int r0 = blockIdx.y * rows_per_block;
     const int r1 = min(rows, r0 + rows_per_block);
-    double s = 0.0, q = 0.0;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
+#pragma unroll 4
         for (int r = r0 + threadIdx.y; r < r1; r += 8) {
             if ((r % seg_rows) < seg_valid) {
-                const float v = x[(size_t)r * C + c];
-                s += v; q += (double)v * v;
+                const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
             }
         }
     }
-    ssum[threadIdx.y][threadIdx.x] = s;
-    ssq[threadIdx.y][threadIdx.x] = q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ssum[threadIdx.y][threadIdx.x][k] = s[k]; ssq[threadIdx.y][threadIdx.x][k] = q[k]; }
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
+        double* out = partials + (size_t)blockIdx.y * 2 * C;
 #pragma unroll
-        for (int j = 1; j < 8; ++j) { s += ssum[j][threadIdx.x]; q += ssq[j][threadIdx.x]; }
-        atomicAdd(&stats[c], s);
-        atomicAdd(&stats[C + c], q);
+        for (int k = 0; k < 4; ++k) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a += ssum[j][threadIdx.x][k]; b += ssq[j][threadIdx.x][k]; }
+            out[c + k] = a; out[C + c + k] = b;
+        }
     }
 }
 
@@ -104,11 +115,17 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ avg_mean, const
     invstd[c] = 1.f / sqrtf(avg_var[c] + eps);
 }
 
-int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid) {
-    AST_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-    const int rpb = std::max(64, cdiv(rows, 148 * 4 / std::max(1, cdiv(C, 32))));
-    dim3 grid(cdiv(C, 32), cdiv(rows, rpb)), block(32, 8);
-    bn_stats_kernel<<<grid, block, 0, st>>>(x, stats, rows, C, seg_rows, seg_valid, rpb);
+int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid, double* partials,
+             int partial_blocks) {
+    AST_CHECK(C % 4 == 0 && partials != nullptr && partial_blocks >= 1, "bn_stats: C %% 4 != 0 or no buffer for the partial sums");
+    const int gx = cdiv(C, 128);
+    int rpb = std::max(32, cdiv(rows, std::max(1, 148 * 4 / gx)));
+    rpb = std::max(rpb, cdiv(rows, partial_blocks));
+    const int gy = cdiv(rows, rpb);
+    dim3 grid(gx, gy), block(32, 8);
+    bn_stats_kernel<<<grid, block, 0, st>>>(x, partials, rows, C, seg_rows, seg_valid, rpb);
+    AST_LAUNCH_OK();
+    bn_partials_sum_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(partials, gy, 2 * C, stats);
     AST_LAUNCH_OK();
     return 0;
 }
@@ -230,8 +247,6 @@ struct DyFromPadded {       // layer 0: dy = da0p[seg][pad + t1][c]
         return *reinterpret_cast<const float4*>(d + ((size_t)seg * S0 + pad + t1) * C + c);
     }
 };
-
-__global__ void bn_partials_sum_kernel(const double* __restrict__ partials, int nblocks, int n, double* __restrict__ stats);
 
 // Both passes walk rows of C contiguous floats with float4 channel vectors: lane x of a (32, 8) block owns channels
 // 4 (32 bx + x) .. + 3, row lane y strides the block's rows, so a warp reads 512 contiguous bytes per row.  The first pass

@@ -666,7 +666,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
                 SkinnyArgs a{};
                 a.X[0] = feed; a.ldx[0] = ldx0; a.K[0] = A; a.W[0] = p.Wo; a.ldw[0] = A; a.bias = p.bo;
                 a.B = B; a.N = p.V; a.epi = EPI_NONE; a.Y = z; a.ldy = Vp;
-                skinny_tile<2, false>(a, tile * SK_COLS, ssm);
+                skinny_tile<2, true>(a, tile * SK_COLS, ssm);      // 3xTF32: the sampled token should be the fp32 argmax of these logits
             }
             const int b = ncta - 1 - cta;                         // CTAs 127, 126, ... take rows 0, 1, ...
             if (b < B) {

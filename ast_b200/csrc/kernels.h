@@ -43,7 +43,8 @@ int gemm_tc3_nt(cudaStream_t st, int M, int N, int K, const float* A, const floa
 // ---- CNN front-end ---------------------------------------------------------------------------
 int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, int Fp, int T1, int kh, int kw, int sh,
             int sw, int ph, int ldc);
-int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid);
+int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid, double* partials,
+             int partial_blocks);
 int bn_finalize(cudaStream_t st, const double* stats, float* mean, float* invstd, float* avg_mean, float* avg_var,
                 int C, double m, float eps, float decay, bool update_running);
 int bn_eval_prepare(cudaStream_t st, const float* avg_mean, const float* avg_var, float* mean, float* invstd, int C,
