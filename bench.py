@@ -422,6 +422,8 @@ def stage_profile(e, opt, resident, torch, peak, n=6):
     fl = step_flops(B, T, L)
     e.set_option("stage_timing", 1)
     acc = {}
+    # rank 0 alone runs this profile: the data-parallel all-reduce hook must not run (the other ranks are not in the collective)
+    hook, opt.pre_update = opt.pre_update, None
     try:
         for it in range(n + 2):
             e.forward_loss(Xd, yd, use_true=bits, noise_sigma=TRAIN_EXTRAS["speech_noise"])
@@ -435,6 +437,7 @@ def stage_profile(e, opt, resident, torch, peak, n=6):
                 acc.setdefault("optimizer", []).append(ev0.elapsed_time(ev1))
     finally:
         e.set_option("stage_timing", 0)
+        opt.pre_update = hook
     med = {k: float(np.median(v)) for k, v in acc.items()}
     Tp, S = fl["Tp"], L - 1
     # (stage mark that ENDS the stage, label, FLOPs, dominant kernel(s), sequence steps of the persistent kernel)
