@@ -5,13 +5,17 @@ TEST INFRASTRUCTURE ONLY.  This module is the parity checker for the CUDA path i
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` and by nothing else.  The
 product path never routes through it.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer files
- and its arithmetic lives in Chainer/CuPy, which are neither
-vendored in /root/reference nor installable here (unpinned ``pip install chainer``,
-2018-era v4/v5).  This file restates the published Chainer semantics (SURVEY.md
-Appendix A) at the reference's own call sites.  The pins are minted by this repo:
-finite differences in float64, a torch-autograd re-expression of the same graph, and
-hand-computed known answers (tests/test_oracle_*.py, tests/golden/).
+PARITY PINNED TO THE REFERENCE'S OWN SOURCE (control flow and data path), op semantics restated.  The reference ships no
+tests, golden vectors or known-answer files and its arithmetic lives in Chainer/CuPy, which are
+neither vendored in /root/reference nor installable here.  oracle/gen_ref_golden.py therefore imports the reference's
+seq2seq.py / nn.py / dataloader.py / config.py / eval.py UNMODIFIED on top of a float64 stand-in for the ~25 Chainer/CuPy names
+they use (oracle/_ref_shim) and records what the reference computes: tests/golden/ref_*.npz (loss, per-step losses, logits,
+encoder states, every gradient, two optimizer steps, BN running statistics, greedy tokens, beam hypotheses, a bucketed epoch).
+tests/test_ref_golden.py checks this oracle against those fixtures to 1e-12 (float64); tests/test_gpu_ref_parity.py checks the
+CUDA path against the same fixtures.  What stays unpinned is the semantics of the Chainer ops themselves (SURVEY.md Appendix
+A: BN running-variance convention, hook order, beam tie order), restated in the stand-in because the library is absent; those
+are additionally covered by finite differences in float64, a torch-autograd re-expression of the same graph and hand-computed
+known answers (tests/test_oracle.py, tests/golden/).
 
 Every function cites the reference file:line it follows.  The execution shape is
 deliberately the one Chainer would run (per-timestep LSTM link calls with separate
