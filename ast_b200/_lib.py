@@ -55,6 +55,7 @@ SIGNATURES = {
     "ast_grad_bucket_wait": (_I, [_P, _I, _P]),
     "ast_get_step_argmax": (_I, [_P, _P, _P]),
     "ast_opt_step": (_I, [_P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _F, C.POINTER(_I), _I, _P]),
+    "ast_opt_step_sgd": (_I, [_P, _F, _F, _F, _F, C.POINTER(_I), _I, _P]),
     "ast_grad_buckets_mark": (_I, [_P, _P]),
     "ast_scale_grads": (_I, [_P, _F, _P]),
     "ast_last_grad_norm": (C.c_double, [_P, _P]),

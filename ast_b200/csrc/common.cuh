@@ -174,6 +174,12 @@ __device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint32_t stream, uint
 __device__ __forceinline__ float rng_uniform(uint64_t seed, uint32_t stream, uint32_t idx) {
     return (rng_u32(seed, stream, idx) >> 8) * (1.0f / 16777216.0f);   // [0,1)
 }
+// N(0, 1) from two counter-RNG draws (Box-Muller); GradientNoise hook
+__device__ __forceinline__ float rng_normal(uint64_t seed, uint32_t stream, uint32_t idx) {
+    const float u1 = ((rng_u32(seed, stream, idx) >> 8) + 1) * (1.0f / 16777216.0f);          // (0, 1]
+    const float u2 = rng_uniform(seed, stream + 1, idx);
+    return sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853071795865f * u2);
+}
 // scaled keep-mask of F.dropout: 0 with prob ratio, else 1/(1-ratio)
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t stream, uint32_t idx, float ratio) {
     if (ratio <= 0.f) return 1.f;

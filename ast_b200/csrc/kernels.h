@@ -198,7 +198,9 @@ struct FrozenRanges { int n; size_t begin[24]; size_t end[24]; };   // merged [b
 int opt_sqnorm(cudaStream_t st, const float* g, const float* p, size_t n, float gscale, float wd, double* norm_sq);
 int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, float* vhat, size_t n, float gscale,
                 float wd, float clip, const double* norm_sq, float alpha_t, float beta1, float beta2, float eps,
-                const FrozenRanges& fr);
+                const FrozenRanges& fr, float noise_sigma = 0.f, unsigned long long noise_seed = 0);
+int opt_sgd(cudaStream_t st, float* p, const float* g, size_t n, float gscale, float wd, float clip, const double* norm_sq, float lr,
+            const FrozenRanges& fr, float noise_sigma = 0.f, unsigned long long noise_seed = 0);
 int pack_cmvn(cudaStream_t st, const float* raw, const long long* row_off, const int* lens, const float* scale,
               const float* offset, const unsigned char* keep, const float* noise, float noise_sigma,
               unsigned long long seed, float* X, int B, int T, int D);

@@ -35,7 +35,7 @@ __global__ void opt_sqnorm_kernel(const float* __restrict__ g, const float* __re
 __global__ void opt_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                    float* __restrict__ v, float* __restrict__ vhat, size_t n, float gscale, float wd,
                                    float clip, const double* __restrict__ norm_sq, float alpha_t, float beta1,
-                                   float beta2, float eps, FrozenRanges fr) {
+                                   float beta2, float eps, FrozenRanges fr, float noise_sigma, unsigned long long noise_seed) {
     const double nrm = sqrt(norm_sq[0]);
     float rate = 1.f;
     if (clip > 0.f && nrm > 0.0) { const double r = (double)clip / nrm; if (r < 1.0) rate = (float)r; }
@@ -47,15 +47,16 @@ __global__ void opt_amsgrad_kernel(float* __restrict__ p, const float* __restric
         float4 pv = reinterpret_cast<float4*>(p)[i];
         const float4 gv = reinterpret_cast<const float4*>(g)[i];
         float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i], hv = reinterpret_cast<float4*>(vhat)[i];
-#define AST_ADAM1(c)                                                      \
+#define AST_ADAM1(c, k)                                                    \
         {                                                                 \
-            const float gg = (gscale * gv.c + wd * pv.c) * rate;          \
+            float gg = (gscale * gv.c + wd * pv.c) * rate;                \
+            if (noise_sigma > 0.f) gg += noise_sigma * rng_normal(noise_seed, 48, (uint32_t)(4 * i + k));      \
             mv.c += (1.f - beta1) * (gg - mv.c);                          \
             vv.c += (1.f - beta2) * (gg * gg - vv.c);                     \
             hv.c = fmaxf(hv.c, vv.c);                                     \
             pv.c -= alpha_t * mv.c / (sqrtf(hv.c) + eps);                 \
         }
-        AST_ADAM1(x) AST_ADAM1(y) AST_ADAM1(z) AST_ADAM1(w)
+        AST_ADAM1(x, 0) AST_ADAM1(y, 1) AST_ADAM1(z, 2) AST_ADAM1(w, 3)
 #undef AST_ADAM1
         reinterpret_cast<float4*>(p)[i] = pv;
         reinterpret_cast<float4*>(m)[i] = mv;
@@ -73,9 +74,38 @@ int opt_sqnorm(cudaStream_t st, const float* g, const float* p, size_t n, float 
 }
 int opt_amsgrad(cudaStream_t st, float* p, const float* g, float* m, float* v, float* vhat, size_t n, float gscale,
                 float wd, float clip, const double* norm_sq, float alpha_t, float beta1, float beta2, float eps,
-                const FrozenRanges& fr) {
+                const FrozenRanges& fr, float noise_sigma, unsigned long long noise_seed) {
     AST_CHECK(n % 4 == 0, "opt_amsgrad: flat size must be a multiple of 4");
-    opt_amsgrad_kernel<<<148 * 4, 256, 0, st>>>(p, g, m, v, vhat, n, gscale, wd, clip, norm_sq, alpha_t, beta1, beta2, eps, fr);
+    opt_amsgrad_kernel<<<148 * 4, 256, 0, st>>>(p, g, m, v, vhat, n, gscale, wd, clip, norm_sq, alpha_t, beta1, beta2, eps, fr, noise_sigma, noise_seed);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
+// optimizers.SGD (nn.py:91-93) behind the same hooks: WeightDecay -> GradientClipping(global norm) -> GradientNoise -> p -= lr * g
+__global__ void opt_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float gscale, float wd, float clip,
+                               const double* __restrict__ norm_sq, float lr, FrozenRanges fr, float noise_sigma, unsigned long long noise_seed) {
+    const double nrm = sqrt(norm_sq[0]);
+    float rate = 1.f;
+    if (clip > 0.f && nrm > 0.0) { const double r = (double)clip / nrm; if (r < 1.0) rate = (float)r; }
+    const size_t n4 = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        bool frozen = false;
+        for (int k = 0; k < fr.n; ++k) frozen |= (i * 4 >= fr.begin[k] && i * 4 < fr.end[k]);
+        if (frozen) continue;
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        float gg[4] = {(gscale * gv.x + wd * pv.x) * rate, (gscale * gv.y + wd * pv.y) * rate, (gscale * gv.z + wd * pv.z) * rate, (gscale * gv.w + wd * pv.w) * rate};
+        if (noise_sigma > 0.f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gg[c] += noise_sigma * rng_normal(noise_seed, 48, (uint32_t)(4 * i + c));
+        pv.x -= lr * gg[0]; pv.y -= lr * gg[1]; pv.z -= lr * gg[2]; pv.w -= lr * gg[3];
+        reinterpret_cast<float4*>(p)[i] = pv;
+    }
+}
+int opt_sgd(cudaStream_t st, float* p, const float* g, size_t n, float gscale, float wd, float clip, const double* norm_sq, float lr,
+            const FrozenRanges& fr, float noise_sigma, unsigned long long noise_seed) {
+    AST_CHECK(n % 4 == 0, "opt_sgd: flat size must be a multiple of 4");
+    opt_sgd_kernel<<<148 * 4, 256, 0, st>>>(p, g, n, gscale, wd, clip, norm_sq, lr, fr, noise_sigma, noise_seed);
     AST_LAUNCH_OK();
     return 0;
 }

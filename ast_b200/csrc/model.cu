@@ -111,6 +111,7 @@ struct ast_model {
     float *WoT, *WcT, *WaT, *WcatT[MAXL];
     float *loss_dev;
     unsigned long long *dec_prof;      // [2][4096] phase-timing probe of the decoder-sequence kernels (option dec_prof)
+    float grad_noise_sigma = 0.f; unsigned long long grad_noise_step = 0;      // GradientNoise hook (nn.py:107-110): sigma of the NEXT update
     int dec_prof_on = 0, dec_fast_barrier = 1, dec_sync = 0;      // dec_sync: grid barrier after every phase of dec_seq2 (debugging)
     unsigned* dec_bar;
     // decode-time state (greedy / beam / decode_step): two banks
@@ -134,7 +135,7 @@ struct ast_model {
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
     unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 7;      // bit 0: 2-CTA GEMM for large K-major-A problems, 1: for weight gradients, 2: grouped weight gradients
     bool queues_ok = false, eager_loading = false, last_fwd_persistent = false; int num_sms = 0;     // residency guards of the spin-wait schedule (persist_allowed)
-    unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
+    unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16, enc_l0dx_ctas = 8;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -478,7 +479,7 @@ static bool persist_allowed(const ast_model* m, bool backward, int B, int warm) 
     const int csz = lstm_seq_tc_cluster_size();
     const int clusters_per_layer = 2 * ((B + 15) / 16);
     const int spin_ctas = m->NL * clusters_per_layer * csz;
-    const int gemm_ctas = 2 * (m->NL - 1) * (backward ? m->enc_gemm_ctas_bwd : m->enc_gemm_ctas);
+    const int gemm_ctas = 2 * (m->NL - 1) * (backward ? m->enc_gemm_ctas_bwd : m->enc_gemm_ctas) + (backward ? 2 * m->enc_l0dx_ctas : 0);
     if (lstm_seq_tc_max_clusters(backward) < m->NL * clusters_per_layer) return false;
     if (spin_ctas + gemm_ctas > m->num_sms) return false;
     return true;
@@ -1203,11 +1204,15 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         unsigned* done = m->enc_flags;
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         cudaEvent_t* ev = m->ev_pool;
+        // layer 0's data gradient (N = 1536: a third of the encoder's backward GEMM FLOPs, needed only by the CNN backward) as a
+        // gated GEMM beside the recurrences as well, on a few CTAs per direction: it finishes about one chunk after layer 0's
+        // recurrence instead of occupying the whole GPU for ~100 us between the encoder and the CNN backward
+        const bool l0gate = m->enc_l0dx_ctas > 0;
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int l = 0; l < NL; ++l) {
             AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
-            if (l > 0) { AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0)); AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0)); }
+            if (l > 0 || l0gate) { AST_CUDA_OK(cudaStreamWaitEvent(m->layg[l], ev[0], 0)); AST_CUDA_OK(cudaStreamWaitEvent(m->layh[l], ev[0], 0)); }
         }
         int ncta = 0;
         for (int l = NL - 1; l >= 0; --l) {
@@ -1217,29 +1222,30 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                     ch.c[d].tile_ready = tiles + (size_t)((l + 1) * 2 + d) * MAXT;
                     ch.c[d].tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(m->in_enc(l + 1));
                 }
-            const LstmGate gate{l > 0 ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)(MAXL + l) * MAXQ : nullptr};
+            const LstmGate gate{(l > 0 || l0gate) ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)(MAXL + l) * MAXQ : nullptr};
             AST_TRY(lstm_seq_bwd_gated(m->lay[l], ch, 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
             AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));       // layer l's dG complete
         }
-        for (int l = NL - 1; l >= 1; --l)
+        for (int l = NL - 1; l >= (l0gate ? 0 : 1); --l)
             for (int d = 0; d < 2; ++d) {
                 const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
                 const int in = m->in_enc(l);
-                const TcGate tg{done + (size_t)l * MAXQ, (unsigned)ncta, B, PCH, Tp, true, tiles + (size_t)(l * 2 + d) * MAXT};
+                float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
+                const TcGate tg{done + (size_t)l * MAXQ, (unsigned)ncta, B, PCH, Tp, true, l > 0 ? tiles + (size_t)(l * 2 + d) * MAXT : nullptr};
                 const int r = gemm_tc_gated(d == 0 ? m->layg[l] : m->layh[l], false, Tp * B, in, 4 * h, m->Genc[l][d], 4 * h,
-                                            m->p((ln + "/upward/W").c_str()), in, m->dHd[l - 1][d], in, nullptr, tg, m->enc_gemm_ctas_bwd);
+                                            m->p((ln + "/upward/W").c_str()), in, dx, in, nullptr, tg, l > 0 ? m->enc_gemm_ctas_bwd : m->enc_l0dx_ctas);
                 AST_CHECK(r == 0, "persistent wavefront: the gated dx GEMM rejected its operands");
             }
         for (int l = NL - 1; l >= 0; --l) {
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
-            if (l > 0) {
+            if (l > 0 || l0gate) {
                 AST_CUDA_OK(cudaEventRecord(ev[1 + MAXL + l], m->layg[l]));
                 AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + MAXL + l], 0));
                 AST_CUDA_OK(cudaEventRecord(ev[1 + 2 * MAXL + l], m->layh[l]));
                 AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + 2 * MAXL + l], 0));
             }
         }
-        AST_TRY(bwd_dx_rows(0, 0, Tp, st));
+        if (!l0gate) AST_TRY(bwd_dx_rows(0, 0, Tp, st));
         for (int l = NL - 1; l >= 0; --l) {
             if (sw != st) AST_CUDA_OK(cudaStreamWaitEvent(sw, ev[1 + l], 0));
             AST_TRY(enc_wgrads(l));
@@ -1471,7 +1477,8 @@ int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, in
 }
 
 int ast_set_option(ast_model* m, const char* key, double value) {
-    if (strcmp(key, "seed") && strncmp(key, "enc_", 4) && strcmp(key, "stage_timing")) m->warm_fwd = m->warm_bwd = 0;   // other kernels may run now
+    if (strcmp(key, "seed") && strncmp(key, "enc_", 4) && strcmp(key, "stage_timing") && strcmp(key, "grad_noise_sigma"))
+        m->warm_fwd = m->warm_bwd = 0;   // other kernels may run now
     if (!strcmp(key, "exact")) m->exact = value != 0;
     else if (!strcmp(key, "tc_gemm")) m->tc_gemm = value != 0;
     else if (!strcmp(key, "tc_mask")) m->tc_mask = (unsigned)value;
@@ -1499,6 +1506,8 @@ int ast_set_option(ast_model* m, const char* key, double value) {
     else if (!strcmp(key, "enc_side_ctas")) m->enc_side_ctas = (int)value;
     else if (!strcmp(key, "dec_fast_barrier")) m->dec_fast_barrier = value != 0;
     else if (!strcmp(key, "dec_sync")) m->dec_sync = value != 0;
+    else if (!strcmp(key, "grad_noise_sigma")) m->grad_noise_sigma = (float)value;
+    else if (!strcmp(key, "enc_l0dx_ctas")) m->enc_l0dx_ctas = (int)value;
     else if (!strcmp(key, "seed")) { m->seed = (unsigned long long)value; m->step_counter = 0; }
     else { ast::set_last_error("unknown option '%s'", key); return -1; }
     return 0;
@@ -1511,6 +1520,9 @@ double ast_get_option(const ast_model* m, const char* key) {
     if (!strcmp(key, "enc_persist")) return m->enc_persist;
     if (!strcmp(key, "beam_tc")) return m->beam_tc;
     if (!strcmp(key, "enc_persist_active")) return m->last_fwd_persistent ? 1 : 0;       // did the last training forward use the spin-wait schedule?
+    if (!strcmp(key, "enc_max_clusters_fwd")) return lstm_seq_tc_max_clusters(false);      // co-resident 8-CTA clusters this GPU can hold
+    if (!strcmp(key, "enc_max_clusters_bwd")) return lstm_seq_tc_max_clusters(true);
+    if (!strcmp(key, "num_sms")) return m->num_sms;
     if (!strcmp(key, "eager_loading")) return m->eager_loading ? 1 : 0;
     if (!strcmp(key, "queues_ok")) return m->queues_ok ? 1 : 0;
     if (!strcmp(key, "live_models")) return g_live_models[m->device & 63].load();
@@ -1595,7 +1607,31 @@ int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr
     const float alpha_t = (float)(lr * sqrt(fix2) / fix1);
     cudaStream_t st = S_(stream);
     AST_TRY(opt_sqnorm(st, m->G, m->P, (size_t)m->nfloats, grad_scale, l2, m->norm_sq));
-    AST_TRY(opt_amsgrad(st, m->P, m->G, m1, v, vhat, (size_t)m->nfloats, grad_scale, l2, clip, m->norm_sq, alpha_t, beta1, beta2, eps, fr));
+    AST_TRY(opt_amsgrad(st, m->P, m->G, m1, v, vhat, (size_t)m->nfloats, grad_scale, l2, clip, m->norm_sq, alpha_t, beta1, beta2, eps, fr,
+                        m->grad_noise_sigma, m->seed ^ (0xA24BAED4963EE407ULL * (++m->grad_noise_step))));
+    m->weights_dirty = true;
+    return 0;
+}
+// optimizers.SGD(lr) (nn.py:91-93) with the same hooks (WeightDecay -> GradientClipping -> GradientNoise) and freeze list
+int ast_opt_step_sgd(ast_model* m, float lr, float l2, float clip, float grad_scale, const int* frozen_idx, int n_frozen, void* stream) {
+    AST_CHECK(m->P && m->G && !m->ws.dry, "opt_step_sgd: params/workspace not bound");
+    std::vector<std::pair<size_t, size_t>> rng;
+    for (int i = 0; i < n_frozen; ++i) {
+        AST_CHECK(frozen_idx[i] >= 0 && frozen_idx[i] < (int)m->pinfo.size(), "opt_step_sgd: bad frozen index");
+        const ParamInfo& pi = m->pinfo[frozen_idx[i]];
+        rng.emplace_back((size_t)pi.off, align_up((size_t)(pi.off + pi.count), 64));
+    }
+    std::sort(rng.begin(), rng.end());
+    FrozenRanges fr{}; fr.n = 0;
+    for (const auto& r : rng) {
+        if (fr.n > 0 && r.first <= fr.end[fr.n - 1]) { fr.end[fr.n - 1] = std::max(fr.end[fr.n - 1], r.second); continue; }
+        AST_CHECK(fr.n < 24, "opt_step_sgd: more than 24 disjoint frozen ranges");
+        fr.begin[fr.n] = r.first; fr.end[fr.n] = r.second; ++fr.n;
+    }
+    cudaStream_t st = S_(stream);
+    AST_TRY(opt_sqnorm(st, m->G, m->P, (size_t)m->nfloats, grad_scale, l2, m->norm_sq));
+    AST_TRY(opt_sgd(st, m->P, m->G, (size_t)m->nfloats, grad_scale, l2, clip, m->norm_sq, lr, fr, m->grad_noise_sigma,
+                    m->seed ^ (0xA24BAED4963EE407ULL * (++m->grad_noise_step))));
     m->weights_dirty = true;
     return 0;
 }

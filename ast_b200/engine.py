@@ -233,6 +233,13 @@ class Engine:
         check(self.lib.ast_opt_step(self.h, ptr(m), ptr(v), ptr(vhat), int(t), lr, l2, clip, beta1, beta2, eps, grad_scale,
                                     arr, len(idx), self.stream()), "ast_opt_step")
 
+    def opt_step_sgd(self, lr, l2, clip, grad_scale=1.0, frozen=()):
+        """optimizers.SGD(lr).update() behind the WeightDecay / GradientClipping (/ GradientNoise) hooks (nn.py:91-110)."""
+        idx = [self.info[n][0] for n in frozen]
+        arr = (C.c_int * max(len(idx), 1))(*idx)
+        self.ensure_workspace()
+        check(self.lib.ast_opt_step_sgd(self.h, lr, l2, clip, grad_scale, arr, len(idx), self.stream()), "ast_opt_step_sgd")
+
     def scale_grads(self, weight):
         """grads *= weight, then re-arm the bucket events so a gated all-reduce sees the scaled values."""
         check(self.lib.ast_scale_grads(self.h, float(weight), self.stream()), "ast_scale_grads")

@@ -53,21 +53,17 @@ class GradientNoise:
         self.eta = eta
 
 
-class Adam:
-    """optimizers.Adam(alpha, beta1, beta2, eps, amsgrad=True) as one fused multi-tensor kernel over the
-    flat parameter buffer: WeightDecay -> GradientClipping (global L2 norm, computed on device, no host
-    sync) -> AMSGrad.  ``grad_scale`` is 1/world_size under data parallelism."""
+class _GradientMethod:
+    """Shared hook handling of the two update rules (chainer.optimizer.GradientMethod): hooks run before the update in the
+    order they were added (WeightDecay, GradientClipping, GradientNoise: nn.py:98-110); ``t`` counts updates."""
 
-    def __init__(self, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, amsgrad=True):
-        if not amsgrad:
-            raise NotImplementedError("the reference always sets amsgrad=True (nn.py:89)")
-        self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
+    def __init__(self):
         self.t = 0
         self.l2 = 0.0
         self.clip = 0.0
+        self.noise_eta = 0.0
         self.grad_scale = 1.0
         self.target = None
-        self._m = self._v = self._vhat = None
         self.pre_update = None        # e.g. the data-parallel all-reduce
 
     def setup(self, model):
@@ -80,15 +76,9 @@ class Adam:
         elif isinstance(hook, GradientClipping):
             self.clip = float(hook.threshold)
         elif isinstance(hook, GradientNoise):
-            raise NotImplementedError("GradientNoise (grad_noise_eta > 0) is not supported; 0 in every shipped config")
+            self.noise_eta = float(hook.eta)
         else:
             raise TypeError(f"unknown hook {hook!r}")
-
-    def _state(self, e):
-        if self._m is None:
-            self._m = torch.zeros_like(e.params)
-            self._v = torch.zeros_like(e.params)
-            self._vhat = torch.zeros_like(e.params)
 
     def frozen(self):
         out = []
@@ -97,19 +87,54 @@ class Adam:
                 out += link.param_keys()
         return out
 
+    def _pre(self, e):
+        if self.pre_update is not None:
+            self.pre_update()
+        # chainer.optimizer_hooks.GradientNoise: N(0, eta / (1 + t)^0.55) per element, t = updates made so far
+        sigma = (self.noise_eta / (1.0 + self.t) ** 0.55) ** 0.5 if self.noise_eta > 0 else 0.0
+        if sigma != getattr(e, "_grad_noise_sigma", 0.0):          # nothing to tell the library on the usual (noise-free) path
+            e.set_option("grad_noise_sigma", sigma)
+            e._grad_noise_sigma = sigma
+        self.t += 1
+
+
+class Adam(_GradientMethod):
+    """optimizers.Adam(alpha, beta1, beta2, eps, amsgrad=True) as one fused multi-tensor kernel over the
+    flat parameter buffer: WeightDecay -> GradientClipping (global L2 norm, computed on device, no host
+    sync) -> GradientNoise -> AMSGrad.  ``grad_scale`` is 1/world_size under data parallelism."""
+
+    def __init__(self, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, amsgrad=True):
+        if not amsgrad:
+            raise NotImplementedError("the reference always sets amsgrad=True (nn.py:89)")
+        super().__init__()
+        self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
+        self._m = self._v = self._vhat = None
+
+    def _state(self, e):
+        if self._m is None:
+            self._m = torch.zeros_like(e.params)
+            self._v = torch.zeros_like(e.params)
+            self._vhat = torch.zeros_like(e.params)
+
     def update(self):
         e = self.target._require()
         self._state(e)
-        if self.pre_update is not None:
-            self.pre_update()
-        self.t += 1
+        self._pre(e)
         e.opt_step(self._m, self._v, self._vhat, self.t, self.alpha, self.l2, self.clip, self.beta1, self.beta2, self.eps,
                    self.grad_scale, self.frozen())
 
 
-class SGD:
+class SGD(_GradientMethod):
+    """optimizers.SGD(lr) (nn.py:91-93, optimizer.type = 1): p -= lr * g behind the same hooks, one fused pass."""
+
     def __init__(self, lr=0.01):
-        raise NotImplementedError("optimizer.type=1 (SGD) is outside the hot path; every shipped config uses Adam (type 0)")
+        super().__init__()
+        self.lr = lr
+
+    def update(self):
+        e = self.target._require()
+        self._pre(e)
+        e.opt_step_sgd(self.lr, self.l2, self.clip, self.grad_scale, self.frozen())
 
 
 def _backtrack(hp, hk, ns):

@@ -756,7 +756,14 @@ def run_ours(args):
                                "fwd + bwd + WD/clip/AMSGrad; dropout .3/.3, speech_noise .25, teach_ratio .8, zero_input .1",
                    "global_batch": BATCH * world, "parallelism": f"dp{world}", "grad_allreduce": ("3 buckets overlapped with backward" if not args.no_allreduce_overlap else "3 buckets after backward") if world > 1 else "none", "l2_flush_between_steps": True,
                    "frames_counted": "true (unpadded, post-truncation) input frames",
-                   "wall_ms_per_step_incl_flush": 1e3 * t_wall / K},
+                   "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+                   # which encoder schedule this box allowed (persistent spin-wait wavefront needs 12 co-resident 8-CTA clusters;
+                   # a GPU whose GPCs cannot hold them falls back to per-chunk launches, ~0.4 ms per step slower)
+                   "encoder_schedule": {"persistent_wavefront": bool(e.get_option("enc_persist_active") == 1),
+                                        "max_clusters_fwd": int(e.get_option("enc_max_clusters_fwd")),
+                                        "max_clusters_bwd": int(e.get_option("enc_max_clusters_bwd")),
+                                        "queues_ok": int(e.get_option("queues_ok")), "live_models": int(e.get_option("live_models")),
+                                        "eager_loading": int(e.get_option("eager_loading")), "sms": int(e.get_option("num_sms"))}},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K},
         "gpu_launches": launches,
         "clocks": clk,

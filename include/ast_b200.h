@@ -92,6 +92,12 @@ int ast_get_step_argmax(ast_model* m, int* out, void* stream);
 int ast_opt_step(ast_model* m, float* m1, float* v, float* vhat, int t, float lr, float l2, float clip,
                  float beta1, float beta2, float eps, float grad_scale, const int* frozen_idx, int n_frozen,
                  void* stream);
+/* optimizers.SGD(lr) (nn.py:91-93, optimizer.type = 1) behind the same hooks: WeightDecay -> GradientClipping(global L2) -> p -= lr * g.
+ * The GradientNoise hook (nn.py:107-110, grad_noise_eta > 0) applies to both update rules: ast_set_option(m, "grad_noise_sigma", s)
+ * sets the standard deviation of the N(0, s^2) noise added to every (clipped) gradient element at the NEXT update
+ * (Chainer: s = sqrt(eta / (1 + t)^0.55), t = updates made so far); device counter RNG, a fresh stream per update. */
+int ast_opt_step_sgd(ast_model* m, float lr, float l2, float clip, float grad_scale, const int* frozen_idx, int n_frozen,
+                     void* stream);
 /* re-record all bucket events on `stream`: the gradients were modified after ast_backward (ast_scale_grads) or no backward ran this
  * step (empty shard), so a collective gated on ast_grad_bucket_wait must wait for work enqueued on `stream` up to here */
 int ast_grad_buckets_mark(ast_model* m, void* stream);

@@ -634,3 +634,52 @@ def test_nn_runtime_trains_on_synthetic_corpus(dev, tmp_path):
     serializers.save_npz(str(tmp_path / "seq2seq_7.model"), nn.model)
     nn2 = NN(str(tmp_path), feat_dim=40, data_loader=loader, cfg=Cfg)
     assert nn2.max_epoch == 7 and torch.equal(nn2.model.out.W.data, nn.model.out.W.data)
+
+
+def test_sgd_update_rule_and_gradient_noise_hook(dev):
+    """optimizer.type = 1 (nn.py:91-93) and grad_noise_eta > 0 (nn.py:107-110): SGD behind WeightDecay -> GradientClipping equals
+    p - lr * clip(g + l2 p) computed on the host from the device's own gradients; the GradientNoise hook adds N(0, sigma^2) with
+    Chainer's schedule sigma^2 = eta / (1 + t)^0.55 to every unfrozen element (both update rules), a fresh draw per update."""
+    from ast_b200.nn import SGD, Adam, WeightDecay, GradientClipping, GradientNoise
+    cfg = O.default_model_cfg(vocab=120)
+    P = _perturbed(cfg, 40, 71)
+    X, y, _ = O.synth_batch(5, 120, 40, 120, 4, 7, seed=72, Tmin=90)
+    e = _engine(cfg, 40, P)
+    e.forward_loss(X, y); e.backward(); torch.cuda.synchronize()
+    p0 = e.params.clone(); g0 = e.grads.clone()
+    lr, l2, clip = 0.05, 1e-3, 2.0
+    e.opt_step_sgd(lr, l2, clip, 1.0, frozen=["context/W"])
+    gg = g0.double() + l2 * p0.double()
+    nrm = float(gg.norm())
+    assert abs(e.last_grad_norm() - nrm) <= 1e-5 * nrm
+    want = p0.double() - lr * gg * min(1.0, clip / nrm)
+    off, cnt = e.info["context/W"][1], int(np.prod(e.info["context/W"][2]))
+    want[off:off + cnt] = p0.double()[off:off + cnt]                                   # frozen link: untouched
+    assert float((e.params.double() - want).abs().max()) < 1e-6
+    # GradientNoise through the drop-in optimizer objects: the difference between a noisy and a noise-free update is -lr * noise
+    class _M:                                                                         # minimal `target` for the optimizer objects
+        _links = {}
+        def _require(self, *a): return e
+    for t_before, eta in ((0, 0.3), (1, 0.3)):
+        e.params.copy_(p0); e.grads.copy_(g0)
+        plain = SGD(lr); plain.setup(_M()); plain.add_hook(WeightDecay(l2)); plain.add_hook(GradientClipping(clip)); plain.t = t_before
+        plain.update()
+        p_plain = e.params.clone()
+        e.params.copy_(p0); e.grads.copy_(g0)
+        noisy = SGD(lr); noisy.setup(_M()); noisy.add_hook(WeightDecay(l2)); noisy.add_hook(GradientClipping(clip)); noisy.add_hook(GradientNoise(eta)); noisy.t = t_before
+        noisy.update()
+        noise = ((p_plain - e.params) / lr).double()
+        noise = noise[: sum(int(np.prod(v[2])) for v in e.info.values())]
+        sigma = (eta / (1.0 + t_before) ** 0.55) ** 0.5
+        used = torch.cat([noise[v[1]:v[1] + int(np.prod(v[2]))] for v in e.info.values()])
+        assert abs(float(used.mean())) < 5 * sigma / used.numel() ** 0.5 + 1e-4
+        assert abs(float(used.std()) - sigma) < 0.01 * sigma + 1e-4, (float(used.std()), sigma)
+    # AMSGrad with the hook: runs, changes the update, and the next update draws different noise
+    m, v, vh = (torch.zeros_like(e.params) for _ in range(3))
+    e.params.copy_(p0); e.grads.copy_(g0)
+    e.set_option("grad_noise_sigma", 0.5); e.opt_step(m, v, vh, 1, 1e-3, 1e-4, 2.0)
+    a = e.params.clone()
+    m.zero_(); v.zero_(); vh.zero_(); e.params.copy_(p0); e.grads.copy_(g0)
+    e.opt_step(m, v, vh, 1, 1e-3, 1e-4, 2.0)
+    assert float((a - e.params).abs().max()) > 0
+    e.set_option("grad_noise_sigma", 0.0)
