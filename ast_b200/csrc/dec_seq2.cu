@@ -49,20 +49,23 @@ constexpr int D2_H = 512, D2_E = 128, D2_A = 512;
 constexpr int D2_XLD = 320 + 16;         // smem row stride of the staged activations (= 16 mod 32: conflict-free ld.shared.v4)
 constexpr int D2_WLD = 256 + 16;         // smem row stride of the context weights
 constexpr int D2_TCOL0 = 0, D2_TCOL1 = 80, D2_TCOL2 = 144;   // TMEM column of each layer's fragments (5 + 4 + 4 blocks of 16)
-constexpr int D2_RECV = 16 * 32 * 16;                        // floats of one exchange buffer: [src 16][row 32][16 cols] (backward D: [32][32][8])
-constexpr uint32_t D2_XBYTES = D2_RECV * 4;
+constexpr int D2_RECV = 4 * 32 * 16;                         // floats of one exchange buffer: [src CTA 4][row 32][16 cols] (backward D: [4][32][8])
+constexpr uint32_t D2_XBYTES = D2_RECV * 4;                  // bytes a CTA receives per exchange (backward D phases: half of it)
+constexpr int D2_PLD16 = 64 + 8, D2_PLD32 = 32 + 8;          // row strides of the in-CTA partial-sum buffer (conflict-free 64-bit stores)
+constexpr int D2_PART = 8 * 32 * D2_PLD32;                   // floats: max(4 k-slices x 32 x 72, 8 k-slices x 32 x 40)
 constexpr uint32_t D2_ABYTES = 4 * 128 * 4 + 4 * 8;          // attention exchange: [src][128 cols] + [src](max, sum)
 
 struct D2Smem {
     float Xs[32 * D2_XLD];               // staged operand; during the attention phase: scores of the local t range (T'/4 <= 2048)
     float recv[2][D2_RECV];              // ring of 2: a peer may send exchange k+1 while this CTA still reads exchange k
+    float part[D2_PART];                 // the warps' K-partial tiles, added up in the CTA before they cross the cluster
     float Wcs[64 * D2_WLD];
     float h2s[D2_H];
     float cvw[8 * D2_H];
     float cvx[4 * 128];
     float statx[4 * 2];
     float wstat[8 * 2];
-    uint64_t mbar_x, mbar_a;
+    uint64_t mbar_x[2], mbar_a;          // mbar_x[i] belongs to recv[i]: bytes of exchange k+1 can never be counted into exchange k
     uint32_t tmem_slot;
 };
 
@@ -264,31 +267,71 @@ __device__ __forceinline__ void mma_run_smem(float (&acc)[2][4][4], uint32_t xa,
     }
 }
 
-// reduce-scatter of the 16 K-partial 32 x 64 products of a cluster (4 CTAs x 4 k-slices): warp (kh, nh) holds n-tiles
-// 4 nh .. 4 nh + 3; n-tile j belongs to CTA j / 2.  Receiver layout [src = 4 rank + kh][row][16 cols].
-__device__ __forceinline__ void exchange16(const float (&acc)[2][4][4], uint32_t recv_sa, uint32_t mbar_sa, int rank, int kh, int nh) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int src = 4 * rank + kh;
+__device__ __forceinline__ void sts64(uint32_t sa, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(a), "f"(b) : "memory");
+}
+// Reduce-scatter of a cluster's K-partial 32 x 64 products.  The four k-slice warps of a CTA first add their tiles in shared
+// memory (st.shared.v2 of the accumulator fragments, one barrier, 8 ld.shared.v4 per thread), then every thread sends its 8 sums
+// (two 16-byte st.async) to the CTAs that own those columns: 8 KB cross the cluster per CTA instead of the 32 KB of sending all
+// 16 partial tiles (the DSMEM path moves ~32 B/clk: 0.8 us per exchange, measured) and the receiver adds 4 sources, not 16.
+// Must be called by all threads (contains a __syncthreads).  Receiver layout [src CTA][row][16 cols]; n-tile j belongs to CTA j / 2.
+__device__ __forceinline__ void exchange16(const float (&acc)[2][4][4], uint32_t part_sa, uint32_t recv_sa, uint32_t mbar_sa, int rank, int kh, int nh) {
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(D2_XBYTES) : "memory");
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const int gnt = 4 * nh + nt, dst = gnt >> 1, col = 8 * (gnt & 1) + 2 * q;
-        const uint32_t base = mapa(recv_sa, dst), bar = mapa(mbar_sa, dst);
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-            const int r0 = 16 * mt + g;
-            st_async_v2(base + (uint32_t)(((src * 32 + r0) * 16 + col) * 4), make_float2(acc[mt][nt][0], acc[mt][nt][1]), bar);
-            st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 16 + col) * 4), make_float2(acc[mt][nt][2], acc[mt][nt][3]), bar);
+            const uint32_t a = part_sa + (uint32_t)(((kh * 32 + 16 * mt + g) * D2_PLD16 + 32 * nh + 8 * nt + 2 * q) * 4);
+            sts64(a, acc[mt][nt][0], acc[mt][nt][1]);
+            sts64(a + 8 * D2_PLD16 * 4, acc[mt][nt][2], acc[mt][nt][3]);
         }
+    __syncthreads();
+    const int row = tid >> 3, c = tid & 7;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 r = lds128(part_sa + (uint32_t)(((k * 32 + row) * D2_PLD16 + 32 * hf + 4 * c) * 4));
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        const int col = 32 * hf + 4 * c, dst = col >> 4;
+        st_async_v4(mapa(recv_sa, dst) + (uint32_t)(((rank * 32 + row) * 16 + (col & 15)) * 4), v, mapa(mbar_sa, dst));
     }
 }
-// sum of the 16 partial float4s of (row, 4 columns c4)
-__device__ __forceinline__ float4 recv_sum16(uint32_t recv_sa, int row, int c4, float4 v) {
+// sum of the 4 CTAs' float4s of (row, 4 columns c4)
+__device__ __forceinline__ float4 recv_sum4(uint32_t recv_sa, int row, int c4, float4 v) {
 #pragma unroll
-    for (int src = 0; src < 16; ++src) {
+    for (int src = 0; src < 4; ++src) {
         const float4 r = lds128(recv_sa + (uint32_t)(((src * 32 + row) * 16 + 4 * c4) * 4));
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     return v;
+}
+// backward D phases: every warp holds the CTA's whole 32 x 32 output tile for its 64-wide k slice; the 8 tiles are added in shared
+// memory, each thread sends 4 sums to the CTA that owns those columns (n-tile j belongs to CTA j).  Receiver layout [src CTA][row][8].
+__device__ __forceinline__ void exchange32(const float (&acc)[2][4][4], uint32_t part_sa, uint32_t recv_sa, uint32_t mbar_sa, int rank, int w) {
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(D2_XBYTES / 2) : "memory");
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t a = part_sa + (uint32_t)(((w * 32 + 16 * mt + g) * D2_PLD32 + 8 * nt + 2 * q) * 4);
+            sts64(a, acc[mt][nt][0], acc[mt][nt][1]);
+            sts64(a + 8 * D2_PLD32 * 4, acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    __syncthreads();
+    const int row = tid >> 3, c = tid & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 r = lds128(part_sa + (uint32_t)(((k * 32 + row) * D2_PLD32 + 4 * c) * 4));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    const int dst = c >> 1;
+    st_async_v4(mapa(recv_sa, dst) + (uint32_t)(((rank * 32 + row) * 8 + 4 * (c & 1)) * 4), v, mapa(mbar_sa, dst));
 }
 
 }  // namespace
@@ -340,7 +383,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
     // ---- one-time setup ------------------------------------------------------------------------------------------
     if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[4090] = gtimer2();
     if (tid == 0) {
-        mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
+        mbar_init(&sm.mbar_x[0], 1); mbar_init(&sm.mbar_x[1], 1); mbar_init(&sm.mbar_a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 0) {
@@ -415,7 +458,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
         creg0 = p.Cd[0][(size_t)e_row * H + e_unit]; creg1 = p.Cd[1][(size_t)e_row * H + e_unit]; creg2 = p.Cd[2][(size_t)e_row * H + e_unit];
     }
     uint32_t par_x = 0, par_a = 0;
-    if (tid == 0) { mbar_expect_tx(&sm.mbar_x, D2_XBYTES); mbar_expect_tx(&sm.mbar_a, D2_ABYTES); }
+    if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);        // mbar_x is armed by each exchange itself (its byte count differs by phase)
     if (p.prof && cta == 0 && tid == 0) p.prof[1] = gtimer2();
     nprof = 1;
     cluster_sync_all();
@@ -424,9 +467,10 @@ dec_seq2_fwd_kernel(DecSeq p) {
     const uint32_t xrow8 = 8 * D2_XLD * 4, wrow8 = 8 * D2_WLD * 4;
     const uint32_t xa_g = saddr(sm.Xs) + (uint32_t)((g * D2_XLD + 4 * q) * 4);                 // + 64 * block
     const uint32_t wa_g = saddr(sm.Wcs) + (uint32_t)(((8 * 4 * nh + g) * D2_WLD + 4 * q) * 4);
-    const uint32_t recv_sa0 = saddr(sm.recv[0]);
+    const uint32_t recv_sa0 = saddr(sm.recv[0]), part_sa = saddr(sm.part);
 #define RECV_SA(b_) (recv_sa0 + (uint32_t)(b_) * D2_XBYTES)
-    const uint32_t mbx_sa = saddr(&sm.mbar_x);
+    const uint32_t mbx_sa0 = saddr(&sm.mbar_x[0]);
+#define MBX_SA(b_) (mbx_sa0 + 8u * (uint32_t)(b_))
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
     int xbuf = 0;
     for (int s = 0; s < S; ++s) {
@@ -469,18 +513,17 @@ dec_seq2_fwd_kernel(DecSeq p) {
             __syncthreads();
             mma_run_tmem<2>(acc, xa_g + 64 * (2 * kh), xrow8, tmem_lane + tcol + 16 * nnc, bfr);
             D2_FINE(s);
-            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
+            exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
             const size_t e = (size_t)e_row * H + e_unit;
             float4 gs = make_float4(0.f, 0.f, 0.f, 0.f); float dm = 1.f;
             if (own) {     // while the exchange is in flight
                 gs = __ldg(reinterpret_cast<const float4*>(p.bup[l] + 4 * e_unit));
                 dm = dropout_scale(p.seed, 16 + l, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
             }
-            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            mbar_wait(&sm.mbar_x[xbuf], (par_x >> xbuf) & 1u); par_x ^= 1u << xbuf;
             D2_FINE(s);
-            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (own) {
-                gs = recv_sum16(RECV_SA(xbuf), e_row, e_ul, gs);
+                gs = recv_sum4(RECV_SA(xbuf), e_row, e_ul, gs);
                 const float ga = ftanh(gs.x), gi = fsig(gs.y), gf = fsig(gs.z), go = fsig(gs.w);
                 const float c = ga * gi + gf * (l == 0 ? creg0 : (l == 1 ? creg1 : creg2));
                 if (l == 0) creg0 = c; else if (l == 1) creg1 = c; else creg2 = c;
@@ -624,15 +667,14 @@ dec_seq2_fwd_kernel(DecSeq p) {
             __syncthreads();
             mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, wa_g + 64 * (2 * kh), wrow8);
             D2_FINE(s);
-            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
+            exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
             const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (own) v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
-            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            mbar_wait(&sm.mbar_x[xbuf], (par_x >> xbuf) & 1u); par_x ^= 1u << xbuf;
             D2_FINE(s);
-            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (own) {
-                v = recv_sum16(RECV_SA(xbuf), e_row, e_ul, v);
+                v = recv_sum4(RECV_SA(xbuf), e_row, e_ul, v);
                 v.x = ftanh(v.x); v.y = ftanh(v.y); v.z = ftanh(v.z); v.w = ftanh(v.w);
                 if (s + 1 < S) st_pub4(p.x0 + ((size_t)(s + 1) * B + e_row) * ldx0 + E + n0, v);
                 *reinterpret_cast<float4*>(p.ht + ((size_t)s * B + e_row) * A + n0) = v;
@@ -693,6 +735,7 @@ dec_seq2_fwd_kernel(DecSeq p) {
 #undef D2_PHASE_END
 #undef D2_FINE
 #undef RECV_SA
+#undef MBX_SA
 }
 
 
@@ -721,6 +764,7 @@ constexpr int B2_WLD = 128 + 16;         // context / attention weight slices: 6
 struct B2Smem {
     float Xs[32 * B2_XLD];               // staged operand; during the attention phase: a_t of the local t range
     float recv[2][D2_RECV];
+    float part[D2_PART];
     float Wcs[64 * B2_WLD];              // Wc^T slice (clusters 0..15)
     float Was[64 * B2_WLD];              // Wa^T slice (clusters 0..7)
     float dcvs[D2_H];
@@ -728,7 +772,7 @@ struct B2Smem {
     float cvx[4 * 128];
     float statx[4 * 2];
     float wstat[8];
-    uint64_t mbar_x, mbar_a;
+    uint64_t mbar_x[2], mbar_a;
     uint32_t tmem_slot;
 };
 
@@ -765,7 +809,7 @@ dec_seq2_bwd_kernel(DecSeq p) {
 
     if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[4090] = gtimer2();
     if (tid == 0) {
-        mbar_init(&sm.mbar_x, 1); mbar_init(&sm.mbar_a, 1);
+        mbar_init(&sm.mbar_x[0], 1); mbar_init(&sm.mbar_x[1], 1); mbar_init(&sm.mbar_a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 0) {
@@ -816,7 +860,7 @@ dec_seq2_bwd_kernel(DecSeq p) {
             *reinterpret_cast<float4*>(sm.Was + j * B2_WLD + k) = make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w));
         }
     uint32_t par_x = 0, par_a = 0;
-    if (tid == 0) { mbar_expect_tx(&sm.mbar_x, D2_XBYTES); mbar_expect_tx(&sm.mbar_a, D2_ABYTES); }
+    if (tid == 0) mbar_expect_tx(&sm.mbar_a, D2_ABYTES);        // mbar_x is armed by each exchange itself (its byte count differs by phase)
     if (p.prof && cta == 0 && tid == 0) p.prof[1] = gtimer2();
     nprof = 1;
     cluster_sync_all();
@@ -826,9 +870,10 @@ dec_seq2_bwd_kernel(DecSeq p) {
     const uint32_t xa_g = saddr(sm.Xs) + (uint32_t)((g * B2_XLD + 4 * q) * 4);
     const uint32_t wca_g = saddr(sm.Wcs) + (uint32_t)(((8 * 4 * nh + g) * B2_WLD + 4 * q) * 4);
     const uint32_t waa_g = saddr(sm.Was) + (uint32_t)(((8 * 4 * nh + g) * B2_WLD + 4 * q) * 4);
-    const uint32_t recv_sa0 = saddr(sm.recv[0]);
+    const uint32_t recv_sa0 = saddr(sm.recv[0]), part_sa = saddr(sm.part);
 #define RECV_SA(b_) (recv_sa0 + (uint32_t)(b_) * D2_XBYTES)
-    const uint32_t mbx_sa = saddr(&sm.mbar_x);
+    const uint32_t mbx_sa0 = saddr(&sm.mbar_x[0]);
+#define MBX_SA(b_) (mbx_sa0 + 8u * (uint32_t)(b_))
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
     const int a_row = tid >> 2, a_c4 = tid & 3;          // phases A, C epilogue: (row, 4 columns of the CTA's 16)
     const int d_row = tid >> 3, d_c = tid & 7;           // D phases epilogue: (row, 1 column of the CTA's 8)
@@ -875,12 +920,11 @@ dec_seq2_bwd_kernel(DecSeq p) {
             float acc[2][4][4] = {};
             mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, wca_g + 64 * (2 * kh), wrow8);
             B2_FINE(s);
-            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
-            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
+            mbar_wait(&sm.mbar_x[xbuf], (par_x >> xbuf) & 1u); par_x ^= 1u << xbuf;
             B2_FINE(s);
-            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (a_ok) {
-                const float4 v4 = recv_sum16(RECV_SA(xbuf), a_row, a_c4, make_float4(0.f, 0.f, 0.f, 0.f));
+                const float4 v4 = recv_sum4(RECV_SA(xbuf), a_row, a_c4, make_float4(0.f, 0.f, 0.f, 0.f));
                 const int n0 = 64 * cl + 16 * rank + 4 * a_c4;
                 if (n0 < H) st_pub4(p.dcv_all + ((size_t)s * B + a_row) * H + n0, v4);
                 else st_pub4(p.dhh_all + ((size_t)s * B + a_row) * H + (n0 - H), v4);
@@ -996,18 +1040,17 @@ dec_seq2_bwd_kernel(DecSeq p) {
             float acc[2][4][4] = {};
             mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, waa_g + 64 * (2 * kh), wrow8);
             B2_FINE(s);
-            exchange16(acc, RECV_SA(xbuf), mbx_sa, rank, kh, nh);
+            exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
             // the other addends (published two and several phases ago) while the exchange is in flight
             float4 addv = make_float4(0.f, 0.f, 0.f, 0.f), rec = addv;
             if (a_ok) {
                 addv = poll4(p.dhh_all + ((size_t)s * B + a_row) * H + n0);
                 if (!last) rec = poll4(p.dxr[2] + ((size_t)(s + 1) * B + a_row) * H + n0);
             }
-            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            mbar_wait(&sm.mbar_x[xbuf], (par_x >> xbuf) & 1u); par_x ^= 1u << xbuf;
             B2_FINE(s);
-            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (a_ok) {
-                const float4 v4 = recv_sum16(RECV_SA(xbuf), a_row, a_c4, addv);
+                const float4 v4 = recv_sum4(RECV_SA(xbuf), a_row, a_c4, addv);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, rr[4] = {rec.x, rec.y, rec.z, rec.w};
                 const float cc[4] = {ccv.x, ccv.y, ccv.z, ccv.w}, cp[4] = {cpv.x, cpv.y, cpv.z, cpv.w};
                 float dc[4] = {dcC.x, dcC.y, dcC.z, dcC.w};
@@ -1067,32 +1110,19 @@ dec_seq2_bwd_kernel(DecSeq p) {
             float acc[2][4][4] = {};
             mma_run_tmem<4>(acc, xa_g + 64 * (4 * w), xrow8, tmem_lane + 64 * l, bfr);
             B2_FINE(s);
-            {   // 32 partial products (4 CTAs x 8 k-slices); n-tile nt belongs to CTA nt.  Receiver layout [src = 8 rank + w][row][8 cols]
-                const int src = 8 * rank + w;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const uint32_t base = mapa(RECV_SA(xbuf), nt), bar = mapa(mbx_sa, nt);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const int r0 = 16 * mt + g;
-                        st_async_v2(base + (uint32_t)(((src * 32 + r0) * 8 + 2 * q) * 4), make_float2(acc[mt][nt][0], acc[mt][nt][1]), bar);
-                        st_async_v2(base + (uint32_t)(((src * 32 + r0 + 8) * 8 + 2 * q) * 4), make_float2(acc[mt][nt][2], acc[mt][nt][3]), bar);
-                    }
-                }
-            }
+            exchange32(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, w);
             float rec = 0.f, dm = 1.f;
             if (fuse) {
                 dm = dropout_scale(p.seed, 16 + lb, (uint32_t)((size_t)s * B * H + e), p.drop_rnn);
                 if (!last) rec = poll1(p.dxr[lb] + ((size_t)(s + 1) * B + d_row) * H + n);
             }
-            mbar_wait(&sm.mbar_x, par_x); par_x ^= 1;
+            mbar_wait(&sm.mbar_x[xbuf], (par_x >> xbuf) & 1u); par_x ^= 1u << xbuf;
             B2_FINE(s);
-            if (tid == 0) mbar_expect_tx(&sm.mbar_x, D2_XBYTES);
             if (d_ok) {
                 float v = 0.f;
                 const float* rv = sm.recv[xbuf];
 #pragma unroll
-                for (int src = 0; src < 32; ++src) v += rv[(src * 32 + d_row) * 8 + d_c];
+                for (int src = 0; src < 4; ++src) v += rv[(src * 32 + d_row) * 8 + d_c];
                 if (n >= H) {                                  // dh_rec of layer l for step s-1
                     st_pub1(p.dxr[l] + ((size_t)s * B + d_row) * H + (n - H), v);
                     if (s == 0) p.dxh[l][(size_t)d_row * (in + H) + in + (n - H)] = v;     // gradient of the decoder's initial state
@@ -1121,6 +1151,7 @@ dec_seq2_bwd_kernel(DecSeq p) {
 #undef B2_PHASE_END
 #undef B2_FINE
 #undef RECV_SA
+#undef MBX_SA
 }
 
 // d_enc[b][t][:] = sum_s alpha[s][b][t] * dcv[s][b][:] + ds[s][b][t] * q[s][b][:]   (one pass after the loop; replaces the
@@ -1195,6 +1226,22 @@ int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p) {
     add(p.dcv_all, SBH); add(p.dhh_all, SBH); add(p.dq, SBH); add(p.dfeed, (size_t)p.S * p.B * p.A);
     for (int l = 0; l < 3; ++l) { add(p.dxr[l], SBH); add(p.dgd[l], 4 * SBH); }
     return fill_ranges(st, r);
+}
+
+// The token a sampled step fed forward is the argmax of its IN-LOOP logits (3xTF32); the batched logits GEMM after the loop is
+// single-pass TF32 and can break a near-tie the other way.  argmax_steps reports what was actually fed: step s <- words_used[s+1].
+__global__ void __launch_bounds__(256) sampled_argmax_kernel(int* __restrict__ argmax_steps, const int* __restrict__ words_used,
+                                                             const unsigned char* __restrict__ use_true, int S, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (S - 1) * B) return;
+    const int s = i / B;
+    if (!use_true[s + 1]) argmax_steps[i] = words_used[i + B];
+}
+int dec_seq2_sampled_argmax(cudaStream_t st, const DecSeq& p) {
+    if (p.use_true == nullptr || p.S < 2) return 0;
+    sampled_argmax_kernel<<<((p.S - 1) * p.B + 255) / 256, 256, 0, st>>>(p.argmax_steps, p.words_used, p.use_true, p.S, p.B);
+    AST_LAUNCH_OK();
+    return 0;
 }
 
 bool dec_seq2_supported(const DecSeq& p) {

@@ -165,6 +165,7 @@ int dec_seq2_bwd(cudaStream_t st, const DecSeq& p);
 // sentinel fill of the per-step hand-off slots the dec_seq2 kernels poll; ordered before init_dec_state / the kernel
 int dec_seq2_prepare_fwd(cudaStream_t st, const DecSeq& p);
 int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p);
+int dec_seq2_sampled_argmax(cudaStream_t st, const DecSeq& p);   // argmax_steps of sampled steps <- the token the loop actually fed
 int embed_all(cudaStream_t st, const DecSeq& p);   // x0[:, :E] / words_used for every step from the ground-truth tokens
 int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float* dcv, const float* q, float* d_enc, int S, int B, int Tp, int H);
 // softmax-CE (+ gradient in place, argmax) for every (step, row) of a decoder pass in one launch

@@ -929,6 +929,7 @@ static int forward_loss_impl(ast_model* m, const float* X, const int* y, int B, 
             }
             AST_TRY(gemm_nt(m, st, S * B, m->V, A, m->ht, A, m->p("out/W"), A, m->logits, m->Vp, m->p("out/b"), SITE_DEC_PRE));
             AST_TRY(softmax_ce_all(st, m->logits, m->Vp, y, L, m->row_loss, m->argmax_steps, S, B, m->V));
+            AST_TRY(dec_seq2_sampled_argmax(st, ds));
         } else {
             AST_TRY(dec_seq_fwd(st, ds, m->exact != 0));
         }
@@ -1416,6 +1417,7 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
+    if (const char* v = getenv("AST_ENC_L0DX_CTAS")) m->enc_l0dx_ctas = atoi(v);      // diagnostics
     if (const char* v = getenv("AST_BEAM_TC")) m->beam_tc = atoi(v);      // experiments: 0 skinny everywhere, 1 batched search on tcgen05, 3 both
     ++g_live_models[device & 63];
     *out = m;
