@@ -158,9 +158,12 @@ __device__ __forceinline__ float poll1(const float* p) {
 // N float4 per thread of an operand other CTAs publish during this launch: all loads in flight first, then only the float4s
 // that still hold a sentinel word are re-read.  a[i] == nullptr: a row beyond the batch (zeros).
 template <int N>
-__device__ __forceinline__ void poll_many(float4 (&v)[N], const float* const (&a)[N]) {
+__device__ __forceinline__ void poll_issue(float4 (&v)[N], const float* const (&a)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = a[i] ? ld_pub4(a[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int N>
+__device__ __forceinline__ void poll_finish(float4 (&v)[N], const float* const (&a)[N]) {
     PollClock pc;
     for (;;) {
         bool bad = false;
@@ -170,6 +173,16 @@ __device__ __forceinline__ void poll_many(float4 (&v)[N], const float* const (&a
         pc.tick();
 #pragma unroll
         for (int i = 0; i < N; ++i) if (unwritten(v[i])) v[i] = ld_pub4(a[i]);
+    }
+}
+template <int N>
+__device__ __forceinline__ void poll_many(float4 (&v)[N], const float* const (&a)[N]) { poll_issue<N>(v, a); poll_finish<N>(v, a); }
+// addresses of one 128-wide activation segment of the K quarter (32 rows, 4 float4 per thread)
+__device__ __forceinline__ void seg_addr128(const float* (&a)[4], const float* ptr, int ld, int B) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + i * D2_THREADS, row = idx >> 5, k = (idx & 31) * 4;
+        a[i] = row < B ? ptr + (size_t)row * ld + k : nullptr;
     }
 }
 // One activation segment of the K quarter: W floats per row starting at ptr[row * ld]; 32 rows
@@ -473,6 +486,9 @@ dec_seq2_fwd_kernel(DecSeq p) {
 #define MBX_SA(b_) (mbx_sa0 + 8u * (uint32_t)(b_))
     const int Tq = (Tp + D2_CS - 1) / D2_CS;
     int xbuf = 0;
+    float4 vold[4]; const float* aold[4];      // a layer's step-old operand, requested one phase early
+    seg_addr128(aold, p.Hd[0] + 128 * rank, H, B);
+    poll_issue<4>(vold, aold);
     for (int s = 0; s < S; ++s) {
         // ---- LSTM stack (seq2seq.py:375) -----------------------------------------------------------------------
 #pragma unroll 1
@@ -483,17 +499,16 @@ dec_seq2_fwd_kernel(DecSeq p) {
             D2_FINE(s);
             uint32_t bfr[16];
             tmem_ld16_nowait(tmem_lane + tcol, bfr);
-            // (1) operands that are a step old: own recurrent state (layer 0: + the embedding rows)
+            // (1) operands that are a step old: own recurrent state (layer 0: + the embedding rows).  For layers 1, 2 the first
+            // loads were issued during the previous phase's exchange (vold / aold), so their L2 round trip is already over.
             {
-                float4 v2[4];
-                seg_poll<128>(v2, p.Hd[l] + (size_t)s * B * H + 128 * rank, H, B);
-                if (l == 0) {
+                if (l == 0) {          // (requested at the end of the previous step)
                     float4 v0[1];
                     seg_poll<32>(v0, x0 + 32 * rank, ldx0, B);
-                    seg_store<32, D2_XLD>(sm.Xs + 128, v0); seg_store<128, D2_XLD>(sm.Xs + 160, v2);
-                } else {
-                    seg_store<128, D2_XLD>(sm.Xs + 128, v2);
+                    seg_store<32, D2_XLD>(sm.Xs + 128, v0);
                 }
+                poll_finish<4>(vold, aold);
+                seg_store<128, D2_XLD>(sm.Xs + (l == 0 ? 160 : 128), vold);
             }
             __syncthreads();
             D2_FINE(s);
@@ -514,6 +529,10 @@ dec_seq2_fwd_kernel(DecSeq p) {
             mma_run_tmem<2>(acc, xa_g + 64 * (2 * kh), xrow8, tmem_lane + tcol + 16 * nnc, bfr);
             D2_FINE(s);
             exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
+            if (l < 2) {   // the next layer's recurrent state is a step old: request it while the exchange is in flight
+                seg_addr128(aold, p.Hd[l + 1] + (size_t)s * B * H + 128 * rank, H, B);
+                poll_issue<4>(vold, aold);
+            }
             const size_t e = (size_t)e_row * H + e_unit;
             float4 gs = make_float4(0.f, 0.f, 0.f, 0.f); float dm = 1.f;
             if (own) {     // while the exchange is in flight
@@ -668,6 +687,10 @@ dec_seq2_fwd_kernel(DecSeq p) {
             mma_run_smem<2>(acc, xa_g + 64 * (2 * kh), xrow8, wa_g + 64 * (2 * kh), wrow8);
             D2_FINE(s);
             exchange16(acc, part_sa, RECV_SA(xbuf), MBX_SA(xbuf), rank, kh, nh);
+            if (s + 1 < S) {       // layer 0's recurrent state of the next step, while the exchange is in flight
+                seg_addr128(aold, p.Hd[0] + (size_t)(s + 1) * B * H + 128 * rank, H, B);
+                poll_issue<4>(vold, aold);
+            }
             const int n0 = 64 * cl + 16 * rank + 4 * e_ul;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (own) v = __ldg(reinterpret_cast<const float4*>(p.bc + n0));
@@ -682,6 +705,9 @@ dec_seq2_fwd_kernel(DecSeq p) {
             xbuf ^= 1;
             D2_FINE(s);
             __syncthreads();
+        } else if (s + 1 < S) {
+            seg_addr128(aold, p.Hd[0] + (size_t)(s + 1) * B * H + 128 * rank, H, B);
+            poll_issue<4>(vold, aold);
         }
         D2_PHASE_END();
         // ---- scheduled sampling: the next input is this step's argmax (seq2seq.py:431-436, 448) ----------------------
