@@ -155,49 +155,55 @@ def _backtrack(hp, hk, ns):
     return toks, slots
 
 
-def _entries(toks, slots, ah, sc, ns, nh, r, go_id):
-    """One utterance's hypothesis dicts.  ``attn_history`` is a (tokens, T') array: indexing, iteration and len() behave like the
-    reference's list of per-step attention vectors (one list of 175 small arrays per hypothesis was most of the conversion time).
-    The device views of the decoder state are cut with a handful of split/unbind calls per utterance, not seven slices per
-    hypothesis."""
+def _entries(toks, hist, sc, ns, nh, r, go_id):
+    """One utterance's hypothesis dicts.  ``hist[s, j]`` is the attention vector hypothesis j's ancestor had at step s (already
+    gathered along the parent chain); ``attn_history`` is a (tokens, T') array - a view when the hypothesis emitted a token at
+    every step - whose indexing, iteration and len() behave like the reference's list of per-step vectors (one list of 175 small
+    arrays per hypothesis was most of the conversion time).  The device views of the decoder state are cut with a handful of
+    split/unbind calls per utterance, not seven slices per hypothesis."""
     st = r["states"]                                                        # (NL, 2, N, H)
     per_layer = [[part.split(1, 0) for part in layer.unbind(0)] for layer in st.unbind(0)]      # [l][c|h][j] -> (1, H)
     av = r["attn_v"].split(1, 0)
     out = []
     for j in range(nh):
-        idx = np.nonzero(toks[:, j] >= 0)[0]
-        out.append({"hyp": [go_id] + toks[idx, j].tolist(), "score": np.float32(sc[j]) if ns > 0 else 0,
+        valid = toks[:, j] >= 0
+        full = bool(valid.all())
+        out.append({"hyp": [go_id] + (toks[:, j] if full else toks[valid, j]).tolist(), "score": np.float32(sc[j]) if ns > 0 else 0,
                     "dec_state": {"c": [Variable(pl[0][j]) for pl in per_layer],
                                   "h": [Variable(pl[1][j]) for pl in per_layer]},
                     "attn_v": Variable(av[j]),
-                    "attn_history": ah[idx, slots[idx, j]]})
+                    "attn_history": hist[:, j] if full else hist[valid, j]})
     return out
 
 
 def beam_result_to_entries(r, go_id=SYMBOLS.GO_ID, model=None):
     """Device beam-search buffers -> the reference's list of hypothesis dicts (nn.py:286-294).  Results of a lock-step group
-    (Engine.beam_search_batch) are copied to the host (pinned, one synchronisation) and backtracked together when the first
-    of them is converted; the host copy is re-fetched if another group was fetched in between."""
+    (Engine.beam_search_batch) are copied to the host (pinned, one synchronisation), backtracked together and their attention
+    histories gathered along the parent chains in ONE pass when the first of them is converted."""
     grp = r.get("_group")
     if grp is not None:
-        eng = grp["engine"]
-        if grp["host"] is None or grp["host"][0] != eng.fetch_gen:
-            hp, hk, sc, ah = eng.fetch_host([grp["hist_parent"], grp["hist_tok"], grp["scores"], grp["alpha_hist"]])
+        if grp["host"] is None:
+            hp, hk, sc, ah = grp["engine"].fetch_host([grp["hist_parent"], grp["hist_tok"], grp["scores"], grp["alpha_hist"]])
             toks, slots = _backtrack(hp, hk, grp["n_steps"])
-            grp["host"] = (eng.fetch_gen, toks, slots, sc.copy(), ah)
-        _, toks, slots, sc, ah = grp["host"]
+            G_, S_, N_, Tp_ = ah.shape                                       # row gather: hist[g, s, j] = ah[g, s, slots[g, s, j]]
+            rows = (np.arange(G_)[:, None, None] * S_ + np.arange(S_)[None, :, None]) * N_ + slots
+            hist = np.take(ah.reshape(G_ * S_ * N_, Tp_), rows.ravel(), axis=0).reshape(G_, S_, N_, Tp_)      # owns its memory
+            grp["host"] = (toks, hist, sc.copy())
+        toks, hist, sc = grp["host"]
         g = r["_slot"]
         ns, nh = grp["n_steps"][g], grp["n_hyps"][g]
-        return _entries(toks[g, :ns], slots[g, :ns], ah[g, :ns, :, :grp["tp"][g]], sc[g], ns, nh, r, go_id)
+        return _entries(toks[g, :ns], hist[g, :ns, :, :grp["tp"][g]], sc[g], ns, nh, r, go_id)
     ns, nh = r["n_steps"], r["n_hyps"]
     hp = r["hist_parent"][:ns].cpu().numpy()
     hk = r["hist_tok"][:ns].cpu().numpy()
     ah = r["alpha_hist"][:ns].cpu().numpy()
     sc = r["scores"].cpu().numpy()
     if ns == 0:
-        return _entries(np.zeros((0, max(nh, 1)), np.int64), np.zeros((0, max(nh, 1)), np.int64), ah, sc, ns, nh, r, go_id)
+        return _entries(np.zeros((0, max(nh, 1)), np.int64), ah, sc, ns, nh, r, go_id)
     toks, slots = _backtrack(hp[None], hk[None], [ns])
-    return _entries(toks[0], slots[0], ah, sc, ns, nh, r, go_id)
+    S_, N_, Tp_ = ah.shape
+    rows = np.arange(S_)[:, None] * N_ + slots[0]
+    return _entries(toks[0], np.take(ah.reshape(S_ * N_, Tp_), rows.ravel(), axis=0).reshape(S_, N_, Tp_), sc, ns, nh, r, go_id)
 
 
 class NN:
