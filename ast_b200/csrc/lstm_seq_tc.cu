@@ -21,6 +21,13 @@
 
 namespace ast {
 
+__global__ void wait_resident_kernel(const unsigned* counter, unsigned target) { spin_until_ge(counter, target); }
+int wait_resident(cudaStream_t st, const unsigned* counter, unsigned target) {
+    wait_resident_kernel<<<1, 1, 0, st>>>(counter, target);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 // optional cycle probe (tools/lstm_step_probe.py): CTA 0 stores clock64() stamps of steps 8..23 of the forward kernel
 static unsigned long long* g_lstm_prof = nullptr;
 void lstm_tc_set_prof(unsigned long long* p) { g_lstm_prof = p; }
@@ -98,6 +105,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     const bool probe = prof != nullptr && blockIdx.x == 0;
 #define PROBE(slot) do { if (probe && i >= 8 && i < 24) prof[(i - 8) * 8 + (slot)] = clock64(); } while (0)
     const int rank = (int)cluster_rank();
+    if (gt.resident && threadIdx.x == 0) atomicAdd(gt.resident, 1u);       // this CTA holds its SM from here on
     const LstmChain a = ch.c[blockIdx.x / TNC];
     constexpr int h = TH, H4 = 4 * TH;
     const int nb = a.nb, b0 = a.b0;
@@ -297,6 +305,7 @@ constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_B
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, LstmGate gt) {
     const int rank = (int)cluster_rank();
+    if (gt.resident && threadIdx.x == 0) atomicAdd(gt.resident, 1u);       // this CTA holds its SM from here on
     const LstmChain a = ch.c[blockIdx.x / TNC];
     constexpr int h = TH, H4 = 4 * TH;
     const int nb = a.nb, b0 = a.b0;

@@ -49,7 +49,7 @@ constexpr int DRAW1_PAD_ROWS = 8;     // zero rows in front of d(raw1): the tran
 constexpr int BN_PART_BLOCKS = 640;   // per-block partial sums of bn_bwd_rnn_reduce (<= 148 * 4 + slack blocks)
 constexpr int MAXQ = 256;     // chunks per layer of the persistent encoder wavefront
 constexpr int MAXT = 512;     // 128-row tiles of a layer's gate buffer (T' * B / 128)
-constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + 64;   // done | tiles
+constexpr size_t ENC_FLAG_WORDS = (size_t)MAXL * MAXQ + (size_t)MAXL * 2 * MAXT + 64;   // done | tiles | [last word] CTAs resident
 constexpr size_t ENC_TS_WORDS = (size_t)2 * MAXL * MAXQ;     // diagnostics: [pass][layer][chunk] %globaltimer stamps
 
 struct ParamInfo { std::string name; long long off; int ndim; int shape[4]; long long count; };
@@ -640,6 +640,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         // GEMM FLOPs) runs first as one GEMM per direction on the whole GPU.
         unsigned* done = m->enc_flags;
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
+        unsigned* resident = m->enc_flags + ENC_FLAG_WORDS - 1;
         cudaEvent_t* ev = m->ev_pool;
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         {   // both directions in one grouped 2-CTA launch: 2 x 80 pair tiles are 3 waves of 74 pairs, two separate launches are 4
@@ -664,9 +665,11 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
             LstmChains ch = fwd_chains(l, 0);
             if (l > 0)
                 for (int d = 0; d < 2; ++d) { ch.c[d].tile_ready = tiles + (size_t)(l * 2 + d) * MAXT; ch.c[d].tile_target = tile_target; }
-            const LstmGate gate{l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)l * MAXQ : nullptr};
+            const LstmGate gate{l < NL - 1 ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)l * MAXQ : nullptr, resident};
             AST_TRY(lstm_seq_fwd_gated(m->lay[l], ch, 2, Tp, B, h, drop, m->cur_seed, gate, &ncta));
         }
+        for (int l = 1; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) AST_TRY(wait_resident(d == 0 ? m->layg[l] : m->layh[l], resident, (unsigned)(NL * ncta)));
         for (int l = 1; l < NL; ++l)
             for (int d = 0; d < 2; ++d) {
                 const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
@@ -695,6 +698,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         // recurrence kernels take their SMs: chunked beside the recurrences it ran on the ~50 SMs they leave free and was the
         // bottleneck of the forward pass (0.77 -> 0.68 ms at B32 x T640)
         const bool l0_whole = m->enc_l0_pre > 0;      // measured: no gain on this path (the hand-offs dominate), off by default
+        if (m->warm_fwd == 0 && m->enc_flags) AST_TRY(wait_resident(st, m->enc_flags, 0u));      // first launch of this kernel outside any spin-wait window (rule a)
         if (l0_whole) AST_TRY(project(0, 0, Tp, st));
         AST_CUDA_OK(cudaEventRecord(ev[NL * nch], st));
         for (int l = 0; l < NL; ++l) {
@@ -1204,6 +1208,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         // the weight gradients of a layer start on the side stream when that layer's kernel has finished.
         unsigned* done = m->enc_flags;
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
+        unsigned* resident = m->enc_flags + ENC_FLAG_WORDS - 1;
         cudaEvent_t* ev = m->ev_pool;
         // layer 0's data gradient (N = 1536: a third of the encoder's backward GEMM FLOPs, needed only by the CNN backward) as a
         // gated GEMM beside the recurrences as well, on a few CTAs per direction: it finishes about one chunk after layer 0's
@@ -1223,10 +1228,12 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                     ch.c[d].tile_ready = tiles + (size_t)((l + 1) * 2 + d) * MAXT;
                     ch.c[d].tile_target = 4u * (unsigned)gemm_tc_tiles_per_row(m->in_enc(l + 1));
                 }
-            const LstmGate gate{(l > 0 || l0gate) ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)(MAXL + l) * MAXQ : nullptr};
+            const LstmGate gate{(l > 0 || l0gate) ? done + (size_t)l * MAXQ : nullptr, PCH, m->enc_ts_on ? m->enc_ts + (size_t)(MAXL + l) * MAXQ : nullptr, resident};
             AST_TRY(lstm_seq_bwd_gated(m->lay[l], ch, 2, Tp, B, h, dr, m->cur_seed, gate, &ncta));
             AST_CUDA_OK(cudaEventRecord(ev[1 + l], m->lay[l]));       // layer l's dG complete
         }
+        for (int l = NL - 1; l >= (l0gate ? 0 : 1); --l)
+            for (int d = 0; d < 2; ++d) AST_TRY(wait_resident(d == 0 ? m->layg[l] : m->layh[l], resident, (unsigned)(NL * ncta)));
         for (int l = NL - 1; l >= (l0gate ? 0 : 1); --l)
             for (int d = 0; d < 2; ++d) {
                 const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
@@ -1412,8 +1419,12 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_fill[i], cudaEventDisableTiming);
     for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_bucket[i], cudaEventDisableTiming);
     for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->lay[i], cudaStreamNonBlocking, prio_hi);
-    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layg[i], cudaStreamNonBlocking, prio_hi);
-    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layh[i], cudaStreamNonBlocking, prio_hi);
+    // The gated GEMMs one priority level below the recurrences: everything of a wavefront becomes eligible at the same event, and
+    // single GEMM CTAs dispatched before an 8-CTA recurrence cluster can leave no GPC with 8 free SMs for it - that cluster then
+    // waits for another layer's kernel to END (measured: layer 1 starting 320-420 us late in some passes, +0.4 ms on the step)
+    const int prio_gemm = std::min(prio_hi + 1, prio_lo);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layg[i], cudaStreamNonBlocking, prio_gemm);
+    for (int i = 0; i < MAXL && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&m->layh[i], cudaStreamNonBlocking, prio_gemm);
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
