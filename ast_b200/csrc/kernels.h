@@ -90,7 +90,7 @@ struct LstmChains { LstmChain c[AST_MAX_CHAINS]; };
 // encoder wavefront, model.cu).  Steps are numbered in PROCESSING order k (forward: k = t, backward: k = T-1-t); every CTA adds 1
 // to done[k / chunk] (after a fence) once its outputs of that chunk are in global memory, and a gated GEMM (TcGate) waits for all
 // CTAs of the launch.  null: no signalling.  (The kernel's own inputs are gated per 128-row tile: LstmChain::tile_ready.)
-struct LstmGate { unsigned* done; int chunk; unsigned long long* ts; unsigned* resident; };   // ts (diagnostics, may be null): %globaltimer of block 0 at each chunk signal; resident (may be null): every CTA counts itself in when it starts
+struct LstmGate { unsigned* done; int chunk; unsigned long long* ts; unsigned* resident; unsigned long long* probe; };   // ts (diagnostics, may be null): %globaltimer of block 0 at each chunk signal; resident (may be null): every CTA counts itself in when it starts
 // One-CTA kernel that returns when *counter >= target (bounded spin): in front of the gated GEMMs of a wavefront, so that their single
 // CTAs are dispatched only after every 8-CTA recurrence cluster is resident (single CTAs placed first can leave no GPC with 8 free SMs;
 // the cluster then waits for another layer's kernel to end)

@@ -37,7 +37,7 @@ constexpr int TH = 256;          // per-direction hidden size handled by this ke
 constexpr int TU = TH / TNC;     // 32 hidden units per CTA
 constexpr int TROWS = 16;        // batch rows per chain = UMMA N
 constexpr int TC_EPI = 256;      // epilogue threads
-constexpr int TC_THREADS = TC_EPI + 32;
+constexpr int TC_THREADS = TC_EPI + 64;       // forward: epilogue warps 0..7, MMA issuer warp 8, chunk signaller warp 9
 
 __device__ __forceinline__ float rnd_tf32(float x) { return __uint_as_float(f2tf32(x)); }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -75,11 +75,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// all epilogue threads: this CTA's global stores of the chunk are visible device-wide, then one arrival on the chunk's counter
-__device__ __forceinline__ void gate_signal(unsigned* counter, int tid) {
-    __threadfence();
-    asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory");
-    if (tid == 0) { __threadfence(); atomicAdd(counter, 1u); }
+// Chunk hand-off through a dedicated signaller warp.  The epilogue warps only count their arrival in shared memory (release at CTA
+// scope, one lane per warp after __syncwarp); the signaller acquires the count, makes the chunk's global stores visible device-wide
+// with ONE gpu-scope fence (cumulative over everything it acquired) and bumps the chunk's counter.  That fence waits for every
+// outstanding store of the SM: executed by the 256 epilogue threads (+ a CTA barrier) it cost 1.4 us (forward) / 3.3 us (backward)
+// per chunk of 8 steps on the recurrence's critical path (tools/enc_timeline.py against tools/enc_step_probe.py).
+__device__ __forceinline__ void chunk_arrive(uint32_t cnt_addr, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(cnt_addr), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void signaller_loop(uint32_t cnt_addr, int nchunks, const LstmGate& gt, bool stamp) {
+    for (int c = 0; c < nchunks; ++c) {
+        const unsigned target = (unsigned)(TC_EPI / 32) * (unsigned)(c + 1);
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(cnt_addr) : "memory");
+            if (v >= target) break;
+            __nanosleep(64);
+        }
+        if (stamp) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gt.ts[c] = t; }
+        if (gt.done) { __threadfence(); atomicAdd(gt.done + c, 1u); }
+    }
 }
 
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B operand made of k-blocks of 32 floats:
@@ -88,6 +104,19 @@ __device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows_per_bloc
     const int kb = k >> 5, c = (k & 31) >> 2;
     return (uint32_t)(kb * rows_per_block * 128 + row * 128 + ((c ^ (row & 7)) << 4) + ((k & 3) << 2));
 }
+
+// explicit shared-state-space accesses: the carve-up pointers come from an aligned-up integer, through which the compiler can only
+// emit generic LD/ST
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 
 // ================================================================================================
 // forward
@@ -102,7 +131,7 @@ constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, unsigned long long* prof, LstmGate gt) {
-    const bool probe = prof != nullptr && blockIdx.x == 0;
+    const bool probe = prof != nullptr && blockIdx.x == 0 && ch.c[0].drop_stream <= 1;      // stand-alone launches (0) or (layer 0, forward direction)
 #define PROBE(slot) do { if (probe && i >= 8 && i < 24) prof[(i - 8) * 8 + (slot)] = clock64(); } while (0)
     const int rank = (int)cluster_rank();
     if (gt.resident && threadIdx.x == 0) atomicAdd(gt.resident, 1u);       // this CTA holds its SM from here on
@@ -118,12 +147,14 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     uint64_t* mbar_h = reinterpret_cast<uint64_t*>(sm + FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_BYTES);   // [2]
     uint64_t* mbar_mma = mbar_h + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_h + 3);
+    uint32_t* chunk_cnt = tmem_slot + 1;               // epilogue warps that finished the current chunk's stores (cumulative)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     for (int idx = tid; idx < (int)(2 * FW_H_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sH)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         mbar_init(&mbar_h[0], 1); mbar_init(&mbar_h[1], 1); mbar_init(mbar_mma, 1);
+        *chunk_cnt = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 8) {
@@ -170,7 +201,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t sH_addr = saddr(sH);
+    const uint32_t sH_addr = saddr(sH), xg_addr = saddr(xg), sStg_addr = saddr(sStg), cnt_addr = saddr(chunk_cnt);
     cluster_sync_all();                   // all CTAs have initialised buffers / barriers before any remote store
 
     if (w == 8) {
@@ -197,6 +228,9 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 PROBE(1);
             }
         }
+    } else if (w == 9) {
+        if (lane == 0 && (gt.done || (gt.ts && blockIdx.x == 0)))
+            signaller_loop(cnt_addr, (T + gt.chunk - 1) / gt.chunk, gt, gt.ts && blockIdx.x == 0);
     } else {
         // ===== epilogue: thread (w, lane) owns hidden unit `lane`, batch rows 2w and 2w+1 =====
         const int ju = TU * rank + lane;
@@ -224,7 +258,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + 8 * bh, v);
                 tc_fence_before();
 #pragma unroll
-                for (int b = 0; b < 8; ++b) xg[(gate * TROWS + 8 * bh + b) * TU + lane] = v[b];
+                for (int b = 0; b < 8; ++b) sts_f1(xg_addr + (uint32_t)(((gate * TROWS + 8 * bh + b) * TU + lane) * 4), v[b]);
             }
             epi_barrier();
             if (tid == 0) PROBE(3);
@@ -232,10 +266,10 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int b = 2 * w + j;
-                const float ga = fast_tanh(xg[(0 * TROWS + b) * TU + lane] + gx[j].x);
-                const float gi = fast_sigmoid(xg[(1 * TROWS + b) * TU + lane] + gx[j].y);
-                const float gf = fast_sigmoid(xg[(2 * TROWS + b) * TU + lane] + gx[j].z);
-                const float go = fast_sigmoid(xg[(3 * TROWS + b) * TU + lane] + gx[j].w);
+                const float ga = fast_tanh(lds_f1(xg_addr + (uint32_t)(((0 * TROWS + b) * TU + lane) * 4)) + gx[j].x);
+                const float gi = fast_sigmoid(lds_f1(xg_addr + (uint32_t)(((1 * TROWS + b) * TU + lane) * 4)) + gx[j].y);
+                const float gf = fast_sigmoid(lds_f1(xg_addr + (uint32_t)(((2 * TROWS + b) * TU + lane) * 4)) + gx[j].z);
+                const float go = fast_sigmoid(lds_f1(xg_addr + (uint32_t)(((3 * TROWS + b) * TU + lane) * 4)) + gx[j].w);
                 const float c = ga * gi + gf * creg[j];
                 const float hval = b < nb ? go * fast_tanh(c) : 0.f;
                 actv[j] = make_float4(ga, gi, gf, go); cv[j] = c; hv[j] = hval;
@@ -247,11 +281,11 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 // [16 rows][128 B, 16-byte chunks XOR-ed with row % 8].  Stage it locally (TF32-rounded) and push it to all 8
                 // CTAs with ONE bulk copy each (cp.async.bulk smem -> dsmem, completing bytes on the receiver's mbarrier)
                 // instead of 4 st.async + 8 mapa per thread (measured: the send section was 1340 of a step's 4500 cycles).
-                uint8_t* stg = sStg + nxt * (TROWS * 128);
+                const uint32_t stg = sStg_addr + (uint32_t)(nxt * (TROWS * 128));
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int b = 2 * w + j;
-                    *reinterpret_cast<float*>(stg + b * 128 + ((((lane >> 2) ^ (b & 7))) << 4) + ((lane & 3) << 2)) = rnd_tf32(hv[j]);
+                    sts_f1(stg + (uint32_t)(b * 128 + ((((lane >> 2) ^ (b & 7))) << 4) + ((lane & 3) << 2)), rnd_tf32(hv[j]));
                 }
                 fence_proxy_async();
                 epi_barrier();
@@ -259,7 +293,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     const uint32_t dst = mapa(sH_addr + nxt * FW_H_BYTES + (uint32_t)rank * (TROWS * 128), tid);
                     const uint32_t bar = mapa(saddr(&mbar_h[nxt]), tid);
                     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst), "r"(saddr(stg)), "r"((uint32_t)(TROWS * 128)), "r"(bar) : "memory");
+                                 ::"r"(dst), "r"(stg), "r"((uint32_t)(TROWS * 128)), "r"(bar) : "memory");
                 }
             }
             if (tid == 0) PROBE(5);
@@ -278,10 +312,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     if (i + 1 < T) gx[j] = __ldcg(reinterpret_cast<const float4*>(a.G + (r + B) * H4 + 4 * ju));
                 }
             }
-            if ((i + 1) % gt.chunk == 0 || i + 1 == T) {
-                if (gt.ts && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gt.ts[i / gt.chunk] = t; }
-                if (gt.done) gate_signal(gt.done + i / gt.chunk, tid);
-            }
+            if ((i + 1) % gt.chunk == 0 || i + 1 == T) chunk_arrive(cnt_addr, lane);
             if (tid == 0) PROBE(6);
         }
     }
@@ -300,13 +331,34 @@ constexpr uint32_t BW_A_BYTES = 8 * 128 * 128;          // W slice as M-major op
 constexpr uint32_t BW_G_BYTES = 4 * TROWS * 128;        // dG: 4 k-blocks x 16 batch rows x 128 B (K-major)
 constexpr uint32_t BW_R_BYTES = TNC * TU * TROWS * 4;   // one reduce buffer [src][unit][batch]
 constexpr uint32_t BW_STG_BYTES = 2 * TNC * TU * TROWS * 4;   // [2][owner] staging of the partial dh blocks (2 KB per owner)
-constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES + 64 + 1024;
+constexpr int BW_THREADS = TC_EPI + 96;                 // epilogue warps 0..7, MMA issuer warp 8, loader warp 9, chunk signaller warp 10
+constexpr int BW_PAIRS = TU * TROWS;                    // (unit, batch row) pairs of a CTA = 2 per epilogue thread
+constexpr uint32_t BW_PRE_BYTES = 2 * BW_PAIRS * (16 + 4 + 4);   // [2] prefetched (gate activations, c_{t-1}, dout) of a step
+constexpr uint32_t BW_SMEM = BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES + BW_PRE_BYTES + 128 + 1024;
+// slot of pair idx = 16*unit + row inside a prefetch buffer: the loader warp writes with lane = unit (fixed row), the epilogue reads
+// with consecutive idx - the XOR keeps both sides off the same banks
+// asynchronous global -> shared copies: no register staging, so the loader warp keeps several steps in flight
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ int pre_slot4(int idx) { return idx ^ ((idx >> 4) & 7); }
+__device__ __forceinline__ int pre_slot1(int idx) { return idx ^ ((idx >> 4) & 15); }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, LstmGate gt) {
     const int rank = (int)cluster_rank();
     if (gt.resident && threadIdx.x == 0) atomicAdd(gt.resident, 1u);       // this CTA holds its SM from here on
     const LstmChain a = ch.c[blockIdx.x / TNC];
+    // cycle probe (tools/lstm_step_probe.py --bwd): CTA 0 of the launch whose first chain is (layer 0, forward direction) stamps
+    // clock64 for its 9th..24th processed step into probe[128 + 8 k + slot]
+    unsigned long long* const bprof = (gt.probe && blockIdx.x == 0 && a.drop_stream == 1) ? gt.probe + 128 : nullptr;
+#define BPROBE(slot) do { if (bprof && step >= 8 && step < 24) bprof[(step - 8) * 8 + (slot)] = clock64(); } while (0)
     constexpr int h = TH, H4 = 4 * TH;
     const int nb = a.nb, b0 = a.b0;
     extern __shared__ uint8_t smem_raw[];
@@ -315,20 +367,26 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     uint8_t* sG = sm + BW_A_BYTES;                      // B[n = batch][k = gate row p] (K-major, SWIZZLE_128B)
     float* red = reinterpret_cast<float*>(sm + BW_A_BYTES + BW_G_BYTES);     // [2][src][unit][batch]
     uint8_t* sStg = sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES;
-    uint64_t* mbar_r = reinterpret_cast<uint64_t*>(sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES);   // [2]
+    float4* sPa = reinterpret_cast<float4*>(sStg + BW_STG_BYTES);            // [2][pairs] gate activations of the step
+    float* sPc = reinterpret_cast<float*>(sPa + 2 * BW_PAIRS);               // [2][pairs] c_{t-1}
+    float* sPd = sPc + 2 * BW_PAIRS;                                         // [2][pairs] dout_t
+    uint64_t* mbar_r = reinterpret_cast<uint64_t*>(sm + BW_A_BYTES + BW_G_BYTES + 2 * BW_R_BYTES + BW_STG_BYTES + BW_PRE_BYTES);   // [2]
     uint64_t* mbar_mma = mbar_r + 2;
     uint64_t* mbar_g = mbar_r + 3;                      // dG operand written by all 256 epilogue threads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_r + 4);
+    uint64_t* mbar_full = mbar_r + 4;                   // [2] prefetch buffer filled (loader warp)
+    uint64_t* mbar_empty = mbar_r + 6;                  // [2] prefetch buffer consumed (one arrival per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_r + 8);
+    uint32_t* chunk_cnt = tmem_slot + 1;               // epilogue warps that finished the current chunk's stores (cumulative)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
     // W slice rows p = 4*unit + gate (natural order, = dG's k index), all 256 unit columns n:
     // chunk j = n/32 at j*16 KB, k-row p at p*128 B, 32-byte sub-chunk ((n%32)/8) XOR (p % 4)
-    for (int base = 0; base < 128 * (h / 4); base += 8 * TC_THREADS) {      // batched loads, see the forward kernel
+    for (int base = 0; base < 128 * (h / 4); base += 8 * BW_THREADS) {      // batched loads, see the forward kernel
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * TC_THREADS + tid;
+            const int idx = base + u * BW_THREADS + tid;
             if (idx < 128 * (h / 4)) {
                 const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
                 v[u] = __ldg(reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n));
@@ -336,7 +394,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * TC_THREADS + tid;
+            const int idx = base + u * BW_THREADS + tid;
             if (idx < 128 * (h / 4)) {
                 const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
                 const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
@@ -344,10 +402,12 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             }
         }
     }
-    for (int idx = tid; idx < (int)(BW_G_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(sG)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int idx = tid; idx < (int)(2 * BW_R_BYTES / 16); idx += TC_THREADS) reinterpret_cast<float4*>(red)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < (int)(BW_G_BYTES / 16); idx += BW_THREADS) reinterpret_cast<float4*>(sG)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < (int)(2 * BW_R_BYTES / 16); idx += BW_THREADS) reinterpret_cast<float4*>(red)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         mbar_init(&mbar_r[0], 1); mbar_init(&mbar_r[1], 1); mbar_init(mbar_mma, 1); mbar_init(mbar_g, TC_EPI);
+        *chunk_cnt = 0u;
+        mbar_init(&mbar_full[0], 32); mbar_init(&mbar_full[1], 32); mbar_init(&mbar_empty[0], TC_EPI / 32); mbar_init(&mbar_empty[1], TC_EPI / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (w == 8) {
@@ -359,7 +419,8 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t sA_addr = saddr(sA), sG_addr = saddr(sG), red_addr = saddr(red);
+    const uint32_t sA_addr = saddr(sA), sG_addr = saddr(sG), red_addr = saddr(red), sStg_addr = saddr(sStg);
+    const uint32_t sPa_addr = saddr(sPa), sPc_addr = saddr(sPc), sPd_addr = saddr(sPd), cnt_addr = saddr(chunk_cnt);
     cluster_sync_all();
 
     if (w == 8) {
@@ -373,6 +434,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             for (int i = T - 1; i >= i_last; --i, ++step) {
                 mbar_expect_tx(&mbar_r[i & 1], BW_R_BYTES);       // arm the reduce buffer this step's sends fill
                 mbar_wait(mbar_g, step & 1);                      // dG_i operand complete in smem
+                BPROBE(6);
                 tc_fence_after();
                 // dh^T (256 x 16) = W_slice^T (256 x 128) · dG^T (128 x 16): two M = 128 halves, 16 k-steps each
 #pragma unroll
@@ -382,35 +444,74 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                         umma_tf32_ss(tmem_base + hm * TROWS, a0 + (uint64_t)((hm * 4 * 16384 + ks * 1024) >> 4),
                                      g0 + (uint64_t)(((ks >> 2) * (TROWS * 128) + (ks & 3) * 32) >> 4), idesc, ks ? 1u : 0u);
                 umma_commit_arrive(mbar_mma);
+                BPROBE(7);
             }
+        }
+    } else if (w == 10) {
+        if (lane == 0 && (gt.done || (gt.ts && blockIdx.x == 0)))
+            signaller_loop(cnt_addr, (T + gt.chunk - 1) / gt.chunk, gt, gt.ts && blockIdx.x == 0);
+    } else if (w == 9) {
+        // ===== loader warp: stages (gate activations, c_{t-1}, dout_t) of a step in shared memory one to two steps ahead (cp.async).
+        // In the epilogue warps these global loads were still in flight at the proxy fence in front of the bulk send
+        // (MEMBAR.ALL.CTA waits for every outstanding access of the thread: +650 cycles per step, tools/enc_step_probe.py). =====
+        const int ju = TU * rank + lane;
+        int tile_next = (T * B - 1) >> 7;          // a.tile_ready gating: tiles above this one are known complete (dout arrives last tile first)
+        int step = 0;
+        for (int i = T - 1; i >= 0; --i, ++step) {
+            const int pb = step & 1;
+            if (step >= 2) mbar_wait(&mbar_empty[pb], ((step >> 1) - 1) & 1);      // epilogue done with this buffer (step - 2)
+            if (a.tile_ready) {
+                const int need = (i * B + b0) >> 7;
+                while (tile_next >= need) { spin_until_ge(a.tile_ready + tile_next, a.tile_target); --tile_next; }
+            }
+#pragma unroll
+            for (int m = 0; m < TROWS; ++m)
+                if (m < nb) {
+                    const size_t r = (size_t)i * B + b0 + m;
+                    const int idx = lane * TROWS + m;
+                    cp_async16(sPa_addr + (uint32_t)((pb * BW_PAIRS + pre_slot4(idx)) * 16), a.G + r * H4 + 4 * ju);
+                    cp_async4(sPc_addr + (uint32_t)((pb * BW_PAIRS + pre_slot1(idx)) * 4), a.Cs + r * h + ju);
+                    // (each 128-byte line of dout is read exactly once, after the acquire on its tile flag: L1 cannot hold it stale)
+                    cp_async4(sPd_addr + (uint32_t)((pb * BW_PAIRS + pre_slot1(idx)) * 4),
+                              a.dout + (long long)i * a.out_si + (long long)(b0 + m) * a.out_sb + ju);
+                }
+            cp_async_arrive(&mbar_full[pb]);       // this lane's arrival fires when its copies above have landed
         }
     } else {
         // ===== epilogue / elementwise: pair e -> batch row m = idx % 16, unit ul = idx / 16 =====
         float dc[2];
         float4 p_act[2]; float p_c[2], p_cp[2], p_dout[2];
-        int tile_next = (T * B - 1) >> 7;          // a.tile_ready gating: tiles above this one are known complete (dout arrives last tile first)
-#define TILE_WAIT_REV(step) do { if (a.tile_ready) { const int need = ((step) * B + b0) >> 7; \
-            while (tile_next >= need) { spin_until_ge(a.tile_ready + tile_next, a.tile_target); --tile_next; } } } while (0)
-        TILE_WAIT_REV(T - 1);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int idx = tid + e * TC_EPI;
             const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
             const bool v = m < nb;
             dc[e] = (v && a.dc_fin) ? a.dc_fin[(size_t)(b0 + m) * a.ld_dc_fin + ju] : 0.f;
-            if (v) {
-                const size_t r = (size_t)(T - 1) * B + b0 + m;
-                p_act[e] = *reinterpret_cast<const float4*>(a.G + r * H4 + 4 * ju);
-                p_c[e] = a.Cs[(r + B) * h + ju]; p_cp[e] = a.Cs[r * h + ju];
-                p_dout[e] = __ldcg(a.dout + (long long)(T - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju);
-            } else { p_act[e] = make_float4(0.f, 0.f, 0.f, 0.f); p_c[e] = p_cp[e] = p_dout[e] = 0.f; }
+            p_c[e] = v ? a.Cs[((size_t)T * B + b0 + m) * h + ju] : 0.f;        // c_{T-1}; afterwards the previous step's c_{t-1}
+            p_act[e] = make_float4(0.f, 0.f, 0.f, 0.f); p_cp[e] = p_dout[e] = 0.f;
         }
         int step = 0;
         for (int i = T - 1; i >= 0; --i, ++step) {
             const int buf = i & 1;
             const bool send = i > 0 || a.dh0 != nullptr;
-            const float* rprev = red + (size_t)(buf ^ 1) * (BW_R_BYTES / 4);
+            const uint32_t rprev_addr = red_addr + (uint32_t)(buf ^ 1) * BW_R_BYTES;
+            {   // this step's prefetched operands (loader warp), read before the wait on the critical-path barrier
+                const int pb = step & 1;
+                mbar_wait(&mbar_full[pb], (step >> 1) & 1);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int idx = tid + e * TC_EPI;
+                    if ((idx & 15) < nb) {
+                        p_act[e] = lds_f4(sPa_addr + (uint32_t)((pb * BW_PAIRS + pre_slot4(idx)) * 16));
+                        p_cp[e] = lds_f1(sPc_addr + (uint32_t)((pb * BW_PAIRS + pre_slot1(idx)) * 4));
+                        p_dout[e] = lds_f1(sPd_addr + (uint32_t)((pb * BW_PAIRS + pre_slot1(idx)) * 4));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mbar_empty[pb]);
+            }
             if (i < T - 1) mbar_wait(&mbar_r[buf ^ 1], ((T - 2 - i) >> 1) & 1);     // partial dh of step i+1 from all CTAs
+            if (tid == 0) BPROBE(0);
             // 1. dG_t for the owned units (K-major UMMA operand, TF32-rounded)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -424,7 +525,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     } else {
                         dh = 0.f;
 #pragma unroll
-                        for (int s = 0; s < TNC; ++s) dh += rprev[(s * TU + ul) * TROWS + m];
+                        for (int s = 0; s < TNC; ++s) dh += lds_f1(rprev_addr + (uint32_t)(((s * TU + ul) * TROWS + m) * 4));
                     }
                     const size_t r = (size_t)i * B + b0 + m;
                     const float dm = dropout_scale(seed, a.drop_stream, (uint32_t)(r * h + ju) + a.drop_off, drop);
@@ -439,17 +540,17 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     dg.w = dh * tc * act.w * (1.f - act.w);
                     dc[e] = dct * act.z;
                     p_act[e] = dg;
+                    p_c[e] = cp;          // rotate here, where c_{t-1} is already in hand: a move after the prefetch load would wait for it
                 }
                 if (send)
-                    *reinterpret_cast<float4*>(sG + kmajor_off(m, 4 * ul, TROWS)) =
-                        make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w));
+                    sts_f4(sG_addr + kmajor_off(m, 4 * ul, TROWS), make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w)));
             }
+            if (tid == 0) BPROBE(1);
             if (send) {
                 fence_proxy_async();
                 mbar_arrive(mbar_g);              // hand the operand to the issuer warp
             }
-            // 2. bookkeeping while the tensor core works: write dG_t in place, prefetch step i-1
-            if (i > 0) TILE_WAIT_REV(i - 1);       // dout of step i-1 published?
+            // 2. bookkeeping while the tensor core works: write dG_t in place
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int idx = tid + e * TC_EPI;
@@ -457,21 +558,14 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 if (m < nb) {
                     const size_t r = (size_t)i * B + b0 + m;
                     *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = p_act[e];
-                    if (i > 0) {
-                        const size_t rp = r - B;
-                        p_act[e] = *reinterpret_cast<const float4*>(a.G + rp * H4 + 4 * ju);
-                        p_c[e] = p_cp[e]; p_cp[e] = a.Cs[rp * h + ju];
-                        p_dout[e] = __ldcg(a.dout + (long long)(i - 1) * a.out_si + (long long)(b0 + m) * a.out_sb + ju);
-                    }
                 }
             }
-            if ((T - i) % gt.chunk == 0 || i == 0) {
-                if (gt.ts && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gt.ts[(T - 1 - i) / gt.chunk] = t; }
-                if (gt.done) gate_signal(gt.done + (T - 1 - i) / gt.chunk, tid);
-            }
+            if ((T - i) % gt.chunk == 0 || i == 0) chunk_arrive(cnt_addr, lane);
+            if (tid == 0) BPROBE(2);
             if (send) {
                 // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
                 mbar_wait(mbar_mma, step & 1);
+                if (tid == 0) BPROBE(3);
                 tc_fence_after();
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (w >> 2) * TROWS, v);
@@ -479,17 +573,21 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 // warp w holds exactly the block owner CTA w needs ([32 units][16 batch] partials = 2 KB contiguous at the
                 // receiver): stage it and push it with ONE bulk copy per warp instead of 4 st.async per lane
                 const int owner = (w >> 2) * 4 + (w & 3);
-                float* stg = reinterpret_cast<float*>(sStg + (size_t)(buf * TNC + owner) * (TU * TROWS * 4)) + lane * TROWS;
+                const uint32_t stg = sStg_addr + (uint32_t)((buf * TNC + owner) * (TU * TROWS * 4));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stg + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)(lane * TROWS * 4 + 16 * j)),
+                                 "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
                 fence_proxy_async();
                 __syncwarp();
+                if (tid == 0) BPROBE(4);
                 if (lane == 0) {
                     const uint32_t dst = mapa(red_addr + (uint32_t)(((buf * TNC + rank) * TU) * TROWS * 4), owner);
                     const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
                     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst), "r"(saddr(stg)), "r"((uint32_t)(TU * TROWS * 4)), "r"(bar) : "memory");
+                                 ::"r"(dst), "r"(stg), "r"((uint32_t)(TU * TROWS * 4)), "r"(bar) : "memory");
                 }
+                if (tid == 0) BPROBE(5);
             }
         }
         // gradients w.r.t. the initial state (slot 0): the carry into the previous chunk of a longer sequence
@@ -503,7 +601,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     if (a.dh0) {
                         float s = 0.f;
 #pragma unroll
-                        for (int sidx = 0; sidx < TNC; ++sidx) s += red[(sidx * TU + ul) * TROWS + m];
+                        for (int sidx = 0; sidx < TNC; ++sidx) s += lds_f1(red_addr + (uint32_t)(((sidx * TU + ul) * TROWS + m) * 4));
                         a.dh0[(size_t)(b0 + m) * h + ju] = s;
                     }
                     if (a.dc0) a.dc0[(size_t)(b0 + m) * h + ju] = dc[e];
@@ -520,10 +618,11 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 template <class KernT>
 static int launch_tc(KernT kern, cudaStream_t st, int nchains, size_t smem, const LstmChains& ch, int T, int B,
                      float drop, unsigned long long seed, LstmGate gate = LstmGate{nullptr, 1, nullptr}) {
+    gate.probe = g_lstm_prof;
     AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nchains * TNC);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(BW_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -560,7 +659,7 @@ int lstm_seq_tc_max_clusters(bool backward) {
     const size_t smem = backward ? BW_SMEM : FW_SMEM;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(TNC * 64);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(backward ? BW_THREADS : TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
