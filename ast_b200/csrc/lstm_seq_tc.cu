@@ -123,7 +123,11 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) { float v; asm volatile("
 // ================================================================================================
 constexpr uint32_t FW_A_BYTES = 8 * 128 * 128;          // W slice: 8 k-blocks x 128 gate rows x 128 B
 constexpr uint32_t FW_TMEM_D = 0;                       // accumulator column
-constexpr uint32_t FW_TMEM_COLS = 32;
+#ifndef FW_NACC
+#define FW_NACC 1
+#endif
+constexpr int FW_ACC = FW_NACC;                         // independent accumulators the k-steps rotate over (summed in the epilogue)
+constexpr uint32_t FW_TMEM_COLS = FW_ACC * TROWS <= 32 ? 32 : 64;
 constexpr uint32_t FW_H_BYTES = 8 * TROWS * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B
 constexpr uint32_t FW_XG_BYTES = 4 * TROWS * TU * 4;    // gate exchange [gate][batch][unit]
 constexpr uint32_t FW_STG_BYTES = 2 * TROWS * 128;      // [2] staging of this CTA's h slice (= one k-block of the operand layout)
@@ -132,7 +136,10 @@ constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long long seed, unsigned long long* prof, LstmGate gt) {
     const bool probe = prof != nullptr && blockIdx.x == 0 && ch.c[0].drop_stream <= 1;      // stand-alone launches (0) or (layer 0, forward direction)
-#define PROBE(slot) do { if (probe && i >= 8 && i < 24) prof[(i - 8) * 8 + (slot)] = clock64(); } while (0)
+    // stamps stay in registers until the end of the step: a global store in front of a fence would be waited for by that fence
+    uint32_t pst[8];
+#define PROBE(slot) do { if (probe) pst[slot] = (uint32_t)clock(); } while (0)
+#define PROBE_FLUSH(first, last) do { if (probe && i >= 8 && i < 24) { for (int q_ = (first); q_ <= (last); ++q_) prof[(i - 8) * 8 + q_] = pst[q_]; } } while (0)
     const int rank = (int)cluster_rank();
     if (gt.resident && threadIdx.x == 0) atomicAdd(gt.resident, 1u);       // this CTA holds its SM from here on
     const LstmChain a = ch.c[blockIdx.x / TNC];
@@ -222,10 +229,11 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 for (int kb = 0; kb < 8; ++kb)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_tf32_ss(tmem_base, a0 + (uint64_t)((kb * 16384 + ks * 32) >> 4),
-                                     bcur + (uint64_t)((kb * (TROWS * 128) + ks * 32) >> 4), idesc, (kb | ks) ? 1u : 0u);
+                        umma_tf32_ss(tmem_base + (uint32_t)(((kb * 4 + ks) % FW_ACC) * TROWS), a0 + (uint64_t)((kb * 16384 + ks * 32) >> 4),
+                                     bcur + (uint64_t)((kb * (TROWS * 128) + ks * 32) >> 4), idesc, (kb * 4 + ks) >= FW_ACC ? 1u : 0u);
                 umma_commit_arrive(mbar_mma);
                 PROBE(1);
+                PROBE_FLUSH(0, 1);
             }
         }
     } else if (w == 9) {
@@ -256,6 +264,13 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             {
                 float v[8];
                 tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + 8 * bh, v);
+#pragma unroll
+                for (int q = 1; q < FW_ACC; ++q) {
+                    float v2[8];
+                    tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + q * TROWS + 8 * bh, v2);
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) v[b] += v2[b];
+                }
                 tc_fence_before();
 #pragma unroll
                 for (int b = 0; b < 8; ++b) sts_f1(xg_addr + (uint32_t)(((gate * TROWS + 8 * bh + b) * TU + lane) * 4), v[b]);
@@ -313,10 +328,11 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 }
             }
             if ((i + 1) % gt.chunk == 0 || i + 1 == T) chunk_arrive(cnt_addr, lane);
-            if (tid == 0) PROBE(6);
+            if (tid == 0) { PROBE(6); PROBE_FLUSH(2, 6); }
         }
     }
 #undef PROBE
+#undef PROBE_FLUSH
 #undef TILE_WAIT
     tc_fence_before();
     __syncthreads();
@@ -358,7 +374,10 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     // cycle probe (tools/lstm_step_probe.py --bwd): CTA 0 of the launch whose first chain is (layer 0, forward direction) stamps
     // clock64 for its 9th..24th processed step into probe[128 + 8 k + slot]
     unsigned long long* const bprof = (gt.probe && blockIdx.x == 0 && a.drop_stream == 1) ? gt.probe + 128 : nullptr;
-#define BPROBE(slot) do { if (bprof && step >= 8 && step < 24) bprof[(step - 8) * 8 + (slot)] = clock64(); } while (0)
+    // layout: [16 steps][16] = epilogue thread 0 slots 0..7, epilogue thread 224 (warp 7) slots 8..15; then [16 steps][2] of the issuer.
+    // Stamps stay in registers until the end of the step (a global store in front of a fence would be waited for by that fence).
+    uint32_t pst[8];
+#define BPROBE(slot) do { if (bprof) pst[slot] = (uint32_t)clock(); } while (0)
     constexpr int h = TH, H4 = 4 * TH;
     const int nb = a.nb, b0 = a.b0;
     extern __shared__ uint8_t smem_raw[];
@@ -434,7 +453,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             for (int i = T - 1; i >= i_last; --i, ++step) {
                 mbar_expect_tx(&mbar_r[i & 1], BW_R_BYTES);       // arm the reduce buffer this step's sends fill
                 mbar_wait(mbar_g, step & 1);                      // dG_i operand complete in smem
-                BPROBE(6);
+                BPROBE(0);
                 tc_fence_after();
                 // dh^T (256 x 16) = W_slice^T (256 x 128) · dG^T (128 x 16): two M = 128 halves, 16 k-steps each
 #pragma unroll
@@ -444,7 +463,8 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                         umma_tf32_ss(tmem_base + hm * TROWS, a0 + (uint64_t)((hm * 4 * 16384 + ks * 1024) >> 4),
                                      g0 + (uint64_t)(((ks >> 2) * (TROWS * 128) + (ks & 3) * 32) >> 4), idesc, ks ? 1u : 0u);
                 umma_commit_arrive(mbar_mma);
-                BPROBE(7);
+                BPROBE(1);
+                if (bprof && step >= 8 && step < 24) { bprof[256 + (step - 8) * 2] = pst[0]; bprof[256 + (step - 8) * 2 + 1] = pst[1]; }
             }
         }
     } else if (w == 10) {
@@ -511,7 +531,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 if (lane == 0) mbar_arrive(&mbar_empty[pb]);
             }
             if (i < T - 1) mbar_wait(&mbar_r[buf ^ 1], ((T - 2 - i) >> 1) & 1);     // partial dh of step i+1 from all CTAs
-            if (tid == 0) BPROBE(0);
+            BPROBE(0);
             // 1. dG_t for the owned units (K-major UMMA operand, TF32-rounded)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -545,31 +565,29 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 if (send)
                     sts_f4(sG_addr + kmajor_off(m, 4 * ul, TROWS), make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w)));
             }
-            if (tid == 0) BPROBE(1);
+            BPROBE(1);
             if (send) {
                 fence_proxy_async();
                 mbar_arrive(mbar_g);              // hand the operand to the issuer warp
             }
-            // 2. bookkeeping while the tensor core works: write dG_t in place
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int idx = tid + e * TC_EPI;
-                const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul;
-                if (m < nb) {
-                    const size_t r = (size_t)i * B + b0 + m;
-                    *reinterpret_cast<float4*>(a.G + r * H4 + 4 * ju) = p_act[e];
-                }
-            }
-            if ((T - i) % gt.chunk == 0 || i == 0) chunk_arrive(cnt_addr, lane);
-            if (tid == 0) BPROBE(2);
+            BPROBE(2);
+#define BW_STORE_DG() do { _Pragma("unroll") for (int e = 0; e < 2; ++e) { \
+                const int idx = tid + e * TC_EPI; const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul; \
+                if (m < nb) *reinterpret_cast<float4*>(a.G + ((size_t)i * B + b0 + m) * H4 + 4 * ju) = p_act[e]; } \
+            if ((T - i) % gt.chunk == 0 || i == 0) chunk_arrive(cnt_addr, lane); } while (0)
+#ifndef BW_STORE_LATE
+            BW_STORE_DG();                         // 2. bookkeeping while the tensor core works: write dG_t in place
+#endif
+            BPROBE(3);
             if (send) {
                 // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
                 mbar_wait(mbar_mma, step & 1);
-                if (tid == 0) BPROBE(3);
+                BPROBE(4);
                 tc_fence_after();
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (w >> 2) * TROWS, v);
                 tc_fence_before();
+                BPROBE(5);
                 // warp w holds exactly the block owner CTA w needs ([32 units][16 batch] partials = 2 KB contiguous at the
                 // receiver): stage it and push it with ONE bulk copy per warp instead of 4 st.async per lane
                 const int owner = (w >> 2) * 4 + (w & 3);
@@ -580,14 +598,21 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                                  "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
                 fence_proxy_async();
                 __syncwarp();
-                if (tid == 0) BPROBE(4);
+                BPROBE(6);
                 if (lane == 0) {
                     const uint32_t dst = mapa(red_addr + (uint32_t)(((buf * TNC + rank) * TU) * TROWS * 4), owner);
                     const uint32_t bar = mapa(saddr(&mbar_r[buf]), owner);
                     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(dst), "r"(stg), "r"((uint32_t)(TU * TROWS * 4)), "r"(bar) : "memory");
                 }
-                if (tid == 0) BPROBE(5);
+                BPROBE(7);
+            }
+#ifdef BW_STORE_LATE
+            BW_STORE_DG();
+#endif
+            if (bprof && step >= 8 && step < 24 && (tid == 0 || tid == 224)) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) bprof[(step - 8) * 16 + (tid ? 8 : 0) + q] = pst[q];
             }
         }
         // gradients w.r.t. the initial state (slot 0): the carry into the previous chunk of a longer sequence

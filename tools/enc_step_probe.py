@@ -17,7 +17,7 @@ e.set_option("exact", 0); e.set_option("tc_gemm", 1)
 X = torch.as_tensor(rng.standard_normal((32, a.T, 40)).astype(np.float32), device=e.device)
 y = rng.integers(4, 1098, (32, a.L)).astype(np.int32); y[:, 0] = 1; y[:, -1] = 2
 y = torch.as_tensor(y, device=e.device)
-prof = torch.zeros(256, dtype=torch.int64, device=e.device)
+prof = torch.zeros(512, dtype=torch.int64, device=e.device)
 for it in range(4):
     if it == 3:
         check(lib.ast_lstm_probe(ptr(prof)))
@@ -25,17 +25,21 @@ for it in range(4):
 torch.cuda.synchronize()
 check(lib.ast_lstm_probe(None))
 print("persistent wavefront active:", bool(e.get_option("enc_persist_active") == 1))
-p = prof.cpu().numpy().astype(np.float64)
+p = prof.cpu().numpy().astype(np.int64)
+rel = lambda x, x0: ((x - x0) & 0xFFFFFFFF).astype(np.float64)          # 32-bit clock stamps
 f = p[:128].reshape(16, 8)[:, :7]
 names = ["h landed (issuer)", "MMAs issued + commit", "accumulator ready (epilogue)", "gates exchanged", "cell math done", "h sent", "bookkeeping done"]
-st = np.diff(f[:, 0])
-print(f"forward step period: median {np.median(st):.0f} cycles = {np.median(st) / 1.965e3:.2f} us")
+st = rel(f[1:, 0], f[:-1, 0])
+print(f"forward step period: median {np.median(st):.0f} cycles = {np.median(st) / 1.965e3:.2f} us; per step:", " ".join(f"{x:.0f}" for x in st))
 for k in range(7):
-    print(f"  {names[k]:34s} +{np.median(f[:, k] - f[:, 0]):7.0f}")
-b = p[128:].reshape(16, 8)
-names = ["partial dh of all CTAs landed", "dG computed, operand in smem", "bookkeeping done (dG store, prefetch, tile wait, chunk signal)",
-         "MMAs retired (epilogue sees commit)", "partial dh staged", "bulk sends issued", "operand ready (issuer)", "MMAs issued + commit (issuer)"]
-st = np.diff(b[:, 0])
-print(f"backward step period: median {np.median(st):.0f} cycles = {np.median(st) / 1.965e3:.2f} us")
-for k in (0, 1, 6, 7, 2, 3, 4, 5):
-    print(f"  {names[k]:62s} +{np.median(b[:, k] - b[:, 0]):7.0f}")
+    print(f"  {names[k]:34s} +{np.median(rel(f[:, k], f[:, 0])):7.0f}")
+b = p[128:384].reshape(16, 16); iss = p[384:416].reshape(16, 2)
+names = ["partial dh of all CTAs landed", "dG computed, operand in smem", "proxy fence + arrive done", "dG stored / bookkeeping done",
+         "MMAs retired (epilogue sees commit)", "accumulator in registers", "partial dh staged (fence + syncwarp)", "bulk send issued"]
+st = rel(b[1:, 0], b[:-1, 0])
+print(f"backward step period: median {np.median(st):.0f} cycles = {np.median(st) / 1.965e3:.2f} us; per step:", " ".join(f"{x:.0f}" for x in st))
+print(f"  {'':40s} {'warp 0':>8s} {'warp 7':>8s}")
+for k in range(8):
+    print(f"  {names[k]:40s} +{np.median(rel(b[:, k], b[:, 0])):7.0f} +{np.median(rel(b[:, 8 + k], b[:, 0])):7.0f}")
+print(f"  {'operand ready (issuer)':40s} +{np.median(rel(iss[:, 0], b[:, 0])):7.0f}")
+print(f"  {'MMAs issued + commit (issuer)':40s} +{np.median(rel(iss[:, 1], b[:, 0])):7.0f}")
