@@ -17,6 +17,7 @@
 // producing CTA), so the tensor core never truncates.  Backward uses the same trick for dh^T (256 x 16) =
 // W_slice^T (256 x 128, M-major operand in the SWIZZLE_128B_BASE32B layout) · dG^T (128 x 16).
 #include "cluster_dev.cuh"
+#include <cuda_fp16.h>
 #include "kernels.h"
 
 namespace ast {
@@ -105,6 +106,17 @@ __device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows_per_bloc
     return (uint32_t)(kb * rows_per_block * 128 + row * 128 + ((c ^ (row & 7)) << 4) + ((k & 3) << 2));
 }
 
+// the same for 2-byte operands: K-major SWIZZLE_64B, k-blocks of 32 elements = [rows][64 B], 16-byte chunks XOR-ed with (row / 2) % 4
+__device__ __forceinline__ uint32_t kmajor_off_h(int row, int k, int rows_per_block) {
+    const int kb = k >> 5, c = (k & 31) >> 3;
+    return (uint32_t)(kb * rows_per_block * 64 + row * 64 + ((c ^ ((row >> 1) & 3)) << 4) + ((k & 7) << 1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+    const __half2 hh = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&hh);
+}
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+
 // explicit shared-state-space accesses: the carve-up pointers come from an aligned-up integer, through which the compiler can only
 // emit generic LD/ST
 __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
@@ -121,16 +133,26 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) { float v; asm volatile("
 // ================================================================================================
 // forward
 // ================================================================================================
-constexpr uint32_t FW_A_BYTES = 8 * 128 * 128;          // W slice: 8 k-blocks x 128 gate rows x 128 B
+// Operand type of the forward recurrence.  FP16 carries the same 11-bit significand as TF32 (h is in (-1, 1), recurrent weights are
+// far inside +-65504, values under 6e-5 keep an absolute error of 3e-8), but one tcgen05.mma covers K = 16 instead of 8: the 128x16xK
+// instruction costs ~60 cycles whatever K is (tools/enc_step_probe.py: 32 of them = 1920 of a step's 4050 cycles, independent
+// accumulators change nothing), so 16 instructions instead of 32 - and the h all-gather moves half the bytes.
+#ifdef FW_OPERAND_TF32
+constexpr bool FW_F16 = false;
+#else
+constexpr bool FW_F16 = true;
+#endif
+constexpr uint32_t FW_ROWB = FW_F16 ? 64 : 128;         // bytes of one operand row inside a k-block of 32 hidden units
+constexpr uint32_t FW_A_BYTES = 8 * 128 * FW_ROWB;      // W slice: 8 k-blocks x 128 gate rows
 constexpr uint32_t FW_TMEM_D = 0;                       // accumulator column
 #ifndef FW_NACC
 #define FW_NACC 1
 #endif
 constexpr int FW_ACC = FW_NACC;                         // independent accumulators the k-steps rotate over (summed in the epilogue)
 constexpr uint32_t FW_TMEM_COLS = FW_ACC * TROWS <= 32 ? 32 : 64;
-constexpr uint32_t FW_H_BYTES = 8 * TROWS * 128;        // one h buffer: 8 k-blocks x 16 rows x 128 B
+constexpr uint32_t FW_H_BYTES = 8 * TROWS * FW_ROWB;    // one h buffer: 8 k-blocks x 16 rows
 constexpr uint32_t FW_XG_BYTES = 4 * TROWS * TU * 4;    // gate exchange [gate][batch][unit]
-constexpr uint32_t FW_STG_BYTES = 2 * TROWS * 128;      // [2] staging of this CTA's h slice (= one k-block of the operand layout)
+constexpr uint32_t FW_STG_BYTES = 2 * TROWS * FW_ROWB;  // [2] staging of this CTA's h slice (= one k-block of the operand layout)
 constexpr uint32_t FW_SMEM = FW_A_BYTES + 2 * FW_H_BYTES + FW_XG_BYTES + FW_STG_BYTES + 64 + 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -192,16 +214,24 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             const int idx = base + u * TC_THREADS + tid;
             if (idx < 128 * (h / 4)) {
                 const int p = idx / (h / 4), k4 = idx % (h / 4);
-                *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) =
-                    make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
+                if constexpr (FW_F16)
+                    *reinterpret_cast<uint2*>(sA + kmajor_off_h(p, 4 * k4, 128)) =
+                        make_uint2(pack_h2(clamp_h(v[u].x), clamp_h(v[u].y)), pack_h2(clamp_h(v[u].z), clamp_h(v[u].w)));
+                else
+                    *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) =
+                        make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
             }
         }
     }
     for (int idx = tid; idx < nb * (h / 4); idx += TC_THREADS) {          // h_{-1} (slot 0 of Hs) into buffer 0
         const int m = idx / (h / 4), k4 = idx % (h / 4);
         float4 v = *reinterpret_cast<const float4*>(a.Hs + (size_t)(b0 + m) * h + k4 * 4);
-        v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
-        *reinterpret_cast<float4*>(sH + kmajor_off(m, 4 * k4, TROWS)) = v;
+        if constexpr (FW_F16) {
+            *reinterpret_cast<uint2*>(sH + kmajor_off_h(m, 4 * k4, TROWS)) = make_uint2(pack_h2(clamp_h(v.x), clamp_h(v.y)), pack_h2(clamp_h(v.z), clamp_h(v.w)));
+        } else {
+            v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
+            *reinterpret_cast<float4*>(sH + kmajor_off(m, 4 * k4, TROWS)) = v;
+        }
     }
     fence_proxy_async();                  // generic-proxy writes of the operands -> visible to the tensor core
     tc_fence_before();
@@ -214,9 +244,9 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     if (w == 8) {
         // ===== MMA issuer: one thread, nothing else on its plate =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(128, TROWS, false, false);
-            const uint64_t a0 = umma_smem_desc(saddr(sA), 16, 1024, 2);
-            const uint64_t b0d = umma_smem_desc(sH_addr, 16, 1024, 2);
+            const uint32_t idesc = FW_F16 ? umma_idesc_f16(128, TROWS, false, false) : umma_idesc_tf32(128, TROWS, false, false);
+            const uint64_t a0 = umma_smem_desc(saddr(sA), 16, 8 * FW_ROWB, FW_F16 ? 4 : 2);       // SWIZZLE_64B / SWIZZLE_128B, 8-row groups
+            const uint64_t b0d = umma_smem_desc(sH_addr, 16, 8 * FW_ROWB, FW_F16 ? 4 : 2);
             for (int i = 0; i < T; ++i) {
                 const int cur = i & 1;
                 if (i + 1 < T) mbar_expect_tx(&mbar_h[cur ^ 1], FW_H_BYTES);    // arm the buffer this step fills
@@ -225,12 +255,17 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 fence_proxy_async();
                 tc_fence_after();
                 const uint64_t bcur = b0d + (uint64_t)((cur * FW_H_BYTES) >> 4);
+                constexpr int KS = FW_ROWB / 32;             // instructions per k-block: 32 bytes of K each
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb)
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_tf32_ss(tmem_base + (uint32_t)(((kb * 4 + ks) % FW_ACC) * TROWS), a0 + (uint64_t)((kb * 16384 + ks * 32) >> 4),
-                                     bcur + (uint64_t)((kb * (TROWS * 128) + ks * 32) >> 4), idesc, (kb * 4 + ks) >= FW_ACC ? 1u : 0u);
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const uint64_t ad = a0 + (uint64_t)((kb * (128 * FW_ROWB) + ks * 32) >> 4);
+                        const uint64_t bd = bcur + (uint64_t)((kb * (TROWS * FW_ROWB) + ks * 32) >> 4);
+                        const uint32_t dcol = tmem_base + (uint32_t)(((kb * KS + ks) % FW_ACC) * TROWS);
+                        if constexpr (FW_F16) umma_f16_ss(dcol, ad, bd, idesc, (kb * KS + ks) >= FW_ACC ? 1u : 0u);
+                        else umma_tf32_ss(dcol, ad, bd, idesc, (kb * KS + ks) >= FW_ACC ? 1u : 0u);
+                    }
                 umma_commit_arrive(mbar_mma);
                 PROBE(1);
                 PROBE_FLUSH(0, 1);
@@ -296,19 +331,24 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 // [16 rows][128 B, 16-byte chunks XOR-ed with row % 8].  Stage it locally (TF32-rounded) and push it to all 8
                 // CTAs with ONE bulk copy each (cp.async.bulk smem -> dsmem, completing bytes on the receiver's mbarrier)
                 // instead of 4 st.async + 8 mapa per thread (measured: the send section was 1340 of a step's 4500 cycles).
-                const uint32_t stg = sStg_addr + (uint32_t)(nxt * (TROWS * 128));
+                const uint32_t stg = sStg_addr + (uint32_t)(nxt * (TROWS * FW_ROWB));
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int b = 2 * w + j;
-                    sts_f1(stg + (uint32_t)(b * 128 + ((((lane >> 2) ^ (b & 7))) << 4) + ((lane & 3) << 2)), rnd_tf32(hv[j]));
+                    if constexpr (FW_F16) {
+                        const unsigned short hb = __half_as_ushort(__float2half_rn(hv[j]));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(b * 64 + ((((lane >> 3) ^ ((b >> 1) & 3))) << 4) + ((lane & 7) << 1))), "h"(hb) : "memory");
+                    } else {
+                        sts_f1(stg + (uint32_t)(b * 128 + ((((lane >> 2) ^ (b & 7))) << 4) + ((lane & 3) << 2)), rnd_tf32(hv[j]));
+                    }
                 }
                 fence_proxy_async();
                 epi_barrier();
                 if (tid < TNC) {
-                    const uint32_t dst = mapa(sH_addr + nxt * FW_H_BYTES + (uint32_t)rank * (TROWS * 128), tid);
+                    const uint32_t dst = mapa(sH_addr + nxt * FW_H_BYTES + (uint32_t)rank * (TROWS * FW_ROWB), tid);
                     const uint32_t bar = mapa(saddr(&mbar_h[nxt]), tid);
                     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst), "r"(stg), "r"((uint32_t)(TROWS * 128)), "r"(bar) : "memory");
+                                 ::"r"(dst), "r"(stg), "r"((uint32_t)(TROWS * FW_ROWB)), "r"(bar) : "memory");
                 }
             }
             if (tid == 0) PROBE(5);
