@@ -115,7 +115,6 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     const __half2 hh = __floats2half2_rn(x, y);
     return *reinterpret_cast<const uint32_t*>(&hh);
 }
-__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 
 // explicit shared-state-space accesses: the carve-up pointers come from an aligned-up integer, through which the compiler can only
 // emit generic LD/ST
@@ -216,7 +215,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 const int p = idx / (h / 4), k4 = idx % (h / 4);
                 if constexpr (FW_F16)
                     *reinterpret_cast<uint2*>(sA + kmajor_off_h(p, 4 * k4, 128)) =
-                        make_uint2(pack_h2(clamp_h(v[u].x), clamp_h(v[u].y)), pack_h2(clamp_h(v[u].z), clamp_h(v[u].w)));
+                        make_uint2(pack_h2(v[u].x, v[u].y), pack_h2(v[u].z, v[u].w));
                 else
                     *reinterpret_cast<float4*>(sA + kmajor_off(p, 4 * k4, 128)) =
                         make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
@@ -227,7 +226,7 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
         const int m = idx / (h / 4), k4 = idx % (h / 4);
         float4 v = *reinterpret_cast<const float4*>(a.Hs + (size_t)(b0 + m) * h + k4 * 4);
         if constexpr (FW_F16) {
-            *reinterpret_cast<uint2*>(sH + kmajor_off_h(m, 4 * k4, TROWS)) = make_uint2(pack_h2(clamp_h(v.x), clamp_h(v.y)), pack_h2(clamp_h(v.z), clamp_h(v.w)));
+            *reinterpret_cast<uint2*>(sH + kmajor_off_h(m, 4 * k4, TROWS)) = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
         } else {
             v.x = rnd_tf32(v.x); v.y = rnd_tf32(v.y); v.z = rnd_tf32(v.z); v.w = rnd_tf32(v.w);
             *reinterpret_cast<float4*>(sH + kmajor_off(m, 4 * k4, TROWS)) = v;
@@ -383,8 +382,19 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 // ================================================================================================
 // backward
 // ================================================================================================
-constexpr uint32_t BW_A_BYTES = 8 * 128 * 128;          // W slice as M-major operand: 8 unit-chunks x 128 gate rows x 128 B
-constexpr uint32_t BW_G_BYTES = 4 * TROWS * 128;        // dG: 4 k-blocks x 16 batch rows x 128 B (K-major)
+// Operand type of the backward recurrence.  FP16 (K = 16 per instruction: 16 MMAs instead of 32, see the forward kernel) needs a
+// range guard for dG: every step the CTA takes the exact maximum |dG| of its operand (warp redux + shared atomic + one barrier of
+// the epilogue warps), scales by the power of two that puts it in [256, 512) and un-scales its partial dh after the accumulator
+// read - exact, so the operand keeps TF32's 11-bit significand for everything within 2^-22 of the maximum and an absolute floor
+// 2^-33 of it below.  The weight sits transposed (K-major, k = gate row) so that both operands use the plain SWIZZLE_64B layout.
+#ifdef BW_OPERAND_TF32
+constexpr bool BW_F16 = false;
+#else
+constexpr bool BW_F16 = true;
+#endif
+constexpr uint32_t BW_A_BYTES = BW_F16 ? 4 * 256 * 64   // W^T: 4 k-blocks (32 gate rows) x 256 unit rows x 64 B (K-major)
+                                       : 8 * 128 * 128; // W slice as M-major operand: 8 unit-chunks x 128 gate rows x 128 B
+constexpr uint32_t BW_G_BYTES = 4 * TROWS * (BW_F16 ? 64 : 128);   // dG: 4 k-blocks x 16 batch rows (K-major)
 constexpr uint32_t BW_R_BYTES = TNC * TU * TROWS * 4;   // one reduce buffer [src][unit][batch]
 constexpr uint32_t BW_STG_BYTES = 2 * TNC * TU * TROWS * 4;   // [2][owner] staging of the partial dh blocks (2 KB per owner)
 constexpr int BW_THREADS = TC_EPI + 96;                 // epilogue warps 0..7, MMA issuer warp 8, loader warp 9, chunk signaller warp 10
@@ -441,23 +451,47 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
 
     // W slice rows p = 4*unit + gate (natural order, = dG's k index), all 256 unit columns n:
     // chunk j = n/32 at j*16 KB, k-row p at p*128 B, 32-byte sub-chunk ((n%32)/8) XOR (p % 4)
-    for (int base = 0; base < 128 * (h / 4); base += 8 * BW_THREADS) {      // batched loads, see the forward kernel
-        float4 v[8];
+    if constexpr (BW_F16) {
+        // item = (quad of gate rows p4, unit column n): four coalesced loads, one 8-byte store of element (row n, k = 4 p4 ..)
+        for (int base = 0; base < 32 * h; base += 4 * BW_THREADS) {
+            float v[4][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * BW_THREADS + tid;
-            if (idx < 128 * (h / 4)) {
-                const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
-                v[u] = __ldg(reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n));
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * BW_THREADS + tid;
+                if (idx < 32 * h) {
+                    const int p4 = idx / h, n = idx % h;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[u][q] = __ldg(a.Wl + (size_t)(128 * rank + 4 * p4 + q) * h + n);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * BW_THREADS + tid;
+                if (idx < 32 * h) {
+                    const int p4 = idx / h, n = idx % h;
+                    *reinterpret_cast<uint2*>(sA + kmajor_off_h(n, 4 * p4, h)) = make_uint2(pack_h2(v[u][0], v[u][1]), pack_h2(v[u][2], v[u][3]));
+                }
             }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * BW_THREADS + tid;
-            if (idx < 128 * (h / 4)) {
-                const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
-                const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
-                *reinterpret_cast<float4*>(sA + off) = make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
+    } else {
+    for (int base = 0; base < 128 * (h / 4); base += 8 * BW_THREADS) {      // batched loads, see the forward kernel
+            float4 v[8];
+    #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * BW_THREADS + tid;
+                if (idx < 128 * (h / 4)) {
+                    const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
+                    v[u] = __ldg(reinterpret_cast<const float4*>(a.Wl + (size_t)(128 * rank + p) * h + n));
+                }
+            }
+    #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * BW_THREADS + tid;
+                if (idx < 128 * (h / 4)) {
+                    const int p = idx / (h / 4), n = 4 * (idx % (h / 4));
+                    const uint32_t off = (uint32_t)((n >> 5) * 16384 + p * 128 + (((((n & 31) >> 3) ^ (p & 3))) << 5) + ((n & 7) << 2));
+                    *reinterpret_cast<float4*>(sA + off) = make_float4(rnd_tf32(v[u].x), rnd_tf32(v[u].y), rnd_tf32(v[u].z), rnd_tf32(v[u].w));
+                }
             }
         }
     }
@@ -465,7 +499,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     for (int idx = tid; idx < (int)(2 * BW_R_BYTES / 16); idx += BW_THREADS) reinterpret_cast<float4*>(red)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         mbar_init(&mbar_r[0], 1); mbar_init(&mbar_r[1], 1); mbar_init(mbar_mma, 1); mbar_init(mbar_g, TC_EPI);
-        *chunk_cnt = 0u;
+        *chunk_cnt = 0u; chunk_cnt[1] = 0u; chunk_cnt[2] = 0u;      // [1], [2]: the per-step |dG| maximum (FP16 operand scale)
         mbar_init(&mbar_full[0], 32); mbar_init(&mbar_full[1], 32); mbar_init(&mbar_empty[0], TC_EPI / 32); mbar_init(&mbar_empty[1], TC_EPI / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -479,15 +513,15 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t sA_addr = saddr(sA), sG_addr = saddr(sG), red_addr = saddr(red), sStg_addr = saddr(sStg);
-    const uint32_t sPa_addr = saddr(sPa), sPc_addr = saddr(sPc), sPd_addr = saddr(sPd), cnt_addr = saddr(chunk_cnt);
+    const uint32_t sPa_addr = saddr(sPa), sPc_addr = saddr(sPc), sPd_addr = saddr(sPd), cnt_addr = saddr(chunk_cnt), amax_addr = cnt_addr + 4;
     cluster_sync_all();
 
     if (w == 8) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(128, TROWS, true, false);
-            const uint64_t a0 = umma_smem_desc(sA_addr, 16384, 512, 1);
-            const uint64_t g0 = umma_smem_desc(sG_addr, 16, 1024, 2);
+            const uint32_t idesc = BW_F16 ? umma_idesc_f16(128, TROWS, false, false) : umma_idesc_tf32(128, TROWS, true, false);
+            const uint64_t a0 = BW_F16 ? umma_smem_desc(sA_addr, 16, 512, 4) : umma_smem_desc(sA_addr, 16384, 512, 1);
+            const uint64_t g0 = BW_F16 ? umma_smem_desc(sG_addr, 16, 512, 4) : umma_smem_desc(sG_addr, 16, 1024, 2);
             int step = 0;
             const int i_last = a.dh0 ? 0 : 1;       // dh0 requested: step 0 also sends (gradient w.r.t. the initial h)
             for (int i = T - 1; i >= i_last; --i, ++step) {
@@ -497,11 +531,20 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 tc_fence_after();
                 // dh^T (256 x 16) = W_slice^T (256 x 128) · dG^T (128 x 16): two M = 128 halves, 16 k-steps each
 #pragma unroll
-                for (int hm = 0; hm < 2; ++hm)
+                for (int hm = 0; hm < 2; ++hm) {
+                    if constexpr (BW_F16) {
+                        // K-major W^T: k-block kb at kb * 256 rows * 64 B, unit half hm at + 128 rows * 64 B; 8 k-steps of 16
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)
-                        umma_tf32_ss(tmem_base + hm * TROWS, a0 + (uint64_t)((hm * 4 * 16384 + ks * 1024) >> 4),
-                                     g0 + (uint64_t)(((ks >> 2) * (TROWS * 128) + (ks & 3) * 32) >> 4), idesc, ks ? 1u : 0u);
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_f16_ss(tmem_base + hm * TROWS, a0 + (uint64_t)(((ks >> 1) * (256 * 64) + hm * (128 * 64) + (ks & 1) * 32) >> 4),
+                                        g0 + (uint64_t)(((ks >> 1) * (TROWS * 64) + (ks & 1) * 32) >> 4), idesc, ks ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 16; ++ks)
+                            umma_tf32_ss(tmem_base + hm * TROWS, a0 + (uint64_t)((hm * 4 * 16384 + ks * 1024) >> 4),
+                                         g0 + (uint64_t)(((ks >> 2) * (TROWS * 128) + (ks & 3) * 32) >> 4), idesc, ks ? 1u : 0u);
+                    }
+                }
                 umma_commit_arrive(mbar_mma);
                 BPROBE(1);
                 if (bprof && step >= 8 && step < 24) { bprof[256 + (step - 8) * 2] = pst[0]; bprof[256 + (step - 8) * 2 + 1] = pst[1]; }
@@ -602,8 +645,42 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     p_act[e] = dg;
                     p_c[e] = cp;          // rotate here, where c_{t-1} is already in hand: a move after the prefetch load would wait for it
                 }
-                if (send)
-                    sts_f4(sG_addr + kmajor_off(m, 4 * ul, TROWS), make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w)));
+                if constexpr (!BW_F16) {
+                    if (send)
+                        sts_f4(sG_addr + kmajor_off(m, 4 * ul, TROWS), make_float4(rnd_tf32(dg.x), rnd_tf32(dg.y), rnd_tf32(dg.z), rnd_tf32(dg.w)));
+                }
+            }
+            float unscale = 1.f;
+            if constexpr (BW_F16) {
+                if (send) {
+                    // exact |dG| maximum of the CTA's operand -> power-of-two scale into fp16's comfortable range
+                    uint32_t mx = 0u;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        mx = max(max(mx, __float_as_uint(fabsf(p_act[e].x))), max(max(__float_as_uint(fabsf(p_act[e].y)), __float_as_uint(fabsf(p_act[e].z))),
+                                                                                  __float_as_uint(fabsf(p_act[e].w))));
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    const uint32_t slot = amax_addr + (uint32_t)((step & 1) * 4);
+                    if (lane == 0) asm volatile("red.shared::cta.max.u32 [%0], %1;" ::"r"(slot), "r"(mx) : "memory");
+                    epi_barrier();
+                    uint32_t am;
+                    asm volatile("ld.shared::cta.u32 %0, [%1];" : "=r"(am) : "r"(slot) : "memory");
+                    if (tid == 0) asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(amax_addr + (uint32_t)(((step & 1) ^ 1) * 4)), "r"(0u) : "memory");
+                    float scale = 1.f;
+                    if (am != 0u) {
+                        const int E = min(max((int)((am >> 23) & 0xFFu), 9), 253);
+                        scale = __uint_as_float((uint32_t)(262 - E) << 23);        // max * scale in [256, 512)
+                        unscale = __uint_as_float((uint32_t)(E - 8) << 23);        // exactly 1 / scale
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int idx = tid + e * TC_EPI;
+                        const int m = idx & 15, ul = idx >> 4;
+                        const float4 dg = p_act[e];
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sG_addr + kmajor_off_h(m, 4 * ul, TROWS)),
+                                     "r"(pack_h2(dg.x * scale, dg.y * scale)), "r"(pack_h2(dg.z * scale, dg.w * scale)) : "memory");
+                    }
+                }
             }
             BPROBE(1);
             if (send) {
@@ -627,6 +704,10 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (w >> 2) * TROWS, v);
                 tc_fence_before();
+                if constexpr (BW_F16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= unscale;
+                }
                 BPROBE(5);
                 // warp w holds exactly the block owner CTA w needs ([32 units][16 batch] partials = 2 KB contiguous at the
                 // receiver): stage it and push it with ONE bulk copy per warp instead of 4 st.async per lane
