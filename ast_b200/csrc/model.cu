@@ -135,7 +135,7 @@ struct ast_model {
     cudaStream_t lay[MAXL] = {}, layg[MAXL] = {}, layh[MAXL] = {}; cudaEvent_t ev_pool[256] = {}; int enc_chunk = 24;
     unsigned long long* enc_ts = nullptr; int enc_ts_on = 0; int tc2 = 7;      // bit 0: 2-CTA GEMM for large K-major-A problems, 1: for weight gradients, 2: grouped weight gradients
     bool queues_ok = false, eager_loading = false, last_fwd_persistent = false; int num_sms = 0;     // residency guards of the spin-wait schedule (persist_allowed)
-    unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 8; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 16, enc_l0dx_ctas = 8;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
+    unsigned* enc_flags = nullptr; int enc_persist = 3, enc_pchunk = 4; int warm_fwd = 0, warm_bwd = 0; int enc_l0_pre = -1, enc_gemm_ctas = 8, enc_gemm_ctas_bwd = 4, enc_side_ctas = 0 /* 0 = every SM the wavefront leaves free */, enc_l0dx_ctas = 0;     // persistent wavefront; enc_flags: done[MAXL][MAXQ] | tiles[MAXL][2][MAXT]
     float *dh_carry[MAXL][2], *dc_carry[MAXL][2];
     // last-call shapes
     int B = 0, T = 0, T1 = 0, Tp = 0, S0 = 0, Rs = 0, L = 0, train = 0;
@@ -1082,7 +1082,13 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // With the persistent encoder wavefront below they run beside the recurrence clusters and are capped to a few CTAs.
     const bool will_persist = bwd_will_persist(m);
     struct CapGuard { ~CapGuard() { gemm_tc_set_cta_cap(0); } } cap_guard;      // an early error return must not leave the cap behind
-    if (will_persist && sw != st) gemm_tc_set_cta_cap(m->enc_side_ctas);
+    if (will_persist && sw != st) {
+        // the SMs left beside the recurrence clusters and their gated dx GEMMs (B = 32: 148 - 96 - 16 = 36).  Sweep on the benchmarked
+        // step (tools/sweep_sched.sh): 16 -> 2.83 ms, 36 with layer 0's dx ungated -> 2.71, plus 4-step chunks -> 2.68
+        const int spin = m->NL * 2 * ((m->B + 15) / 16) * lstm_seq_tc_cluster_size();
+        const int gated = 2 * (m->NL - 1) * m->enc_gemm_ctas_bwd + 2 * m->enc_l0dx_ctas;
+        gemm_tc_set_cta_cap(m->enc_side_ctas > 0 ? m->enc_side_ctas : std::max(8, m->num_sms - spin - gated));
+    }
     AST_TRY(fork());
     // dG of the decoder layers: dec_seq2 keeps the forward gates intact and writes dG to its own per-step slots
     float* dGd[MAXL];
@@ -1210,9 +1216,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         unsigned* resident = m->enc_flags + ENC_FLAG_WORDS - 1;
         cudaEvent_t* ev = m->ev_pool;
-        // layer 0's data gradient (N = 1536: a third of the encoder's backward GEMM FLOPs, needed only by the CNN backward) as a
-        // gated GEMM beside the recurrences as well, on a few CTAs per direction: it finishes about one chunk after layer 0's
-        // recurrence instead of occupying the whole GPU for ~100 us between the encoder and the CNN backward
+        // layer 0's data gradient (N = 1536: a third of the encoder's backward GEMM FLOPs, needed only by the CNN backward) CAN run
+        // as a gated GEMM beside the recurrences too (enc_l0dx_ctas > 0).  That paid while a recurrence step took 3.4 us; with
+        // 2.2 us steps the few CTAs it can get finish ~150 us after layer 0 and starve the side stream's weight gradients:
+        // one GEMM per direction on the whole GPU after the wavefront is 0.12 ms faster on the benchmarked step (default 0).
         const bool l0gate = m->enc_l0dx_ctas > 0;
         AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
@@ -1428,7 +1435,11 @@ int ast_create(const ast_config* cfg, int device, ast_model** out) {
     for (int i = 0; i < 256 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&m->ev_pool[i], cudaEventDisableTiming);
     AST_CREATE_CHECK(e == cudaSuccess, "cudaEventCreate: %s", cudaGetErrorString(e));
 #undef AST_CREATE_CHECK
-    if (const char* v = getenv("AST_ENC_L0DX_CTAS")) m->enc_l0dx_ctas = atoi(v);      // diagnostics
+    if (const char* v = getenv("AST_ENC_L0DX_CTAS")) m->enc_l0dx_ctas = atoi(v);      // diagnostics / schedule sweeps
+    if (const char* v = getenv("AST_ENC_PCHUNK")) m->enc_pchunk = std::max(1, atoi(v));
+    if (const char* v = getenv("AST_ENC_SIDE_CTAS")) m->enc_side_ctas = std::max(0, atoi(v));
+    if (const char* v = getenv("AST_ENC_GEMM_CTAS")) m->enc_gemm_ctas = std::max(1, atoi(v));
+    if (const char* v = getenv("AST_ENC_GEMM_CTAS_BWD")) m->enc_gemm_ctas_bwd = std::max(1, atoi(v));
     if (const char* v = getenv("AST_BEAM_TC")) m->beam_tc = atoi(v);      // experiments: 0 skinny everywhere, 1 batched search on tcgen05, 3 both
     ++g_live_models[device & 63];
     *out = m;
