@@ -144,11 +144,7 @@ constexpr bool FW_F16 = true;
 constexpr uint32_t FW_ROWB = FW_F16 ? 64 : 128;         // bytes of one operand row inside a k-block of 32 hidden units
 constexpr uint32_t FW_A_BYTES = 8 * 128 * FW_ROWB;      // W slice: 8 k-blocks x 128 gate rows
 constexpr uint32_t FW_TMEM_D = 0;                       // accumulator column
-#ifndef FW_NACC
-#define FW_NACC 1
-#endif
-constexpr int FW_ACC = FW_NACC;                         // independent accumulators the k-steps rotate over (summed in the epilogue)
-constexpr uint32_t FW_TMEM_COLS = FW_ACC * TROWS <= 32 ? 32 : 64;
+constexpr uint32_t FW_TMEM_COLS = 32;
 constexpr uint32_t FW_H_BYTES = 8 * TROWS * FW_ROWB;    // one h buffer: 8 k-blocks x 16 rows
 constexpr uint32_t FW_XG_BYTES = 4 * TROWS * TU * 4;    // gate exchange [gate][batch][unit]
 constexpr uint32_t FW_STG_BYTES = 2 * TROWS * FW_ROWB;  // [2] staging of this CTA's h slice (= one k-block of the operand layout)
@@ -261,9 +257,8 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                     for (int ks = 0; ks < KS; ++ks) {
                         const uint64_t ad = a0 + (uint64_t)((kb * (128 * FW_ROWB) + ks * 32) >> 4);
                         const uint64_t bd = bcur + (uint64_t)((kb * (TROWS * FW_ROWB) + ks * 32) >> 4);
-                        const uint32_t dcol = tmem_base + (uint32_t)(((kb * KS + ks) % FW_ACC) * TROWS);
-                        if constexpr (FW_F16) umma_f16_ss(dcol, ad, bd, idesc, (kb * KS + ks) >= FW_ACC ? 1u : 0u);
-                        else umma_tf32_ss(dcol, ad, bd, idesc, (kb * KS + ks) >= FW_ACC ? 1u : 0u);
+                        if constexpr (FW_F16) umma_f16_ss(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+                        else umma_tf32_ss(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
                     }
                 umma_commit_arrive(mbar_mma);
                 PROBE(1);
@@ -298,13 +293,6 @@ lstm_seq_fwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
             {
                 float v[8];
                 tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + 8 * bh, v);
-#pragma unroll
-                for (int q = 1; q < FW_ACC; ++q) {
-                    float v2[8];
-                    tmem_ld8(tmem_base + ((uint32_t)(32 * gate) << 16) + FW_TMEM_D + q * TROWS + 8 * bh, v2);
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) v[b] += v2[b];
-                }
                 tc_fence_before();
 #pragma unroll
                 for (int b = 0; b < 8; ++b) sts_f1(xg_addr + (uint32_t)(((gate * TROWS + 8 * bh + b) * TU + lane) * 4), v[b]);
@@ -692,9 +680,7 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 const int idx = tid + e * TC_EPI; const int m = idx & 15, ul = idx >> 4, ju = TU * rank + ul; \
                 if (m < nb) *reinterpret_cast<float4*>(a.G + ((size_t)i * B + b0 + m) * H4 + 4 * ju) = p_act[e]; } \
             if ((T - i) % gt.chunk == 0 || i == 0) chunk_arrive(cnt_addr, lane); } while (0)
-#ifndef BW_STORE_LATE
             BW_STORE_DG();                         // 2. bookkeeping while the tensor core works: write dG_t in place
-#endif
             BPROBE(3);
             if (send) {
                 // 3. reduce-scatter: TMEM lane = unit n (half hm = w/4, quadrant w%4) -> owner CTA n/32, 16 batch partials
@@ -728,9 +714,6 @@ lstm_seq_bwd_tc_kernel(LstmChains ch, int T, int B, float drop, unsigned long lo
                 }
                 BPROBE(7);
             }
-#ifdef BW_STORE_LATE
-            BW_STORE_DG();
-#endif
             if (bprof && step >= 8 && step < 24 && (tid == 0 || tid == 224)) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) bprof[(step - 8) * 16 + (tid ? 8 : 0) + q] = pst[q];

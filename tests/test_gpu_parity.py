@@ -107,6 +107,45 @@ def test_persistent_lstm_recurrence(lib, dev, T, B, h, exact):
     assert _relerr(dG.cpu().numpy(), want) < btol
 
 
+def test_recurrence_backward_gradient_dynamic_range(lib, dev):
+    """The tcgen05 backward recurrence multiplies FP16 operands; every step it scales dG by the exact power of two that puts the
+    CTA's largest |dG| in [256, 512) (lstm_seq_tc.cu).  Gradients that span 1e-9 .. 1e+5 across time steps, steps whose upstream
+    gradient is exactly zero, and a jump of 12 orders of magnitude between neighbouring steps must all come out with TF32-level
+    error relative to the step's own magnitude (no flush to zero, no saturation)."""
+    from ast_b200._lib import check, ptr
+    T, B, h = 24, 32, 256
+    rng = np.random.default_rng(11)
+    G = rng.standard_normal((T, B, 4 * h)).astype(np.float32)
+    Wl = (rng.standard_normal((4 * h, h)) / np.sqrt(h)).astype(np.float32)
+    Hs = np.zeros((T + 1, B, h)); Cs = np.zeros((T + 1, B, h)); act = np.zeros((T, B, 4 * h))
+    for t in range(T):
+        c, hh, (a, i, f, o) = O.lstm_cell(Cs[t], G[t].astype(np.float64) + Hs[t] @ Wl.T.astype(np.float64))
+        Hs[t + 1], Cs[t + 1] = hh, c
+        act[t] = np.stack((a, i, f, o), axis=2).reshape(B, 4 * h)
+    # processed from t = T-1 down: zero gradient first (padding), then tiny, then a jump to huge, then decaying again
+    scale = np.zeros(T)
+    scale[T - 6:T - 3] = 1e-9
+    scale[T - 9:T - 6] = 1e+5
+    scale[:T - 9] = 10.0 ** np.linspace(-6, 2, T - 9)
+    dout = rng.standard_normal((T, B, h)) * scale[:, None, None]
+    dhf, dcf = np.zeros((B, h)), np.zeros((B, h))
+    want = np.zeros((T, B, 4 * h)); dh, dc = dhf.copy(), dcf.copy()
+    for t in reversed(range(T)):
+        a4 = act[t].reshape(B, h, 4)
+        dg, dc = O.lstm_cell_bwd(dout[t] + dh, dc, Cs[t], Cs[t + 1], (a4[:, :, 0], a4[:, :, 1], a4[:, :, 2], a4[:, :, 3]))
+        want[t] = dg
+        dh = dg @ Wl.astype(np.float64)
+    t32 = lambda x: torch.as_tensor(np.asarray(x).astype(np.float32), device=dev)
+    dG, dW, dH, dC = t32(act), t32(Wl), t32(Hs), t32(Cs)
+    ddout, ddh, ddc = t32(dout), t32(dhf), t32(dcf)
+    check(lib.ast_lstm_seq(1, ptr(dG), ptr(dW), ptr(dH), ptr(dC), ptr(ddout), T, B, h, ptr(ddh), ptr(ddc), 0, _stream(dev)))
+    got = dG.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert (got[T - 3:] == 0).all() and (want[T - 3:] == 0).all()
+    for t in range(T - 3):
+        assert _relerr(got[t], want[t]) < 5e-3, (t, scale[t], _relerr(got[t], want[t]))
+
+
 def test_softmax_cross_entropy_kernel(lib, dev):
     from ast_b200._lib import check, ptr
     rng = np.random.default_rng(2)
