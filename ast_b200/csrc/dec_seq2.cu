@@ -1222,9 +1222,10 @@ int attn_denc(cudaStream_t st, const float* alpha, const float* ds, const float*
 // Sentinel fill of the hand-off slots of one launch (one kernel for all ranges).  Must be ordered before anything that writes
 // real values into them (init_dec_state writes slot 0 of Hd, which is therefore not part of the range).
 namespace {
-struct FillRanges { int n; uint4* ptr[12]; size_t n4[12]; };
+struct FillRanges { int n; uint4* ptr[12]; size_t n4[12]; unsigned* zero_word; };
 __global__ void __launch_bounds__(256) fill_sentinel_kernel(FillRanges r) {
     const uint4 v = make_uint4(D2_SENT, D2_SENT, D2_SENT, D2_SENT);
+    if (r.zero_word && blockIdx.x == 0 && threadIdx.x == 0) *r.zero_word = 0u;      // the launch's grid-barrier word (was a memset in front of the launch)
     for (int i = 0; i < r.n; ++i)
         for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < r.n4[i]; j += (size_t)gridDim.x * blockDim.x) r.ptr[i][j] = v;
 }
@@ -1242,6 +1243,7 @@ int dec_seq2_prepare_fwd(cudaStream_t st, const DecSeq& p) {
     for (int l = 0; l < 3; ++l) add(p.Hd[l] + (size_t)p.B * p.H, SBH);
     add(p.hdd[0], SBH); add(p.hdd[1], SBH); add(p.cvh, 2 * SBH);
     if (p.use_true != nullptr) add(p.logits, (size_t)p.S * p.B * p.Vp);      // in-loop logits of sampled steps (the batched GEMM after the loop rewrites them all)
+    r.zero_word = p.bar;
     return fill_ranges(st, r);
 }
 
@@ -1251,6 +1253,7 @@ int dec_seq2_prepare_bwd(cudaStream_t st, const DecSeq& p) {
     auto add = [&](float* ptr, size_t words) { r.ptr[r.n] = reinterpret_cast<uint4*>(ptr); r.n4[r.n] = words / 4; ++r.n; };
     add(p.dcv_all, SBH); add(p.dhh_all, SBH); add(p.dq, SBH); add(p.dfeed, (size_t)p.S * p.B * p.A);
     for (int l = 0; l < 3; ++l) { add(p.dxr[l], SBH); add(p.dgd[l], 4 * SBH); }
+    r.zero_word = p.bar;
     return fill_ranges(st, r);
 }
 
@@ -1282,7 +1285,7 @@ bool dec_seq2_supported(const DecSeq& p) {
 template <class KernT>
 static int launch_d2(KernT kern, cudaStream_t st, const DecSeq& p, size_t smem) {
     AST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AST_CUDA_OK(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), st));
+    // p.bar was zeroed by dec_seq2_prepare_fwd / _bwd (every launch needs its sentinel fill anyway)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(D2_NCL * D2_CS);
     cfg.blockDim = dim3(D2_THREADS);

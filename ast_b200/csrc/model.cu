@@ -498,6 +498,27 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     if (m->weights_dirty) AST_TRY(refresh_weights(m, st));
     const int Fp = m->Fp, C0 = m->C0, C1 = m->C1, h = m->h, R = m->R, NL = m->NL;
     const int M0 = B * Fp * T1, M1 = B * Fp * Rs, TB = Tp * B;
+    {   // everything the encoder needs zeroed, in one launch up front (each was a memset + launch gap between the kernels below):
+        // initial link states, the zero rows behind the padded CNN_0 activations, the wavefront's flag words
+        ZeroBatch zb{};
+        bool one = (B * h) % 4 == 0 && 4 * NL + 2 <= 16 && (((size_t)(c.cnn_kh[1] + 8) * C0) % 4 == 0);
+        for (int l = 0; l < NL; ++l)
+            for (int d = 0; d < 2; ++d) {
+                if (one) { zb.ptr[zb.n] = m->Hs[l][d]; zb.count[zb.n++] = (size_t)B * h; zb.ptr[zb.n] = m->Cs[l][d]; zb.count[zb.n++] = (size_t)B * h; }
+                else {
+                    AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
+                    AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
+                }
+            }
+        if (one) {
+            zb.ptr[zb.n] = m->a0p + (size_t)B * Fp * S0 * C0; zb.count[zb.n++] = (size_t)(c.cnn_kh[1] + 8) * C0;
+            if (m->enc_flags) { zb.ptr[zb.n] = reinterpret_cast<float*>(m->enc_flags); zb.count[zb.n++] = ENC_FLAG_WORDS; }
+            AST_TRY(zero_multi(st, zb));
+        } else {
+            AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
+            if (m->enc_flags) AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
+        }
+    }
     const float drop = train ? c.drop_rnn : 0.f;
     if (train) m->cur_seed = m->seed + 0x9E3779B97F4A7C15ULL * (++m->step_counter);
 
@@ -527,7 +548,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     }
     AST_TRY(bn_relu_pad(st, m->raw0, m->a0p, m->mean0, m->invstd0, m->p("CNN_0_bn/gamma"), m->p("CNN_0_bn/beta"),
                         B * Fp, T1, S0, c.cnn_ph[1], C0));
-    AST_CUDA_OK(cudaMemsetAsync(m->a0p + (size_t)B * Fp * S0 * C0, 0, sizeof(float) * (c.cnn_kh[1] + 8) * C0, st));
+    // (the (kh + 8) zero rows behind a0p: zeroed by the launch at the top of this function)
     // CNN_1: implicit GEMM over overlapping rows (lda = sh*C0), no im2col buffer
     int conv1_done = 0;
     if (((m->tc_gemm && !m->exact) || m->enc_tc3) && (m->conv3x & 1) && m->K1 % 4 == 0) {
@@ -557,21 +578,6 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
     const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
-    if ((B * h) % 4 == 0 && 4 * NL <= 16) {      // initial link states: one launch
-        ZeroBatch zb{};
-        for (int l = 0; l < NL; ++l)
-            for (int d = 0; d < 2; ++d) {
-                zb.ptr[zb.n] = m->Hs[l][d]; zb.count[zb.n++] = (size_t)B * h;
-                zb.ptr[zb.n] = m->Cs[l][d]; zb.count[zb.n++] = (size_t)B * h;
-            }
-        AST_TRY(zero_multi(st, zb));
-    } else {
-        for (int l = 0; l < NL; ++l)
-            for (int d = 0; d < 2; ++d) {
-                AST_CUDA_OK(cudaMemsetAsync(m->Hs[l][d], 0, sizeof(float) * B * h, st));
-                AST_CUDA_OK(cudaMemsetAsync(m->Cs[l][d], 0, sizeof(float) * B * h, st));
-            }
-    }
     auto project = [&](int l, int t0, int tn, cudaStream_t s) -> int {
         const size_t r0 = (size_t)t0 * B;
         for (int d = 0; d < 2; ++d) {
@@ -641,8 +647,7 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
         unsigned* done = m->enc_flags;
         unsigned* tiles = m->enc_flags + (size_t)MAXL * MAXQ;
         unsigned* resident = m->enc_flags + ENC_FLAG_WORDS - 1;
-        cudaEvent_t* ev = m->ev_pool;
-        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
+        cudaEvent_t* ev = m->ev_pool;       // (enc_flags: zeroed by the launch at the top of this function)
         {   // both directions in one grouped 2-CTA launch: 2 x 80 pair tiles are 3 waves of 74 pairs, two separate launches are 4
             const float* Ag[2] = {m->rnn_in, m->rnn_rev};
             const float* Bg[2] = {m->p("L0_enc/upward/W"), m->p("L0_rev_enc/upward/W")};
@@ -1010,9 +1015,19 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         }
         AST_CUDA_OK(cudaMemsetAsync(m->G, 0, sizeof(float) * (size_t)m->nfloats, zs));
         if (dec_bwd_v2) AST_TRY(dec_seq2_prepare_bwd(zs, ds));
+        {   // every small buffer the backward pass needs zeroed, in ONE launch beside the dz . Wo GEMM (each was a memset + launch gap
+            // on the main stream): decoder cell-gradient carries, the wavefront's flag words, the zero rows in front of d(raw1)
+            ZeroBatch zb{};
+            for (int l = 0; l < NL; ++l) { zb.ptr[zb.n] = m->dcd[l]; zb.count[zb.n++] = (size_t)B * H; }
+            if (m->enc_flags) { zb.ptr[zb.n] = reinterpret_cast<float*>(m->enc_flags); zb.count[zb.n++] = ENC_FLAG_WORDS; }
+            if (m->draw1) { zb.ptr[zb.n] = m->draw1 - (size_t)DRAW1_PAD_ROWS * m->C1; zb.count[zb.n++] = (size_t)DRAW1_PAD_ROWS * m->C1; }
+            bool ok4 = true;
+            for (int i = 0; i < zb.n; ++i) ok4 = ok4 && zb.count[i] % 4 == 0;
+            if (ok4) AST_TRY(zero_multi(zs, zb));
+            else for (int i = 0; i < zb.n; ++i) AST_CUDA_OK(cudaMemsetAsync(zb.ptr[i], 0, sizeof(float) * zb.count[i], zs));
+        }
         if (zs != st) AST_CUDA_OK(cudaEventRecord(m->ev_fill[1], zs));
         if (!dec_bwd_v2) AST_CUDA_OK(cudaMemsetAsync(m->d_enc, 0, sizeof(float) * (size_t)TB * H, st));      // accumulated step by step
-        for (int l = 0; l < NL; ++l) AST_CUDA_OK(cudaMemsetAsync(m->dcd[l], 0, sizeof(float) * B * H, st));
     }
     // ---- decoder BPTT: data gradients step by step -----------------------------------------------
     if (m->dec_fused) {
@@ -1220,8 +1235,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         // as a gated GEMM beside the recurrences too (enc_l0dx_ctas > 0).  That paid while a recurrence step took 3.4 us; with
         // 2.2 us steps the few CTAs it can get finish ~150 us after layer 0 and starve the side stream's weight gradients:
         // one GEMM per direction on the whole GPU after the wavefront is 0.12 ms faster on the benchmarked step (default 0).
-        const bool l0gate = m->enc_l0dx_ctas > 0;
-        AST_CUDA_OK(cudaMemsetAsync(m->enc_flags, 0, sizeof(unsigned) * ENC_FLAG_WORDS, st));
+        const bool l0gate = m->enc_l0dx_ctas > 0;       // (enc_flags: zeroed at the top of backward_impl)
         AST_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int l = 0; l < NL; ++l) {
             AST_CUDA_OK(cudaStreamWaitEvent(m->lay[l], ev[0], 0));
@@ -1307,7 +1321,7 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
         // segment are the previous segment's junk rows (>= T', written as zeros by the BN backward) or the zero pad in front of the
         // buffer, so row R = seg*Rs + j of the overlapping-rows operand simply starts U_p rows before d(raw1)[R]; the output row
         // is da0p row 2R + p.  Two GEMMs (K = 5*C1 and 4*C1), no d(im2col) buffer (72.5 MB at B32 x T640), no col2im pass.
-        AST_CUDA_OK(cudaMemsetAsync(m->draw1 - (size_t)DRAW1_PAD_ROWS * C1, 0, sizeof(float) * DRAW1_PAD_ROWS * C1, st));
+        // (the DRAW1_PAD_ROWS zero rows in front of d(raw1): zeroed at the top of backward_impl)
         for (int p = 0; p < 2; ++p) {
             const int ntaps = (c.cnn_kh[1] - p + 1) / 2, U = ntaps - 1;
             AST_TRY(gemm(m, st, false, false, M1, C0, ntaps * C1, m->draw1 - (size_t)U * C1, C1, m->W1t[p], C0, m->da0p + (size_t)p * C0, 2 * C0,
