@@ -749,7 +749,7 @@ def run_ours(args):
     line = {
         "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32 tensor-core GEMMs, fp32 accumulate/state" if args.precision == "tf32" else "f32 (3xTF32 / fp32 FMA, fp32-faithful)",
+        "dtype": "tf32 tensor-core GEMMs (encoder recurrences: fp16 operands, same 11-bit significand), fp32 accumulate/state" if args.precision == "tf32" else "f32 (3xTF32 / fp32 FMA, fp32-faithful)",
         "data": "synthetic",
         "config": {"workload": "es_en_20h bucketed training steps (configs[1]): B=32/GPU, Fisher-shaped lengths (20x80-frame buckets, "
                                "truncated at 1680), D=40 fbank, V=1098, 2xCNN + 2x3-layer LSTM encoder + 3-layer attention decoder; "
@@ -810,7 +810,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["f32", "tf32"],
-                    help="tf32: tcgen05 TF32 GEMMs + single-pass TF32 recurrences (training mode, inside the parity "
+                    help="tf32: tcgen05 TF32 GEMMs + single-pass TF32 / FP16-operand recurrences (training mode, inside the parity "
                          "tolerances); f32: fp32-faithful everywhere (the decode / hypothesis-identity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true")
