@@ -1097,45 +1097,53 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     // With the persistent encoder wavefront below they run beside the recurrence clusters and are capped to a few CTAs.
     const bool will_persist = bwd_will_persist(m);
     struct CapGuard { ~CapGuard() { gemm_tc_set_cta_cap(0); } } cap_guard;      // an early error return must not leave the cap behind
-    if (will_persist && sw != st) {
-        // the SMs left beside the recurrence clusters and their gated dx GEMMs (B = 32: 148 - 96 - 16 = 36).  Sweep on the benchmarked
-        // step (tools/sweep_sched.sh): 16 -> 2.83 ms, 36 with layer 0's dx ungated -> 2.71, plus 4-step chunks -> 2.68
-        const int spin = m->NL * 2 * ((m->B + 15) / 16) * lstm_seq_tc_cluster_size();
-        const int gated = 2 * (m->NL - 1) * m->enc_gemm_ctas_bwd + 2 * m->enc_l0dx_ctas;
-        gemm_tc_set_cta_cap(m->enc_side_ctas > 0 ? m->enc_side_ctas : std::max(8, m->num_sms - spin - gated));
-    }
     AST_TRY(fork());
-    // dG of the decoder layers: dec_seq2 keeps the forward gates intact and writes dG to its own per-step slots
-    float* dGd[MAXL];
-    for (int l = 0; l < NL; ++l) dGd[l] = dec_bwd_v2 ? m->dgd[l] : m->actd[l];
-    if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
-        AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, dGd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
-        AST_TRY(embed_scatter(sw, m->g("embed_dec/W"), m->dE, E, m->words_used, SB, E, 0, de, m->cur_seed, 32));
-    }
-    AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 1.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, true));
-    AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->du, A, m->g("context/b"), SB, A, true));
-    AST_TRY(gemm(m, sw, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
-    AST_TRY(colsum(sw, m->dq, H, m->g("attn_Wa/b"), SB, H, true));
-    for (int l = 0; l < NL; ++l) {
-        const std::string ln = lname(l, "dec");
-        const int in = m->in_dec(l);
-        const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
-        AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, dGd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 1.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, dGd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
-        AST_TRY(colsum(sw, dGd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, true));
-    }
-    gemm_tc_set_cta_cap(0);
-    // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
-    // starts its all-reduce now (ast_grad_bucket_wait) and overlaps it with the encoder + CNN backward below
-    AST_CUDA_OK(cudaEventRecord(m->ev_bucket[0], sw));
-    // ---- encoder BPTT, top-down; both directions per launch.  Same chunked layer wavefront as the forward pass, in
-    // reverse time: layer l works on chunk c while layer l+1 is already on chunk c-1; the (dh, dc) carry between the
-    // chunks of one layer goes through dh_carry / dc_carry (the kernels' dh0/dc0 outputs).
+    // With the persistent wavefront the decoder weight gradients are ENQUEUED after the recurrence clusters and gated GEMMs and wait
+    // for the clusters to be resident (wait_resident on the side stream): up to 36 single GEMM CTAs dispatched first could leave no
+    // GPC with room for two 8-CTA clusters (rule (d) in DESIGN.md 3 - seen with the gated GEMMs: a layer starting 0.3-0.4 ms late).
     const int CH = (m->enc_chunk > 0 && m->overlap && NL > 1 && Tp > m->enc_chunk) ? (Tp >= 64 ? m->enc_chunk : std::max(8, m->enc_chunk / 2)) : Tp;
     const int nch = (Tp + CH - 1) / CH;
     const bool wave = nch > 1 && 2 * NL * nch + 2 <= 256;
+    const bool defer_dec_wgrads = will_persist && wave && sw != st;
+    auto dec_wgrads = [&]() -> int {
+        if (will_persist && sw != st) {
+            // the SMs left beside the recurrence clusters and their gated dx GEMMs (B = 32: 148 - 96 - 16 = 36).  Sweep on the benchmarked
+            // step (tools/sweep_sched.sh): 16 -> 2.83 ms, 36 with layer 0's dx ungated -> 2.71, plus 4-step chunks -> 2.68
+            const int spin = m->NL * 2 * ((m->B + 15) / 16) * lstm_seq_tc_cluster_size();
+            const int gated = 2 * (m->NL - 1) * m->enc_gemm_ctas_bwd + 2 * m->enc_l0dx_ctas;
+            gemm_tc_set_cta_cap(m->enc_side_ctas > 0 ? m->enc_side_ctas : std::max(8, m->num_sms - spin - gated));
+        }
+        // dG of the decoder layers: dec_seq2 keeps the forward gates intact and writes dG to its own per-step slots
+        float* dGd[MAXL];
+        for (int l = 0; l < NL; ++l) dGd[l] = dec_bwd_v2 ? m->dgd[l] : m->actd[l];
+        if (dec_bwd_v2) {      // EmbedID backward, deferred out of the loop: dE = dG_0 . W_up0[:, :E], then the scatter-add
+            AST_TRY(gemm(m, sw, false, false, SB, E, 4 * H, dGd[0], 4 * H, m->p("L0_dec/upward/W"), E + A, m->dE, E, nullptr, 0.f, 0, SITE_DEC_PRE));
+            AST_TRY(embed_scatter(sw, m->g("embed_dec/W"), m->dE, E, m->words_used, SB, E, 0, de, m->cur_seed, 32));
+        }
+        AST_TRY(gemm(m, sw, true, false, V, A, SB, m->logits, Vp, m->ht, A, m->g("out/W"), A, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, m->logits, Vp, m->g("out/b"), SB, V, true));
+        AST_TRY(gemm(m, sw, true, false, A, 2 * H, SB, m->du, A, m->cvh, 2 * H, m->g("context/W"), 2 * H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, m->du, A, m->g("context/b"), SB, A, true));
+        AST_TRY(gemm(m, sw, true, false, H, H, SB, m->dq, H, m->cvh + H, 2 * H, m->g("attn_Wa/W"), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+        AST_TRY(colsum(sw, m->dq, H, m->g("attn_Wa/b"), SB, H, true));
+        for (int l = 0; l < NL; ++l) {
+            const std::string ln = lname(l, "dec");
+            const int in = m->in_dec(l);
+            const float* xin = l == 0 ? m->x0 : (l - 1 == NL - 1 ? nullptr : m->hdd[l - 1]);
+            AST_TRY(gemm(m, sw, true, false, 4 * H, in, SB, dGd[l], 4 * H, xin, in, m->g((ln + "/upward/W").c_str()), in, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+            AST_TRY(gemm(m, sw, true, false, 4 * H, H, SB, dGd[l], 4 * H, m->Hdec[l], H, m->g((ln + "/lateral/W").c_str()), H, nullptr, 1.f, -1, SITE_DEC_WGRAD));
+            AST_TRY(colsum(sw, dGd[l], 4 * H, m->g((ln + "/upward/b").c_str()), SB, 4 * H, true));
+        }
+        gemm_tc_set_cta_cap(0);
+        // gradient bucket 0 (attn_Wa .. out: 56 % of the bytes) is final once the side stream gets here: a data-parallel caller
+        // starts its all-reduce now (ast_grad_bucket_wait) and overlaps it with the encoder + CNN backward below
+        AST_CUDA_OK(cudaEventRecord(m->ev_bucket[0], sw));
+        return 0;
+    };
+    if (!defer_dec_wgrads) AST_TRY(dec_wgrads());
+    // ---- encoder BPTT, top-down; both directions per launch.  Same chunked layer wavefront as the forward pass, in
+    // reverse time: layer l works on chunk c while layer l+1 is already on chunk c-1; the (dh, dc) carry between the
+    // chunks of one layer goes through dh_carry / dc_carry (the kernels' dh0/dc0 outputs).
     auto bwd_chains = [&](int l, int t0, bool last_in_time, bool carry_out) -> LstmChains {
         const size_t r0 = (size_t)t0 * B;
         LstmChains ch{};
@@ -1265,6 +1273,10 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
                                             m->p((ln + "/upward/W").c_str()), in, dx, in, nullptr, tg, l > 0 ? m->enc_gemm_ctas_bwd : m->enc_l0dx_ctas);
                 AST_CHECK(r == 0, "persistent wavefront: the gated dx GEMM rejected its operands");
             }
+        if (defer_dec_wgrads) {
+            AST_TRY(wait_resident(sw, resident, (unsigned)(NL * ncta)));
+            AST_TRY(dec_wgrads());
+        }
         for (int l = NL - 1; l >= 0; --l) {
             AST_CUDA_OK(cudaStreamWaitEvent(st, ev[1 + l], 0));
             if (l > 0 || l0gate) {
