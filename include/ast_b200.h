@@ -172,8 +172,9 @@ int ast_gemm3_nt(int M, int N, int K, const float* A, float* Ahi, float* Alo, lo
 int ast_lstm_seq(int backward, float* G, const float* Wl, float* Hs, float* Cs, float* out_or_dout, int T, int B, int h,
                  const float* dh_fin, const float* dc_fin, int exact, void* stream);
 
-/* diagnostics: device buffer (>= 128 uint64) that receives clock64() stamps of steps 8..23 of the tcgen05 LSTM forward kernel
-   (8 slots per step); NULL switches the probe off */
+/* diagnostics: device buffer (>= 512 uint64) that receives 32-bit clock stamps of steps 8..23 of the tcgen05 LSTM kernels:
+   forward [0, 128) = 16 steps x 8 slots; backward [128, 384) = 16 steps x (8 slots of epilogue thread 0, 8 of thread 224),
+   [384, 416) = 16 steps x 2 slots of the MMA issuer (tools/enc_step_probe.py decodes them); NULL switches the probe off */
 int ast_lstm_probe(unsigned long long* dev_buf);
 /* diagnostics: with ast_set_option(m, "stage_timing", 1), milliseconds between the stage marks (CNN / encoder / decoder ...) of the
    last forward_loss + backward on the caller's stream; synchronises; returns the number of intervals */

@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--T", type=int, default=640)
 ap.add_argument("--L", type=int, default=24)
-ap.add_argument("--pchunk", type=int, default=8)
+ap.add_argument("--pchunk", type=int, default=8)      # the engine default is 4; 8 keeps the periods comparable with earlier profiles
 ap.add_argument("--opt", action="append", default=[])
 a = ap.parse_args()
 rng = np.random.default_rng(0)

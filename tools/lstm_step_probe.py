@@ -19,7 +19,7 @@ rng = np.random.default_rng(0)
 G = torch.as_tensor(rng.standard_normal((T, B, 4 * h)).astype(np.float32), device=dev)
 W = torch.as_tensor((rng.standard_normal((4 * h, h)) / 16).astype(np.float32), device=dev)
 Hs = torch.zeros(T + 1, B, h, device=dev); Cs = torch.zeros(T + 1, B, h, device=dev); out = torch.zeros(T, B, h, device=dev)
-prof = torch.zeros(128, dtype=torch.int64, device=dev)
+prof = torch.zeros(512, dtype=torch.int64, device=dev)
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 for it in range(3):
     Gc = G.clone()
@@ -27,12 +27,12 @@ for it in range(3):
     check(lib.ast_lstm_seq(0, ptr(Gc), ptr(W), ptr(Hs), ptr(Cs), ptr(out), T, B, h, None, None, 0, st))
     torch.cuda.synchronize()
 check(lib.ast_lstm_probe(None))
-p = prof.cpu().numpy().reshape(16, 8)[:, :7].astype(np.float64)
+p = prof.cpu().numpy()[:128].reshape(16, 8)[:, :7]          # 32-bit clock stamps
 names = ["h landed (issuer)", "MMAs issued + commit", "accumulator ready (epilogue)", "gates exchanged (tcgen05.ld, smem, bar)",
          "cell math done", "h sent (st.async)", "bookkeeping done"]
-step = np.diff(p[:, 0])
+step = ((p[1:, 0] - p[:-1, 0]) & 0xFFFFFFFF).astype(np.float64)
 print(f"step period: median {np.median(step):.0f} cycles = {np.median(step) / 1.965e3:.2f} us @1.965 GHz")
-rel = p - p[:, :1]
+rel = ((p - p[:, :1]) & 0xFFFFFFFF).astype(np.float64)
 for k in range(7):
     print(f"  {names[k]:42s} +{np.median(rel[:, k]):7.0f} cycles after 'h landed'")
 print("  next 'h landed' (other CTAs' sends + mbarrier)   +%7.0f" % np.median(step))
