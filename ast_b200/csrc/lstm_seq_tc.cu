@@ -1,21 +1,23 @@
-// Persistent LSTM recurrence on 5th-generation tensor cores (TF32 training mode, per-direction h = 256).
+// Persistent LSTM recurrence on 5th-generation tensor cores (training mode, per-direction h = 256); seq2seq.py:293-315 is the
+// reference loop this replaces (L.NStepBiLSTM per layer), nn.py:176-199 its backward through Chainer's autograd.
 //
-// Same cluster organisation as lstm_seq.cu (8 CTAs per chain, each owning 32 hidden units = 128 gate rows, W_h
-// resident in shared memory for all T steps, h exchanged with st.async + mbarrier complete_tx), but the per-step
-// GEMM is issued as tcgen05.mma with the operands SWAPPED: gates^T (128 gate rows x 16 batch rows) =
-// W_slice (128 x 256, the M side, K-major, resident) · h^T (256 x 16, the N side).  With the weight on the
-// M = 128 side the tensor core runs at full rate (32 MMAs of 128x16x8, ~8 cycles each) instead of the legacy
-// mma.sync path, whose issue rate (~16 cycles per m16n8k8 per SM sub-partition, measured) made the recurrent
-// GEMM cost ~2050 cycles per step.  The fp32 accumulator lives in TMEM (16 columns) and is read back with
-// tcgen05.ld for the fused gate / cell / dropout epilogue.
+// Same cluster organisation as lstm_seq.cu (8 CTAs per chain, each owning 32 hidden units = 128 gate rows, W_h resident in
+// shared memory for all T steps), but the per-step GEMM is issued as tcgen05.mma with the operands SWAPPED: gates^T (128 gate
+// rows x 16 batch rows) = W_slice (128 x 256, the M side, K-major, resident) · h^T (256 x 16, the N side).  The fp32
+// accumulator lives in TMEM (16 columns) and is read back with tcgen05.ld for the fused gate / cell / dropout epilogue.
 //
-// Warp roles: warps 0..7 = epilogue (gates, cell, sends, bookkeeping), warp 8 = MMA issuer.  The issuer does
-// nothing else, so the tensor core starts the moment the last slice of h lands; its descriptors are precomputed
-// and advanced by immediates (building them per MMA cost ~66 cycles each in a single dependent thread, measured).
+// A 128 x 16 x K instruction costs ~60 cycles whatever K is (measured: from smem or TMEM, with 1, 2 or 4 accumulators), so the
+// operands are FP16 (kind::f16, K = 16: 16 instructions per step instead of TF32's 32) - the same 11-bit significand; see
+// FW_F16 / BW_F16 below for the range argument (forward) and the exact per-step scale (backward).  -DFW_OPERAND_TF32 /
+// -DBW_OPERAND_TF32 build the TF32 variants (SWIZZLE_128B operands, M-major W^T in SWIZZLE_128B_BASE32B for backward).
 //
-// Operands are rounded to TF32 with round-to-nearest when they are written to shared memory (W once, h by the
-// producing CTA), so the tensor core never truncates.  Backward uses the same trick for dh^T (256 x 16) =
-// W_slice^T (256 x 128, M-major operand in the SWIZZLE_128B_BASE32B layout) · dG^T (128 x 16).
+// Warp roles: warps 0..7 = epilogue (gates, cell, sends, bookkeeping); warp 8 = MMA issuer (nothing else, so the tensor core
+// starts the moment the last slice of h lands; descriptors precomputed and advanced by immediates); then the chunk signaller
+// (forward warp 9, backward warp 10: publishes a finished chunk device-wide, see chunk_arrive / signaller_loop) and, backward,
+// the loader warp 9 (cp.async prefetch of the next steps' operands into a two-deep shared-memory ring).
+//
+// Operands are rounded to nearest when they are written to shared memory (W once, h / dG by the producing CTA), so the tensor
+// core never truncates.  tools/enc_step_probe.py prints the cycle breakdown of a step inside a real training step.
 #include "cluster_dev.cuh"
 #include <cuda_fp16.h>
 #include "kernels.h"
