@@ -55,8 +55,14 @@ int ast_weights_changed(ast_model* m);
 long long ast_workspace_bytes(const ast_model* m, int B, int T, int L, int beam_n, int max_steps);
 int ast_bind_workspace(ast_model* m, void* ws, long long bytes, int B, int T, int L, int beam_n, int max_steps);
 
-/* options: "exact" (1: fp32-faithful 3xTF32 / fp32 FMA everywhere, 0: single-pass TF32 tensor cores),
- *          "seed" (dropout / noise RNG), "tc_gemm" (1: tcgen05 GEMM for the batched contractions). */
+/* options: "exact" (1: fp32-faithful 3xTF32 / fp32 FMA everywhere, 0: single-pass TF32 tensor cores, FP16-operand encoder recurrences),
+ *          "seed" (dropout / noise RNG), "tc_gemm" (1: tcgen05 GEMM for the batched contractions).
+ * Schedule of the persistent encoder wavefront (defaults from tools/sweep_sched.sh on the benchmarked step):
+ *          "enc_pchunk" (steps per hand-off chunk, 4), "enc_gemm_ctas" / "enc_gemm_ctas_bwd" (CTAs of each gated projection /
+ *          data-gradient GEMM, 8 / 4), "enc_l0dx_ctas" (> 0: layer 0's data gradient as a gated GEMM beside the recurrences, 0),
+ *          "enc_side_ctas" (CTA cap of the side stream's GEMMs beside the backward wavefront; 0 = every SM it leaves free).
+ *          The same five can be preset from the environment: AST_ENC_PCHUNK, AST_ENC_GEMM_CTAS, AST_ENC_GEMM_CTAS_BWD,
+ *          AST_ENC_L0DX_CTAS, AST_ENC_SIDE_CTAS (read at ast_create). */
 int ast_set_option(ast_model* m, const char* key, double value);
 double ast_get_option(const ast_model* m, const char* key);
 
