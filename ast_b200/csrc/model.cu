@@ -1176,6 +1176,21 @@ static int backward_impl(ast_model* m, cudaStream_t st) {
     };
     auto bwd_dx_rows = [&](int l, int t0, int tn, cudaStream_t s) -> int {   // dx = dG . W_up for rows of steps [t0, t0+tn) (feeds the layer below)
         const size_t r0 = (size_t)t0 * B;
+        {   // both directions in ONE grouped 2-CTA launch when each fills the GPU on its own (layer 0 after the wavefront: 2 x 100 pair
+            // tiles are 3 waves of 74 pairs, two launches are 2 + 2; same kernel, same arithmetic as the per-direction gemm() below)
+            const int in = m->in_enc(l);
+            if (m->tc_gemm && !m->exact && m->tc2 && !((m->tc_mask >> SITE_ENC_DX) & 1u) && in % 256 == 0 &&
+                ((tn * B + 255) / 256) * (in / 256) >= 60) {
+                const float* Ag[2]; const float* Bg[2]; float* Cg[2];
+                for (int d = 0; d < 2; ++d) {
+                    const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
+                    float* dx = l == 0 ? (d == 0 ? m->d_rnn_in : m->d_rnn_rev) : m->dHd[l - 1][d];
+                    Ag[d] = m->Genc[l][d] + r0 * 4 * h; Bg[d] = m->p((ln + "/upward/W").c_str()); Cg[d] = dx + r0 * in;
+                }
+                const int r = gemm_tc2_grouped(s, 2, false, false, tn * B, in, 4 * h, Ag, 4 * h, Bg, in, Cg, in, nullptr, 0.f, 0);
+                if (r <= 0) return r;
+            }
+        }
         for (int d = 0; d < 2; ++d) {
             const std::string ln = lname(l, d == 0 ? "enc" : "rev_enc");
             const int in = m->in_enc(l);
