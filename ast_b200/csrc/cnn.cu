@@ -130,6 +130,56 @@ int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, in
     return 0;
 }
 
+// bn_partials_sum + bn_finalize in one launch (forward, train mode): block = 16 channels, thread (y, x): x < 16 sums the partial
+// SUMS of channel c0 + x, x >= 16 the partial SUMS OF SQUARES of channel c0 + x - 16 over blocks y, y + 32, ...; tree over y; the
+// first 16 threads then finish mean / invstd / running statistics exactly as bn_finalize_kernel does.
+__global__ void __launch_bounds__(1024) bn_sum_finalize_kernel(const double* __restrict__ partials, int nblocks, int C, double* __restrict__ stats,
+                                                               float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ avg_mean,
+                                                               float* __restrict__ avg_var, double m, float eps, float decay, int update_running) {
+    __shared__ double red[32][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 16 + (x & 15);
+    const int col = (x < 16 ? 0 : C) + c;
+    double s = 0.0;
+    if (c < C)
+        for (int b = y; b < nblocks; b += 32) s += partials[(size_t)b * 2 * C + col];
+    red[y][x] = s;
+    __syncthreads();
+    for (int hh = 16; hh > 0; hh >>= 1) {
+        if (y < hh) red[y][x] += red[y + hh][x];
+        __syncthreads();
+    }
+    if (y == 0 && c < C) stats[col] = red[0][x];
+    if (y == 0 && x < 16 && c < C) {
+        const double mu = red[0][x] / m;
+        double var = red[0][x + 16] / m - mu * mu;
+        if (var < 0) var = 0;
+        mean[c] = (float)mu;
+        invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (update_running) {
+            const double adj = m / fmax(m - 1.0, 1.0);
+            avg_mean[c] = decay * avg_mean[c] + (1.f - decay) * (float)mu;
+            avg_var[c] = decay * avg_var[c] + (1.f - decay) * (float)(var * adj);
+        }
+    }
+}
+
+int bn_stats_finalize(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid, double* partials,
+                      int partial_blocks, float* mean, float* invstd, float* avg_mean, float* avg_var, double m, float eps, float decay,
+                      bool update_running) {
+    AST_CHECK(C % 4 == 0 && partials != nullptr && partial_blocks >= 1, "bn_stats_finalize: C %% 4 != 0 or no buffer for the partial sums");
+    const int gx = cdiv(C, 128);
+    int rpb = std::max(32, cdiv(rows, std::max(1, 148 * 4 / gx)));
+    rpb = std::max(rpb, cdiv(rows, partial_blocks));
+    const int gy = cdiv(rows, rpb);
+    dim3 grid(gx, gy), block(32, 8);
+    bn_stats_kernel<<<grid, block, 0, st>>>(x, partials, rows, C, seg_rows, seg_valid, rpb);
+    AST_LAUNCH_OK();
+    bn_sum_finalize_kernel<<<cdiv(C, 16), 1024, 0, st>>>(partials, gy, C, stats, mean, invstd, avg_mean, avg_var, m, eps, decay, update_running ? 1 : 0);
+    AST_LAUNCH_OK();
+    return 0;
+}
+
 int bn_finalize(cudaStream_t st, const double* stats, float* mean, float* invstd, float* avg_mean,
                 float* avg_var, int C, double m, float eps, float decay, bool update_running) {
     bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats, mean, invstd, avg_mean, avg_var, C, m, eps, decay,

@@ -45,6 +45,9 @@ int im2col0(cudaStream_t st, const float* X, float* cols, int B, int T, int D, i
             int sw, int ph, int ldc);
 int bn_stats(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid, double* partials,
              int partial_blocks);
+int bn_stats_finalize(cudaStream_t st, const float* x, double* stats, int rows, int C, int seg_rows, int seg_valid, double* partials,
+                      int partial_blocks, float* mean, float* invstd, float* avg_mean, float* avg_var, double m, float eps, float decay,
+                      bool update_running);      // bn_stats + bn_finalize with the partial-sum pass and the finalisation in one launch
 int bn_finalize(cudaStream_t st, const double* stats, float* mean, float* invstd, float* avg_mean, float* avg_var,
                 int C, double m, float eps, float decay, bool update_running);
 int bn_eval_prepare(cudaStream_t st, const float* avg_mean, const float* avg_var, float* mean, float* invstd, int C,

@@ -541,8 +541,8 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     if (!conv0_done) AST_TRY(gemm_nt(m, st, M0, C0, m->ld0, m->cols0, m->ld0, m->W0pad, m->ld0, m->raw0, C0, nullptr, SITE_CONV0));
     float* bn0 = m->bn_state; float* bn1 = m->bn_state + 2 * C0;
     if (train) {
-        AST_TRY(bn_stats(st, m->raw0, m->bnstats, M0, C0, T1, T1, m->bnpart, BN_PART_BLOCKS));
-        AST_TRY(bn_finalize(st, m->bnstats, m->mean0, m->invstd0, bn0, bn0 + C0, C0, (double)M0, BN_EPS, BN_DECAY, true));
+        AST_TRY(bn_stats_finalize(st, m->raw0, m->bnstats, M0, C0, T1, T1, m->bnpart, BN_PART_BLOCKS, m->mean0, m->invstd0, bn0, bn0 + C0,
+                                  (double)M0, BN_EPS, BN_DECAY, true));
     } else {
         AST_TRY(bn_eval_prepare(st, bn0, bn0 + C0, m->mean0, m->invstd0, C0, BN_EPS));
     }
@@ -562,8 +562,8 @@ static int encode_impl(ast_model* m, const float* X, int B, int T, int train, co
     }
     if (!conv1_done) AST_TRY(gemm_nt(m, st, M1, C1, m->K1, m->a0p, c.cnn_sh[1] * C0, m->W1p, m->K1, m->raw1, C1, nullptr, SITE_CONV1));
     if (train) {
-        AST_TRY(bn_stats(st, m->raw1, m->bnstats, M1, C1, Rs, Tp, m->bnpart, BN_PART_BLOCKS));
-        AST_TRY(bn_finalize(st, m->bnstats, m->mean1, m->invstd1, bn1, bn1 + C1, C1, (double)B * Fp * Tp, BN_EPS, BN_DECAY, true));
+        AST_TRY(bn_stats_finalize(st, m->raw1, m->bnstats, M1, C1, Rs, Tp, m->bnpart, BN_PART_BLOCKS, m->mean1, m->invstd1, bn1, bn1 + C1,
+                                  (double)B * Fp * Tp, BN_EPS, BN_DECAY, true));
     } else {
         AST_TRY(bn_eval_prepare(st, bn1, bn1 + C1, m->mean1, m->invstd1, C1, BN_EPS));
     }
